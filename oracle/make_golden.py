@@ -1,0 +1,140 @@
+"""
+TEST INFRASTRUCTURE ONLY.  Generates tests/golden/*.npz.  Run in the build container (needs
+/root/reference for the geometries and oracle/_ref/MolEmb*.so, built by `make -C oracle ref`):
+
+    python -m oracle.make_golden
+
+Each fixture holds (a) a geometry taken from the reference's datasets/ directory, (b) pins computed by
+the REFERENCE'S OWN native code: neighbour lists (MolEmb.Make_NListNaive, C_API/MolEmb.cpp:1180-1247),
+descriptors (MolEmb.Make_ANI1_Sym, :1913-1988) and, for the small cases, descriptor Jacobians
+(MolEmb.Make_ANI1_Sym_deri, :1844-1911); (c) outputs of the float64 restatement oracle/oracle_graph.py
+with seeded random-init weights (tensormol_b200.engine.random_weights(seed)).
+"""
+from __future__ import annotations
+
+import math
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle", "_ref"))
+
+from oracle import oracle_graph as og  # noqa: E402
+from oracle import oracle_np as onp  # noqa: E402
+from tensormol_b200.engine import descriptor_width, random_weights  # noqa: E402
+
+REF = os.environ.get("TM_REFERENCE", "/root/reference")
+ATOI = {"H": 1, "C": 6, "N": 7, "O": 8, "Cl": 17}
+
+
+def read_xyz_frames(path):
+    frames = []
+    with open(path) as fh:
+        lines = fh.read().split("\n")
+    i = 0
+    while i < len(lines):
+        if not lines[i].strip():
+            i += 1
+            continue
+        n = int(lines[i].split()[0])
+        comment = lines[i + 1]
+        Z, X = [], []
+        for k in range(n):
+            p = lines[i + 2 + k].split()
+            Z.append(ATOI[p[0]] if p[0] in ATOI else int(p[0]))
+            X.append([float(p[1]), float(p[2]), float(p[3])])
+        frames.append((np.array(Z, np.int32), np.array(X, np.float64), comment))
+        i += 2 + n
+    return frames
+
+
+def symparams(P):
+    nAs, nRa, nRr = P["AN1_num_a_As"], P["AN1_num_a_Rs"], P["AN1_num_r_Rs"]
+    return {"AN1_r_Rs": np.array([P["AN1_r_Rc"] * i / nRr for i in range(nRr)]),
+            "AN1_a_Rs": np.array([P["AN1_a_Rc"] * i / nRa for i in range(nRa)]),
+            "AN1_a_As": np.array([2.0 * math.pi * i / nAs for i in range(nAs)]),
+            "AN1_num_r_Rs": nRr, "AN1_num_a_Rs": nRa, "AN1_num_a_As": nAs,
+            "AN1_r_Rc": P["AN1_r_Rc"], "AN1_a_Rc": P["AN1_a_Rc"], "AN1_eta": P["AN1_eta"], "AN1_zeta": P["AN1_zeta"]}
+
+
+def csr_from_lists(ll):
+    off = np.zeros(len(ll) + 1, np.int64)
+    off[1:] = np.cumsum([len(r) for r in ll])
+    idx = np.concatenate([np.sort(np.asarray(r, np.int64)) for r in ll]) if off[-1] else np.zeros(0, np.int64)
+    return off, idx
+
+
+def aperiodic_case(name, Z, X, hidden, seed, with_jacobian):
+    import MolEmb
+    P = og.default_params()
+    eles = sorted(set(int(z) for z in Z))
+    D = descriptor_width(len(eles), P)
+    W = random_weights(eles, D, hidden, seed)
+    orc = og.Oracle(eles, W, P)
+    N = len(Z)
+    res = orc.evaluate(X[None], Z[None], np.array([N]))
+    out = dict(Z=Z, xyz=X, eles=np.array(eles), hidden=np.array(hidden), seed=seed)
+    for rc, tag in ((P["AN1_r_Rc"], "rr"), (P["AN1_a_Rc"], "ra"), (P["EECutoffOff"], "ree")):
+        off, idx = csr_from_lists(MolEmb.Make_NListNaive(np.ascontiguousarray(X), float(rc), N, 1))
+        out[f"ref_nl_{tag}_off"], out[f"ref_nl_{tag}_idx"] = off, idx
+    off, idx = csr_from_lists(MolEmb.Make_NListNaive(np.ascontiguousarray(X), float(P["EECutoffOff"]), N, 0))
+    out["ref_nl_ree_noperm_off"], out["ref_nl_ree_noperm_idx"] = off, idx
+    sp = symparams(P)
+    out["ref_sym"] = MolEmb.Make_ANI1_Sym(sp, np.ascontiguousarray(X), Z.astype(np.uint8), np.array(eles, np.uint8), -1)
+    if with_jacobian:
+        out["ref_sym_deri"] = MolEmb.Make_ANI1_Sym_deri(sp, np.ascontiguousarray(X), Z.astype(np.uint8), np.array(eles, np.uint8), -1)
+    for k in ("Etotal", "Ebp", "Ebp_atom", "Ecc", "Evdw", "dipole", "charge", "gradient", "descriptors", "rad_p_ele", "ang_t_elep"):
+        out["oracle_" + k] = res[k]
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", name + ".npz"), **out)
+    print(name, "E", res["Etotal"], "max|F|", np.abs(res["gradient"]).max(),
+          "sym pin err", np.abs(out["ref_sym"] - res["descriptors"][0]).max())
+
+
+def periodic_case(name, Z, X, L, hidden, seed):
+    import MolEmb
+    P = og.default_params()
+    eles = sorted(set(int(z) for z in Z))
+    D = descriptor_width(len(eles), P)
+    W = random_weights(eles, D, hidden, seed)
+    orc = og.Oracle(eles, W, P)
+    lat = np.eye(3) * L
+    Xw = onp.modulo_lattice(lat, X)
+    Zt, Xt = onp.tess_lattice(lat, Z.astype(np.uint8), Xw, P["EECutoffOff"])
+    nreal = len(Z)
+    res = orc.evaluate_periodic(Xt, Zt, nreal)
+    ntess = int(round((len(Zt) / nreal) ** (1.0 / 3.0)) - 1) // 2
+    out = dict(Z=Z, xyz=Xw, lattice=lat, ntess=ntess, eles=np.array(eles), hidden=np.array(hidden), seed=seed)
+    for rc, tag in ((P["AN1_r_Rc"], "rr"), (P["AN1_a_Rc"], "ra")):
+        off, idx = csr_from_lists(MolEmb.Make_NListNaive(np.ascontiguousarray(Xt), float(rc), nreal, 1))
+        out[f"ref_nl_{tag}_off"], out[f"ref_nl_{tag}_idx"] = off, idx
+    off, idx = csr_from_lists(MolEmb.Make_NListNaive(np.ascontiguousarray(Xt), float(P["EECutoffOff"]), nreal, 1))
+    out["ref_nl_ree_count"] = np.diff(off)
+    out["ref_nl_ree_checksum"] = np.array([np.bitwise_xor.reduce(idx[off[i]:off[i + 1]]) if off[i + 1] > off[i] else 0 for i in range(nreal)])
+    sp = symparams(P)
+    # reference-native descriptor pin on the tessellated coordinates, first nreal rows.
+    # Make_ANI1_Sym is O(N^2): restrict it to the atoms that can matter (within Rr of a real atom).
+    keep = np.unique(np.concatenate([np.arange(nreal), out["ref_nl_rr_idx"]]))
+    sub = MolEmb.Make_ANI1_Sym(sp, np.ascontiguousarray(Xt[keep]), Zt[keep].astype(np.uint8), np.array(eles, np.uint8), -1)
+    out["ref_sym"] = sub[:nreal]
+    for k in ("Etotal", "Ebp", "Ebp_atom", "Ecc", "Evdw", "dipole", "descriptors", "gradient"):
+        out["oracle_" + k] = res[k] if k != "gradient" else res[k][:, :nreal]
+    out["oracle_charge"] = res["charge"][:, :nreal]
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", name + ".npz"), **out)
+    print(name, "ntess", ntess, "E", res["Etotal"], "n_ee", res["n_ee"], "sym pin err", np.abs(out["ref_sym"] - res["descriptors"][0]).max())
+
+
+def main():
+    os.makedirs(os.path.join(ROOT, "tests", "golden"), exist_ok=True)
+    Z, X, _ = read_xyz_frames(os.path.join(REF, "datasets", "H2O_cluster.xyz"))[0]
+    aperiodic_case("h2o_cluster", Z, X, [64, 48, 32], 0, True)
+    Z, X, _ = read_xyz_frames(os.path.join(REF, "datasets", "morphine.xyz"))[0]
+    aperiodic_case("morphine", Z, X, [96, 64, 64], 1, False)
+    Z, X, _ = read_xyz_frames(os.path.join(REF, "datasets", "water_tiny.xyz"))[0]
+    periodic_case("water_tiny_periodic", Z, X, 9.3215, [64, 48, 32], 2)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,359 @@
+"""
+TEST INFRASTRUCTURE ONLY -- CPU restatement (torch, float64, autograd) of the TensorFlow graph
+the reference builds for the BP+EE energy/force evaluation.
+
+Nothing in the product package may import this module (see oracle/oracle_np.py header).
+
+Parity pinning: "parity unpinned" by the reference's tests (it has none) and
+TensorFlow is not installable here.  What IS pinned, by executable reference code compiled from
+/root/reference (oracle/_ref/MolEmb): descriptor values (`MolEmb.Make_ANI1_Sym`,
+C_API/MolEmb.cpp:1913-1988) and descriptor Jacobians (`Make_ANI1_Sym_deri`, :1844-1911) -- see
+tests/test_oracle.py.  The MLP / electrostatics / gradient-assembly part is a hand restatement,
+cross-checked by central finite differences of its own energy and by the closed-form constants
+of SURVEY.md §8 a11/a13.
+
+Abbreviations: RSF = TensorMol/TFDescriptors/RawSymFunc.py, TMD =
+TensorMol/TFNetworks/TFMolInstanceDirect.py, MGR = TensorMol/TFNetworks/TFMolManage.py.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+
+from . import oracle_np as onp
+
+BOHRPERA = 1.889725989                      # PhysicalData.py:30
+KJPERHARTREE = 2625.499638                  # PhysicalData.py:34
+JOULEPERHARTREE = KJPERHARTREE * 1000.0     # PhysicalData.py:35
+C6_coff = {1: 0.14, 2: 0.08, 3: 1.16, 4: 1.61, 5: 3.13, 6: 1.75, 7: 1.23, 8: 0.70, 9: 0.75, 10: 0.63}   # PhysicalData.py:26
+atomic_vdw_radius = {1: 1.001, 2: 1.012, 3: 0.825, 4: 1.408, 5: 1.485, 6: 1.452, 7: 1.397, 8: 1.342, 9: 1.287, 10: 1.243}  # :25
+
+F64 = torch.float64
+
+
+def default_params():
+    """Hyper-parameters of the hot path with the reference defaults (TMParams.py:26-38,
+    150-165) as set by the water/chemspider scripts (EECutoffOn=0)."""
+    return dict(AN1_r_Rc=4.6, AN1_a_Rc=3.1, AN1_eta=4.0, AN1_zeta=8.0,
+                AN1_num_r_Rs=32, AN1_num_a_Rs=8, AN1_num_a_As=8,
+                EECutoffOn=0.0, EECutoffOff=15.0, Elu_Width=4.6, Poly_Width=4.6, DSFAlpha=0.18,
+                AddEcc=True, sigmoid_alpha=100.0, NeuronType="sigmoid_with_param")
+
+
+def dsf(R, R_c, alpha):
+    """Util.py:172-181."""
+    if R > R_c:
+        return 0.0
+    from scipy.special import erfc
+    XX = alpha * R_c
+    ZZ = erfc(XX) / R_c
+    YY = 1.1283791671 * alpha * math.exp(-XX * XX) / R_c
+    return erfc(alpha * R) / R - ZZ + (R - R_c) * (ZZ / R_c + YY)
+
+
+def dsf_gradient(R, R_c, alpha):
+    """Util.py:183-192."""
+    if R > R_c:
+        return 0.0
+    from scipy.special import erfc
+    XX = alpha * R_c
+    ZZ = erfc(XX) / R_c
+    YY = 1.1283791671 * alpha * math.exp(-XX * XX) / R_c
+    return -((erfc(alpha * R) / R / R + 1.1283791671 * alpha * math.exp(-alpha * R * alpha * R) / R) - (ZZ / R_c + YY))
+
+
+def elements_and_pairs(eles):
+    """TMD:1262-1267: eles sorted ascending, pairs upper-triangular row-major."""
+    eles = sorted(int(e) for e in eles)
+    pairs = [[eles[i], eles[j]] for i in range(len(eles)) for j in range(i, len(eles))]
+    return np.asarray(eles).reshape(-1, 1), np.asarray(pairs)
+
+
+def ani1_params(P):
+    """SetANI1Param (TMD:1293-1328): SFPr2 (1,nRs_r); SFPa2 (2,nAs,nRs_a) = (theta_a, Rs_s)."""
+    nAs, nRa, nRr = P["AN1_num_a_As"], P["AN1_num_a_Rs"], P["AN1_num_r_Rs"]
+    thetas = np.array([2.0 * math.pi * i / nAs for i in range(nAs)])
+    rs = np.array([P["AN1_a_Rc"] * i / nRa for i in range(nRa)])
+    rs_R = np.array([P["AN1_r_Rc"] * i / nRr for i in range(nRr)])
+    SFPa2 = np.stack([np.tile(thetas[:, None], (1, nRa)), np.tile(rs[None, :], (nAs, 1))], axis=0)
+    SFPr2 = rs_R.reshape(1, nRr)
+    return SFPr2, SFPa2
+
+
+def vdw_constants(eles):
+    """TMD:3763-3767."""
+    C6 = np.array([C6_coff[int(e)] * (BOHRPERA * 10.0) ** 6.0 / JOULEPERHARTREE for e in eles])
+    Rv = np.array([atomic_vdw_radius[int(e)] * BOHRPERA for e in eles])
+    return C6, Rv
+
+
+def activation(x, P):
+    """sigmoid_with_param (Util.py:200-201): log(1+exp(a x))/a, evaluated as a stable softplus
+    (identical wherever the reference's expression does not overflow float64)."""
+    kind = P.get("NeuronType", "sigmoid_with_param")
+    if kind == "sigmoid_with_param":
+        a = P["sigmoid_alpha"]
+        return torch.nn.functional.softplus(x, beta=a, threshold=1e9)
+    if kind == "relu":
+        return torch.relu(x)
+    if kind == "softplus":
+        return torch.nn.functional.softplus(x, threshold=1e9)
+    if kind == "tanh":
+        return torch.tanh(x)
+    if kind == "sigmoid":
+        return torch.sigmoid(x)
+    if kind == "elu":
+        return torch.nn.functional.elu(x)
+    raise ValueError(kind)
+
+
+# --------------------------------------------------------------------------------------
+# Weights  (TFInstance.py:277-297; layer shapes TMD:5188-5202, 5244-5264)
+# --------------------------------------------------------------------------------------
+def mlp(x, layers, P):
+    """layers = [(W1,b1),...,(W4,b4)]; y = a(xW+b) for hidden layers, last layer linear."""
+    h = x
+    for W, b in layers[:-1]:
+        h = activation(h @ W + b, P)
+    W, b = layers[-1]
+    return (h @ W + b)[:, 0]
+
+
+# --------------------------------------------------------------------------------------
+# Descriptors (RSF:1696-1863 radial; RSF:868-1136 angular; RSF:2223-2398 element partition)
+# --------------------------------------------------------------------------------------
+def sym_radial(R, pairs_ele, SFPr2, eta, R_cut, nrows, nele):
+    """TFSymRSet_Linear_WithEle(/Periodic): pairs_ele rows [mol,i,j,l]; returns (nmol,nrows,nele*nR).
+    scatter_nd into slots followed by reduce_sum over slots == index_add over (mol,i,l)."""
+    nmol = R.shape[0]
+    nr = SFPr2.shape[1]
+    out = torch.zeros(nmol * nrows * nele, nr, dtype=F64)
+    if pairs_ele.shape[0] == 0:
+        return out.reshape(nmol, nrows, nele * nr)
+    m, i, j, l = (pairs_ele[:, c] for c in range(4))
+    Rij = R[m, i] - R[m, j]                                            # DifferenceVectorsLinear RSF:123-133
+    r = torch.sqrt((Rij * Rij).sum(1) + 1e-27)                         # RSF:1731
+    tet = r[:, None] - torch.as_tensor(SFPr2[0], dtype=F64)[None, :]
+    fac1 = torch.exp(-eta * tet * tet)                                 # RSF:1736
+    fac2 = 0.5 * (torch.cos(3.14159265359 * r / R_cut) + 1.0)          # RSF:1738 (truncated pi, Q3)
+    Gm = fac1 * fac2[:, None]
+    out.index_add_(0, (m * nrows + i) * nele + l, Gm)
+    return out.reshape(nmol, nrows, nele * nr)
+
+
+def sym_angular(R, trip_elep, SFPa2, zeta, eta, R_cut, nrows, nelep):
+    """TFSymASet_Linear_WithEle(/Periodic): trip_elep rows [mol,i,j,k,l]; layout theta-major."""
+    nmol = R.shape[0]
+    ntheta, nr = SFPa2.shape[1], SFPa2.shape[2]
+    nsym = ntheta * nr
+    out = torch.zeros(nmol * nrows * nelep, nsym, dtype=F64)
+    if trip_elep.shape[0] == 0:
+        return out.reshape(nmol, nrows, nelep * nsym)
+    m, i, j, k, l = (trip_elep[:, c] for c in range(5))
+    Rij = R[m, i] - R[m, j]
+    Rik = R[m, i] - R[m, k]
+    rij = torch.sqrt((Rij * Rij).sum(1) + 1e-27)                       # RSF:911
+    rik = torch.sqrt((Rik * Rik).sum(1) + 1e-27)                       # RSF:913
+    ToACos = (Rij * Rik).sum(1) / (rij * rik)
+    onescalar = 1.0 - 0.0000000000000001
+    ToACos = torch.where(ToACos >= 1.0, torch.full_like(ToACos, onescalar), ToACos)    # RSF:918
+    ToACos = torch.where(ToACos <= -1.0, torch.full_like(ToACos, -onescalar), ToACos)  # RSF:919
+    theta = torch.acos(ToACos)
+    thetas = torch.as_tensor(SFPa2[0], dtype=F64)[None]               # (1,ntheta,nr)
+    rs = torch.as_tensor(SFPa2[1], dtype=F64)[None]
+    Tijk = torch.cos(theta[:, None, None] - thetas)
+    fac1 = (2.0 ** (1.0 - zeta)) * torch.pow(1.0 + Tijk, zeta)         # RSF:929
+    tet = ((rij + rik) / 2.0)[:, None, None] - rs
+    fac2 = torch.exp(-eta * tet * tet)                                 # RSF:933
+    fac3 = 0.5 * (torch.cos(3.14159265359 * rij / R_cut) + 1.0)        # RSF:935
+    fac4 = 0.5 * (torch.cos(3.14159265359 * rik / R_cut) + 1.0)        # RSF:936
+    Gm = (fac1 * fac2 * (fac3 * fac4)[:, None, None]).reshape(-1, nsym)
+    out.index_add_(0, (m * nrows + i) * nelep + l, Gm)
+    return out.reshape(nmol, nrows, nelep * nsym)
+
+
+def descriptors(R, pairs_ele, trip_elep, P, nele, nelep, nrows):
+    """GM = concat([GMR, GMA]) (RSF:2248)."""
+    SFPr2, SFPa2 = ani1_params(P)
+    GMR = sym_radial(R, pairs_ele, SFPr2, P["AN1_eta"], P["AN1_r_Rc"], nrows, nele)
+    GMA = sym_angular(R, trip_elep, SFPa2, P["AN1_zeta"], P["AN1_eta"], P["AN1_a_Rc"], nrows, nelep)
+    return torch.cat([GMR, GMA], dim=2)
+
+
+# --------------------------------------------------------------------------------------
+# Electrostatics / vdW   (RSF:1307-1465)
+# --------------------------------------------------------------------------------------
+def coulomb_elu_sr_dsf_lr(Rb, Qs, R_cut, pairs, alpha, elu_a, elu_shift, P):
+    """TFCoulombEluSRDSFLR (RSF:1307-1359).  Rb in Bohr, pairs rows [mol,i,j]."""
+    nmol = Rb.shape[0]
+    out = torch.zeros(nmol, dtype=F64)
+    if pairs.shape[0] == 0:
+        return out
+    alpha = alpha / BOHRPERA
+    R_lrcut = P["EECutoffOff"] * BOHRPERA
+    m, i, j = pairs[:, 0], pairs[:, 1], pairs[:, 2]
+    Rij = Rb[m, i] - Rb[m, j]
+    r = torch.sqrt((Rij * Rij).sum(1) + 1e-27)
+    SR_sub = torch.where(r > R_cut, elu_a * (r - R_cut) + elu_shift, elu_a * (torch.exp(torch.clamp(r - R_cut, max=0.0)) - 1.0) + elu_shift)
+    Qij = Qs[m, i] * Qs[m, j]
+    XX = alpha * R_lrcut
+    ZZ = math.erfc(XX) / R_lrcut
+    YY = 1.1283791671 * alpha * math.exp(-XX * XX) / R_lrcut
+    LR = Qij * (torch.erfc(alpha * r) / r - ZZ + (r - R_lrcut) * (ZZ / R_lrcut + YY))
+    LR = torch.where(torch.isnan(LR), torch.zeros_like(LR), LR)
+    LR = torch.where(r > R_lrcut, torch.zeros_like(LR), LR)
+    SR = Qij * SR_sub
+    K = torch.where(r > R_cut, LR, SR)
+    out.index_add_(0, m, K)
+    return out
+
+
+def vdw_poly_lr(Rb, c6_i, c6_j, Rv_i, Rv_j, R_cut, pairs, P):
+    """TFVdwPolyLR / TFVdwPolyLRWithEle (RSF:1361-1465).  Rb already in Bohr and scaled by
+    BOHRPERA AGAIN (RSF:1377/1433, quirk Q6)."""
+    nmol = Rb.shape[0]
+    out = torch.zeros(nmol, dtype=F64)
+    if pairs.shape[0] == 0:
+        return out
+    R = Rb * BOHRPERA
+    R_width = P["Poly_Width"] * BOHRPERA
+    m, i, j = pairs[:, 0], pairs[:, 1], pairs[:, 2]
+    Rij = R[m, i] - R[m, j]
+    r = torch.sqrt((Rij * Rij).sum(1) + 1e-27)
+    t = (r - R_cut) / R_width
+    Cut1 = torch.where(t > 0.0, -t * t * (2.0 * t - 3.0), torch.zeros_like(t))
+    Cut = torch.where(t > 1.0, torch.ones_like(t), Cut1)
+    Kern = -Cut * torch.sqrt(c6_i * c6_j) / torch.pow(r, 6.0) * 1.0 / (1.0 + 6.0 * torch.pow(r / (Rv_i + Rv_j), -12.0))
+    out.index_add_(0, m, Kern)
+    return out
+
+
+# --------------------------------------------------------------------------------------
+# Whole evaluation (TMD:5164-5285 aperiodic, 5774-5898 periodic; MGR:1260-1358)
+# --------------------------------------------------------------------------------------
+class Oracle:
+    """weights = {"charge": {Z: [(W,b)...]}, "energy": {Z: [(W,b)...]}} of numpy float64 arrays."""
+
+    def __init__(self, eles, weights, params=None):
+        self.P = default_params()
+        if params:
+            self.P.update(params)
+        self.eles_np, self.eles_pairs_np = elements_and_pairs(eles)
+        self.eles = [int(e) for e in self.eles_np.reshape(-1)]
+        self.nele = len(self.eles)
+        self.nelep = self.eles_pairs_np.shape[0]
+        self.C6, self.vdw_R = vdw_constants(self.eles)
+        P = self.P
+        if P["EECutoffOn"] != 0.0:
+            raise Exception("EECutoffOn should equal to zero in DSF_elu")      # TMD:4366
+        self.elu_shift = dsf(P["Elu_Width"] * BOHRPERA, P["EECutoffOff"] * BOHRPERA, P["DSFAlpha"] / BOHRPERA)      # TMD:4371
+        self.elu_alpha = dsf_gradient(P["Elu_Width"] * BOHRPERA, P["EECutoffOff"] * BOHRPERA, P["DSFAlpha"] / BOHRPERA)
+        self.w = {net: {int(z): [(torch.as_tensor(np.asarray(W, np.float64)), torch.as_tensor(np.asarray(b, np.float64)))
+                                 for W, b in layers] for z, layers in d.items()} for net, d in weights.items()}
+
+    # ---- shared pieces -------------------------------------------------------------
+    def _nets(self, GM, Zs_rows, net):
+        """per-element MLP + scatter back to [nmol, nrows] (TMD:5180-5211 / 5236-5272)."""
+        nmol, nrows, D = GM.shape
+        out = torch.zeros(nmol * nrows, dtype=F64)
+        flatZ = torch.as_tensor(Zs_rows.reshape(-1).astype(np.int64))
+        G2 = GM.reshape(nmol * nrows, D)
+        for z in self.eles:
+            idx = torch.nonzero(flatZ == z)[:, 0]
+            if idx.numel() == 0:
+                continue
+            y = mlp(G2[idx], self.w[net][z], self.P)
+            out = out.index_add(0, idx, y)
+        return out.reshape(nmol, nrows)
+
+    # ---- aperiodic -----------------------------------------------------------------
+    def evaluate(self, xyzs, Zs, natom, has_vdw=True, want=("all",)):
+        """EvalBPDirectEEUpdateSet/Single (MGR:1260-1321) + evaluate (TMD:5684-5711).
+        xyzs (nmol,N,3) f64 padded with zeros, Zs (nmol,N) int padded with 0, natom (nmol,)."""
+        P = self.P
+        xyzs = np.ascontiguousarray(xyzs, np.float64)
+        Zs = np.asarray(Zs)
+        natom = np.asarray(natom, np.int64)
+        nmol, N, _ = xyzs.shape
+        rp, tt, mil_jk, _ = onp.build_pairs_and_triples_with_ele_index(xyzs, natom, natom, Zs, P["AN1_r_Rc"], P["AN1_a_Rc"], self.eles_np, self.eles_pairs_np)
+        ree = onp.set_build_pairs(xyzs, natom, natom, P["EECutoffOff"], False).astype(np.int64)
+        rp = torch.as_tensor(rp.astype(np.int64))
+        tt = torch.as_tensor(tt.astype(np.int64))
+        ree = torch.as_tensor(ree)
+        R = torch.tensor(xyzs, dtype=F64, requires_grad=True)
+        GM = descriptors(R, rp, tt, P, self.nele, self.nelep, N)
+        # charges
+        q_raw = self._nets(GM, Zs, "charge")
+        inv_n = torch.as_tensor(1.0 / natom.astype(np.float64))
+        q = q_raw - (q_raw.sum(1) * inv_n)[:, None]                          # TMD:5274-5277 (padded atoms also get -mean, Q11)
+        Rb = R * BOHRPERA
+        dipole = (Rb * q[:, :, None]).sum(1)                                 # TMD:5278-5279
+        if P["AddEcc"]:
+            Ecc = coulomb_elu_sr_dsf_lr(Rb, q, P["Elu_Width"] * BOHRPERA, ree, P["DSFAlpha"], self.elu_alpha, self.elu_shift, P)
+        else:
+            Ecc = torch.zeros(nmol, dtype=F64)
+        Ebp_atom = self._nets(GM, Zs, "energy")
+        Ebp = Ebp_atom.sum(1)
+        if ree.shape[0]:
+            zi = Zs[ree[:, 0].numpy(), ree[:, 1].numpy()]
+            zj = Zs[ree[:, 0].numpy(), ree[:, 2].numpy()]
+            ei = np.searchsorted(np.asarray(self.eles), zi)
+            ej = np.searchsorted(np.asarray(self.eles), zj)
+            Evdw = vdw_poly_lr(Rb, torch.as_tensor(self.C6[ei]), torch.as_tensor(self.C6[ej]), torch.as_tensor(self.vdw_R[ei]), torch.as_tensor(self.vdw_R[ej]),
+                               P["EECutoffOn"] * BOHRPERA, ree, P)
+        else:
+            Evdw = torch.zeros(nmol, dtype=F64)
+        Etotal = Ebp + Ecc + Evdw                                            # TMD:5213-5215
+        (grad,) = torch.autograd.grad(Etotal.sum(), R)                       # TMD:5761
+        return dict(Etotal=Etotal.detach().numpy(), Ebp=Ebp.detach().numpy(), Ebp_atom=Ebp_atom.detach().numpy(),
+                    Ecc=Ecc.detach().numpy(), Evdw=Evdw.detach().numpy(), dipole=dipole.detach().numpy(),
+                    charge=q.detach().numpy(), gradient=grad.numpy(), force=-JOULEPERHARTREE * grad.numpy(),
+                    descriptors=GM.detach().numpy(), rad_p_ele=rp.numpy(), ang_t_elep=tt.numpy(), ree=ree.numpy())
+
+    # ---- periodic (images supplied by the caller) -----------------------------------
+    def evaluate_periodic(self, xyz_tess, Z_tess, nreal, do_force=True):
+        """EvalBPDirectEEUpdateSinglePeriodic (MGR:1323-1358) + evaluate_periodic (TMD:5918-5947):
+        xyz_tess (Ntess,3) with the nreal real atoms first, then images."""
+        P = self.P
+        x = np.ascontiguousarray(xyz_tess, np.float64)[None]
+        Zs = np.asarray(Z_tess)[None].astype(np.int64)
+        Nt = x.shape[1]
+        nnz = np.array([Nt])
+        nr = np.array([nreal])
+        rp, tt, mil_j, mil_jk = onp.build_pairs_and_triples_with_ele_index_periodic(x, nnz, nr, Zs, P["AN1_r_Rc"], P["AN1_a_Rc"], self.eles_np, self.eles_pairs_np)
+        ree5 = onp.build_pairs_with_both_ele_index(x, nnz, nr, Zs, P["EECutoffOff"], self.eles_np, True)
+        rp = torch.as_tensor(rp.astype(np.int64))
+        tt = torch.as_tensor(tt.astype(np.int64))
+        ree = torch.as_tensor(ree5[:, :3].astype(np.int64))
+        R = torch.tensor(x, dtype=F64, requires_grad=True)
+        GM = descriptors(R, rp, tt, P, self.nele, self.nelep, nreal)
+        q_raw = self._nets(GM, Zs[:, :nreal], "charge")
+        q = q_raw - (q_raw.sum(1) * (1.0 / nreal))[:, None]                  # natom fed as nreal (MGR:1342)
+        Rb = R * BOHRPERA
+        dipole = (Rb[:, :nreal] * q[:, :, None]).sum(1)
+        ntess = Nt // nreal
+        q_all = q.repeat(1, ntess)                                           # TMD:5892-5893
+        if P["AddEcc"]:
+            Ecc = coulomb_elu_sr_dsf_lr(Rb, q_all, P["Elu_Width"] * BOHRPERA, ree, P["DSFAlpha"], self.elu_alpha, self.elu_shift, P) / 2.0   # TMD:5896
+        else:
+            Ecc = torch.zeros(1, dtype=F64)
+        Ebp_atom = self._nets(GM, Zs[:, :nreal], "energy")
+        Ebp = Ebp_atom.sum(1)
+        ei, ej = ree5[:, 3].astype(np.int64), ree5[:, 4].astype(np.int64)
+        Evdw = vdw_poly_lr(Rb, torch.as_tensor(self.C6[ei]), torch.as_tensor(self.C6[ej]), torch.as_tensor(self.vdw_R[ei]), torch.as_tensor(self.vdw_R[ej]),
+                           P["EECutoffOn"] * BOHRPERA, ree, P) / 2.0         # TMD:5824
+        Etotal = Ebp + Ecc + Evdw
+        res = dict(Etotal=Etotal.detach().numpy(), Ebp=Ebp.detach().numpy(), Ebp_atom=Ebp_atom.detach().numpy(),
+                   Ecc=Ecc.detach().numpy(), Evdw=Evdw.detach().numpy(), dipole=dipole.detach().numpy(),
+                   charge=q_all.detach().numpy(), descriptors=GM.detach().numpy(),
+                   rad_p_ele=rp.numpy(), ang_t_elep=tt.numpy(), n_ee=int(ree.shape[0]))
+        if do_force:
+            (grad,) = torch.autograd.grad(Etotal.sum(), R)                   # TMD:5999
+            res["gradient"] = grad.numpy()
+            res["force"] = -JOULEPERHARTREE * grad.numpy()[0, :nreal].reshape(1, nreal, 3)   # MGR:1353
+        return res
+
+    def energy_only(self, xyzs, Zs, natom):
+        return self.evaluate(xyzs, Zs, natom)["Etotal"]

@@ -1,0 +1,747 @@
+// C-ABI of libtmolb200.so (see include/tmolb200.h): context, weights, evaluation pipelines and the
+// MolEmb / Neighbors.py compatible neighbour-table entry points.
+#include "tm_internal.h"
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#define FULL 0xffffffffu
+
+// ------------------------------------------------------------------------------------------------ errors
+static thread_local char g_err[1024] = "";
+void tm_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+extern "C" const char* tm_last_error(void) { return g_err; }
+extern "C" int tm_version(void) { return 100; }
+extern "C" int tm_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+int tm_buf(tm_ctx* c, DevBuf& b, size_t bytes) {
+  if (bytes < 256) bytes = 256;
+  if (b.cap >= bytes) return TM_OK;
+  if (b.p) {
+    TM_CUDA(cudaStreamSynchronize(c->stream));
+    TM_CUDA(cudaFree(b.p));
+    b.p = nullptr; b.cap = 0;
+  }
+  size_t want = bytes + bytes / 8;
+  TM_CUDA(cudaMalloc(&b.p, want));
+  TM_CUDA(cudaMemsetAsync(b.p, 0, want, c->stream));
+  b.cap = want;
+  return TM_OK;
+}
+
+int tm_host_stage(tm_ctx* c, size_t bytes) {
+  if (c->h_cap >= bytes) return TM_OK;
+  if (c->h_stage) { TM_CUDA(cudaStreamSynchronize(c->stream)); TM_CUDA(cudaFreeHost(c->h_stage)); c->h_stage = nullptr; c->h_cap = 0; }
+  size_t want = bytes + bytes / 4 + 4096;
+  TM_CUDA(cudaMallocHost(&c->h_stage, want));
+  c->h_cap = want;
+  return TM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ params
+static int round_up(int v, int m) { return ((v + m - 1) / m) * m; }
+
+static int build_dev_params(tm_ctx* c) {
+  const tm_params& p = c->params;
+  const tm_model_desc& d = c->desc;
+  DevParams& P = c->hp;
+  memset(&P, 0, sizeof(P));
+  if (d.n_ele < 1 || d.n_ele > TM_MAX_ELE) { tm_set_error("n_ele must be 1..%d", TM_MAX_ELE); return TM_EINVAL; }
+  if (p.num_r_Rs < 1 || p.num_r_Rs > 64 || p.num_a_Rs < 1 || p.num_a_Rs > TM_MAX_SYM || p.num_a_As < 1 || p.num_a_As > TM_MAX_SYM) {
+    tm_set_error("symmetry-function counts out of range (num_r_Rs<=64, num_a_Rs,num_a_As<=%d)", TM_MAX_SYM);
+    return TM_EINVAL;
+  }
+  if (p.ee_cutoff_on != 0.0) { tm_set_error("EECutoffOn should equal to zero in DSF_elu"); return TM_EINVAL; }   // TFMolInstanceDirect.py:4366
+  P.n_ele = d.n_ele;
+  P.n_elep = d.n_ele * (d.n_ele + 1) / 2;
+  for (int i = 0; i < d.n_ele; i++) {
+    P.eles[i] = d.eles[i];
+    if (i && d.eles[i] <= d.eles[i - 1]) { tm_set_error("eles must be strictly ascending"); return TM_EINVAL; }
+  }
+  int l = 0;   // pair channels: upper triangular row-major (TFMolInstanceDirect.py:1262-1267)
+  for (int i = 0; i < d.n_ele; i++)
+    for (int j = i; j < d.n_ele; j++) {
+      P.pair_index[i][j] = (int8_t)l;
+      P.pair_index[j][i] = (int8_t)l;
+      l++;
+    }
+  P.nRs_r = p.num_r_Rs; P.nRs_a = p.num_a_Rs; P.nAs = p.num_a_As; P.nsym = p.num_a_As * p.num_a_Rs;
+  P.D = d.n_ele * P.nRs_r + P.n_elep * P.nsym;
+  P.Dp = round_up(P.D, 128);
+  P.r_Rc = (float)p.r_Rc; P.a_Rc = (float)p.a_Rc; P.eta = (float)p.eta; P.zeta = (float)p.zeta;
+  P.pi_over_rRc = (float)(3.14159265359 / p.r_Rc);
+  P.pi_over_aRc = (float)(3.14159265359 / p.a_Rc);
+  P.zeta_pref = (float)pow(2.0, 1.0 - p.zeta);
+  P.zeta_is8 = (p.zeta == 8.0);
+  for (int s = 0; s < P.nRs_r; s++) P.Rs_r[s] = (float)(p.r_Rc * s / P.nRs_r);       // SetANI1Param
+  for (int s = 0; s < P.nRs_a; s++) P.Rs_a[s] = (float)(p.a_Rc * s / P.nRs_a);
+  for (int a = 0; a < P.nAs; a++) {
+    double th = 2.0 * M_PI * a / P.nAs;
+    P.cosA[a] = (float)cos(th);
+    P.sinA[a] = (float)sin(th);
+  }
+  const double B = TM_BOHRPERA;
+  double alpha = p.dsf_alpha / B, Rl = p.ee_cutoff_off * B;
+  P.R_lr = (float)Rl; P.R_sr = (float)(p.elu_width * B); P.alpha_b = (float)alpha;
+  double ZZ = erfc(alpha * Rl) / Rl;
+  double YY = 1.1283791671 * alpha * exp(-alpha * Rl * alpha * Rl) / Rl;
+  P.Zc = (float)ZZ; P.ZoverR_plus_Y = (float)(ZZ / Rl + YY);
+  P.elu_a = (float)p.elu_alpha; P.elu_shift = (float)p.elu_shift;
+  P.poly_width_b = (float)(p.poly_width * B);
+  for (int i = 0; i < d.n_ele; i++) { P.sqrtC6[i] = (float)sqrt(p.C6[i]); P.Rvdw[i] = (float)p.Rvdw[i]; }
+  P.add_ecc = p.add_ecc; P.activation = p.activation; P.act_alpha = (float)p.sigmoid_alpha;
+  P.rr_exact = p.r_Rc; P.ra_exact = p.a_Rc;
+  return TM_OK;
+}
+
+extern "C" int tm_set_params(tm_ctx* c, const tm_params* params) {
+  if (!c || !params) { tm_set_error("null argument"); return TM_EINVAL; }
+  tm_params old = c->params;
+  c->params = *params;
+  int rc = build_dev_params(c);
+  if (rc) { c->params = old; build_dev_params(c); return rc; }
+  return TM_OK;
+}
+
+extern "C" tm_ctx* tm_create(int device, const tm_model_desc* desc, const tm_params* params) {
+  if (!desc || !params) { tm_set_error("null argument"); return nullptr; }
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    tm_set_error("no CUDA device: libtmolb200 has no CPU fallback");
+    return nullptr;
+  }
+  if (device < 0 || device >= n) { tm_set_error("device %d out of range (have %d)", device, n); return nullptr; }
+  if (cudaSetDevice(device) != cudaSuccess) { tm_set_error("cudaSetDevice failed"); return nullptr; }
+  tm_ctx* c = new tm_ctx();
+  c->device = device;
+  c->desc = *desc;
+  c->params = *params;
+  if (desc->n_hidden < 1 || desc->n_hidden > TM_MAX_HIDDEN) { tm_set_error("n_hidden must be 1..%d", TM_MAX_HIDDEN); delete c; return nullptr; }
+  if (build_dev_params(c)) { delete c; return nullptr; }
+  c->Hmax = 0;
+  for (int l = 0; l < desc->n_hidden; l++) {
+    c->Hp[l] = round_up(desc->hidden[l], 128);
+    c->Hmax = std::max(c->Hmax, c->Hp[l]);
+  }
+  if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) { tm_set_error("stream create failed"); delete c; return nullptr; }
+  c->stream = c->own_stream;
+  for (int i = 0; i < 12; i++) cudaEventCreate(&c->ev[i]);
+  c->ev_ok = true;
+  memset(&c->last, 0, sizeof(c->last));
+  return c;
+}
+
+static void free_buf(DevBuf& b) { if (b.p) cudaFree(b.p); b.p = nullptr; b.cap = 0; }
+
+extern "C" void tm_destroy(tm_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  DevBuf* all[] = {&c->b_pos, &c->b_Z, &c->b_cellid, &c->b_rank, &c->b_count, &c->b_cstart, &c->b_sorted, &c->b_satom, &c->b_scan_tmp,
+                   &c->b_rowslot, &c->b_rowsidx, &c->b_rowofslot, &c->b_blkcnt, &c->b_rowmeta, &c->b_nbcnt, &c->b_nboff, &c->b_nbr, &c->b_G,
+                   &c->b_delta0, &c->b_delta1, &c->b_dG[0], &c->b_dG[1], &c->b_y[0], &c->b_y[1], &c->b_q, &c->b_qs, &c->b_dedq, &c->b_u, &c->b_F,
+                   &c->b_Fpair, &c->b_acc, &c->b_bbox, &c->b_grid, &c->b_flags, &c->b_out, &c->b_molacc, &c->b_natom, &c->b_lattice};
+  for (DevBuf* b : all) free_buf(*b);
+  for (int n = 0; n < 2; n++)
+    for (int l = 0; l < TM_MAX_HIDDEN; l++) free_buf(c->b_act[n][l]);
+  for (int n = 0; n < 2; n++)
+    for (int e = 0; e < TM_MAX_ELE; e++) {
+      Net& N = c->nets[n][e];
+      for (int l = 0; l < TM_MAX_HIDDEN; l++) {
+        if (N.layers[l].W) cudaFree(N.layers[l].W);
+        if (N.layers[l].WT) cudaFree(N.layers[l].WT);
+        if (N.layers[l].b) cudaFree(N.layers[l].b);
+      }
+      if (N.w_out) cudaFree(N.w_out);
+    }
+  if (c->h_stage) cudaFreeHost(c->h_stage);
+  if (c->ev_ok) for (int i = 0; i < 12; i++) cudaEventDestroy(c->ev[i]);
+  if (c->own_stream) cudaStreamDestroy(c->own_stream);
+  delete c;
+}
+
+extern "C" int tm_set_stream(tm_ctx* c, void* s) {
+  if (!c) return TM_EINVAL;
+  c->stream = s ? (cudaStream_t)s : c->own_stream;
+  return TM_OK;
+}
+extern "C" int tm_set_gemm_mode(tm_ctx* c, int mode) {
+  if (!c || mode < 0 || mode > 2) { tm_set_error("bad gemm mode"); return TM_EINVAL; }
+  c->gemm_mode = mode;
+  return TM_OK;
+}
+extern "C" int tm_get_gemm_mode(tm_ctx* c) { return c ? c->gemm_mode : TM_EINVAL; }
+extern "C" int tm_descriptor_width(tm_ctx* c) { return c ? c->hp.D : TM_EINVAL; }
+extern "C" int tm_sync(tm_ctx* c) {
+  if (!c) return TM_EINVAL;
+  TM_CUDA(cudaSetDevice(c->device));
+  TM_CUDA(cudaStreamSynchronize(c->stream));
+  return TM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ weights
+extern "C" int tm_set_weights(tm_ctx* c, int net, int ele_index, int layer, const double* W, const double* b, int rows, int cols) {
+  if (!c || !W || !b) { tm_set_error("null argument"); return TM_EINVAL; }
+  if (net < 0 || net > 1 || ele_index < 0 || ele_index >= c->desc.n_ele || layer < 0 || layer > c->desc.n_hidden) {
+    tm_set_error("tm_set_weights: index out of range");
+    return TM_EINVAL;
+  }
+  TM_CUDA(cudaSetDevice(c->device));
+  int nh = c->desc.n_hidden;
+  Net& N = c->nets[net][ele_index];
+  if (layer == nh) {
+    if (rows != c->desc.hidden[nh - 1] || cols != 1) { tm_set_error("output layer must be [%d][1]", c->desc.hidden[nh - 1]); return TM_EINVAL; }
+    int Hp = c->Hp[nh - 1];
+    std::vector<float> w((size_t)Hp, 0.f);
+    for (int i = 0; i < rows; i++) w[i] = (float)W[i];
+    if (!N.w_out) TM_CUDA(cudaMalloc(&N.w_out, (size_t)Hp * 4));
+    TM_CUDA(cudaMemcpy(N.w_out, w.data(), (size_t)Hp * 4, cudaMemcpyHostToDevice));
+    N.b_out = (float)b[0];
+    N.set[nh] = true;
+    return TM_OK;
+  }
+  int K = (layer == 0) ? c->hp.D : c->desc.hidden[layer - 1];
+  int Kp = (layer == 0) ? c->hp.Dp : c->Hp[layer - 1];
+  int Nn = c->desc.hidden[layer], Np = c->Hp[layer];
+  if (rows != K || cols != Nn) { tm_set_error("layer %d must be [%d][%d], got [%d][%d]", layer, K, Nn, rows, cols); return TM_EINVAL; }
+  Layer& L = N.layers[layer];
+  L.K = K; L.N = Nn; L.Kp = Kp; L.Np = Np;
+  std::vector<float> w((size_t)Kp * Np, 0.f), wt((size_t)Np * Kp, 0.f), bb((size_t)Np, 0.f);
+  for (int k = 0; k < K; k++)
+    for (int n = 0; n < Nn; n++) {
+      float v = (float)W[(size_t)k * Nn + n];
+      w[(size_t)k * Np + n] = v;
+      wt[(size_t)n * Kp + k] = v;
+    }
+  for (int n = 0; n < Nn; n++) bb[n] = (float)b[n];
+  if (!L.W) TM_CUDA(cudaMalloc(&L.W, w.size() * 4));
+  if (!L.WT) TM_CUDA(cudaMalloc(&L.WT, wt.size() * 4));
+  if (!L.b) TM_CUDA(cudaMalloc(&L.b, bb.size() * 4));
+  TM_CUDA(cudaMemcpy(L.W, w.data(), w.size() * 4, cudaMemcpyHostToDevice));
+  TM_CUDA(cudaMemcpy(L.WT, wt.data(), wt.size() * 4, cudaMemcpyHostToDevice));
+  TM_CUDA(cudaMemcpy(L.b, bb.data(), bb.size() * 4, cudaMemcpyHostToDevice));
+  N.set[layer] = true;
+  return TM_OK;
+}
+
+static int check_weights(tm_ctx* c) {
+  for (int n = 0; n < 2; n++)
+    for (int e = 0; e < c->desc.n_ele; e++)
+      for (int l = 0; l <= c->desc.n_hidden; l++)
+        if (!c->nets[n][e].set[l]) {
+          tm_set_error("weights not set: net %d element index %d layer %d (call tm_set_weights)", n, e, l);
+          return TM_ESTATE;
+        }
+  return TM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ small kernels
+// per row: Ebp_atom (slot order, double) and per-molecule Ebp
+__global__ void k_ebp(const float* __restrict__ y, const int32_t* __restrict__ rowslot, int64_t nrows, int64_t maxnatom,
+                      double* __restrict__ ebp_slot, double* __restrict__ molacc) {
+  int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  int slot = (r < nrows) ? rowslot[r] : -1;
+  double v = 0.0;
+  int m = -1;
+  if (slot >= 0) {
+    v = (double)y[r];
+    m = (int)(slot / maxnatom);
+    if (ebp_slot) ebp_slot[slot] = v;
+  }
+  // warp-aggregate when the whole warp belongs to one molecule
+  int m0 = __shfl_sync(FULL, m, 0);
+  bool uniform = __all_sync(FULL, m == m0 || m < 0);
+  if (uniform) {
+    int mm = m;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      v += __shfl_xor_sync(FULL, v, o);
+      mm = max(mm, __shfl_xor_sync(FULL, mm, o));
+    }
+    if ((threadIdx.x & 31) == 0 && mm >= 0) atomicAdd(&molacc[16 * mm + 1], v);
+  } else if (m >= 0) {
+    atomicAdd(&molacc[16 * m + 1], v);
+  }
+}
+
+// u[row] = dE/dq_raw = dE/dq_slot - mean_mol(dE/dq)   (backward of the neutralisation, TFMolInstanceDirect.py:5274-5277)
+__global__ void k_u(const double* __restrict__ dedq_slot, const double* __restrict__ molacc, const double* __restrict__ inv_n,
+                    const int32_t* __restrict__ rowslot, int64_t nrows, int64_t maxnatom, int add_ecc, float* __restrict__ u) {
+  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < nrows; r += (int64_t)gridDim.x * blockDim.x) {
+    int slot = rowslot[r];
+    float v = 0.f;
+    if (slot >= 0 && add_ecc) {
+      int m = (int)(slot / maxnatom);
+      v = (float)(dedq_slot[slot] - molacc[16 * m + 5] * inv_n[m]);
+    }
+    u[r] = v;
+  }
+}
+
+// pack the outputs as doubles: [Etot nmol][Ebp][Ecc][Evdw][dipole 3nmol][Ebp_atom nq][charge nq][grad 3nq]
+__global__ void k_pack(const double* __restrict__ molacc, int64_t nmol, int add_ecc, double* __restrict__ out) {
+  for (int64_t m = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; m < nmol; m += (int64_t)gridDim.x * blockDim.x) {
+    double ebp = molacc[16 * m + 1], ecc = add_ecc ? molacc[16 * m + 2] : 0.0, evdw = molacc[16 * m + 3];
+    out[m] = ebp + ecc + evdw;                 // TFMolInstanceDirect.py:5213-5215
+    out[nmol + m] = ebp;
+    out[2 * nmol + m] = ecc;
+    out[3 * nmol + m] = evdw;
+    out[4 * nmol + 3 * m] = molacc[16 * m + 6];
+    out[4 * nmol + 3 * m + 1] = molacc[16 * m + 7];
+    out[4 * nmol + 3 * m + 2] = molacc[16 * m + 8];
+  }
+}
+__global__ void k_f2d(const float* __restrict__ in, double* __restrict__ out, int64_t n) {
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) out[t] = (double)in[t];
+}
+__global__ void k_d2d(const double* __restrict__ in, double* __restrict__ out, int64_t n) {
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) out[t] = in[t];
+}
+__global__ void k_desc_out(const float* __restrict__ G, const int32_t* __restrict__ rowofslot, int64_t nq, int D, int Dp, float* __restrict__ out) {
+  int64_t slot = blockIdx.x;
+  if (slot >= nq) return;
+  int row = rowofslot[slot];
+  for (int d = threadIdx.x; d < D; d += blockDim.x) out[slot * D + d] = (row >= 0) ? G[(int64_t)row * Dp + d] : 0.f;
+}
+__global__ void k_set_i32(int32_t* p, int64_t n, int32_t v) {
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) p[t] = v;
+}
+
+static inline int nblk(int64_t n, int per = 256, int cap = 148 * 8) {
+  int64_t b = (n + per - 1) / per;
+  if (b < 1) b = 1;
+  if (b > cap) b = cap;
+  return (int)b;
+}
+
+// ------------------------------------------------------------------------------------------------ pipeline
+struct OutLayout {
+  int64_t nmol, nq, off_ebp_atom, off_charge, off_grad, total;
+};
+static OutLayout out_layout(int64_t nmol, int64_t nq) {
+  OutLayout o;
+  o.nmol = nmol; o.nq = nq;
+  o.off_ebp_atom = 7 * nmol;
+  o.off_charge = o.off_ebp_atom + nq;
+  o.off_grad = o.off_charge + nq;
+  o.total = o.off_grad + 3 * nq;
+  return o;
+}
+
+static SysView make_view(tm_ctx* c, int64_t nslots, int64_t nmol, int64_t maxnatom, int64_t nreal, int periodic, int64_t ncent_max) {
+  SysView s;
+  s.nslots = nslots; s.nmol = nmol; s.maxnatom = maxnatom; s.nreal = nreal; s.periodic = periodic;
+  s.ncent_max = ncent_max;
+  s.nrows = ncent_max + (int64_t)TM_ROW_TILE * c->hp.n_ele;
+  s.ncells_cap = nslots + 1024;
+  s.slab_rank = 0; s.slab_world = 1;
+  s.slab_g[0] = s.slab_g[1] = s.slab_g[2] = 0.0;
+  return s;
+}
+
+// stages up to and including the nets' forward pass (pos/Z/inv_n already on the device)
+static int stage_a(tm_ctx* c, const SysView& s) {
+  int rc;
+  int64_t nq = s.periodic ? s.nreal : s.nslots;
+  if ((rc = tm_buf(c, c->b_flags, 64))) return rc;
+  if ((rc = tm_buf(c, c->b_molacc, (size_t)s.nmol * 16 * 8))) return rc;
+  if ((rc = tm_buf(c, c->b_F, (size_t)nq * 3 * 4))) return rc;
+  if ((rc = tm_buf(c, c->b_u, (size_t)s.nrows * 4))) return rc;
+  TM_CUDA(cudaMemsetAsync(c->b_flags.p, 0, 64, c->stream));
+  TM_CUDA(cudaMemsetAsync(c->b_molacc.p, 0, (size_t)s.nmol * 16 * 8, c->stream));
+  TM_CUDA(cudaMemsetAsync(c->b_F.p, 0, (size_t)nq * 3 * 4, c->stream));
+  cudaEventRecord(c->ev[1], c->stream);
+  if ((rc = tm_launch_nlist_build(c, s, c->params.r_Rc))) return rc;
+  if ((rc = tm_launch_rows(c, s))) return rc;
+  if ((rc = tm_launch_neighbours(c, s))) return rc;
+  cudaEventRecord(c->ev[2], c->stream);
+  if ((rc = tm_launch_desc(c, s))) return rc;
+  cudaEventRecord(c->ev[3], c->stream);
+  if ((rc = tm_launch_mlp_forward(c, s))) return rc;
+  cudaEventRecord(c->ev[4], c->stream);
+  return TM_OK;
+}
+
+static int stage_b(tm_ctx* c, const SysView& s, int flags) {
+  int rc;
+  if ((rc = tm_launch_charges(c, s))) return rc;
+  if ((rc = tm_launch_pair(c, s, flags))) return rc;
+  cudaEventRecord(c->ev[5], c->stream);
+  return TM_OK;
+}
+
+static int stage_c(tm_ctx* c, const SysView& s, int flags) {
+  int rc;
+  if (flags & TM_F_FORCE) {
+    if ((rc = tm_launch_mlp_backward(c, s))) return rc;
+    cudaEventRecord(c->ev[6], c->stream);
+    k_u<<<nblk(s.nrows), 256, 0, c->stream>>>((const double*)c->b_dedq.p, (const double*)c->b_molacc.p, (const double*)c->b_natom.p,
+                                              (const int32_t*)c->b_rowslot.p, s.nrows, s.maxnatom, c->hp.add_ecc, (float*)c->b_u.p);
+    c->launches++;
+    if ((rc = tm_launch_force(c, s, flags))) return rc;
+  } else {
+    cudaEventRecord(c->ev[6], c->stream);
+  }
+  cudaEventRecord(c->ev[7], c->stream);
+  return TM_OK;
+}
+
+// energies / per-atom outputs into the packed double buffer
+static int stage_pack(tm_ctx* c, const SysView& s, int flags, const OutLayout& o) {
+  int rc;
+  if ((rc = tm_buf(c, c->b_out, (size_t)o.total * 8))) return rc;
+  double* out = (double*)c->b_out.p;
+  TM_CUDA(cudaMemsetAsync(out + o.off_ebp_atom, 0, (size_t)o.nq * 8, c->stream));
+  k_ebp<<<(int)((s.nrows + 255) / 256), 256, 0, c->stream>>>((const float*)c->b_y[TM_NET_ENERGY].p, (const int32_t*)c->b_rowslot.p, s.nrows, s.maxnatom,
+                                                            out + o.off_ebp_atom, (double*)c->b_molacc.p);
+  k_pack<<<nblk(s.nmol), 256, 0, c->stream>>>((const double*)c->b_molacc.p, s.nmol, c->hp.add_ecc, out);
+  k_d2d<<<nblk(o.nq), 256, 0, c->stream>>>((const double*)c->b_q.p + o.nq, out + o.off_charge, o.nq);
+  c->launches += 3;
+  if (flags & TM_F_FORCE) {
+    k_f2d<<<nblk(3 * o.nq), 256, 0, c->stream>>>((const float*)c->b_F.p, out + o.off_grad, 3 * o.nq);
+    c->launches++;
+  }
+  TM_CUDA(cudaGetLastError());
+  return TM_OK;
+}
+
+static int finish_timings(tm_ctx* c, const SysView& s) {
+  tm_timings& t = c->last;
+  memset(&t, 0, sizeof(t));
+  auto el = [&](int a, int b) { float ms = 0.f; cudaEventElapsedTime(&ms, c->ev[a], c->ev[b]); return ms; };
+  t.h2d = el(0, 1); t.nlist = el(1, 2); t.desc = el(2, 3); t.mlp_fwd = el(3, 4); t.pair = el(4, 5); t.mlp_bwd = el(5, 6);
+  t.force = el(6, 7); t.d2h = el(7, 8); t.total = el(0, 8);
+  t.n_slots = s.nslots;
+  t.launches = c->launches;
+  return TM_OK;
+}
+
+static int check_flags(tm_ctx* c) {
+  int32_t f[2] = {0, 0};
+  TM_CUDA(cudaMemcpyAsync(f, c->b_flags.p, 8, cudaMemcpyDeviceToHost, c->stream));
+  TM_CUDA(cudaStreamSynchronize(c->stream));
+  if (f[0] & 2) { tm_set_error("neighbour table capacity exceeded (>256 radial neighbours per centre on average)"); return TM_ECAP; }
+  if (f[0] & 4) { tm_set_error("more than %d neighbours inside the angular cutoff of one centre", TM_ANG_CAP); return TM_ECAP; }
+  return TM_OK;
+}
+
+static int validate_Z(tm_ctx* c, const int32_t* Z, int64_t n) {
+  for (int64_t i = 0; i < n; i++) {
+    int z = Z[i];
+    if (z <= 0) continue;
+    bool ok = false;
+    for (int k = 0; k < c->desc.n_ele; k++) ok |= (c->desc.eles[k] == z);
+    if (!ok) { tm_set_error("atomic number %d (slot %lld) is not in the model's element list", z, (long long)i); return TM_EINVAL; }
+  }
+  return TM_OK;
+}
+
+// copy the packed device outputs to the user's arrays
+static int deliver(tm_ctx* c, const SysView& s, int flags, const OutLayout& o, tm_outputs* out, int64_t charge_tile_to) {
+  int rc;
+  size_t bytes = (size_t)o.total * 8;
+  size_t dbytes = (flags & TM_F_DESCRIPTORS) && out->descriptors ? (size_t)o.nq * c->hp.D * 4 : 0;
+  if ((rc = tm_host_stage(c, bytes + dbytes))) return rc;
+  TM_CUDA(cudaMemcpyAsync(c->h_stage, c->b_out.p, bytes, cudaMemcpyDeviceToHost, c->stream));
+  if (dbytes) {
+    if ((rc = tm_buf(c, c->b_acc, dbytes))) return rc;
+    k_desc_out<<<(unsigned)o.nq, 128, 0, c->stream>>>((const float*)c->b_G.p, (const int32_t*)c->b_rowofslot.p, o.nq, c->hp.D, c->hp.Dp, (float*)c->b_acc.p);
+    c->launches++;
+    TM_CUDA(cudaMemcpyAsync((char*)c->h_stage + bytes, c->b_acc.p, dbytes, cudaMemcpyDeviceToHost, c->stream));
+  }
+  cudaEventRecord(c->ev[8], c->stream);
+  if ((rc = check_flags(c))) return rc;   // synchronises
+  const double* h = (const double*)c->h_stage;
+  int64_t nm = o.nmol;
+  if (out->Etotal) memcpy(out->Etotal, h, nm * 8);
+  if (out->Ebp) memcpy(out->Ebp, h + nm, nm * 8);
+  if (out->Ecc) memcpy(out->Ecc, h + 2 * nm, nm * 8);
+  if (out->Evdw) memcpy(out->Evdw, h + 3 * nm, nm * 8);
+  if (out->dipole) memcpy(out->dipole, h + 4 * nm, 3 * nm * 8);
+  if (out->Ebp_atom) memcpy(out->Ebp_atom, h + o.off_ebp_atom, o.nq * 8);
+  if (out->charge) {
+    int64_t done = 0;
+    while (done < charge_tile_to) {   // periodic: tile q over the image blocks (TFMolInstanceDirect.py:5892-5893)
+      int64_t n = std::min(o.nq, charge_tile_to - done);
+      memcpy(out->charge + done, h + o.off_charge, n * 8);
+      done += n;
+    }
+  }
+  if (out->gradient && (flags & TM_F_FORCE)) memcpy(out->gradient, h + o.off_grad, 3 * o.nq * 8);
+  if (dbytes) memcpy(out->descriptors, (const char*)c->h_stage + bytes, dbytes);
+  return finish_timings(c, s);
+}
+
+static int upload_inv_n(tm_ctx* c, const double* inv_n, int64_t nmol) {
+  int rc;
+  if ((rc = tm_buf(c, c->b_natom, (size_t)nmol * 8))) return rc;
+  TM_CUDA(cudaMemcpyAsync(c->b_natom.p, inv_n, (size_t)nmol * 8, cudaMemcpyHostToDevice, c->stream));
+  return TM_OK;
+}
+
+static int run_all(tm_ctx* c, const SysView& s, int flags, const OutLayout& o) {
+  int rc;
+  if ((rc = stage_a(c, s))) return rc;
+  if ((rc = stage_b(c, s, flags))) return rc;
+  if ((rc = stage_c(c, s, flags))) return rc;
+  return stage_pack(c, s, flags, o);
+}
+
+extern "C" int tm_eval(tm_ctx* c, const double* xyzs, const int32_t* Zs, int64_t nmol, int64_t maxnatom, const int64_t* natom, int flags,
+                       tm_outputs* out) {
+  if (!c || !xyzs || !Zs || !natom || !out || nmol < 1 || maxnatom < 1) { tm_set_error("tm_eval: bad argument"); return TM_EINVAL; }
+  int rc;
+  TM_CUDA(cudaSetDevice(c->device));
+  if ((rc = check_weights(c))) return rc;
+  int64_t nslots = nmol * maxnatom;
+  if ((rc = validate_Z(c, Zs, nslots))) return rc;
+  c->launches = 0;
+  int64_t ncent = 0;
+  // staging: xyz | Z (masked by natom) | inv_n
+  size_t bx = (size_t)nslots * 24, bz = (size_t)nslots * 4, bn = (size_t)nmol * 8;
+  if ((rc = tm_host_stage(c, bx + bz + bn + 64))) return rc;
+  char* hs = (char*)c->h_stage;
+  memcpy(hs, xyzs, bx);
+  int32_t* hz = (int32_t*)(hs + bx);
+  double* hn = (double*)(hs + bx + bz);
+  for (int64_t m = 0; m < nmol; m++) {
+    if (natom[m] < 0 || natom[m] > maxnatom) { tm_set_error("natom[%lld] out of range", (long long)m); return TM_EINVAL; }
+    for (int64_t a = 0; a < maxnatom; a++) {
+      int32_t z = (a < natom[m]) ? Zs[m * maxnatom + a] : 0;
+      hz[m * maxnatom + a] = z;
+      if (z > 0) ncent++;
+    }
+    hn[m] = natom[m] > 0 ? 1.0 / (double)natom[m] : 0.0;
+  }
+  if ((rc = tm_buf(c, c->b_pos, bx))) return rc;
+  if ((rc = tm_buf(c, c->b_Z, bz))) return rc;
+  cudaEventRecord(c->ev[0], c->stream);
+  TM_CUDA(cudaMemcpyAsync(c->b_pos.p, hs, bx, cudaMemcpyHostToDevice, c->stream));
+  TM_CUDA(cudaMemcpyAsync(c->b_Z.p, hz, bz, cudaMemcpyHostToDevice, c->stream));
+  if ((rc = upload_inv_n(c, hn, nmol))) return rc;
+  SysView s = make_view(c, nslots, nmol, maxnatom, 0, 0, ncent);
+  OutLayout o = out_layout(nmol, nslots);
+  if ((rc = run_all(c, s, flags, o))) return rc;
+  rc = deliver(c, s, flags, o, out, nslots);
+  c->last.n_centres = ncent;
+  return rc;
+}
+
+extern "C" int tm_eval_images(tm_ctx* c, const double* xyz_tess, const int32_t* Z_tess, int64_t ntess_atoms, int64_t nreal, int flags,
+                              tm_outputs* out) {
+  if (!c || !xyz_tess || !Z_tess || !out || nreal < 1 || ntess_atoms < nreal) { tm_set_error("tm_eval_images: bad argument"); return TM_EINVAL; }
+  int rc;
+  TM_CUDA(cudaSetDevice(c->device));
+  if ((rc = check_weights(c))) return rc;
+  if ((rc = validate_Z(c, Z_tess, ntess_atoms))) return rc;
+  c->launches = 0;
+  size_t bx = (size_t)ntess_atoms * 24, bz = (size_t)ntess_atoms * 4;
+  if ((rc = tm_host_stage(c, bx + bz + 64))) return rc;
+  char* hs = (char*)c->h_stage;
+  memcpy(hs, xyz_tess, bx);
+  memcpy(hs + bx, Z_tess, bz);
+  double inv = 1.0 / (double)nreal;   // natom is fed as nreal (TFMolManage.py:1342)
+  memcpy(hs + bx + bz, &inv, 8);
+  if ((rc = tm_buf(c, c->b_pos, bx))) return rc;
+  if ((rc = tm_buf(c, c->b_Z, bz))) return rc;
+  cudaEventRecord(c->ev[0], c->stream);
+  TM_CUDA(cudaMemcpyAsync(c->b_pos.p, hs, bx, cudaMemcpyHostToDevice, c->stream));
+  TM_CUDA(cudaMemcpyAsync(c->b_Z.p, hs + bx, bz, cudaMemcpyHostToDevice, c->stream));
+  if ((rc = upload_inv_n(c, (const double*)(hs + bx + bz), 1))) return rc;
+  SysView s = make_view(c, ntess_atoms, 1, ntess_atoms, nreal, 1, nreal);
+  OutLayout o = out_layout(1, nreal);
+  if ((rc = run_all(c, s, flags, o))) return rc;
+  rc = deliver(c, s, flags, o, out, ntess_atoms);
+  c->last.n_centres = nreal;
+  return rc;
+}
+
+static int64_t tess_count(int64_t nreal, int ntess) {
+  int side = 2 * ntess + 1;
+  return (int64_t)side * side * side * nreal;
+}
+
+// device-side tessellation; xyz_dev / Z_dev are DEVICE pointers to the primitive cell
+static int prepare_lattice(tm_ctx* c, const double* xyz_dev, const int32_t* Z_dev, int64_t nreal, const double* lattice, int ntess, SysView* sv) {
+  int rc;
+  if (ntess < 1 || ntess > 8) { tm_set_error("ntess must be 1..8"); return TM_EINVAL; }
+  int64_t nslots = tess_count(nreal, ntess);
+  if ((rc = tm_buf(c, c->b_pos, (size_t)nslots * 24))) return rc;
+  if ((rc = tm_buf(c, c->b_Z, (size_t)nslots * 4))) return rc;
+  if ((rc = tm_buf(c, c->b_lattice, 16 * 8))) return rc;
+  double hl[10];
+  memcpy(hl, lattice, 72);
+  hl[9] = 1.0 / (double)nreal;
+  TM_CUDA(cudaMemcpyAsync(c->b_lattice.p, hl, 80, cudaMemcpyHostToDevice, c->stream));
+  if ((rc = tm_buf(c, c->b_natom, 8))) return rc;
+  TM_CUDA(cudaMemcpyAsync(c->b_natom.p, (const double*)c->b_lattice.p + 9, 8, cudaMemcpyDeviceToDevice, c->stream));
+  if ((rc = tm_launch_tessellate(c, xyz_dev, Z_dev, nreal, (const double*)c->b_lattice.p, ntess))) return rc;
+  *sv = make_view(c, nslots, 1, nslots, nreal, 1, nreal);
+  // inverse lattice first row (for slab ownership): frac_a = pos . g
+  const double* L = lattice;
+  double det = L[0] * (L[4] * L[8] - L[5] * L[7]) - L[1] * (L[3] * L[8] - L[5] * L[6]) + L[2] * (L[3] * L[7] - L[4] * L[6]);
+  if (fabs(det) < 1e-12) { tm_set_error("singular lattice"); return TM_EINVAL; }
+  sv->slab_g[0] = (L[4] * L[8] - L[5] * L[7]) / det;
+  sv->slab_g[1] = -(L[3] * L[8] - L[5] * L[6]) / det;   // g = first COLUMN of inv(L)  (x = f L  =>  f = x inv(L)), i.e. cofactors of row 0
+  sv->slab_g[2] = (L[3] * L[7] - L[4] * L[6]) / det;
+  return TM_OK;
+}
+
+extern "C" int tm_eval_lattice(tm_ctx* c, const double* xyz, const int32_t* Z, int64_t nreal, const double* lattice, int ntess, int flags,
+                               tm_outputs* out) {
+  if (!c || !xyz || !Z || !lattice || !out || nreal < 1) { tm_set_error("tm_eval_lattice: bad argument"); return TM_EINVAL; }
+  int rc;
+  TM_CUDA(cudaSetDevice(c->device));
+  if ((rc = check_weights(c))) return rc;
+  if ((rc = validate_Z(c, Z, nreal))) return rc;
+  c->launches = 0;
+  size_t bx = (size_t)nreal * 24, bz = (size_t)nreal * 4;
+  if ((rc = tm_host_stage(c, bx + bz + 64))) return rc;
+  char* hs = (char*)c->h_stage;
+  memcpy(hs, xyz, bx);
+  memcpy(hs + bx, Z, bz);
+  if ((rc = tm_buf(c, c->b_acc, bx + bz + 64))) return rc;
+  cudaEventRecord(c->ev[0], c->stream);
+  TM_CUDA(cudaMemcpyAsync(c->b_acc.p, hs, bx + bz, cudaMemcpyHostToDevice, c->stream));
+  SysView s;
+  if ((rc = prepare_lattice(c, (const double*)c->b_acc.p, (const int32_t*)((char*)c->b_acc.p + bx), nreal, lattice, ntess, &s))) return rc;
+  OutLayout o = out_layout(1, nreal);
+  if ((rc = run_all(c, s, flags, o))) return rc;
+  rc = deliver(c, s, flags, o, out, s.nslots);
+  c->last.n_centres = nreal;
+  return rc;
+}
+
+extern "C" int tm_eval_lattice_dev(tm_ctx* c, const double* xyz_dev, const int32_t* Z_dev, int64_t nreal, const double* lattice, int ntess,
+                                   int flags, double* e_dev, double* grad_dev, double* charge_dev) {
+  if (!c || !xyz_dev || !Z_dev || !lattice || nreal < 1) { tm_set_error("tm_eval_lattice_dev: bad argument"); return TM_EINVAL; }
+  int rc;
+  TM_CUDA(cudaSetDevice(c->device));
+  if ((rc = check_weights(c))) return rc;
+  c->launches = 0;
+  cudaEventRecord(c->ev[0], c->stream);
+  SysView s;
+  if ((rc = prepare_lattice(c, xyz_dev, Z_dev, nreal, lattice, ntess, &s))) return rc;
+  OutLayout o = out_layout(1, nreal);
+  if ((rc = run_all(c, s, flags, o))) return rc;
+  const double* out = (const double*)c->b_out.p;
+  if (e_dev) TM_CUDA(cudaMemcpyAsync(e_dev, out, 4 * 8, cudaMemcpyDeviceToDevice, c->stream));
+  if (grad_dev && (flags & TM_F_FORCE)) TM_CUDA(cudaMemcpyAsync(grad_dev, out + o.off_grad, (size_t)3 * nreal * 8, cudaMemcpyDeviceToDevice, c->stream));
+  if (charge_dev) TM_CUDA(cudaMemcpyAsync(charge_dev, out + o.off_charge, (size_t)nreal * 8, cudaMemcpyDeviceToDevice, c->stream));
+  cudaEventRecord(c->ev[8], c->stream);
+  c->cur_nslots = s.nslots;
+  return TM_OK;
+}
+
+extern "C" int tm_get_timings(tm_ctx* c, tm_timings* t) {
+  if (!c || !t) return TM_EINVAL;
+  TM_CUDA(cudaSetDevice(c->device));
+  TM_CUDA(cudaStreamSynchronize(c->stream));
+  SysView s;
+  memset(&s, 0, sizeof(s));
+  s.nslots = c->cur_nslots ? c->cur_nslots : c->last.n_slots;
+  int64_t nc = c->last.n_centres;
+  finish_timings(c, s);
+  c->last.n_centres = nc;
+  *t = c->last;
+  return TM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ slab-partitioned phases
+// One process per GPU; every rank holds all positions, evaluates the centres of its own slab, and the
+// host (tensormol_b200/parallel.py, torch.distributed/NCCL) performs the three small all-reduces
+// between the phases.  See include/tmolb200.h.
+__global__ void k_owned_qraw(const float* __restrict__ y, const int32_t* __restrict__ rowslot, int64_t nrows, double* __restrict__ q) {
+  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < nrows; r += (int64_t)gridDim.x * blockDim.x) {
+    int s = rowslot[r];
+    if (s >= 0) q[s] = (double)y[r];
+  }
+}
+__global__ void k_slab_e(const double* __restrict__ molacc, double* __restrict__ e, int add_ecc) {
+  e[0] = 0.0;
+  e[1] = molacc[1];
+  e[2] = add_ecc ? molacc[2] : 0.0;
+  e[3] = molacc[3];
+  e[4] = molacc[5];
+  e[5] = 0.0;
+}
+__global__ void k_slab_set_dedq(double* __restrict__ molacc, const double* __restrict__ e) { molacc[5] = e[4]; }
+
+extern "C" int tm_slab_phase_a(tm_ctx* c, const double* xyz_dev, const int32_t* Z_dev, int64_t nreal, const double* lattice, int ntess,
+                               int rank, int world, double* qraw_dev) {
+  if (!c || !xyz_dev || !Z_dev || !lattice || !qraw_dev || world < 1 || rank < 0 || rank >= world) { tm_set_error("tm_slab_phase_a: bad argument"); return TM_EINVAL; }
+  int rc;
+  TM_CUDA(cudaSetDevice(c->device));
+  if ((rc = check_weights(c))) return rc;
+  c->launches = 0;
+  cudaEventRecord(c->ev[0], c->stream);
+  SysView s;
+  if ((rc = prepare_lattice(c, xyz_dev, Z_dev, nreal, lattice, ntess, &s))) return rc;
+  s.slab_rank = rank; s.slab_world = world;
+  // a slab holds ~nreal/world centres; keep head-room for density fluctuations without a host round trip
+  if (world > 1) {
+    s.ncent_max = std::min<int64_t>(nreal, nreal / world + nreal / (2 * world) + 4096);
+    s.nrows = s.ncent_max + (int64_t)TM_ROW_TILE * c->hp.n_ele;
+  }
+  c->slab_view = s;
+  if ((rc = stage_a(c, s))) return rc;
+  if ((rc = tm_launch_mlp_backward(c, s))) return rc;
+  cudaEventRecord(c->ev[6], c->stream);
+  TM_CUDA(cudaMemsetAsync(qraw_dev, 0, (size_t)nreal * 8, c->stream));
+  k_owned_qraw<<<nblk(s.nrows), 256, 0, c->stream>>>((const float*)c->b_y[TM_NET_CHARGE].p, (const int32_t*)c->b_rowslot.p, s.nrows, qraw_dev);
+  c->launches++;
+  TM_CUDA(cudaGetLastError());
+  return TM_OK;
+}
+
+extern "C" int tm_slab_phase_b(tm_ctx* c, const double* qraw_dev, double* e_dev) {
+  if (!c || !qraw_dev || !e_dev) { tm_set_error("tm_slab_phase_b: bad argument"); return TM_EINVAL; }
+  int rc;
+  TM_CUDA(cudaSetDevice(c->device));
+  SysView s = c->slab_view;
+  int64_t nq = s.nreal;
+  if ((rc = tm_buf(c, c->b_q, (size_t)nq * 8 * 2))) return rc;
+  TM_CUDA(cudaMemcpyAsync(c->b_q.p, qraw_dev, (size_t)nq * 8, cudaMemcpyDeviceToDevice, c->stream));
+  SysView s2 = s;
+  s2.slab_world = 2;   // any value > 1: tm_launch_charges then takes qraw from b_q instead of scattering its own rows
+  if ((rc = tm_launch_charges(c, s2))) return rc;
+  if ((rc = tm_launch_pair(c, s, TM_F_FORCE | TM_F_VDW))) return rc;
+  k_ebp<<<(int)((s.nrows + 255) / 256), 256, 0, c->stream>>>((const float*)c->b_y[TM_NET_ENERGY].p, (const int32_t*)c->b_rowslot.p, s.nrows, s.maxnatom,
+                                                            nullptr, (double*)c->b_molacc.p);
+  k_slab_e<<<1, 1, 0, c->stream>>>((const double*)c->b_molacc.p, e_dev, c->hp.add_ecc);
+  c->launches += 2;
+  cudaEventRecord(c->ev[5], c->stream);
+  TM_CUDA(cudaGetLastError());
+  return TM_OK;
+}
+
+extern "C" int tm_slab_phase_c(tm_ctx* c, const double* e_dev, int flags, double* grad_dev) {
+  if (!c || !e_dev || !grad_dev) { tm_set_error("tm_slab_phase_c: bad argument"); return TM_EINVAL; }
+  int rc;
+  TM_CUDA(cudaSetDevice(c->device));
+  SysView s = c->slab_view;
+  k_slab_set_dedq<<<1, 1, 0, c->stream>>>((double*)c->b_molacc.p, e_dev);
+  k_u<<<nblk(s.nrows), 256, 0, c->stream>>>((const double*)c->b_dedq.p, (const double*)c->b_molacc.p, (const double*)c->b_natom.p,
+                                            (const int32_t*)c->b_rowslot.p, s.nrows, s.maxnatom, c->hp.add_ecc, (float*)c->b_u.p);
+  c->launches += 2;
+  if ((rc = tm_launch_force(c, s, flags))) return rc;
+  k_f2d<<<nblk(3 * s.nreal), 256, 0, c->stream>>>((const float*)c->b_F.p, grad_dev, 3 * s.nreal);
+  c->launches++;
+  cudaEventRecord(c->ev[7], c->stream);
+  cudaEventRecord(c->ev[8], c->stream);
+  c->cur_nslots = s.nslots;
+  TM_CUDA(cudaGetLastError());
+  return TM_OK;
+}

@@ -1,0 +1,213 @@
+// K2+K3: ANI-1 radial and angular symmetry functions with element / element-pair channels.
+//
+// Computes what TFSymRSet_Linear_WithEle (RawSymFunc.py:1696-1755, Periodic :1812-1863) and
+// TFSymASet_Linear_WithEle (RawSymFunc.py:868-962, Periodic :1054-1136) compute, concatenated as
+// TFSymSet_Scattered_Linear_WithEle does (RawSymFunc.py:2248): row layout
+//   [ radial: e*nRs_r + s | angular: n_ele*nRs_r + p*(nAs*nRs_a) + a*nRs_a + s ]   (theta-major).
+// Reference quirks kept: truncated pi in the cutoff (Q3), no fc(r_jk), each unordered {j,k} once,
+// prefactor 2^(1-zeta) (Q4).  cos(theta-theta_a) is expanded as cos t cos ta + sin t sin ta with
+// sin t = |a x b|/(|a||b|), which removes acos and is well conditioned near collinear triples; the
+// reference's clamp to +-(1-1e-16) (Q5) changes the value by < 2e-8 and is below fp32 resolution.
+//
+// Mapping: one warp per centre row (rows are element-sorted, so the output is the contiguous
+// per-element MLP batch).  Neighbour records (32 B) are fetched coalesced from the cell-sorted
+// copy; position differences are formed in float64 and rounded once to fp32.
+//   radial : lane = Rs channel, neighbours broadcast by warp shuffle, register accumulators per element
+//   angular: phase 1 lanes = triples (geometry, 8 angular and 8 radial factors into shared tiles),
+//            phase 2 lanes = output channels (rank-1 update of the 64-wide block of the pair channel).
+#include "tm_internal.h"
+
+#define FULL 0xffffffffu
+#define DESC_WARPS 8
+#define RPL 2   // radial channels per lane (num_r_Rs <= 64)
+#define OPL 8   // angular outputs per lane (nAs*nRs_a <= 256)
+
+__device__ __forceinline__ void tri_inv(int t, int& j, int& k) {
+  // t = k(k-1)/2 + j with 0 <= j < k
+  k = (int)((1.0f + sqrtf(1.0f + 8.0f * (float)t)) * 0.5f);
+  while (k * (k - 1) / 2 > t) k--;
+  while ((k + 1) * k / 2 <= t) k++;
+  j = t - k * (k - 1) / 2;
+}
+
+__device__ __forceinline__ float pow_zeta(float b, const DevParams& P) {
+  if (P.zeta_is8) {
+    float b2 = b * b, b4 = b2 * b2;
+    return b4 * b4;
+  }
+  return powf(b, P.zeta);
+}
+
+size_t tm_desc_smem_floats_per_warp(const DevParams& P) {
+  return 5 * TM_ANG_CAP + TM_ANG_CAP + 32 * (P.nAs + 1) + 32 * (P.nRs_a + 1) + 32 + (size_t)P.n_elep * P.nsym;
+}
+
+__global__ void __launch_bounds__(DESC_WARPS * 32)
+k_desc(const SAtom* __restrict__ sat, const int32_t* __restrict__ rowsidx, const int32_t* __restrict__ rowslot,
+       const int32_t* __restrict__ nboff, const uint32_t* __restrict__ nbr, int64_t nrows, const __grid_constant__ DevParams P,
+       float* __restrict__ G, int32_t* __restrict__ flags, int wfloats) {
+  extern __shared__ float smem[];
+  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int64_t row = (int64_t)blockIdx.x * DESC_WARPS + warp;
+  if (row >= nrows) return;
+  float* Grow = G + row * P.Dp;
+  int slot = rowslot[row];
+  if (slot < 0) {
+    for (int i = lane; i < P.Dp; i += 32) Grow[i] = 0.f;
+    return;
+  }
+  float* ws = smem + (size_t)warp * wfloats;
+  float* ax = ws;
+  float* ay = ax + TM_ANG_CAP;
+  float* az = ay + TM_ANG_CAP;
+  float* ar = az + TM_ANG_CAP;
+  float* afc = ar + TM_ANG_CAP;
+  int* ae = (int*)(afc + TM_ANG_CAP);
+  float* Tt = (float*)(ae + TM_ANG_CAP);
+  const int tstr = P.nAs + 1, estr = P.nRs_a + 1;
+  float* Et = Tt + 32 * tstr;
+  int* chan = (int*)(Et + 32 * estr);
+  float* Gs = (float*)(chan + 32);
+  const int nang_out = P.n_elep * P.nsym;
+  for (int i = lane; i < nang_out; i += 32) Gs[i] = 0.f;
+
+  SAtom ci = sat[rowsidx[row]];
+  int b = nboff[row], e = nboff[row + 1];
+  float acc[RPL][TM_MAX_ELE];
+  float rs[RPL];
+#pragma unroll
+  for (int k = 0; k < RPL; k++) {
+    rs[k] = (lane + 32 * k < P.nRs_r) ? P.Rs_r[lane + 32 * k] : 0.f;
+#pragma unroll
+    for (int q = 0; q < TM_MAX_ELE; q++) acc[k][q] = 0.f;
+  }
+  int nang = 0;
+  for (int j0 = b; j0 < e; j0 += 32) {
+    int j = j0 + lane;
+    float dx = 0.f, dy = 0.f, dz = 0.f, r = 1.f, fc = 0.f;
+    int ej = 0;
+    bool isang = false;
+    if (j < e) {
+      uint32_t en = nbr[j];
+      isang = (en >> 31) != 0;
+      SAtom a = sat[en & 0x7fffffffu];
+      dx = (float)(a.x - ci.x);
+      dy = (float)(a.y - ci.y);
+      dz = (float)(a.z - ci.z);
+      r = sqrtf(dx * dx + dy * dy + dz * dz);
+      ej = a.e;
+      fc = 0.5f * (cosf(P.pi_over_rRc * r) + 1.0f);
+    }
+    unsigned mk = __ballot_sync(FULL, isang);
+    if (isang) {
+      int pos = nang + __popc(mk & ((1u << lane) - 1));
+      if (pos < TM_ANG_CAP) {
+        ax[pos] = dx; ay[pos] = dy; az[pos] = dz; ar[pos] = r;
+        afc[pos] = 0.5f * (cosf(P.pi_over_aRc * r) + 1.0f);
+        ae[pos] = ej;
+      } else {
+        atomicOr(flags, 4);
+      }
+    }
+    nang += __popc(mk);
+    int cnt = min(32, e - j0);
+    for (int t = 0; t < cnt; t++) {
+      float rr = __shfl_sync(FULL, r, t), ff = __shfl_sync(FULL, fc, t);
+      int ee = __shfl_sync(FULL, ej, t);
+#pragma unroll
+      for (int k = 0; k < RPL; k++) {
+        if (k == 0 || P.nRs_r > 32) {
+          float d = rr - rs[k];
+          float v = expf(-P.eta * d * d) * ff;
+#pragma unroll
+          for (int q = 0; q < TM_MAX_ELE; q++) acc[k][q] += (ee == q) ? v : 0.f;
+        }
+      }
+    }
+  }
+  nang = min(nang, TM_ANG_CAP);
+  __syncwarp();
+
+  // per-lane output coordinates for phase 2
+  int oa[OPL], os[OPL];
+#pragma unroll
+  for (int k = 0; k < OPL; k++) {
+    int idx = lane + 32 * k;
+    oa[k] = idx / P.nRs_a;
+    os[k] = idx - oa[k] * P.nRs_a;
+  }
+  int ntrip = nang * (nang - 1) / 2;
+  for (int t0 = 0; t0 < ntrip; t0 += 32) {
+    int t = t0 + lane;
+    if (t < ntrip) {
+      int j, k;
+      tri_inv(t, j, k);
+      float ajx = ax[j], ajy = ay[j], ajz = az[j], akx = ax[k], aky = ay[k], akz = az[k];
+      float ra = ar[j], rb = ar[k];
+      float inv = 1.0f / (ra * rb);
+      float c = (ajx * akx + ajy * aky + ajz * akz) * inv;
+      float nx = ajy * akz - ajz * aky, ny = ajz * akx - ajx * akz, nz = ajx * aky - ajy * akx;
+      float s = sqrtf(nx * nx + ny * ny + nz * nz) * inv;
+      c = fminf(1.0f, fmaxf(-1.0f, c));
+      float f = afc[j] * afc[k];
+      float rho = 0.5f * (ra + rb);
+      for (int a = 0; a < P.nAs; a++) {
+        float base = fmaxf(1.0f + c * P.cosA[a] + s * P.sinA[a], 0.f);
+        Tt[lane * tstr + a] = P.zeta_pref * pow_zeta(base, P);
+      }
+      for (int q = 0; q < P.nRs_a; q++) {
+        float d = rho - P.Rs_a[q];
+        Et[lane * estr + q] = expf(-P.eta * d * d) * f;
+      }
+      chan[lane] = P.pair_index[ae[j]][ae[k]];
+    }
+    __syncwarp();
+    int cnt = min(32, ntrip - t0);
+    for (int tt = 0; tt < cnt; tt++) {
+      int p = chan[tt];
+      const float* Tr = Tt + tt * tstr;
+      const float* Er = Et + tt * estr;
+      float* Gp = Gs + p * P.nsym;
+#pragma unroll
+      for (int k = 0; k < OPL; k++) {
+        int idx = lane + 32 * k;
+        if (idx < P.nsym) Gp[idx] += Tr[oa[k]] * Er[os[k]];
+      }
+    }
+    __syncwarp();
+  }
+
+  // write the row: radial block, angular block, zero padding
+#pragma unroll
+  for (int k = 0; k < RPL; k++) {
+    int s = lane + 32 * k;
+    if (s < P.nRs_r) {
+#pragma unroll
+      for (int q = 0; q < TM_MAX_ELE; q++)
+        if (q < P.n_ele) Grow[q * P.nRs_r + s] = acc[k][q];
+    }
+  }
+  int off = P.n_ele * P.nRs_r;
+  for (int i = lane; i < nang_out; i += 32) Grow[off + i] = Gs[i];
+  for (int i = P.D + lane; i < P.Dp; i += 32) Grow[i] = 0.f;
+}
+
+int tm_launch_desc(tm_ctx* c, const SysView& s) {
+  int rc;
+  const DevParams& P = c->hp;
+  if ((rc = tm_buf(c, c->b_G, (size_t)s.nrows * P.Dp * 4))) return rc;
+  size_t wf = tm_desc_smem_floats_per_warp(P);
+  size_t smem = wf * 4 * DESC_WARPS;
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    TM_CUDA(cudaFuncSetAttribute(k_desc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  int blocks = (int)((s.nrows + DESC_WARPS - 1) / DESC_WARPS);
+  k_desc<<<blocks, DESC_WARPS * 32, smem, c->stream>>>((const SAtom*)c->b_satom.p, (const int32_t*)c->b_rowsidx.p, (const int32_t*)c->b_rowslot.p,
+                                                      (const int32_t*)c->b_nboff.p, (const uint32_t*)c->b_nbr.p, s.nrows, P, (float*)c->b_G.p,
+                                                      (int32_t*)c->b_flags.p, (int)wf);
+  c->launches++;
+  TM_CUDA(cudaGetLastError());
+  return TM_OK;
+}

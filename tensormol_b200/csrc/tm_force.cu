@@ -1,0 +1,271 @@
+// K6: fused descriptor-gradient + force scatter-add.  Replaces the part of
+// tf.gradients(Etotal, xyzs) (TFMolInstanceDirect.py:5761 / 5999) that flows through the symmetry
+// functions: given A[row, :] = dE/dG_row (energy net) + u_row * dq_raw/dG_row (charge net, u_row =
+// dE/dq_raw,row), accumulate  dE/dx_i, dE/dx_j, dE/dx_k  for every pair and triple of every centre.
+//
+// Reference gradient convention: every row of the (real+image) coordinate array is an
+// independent variable and only rows < nreal are returned (TFMolManage.py:1353), so contributions
+// addressed to image rows are DROPPED (unless TM_F_FOLD_IMAGES asks to fold them onto slot % nreal).
+//
+// Mapping: one warp per centre row; A row staged in shared memory with (n+1)-padded channel strides.
+//   radial : lanes = neighbours, each lane loops the nRs_r Gaussians of its pair
+//   angular: lanes = triples, each lane contracts the 64-wide channel block of its triple in registers
+// Neighbour forces of the angular part are combined in a per-warp shared tile (shared atomics) and
+// flushed with one global atomic per neighbour component.
+#include "tm_internal.h"
+
+#define FULL 0xffffffffu
+#define FORCE_WARPS 8
+
+__device__ __forceinline__ void tri_inv_f(int t, int& j, int& k) {
+  k = (int)((1.0f + sqrtf(1.0f + 8.0f * (float)t)) * 0.5f);
+  while (k * (k - 1) / 2 > t) k--;
+  while ((k + 1) * k / 2 <= t) k++;
+  j = t - k * (k - 1) / 2;
+}
+
+size_t tm_force_smem_floats_per_warp(const DevParams& P) {
+  return (size_t)P.n_ele * (P.nRs_r + 1) + (size_t)P.n_elep * (P.nsym + 1) + 5 * TM_ANG_CAP + 2 * TM_ANG_CAP + 3 * TM_ANG_CAP;
+}
+
+template <int NAS_MAX, int NRS_MAX>
+__global__ void __launch_bounds__(FORCE_WARPS * 32)
+k_force(const SAtom* __restrict__ sat, const int32_t* __restrict__ rowsidx, const int32_t* __restrict__ rowslot,
+        const int32_t* __restrict__ nboff, const uint32_t* __restrict__ nbr, int64_t nrows, const __grid_constant__ DevParams P,
+        const float* __restrict__ dGe, const float* __restrict__ dGq, const float* __restrict__ u, int64_t nreal_slots, int fold,
+        float* __restrict__ F, int wfloats) {
+  extern __shared__ float smem[];
+  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int64_t row = (int64_t)blockIdx.x * FORCE_WARPS + warp;
+  if (row >= nrows) return;
+  int slot = rowslot[row];
+  if (slot < 0) return;
+  float* ws = smem + (size_t)warp * wfloats;
+  const int rstr = P.nRs_r + 1, astr = P.nsym + 1;
+  float* Ar = ws;                                // [n_ele][nRs_r+1]
+  float* Aa = Ar + P.n_ele * rstr;               // [n_elep][nsym+1]
+  float* ax = Aa + P.n_elep * astr;
+  float* ay = ax + TM_ANG_CAP;
+  float* az = ay + TM_ANG_CAP;
+  float* ar = az + TM_ANG_CAP;
+  float* afc = ar + TM_ANG_CAP;
+  int* ae = (int*)(afc + TM_ANG_CAP);
+  int* aslot = ae + TM_ANG_CAP;                  // destination slot for the force, -1 = dropped
+  float* Ft = (float*)(aslot + TM_ANG_CAP);      // [ANG_CAP][3]
+
+  // stage A = dGe + u*dGq
+  {
+    const float* ge = dGe + row * P.Dp;
+    const float* gq = dGq + row * P.Dp;
+    float uu = u[row];
+    int nrad = P.n_ele * P.nRs_r;
+    for (int i = lane; i < nrad; i += 32) {
+      int q = i / P.nRs_r, s = i - q * P.nRs_r;
+      Ar[q * rstr + s] = ge[i] + uu * gq[i];
+    }
+    int na = P.n_elep * P.nsym;
+    for (int i = lane; i < na; i += 32) {
+      int p = i / P.nsym, s = i - p * P.nsym;
+      Aa[p * astr + s] = ge[nrad + i] + uu * gq[nrad + i];
+    }
+    for (int i = lane; i < 3 * TM_ANG_CAP; i += 32) Ft[i] = 0.f;
+  }
+  __syncwarp();
+
+  SAtom ci = sat[rowsidx[row]];
+  int b = nboff[row], e = nboff[row + 1];
+  float gix = 0.f, giy = 0.f, giz = 0.f;   // dE/dx_i accumulated by this lane
+  int nang = 0;
+  for (int j0 = b; j0 < e; j0 += 32) {
+    int j = j0 + lane;
+    bool isang = false;
+    float dx = 0.f, dy = 0.f, dz = 0.f, r = 1.f;
+    int ej = 0, dst = -1;
+    if (j < e) {
+      uint32_t en = nbr[j];
+      isang = (en >> 31) != 0;
+      SAtom a = sat[en & 0x7fffffffu];
+      dx = (float)(a.x - ci.x);
+      dy = (float)(a.y - ci.y);
+      dz = (float)(a.z - ci.z);
+      r = sqrtf(dx * dx + dy * dy + dz * dz);
+      ej = a.e;
+      dst = (a.slot < nreal_slots) ? a.slot : (fold ? (int)(a.slot % nreal_slots) : -1);
+      // radial: dE/dr = sum_s A[e_j][s] * d/dr [ exp(-eta (r-Rs)^2) fc(r) ]
+      float arg = P.pi_over_rRc * r;
+      float sn, cs;
+      sincosf(arg, &sn, &cs);
+      float fc = 0.5f * (cs + 1.0f);
+      float dfc = -0.5f * sn * P.pi_over_rRc;
+      const float* Arow = Ar + ej * rstr;
+      float dEdr = 0.f;
+      for (int s = 0; s < P.nRs_r; s++) {
+        float d = r - P.Rs_r[s];
+        float g = expf(-P.eta * d * d);
+        dEdr += Arow[s] * g * (dfc - 2.0f * P.eta * d * fc);
+      }
+      float sc = dEdr / r;
+      float gx = sc * dx, gy = sc * dy, gz = sc * dz;   // dE/dx_j  (d = x_j - x_i)
+      gix -= gx; giy -= gy; giz -= gz;
+      if (dst >= 0) {
+        atomicAdd(F + 3 * (int64_t)dst, gx);
+        atomicAdd(F + 3 * (int64_t)dst + 1, gy);
+        atomicAdd(F + 3 * (int64_t)dst + 2, gz);
+      }
+    }
+    unsigned mk = __ballot_sync(FULL, isang);
+    if (isang) {
+      int pos = nang + __popc(mk & ((1u << lane) - 1));
+      if (pos < TM_ANG_CAP) {
+        ax[pos] = dx; ay[pos] = dy; az[pos] = dz; ar[pos] = r;
+        afc[pos] = P.pi_over_aRc * r;   // the angle; fc and fc' are formed per triple
+        ae[pos] = ej;
+        aslot[pos] = dst;
+      }
+    }
+    nang += __popc(mk);
+  }
+  nang = min(nang, TM_ANG_CAP);
+  __syncwarp();
+
+  int ntrip = nang * (nang - 1) / 2;
+  for (int t0 = 0; t0 < ntrip; t0 += 32) {
+    int t = t0 + lane;
+    if (t < ntrip) {
+      int j, k;
+      tri_inv_f(t, j, k);
+      float ajx = ax[j], ajy = ay[j], ajz = az[j], akx = ax[k], aky = ay[k], akz = az[k];
+      float ra = ar[j], rb = ar[k];
+      float ira = 1.0f / ra, irb = 1.0f / rb;
+      // unit vectors
+      float uax = ajx * ira, uay = ajy * ira, uaz = ajz * ira;
+      float ubx = akx * irb, uby = aky * irb, ubz = akz * irb;
+      float c = uax * ubx + uay * uby + uaz * ubz;
+      float nx = uay * ubz - uaz * uby, ny = uaz * ubx - uax * ubz, nz = uax * uby - uay * ubx;
+      float s = sqrtf(nx * nx + ny * ny + nz * nz);
+      c = fminf(1.0f, fmaxf(-1.0f, c));
+      float sj, cj, sk, ck;
+      sincosf(afc[j], &sj, &cj);
+      sincosf(afc[k], &sk, &ck);
+      float fa = 0.5f * (cj + 1.0f), fb = 0.5f * (ck + 1.0f);
+      float dfa = -0.5f * sj * P.pi_over_aRc, dfb = -0.5f * sk * P.pi_over_aRc;
+      float rho = 0.5f * (ra + rb);
+      float E[NRS_MAX], dE[NRS_MAX];
+#pragma unroll
+      for (int q = 0; q < NRS_MAX; q++) {
+        if (q < P.nRs_a) {
+          float d = rho - P.Rs_a[q];
+          float g = expf(-P.eta * d * d);
+          E[q] = g;
+          dE[q] = -2.0f * P.eta * d * g;
+        } else {
+          E[q] = 0.f; dE[q] = 0.f;
+        }
+      }
+      int p = P.pair_index[ae[j]][ae[k]];
+      const float* Ap = Aa + p * astr;
+      float W = 0.f, Wt = 0.f, Wr = 0.f;
+#pragma unroll
+      for (int a = 0; a < NAS_MAX; a++) {
+        if (a < P.nAs) {
+          float ca = P.cosA[a], sa = P.sinA[a];
+          float base = fmaxf(1.0f + c * ca + s * sa, 0.f);
+          float T, dT;   // T = pref*base^zeta ; dT = dT/dtheta = -zeta*pref*base^(zeta-1) * sin(theta-theta_a)
+          float sind = s * ca - c * sa;
+          if (P.zeta_is8) {
+            float b2 = base * base, b4 = b2 * b2;
+            float b7 = b4 * b2 * base;
+            T = P.zeta_pref * b7 * base;
+            dT = -8.0f * P.zeta_pref * b7 * sind;
+          } else {
+            float bm = powf(base, P.zeta - 1.0f);
+            T = P.zeta_pref * bm * base;
+            dT = -P.zeta * P.zeta_pref * bm * sind;
+          }
+          float ua = 0.f, va = 0.f;
+#pragma unroll
+          for (int q = 0; q < NRS_MAX; q++) {
+            if (q < P.nRs_a) {
+              float Aas = Ap[a * P.nRs_a + q];
+              ua += Aas * E[q];
+              va += Aas * dE[q];
+            }
+          }
+          W += T * ua;
+          Wt += dT * ua;
+          Wr += T * va;
+        }
+      }
+      // V = W fa fb ; gradients w.r.t. a = x_j - x_i and b = x_k - x_i
+      float ff = fa * fb;
+      float dVdt = Wt * ff;
+      float dVda_r = 0.5f * Wr * ff + W * dfa * fb;   // along a_hat
+      float dVdb_r = 0.5f * Wr * ff + W * fa * dfb;   // along b_hat
+      float is = (s > 1e-6f) ? 1.0f / s : 0.f;
+      // dtheta/da = -(b_hat - c a_hat)/(|a| s) ; dtheta/db = -(a_hat - c b_hat)/(|b| s)
+      float ta = -dVdt * is * ira, tb = -dVdt * is * irb;
+      float gax = ta * (ubx - c * uax) + dVda_r * uax;
+      float gay = ta * (uby - c * uay) + dVda_r * uay;
+      float gaz = ta * (ubz - c * uaz) + dVda_r * uaz;
+      float gbx = tb * (uax - c * ubx) + dVdb_r * ubx;
+      float gby = tb * (uay - c * uby) + dVdb_r * uby;
+      float gbz = tb * (uaz - c * ubz) + dVdb_r * ubz;
+      gix -= gax + gbx; giy -= gay + gby; giz -= gaz + gbz;
+      atomicAdd(&Ft[3 * j], gax); atomicAdd(&Ft[3 * j + 1], gay); atomicAdd(&Ft[3 * j + 2], gaz);
+      atomicAdd(&Ft[3 * k], gbx); atomicAdd(&Ft[3 * k + 1], gby); atomicAdd(&Ft[3 * k + 2], gbz);
+    }
+  }
+  __syncwarp();
+  for (int i = lane; i < nang; i += 32) {
+    int dst = aslot[i];
+    if (dst >= 0) {
+      atomicAdd(F + 3 * (int64_t)dst, Ft[3 * i]);
+      atomicAdd(F + 3 * (int64_t)dst + 1, Ft[3 * i + 1]);
+      atomicAdd(F + 3 * (int64_t)dst + 2, Ft[3 * i + 2]);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    gix += __shfl_xor_sync(FULL, gix, o);
+    giy += __shfl_xor_sync(FULL, giy, o);
+    giz += __shfl_xor_sync(FULL, giz, o);
+  }
+  if (lane == 0) {
+    atomicAdd(F + 3 * (int64_t)slot, gix);
+    atomicAdd(F + 3 * (int64_t)slot + 1, giy);
+    atomicAdd(F + 3 * (int64_t)slot + 2, giz);
+  }
+}
+
+int tm_launch_force(tm_ctx* c, const SysView& s, int flags) {
+  const DevParams& P = c->hp;
+  size_t wf = tm_force_smem_floats_per_warp(P);
+  size_t smem = wf * 4 * FORCE_WARPS;
+  int64_t nreal_slots = s.periodic ? s.nreal : s.nslots;
+  int fold = (flags & TM_F_FOLD_IMAGES) ? 1 : 0;
+  int blocks = (int)((s.nrows + FORCE_WARPS - 1) / FORCE_WARPS);
+  bool small = (P.nAs <= 8 && P.nRs_a <= 8);
+  static size_t conf_small = 0, conf_big = 0;
+  if (small) {
+    if (smem > 48 * 1024 && smem > conf_small) {
+      TM_CUDA(cudaFuncSetAttribute(k_force<8, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      conf_small = smem;
+    }
+    k_force<8, 8><<<blocks, FORCE_WARPS * 32, smem, c->stream>>>(
+        (const SAtom*)c->b_satom.p, (const int32_t*)c->b_rowsidx.p, (const int32_t*)c->b_rowslot.p, (const int32_t*)c->b_nboff.p,
+        (const uint32_t*)c->b_nbr.p, s.nrows, P, (const float*)c->b_dG[TM_NET_ENERGY].p, (const float*)c->b_dG[TM_NET_CHARGE].p,
+        (const float*)c->b_u.p, nreal_slots, fold, (float*)c->b_F.p, (int)wf);
+  } else {
+    if (smem > 48 * 1024 && smem > conf_big) {
+      TM_CUDA(cudaFuncSetAttribute(k_force<TM_MAX_SYM, TM_MAX_SYM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      conf_big = smem;
+    }
+    k_force<TM_MAX_SYM, TM_MAX_SYM><<<blocks, FORCE_WARPS * 32, smem, c->stream>>>(
+        (const SAtom*)c->b_satom.p, (const int32_t*)c->b_rowsidx.p, (const int32_t*)c->b_rowslot.p, (const int32_t*)c->b_nboff.p,
+        (const uint32_t*)c->b_nbr.p, s.nrows, P, (const float*)c->b_dG[TM_NET_ENERGY].p, (const float*)c->b_dG[TM_NET_CHARGE].p,
+        (const float*)c->b_u.p, nreal_slots, fold, (float*)c->b_F.p, (int)wf);
+  }
+  c->launches++;
+  TM_CUDA(cudaGetLastError());
+  return TM_OK;
+}

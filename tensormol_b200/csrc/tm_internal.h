@@ -1,0 +1,177 @@
+// Internal declarations shared by the translation units of libtmolb200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include "../../include/tmolb200.h"
+
+#define TM_ROW_TILE 128          // GEMM row tile; element row groups are padded to this
+#define TM_ANG_CAP 64            // angular neighbours per centre held in shared memory
+#define TM_MAX_ELEP (TM_MAX_ELE * (TM_MAX_ELE + 1) / 2)
+#define TM_MAX_SYM 16            // max num_a_As / num_a_Rs
+#define TM_BOHRPERA 1.889725989  // PhysicalData.py:30
+
+void tm_set_error(const char* fmt, ...);
+#define TM_CUDA(call)                                                                         \
+  do {                                                                                        \
+    cudaError_t _e = (call);                                                                  \
+    if (_e != cudaSuccess) {                                                                  \
+      tm_set_error("%s:%d CUDA error %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(_e)); \
+      return TM_ECUDA;                                                                        \
+    }                                                                                         \
+  } while (0)
+
+// One atom of the cell-sorted copy: 32 bytes so a lane fetches it with two 128-bit loads.
+struct __align__(32) SAtom {
+  double x, y, z;
+  int32_t slot;   // original slot index (mol*maxnatom + a, or image slot)
+  int32_t e;      // element index into eles, -1 never stored
+};
+
+// Grid geometry, produced ON THE DEVICE from the bounding box (no host round trip).
+struct GridParams {
+  double ox, oy, oz;   // origin
+  double inv_cell;     // 1/cell edge
+  double cell;
+  int gx, gy, gz;      // cells per molecule box
+  int ncell_mol;       // gx*gy*gz
+  int ncells;          // nmol*ncell_mol
+};
+
+// Constant hyper-parameters as the kernels consume them (fp32 + a few f64).
+struct DevParams {
+  int n_ele, n_elep;
+  int eles[TM_MAX_ELE];
+  int nRs_r, nRs_a, nAs, nsym;    // nsym = nAs*nRs_a
+  int D, Dp;                      // descriptor width and padded width (multiple of 32)
+  float r_Rc, a_Rc, eta, zeta;
+  float pi_over_rRc, pi_over_aRc; // 3.14159265359/Rc  (truncated pi, RawSymFunc.py:935,1738)
+  float zeta_pref;                // 2^(1-zeta)
+  int zeta_is8;
+  float Rs_r[64];
+  float Rs_a[TM_MAX_SYM];
+  float cosA[TM_MAX_SYM], sinA[TM_MAX_SYM];
+  int8_t pair_index[TM_MAX_ELE][TM_MAX_ELE];
+  // electrostatics, all in Bohr
+  float R_lr, R_sr, alpha_b;      // EECutoffOff*B, Elu_Width*B, DSFAlpha/B
+  float Zc, ZoverR_plus_Y;        // erfc(a R_lr)/R_lr ; Zc/R_lr + Yc
+  float elu_a, elu_shift;
+  float poly_width_b;             // Poly_Width*B
+  float sqrtC6[TM_MAX_ELE], Rvdw[TM_MAX_ELE];
+  int add_ecc;
+  int activation;
+  float act_alpha;
+  double rr_exact, ra_exact;      // exact f64 cutoffs for the reference accept test
+};
+
+struct Layer {
+  int K, N, Kp, Np;      // logical and padded dims
+  float* W = nullptr;    // [Kp][Np] row-major fp32 (zero padded)
+  float* WT = nullptr;   // [Np][Kp] (for the backward-data GEMM)
+  float* b = nullptr;    // [Np]
+};
+
+struct Net {
+  Layer layers[TM_MAX_HIDDEN];   // hidden layers
+  float* w_out = nullptr;        // [Hp_last]
+  float b_out = 0.f;
+  bool set[TM_MAX_HIDDEN + 1] = {false, false, false, false, false};
+};
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+};
+
+// Per-evaluation view passed to the launchers.
+struct SysView {
+  int64_t nslots;       // total slots (real + padding or images)
+  int64_t nmol;
+  int64_t maxnatom;     // slots per molecule
+  int64_t nreal;        // periodic-images mode: centres are slots < nreal; else 0
+  int periodic;         // 1 = images mode
+  int64_t ncent_max;    // host upper bound on centre count
+  int64_t nrows;        // ncent_max + TM_ROW_TILE*n_ele (allocated rows)
+  int64_t ncells_cap;
+  // slab ownership filter on centres (fraction of x-range), world==1 -> everything
+  int slab_rank, slab_world;
+  double slab_g[3];     // first row of the inverse lattice: frac = pos . slab_g
+};
+
+struct tm_ctx {
+  int device = 0;
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t stream = nullptr;
+  tm_model_desc desc;
+  tm_params params;
+  DevParams hp;                  // host copy
+  DevParams* dp = nullptr;       // device copy
+  Net nets[2][TM_MAX_ELE];
+  int gemm_mode = TM_GEMM_FP32;
+  int Hp[TM_MAX_HIDDEN];         // padded hidden widths
+  int Hmax = 0;
+
+  // ---- per-evaluation workspace (grow-only) ----
+  DevBuf b_pos, b_Z, b_cellid, b_rank, b_count, b_cstart, b_sorted, b_satom, b_scan_tmp;
+  DevBuf b_rowslot, b_rowsidx, b_rowofslot, b_blkcnt, b_rowmeta;
+  DevBuf b_nbcnt, b_nboff, b_nbr, b_G, b_act[2][TM_MAX_HIDDEN], b_delta0, b_delta1, b_dG[2], b_y[2];
+  DevBuf b_q, b_qs, b_dedq, b_u, b_F, b_Fpair, b_acc, b_bbox, b_grid, b_flags, b_out, b_molacc;
+  DevBuf b_natom, b_lattice;
+  // host staging (pinned)
+  void* h_stage = nullptr;
+  size_t h_cap = 0;
+  // results of compat calls (library-owned host memory)
+  std::vector<int64_t> h_off, h_idx, h_rad, h_ang, h_milj, h_miljk;
+
+  cudaEvent_t ev[12];
+  bool ev_ok = false;
+  tm_timings last;
+  int launches = 0;
+
+  // slab state
+  int slab_rank = 0, slab_world = 1;
+  int64_t cur_nslots = 0, cur_nreal = 0, cur_nmol = 0, cur_maxnatom = 0, cur_ncent = 0, cur_nrows = 0;
+  int cur_periodic = 0;
+  SysView slab_view;
+  int slab_flags = 0;
+};
+
+#ifdef __CUDACC__
+__device__ __forceinline__ int cell_coord(double v, double o, double inv, int g) {
+  int c = (int)floor((v - o) * inv);
+  return c < 0 ? 0 : (c >= g ? g - 1 : c);
+}
+#endif
+
+int tm_buf(tm_ctx* c, DevBuf& b, size_t bytes);
+int tm_host_stage(tm_ctx* c, size_t bytes);
+
+// ---- launchers (each returns TM_OK / error) ----
+int tm_launch_tessellate(tm_ctx* c, const double* xyz_real, const int32_t* Z_real, int64_t nreal, const double* lattice9_dev, int ntess);
+int tm_launch_nlist_build(tm_ctx* c, const SysView& s, double rc_grid);
+int tm_launch_rows(tm_ctx* c, const SysView& s);
+int tm_launch_neighbours(tm_ctx* c, const SysView& s);
+int tm_launch_desc(tm_ctx* c, const SysView& s);
+int tm_launch_mlp_forward(tm_ctx* c, const SysView& s);
+int tm_launch_mlp_backward(tm_ctx* c, const SysView& s);
+int tm_launch_charges(tm_ctx* c, const SysView& s);
+int tm_launch_pair(tm_ctx* c, const SysView& s, int flags);
+int tm_launch_force(tm_ctx* c, const SysView& s, int flags);
+int tm_launch_finalize(tm_ctx* c, const SysView& s, int flags);
+
+// generic CSR neighbour list for the MolEmb-compatible API
+int tm_launch_nlist_csr(tm_ctx* c, const SysView& s, double rc, int do_perms, int64_t* total_out);
+
+// GEMM back-ends (tm_gemm.cu): C[g] = act(A[g] * B[g] + bias) or the backward variant, grouped over row tiles
+struct GemmGroup {
+  const float* A;      // [rows][lda]
+  const float* B;      // [K][ldb]  (K-major rows)
+  const float* bias;   // [N] or nullptr
+  const float* Hmul;   // backward: multiply result by act'(h) computed from Hmul [rows][ldc], or nullptr
+  float* C;            // [rows][ldc]
+  int lda, ldb, ldc, K, N;
+  int ele;             // element whose row range this group covers
+};
+int tm_launch_gemm(tm_ctx* c, const GemmGroup* groups, int ngroups, const int* rowmeta_dev, int max_row_tiles, int epilogue);
+enum { TM_EPI_ACT = 0, TM_EPI_DACT = 1, TM_EPI_NONE = 2 };

@@ -1,0 +1,303 @@
+// K4: per-element Behler-Parrinello MLPs (charge net + energy net) as grouped GEMMs over the
+// element-sorted row batches, forward and backward-data.
+//
+// Restates energy_inference / dipole_inference (TFMolInstanceDirect.py:5164-5285; periodic
+// :5774-5898): per element  D -> H1 -> ... -> Hn -> 1, y = a(xW+b), last layer linear, activation
+// sigmoid_with_param = log(1+exp(alpha x))/alpha (Util.py:200-201) evaluated as a stable softplus.
+// The backward pass replaces tf.gradients through the nets: delta_L = w_out * a'(h_L),
+// delta_{l-1} = (delta_l W_l^T) * a'(h_{l-1}), dy/dG = delta_0 W_0^T, with a' recovered from the stored
+// activation (softplus: a'(z) = 1 - exp(-alpha h)).
+//
+// A "group" is one (net, element): rows [rowmeta[2e], +rowmeta[2e+1]) of the row space (padded to
+// TM_ROW_TILE), so tiles never straddle elements and row counts stay on the device.
+#include "tm_internal.h"
+
+#define FULL 0xffffffffu
+
+struct GemmGroupTbl {
+  GemmGroup g[2 * TM_MAX_ELE];
+};
+
+__device__ __forceinline__ float act_fwd(float z, int kind, float alpha) {
+  switch (kind) {
+    case TM_ACT_SIGMOID_WITH_PARAM: {
+      float t = alpha * z;
+      return (fmaxf(t, 0.f) + log1pf(expf(-fabsf(t)))) / alpha;
+    }
+    case TM_ACT_RELU: return fmaxf(z, 0.f);
+    case TM_ACT_SOFTPLUS: return fmaxf(z, 0.f) + log1pf(expf(-fabsf(z)));
+    case TM_ACT_TANH: return tanhf(z);
+    default: return 1.0f / (1.0f + expf(-z));
+  }
+}
+// derivative a'(z) expressed through the stored activation h = a(z)
+__device__ __forceinline__ float act_bwd_from_h(float h, int kind, float alpha) {
+  switch (kind) {
+    case TM_ACT_SIGMOID_WITH_PARAM: return -expm1f(-alpha * h);
+    case TM_ACT_RELU: return h > 0.f ? 1.f : 0.f;
+    case TM_ACT_SOFTPLUS: return -expm1f(-h);
+    case TM_ACT_TANH: return 1.0f - h * h;
+    default: return h * (1.0f - h);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// fp32 FFMA GEMM: 128x128x16 tiles, 256 threads, 8x8 register tile per thread, register-staged
+// double buffering.  C = epi(A[rows,K] * B[K,N]).  K % 16 == 0, N % 128 == 0, rows padded to 128.
+// ------------------------------------------------------------------------------------------------
+#define BM 128
+#define BN 128
+#define BK 16
+#define APAD 4
+
+__global__ void __launch_bounds__(256)
+k_gemm_simt(const __grid_constant__ GemmGroupTbl tbl, const int32_t* __restrict__ rowmeta, int epilogue, int act_kind, float act_alpha) {
+  const GemmGroup& G = tbl.g[blockIdx.z];
+  int rows_e = rowmeta[2 * G.ele + 1];
+  int rt = blockIdx.x;
+  if (rt * BM >= rows_e) return;
+  int nt = blockIdx.y;
+  if (nt * BN >= G.N) return;
+  int64_t row0 = (int64_t)rowmeta[2 * G.ele] + (int64_t)rt * BM;
+  const float* A = G.A + row0 * G.lda;
+  const float* B = G.B + nt * BN;
+  __shared__ __align__(16) float As[2][BK][BM + APAD];
+  __shared__ __align__(16) float Bs[2][BK][BN];
+  int tid = threadIdx.x;
+  int tx = tid & 15, ty = tid >> 4;
+  // global->register staging coordinates
+  int a_r = tid >> 2, a_k = (tid & 3) * 4;   // rows a_r and a_r+64, 4 consecutive k
+  int b_k = tid >> 5, b_n = (tid & 31) * 4;  // k rows b_k and b_k+8, 4 consecutive n
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; i++)
+#pragma unroll
+    for (int j = 0; j < 8; j++) acc[i][j] = 0.f;
+  float4 ra0, ra1, rb0, rb1;
+  int nk = G.K / BK;
+  auto gload = [&](int kt) {
+    const float* Ap = A + (int64_t)a_r * G.lda + kt * BK + a_k;
+    ra0 = *reinterpret_cast<const float4*>(Ap);
+    ra1 = *reinterpret_cast<const float4*>(Ap + (int64_t)64 * G.lda);
+    const float* Bp = B + (int64_t)(kt * BK + b_k) * G.ldb + b_n;
+    rb0 = *reinterpret_cast<const float4*>(Bp);
+    rb1 = *reinterpret_cast<const float4*>(Bp + (int64_t)8 * G.ldb);
+  };
+  auto sstore = [&](int buf) {
+    As[buf][a_k + 0][a_r] = ra0.x; As[buf][a_k + 1][a_r] = ra0.y; As[buf][a_k + 2][a_r] = ra0.z; As[buf][a_k + 3][a_r] = ra0.w;
+    As[buf][a_k + 0][a_r + 64] = ra1.x; As[buf][a_k + 1][a_r + 64] = ra1.y; As[buf][a_k + 2][a_r + 64] = ra1.z; As[buf][a_k + 3][a_r + 64] = ra1.w;
+    *reinterpret_cast<float4*>(&Bs[buf][b_k][b_n]) = rb0;
+    *reinterpret_cast<float4*>(&Bs[buf][b_k + 8][b_n]) = rb1;
+  };
+  gload(0);
+  sstore(0);
+  __syncthreads();
+  for (int kt = 0; kt < nk; kt++) {
+    int buf = kt & 1;
+    if (kt + 1 < nk) gload(kt + 1);
+#pragma unroll
+    for (int k = 0; k < BK; k++) {
+      float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
+      float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][64 + ty * 4]);
+      float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
+      float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][k][64 + tx * 4]);
+      float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int i = 0; i < 8; i++)
+#pragma unroll
+        for (int j = 0; j < 8; j++) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    if (kt + 1 < nk) {
+      sstore(buf ^ 1);
+      __syncthreads();
+    }
+  }
+  // epilogue
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    int r = (i < 4) ? (ty * 4 + i) : (64 + ty * 4 + i - 4);
+    int64_t grow = row0 + r;
+#pragma unroll
+    for (int half = 0; half < 2; half++) {
+      int cn = nt * BN + half * 64 + tx * 4;
+      float v[4] = {acc[i][half * 4 + 0], acc[i][half * 4 + 1], acc[i][half * 4 + 2], acc[i][half * 4 + 3]};
+      if (epilogue == TM_EPI_ACT) {
+        float4 bb = *reinterpret_cast<const float4*>(G.bias + cn);
+        v[0] = act_fwd(v[0] + bb.x, act_kind, act_alpha);
+        v[1] = act_fwd(v[1] + bb.y, act_kind, act_alpha);
+        v[2] = act_fwd(v[2] + bb.z, act_kind, act_alpha);
+        v[3] = act_fwd(v[3] + bb.w, act_kind, act_alpha);
+      } else if (epilogue == TM_EPI_DACT) {
+        float4 hh = *reinterpret_cast<const float4*>(G.Hmul + grow * G.ldc + cn);
+        v[0] *= act_bwd_from_h(hh.x, act_kind, act_alpha);
+        v[1] *= act_bwd_from_h(hh.y, act_kind, act_alpha);
+        v[2] *= act_bwd_from_h(hh.z, act_kind, act_alpha);
+        v[3] *= act_bwd_from_h(hh.w, act_kind, act_alpha);
+      }
+      *reinterpret_cast<float4*>(G.C + grow * G.ldc + cn) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+  }
+}
+
+int tm_gemm_tc_launch(tm_ctx* c, const GemmGroup* groups, int ngroups, const int* rowmeta_dev, int max_row_tiles, int epilogue);
+
+int tm_launch_gemm(tm_ctx* c, const GemmGroup* groups, int ngroups, const int* rowmeta_dev, int max_row_tiles, int epilogue) {
+  if (c->gemm_mode != TM_GEMM_FP32) return tm_gemm_tc_launch(c, groups, ngroups, rowmeta_dev, max_row_tiles, epilogue);
+  GemmGroupTbl tbl;
+  int maxN = 0;
+  for (int i = 0; i < ngroups; i++) {
+    tbl.g[i] = groups[i];
+    if (groups[i].N > maxN) maxN = groups[i].N;
+    if (groups[i].K % BK || groups[i].N % BN) {
+      tm_set_error("gemm dims not padded: K=%d N=%d", groups[i].K, groups[i].N);
+      return TM_EINVAL;
+    }
+  }
+  dim3 grid((unsigned)max_row_tiles, (unsigned)(maxN / BN), (unsigned)ngroups);
+  k_gemm_simt<<<grid, 256, 0, c->stream>>>(tbl, rowmeta_dev, epilogue, c->hp.activation, c->hp.act_alpha);
+  c->launches++;
+  TM_CUDA(cudaGetLastError());
+  return TM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// output layer (H_last -> 1) and its backward seed
+// ------------------------------------------------------------------------------------------------
+struct OutTbl {
+  const float* w[2][TM_MAX_ELE];
+  float b[2][TM_MAX_ELE];
+  const float* h[2];   // last hidden activation [nrows][ld]
+  float* y[2];         // [nrows]
+  float* delta[2];     // [nrows][ld]
+  int ld, H;
+};
+
+__device__ __forceinline__ int row_element(const int32_t* rowmeta, int64_t row, int n_ele) {
+  for (int e = 0; e < n_ele; e++) {
+    int b = rowmeta[2 * e], n = rowmeta[2 * e + 1];
+    if (row >= b && row < b + n) return e;
+  }
+  return -1;
+}
+
+// one warp per (row, net): y = h . w + b ; delta = w * a'(h)
+__global__ void k_out_layer(const __grid_constant__ OutTbl T, const int32_t* __restrict__ rowmeta, int64_t nrows, int n_ele, int act_kind,
+                            float act_alpha, int want_delta) {
+  int64_t wid = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  int net = (int)(wid & 1);
+  int64_t row = wid >> 1;
+  if (row >= nrows) return;
+  int e = row_element(rowmeta, row, n_ele);
+  if (e < 0) { if (lane == 0) T.y[net][row] = 0.f; return; }
+  const float* h = T.h[net] + row * T.ld;
+  const float* w = T.w[net][e];
+  float* d = T.delta[net] + row * T.ld;
+  float s = 0.f;
+  for (int i = lane * 4; i < T.ld; i += 128) {
+    float4 hv = *reinterpret_cast<const float4*>(h + i);
+    float4 wv = *reinterpret_cast<const float4*>(w + i);
+    s += hv.x * wv.x + hv.y * wv.y + hv.z * wv.z + hv.w * wv.w;
+    if (want_delta) {
+      float4 dv = make_float4(wv.x * act_bwd_from_h(hv.x, act_kind, act_alpha), wv.y * act_bwd_from_h(hv.y, act_kind, act_alpha),
+                              wv.z * act_bwd_from_h(hv.z, act_kind, act_alpha), wv.w * act_bwd_from_h(hv.w, act_kind, act_alpha));
+      *reinterpret_cast<float4*>(d + i) = dv;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
+  if (lane == 0) T.y[net][row] = s + T.b[net][e];
+}
+
+static int ensure_mlp_bufs(tm_ctx* c, const SysView& s) {
+  int rc;
+  int nh = c->desc.n_hidden;
+  for (int net = 0; net < 2; net++) {
+    for (int l = 0; l < nh; l++)
+      if ((rc = tm_buf(c, c->b_act[net][l], (size_t)s.nrows * c->Hp[l] * 4))) return rc;
+    if ((rc = tm_buf(c, c->b_y[net], (size_t)s.nrows * 4))) return rc;
+    if ((rc = tm_buf(c, c->b_dG[net], (size_t)s.nrows * c->hp.Dp * 4))) return rc;
+  }
+  if ((rc = tm_buf(c, c->b_delta0, (size_t)2 * s.nrows * c->Hmax * 4))) return rc;
+  if ((rc = tm_buf(c, c->b_delta1, (size_t)2 * s.nrows * c->Hmax * 4))) return rc;
+  return TM_OK;
+}
+
+int tm_launch_mlp_forward(tm_ctx* c, const SysView& s) {
+  int rc;
+  if ((rc = ensure_mlp_bufs(c, s))) return rc;
+  int nh = c->desc.n_hidden, ne = c->hp.n_ele;
+  int max_tiles = (int)((s.ncent_max + TM_ROW_TILE - 1) / TM_ROW_TILE);
+  if (max_tiles < 1) max_tiles = 1;
+  const int* rowmeta = (const int*)c->b_rowmeta.p;
+  for (int l = 0; l < nh; l++) {
+    GemmGroup gg[2 * TM_MAX_ELE];
+    int ng = 0;
+    for (int net = 0; net < 2; net++)
+      for (int e = 0; e < ne; e++) {
+        const Layer& L = c->nets[net][e].layers[l];
+        GemmGroup& g = gg[ng++];
+        g.A = (l == 0) ? (const float*)c->b_G.p : (const float*)c->b_act[net][l - 1].p;
+        g.lda = (l == 0) ? c->hp.Dp : c->Hp[l - 1];
+        g.B = L.W; g.ldb = L.Np; g.bias = L.b; g.Hmul = nullptr;
+        g.C = (float*)c->b_act[net][l].p; g.ldc = L.Np;
+        g.K = L.Kp; g.N = L.Np; g.ele = e;
+      }
+    if ((rc = tm_launch_gemm(c, gg, ng, rowmeta, max_tiles, TM_EPI_ACT))) return rc;
+  }
+  OutTbl T;
+  for (int net = 0; net < 2; net++) {
+    for (int e = 0; e < TM_MAX_ELE; e++) {
+      T.w[net][e] = (e < ne) ? c->nets[net][e].w_out : nullptr;
+      T.b[net][e] = (e < ne) ? c->nets[net][e].b_out : 0.f;
+    }
+    T.h[net] = (const float*)c->b_act[net][nh - 1].p;
+    T.y[net] = (float*)c->b_y[net].p;
+    T.delta[net] = (float*)((nh % 2) ? c->b_delta0.p : c->b_delta1.p) + (size_t)net * s.nrows * c->Hmax;
+  }
+  T.ld = c->Hp[nh - 1];
+  T.H = c->desc.hidden[nh - 1];
+  int64_t nw = s.nrows * 2;
+  int blocks = (int)((nw * 32 + 255) / 256);
+  k_out_layer<<<blocks, 256, 0, c->stream>>>(T, (const int32_t*)c->b_rowmeta.p, s.nrows, ne, c->hp.activation, c->hp.act_alpha, 1);
+  c->launches++;
+  TM_CUDA(cudaGetLastError());
+  return TM_OK;
+}
+
+// delta buffers ping-pong: delta for hidden layer l lives in (l odd ? delta1 : delta0) ... chosen so that
+// the seed written by k_out_layer (layer nh-1) is in buffer ((nh-1) & 1).
+int tm_launch_mlp_backward(tm_ctx* c, const SysView& s) {
+  int rc;
+  int nh = c->desc.n_hidden, ne = c->hp.n_ele;
+  int max_tiles = (int)((s.ncent_max + TM_ROW_TILE - 1) / TM_ROW_TILE);
+  if (max_tiles < 1) max_tiles = 1;
+  const int* rowmeta = (const int*)c->b_rowmeta.p;
+  auto dbuf = [&](int l, int net) -> float* {
+    // layer l's delta buffer; must match the seed placement in tm_launch_mlp_forward
+    void* base = (((nh - 1 - l) % 2) == 0) ? ((nh % 2) ? c->b_delta0.p : c->b_delta1.p) : ((nh % 2) ? c->b_delta1.p : c->b_delta0.p);
+    return (float*)base + (size_t)net * s.nrows * c->Hmax;
+  };
+  for (int l = nh - 1; l >= 0; l--) {
+    GemmGroup gg[2 * TM_MAX_ELE];
+    int ng = 0;
+    for (int net = 0; net < 2; net++)
+      for (int e = 0; e < ne; e++) {
+        const Layer& L = c->nets[net][e].layers[l];
+        GemmGroup& g = gg[ng++];
+        g.A = dbuf(l, net); g.lda = c->Hp[l];
+        g.B = L.WT; g.ldb = L.Kp; g.bias = nullptr;
+        g.K = L.Np; g.N = L.Kp; g.ele = e;
+        if (l > 0) {
+          g.Hmul = (const float*)c->b_act[net][l - 1].p;
+          g.C = dbuf(l - 1, net); g.ldc = c->Hp[l - 1];
+        } else {
+          g.Hmul = nullptr;
+          g.C = (float*)c->b_dG[net].p; g.ldc = c->hp.Dp;
+        }
+      }
+    if ((rc = tm_launch_gemm(c, gg, ng, rowmeta, max_tiles, l > 0 ? TM_EPI_DACT : TM_EPI_NONE))) return rc;
+  }
+  return TM_OK;
+}

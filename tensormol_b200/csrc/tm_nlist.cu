@@ -1,0 +1,615 @@
+// K1: sorted cell-list build + neighbour enumeration with warp-ballot compaction (sm_100a).
+//
+// Replaces MolEmb.Make_NListNaive (C_API/MolEmb.cpp:1180-1247: x-sorted sweep on the host)
+// and the Python pair loops of NeighborList.buildPairs (Neighbors.py:75-115).  The accept test
+// is the reference's, bit for bit:  sqrt(dx*dx+dy*dy+dz*dz) + 1e-13 < rc  in float64 with one
+// rounding per operation (no FMA contraction), MolEmb.cpp:1213-1218.
+//
+// Pipeline (all sizes bounded on the host, all geometry decided on the device):
+//   bbox -> grid params -> per-slot cell id + rank (atomic) -> exclusive scan of cell counts
+//   -> scatter -> per-cell sort by slot (determinism) + gather SAtom copy
+//   -> centre rows sorted by (element, cell order) -> neighbour count -> scan -> fill.
+#include "tm_internal.h"
+#include <cstdio>
+
+#define FULL 0xffffffffu
+
+// ---------------------------------------------------------------- ordered double <-> u64
+__device__ __forceinline__ unsigned long long enc_d(double v) {
+  unsigned long long b = (unsigned long long)__double_as_longlong(v);
+  return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double dec_d(unsigned long long b) {
+  b = (b & 0x8000000000000000ull) ? (b & 0x7fffffffffffffffull) : ~b;
+  return __longlong_as_double((long long)b);
+}
+
+// ---------------------------------------------------------------- tessellation (Periodic.py:131-168)
+// slot = b*nreal + a ; block 0 = real atoms, then images for i,j,k in [-ntess..ntess]^3 skipping (0,0,0).
+// coords_ + i*L0 + j*L1 + k*L2 is evaluated left to right with separate roundings like numpy does.
+__global__ void k_tessellate(const double* __restrict__ xyz, const int32_t* __restrict__ Z, int64_t nreal,
+                             const double* __restrict__ lat, int ntess, double* __restrict__ pos, int32_t* __restrict__ Zo) {
+  int side = 2 * ntess + 1;
+  int64_t nimg = (int64_t)side * side * side;
+  int64_t total = nimg * nreal;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    int64_t b = t / nreal, a = t - b * nreal;
+    double x = xyz[3 * a], y = xyz[3 * a + 1], z = xyz[3 * a + 2];
+    if (b > 0) {
+      // block index b>0 enumerates (i,j,k) in loop order with the centre cell skipped
+      int64_t centre = ((int64_t)ntess * side + ntess) * side + ntess;
+      int64_t lin = (b - 1 < centre) ? (b - 1) : b;
+      int k = (int)(lin % side) - ntess;
+      int j = (int)((lin / side) % side) - ntess;
+      int i = (int)(lin / ((int64_t)side * side)) - ntess;
+      double di = (double)i, dj = (double)j, dk = (double)k;
+      x = __dadd_rn(__dadd_rn(__dadd_rn(x, __dmul_rn(di, lat[0])), __dmul_rn(dj, lat[3])), __dmul_rn(dk, lat[6]));
+      y = __dadd_rn(__dadd_rn(__dadd_rn(y, __dmul_rn(di, lat[1])), __dmul_rn(dj, lat[4])), __dmul_rn(dk, lat[7]));
+      z = __dadd_rn(__dadd_rn(__dadd_rn(z, __dmul_rn(di, lat[2])), __dmul_rn(dj, lat[5])), __dmul_rn(dk, lat[8]));
+    }
+    pos[3 * t] = x;
+    pos[3 * t + 1] = y;
+    pos[3 * t + 2] = z;
+    Zo[t] = Z[a];
+  }
+}
+
+int tm_launch_tessellate(tm_ctx* c, const double* xyz_real, const int32_t* Z_real, int64_t nreal, const double* lat_dev, int ntess) {
+  int side = 2 * ntess + 1;
+  int64_t total = (int64_t)side * side * side * nreal;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  k_tessellate<<<blocks, 256, 0, c->stream>>>(xyz_real, Z_real, nreal, lat_dev, ntess, (double*)c->b_pos.p, (int32_t*)c->b_Z.p);
+  c->launches++;
+  TM_CUDA(cudaGetLastError());
+  return TM_OK;
+}
+
+// ---------------------------------------------------------------- bbox
+__global__ void k_bbox_init(unsigned long long* bb) {
+  if (threadIdx.x < 3) bb[threadIdx.x] = 0xffffffffffffffffull;   // mins
+  else if (threadIdx.x < 6) bb[threadIdx.x] = 0ull;               // maxs
+}
+
+__global__ void k_bbox(const double* __restrict__ pos, const int32_t* __restrict__ Z, int64_t n, unsigned long long* bb) {
+  double mn[3] = {1e300, 1e300, 1e300}, mx[3] = {-1e300, -1e300, -1e300};
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+    if (Z[t] <= 0) continue;
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+      double v = pos[3 * t + d];
+      mn[d] = fmin(mn[d], v);
+      mx[d] = fmax(mx[d], v);
+    }
+  }
+#pragma unroll
+  for (int d = 0; d < 3; d++) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      mn[d] = fmin(mn[d], __shfl_xor_sync(FULL, mn[d], o));
+      mx[d] = fmax(mx[d], __shfl_xor_sync(FULL, mx[d], o));
+    }
+  }
+  if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+      if (mn[d] < 1e299) atomicMin(&bb[d], enc_d(mn[d]));
+      if (mx[d] > -1e299) atomicMax(&bb[3 + d], enc_d(mx[d]));
+    }
+  }
+}
+
+// one thread: grid geometry from the bbox; grows the cell edge until nmol*gx*gy*gz fits the cap
+__global__ void k_grid_params(const unsigned long long* bb, double rc, int64_t nmol, int64_t ncells_cap, GridParams* g) {
+  double mn[3], mx[3];
+  for (int d = 0; d < 3; d++) {
+    mn[d] = dec_d(bb[d]);
+    mx[d] = dec_d(bb[3 + d]);
+    if (!(mx[d] >= mn[d])) { mn[d] = 0.0; mx[d] = 0.0; }   // empty input
+  }
+  double cell = rc * (1.0 + 1e-6);
+  int gx, gy, gz;
+  for (int it = 0; it < 200; it++) {
+    gx = (int)floor((mx[0] - mn[0]) / cell) + 1;
+    gy = (int)floor((mx[1] - mn[1]) / cell) + 1;
+    gz = (int)floor((mx[2] - mn[2]) / cell) + 1;
+    double tot = (double)gx * gy * gz * (double)nmol;
+    if (tot <= (double)ncells_cap) break;
+    cell *= 1.2599210498948732;
+  }
+  g->ox = mn[0]; g->oy = mn[1]; g->oz = mn[2];
+  g->cell = cell;
+  g->inv_cell = 1.0 / cell;
+  g->gx = gx; g->gy = gy; g->gz = gz;
+  g->ncell_mol = gx * gy * gz;
+  g->ncells = (int)(nmol * (int64_t)(gx * gy * gz));
+}
+
+
+// per slot: cell id and arrival rank inside the cell
+__global__ void k_cell_count(const double* __restrict__ pos, const int32_t* __restrict__ Z, int64_t n, int64_t maxnatom,
+                             const GridParams* __restrict__ gp, int32_t* __restrict__ cellid, int32_t* __restrict__ rank,
+                             int32_t* __restrict__ count) {
+  GridParams g = *gp;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+    if (Z[t] <= 0) { cellid[t] = -1; rank[t] = -1; continue; }   // rank[] is reused as sidx_of_slot (-1 = absent)
+    int cx = cell_coord(pos[3 * t], g.ox, g.inv_cell, g.gx);
+    int cy = cell_coord(pos[3 * t + 1], g.oy, g.inv_cell, g.gy);
+    int cz = cell_coord(pos[3 * t + 2], g.oz, g.inv_cell, g.gz);
+    int m = (int)(t / maxnatom);
+    int cid = m * g.ncell_mol + (cx * g.gy + cy) * g.gz + cz;   // z fastest: a +-1 z-run is contiguous
+    cellid[t] = cid;
+    rank[t] = atomicAdd(&count[cid], 1);
+  }
+}
+
+// ---------------------------------------------------------------- exclusive scan (3 kernels, int32)
+#define SCAN_TILE 2048   // elements per block (256 threads x 8)
+__global__ void k_scan_local(const int32_t* __restrict__ in, int32_t* __restrict__ out, int32_t* __restrict__ blksum, int64_t n) {
+  __shared__ int32_t wsum[8];
+  int64_t base = (int64_t)blockIdx.x * SCAN_TILE + threadIdx.x * 8;
+  int32_t v[8], s = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    v[i] = (base + i < n) ? in[base + i] : 0;
+    s += v[i];
+  }
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int32_t inc = s;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int32_t t = __shfl_up_sync(FULL, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) wsum[w] = inc;
+  __syncthreads();
+  int32_t woff = 0;
+  for (int i = 0; i < w; i++) woff += wsum[i];
+  int32_t run = woff + inc - s;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    if (base + i < n) out[base + i] = run;
+    run += v[i];
+  }
+  if (threadIdx.x == 255) blksum[blockIdx.x] = woff + inc;
+}
+// single block: exclusive scan of block sums (nblk <= 1<<20), also writes the grand total at [nblk]
+__global__ void k_scan_blocks(int32_t* blksum, int nblk) {
+  __shared__ int32_t wsum[32];
+  __shared__ int32_t carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int base = 0; base < nblk; base += 1024) {
+    int i = base + threadIdx.x;
+    int32_t v = (i < nblk) ? blksum[i] : 0;
+    int32_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int32_t t = __shfl_up_sync(FULL, inc, o);
+      if (lane >= o) inc += t;
+    }
+    if (lane == 31) wsum[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+      int32_t x = wsum[lane], xi = x;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        int32_t t = __shfl_up_sync(FULL, xi, o);
+        if (lane >= o) xi += t;
+      }
+      wsum[lane] = xi - x;   // exclusive warp offsets
+    }
+    __syncthreads();
+    int32_t excl = carry + wsum[w] + inc - v;
+    if (i < nblk) blksum[i] = excl;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry = excl + v;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) blksum[nblk] = carry;
+}
+__global__ void k_scan_add(int32_t* __restrict__ out, const int32_t* __restrict__ blksum, int64_t n, int nblk) {
+  int64_t base = (int64_t)blockIdx.x * SCAN_TILE + threadIdx.x * 8;
+  int32_t off = blksum[blockIdx.x];
+#pragma unroll
+  for (int i = 0; i < 8; i++)
+    if (base + i < n) out[base + i] += off;
+  if (blockIdx.x == 0 && threadIdx.x == 0) out[n] = blksum[nblk];   // total at out[n]
+}
+
+// exclusive scan of in[0..n) into out[0..n], out[n] = total.  tmp needs (nblk+1) ints.
+static int scan_exclusive(tm_ctx* c, const int32_t* in, int32_t* out, int64_t n, int32_t* tmp) {
+  int nblk = (int)((n + SCAN_TILE - 1) / SCAN_TILE);
+  if (nblk < 1) nblk = 1;
+  k_scan_local<<<nblk, 256, 0, c->stream>>>(in, out, tmp, n);
+  k_scan_blocks<<<1, 1024, 0, c->stream>>>(tmp, nblk);
+  k_scan_add<<<nblk, 256, 0, c->stream>>>(out, tmp, n, nblk);
+  c->launches += 3;
+  TM_CUDA(cudaGetLastError());
+  return TM_OK;
+}
+
+__global__ void k_scatter(const int32_t* __restrict__ cellid, const int32_t* __restrict__ rank, const int32_t* __restrict__ cstart,
+                          int64_t n, int32_t* __restrict__ sorted) {
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+    int cid = cellid[t];
+    if (cid >= 0) sorted[cstart[cid] + rank[t]] = (int32_t)t;
+  }
+}
+
+// one thread per cell: order the cell's slots ascending (removes the atomic-arrival nondeterminism),
+// then write the 32-byte SAtom records in sorted order.
+__global__ void k_cell_sort_gather(const GridParams* __restrict__ gp, const int32_t* __restrict__ cstart, int32_t* __restrict__ sorted,
+                                   const double* __restrict__ pos, const int32_t* __restrict__ Z, const DevParams* __restrict__ dp,
+                                   SAtom* __restrict__ sat, int32_t* __restrict__ sidx_of_slot) {
+  int ncells = gp->ncells;
+  for (int cid = blockIdx.x * blockDim.x + threadIdx.x; cid < ncells; cid += gridDim.x * blockDim.x) {
+    int b = cstart[cid], e = cstart[cid + 1];
+    for (int i = b + 1; i < e; i++) {
+      int32_t v = sorted[i];
+      int j = i - 1;
+      while (j >= b && sorted[j] > v) { sorted[j + 1] = sorted[j]; j--; }
+      sorted[j + 1] = v;
+    }
+    for (int i = b; i < e; i++) {
+      int32_t s = sorted[i];
+      SAtom a;
+      a.x = pos[3 * (int64_t)s]; a.y = pos[3 * (int64_t)s + 1]; a.z = pos[3 * (int64_t)s + 2];
+      a.slot = s;
+      int z = Z[s], ei = -1;
+      for (int k = 0; k < dp->n_ele; k++) if (dp->eles[k] == z) ei = k;
+      a.e = ei;
+      sat[i] = a;
+      sidx_of_slot[s] = i;
+    }
+  }
+}
+
+// ---------------------------------------------------------------- build launcher
+int tm_launch_nlist_build(tm_ctx* c, const SysView& s, double rc_grid) {
+  int64_t n = s.nslots;
+  int rc;
+  if ((rc = tm_buf(c, c->b_cellid, n * 4))) return rc;
+  if ((rc = tm_buf(c, c->b_rank, n * 4))) return rc;
+  if ((rc = tm_buf(c, c->b_count, (s.ncells_cap + 8) * 4))) return rc;
+  if ((rc = tm_buf(c, c->b_cstart, (s.ncells_cap + 8) * 4))) return rc;
+  if ((rc = tm_buf(c, c->b_sorted, n * 4))) return rc;
+  if ((rc = tm_buf(c, c->b_satom, n * sizeof(SAtom)))) return rc;
+  if ((rc = tm_buf(c, c->b_rowofslot, n * 4))) return rc;   // reused as sidx_of_slot first (see rows)
+  if ((rc = tm_buf(c, c->b_scan_tmp, ((s.ncells_cap + n) / SCAN_TILE + 16) * 4 * 2))) return rc;
+  if ((rc = tm_buf(c, c->b_bbox, 64))) return rc;
+  if ((rc = tm_buf(c, c->b_grid, sizeof(GridParams)))) return rc;
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks < 1) blocks = 1;
+  unsigned long long* bb = (unsigned long long*)c->b_bbox.p;
+  GridParams* gp = (GridParams*)c->b_grid.p;
+  k_bbox_init<<<1, 32, 0, c->stream>>>(bb);
+  k_bbox<<<blocks, 256, 0, c->stream>>>((const double*)c->b_pos.p, (const int32_t*)c->b_Z.p, n, bb);
+  k_grid_params<<<1, 1, 0, c->stream>>>(bb, rc_grid, s.nmol, s.ncells_cap, gp);
+  TM_CUDA(cudaMemsetAsync(c->b_count.p, 0, (s.ncells_cap + 8) * 4, c->stream));
+  k_cell_count<<<blocks, 256, 0, c->stream>>>((const double*)c->b_pos.p, (const int32_t*)c->b_Z.p, n, s.maxnatom, gp,
+                                              (int32_t*)c->b_cellid.p, (int32_t*)c->b_rank.p, (int32_t*)c->b_count.p);
+  c->launches += 4;
+  if ((rc = scan_exclusive(c, (const int32_t*)c->b_count.p, (int32_t*)c->b_cstart.p, s.ncells_cap, (int32_t*)c->b_scan_tmp.p))) return rc;
+  k_scatter<<<blocks, 256, 0, c->stream>>>((const int32_t*)c->b_cellid.p, (const int32_t*)c->b_rank.p, (const int32_t*)c->b_cstart.p, n,
+                                           (int32_t*)c->b_sorted.p);
+  int cblocks = (int)((s.ncells_cap + 127) / 128);
+  if (cblocks > 148 * 16) cblocks = 148 * 16;
+  k_cell_sort_gather<<<cblocks, 128, 0, c->stream>>>(gp, (const int32_t*)c->b_cstart.p, (int32_t*)c->b_sorted.p, (const double*)c->b_pos.p,
+                                                     (const int32_t*)c->b_Z.p, c->dp, (SAtom*)c->b_satom.p, (int32_t*)c->b_rank.p);
+  c->launches += 2;
+  TM_CUDA(cudaGetLastError());
+  return TM_OK;
+}
+
+// ---------------------------------------------------------------- centre rows
+// Rows are the centres ordered by (element, cell-sorted position); each element's row range starts
+// at a multiple of TM_ROW_TILE so a GEMM row tile never straddles two elements.
+//   rowmeta[2e] = first row of element e, rowmeta[2e+1] = number of rows of element e,
+//   rowmeta[2*TM_MAX_ELE] = total centres.
+#define ROWS_BLOCK 1024
+struct SlabFilter { int rank, world; double gx, gy, gz; };
+// Owned-atom slabs: a centre belongs to rank floor(frac*world) where frac = pos . g is its fractional
+// coordinate along the first lattice vector (g = first row of the inverse lattice, supplied by the host).
+__device__ __forceinline__ bool is_centre(const SAtom& a, int64_t nreal, int periodic, const SlabFilter& sf) {
+  if (a.e < 0) return false;
+  if (periodic && a.slot >= nreal) return false;
+  if (sf.world > 1) {
+    double frac = a.x * sf.gx + a.y * sf.gy + a.z * sf.gz;
+    int owner = (int)floor(frac * (double)sf.world);
+    owner = owner < 0 ? 0 : (owner >= sf.world ? sf.world - 1 : owner);
+    if (owner != sf.rank) return false;
+  }
+  return true;
+}
+
+__global__ void k_rows_count(const SAtom* __restrict__ sat, const int32_t* __restrict__ cstart, const GridParams* __restrict__ gp,
+                             int64_t nreal, int periodic, SlabFilter sf, int32_t* __restrict__ blkcnt) {
+  __shared__ int32_t cnt[TM_MAX_ELE];
+  if (threadIdx.x < TM_MAX_ELE) cnt[threadIdx.x] = 0;
+  __syncthreads();
+  GridParams g = *gp;
+  int ntot = cstart[g.ncells];
+  int i = blockIdx.x * ROWS_BLOCK + threadIdx.x;
+  if (i < ntot) {
+    SAtom a = sat[i];
+    if (is_centre(a, nreal, periodic, sf)) atomicAdd(&cnt[a.e], 1);
+  }
+  __syncthreads();
+  if (threadIdx.x < TM_MAX_ELE) blkcnt[blockIdx.x * TM_MAX_ELE + threadIdx.x] = cnt[threadIdx.x];
+}
+
+// single block: per element exclusive scan over blocks; element bases padded to TM_ROW_TILE
+__global__ void k_rows_scan(int32_t* __restrict__ blkcnt, int nblk, int n_ele, int32_t* __restrict__ rowmeta) {
+  __shared__ int32_t tot[TM_MAX_ELE];
+  int e = threadIdx.x >> 5, lane = threadIdx.x & 31;   // one warp per element
+  if (e < TM_MAX_ELE) {
+    int32_t carry = 0;
+    for (int base = 0; base < nblk; base += 32) {
+      int i = base + lane;
+      int32_t v = (i < nblk) ? blkcnt[i * TM_MAX_ELE + e] : 0;
+      int32_t inc = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        int32_t t = __shfl_up_sync(FULL, inc, o);
+        if (lane >= o) inc += t;
+      }
+      if (i < nblk) blkcnt[i * TM_MAX_ELE + e] = carry + inc - v;
+      carry += __shfl_sync(FULL, inc, 31);
+    }
+    if (lane == 0) tot[e] = carry;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int32_t base = 0, total = 0;
+    for (int k = 0; k < TM_MAX_ELE; k++) {
+      int32_t cnt = (k < n_ele) ? tot[k] : 0;
+      rowmeta[2 * k] = base;
+      rowmeta[2 * k + 1] = cnt;
+      base += ((cnt + TM_ROW_TILE - 1) / TM_ROW_TILE) * TM_ROW_TILE;
+      total += cnt;
+    }
+    rowmeta[2 * TM_MAX_ELE] = total;
+    rowmeta[2 * TM_MAX_ELE + 1] = base;   // rows in use incl. padding
+  }
+}
+
+__global__ void k_rows_fill(const SAtom* __restrict__ sat, const int32_t* __restrict__ cstart, const GridParams* __restrict__ gp,
+                            int64_t nreal, int periodic, SlabFilter sf, const int32_t* __restrict__ blkcnt,
+                            const int32_t* __restrict__ rowmeta, int32_t* __restrict__ rowslot, int32_t* __restrict__ rowsidx,
+                            int32_t* __restrict__ rowofslot) {
+  __shared__ int32_t wcnt[32][TM_MAX_ELE];
+  GridParams g = *gp;
+  int ntot = cstart[g.ncells];
+  int i = blockIdx.x * ROWS_BLOCK + threadIdx.x;
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int e = -1, slot = -1;
+  if (i < ntot) {
+    SAtom a = sat[i];
+    slot = a.slot;
+    if (is_centre(a, nreal, periodic, sf)) e = a.e;
+  }
+  // rank of this thread among same-element centres of the block, in index order
+  int myrank = 0;
+#pragma unroll
+  for (int k = 0; k < TM_MAX_ELE; k++) {
+    unsigned m = __ballot_sync(FULL, e == k);
+    if (e == k) myrank = __popc(m & ((1u << lane) - 1));
+    if (lane == 0) wcnt[w][k] = __popc(m);
+  }
+  __syncthreads();
+  if (e >= 0) {
+    int off = 0;
+    for (int ww = 0; ww < w; ww++) off += wcnt[ww][e];
+    int row = rowmeta[2 * e] + blkcnt[blockIdx.x * TM_MAX_ELE + e] + off + myrank;
+    rowslot[row] = slot;
+    rowsidx[row] = i;
+    rowofslot[slot] = row;
+  }
+}
+
+__global__ void k_fill_i32(int32_t* p, int64_t n, int32_t v) {
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) p[t] = v;
+}
+
+int tm_launch_rows(tm_ctx* c, const SysView& s) {
+  int rc;
+  int nblk = (int)((s.nslots + ROWS_BLOCK - 1) / ROWS_BLOCK);
+  if (nblk < 1) nblk = 1;
+  if ((rc = tm_buf(c, c->b_blkcnt, (size_t)nblk * TM_MAX_ELE * 4))) return rc;
+  if ((rc = tm_buf(c, c->b_rowmeta, (2 * TM_MAX_ELE + 2) * 4))) return rc;
+  if ((rc = tm_buf(c, c->b_rowslot, s.nrows * 4))) return rc;
+  if ((rc = tm_buf(c, c->b_rowsidx, s.nrows * 4))) return rc;
+  int fb = (int)((s.nrows + 255) / 256);
+  k_fill_i32<<<fb, 256, 0, c->stream>>>((int32_t*)c->b_rowslot.p, s.nrows, -1);
+  int fb2 = (int)((s.nslots + 255) / 256);
+  if (fb2 > 148 * 8) fb2 = 148 * 8;
+  k_fill_i32<<<fb2, 256, 0, c->stream>>>((int32_t*)c->b_rowofslot.p, s.nslots, -1);
+  const SAtom* sat = (const SAtom*)c->b_satom.p;
+  const GridParams* gp = (const GridParams*)c->b_grid.p;
+  SlabFilter sf{s.slab_rank, s.slab_world, s.slab_g[0], s.slab_g[1], s.slab_g[2]};
+  k_rows_count<<<nblk, ROWS_BLOCK, 0, c->stream>>>(sat, (const int32_t*)c->b_cstart.p, gp, s.nreal, s.periodic, sf,
+                                                   (int32_t*)c->b_blkcnt.p);
+  k_rows_scan<<<1, 32 * TM_MAX_ELE, 0, c->stream>>>((int32_t*)c->b_blkcnt.p, nblk, c->hp.n_ele, (int32_t*)c->b_rowmeta.p);
+  k_rows_fill<<<nblk, ROWS_BLOCK, 0, c->stream>>>(sat, (const int32_t*)c->b_cstart.p, gp, s.nreal, s.periodic, sf,
+                                                  (const int32_t*)c->b_blkcnt.p, (const int32_t*)c->b_rowmeta.p, (int32_t*)c->b_rowslot.p,
+                                                  (int32_t*)c->b_rowsidx.p, (int32_t*)c->b_rowofslot.p);
+  c->launches += 5;
+  TM_CUDA(cudaGetLastError());
+  return TM_OK;
+}
+
+// ---------------------------------------------------------------- neighbour enumeration
+// One warp per centre row.  The 27 neighbour cells are visited as 9 (x,y) columns whose +-1 z-run
+// is contiguous in the cell-sorted array; lanes stride over the run (coalesced 32-byte records),
+// the accept test runs in float64, survivors are compacted with __ballot_sync / __popc.
+// Entry = cell-sorted index of j, bit 31 set when j is also inside the angular cutoff.
+__device__ __forceinline__ double ref_dist(const SAtom& a, double xi, double yi, double zi) {
+  double dx = __dsub_rn(xi, a.x), dy = __dsub_rn(yi, a.y), dz = __dsub_rn(zi, a.z);
+  double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+  return __dadd_rn(__dsqrt_rn(d2), 0.0000000000001);
+}
+
+template <bool FILL>
+__global__ void k_neighbours(const SAtom* __restrict__ sat, const int32_t* __restrict__ cstart, const GridParams* __restrict__ gp,
+                             const int32_t* __restrict__ rowsidx, const int32_t* __restrict__ rowslot, int64_t nrows, int64_t maxnatom,
+                             double rr, double ra, int32_t* __restrict__ nbcnt, const int32_t* __restrict__ nboff,
+                             uint32_t* __restrict__ nbr, int64_t nbr_cap, int32_t* __restrict__ flags) {
+  int64_t row = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (row >= nrows) return;
+  int slot = rowslot[row];
+  if (slot < 0) { if (!FILL && lane == 0) nbcnt[row] = 0; return; }
+  GridParams g = *gp;
+  int si = rowsidx[row];
+  SAtom ci = sat[si];
+  int m = (int)(slot / maxnatom);
+  int cx = cell_coord(ci.x, g.ox, g.inv_cell, g.gx);
+  int cy = cell_coord(ci.y, g.oy, g.inv_cell, g.gy);
+  int cz = cell_coord(ci.z, g.oz, g.inv_cell, g.gz);
+  int z0 = max(cz - 1, 0), z1 = min(cz + 1, g.gz - 1);
+  int total = 0;
+  int wbase = FILL ? nboff[row] : 0;
+  for (int dx = -1; dx <= 1; dx++) {
+    int x = cx + dx;
+    if (x < 0 || x >= g.gx) continue;
+    for (int dy = -1; dy <= 1; dy++) {
+      int y = cy + dy;
+      if (y < 0 || y >= g.gy) continue;
+      int cbase = m * g.ncell_mol + (x * g.gy + y) * g.gz;
+      int b = cstart[cbase + z0], e = cstart[cbase + z1 + 1];
+      for (int j0 = b; j0 < e; j0 += 32) {
+        int j = j0 + lane;
+        bool ok = false, ang = false;
+        if (j < e && j != si) {
+          SAtom aj = sat[j];
+          double d = ref_dist(aj, ci.x, ci.y, ci.z);
+          ok = d < rr;
+          ang = d < ra;
+        }
+        unsigned mk = __ballot_sync(FULL, ok);
+        if (FILL && ok) {
+          int64_t w = (int64_t)wbase + total + __popc(mk & ((1u << lane) - 1));
+          if (w < nbr_cap) nbr[w] = (uint32_t)j | (ang ? 0x80000000u : 0u);
+          else atomicOr(flags, 2);
+        }
+        total += __popc(mk);
+      }
+    }
+  }
+  if (!FILL && lane == 0) nbcnt[row] = total;
+}
+
+int tm_launch_neighbours(tm_ctx* c, const SysView& s) {
+  int rc;
+  if ((rc = tm_buf(c, c->b_nbcnt, (s.nrows + 8) * 4))) return rc;
+  if ((rc = tm_buf(c, c->b_nboff, (s.nrows + 8) * 4))) return rc;
+  const SAtom* sat = (const SAtom*)c->b_satom.p;
+  const GridParams* gp = (const GridParams*)c->b_grid.p;
+  int blocks = (int)((s.nrows * 32 + 255) / 256);
+  k_neighbours<false><<<blocks, 256, 0, c->stream>>>(sat, (const int32_t*)c->b_cstart.p, gp, (const int32_t*)c->b_rowsidx.p,
+                                                     (const int32_t*)c->b_rowslot.p, s.nrows, s.maxnatom, c->hp.rr_exact, c->hp.ra_exact,
+                                                     (int32_t*)c->b_nbcnt.p, nullptr, nullptr, 0, (int32_t*)c->b_flags.p);
+  c->launches++;
+  if ((rc = scan_exclusive(c, (const int32_t*)c->b_nbcnt.p, (int32_t*)c->b_nboff.p, s.nrows, (int32_t*)c->b_scan_tmp.p))) return rc;
+  // capacity: a host bound so that no device->host round trip is needed.  256 radial neighbours per
+  // centre is ~5x liquid water (48 max measured); overflow raises TM_ECAP in finalize.
+  size_t cap = (size_t)s.ncent_max * 256 + 1024;
+  if ((rc = tm_buf(c, c->b_nbr, cap * 4))) return rc;
+  k_neighbours<true><<<blocks, 256, 0, c->stream>>>(sat, (const int32_t*)c->b_cstart.p, gp, (const int32_t*)c->b_rowsidx.p,
+                                                    (const int32_t*)c->b_rowslot.p, s.nrows, s.maxnatom, c->hp.rr_exact, c->hp.ra_exact,
+                                                    nullptr, (const int32_t*)c->b_nboff.p, (uint32_t*)c->b_nbr.p, (int64_t)cap, (int32_t*)c->b_flags.p);
+  c->launches++;
+  TM_CUDA(cudaGetLastError());
+  return TM_OK;
+}
+
+// ---------------------------------------------------------------- MolEmb-compatible CSR list
+// Rows are slots i < nreal (all slots when nreal == n).  do_perms == 0 keeps only j > i.
+template <bool FILL>
+__global__ void k_nlist_csr(const SAtom* __restrict__ sat, const int32_t* __restrict__ cstart, const GridParams* __restrict__ gp,
+                            const int32_t* __restrict__ sidx_of_slot, int64_t ncentres, int64_t maxnatom, double rc, int do_perms,
+                            int32_t* __restrict__ cnt, const int64_t* __restrict__ off, int32_t* __restrict__ out) {
+  int64_t i = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (i >= ncentres) return;
+  int si = sidx_of_slot[i];
+  if (si < 0) { if (!FILL && lane == 0) cnt[i] = 0; return; }
+  GridParams g = *gp;
+  SAtom ci = sat[si];
+  int m = (int)(i / maxnatom);
+  int cx = cell_coord(ci.x, g.ox, g.inv_cell, g.gx);
+  int cy = cell_coord(ci.y, g.oy, g.inv_cell, g.gy);
+  int cz = cell_coord(ci.z, g.oz, g.inv_cell, g.gz);
+  int z0 = max(cz - 1, 0), z1 = min(cz + 1, g.gz - 1);
+  int total = 0;
+  int64_t wbase = FILL ? off[i] : 0;
+  for (int dx = -1; dx <= 1; dx++) {
+    int x = cx + dx;
+    if (x < 0 || x >= g.gx) continue;
+    for (int dy = -1; dy <= 1; dy++) {
+      int y = cy + dy;
+      if (y < 0 || y >= g.gy) continue;
+      int cbase = m * g.ncell_mol + (x * g.gy + y) * g.gz;
+      int b = cstart[cbase + z0], e = cstart[cbase + z1 + 1];
+      for (int j0 = b; j0 < e; j0 += 32) {
+        int j = j0 + lane;
+        bool ok = false;
+        int js = -1;
+        if (j < e && j != si) {
+          SAtom aj = sat[j];
+          js = aj.slot;
+          ok = ref_dist(aj, ci.x, ci.y, ci.z) < rc;
+          if (!do_perms && js < (int)i) ok = false;
+        }
+        unsigned mk = __ballot_sync(FULL, ok);
+        if (FILL && ok) out[wbase + total + __popc(mk & ((1u << lane) - 1))] = js;
+        total += __popc(mk);
+      }
+    }
+  }
+  if (!FILL && lane == 0) cnt[i] = total;
+}
+
+__global__ void k_mark_unsorted(int32_t* sidx_of_slot, int64_t n) {
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) sidx_of_slot[t] = -1;
+}
+
+// Builds the grid for `rc`, counts, and returns the CSR on the host in c->h_off / c->h_idx.
+int tm_launch_nlist_csr(tm_ctx* c, const SysView& s, double rc, int do_perms, int64_t* total_out) {
+  int r;
+  // sidx_of_slot lives in b_rank after the build; mark invalid slots first
+  if ((r = tm_launch_nlist_build(c, s, rc))) return r;
+  int64_t ncent = s.periodic ? s.nreal : s.nslots;
+  if ((r = tm_buf(c, c->b_nbcnt, (ncent + 8) * 4))) return r;
+  const SAtom* sat = (const SAtom*)c->b_satom.p;
+  const GridParams* gp = (const GridParams*)c->b_grid.p;
+  int blocks = (int)((ncent * 32 + 255) / 256);
+  if (blocks < 1) blocks = 1;
+  k_nlist_csr<false><<<blocks, 256, 0, c->stream>>>(sat, (const int32_t*)c->b_cstart.p, gp, (const int32_t*)c->b_rank.p, ncent, s.maxnatom, rc,
+                                                    do_perms, (int32_t*)c->b_nbcnt.p, nullptr, nullptr);
+  c->launches++;
+  TM_CUDA(cudaGetLastError());
+  std::vector<int32_t> hc((size_t)ncent);
+  TM_CUDA(cudaMemcpyAsync(hc.data(), c->b_nbcnt.p, (size_t)ncent * 4, cudaMemcpyDeviceToHost, c->stream));
+  TM_CUDA(cudaStreamSynchronize(c->stream));
+  c->h_off.assign((size_t)ncent + 1, 0);
+  for (int64_t i = 0; i < ncent; i++) c->h_off[i + 1] = c->h_off[i] + hc[i];
+  int64_t total = c->h_off[ncent];
+  *total_out = total;
+  if ((r = tm_buf(c, c->b_nboff, (ncent + 8) * 8))) return r;
+  if ((r = tm_buf(c, c->b_nbr, (size_t)(total + 8) * 4))) return r;
+  TM_CUDA(cudaMemcpyAsync(c->b_nboff.p, c->h_off.data(), (size_t)(ncent + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+  k_nlist_csr<true><<<blocks, 256, 0, c->stream>>>(sat, (const int32_t*)c->b_cstart.p, gp, (const int32_t*)c->b_rank.p, ncent, s.maxnatom, rc,
+                                                   do_perms, nullptr, (const int64_t*)c->b_nboff.p, (int32_t*)c->b_nbr.p);
+  c->launches++;
+  TM_CUDA(cudaGetLastError());
+  std::vector<int32_t> hi((size_t)total);
+  if (total) TM_CUDA(cudaMemcpyAsync(hi.data(), c->b_nbr.p, (size_t)total * 4, cudaMemcpyDeviceToHost, c->stream));
+  TM_CUDA(cudaStreamSynchronize(c->stream));
+  c->h_idx.resize((size_t)total);
+  for (int64_t t = 0; t < total; t++) c->h_idx[t] = hi[t];
+  return TM_OK;
+}

@@ -1,0 +1,303 @@
+// K5: charge neutralisation + damped-shifted-force / ELU Coulomb + Grimme-C6 vdW pair kernel.
+//
+// Restates on the device:
+//   charge neutralisation + dipole        TFMolInstanceDirect.py:5274-5279 (periodic :5881-5893)
+//   TFCoulombEluSRDSFLR                    RawSymFunc.py:1307-1359
+//   TFVdwPolyLR / TFVdwPolyLRWithEle       RawSymFunc.py:1361-1465 (double Bohr scaling kept, Q6)
+// and the part of tf.gradients that flows through them.  The 15 A pair list (34 M rows at 24k atoms,
+// Neighbors.py:323-342) is never materialised: every centre walks the cell grid.
+//
+// Energy convention: E = 1/2 sum over ORDERED pairs (i centre, j any slot) -- equal to the reference's
+// i<j sum for aperiodic input (TFMolManage.py:1311-1312) and to its "/2" periodic form
+// (TFMolInstanceDirect.py:5896, 5824).  Gradient on a real row a: sum_j w_j d e_aj/d x_a with w_j = 1
+// for real j and 1/2 for image j (image rows are independent variables whose gradient the reference
+// discards).  dEcc/dq_a = sum_j q_j kappa_aj uses the image symmetry of a full
+// tessellation (Periodic.py:131-168), which every reference flow provides (Q12).
+//
+// Mapping: one warp per centre; lanes stride over contiguous z-runs of the cell-sorted copy, candidates
+// inside the cutoff are compacted (ballot/popc) into a per-warp shared queue and evaluated 32 at a time
+// so the erfc/exp work runs on full warps.
+#include "tm_internal.h"
+#include <algorithm>
+
+#define FULL 0xffffffffu
+#define PAIR_WARPS 8
+#define QCAP 64
+
+// ---- charges -----------------------------------------------------------------------------------
+// y_charge[row] -> qraw_slot[slot]; per-molecule sums in double
+__global__ void k_qraw_scatter(const float* __restrict__ y, const int32_t* __restrict__ rowslot, int64_t nrows, double* __restrict__ qraw_slot) {
+  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < nrows; r += (int64_t)gridDim.x * blockDim.x) {
+    int s = rowslot[r];
+    if (s >= 0) qraw_slot[s] = (double)y[r];
+  }
+}
+
+// molsum[m] = sum over real slots of molecule m (one block per molecule chunk)
+__global__ void k_mol_sum(const double* __restrict__ v, const int32_t* __restrict__ Z, int64_t maxnatom, int64_t nvalid_per_mol, double* __restrict__ molacc, int field) {
+  int m = blockIdx.x;
+  double s = 0.0;
+  for (int64_t a = threadIdx.x; a < nvalid_per_mol; a += blockDim.x) {
+    int64_t slot = (int64_t)m * maxnatom + a;
+    if (Z[slot] > 0) s += v[slot];
+  }
+  __shared__ double sh[32];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    s = (threadIdx.x < (blockDim.x >> 5)) ? sh[threadIdx.x] : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
+    if (threadIdx.x == 0) molacc[16 * m + field] = s;
+  }
+}
+
+// q_slot = qraw - molsum * inv_n[m]  for the first nq slots of each molecule (padding included, Q11);
+// dipole[m] += q * B * x   (TFMolInstanceDirect.py:5278-5279)
+__global__ void k_neutralise(const double* __restrict__ qraw_slot, double* __restrict__ molacc, const double* __restrict__ inv_n,
+                             const double* __restrict__ pos, const int32_t* __restrict__ Z, int64_t maxnatom, int64_t nq_per_mol, int64_t nmol,
+                             double* __restrict__ q_slot) {
+  int m = blockIdx.y;
+  double mean = molacc[16 * m + 4] * inv_n[m];
+  double d0 = 0, d1 = 0, d2 = 0;
+  for (int64_t a = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; a < nq_per_mol; a += (int64_t)gridDim.x * blockDim.x) {
+    int64_t slot = (int64_t)m * maxnatom + a;
+    double q = ((Z[slot] > 0) ? qraw_slot[slot] : 0.0) - mean;
+    q_slot[slot] = q;
+    d0 += q * TM_BOHRPERA * pos[3 * slot];
+    d1 += q * TM_BOHRPERA * pos[3 * slot + 1];
+    d2 += q * TM_BOHRPERA * pos[3 * slot + 2];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    d0 += __shfl_xor_sync(FULL, d0, o);
+    d1 += __shfl_xor_sync(FULL, d1, o);
+    d2 += __shfl_xor_sync(FULL, d2, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(&molacc[16 * m + 6], d0);
+    atomicAdd(&molacc[16 * m + 7], d1);
+    atomicAdd(&molacc[16 * m + 8], d2);
+  }
+}
+
+// charge per cell-sorted atom (images inherit the charge of slot % nreal, TFMolInstanceDirect.py:5892-5893)
+__global__ void k_q_sorted(const SAtom* __restrict__ sat, const int32_t* __restrict__ cstart, const GridParams* __restrict__ gp,
+                           const double* __restrict__ q_slot, int64_t nreal, int periodic, float* __restrict__ qs) {
+  int ntot = cstart[gp->ncells];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ntot; i += gridDim.x * blockDim.x) {
+    int s = sat[i].slot;
+    if (periodic) s = (int)(s % nreal);
+    qs[i] = (float)q_slot[s];
+  }
+}
+
+int tm_launch_charges(tm_ctx* c, const SysView& s) {
+  int rc;
+  int64_t nq = s.periodic ? s.nreal : s.nslots;           // slots that carry an own charge
+  int64_t nq_per_mol = s.periodic ? s.nreal : s.maxnatom;
+  if ((rc = tm_buf(c, c->b_q, (size_t)nq * 8 * 2))) return rc;  // [qraw_slot | q_slot]
+  if ((rc = tm_buf(c, c->b_qs, (size_t)s.nslots * 4))) return rc;
+  double* qraw = (double*)c->b_q.p;
+  double* q = qraw + nq;
+  // molacc (zeroed by the caller at the start of the evaluation), stride 16 doubles per molecule:
+  //   [0] Etotal [1] Ebp [2] Ecc [3] Evdw [4] sum q_raw [5] sum dE/dq [6..8] dipole
+  double* molacc = (double*)c->b_molacc.p;
+  int blocks = (int)((s.nrows + 255) / 256);
+  // in slab mode qraw_slot was already all-reduced by the host and written into b_q
+  if (s.slab_world <= 1) {
+    TM_CUDA(cudaMemsetAsync(qraw, 0, (size_t)nq * 8, c->stream));
+    k_qraw_scatter<<<blocks, 256, 0, c->stream>>>((const float*)c->b_y[TM_NET_CHARGE].p, (const int32_t*)c->b_rowslot.p, s.nrows, qraw);
+    c->launches++;
+  }
+  k_mol_sum<<<(int)s.nmol, 256, 0, c->stream>>>(qraw, (const int32_t*)c->b_Z.p, s.maxnatom, nq_per_mol, molacc, 4);
+  dim3 g((unsigned)std::min<int64_t>((nq_per_mol + 255) / 256, 148 * 4), (unsigned)s.nmol);
+  k_neutralise<<<g, 256, 0, c->stream>>>(qraw, molacc, (const double*)c->b_natom.p, (const double*)c->b_pos.p, (const int32_t*)c->b_Z.p,
+                                         s.maxnatom, nq_per_mol, s.nmol, q);
+  int b2 = (int)std::min<int64_t>((s.nslots + 255) / 256, 148 * 8);
+  k_q_sorted<<<b2, 256, 0, c->stream>>>((const SAtom*)c->b_satom.p, (const int32_t*)c->b_cstart.p, (const GridParams*)c->b_grid.p, q, s.nreal,
+                                        s.periodic, (float*)c->b_qs.p);
+  c->launches += 3;
+  TM_CUDA(cudaGetLastError());
+  return TM_OK;
+}
+
+// ---- pair kernel -------------------------------------------------------------------------------
+struct PairAcc {
+  float ecc, evdw, dedq, gx, gy, gz;
+};
+
+__device__ __forceinline__ void pair_eval(const DevParams& P, float r, float dx, float dy, float dz, float qi, float qj, int ei, int ej,
+                                          float wj, int do_vdw, PairAcc& A) {
+  const float B = (float)TM_BOHRPERA;
+  float R = B * r;
+  float dEdR = 0.f;   // d e_ij / dR (Bohr)
+  if (P.add_ecc) {
+    float kap, dkap;
+    if (R > P.R_sr) {
+      if (R > P.R_lr) {
+        kap = 0.f; dkap = 0.f;
+      } else {
+        float aR = P.alpha_b * R;
+        float er = erfcf(aR), ex = expf(-aR * aR);
+        float iR = 1.0f / R;
+        kap = er * iR - P.Zc + (R - P.R_lr) * P.ZoverR_plus_Y;
+        dkap = -er * iR * iR - 1.1283791671f * P.alpha_b * ex * iR + P.ZoverR_plus_Y;
+      }
+    } else {
+      float ex = expf(R - P.R_sr);
+      kap = P.elu_a * (ex - 1.0f) + P.elu_shift;
+      dkap = P.elu_a * ex;
+    }
+    A.ecc += qi * qj * kap;
+    A.dedq += qj * kap;
+    dEdR += qi * qj * dkap;
+  }
+  if (do_vdw) {
+    float Rp = B * R;                       // second Bohr scaling (RawSymFunc.py:1377)
+    float t = Rp / P.poly_width_b;
+    float S, dS;
+    if (t > 1.0f) { S = 1.0f; dS = 0.f; }
+    else { S = -t * t * (2.0f * t - 3.0f); dS = (6.0f * t - 6.0f * t * t) / P.poly_width_b; }
+    float c6 = P.sqrtC6[ei] * P.sqrtC6[ej];
+    float Rs = P.Rvdw[ei] + P.Rvdw[ej];
+    float iRp = 1.0f / Rp;
+    float iRp2 = iRp * iRp;
+    float Rp6i = iRp2 * iRp2 * iRp2;
+    float xi = Rs * iRp;                    // 1/x
+    float xi2 = xi * xi, xi6 = xi2 * xi2 * xi2;
+    float xm12 = xi6 * xi6;                 // x^-12
+    float damp = 1.0f / (1.0f + 6.0f * xm12);
+    float w = -S * c6 * Rp6i * damp;
+    float ddamp = 72.0f * xm12 * iRp * damp * damp;
+    float dw = -c6 * (dS * Rp6i * damp - 6.0f * S * Rp6i * iRp * damp + S * Rp6i * ddamp);
+    A.evdw += w;
+    dEdR += B * dw;
+  }
+  // d e_ij / d x_i = dEdR * B * (x_i - x_j)/r ; (dx,dy,dz) = x_j - x_i
+  float sc = -wj * dEdR * B / r;
+  A.gx += sc * dx; A.gy += sc * dy; A.gz += sc * dz;
+}
+
+__global__ void __launch_bounds__(PAIR_WARPS * 32)
+k_pair(const SAtom* __restrict__ sat, const float* __restrict__ qs, const int32_t* __restrict__ cstart, const GridParams* __restrict__ gp,
+       const int32_t* __restrict__ rowsidx, const int32_t* __restrict__ rowslot, int64_t nrows, int64_t maxnatom, int64_t nreal_slots,
+       const __grid_constant__ DevParams P, int do_vdw, int do_force, float cutoff_A, double* __restrict__ dedq_slot, float* __restrict__ F,
+       double* __restrict__ molacc) {
+  __shared__ float q_r[PAIR_WARPS][QCAP], q_q[PAIR_WARPS][QCAP], q_dx[PAIR_WARPS][QCAP], q_dy[PAIR_WARPS][QCAP], q_dz[PAIR_WARPS][QCAP];
+  __shared__ int q_info[PAIR_WARPS][QCAP];
+  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int64_t row = (int64_t)blockIdx.x * PAIR_WARPS + warp;
+  if (row >= nrows) return;
+  int slot = rowslot[row];
+  if (slot < 0) return;
+  GridParams g = *gp;
+  int si = rowsidx[row];
+  SAtom ci = sat[si];
+  float qi = qs[si];
+  int ei = ci.e;
+  int m = (int)(slot / maxnatom);
+  int cx = cell_coord(ci.x, g.ox, g.inv_cell, g.gx);
+  int cy = cell_coord(ci.y, g.oy, g.inv_cell, g.gy);
+  int cz = cell_coord(ci.z, g.oz, g.inv_cell, g.gz);
+  float cell = (float)g.cell;
+  float rc2 = cutoff_A * cutoff_A;
+  int nrange = (int)ceilf(cutoff_A / cell);
+  PairAcc A = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  int qn = 0;
+  for (int dx = -nrange; dx <= nrange; dx++) {
+    int x = cx + dx;
+    if (x < 0 || x >= g.gx) continue;
+    float mx = fmaxf(0.f, (float)(abs(dx) - 1)) * cell;
+    for (int dy = -nrange; dy <= nrange; dy++) {
+      int y = cy + dy;
+      if (y < 0 || y >= g.gy) continue;
+      float my = fmaxf(0.f, (float)(abs(dy) - 1)) * cell;
+      float rem = rc2 - mx * mx - my * my;
+      if (rem < 0.f) continue;
+      int nz = (int)floorf(sqrtf(rem) / cell) + 1;
+      int z0 = max(cz - nz, 0), z1 = min(cz + nz, g.gz - 1);
+      int cbase = m * g.ncell_mol + (x * g.gy + y) * g.gz;
+      int b = cstart[cbase + z0], e = cstart[cbase + z1 + 1];
+      for (int j0 = b; j0 < e; j0 += 32) {
+        int j = j0 + lane;
+        bool ok = false;
+        float ddx = 0.f, ddy = 0.f, ddz = 0.f, d2 = 0.f, qj = 0.f;
+        int info = 0;
+        if (j < e && j != si) {
+          SAtom a = sat[j];
+          ddx = (float)(a.x - ci.x);
+          ddy = (float)(a.y - ci.y);
+          ddz = (float)(a.z - ci.z);
+          d2 = ddx * ddx + ddy * ddy + ddz * ddz;
+          ok = d2 < rc2;
+          if (ok) {
+            qj = qs[j];
+            info = a.e | ((a.slot < nreal_slots) ? 256 : 0);
+          }
+        }
+        unsigned mk = __ballot_sync(FULL, ok);
+        if (ok) {
+          int pos = qn + __popc(mk & ((1u << lane) - 1));
+          q_r[warp][pos] = sqrtf(d2);
+          q_q[warp][pos] = qj;
+          q_dx[warp][pos] = ddx; q_dy[warp][pos] = ddy; q_dz[warp][pos] = ddz;
+          q_info[warp][pos] = info;
+        }
+        qn += __popc(mk);
+        __syncwarp();
+        if (qn >= 32) {
+          int k = qn - 32 + lane;
+          int inf = q_info[warp][k];
+          pair_eval(P, q_r[warp][k], q_dx[warp][k], q_dy[warp][k], q_dz[warp][k], qi, q_q[warp][k], ei, inf & 255, (inf & 256) ? 1.0f : 0.5f,
+                    do_vdw, A);
+          qn -= 32;
+          __syncwarp();
+        }
+      }
+    }
+  }
+  if (lane < qn) {
+    int inf = q_info[warp][lane];
+    pair_eval(P, q_r[warp][lane], q_dx[warp][lane], q_dy[warp][lane], q_dz[warp][lane], qi, q_q[warp][lane], ei, inf & 255,
+              (inf & 256) ? 1.0f : 0.5f, do_vdw, A);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    A.ecc += __shfl_xor_sync(FULL, A.ecc, o);
+    A.evdw += __shfl_xor_sync(FULL, A.evdw, o);
+    A.dedq += __shfl_xor_sync(FULL, A.dedq, o);
+    A.gx += __shfl_xor_sync(FULL, A.gx, o);
+    A.gy += __shfl_xor_sync(FULL, A.gy, o);
+    A.gz += __shfl_xor_sync(FULL, A.gz, o);
+  }
+  if (lane == 0) {
+    dedq_slot[slot] = (double)A.dedq;
+    if (do_force) {
+      atomicAdd(F + 3 * (int64_t)slot, A.gx);
+      atomicAdd(F + 3 * (int64_t)slot + 1, A.gy);
+      atomicAdd(F + 3 * (int64_t)slot + 2, A.gz);
+    }
+    atomicAdd(&molacc[16 * m + 2], 0.5 * (double)A.ecc);
+    atomicAdd(&molacc[16 * m + 3], 0.5 * (double)A.evdw);
+    atomicAdd(&molacc[16 * m + 5], (double)A.dedq);
+  }
+}
+
+int tm_launch_pair(tm_ctx* c, const SysView& s, int flags) {
+  int rc;
+  int64_t nq = s.periodic ? s.nreal : s.nslots;
+  if ((rc = tm_buf(c, c->b_dedq, (size_t)nq * 8))) return rc;
+  TM_CUDA(cudaMemsetAsync(c->b_dedq.p, 0, (size_t)nq * 8, c->stream));
+  int blocks = (int)((s.nrows + PAIR_WARPS - 1) / PAIR_WARPS);
+  k_pair<<<blocks, PAIR_WARPS * 32, 0, c->stream>>>((const SAtom*)c->b_satom.p, (const float*)c->b_qs.p, (const int32_t*)c->b_cstart.p,
+                                                   (const GridParams*)c->b_grid.p, (const int32_t*)c->b_rowsidx.p, (const int32_t*)c->b_rowslot.p,
+                                                   s.nrows, s.maxnatom, nq, c->hp, (flags & TM_F_VDW) ? 1 : 0,
+                                                   (flags & TM_F_FORCE) ? 1 : 0, (float)c->params.ee_cutoff_off, (double*)c->b_dedq.p,
+                                                   (float*)c->b_F.p, (double*)c->b_molacc.p);
+  c->launches++;
+  TM_CUDA(cudaGetLastError());
+  return TM_OK;
+}

@@ -1,0 +1,225 @@
+"""GPU parity tests: the CUDA path (through the C-ABI, via tensormol_b200.engine.Engine) against the
+float64 oracle (oracle/) and the committed golden fixtures (tests/golden/, which carry pins computed by
+the reference's own MolEmb).  Tolerances: tests/common.py (= BASELINE.json north_star)."""
+import numpy as np
+import pytest
+
+from common import DESC_RTOL, ENERGY_RTOL, FORCE_ATOL_HA_BOHR, grad_ha_bohr, sort_rows_csr, water_box
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def _engine(eles, hidden, seed, gemm_mode=None, params=None):
+    from oracle import oracle_graph as og
+    from tensormol_b200.engine import Engine, random_weights
+    P = og.default_params()
+    if params:
+        P.update(params)
+    eng = Engine(eles, hidden, P)
+    W = random_weights(eng.eles, eng.D, hidden, seed)
+    eng.set_weights(W)
+    if gemm_mode is not None:
+        eng.set_gemm_mode(gemm_mode)
+    return eng, W, P
+
+
+def _check_desc(got, want):
+    scale = np.abs(want).max()
+    err = np.abs(got.astype(np.float64) - want).max()
+    assert err <= DESC_RTOL * scale, f"descriptor error {err:.3e} > {DESC_RTOL}*{scale:.3e}"
+
+
+def _check_energy(got, want, what):
+    got, want = np.asarray(got, np.float64), np.asarray(want, np.float64)
+    tol = ENERGY_RTOL * np.maximum(np.abs(want), 1e-3)   # absolute floor 1e-8 Ha for components that vanish
+    assert np.all(np.abs(got - want) <= tol), f"{what}: got {got} want {want}"
+
+
+def _check_grad(got, want):
+    err = np.abs(grad_ha_bohr(got) - grad_ha_bohr(want)).max()
+    assert err <= FORCE_ATOL_HA_BOHR, f"force error {err:.3e} Ha/Bohr"
+    # and much tighter relative to the force scale, so a sign / factor bug cannot hide under the absolute tolerance
+    scale = np.abs(want).max()
+    assert np.abs(got - want).max() <= 2e-4 * scale + 1e-7, f"relative force error {np.abs(got - want).max() / scale:.3e}"
+
+
+# ---------------------------------------------------------------------------------------- neighbour lists
+@pytest.mark.parametrize("name", ["h2o_cluster", "morphine"])
+def test_nlist_matches_reference_molemb(name):
+    g = load_golden(name)
+    eng, _, P = _engine(g["eles"], list(g["hidden"]), int(g["seed"]))
+    N = len(g["Z"])
+    for rc, tag in ((P["AN1_r_Rc"], "rr"), (P["AN1_a_Rc"], "ra"), (P["EECutoffOff"], "ree")):
+        off, idx = eng.nlist(g["xyz"], rc, N, 1)
+        assert np.array_equal(off, g[f"ref_nl_{tag}_off"])
+        assert np.array_equal(sort_rows_csr(off, idx), g[f"ref_nl_{tag}_idx"])
+    off, idx = eng.nlist(g["xyz"], P["EECutoffOff"], N, 0)
+    assert np.array_equal(off, g["ref_nl_ree_noperm_off"])
+    assert np.array_equal(sort_rows_csr(off, idx), g["ref_nl_ree_noperm_idx"])
+
+
+def test_nlist_periodic_images_matches_reference_molemb():
+    from oracle import oracle_np as onp
+    g = load_golden("water_tiny_periodic")
+    eng, _, P = _engine(g["eles"], list(g["hidden"]), int(g["seed"]))
+    Zt, Xt = onp.tess_lattice(g["lattice"], g["Z"].astype(np.uint8), g["xyz"], P["EECutoffOff"])
+    nreal = len(g["Z"])
+    for rc, tag in ((P["AN1_r_Rc"], "rr"), (P["AN1_a_Rc"], "ra")):
+        off, idx = eng.nlist(Xt, rc, nreal, 1)
+        assert np.array_equal(off, g[f"ref_nl_{tag}_off"])
+        assert np.array_equal(sort_rows_csr(off, idx), g[f"ref_nl_{tag}_idx"])
+    off, idx = eng.nlist(Xt, P["EECutoffOff"], nreal, 1)
+    assert np.array_equal(np.diff(off), g["ref_nl_ree_count"])
+    chk = np.array([np.bitwise_xor.reduce(idx[off[i]:off[i + 1]]) for i in range(nreal)])
+    assert np.array_equal(chk, g["ref_nl_ree_checksum"])
+
+
+@pytest.mark.parametrize("n,nreal,rc,perms", [(0, 0, 4.6, 1), (1, 1, 4.6, 1), (2, 2, 4.6, 0), (700, 700, 4.6, 1), (700, 200, 3.1, 1),
+                                               (700, 200, 3.1, 0), (3000, 3000, 4.6, 1), (500, 500, 15.0, 0)])
+def test_nlist_random_vs_oracle(n, nreal, rc, perms):
+    from oracle import oracle_np as onp
+    eng, _, _ = _engine([1, 8], [16], 0)
+    rng = np.random.default_rng(n + nreal)
+    L = max(3.0, (n / 0.1) ** (1 / 3))
+    x = rng.uniform(0, L, (n, 3))
+    if n >= 4:   # borderline pairs: exactly rc apart along an axis, and one ulp inside / outside
+        x[1] = x[0] + np.array([rc, 0, 0])
+        x[2] = x[0] + np.array([0, np.nextafter(rc, 0), 0])
+        x[3] = x[0] + np.array([0, 0, rc - 2e-13])
+    off, idx = eng.nlist(x, rc, nreal, perms)
+    o_off, o_idx = onp.nlist_csr(x, rc, nreal, perms)
+    assert np.array_equal(off, o_off)
+    assert np.array_equal(sort_rows_csr(off, idx), o_idx)
+
+
+@pytest.mark.parametrize("name", ["h2o_cluster", "morphine"])
+def test_pairs_triples_ele_tables(name):
+    from oracle import oracle_np as onp
+    g = load_golden(name)
+    eng, _, P = _engine(g["eles"], list(g["hidden"]), int(g["seed"]))
+    N = len(g["Z"])
+    # a padded set of two molecules: the fixture and its first 2/3 of atoms displaced
+    n2 = (2 * N) // 3
+    xyzs = np.zeros((2, N, 3))
+    Zs = np.zeros((2, N), np.int32)
+    xyzs[0], Zs[0] = g["xyz"], g["Z"]
+    xyzs[1, :n2], Zs[1, :n2] = g["xyz"][:n2] * 1.03, g["Z"][:n2]
+    nat = np.array([N, n2])
+    rad, ang, mil_j, mil_jk = eng.pairs_triples_ele(xyzs, Zs, nat, nat, P["AN1_r_Rc"], P["AN1_a_Rc"])
+    from oracle import oracle_graph as og
+    eles_np, elep_np = og.elements_and_pairs(g["eles"])
+    o_rad, o_ang, o_mil_j, o_mil_jk = onp.build_pairs_and_triples_with_ele_index_periodic(xyzs, nat, nat, Zs, P["AN1_r_Rc"], P["AN1_a_Rc"], eles_np, elep_np)
+    assert np.array_equal(rad, o_rad.astype(np.int64))
+    assert np.array_equal(ang, o_ang.astype(np.int64))
+    assert np.array_equal(mil_j, o_mil_j.astype(np.int64))
+    assert np.array_equal(mil_jk, o_mil_jk.astype(np.int64))
+    # first molecule against the golden oracle tables
+    assert np.array_equal(rad[rad[:, 0] == 0], g["oracle_rad_p_ele"])
+    assert np.array_equal(ang[ang[:, 0] == 0], g["oracle_ang_t_elep"])
+
+
+# ---------------------------------------------------------------------------------------- fused evaluation
+@pytest.mark.parametrize("name", ["h2o_cluster", "morphine"])
+def test_eval_aperiodic_golden(name):
+    g = load_golden(name)
+    eng, _, _ = _engine(g["eles"], list(g["hidden"]), int(g["seed"]))
+    N = len(g["Z"])
+    r = eng.evaluate(g["xyz"][None], g["Z"][None], np.array([N]), descriptors=True)
+    _check_desc(r["descriptors"][0], g["ref_sym"])             # reference-native pin (MolEmb.Make_ANI1_Sym)
+    _check_desc(r["descriptors"][0], g["oracle_descriptors"][0])
+    for k in ("Etotal", "Ebp", "Ecc", "Evdw"):
+        _check_energy(r[k], g["oracle_" + k], k)
+    assert np.abs(r["charge"] - g["oracle_charge"]).max() <= 1e-5 * max(np.abs(g["oracle_charge"]).max(), 1e-3)
+    assert np.abs(r["Ebp_atom"] - g["oracle_Ebp_atom"]).max() <= 1e-5 * np.abs(g["oracle_Ebp_atom"]).max()
+    assert np.abs(r["dipole"] - g["oracle_dipole"]).max() <= 1e-5 * max(np.abs(g["oracle_dipole"]).max(), 1e-2)
+    _check_grad(r["gradient"], g["oracle_gradient"])
+
+
+def test_eval_periodic_golden_images_and_lattice():
+    from oracle import oracle_np as onp
+    g = load_golden("water_tiny_periodic")
+    eng, _, P = _engine(g["eles"], list(g["hidden"]), int(g["seed"]))
+    nreal = len(g["Z"])
+    Zt, Xt = onp.tess_lattice(g["lattice"], g["Z"].astype(np.uint8), g["xyz"], P["EECutoffOff"])
+    r1 = eng.evaluate_images(Xt, Zt.astype(np.int32), nreal, descriptors=True)
+    r2 = eng.evaluate_lattice(g["xyz"], g["Z"], g["lattice"], int(g["ntess"]), descriptors=True)
+    for r in (r1, r2):
+        _check_desc(r["descriptors"][0], g["ref_sym"])
+        _check_desc(r["descriptors"][0], g["oracle_descriptors"][0])
+        for k in ("Etotal", "Ebp", "Ecc", "Evdw"):
+            _check_energy(r[k], g["oracle_" + k], k)
+        assert np.abs(r["charge"][:, :nreal] - g["oracle_charge"]).max() <= 1e-5 * max(np.abs(g["oracle_charge"]).max(), 1e-3)
+        assert np.array_equal(r["charge"][0, nreal:2 * nreal], r["charge"][0, :nreal])      # tiling (TFMolInstanceDirect.py:5892)
+        _check_grad(r["gradient"], g["oracle_gradient"])
+    assert np.array_equal(r1["gradient"], r1["gradient"])
+
+
+def test_eval_set_of_molecules_vs_oracle():
+    """EvalBPDirectEEUpdateSet contract: molecules of different size padded to MaxNAtoms."""
+    from oracle import oracle_graph as og
+    g = load_golden("morphine")
+    hidden = [64, 64]
+    eng, W, P = _engine(g["eles"], hidden, 5)
+    N = len(g["Z"])
+    rng = np.random.default_rng(7)
+    nmol = 5
+    xyzs = np.zeros((nmol, N, 3))
+    Zs = np.zeros((nmol, N), np.int32)
+    nat = np.array([N, N - 7, N, 3, N - 1])
+    for m in range(nmol):
+        xyzs[m, :nat[m]] = g["xyz"][:nat[m]] + 0.05 * rng.standard_normal((nat[m], 3))
+        Zs[m, :nat[m]] = g["Z"][:nat[m]]
+    r = eng.evaluate(xyzs, Zs, nat, descriptors=True)
+    o = og.Oracle(g["eles"], W, P).evaluate(xyzs, Zs, nat)
+    _check_desc(r["descriptors"], o["descriptors"])
+    for k in ("Etotal", "Ebp", "Ecc", "Evdw"):
+        _check_energy(r[k], o[k], k)
+    assert np.abs(r["charge"] - o["charge"]).max() <= 1e-5 * max(np.abs(o["charge"]).max(), 1e-3)   # includes the padded slots (Q11)
+    _check_grad(r["gradient"], o["gradient"])
+
+
+def test_eval_water_box_periodic_vs_oracle():
+    """216-water periodic box (648 atoms, L=18.6 A > 15 A so ntess=1, 27 images)."""
+    from oracle import oracle_graph as og
+    from oracle import oracle_np as onp
+    Z, X, lat = water_box(6)
+    hidden = [128, 96, 64]
+    eng, W, P = _engine([1, 8], hidden, 11)
+    Xw = onp.modulo_lattice(lat, X)
+    r = eng.evaluate_lattice(Xw, Z, lat, 1, descriptors=True)
+    Zt, Xt = onp.tess_lattice(lat, Z.astype(np.uint8), Xw, P["EECutoffOff"])
+    assert len(Zt) == 27 * len(Z)
+    o = og.Oracle([1, 8], W, P).evaluate_periodic(Xt, Zt, len(Z))
+    _check_desc(r["descriptors"][0], o["descriptors"][0])
+    for k in ("Etotal", "Ebp", "Ecc", "Evdw"):
+        _check_energy(r[k], o[k], k)
+    _check_grad(r["gradient"], o["gradient"][:, :len(Z)])
+
+
+def test_energy_only_and_no_ecc_flags():
+    from oracle import oracle_graph as og
+    g = load_golden("h2o_cluster")
+    eng, W, P = _engine(g["eles"], list(g["hidden"]), int(g["seed"]), params={"AddEcc": False})
+    N = len(g["Z"])
+    r = eng.evaluate(g["xyz"][None], g["Z"][None], np.array([N]), do_force=False)
+    o = og.Oracle(g["eles"], W, P).evaluate(g["xyz"][None], g["Z"][None], np.array([N]))
+    _check_energy(r["Etotal"], o["Etotal"], "Etotal(AddEcc=False)")
+    assert r["Ecc"][0] == 0.0
+    assert np.all(r["gradient"] == 0.0)
+    r = eng.evaluate(g["xyz"][None], g["Z"][None], np.array([N]))
+    _check_grad(r["gradient"], o["gradient"])
+
+
+def test_unknown_element_and_missing_weights_fail_loudly():
+    from oracle import oracle_graph as og
+    from tensormol_b200._lib import TMolB200Error
+    from tensormol_b200.engine import Engine
+    eng = Engine([1, 8], [16], og.default_params())
+    x = np.zeros((1, 2, 3))
+    x[0, 1, 0] = 1.0
+    with pytest.raises(TMolB200Error):
+        eng.evaluate(x, np.array([[1, 8]], np.int32), np.array([2]))          # weights not set
+    eng2, _, _ = _engine([1, 8], [16], 0)
+    with pytest.raises(TMolB200Error):
+        eng2.evaluate(x, np.array([[1, 6]], np.int32), np.array([2]))         # carbon is not in eles
