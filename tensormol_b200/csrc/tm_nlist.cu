@@ -241,7 +241,7 @@ __global__ void k_scatter(const int32_t* __restrict__ cellid, const int32_t* __r
 // one thread per cell: order the cell's slots ascending (removes the atomic-arrival nondeterminism),
 // then write the 32-byte SAtom records in sorted order.
 __global__ void k_cell_sort_gather(const GridParams* __restrict__ gp, const int32_t* __restrict__ cstart, int32_t* __restrict__ sorted,
-                                   const double* __restrict__ pos, const int32_t* __restrict__ Z, const DevParams* __restrict__ dp,
+                                   const double* __restrict__ pos, const int32_t* __restrict__ Z, const __grid_constant__ DevParams P,
                                    SAtom* __restrict__ sat, int32_t* __restrict__ sidx_of_slot) {
   int ncells = gp->ncells;
   for (int cid = blockIdx.x * blockDim.x + threadIdx.x; cid < ncells; cid += gridDim.x * blockDim.x) {
@@ -258,7 +258,7 @@ __global__ void k_cell_sort_gather(const GridParams* __restrict__ gp, const int3
       a.x = pos[3 * (int64_t)s]; a.y = pos[3 * (int64_t)s + 1]; a.z = pos[3 * (int64_t)s + 2];
       a.slot = s;
       int z = Z[s], ei = -1;
-      for (int k = 0; k < dp->n_ele; k++) if (dp->eles[k] == z) ei = k;
+      for (int k = 0; k < P.n_ele; k++) if (P.eles[k] == z) ei = k;
       a.e = ei;
       sat[i] = a;
       sidx_of_slot[s] = i;
@@ -298,7 +298,7 @@ int tm_launch_nlist_build(tm_ctx* c, const SysView& s, double rc_grid) {
   int cblocks = (int)((s.ncells_cap + 127) / 128);
   if (cblocks > 148 * 16) cblocks = 148 * 16;
   k_cell_sort_gather<<<cblocks, 128, 0, c->stream>>>(gp, (const int32_t*)c->b_cstart.p, (int32_t*)c->b_sorted.p, (const double*)c->b_pos.p,
-                                                     (const int32_t*)c->b_Z.p, c->dp, (SAtom*)c->b_satom.p, (int32_t*)c->b_rank.p);
+                                                     (const int32_t*)c->b_Z.p, c->hp, (SAtom*)c->b_satom.p, (int32_t*)c->b_rank.p);
   c->launches += 2;
   TM_CUDA(cudaGetLastError());
   return TM_OK;

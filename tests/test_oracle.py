@@ -1,0 +1,203 @@
+"""CPU tests that pin the ORACLE (oracle/) before it is trusted as the checker:
+  * neighbour lists against lists produced by the reference's own MolEmb.Make_NListNaive (golden fixtures,
+    and live against oracle/_ref when that build is present),
+  * descriptors and descriptor Jacobians against MolEmb.Make_ANI1_Sym / Make_ANI1_Sym_deri (golden),
+  * the index assembly against a literal loop transcription of Neighbors.py on a tiny case,
+  * closed-form constants and finite differences of the oracle energy.
+"""
+import glob
+import importlib.util
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT, load_golden
+from oracle import oracle_graph as og
+from oracle import oracle_np as onp
+from tensormol_b200.engine import descriptor_width, random_weights
+
+
+def _ref_molemb():
+    so = glob.glob(os.path.join(ROOT, "oracle", "_ref", "MolEmb*.so"))
+    if not so:
+        return None
+    spec = importlib.util.spec_from_file_location("MolEmb", so[0])
+    mod = importlib.util.module_from_spec(spec)
+    try:
+        spec.loader.exec_module(mod)
+    except Exception:
+        return None
+    return mod
+
+
+@pytest.mark.parametrize("name", ["h2o_cluster", "morphine"])
+def test_oracle_nlist_vs_reference_golden(name):
+    g = load_golden(name)
+    P = og.default_params()
+    N = len(g["Z"])
+    for rc, tag in ((P["AN1_r_Rc"], "rr"), (P["AN1_a_Rc"], "ra"), (P["EECutoffOff"], "ree")):
+        off, idx = onp.nlist_csr(g["xyz"], rc, N, 1)
+        assert np.array_equal(off, g[f"ref_nl_{tag}_off"]) and np.array_equal(idx, g[f"ref_nl_{tag}_idx"])
+    off, idx = onp.nlist_csr(g["xyz"], P["EECutoffOff"], N, 0)
+    assert np.array_equal(off, g["ref_nl_ree_noperm_off"]) and np.array_equal(idx, g["ref_nl_ree_noperm_idx"])
+
+
+def test_oracle_nlist_periodic_vs_reference_golden():
+    g = load_golden("water_tiny_periodic")
+    P = og.default_params()
+    Zt, Xt = onp.tess_lattice(g["lattice"], g["Z"].astype(np.uint8), g["xyz"], P["EECutoffOff"])
+    assert len(Zt) == (2 * int(g["ntess"]) + 1) ** 3 * len(g["Z"])
+    nreal = len(g["Z"])
+    for rc, tag in ((P["AN1_r_Rc"], "rr"), (P["AN1_a_Rc"], "ra")):
+        off, idx = onp.nlist_csr(Xt, rc, nreal, 1)
+        assert np.array_equal(off, g[f"ref_nl_{tag}_off"]) and np.array_equal(idx, g[f"ref_nl_{tag}_idx"])
+    off, idx = onp.nlist_csr(Xt, P["EECutoffOff"], nreal, 1)
+    assert np.array_equal(np.diff(off), g["ref_nl_ree_count"])
+
+
+def test_oracle_nlist_vs_live_reference_build():
+    M = _ref_molemb()
+    if M is None:
+        pytest.skip("oracle/_ref/MolEmb not built here (make -C oracle ref)")
+    rng = np.random.default_rng(5)
+    for n, nreal, rc, perms in [(300, 300, 4.6, 1), (300, 100, 3.1, 1), (300, 100, 3.1, 0), (900, 900, 4.6, 0), (64, 64, 15.0, 1)]:
+        x = rng.uniform(0, (n / 0.1) ** (1 / 3), (n, 3))
+        x[1] = x[0] + np.array([rc, 0, 0])
+        x[2] = x[0] + np.array([0, np.nextafter(rc, 0), 0])
+        ref = M.Make_NListNaive(np.ascontiguousarray(x), float(rc), int(nreal), int(perms))
+        mine = onp.make_nlist_naive(x, rc, nreal, perms)
+        assert [sorted(r) for r in ref] == mine
+
+
+@pytest.mark.parametrize("name", ["h2o_cluster", "morphine"])
+def test_oracle_descriptors_vs_reference_molemb(name):
+    g = load_golden(name)
+    P = og.default_params()
+    W = random_weights(list(g["eles"]), descriptor_width(len(g["eles"]), P), list(g["hidden"]), int(g["seed"]))
+    o = og.Oracle(g["eles"], W, P).evaluate(g["xyz"][None], g["Z"][None], np.array([len(g["Z"])]))
+    assert np.abs(o["descriptors"][0] - g["ref_sym"]).max() < 1e-11      # reference-native pin
+    # regression against the stored oracle outputs
+    for k in ("Etotal", "Ebp", "Ecc", "Evdw", "charge", "gradient"):
+        assert np.allclose(o[k], g["oracle_" + k], rtol=1e-10, atol=1e-13), k
+
+
+def test_oracle_descriptor_jacobian_vs_reference_molemb():
+    g = load_golden("h2o_cluster")
+    P = og.default_params()
+    N = len(g["Z"])
+    eles_np, elep_np = og.elements_and_pairs(g["eles"])
+    x = g["xyz"][None]
+    Zs = g["Z"][None].astype(np.int64)
+    nat = np.array([N])
+    rp, tt, _, _ = onp.build_pairs_and_triples_with_ele_index(x, nat, nat, Zs, P["AN1_r_Rc"], P["AN1_a_Rc"], eles_np, elep_np)
+    R = torch.tensor(x, dtype=torch.float64, requires_grad=True)
+    GM = og.descriptors(R, torch.as_tensor(rp.astype(np.int64)), torch.as_tensor(tt.astype(np.int64)), P, len(g["eles"]), elep_np.shape[0], N)
+    ref = g["ref_sym_deri"]                      # (N, D, 3N)
+    rng = np.random.default_rng(0)
+    for _ in range(40):
+        i, d = int(rng.integers(N)), int(rng.integers(GM.shape[2]))
+        (gr,) = torch.autograd.grad(GM[0, i, d], R, retain_graph=True)
+        assert np.abs(gr.numpy().reshape(-1) - ref[i, d]).max() < 1e-8
+
+
+def test_oracle_forces_are_the_gradient_of_its_energy():
+    g = load_golden("h2o_cluster")
+    P = og.default_params()
+    W = random_weights(list(g["eles"]), descriptor_width(len(g["eles"]), P), [24, 16], 3)
+    orc = og.Oracle(g["eles"], W, P)
+    N = len(g["Z"])
+    x0 = g["xyz"][None].copy()
+    o = orc.evaluate(x0, g["Z"][None], np.array([N]))
+    rng = np.random.default_rng(1)
+    h = 1e-5
+    for _ in range(6):
+        a, d = int(rng.integers(N)), int(rng.integers(3))
+        xp, xm = x0.copy(), x0.copy()
+        xp[0, a, d] += h
+        xm[0, a, d] -= h
+        fd = (orc.energy_only(xp, g["Z"][None], np.array([N]))[0] - orc.energy_only(xm, g["Z"][None], np.array([N]))[0]) / (2 * h)
+        assert abs(fd - o["gradient"][0, a, d]) < 1e-8
+
+
+def test_known_answer_constants():
+    orc = og.Oracle([1, 8], random_weights([1, 8], 256, [4], 0))
+    assert abs(orc.elu_shift - 0.027735738454600072) < 1e-15
+    assert abs(orc.elu_alpha - (-0.009423816979327905)) < 1e-15
+    C6, Rv = og.vdw_constants([1, 6, 7, 8])
+    assert np.allclose(C6, [2.42833773, 30.35422166, 21.33468151, 12.14168866], rtol=1e-8)
+    assert np.allclose(Rv, [1.89161571, 2.74388214, 2.63994721, 2.53601228], rtol=1e-8)
+    eles, pairs = og.elements_and_pairs([8, 1, 6])
+    assert eles.reshape(-1).tolist() == [1, 6, 8]
+    assert pairs.tolist() == [[1, 1], [1, 6], [1, 8], [6, 6], [6, 8], [8, 8]]
+
+
+def _loop_tables(x, Z, rr, ra, eles, elep):
+    """Literal loop transcription of Neighbors.py:117-201 + 344-423 + 440-465 for ONE molecule."""
+    N = len(Z)
+    pair = onp.make_nlist_naive(x, rr, N, 1)
+    tpair = onp.make_nlist_naive(x, ra, N, 1)
+    p, t = [], []
+    for i in range(N):
+        for j in pair[i]:
+            p.append([0, i, j])
+        for j in tpair[i]:
+            for k in tpair[i]:
+                if k > j:
+                    if Z[j] > Z[k]:
+                        t.append([0, i, k, j])
+                    else:
+                        t.append([0, i, j, k])
+    p, t = np.array(p).reshape(-1, 3), np.array(t).reshape(-1, 4)
+    el = [int(e) for e in eles]
+    pl = [el.index(int(Z[r[2]])) for r in p]
+    tl = []
+    for r in t:
+        for l, (a, b) in enumerate(elep):
+            if sorted([int(Z[r[2]]), int(Z[r[3]])]) == sorted([int(a), int(b)]):
+                tl.append(l)
+    trpE = np.concatenate([p, np.array(pl).reshape(-1, 1)], axis=1)
+    trtE = np.concatenate([t, np.array(tl).reshape(-1, 1)], axis=1)
+    trpE = trpE[np.lexsort((trpE[:, 2], trpE[:, 3], trpE[:, 1], trpE[:, 0]))]
+    trtE = trtE[np.lexsort((trtE[:, 2], trtE[:, 3], trtE[:, 4], trtE[:, 1], trtE[:, 0]))]
+
+    def slots(keys):
+        out, prev, c = [], None, 0
+        for k in keys:
+            k = tuple(k)
+            c = c + 1 if k == prev else 0
+            prev = k
+            out.append(c)
+        return np.array(out)
+
+    mil_jk = np.concatenate([trtE[:, [0, 1, 4]], slots(trtE[:, [0, 1, 4]]).reshape(-1, 1)], axis=1)
+    mil_j = np.concatenate([trpE[:, [0, 1, 3]], slots(trpE[:, [0, 1, 3]]).reshape(-1, 1)], axis=1)
+    return trpE, trtE, mil_j, mil_jk
+
+
+def test_index_assembly_vs_loop_transcription():
+    g = load_golden("h2o_cluster")
+    P = og.default_params()
+    eles_np, elep_np = og.elements_and_pairs(g["eles"])
+    N = len(g["Z"])
+    x, Z = g["xyz"], g["Z"].astype(np.int64)
+    a = onp.build_pairs_and_triples_with_ele_index_periodic(x[None], np.array([N]), np.array([N]), Z[None], P["AN1_r_Rc"], P["AN1_a_Rc"], eles_np, elep_np)
+    b = _loop_tables(x, Z, P["AN1_r_Rc"], P["AN1_a_Rc"], eles_np.reshape(-1), elep_np)
+    for u, v in zip(a, b):
+        assert np.array_equal(u.astype(np.int64), v)
+    assert a[0].dtype == np.float64          # quirk Q16
+
+
+def test_tessellation_order_and_modulo():
+    lat = np.array([[9.0, 0, 0], [0.5, 8.0, 0], [0, 0.3, 7.0]])
+    x = np.array([[-1.0, 2.0, 3.0], [10.0, 9.0, 8.0], [4.0, 4.0, 4.0]])
+    w = onp.modulo_lattice(lat, x)
+    f = w @ np.linalg.inv(lat)
+    assert np.all(f >= -1e-12) and np.all(f < 1 + 1e-12)
+    Zt, Xt = onp.tess_lattice(lat, np.array([1, 1, 8], np.uint8), w, 3.0)
+    assert len(Zt) == 27 * 3 and np.array_equal(Xt[:3], w)
+    # first image block is (i,j,k) = (-1,-1,-1)
+    assert np.allclose(Xt[3:6], w - lat[0] - lat[1] - lat[2])
+    assert np.array_equal(Zt[3:6], [1, 1, 8])
