@@ -150,7 +150,10 @@ def run_b200(args, rank, world, local_rank):
     eng = Engine([1, 8], HIDDEN, P, device=local_rank)
     eng.set_weights(random_weights([1, 8], eng.D, HIDDEN, 0))
     eng.set_gemm_mode(args.gemm_mode)
-    eng.set_stream(C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    # a non-default torch stream shared with the library, so torch.cuda.Event brackets the library's kernels
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    eng.set_stream(C.c_void_p(stream.cuda_stream))
     xyz_t = torch.tensor(X, dtype=torch.float64, device=dev)
     Z_t = torch.tensor(Z, dtype=torch.int32, device=dev)
     e_t = torch.zeros(6, dtype=torch.float64, device=dev)
