@@ -281,7 +281,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--nx", type=int, default=20, help="waters per box edge (20 -> 24,000 atoms)")
-    ap.add_argument("--gemm-mode", type=int, default=0)
+    ap.add_argument("--gemm-mode", type=int, default=1, help="0 = fp32 FFMA, 1 = tcgen05 3xTF32 (default)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -55,7 +55,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if failed:
         sys.stderr.write(log)
         raise RuntimeError("nvcc failed (see tensormol_b200/csrc/build.log)")
-    cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-lcudart", "-lcuda"]
+    cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-lcudart"]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout)

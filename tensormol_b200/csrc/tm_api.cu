@@ -150,7 +150,7 @@ extern "C" void tm_destroy(tm_ctx* c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   DevBuf* all[] = {&c->b_pos, &c->b_Z, &c->b_cellid, &c->b_rank, &c->b_count, &c->b_cstart, &c->b_sorted, &c->b_satom, &c->b_scan_tmp,
-                   &c->b_rowslot, &c->b_rowsidx, &c->b_rowofslot, &c->b_blkcnt, &c->b_rowmeta, &c->b_nbcnt, &c->b_nboff, &c->b_nbr, &c->b_G,
+                   &c->b_rowslot, &c->b_rowsidx, &c->b_rowofslot, &c->b_blkcnt, &c->b_rowmeta, &c->b_nbcnt, &c->b_nboff, &c->b_nbr, &c->b_G, &c->b_Gs,
                    &c->b_delta0, &c->b_delta1, &c->b_dG[0], &c->b_dG[1], &c->b_y[0], &c->b_y[1], &c->b_q, &c->b_qs, &c->b_dedq, &c->b_u, &c->b_F,
                    &c->b_Fpair, &c->b_acc, &c->b_bbox, &c->b_grid, &c->b_flags, &c->b_out, &c->b_molacc, &c->b_natom, &c->b_lattice};
   for (DevBuf* b : all) free_buf(*b);
@@ -163,6 +163,8 @@ extern "C" void tm_destroy(tm_ctx* c) {
         if (N.layers[l].W) cudaFree(N.layers[l].W);
         if (N.layers[l].WT) cudaFree(N.layers[l].WT);
         if (N.layers[l].b) cudaFree(N.layers[l].b);
+        if (N.layers[l].Ws) cudaFree(N.layers[l].Ws);
+        if (N.layers[l].WTs) cudaFree(N.layers[l].WTs);
       }
       if (N.w_out) cudaFree(N.w_out);
     }
@@ -232,6 +234,28 @@ extern "C" int tm_set_weights(tm_ctx* c, int net, int ele_index, int layer, cons
   TM_CUDA(cudaMemcpy(L.W, w.data(), w.size() * 4, cudaMemcpyHostToDevice));
   TM_CUDA(cudaMemcpy(L.WT, wt.data(), wt.size() * 4, cudaMemcpyHostToDevice));
   TM_CUDA(cudaMemcpy(L.b, bb.data(), bb.size() * 4, cudaMemcpyHostToDevice));
+  // hi/lo tf32 planes for the tcgen05 3xTF32 path: hi = rna_tf32(x) (13 low mantissa bits cleared after
+  // rounding to nearest, ties away), lo = x - hi (exact in fp32)
+  auto split = [](const std::vector<float>& src, std::vector<float>& dst) {
+    size_t n = src.size();
+    dst.resize(2 * n);
+    for (size_t i = 0; i < n; i++) {
+      uint32_t u;
+      memcpy(&u, &src[i], 4);
+      u = (u + 0x1000u) & 0xffffe000u;
+      float hi;
+      memcpy(&hi, &u, 4);
+      dst[i] = hi;
+      dst[n + i] = src[i] - hi;
+    }
+  };
+  std::vector<float> ws, wts;
+  split(w, ws);
+  split(wt, wts);
+  if (!L.Ws) TM_CUDA(cudaMalloc(&L.Ws, ws.size() * 4));
+  if (!L.WTs) TM_CUDA(cudaMalloc(&L.WTs, wts.size() * 4));
+  TM_CUDA(cudaMemcpy(L.Ws, ws.data(), ws.size() * 4, cudaMemcpyHostToDevice));
+  TM_CUDA(cudaMemcpy(L.WTs, wts.data(), wts.size() * 4, cudaMemcpyHostToDevice));
   N.set[layer] = true;
   return TM_OK;
 }

@@ -1,9 +1,457 @@
-// tcgen05 (5th-gen tensor core) grouped GEMM back-end for the per-element MLPs.
-// Placeholder until the TMEM/TMA kernel lands: refuses instead of silently falling back.
+// tcgen05 grouped GEMM for the per-element MLPs (sm_100a): 3xTF32 split precision, fp32 accumulate in TMEM.
+//
+//   C[rows,N] = epi( A[rows,K] * B^T ),  A row-major (K contiguous), B given K-major as [N][K]
+//
+// Why 3xTF32: the reference is float64 and the parity bar is 1e-5 relative on the energy
+// (BASELINE.json north_star); single-pass tf32/bf16 misses it (weight rounding is systematic over atoms).
+// Operands are stored pre-split in HBM as two fp32 planes  x = hi + lo,  hi = rna_tf32(x), lo = x - hi
+// (weights once at tm_set_weights, activations by the producing epilogue), and every K-step issues
+//   D += A_hi*B_hi + A_lo*B_hi + A_hi*B_lo            (the dropped lo*lo term is ~2^-22 relative)
+//
+// Structure (one CTA per SM, persistent over a device-side tile list so row counts never visit the host):
+//   warp 0      TMA producer   cp.async.bulk.tensor.2d, 128B swizzle, mbarrier expect_tx       (1 lane)
+//   warp 1      MMA issuer     tcgen05.mma.cta_group::1.kind::tf32, 128 x BN x 8, commit->mbarrier (1 lane)
+//   warps 2..5  epilogue       tcgen05.ld 32x32b.x32 -> bias/activation (or act' product) -> hi/lo split -> global
+// TMEM: 2 accumulator buffers of BN columns (double buffered so the epilogue of tile i overlaps the MMAs of i+1).
 #include "tm_internal.h"
+#include <cuda.h>
+#include <map>
+#include <tuple>
+
+#define TC_BM 128
+#define TC_BK 32                 // 32 fp32 = 128 bytes = one swizzle row
+#define TC_THREADS 320           // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quarter)
+#define TC_EPI_WARPS 8
+#define TC_NACC 4                 // TMEM accumulator buffers (4 x 128 columns = all 512)
+#define TC_CHUNK 1                // k-blocks accumulated inside TMEM before the fp32 register add
+#define TC_MAX_GROUPS (2 * TM_MAX_ELE)
+
+struct alignas(64) TcGroup {
+  CUtensorMap mapA_hi, mapA_lo, mapB_hi, mapB_lo;
+  const float* bias;
+  const float* Hmul_hi;
+  const float* Hmul_lo;
+  float* C_hi;
+  float* C_lo;
+  int ldc, K, N, ele;
+};
+struct alignas(64) TcParams {
+  TcGroup g[TC_MAX_GROUPS];
+  int ngroups, epilogue, act_kind;
+  float act_alpha;
+};
+
+// ------------------------------------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t addr = smem_u32(bar);
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t"
+      "}" ::"r"(addr), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)map) : "memory");
+}
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 %%rx;\n\t"
+      ".reg .pred %%px;\n\t"
+      "elect.sync %%rx|%%px, %1;\n\t"
+      "@%%px mov.s32 %0, 1;\n\t"
+      "}" : "+r"(pred) : "r"(0xffffffffu));
+  return pred;
+}
+// K-major, 128B-swizzled operand tile: rows of 128 bytes, 8-row groups 1024 bytes apart
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3fff);   // start address
+  d |= (uint64_t)1 << 16;                   // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;         // stride byte offset between 8-row groups
+  d |= (uint64_t)1 << 46;                   // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                   // SWIZZLE_128B
+  return d;
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
+        "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
+        "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ float tf32_hi(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+__device__ __forceinline__ float tc_act_fwd(float z, int kind, float alpha) {
+  switch (kind) {
+    case TM_ACT_SIGMOID_WITH_PARAM: {
+      // fast intrinsics: absolute error of log(1+e) <= ~1e-7, i.e. <= 1e-9 on h after the 1/alpha (alpha = 100)
+      float t = alpha * z;
+      return (fmaxf(t, 0.f) + __logf(1.0f + __expf(-fabsf(t)))) * __frcp_rn(alpha);
+    }
+    case TM_ACT_RELU: return fmaxf(z, 0.f);
+    case TM_ACT_SOFTPLUS: return fmaxf(z, 0.f) + log1pf(expf(-fabsf(z)));
+    case TM_ACT_TANH: return tanhf(z);
+    default: return 1.0f / (1.0f + expf(-z));
+  }
+}
+__device__ __forceinline__ float tc_act_bwd(float h, int kind, float alpha) {
+  switch (kind) {
+    case TM_ACT_SIGMOID_WITH_PARAM: return 1.0f - __expf(-alpha * h);
+    case TM_ACT_RELU: return h > 0.f ? 1.f : 0.f;
+    case TM_ACT_SOFTPLUS: return -expm1f(-h);
+    case TM_ACT_TANH: return 1.0f - h * h;
+    default: return h * (1.0f - h);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ kernel
+// EPI: TM_EPI_* (compile time, so each instantiation carries ONE epilogue: the runtime-switched version was
+// 30k SASS instructions and stalled on instruction fetch); ACTK: activation kind or -1 for a runtime switch.
+template <int BN, int STAGES, int EPI, int ACTK>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k_gemm_tc(const __grid_constant__ TcParams P, const int32_t* __restrict__ rowmeta) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  constexpr uint32_t A_BYTES = TC_BM * TC_BK * 4;    // 16 KB per plane
+  constexpr uint32_t B_BYTES = BN * TC_BK * 4;
+  constexpr uint32_t STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = (uint64_t*)(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;     // [TC_NACC]
+  uint64_t* tempty_bar = tfull_bar + TC_NACC;   // [TC_NACC]
+  uint32_t* tmem_slot = (uint32_t*)(tempty_bar + TC_NACC);
+  int* tile_base = (int*)(tmem_slot + 4);       // [TC_MAX_GROUPS+1]
+  int* row_first = tile_base + TC_MAX_GROUPS + 1;   // [TC_MAX_GROUPS]
+  float* tbuf = (float*)(row_first + TC_MAX_GROUPS);  // TC_EPI_WARPS x [32][33] transpose tiles
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    for (int g = 0; g < P.ngroups; g++) {
+      tile_base[g] = acc;
+      int rows = rowmeta[2 * P.g[g].ele + 1];
+      row_first[g] = rowmeta[2 * P.g[g].ele];
+      acc += ((rows + TC_BM - 1) / TC_BM) * (P.g[g].N / BN);
+    }
+    tile_base[P.ngroups] = acc;
+    for (int s = 0; s < STAGES; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int a = 0; a < TC_NACC; a++) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], TC_EPI_WARPS); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {   // TMEM allocation by one warp: 2 accumulators of BN fp32 columns
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)(TC_NACC * BN)));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+  const int total_tiles = tile_base[P.ngroups];
+
+  auto decode = [&](int t, int& g, int& rt, int& ct) {
+    g = 0;
+    while (g + 1 < P.ngroups && t >= tile_base[g + 1]) g++;
+    int local = t - tile_base[g];
+    int nct = P.g[g].N / BN;
+    rt = local / nct;
+    ct = local - rt * nct;
+  };
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      for (int g = 0; g < P.ngroups; g++) {
+        prefetch_tmap(&P.g[g].mapA_hi); prefetch_tmap(&P.g[g].mapA_lo);
+        prefetch_tmap(&P.g[g].mapB_hi); prefetch_tmap(&P.g[g].mapB_lo);
+      }
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        int g, rt, ct;
+        decode(t, g, rt, ct);
+        const TcGroup& G = P.g[g];
+        int row0 = row_first[g] + rt * TC_BM, n0 = ct * BN;
+        int nkb = G.K / TC_BK;
+        for (int kb = 0; kb < nkb; kb++) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* st = smem + stage * STAGE_BYTES;
+          mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+          tma_load_2d(&G.mapA_hi, &full_bar[stage], st, kb * TC_BK, row0);
+          tma_load_2d(&G.mapA_lo, &full_bar[stage], st + A_BYTES, kb * TC_BK, row0);
+          tma_load_2d(&G.mapB_hi, &full_bar[stage], st + 2 * A_BYTES, kb * TC_BK, n0);
+          tma_load_2d(&G.mapB_lo, &full_bar[stage], st + 2 * A_BYTES + B_BYTES, kb * TC_BK, n0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    // The K loop is cut into chunks of TC_CHUNK k-blocks; each chunk accumulates into a fresh TMEM buffer
+    // (ping-pong) that the epilogue warps drain into fp32 REGISTER accumulators with round-to-nearest adds.
+    // Reason: the tensor core adds into its accumulator with truncation, and over a K=512 loop (192 MMA
+    // accumulations per output) that is a systematic ~1.6e-5 relative bias on the energy (measured); 24
+    // accumulations per chunk keep it below 1e-6.
+    if (elect_one()) {
+      // instruction descriptor: D=f32, A=B=tf32, both K-major, N=BN, M=128
+      constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t chunk_it = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        int g, rt, ct;
+        decode(t, g, rt, ct);
+        int nkb = P.g[g].K / TC_BK;
+        for (int kb0 = 0; kb0 < nkb; kb0 += TC_CHUNK, chunk_it++) {
+          int acc = chunk_it % TC_NACC;
+          uint32_t acc_phase = (chunk_it / TC_NACC) & 1;
+          mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+          int kb1 = min(kb0 + TC_CHUNK, nkb);
+          for (int kb = kb0; kb < kb1; kb++) {
+            mbar_wait(&full_bar[stage], phase);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+            uint64_t a_hi = umma_desc(sa), a_lo = umma_desc(sa + A_BYTES);
+            uint64_t b_hi = umma_desc(sa + 2 * A_BYTES), b_lo = umma_desc(sa + 2 * A_BYTES + B_BYTES);
+            // small correction terms first (accumulator still small, so its truncating adds cost nothing),
+            // then the hi*hi terms: only TC_BK/8 full-magnitude accumulations per chunk
+#pragma unroll
+            for (int k = 0; k < TC_BK / 8; k++) {
+              uint64_t koff = (uint64_t)((k * 8 * 4) >> 4);   // 32 bytes per K=8 step inside the 128B swizzle row
+              umma_tf32(d_tmem, a_lo + koff, b_hi + koff, idesc, ((kb - kb0) | k) ? 1u : 0u);
+              umma_tf32(d_tmem, a_hi + koff, b_lo + koff, idesc, 1u);
+            }
+#pragma unroll
+            for (int k = 0; k < TC_BK / 8; k++) {
+              uint64_t koff = (uint64_t)((k * 8 * 4) >> 4);
+              umma_tf32(d_tmem, a_hi + koff, b_hi + koff, idesc, 1u);
+            }
+            umma_commit(&empty_bar[stage]);          // frees the smem stage once these MMAs have read it
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+          umma_commit(&tfull_bar[acc]);              // chunk complete -> epilogue drains it
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..9) =====================
+    // warp%4 selects the TMEM lane quarter (hardware rule); the two warps of a quarter split the BN columns.
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    constexpr int NC = BN / 2;                     // columns per thread
+    const int act_kind = (ACTK >= 0) ? ACTK : P.act_kind;
+    const float act_alpha = P.act_alpha;
+    float* tb = tbuf + (warp - 2) * (32 * 33);
+    uint32_t chunk_it = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      int g, rt, ct;
+      decode(t, g, rt, ct);
+      const TcGroup& G = P.g[g];
+      int nkb = G.K / TC_BK;
+      float accr[NC];
+#pragma unroll
+      for (int i = 0; i < NC; i++) accr[i] = 0.f;
+      for (int kb0 = 0; kb0 < nkb; kb0 += TC_CHUNK, chunk_it++) {
+        int acc = chunk_it % TC_NACC;
+        uint32_t acc_phase = (chunk_it / TC_NACC) & 1;
+        mbar_wait(&tfull_bar[acc], acc_phase);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        uint32_t v[NC];
+#pragma unroll
+        for (int c = 0; c < NC / 32; c++)
+          tmem_ld32(tmem_base + (uint32_t)(acc * BN + half * NC + c * 32) + ((uint32_t)(q * 32) << 16), v + c * 32);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[acc]);   // TMEM buffer is free again; the adds below overlap the next MMAs
+#pragma unroll
+        for (int i = 0; i < NC; i++) accr[i] += __uint_as_float(v[i]);
+      }
+      // Output: thread = row of the warp's 32-row band.  Each 32x32 block goes through a padded shared tile so that
+      // global accesses are 128-byte coalesced row segments (thread-per-row stores cost 32 L1 wavefronts each).
+      int64_t wrow0 = (int64_t)row_first[g] + (int64_t)rt * TC_BM + q * 32;
+      int n0 = ct * BN + half * NC;
+#pragma unroll
+      for (int c = 0; c < NC / 32; c++) {   // unrolled: accr[] indices must be static
+        int64_t off0 = wrow0 * G.ldc + n0 + c * 32;
+        float x[32];
+        if (EPI == TM_EPI_DACT) {
+          // all 64 coalesced row-segment loads in flight at once (latency, not bandwidth, is the cost here)
+          float h1[32], h2[32];
+#pragma unroll
+          for (int r = 0; r < 32; r++) {
+            int64_t o = off0 + (int64_t)r * G.ldc + lane;
+            h1[r] = __ldg(G.Hmul_hi + o);
+            h2[r] = __ldg(G.Hmul_lo + o);
+          }
+#pragma unroll
+          for (int r = 0; r < 32; r++) tb[r * 33 + lane] = h1[r] + h2[r];
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 32; i++) x[i] = accr[c * 32 + i] * tc_act_bwd(tb[lane * 33 + i], act_kind, act_alpha);
+          __syncwarp();
+        } else if (EPI == TM_EPI_ACT) {
+          float bl = G.bias[n0 + c * 32 + lane];
+#pragma unroll
+          for (int i = 0; i < 32; i++) x[i] = tc_act_fwd(accr[c * 32 + i] + __shfl_sync(0xffffffffu, bl, i), act_kind, act_alpha);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; i++) x[i] = accr[c * 32 + i];
+        }
+#pragma unroll
+        for (int i = 0; i < 32; i++) tb[lane * 33 + i] = (EPI == TM_EPI_NONE) ? x[i] : tf32_hi(x[i]);
+        __syncwarp();
+#pragma unroll 4
+        for (int r = 0; r < 32; r++) G.C_hi[off0 + (int64_t)r * G.ldc + lane] = tb[r * 33 + lane];
+        __syncwarp();
+        if (EPI != TM_EPI_NONE) {
+#pragma unroll
+          for (int i = 0; i < 32; i++) tb[lane * 33 + i] = x[i] - tf32_hi(x[i]);
+          __syncwarp();
+#pragma unroll 4
+          for (int r = 0; r < 32; r++) G.C_lo[off0 + (int64_t)r * G.ldc + lane] = tb[r * 33 + lane];
+          __syncwarp();
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(TC_NACC * BN)));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_encodeTiled g_encode = nullptr;
+
+static int get_encode() {
+  if (g_encode) return TM_OK;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || !fn || qres != cudaDriverEntryPointSuccess) {
+    tm_set_error("cuTensorMapEncodeTiled not available from the driver");
+    return TM_ECUDA;
+  }
+  g_encode = (PFN_encodeTiled)fn;
+  return TM_OK;
+}
+
+// 2D fp32 tensor [rows][cols] with row pitch ld (elements); box = 32 x box_rows, 128B swizzle
+static int make_map(CUtensorMap* m, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+  static std::map<std::tuple<const void*, int64_t, int64_t, int64_t, int>, CUtensorMap> cache;
+  auto key = std::make_tuple((const void*)base, rows, cols, ld, box_rows);
+  auto it = cache.find(key);
+  if (it != cache.end()) { *m = it->second; return TM_OK; }
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {TC_BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    tm_set_error("cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld ld=%lld", (int)r, (long long)rows, (long long)cols, (long long)ld);
+    return TM_ECUDA;
+  }
+  if (cache.size() > 4096) cache.clear();
+  cache[key] = *m;
+  return TM_OK;
+}
+
+template <int BN, int STAGES, int EPI, int ACTK>
+static int launch_tc(tm_ctx* c, const TcParams& P, const int* rowmeta_dev, int total_tiles_bound) {
+  constexpr size_t smem = (size_t)STAGES * (2 * TC_BM * TC_BK * 4 + 2 * BN * TC_BK * 4) + 1024 + 512 + TC_EPI_WARPS * 32 * 33 * 4;
+  static bool configured = false;
+  if (!configured) {
+    TM_CUDA(cudaFuncSetAttribute(k_gemm_tc<BN, STAGES, EPI, ACTK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
+  int grid = total_tiles_bound < sms ? total_tiles_bound : sms;
+  if (grid < 1) grid = 1;
+  k_gemm_tc<BN, STAGES, EPI, ACTK><<<grid, TC_THREADS, smem, c->stream>>>(P, rowmeta_dev);
+  c->launches++;
+  TM_CUDA(cudaGetLastError());
+  return TM_OK;
+}
+
+template <int EPI>
+static int launch_tc_act(tm_ctx* c, const TcParams& P, const int* rowmeta_dev, int bound) {
+  if (EPI == TM_EPI_NONE) return launch_tc<128, 3, EPI, 0>(c, P, rowmeta_dev, bound);
+  if (P.act_kind == TM_ACT_SIGMOID_WITH_PARAM) return launch_tc<128, 3, EPI, TM_ACT_SIGMOID_WITH_PARAM>(c, P, rowmeta_dev, bound);
+  return launch_tc<128, 3, EPI, -1>(c, P, rowmeta_dev, bound);
+}
 
 int tm_gemm_tc_launch(tm_ctx* c, const GemmGroup* groups, int ngroups, const int* rowmeta_dev, int max_row_tiles, int epilogue) {
-  (void)c; (void)groups; (void)ngroups; (void)rowmeta_dev; (void)max_row_tiles; (void)epilogue;
-  tm_set_error("tensor-core GEMM mode is not available in this build");
-  return TM_ESTATE;
+  int rc;
+  if (c->gemm_mode != TM_GEMM_TC_3XTF32) { tm_set_error("gemm mode %d is not implemented (use 0 = fp32 or 1 = tcgen05 3xTF32)", c->gemm_mode); return TM_ESTATE; }
+  if ((rc = get_encode())) return rc;
+  if (ngroups > TC_MAX_GROUPS) { tm_set_error("too many GEMM groups"); return TM_EINVAL; }
+  static TcParams P;   // large; filled per launch (calls on one ctx are serialised by contract)
+  P.ngroups = ngroups; P.epilogue = epilogue; P.act_kind = c->hp.activation; P.act_alpha = c->hp.act_alpha;
+  bool all256 = true;
+  int64_t tiles = 0;
+  for (int i = 0; i < ngroups; i++)
+    if (groups[i].N % 256) all256 = false;
+  (void)all256;
+  int BN = 128;   // register accumulators of the epilogue hold 128 columns per thread
+  for (int i = 0; i < ngroups; i++) {
+    const GemmGroup& g = groups[i];
+    if (g.K % TC_BK || g.N % BN || !g.A2 || !g.B2) { tm_set_error("tc gemm: bad group (K=%d N=%d)", g.K, g.N); return TM_EINVAL; }
+    TcGroup& T = P.g[i];
+    if ((rc = make_map(&T.mapA_hi, g.A, g.rows_alloc, g.K, g.lda, TC_BM))) return rc;
+    if ((rc = make_map(&T.mapA_lo, g.A2, g.rows_alloc, g.K, g.lda, TC_BM))) return rc;
+    if ((rc = make_map(&T.mapB_hi, g.B, g.N, g.K, g.ldb, BN))) return rc;
+    if ((rc = make_map(&T.mapB_lo, g.B2, g.N, g.K, g.ldb, BN))) return rc;
+    T.bias = g.bias; T.Hmul_hi = g.Hmul; T.Hmul_lo = g.Hmul2; T.C_hi = g.C; T.C_lo = g.C2;
+    T.ldc = g.ldc; T.K = g.K; T.N = g.N; T.ele = g.ele;
+    tiles += (int64_t)max_row_tiles * (g.N / BN);
+  }
+  int bound = tiles > 100000 ? 100000 : (int)tiles;
+  if (epilogue == TM_EPI_ACT) return launch_tc_act<TM_EPI_ACT>(c, P, rowmeta_dev, bound);
+  if (epilogue == TM_EPI_DACT) return launch_tc_act<TM_EPI_DACT>(c, P, rowmeta_dev, bound);
+  return launch_tc_act<TM_EPI_NONE>(c, P, rowmeta_dev, bound);
 }

@@ -70,6 +70,9 @@ struct Layer {
   float* W = nullptr;    // [Kp][Np] row-major fp32 (zero padded)
   float* WT = nullptr;   // [Np][Kp] (for the backward-data GEMM)
   float* b = nullptr;    // [Np]
+  // hi/lo tf32 split planes for the tcgen05 path: Ws = [W_hi | W_lo] each [Kp][Np]; WTs = [WT_hi | WT_lo] each [Np][Kp]
+  float* Ws = nullptr;
+  float* WTs = nullptr;
 };
 
 struct Net {
@@ -108,14 +111,14 @@ struct tm_ctx {
   DevParams hp;                  // host copy
   DevParams* dp = nullptr;       // device copy
   Net nets[2][TM_MAX_ELE];
-  int gemm_mode = TM_GEMM_FP32;
+  int gemm_mode = TM_GEMM_TC_3XTF32;   // parity-preserving tensor-core path is the default
   int Hp[TM_MAX_HIDDEN];         // padded hidden widths
   int Hmax = 0;
 
   // ---- per-evaluation workspace (grow-only) ----
   DevBuf b_pos, b_Z, b_cellid, b_rank, b_count, b_cstart, b_sorted, b_satom, b_scan_tmp;
   DevBuf b_rowslot, b_rowsidx, b_rowofslot, b_blkcnt, b_rowmeta;
-  DevBuf b_nbcnt, b_nboff, b_nbr, b_G, b_act[2][TM_MAX_HIDDEN], b_delta0, b_delta1, b_dG[2], b_y[2];
+  DevBuf b_nbcnt, b_nboff, b_nbr, b_G, b_Gs, b_act[2][TM_MAX_HIDDEN], b_delta0, b_delta1, b_dG[2], b_y[2];
   DevBuf b_q, b_qs, b_dedq, b_u, b_F, b_Fpair, b_acc, b_bbox, b_grid, b_flags, b_out, b_molacc;
   DevBuf b_natom, b_lattice;
   // host staging (pinned)
@@ -172,6 +175,12 @@ struct GemmGroup {
   float* C;            // [rows][ldc]
   int lda, ldb, ldc, K, N;
   int ele;             // element whose row range this group covers
+  // tensor-core (3xTF32) mode only: the "lo" planes of the hi/lo split operands, B given K-major as [N][K]
+  const float* A2 = nullptr;
+  const float* B2 = nullptr;
+  const float* Hmul2 = nullptr;
+  float* C2 = nullptr;
+  int64_t rows_alloc = 0;
 };
 int tm_launch_gemm(tm_ctx* c, const GemmGroup* groups, int ngroups, const int* rowmeta_dev, int max_row_tiles, int epilogue);
 enum { TM_EPI_ACT = 0, TM_EPI_DACT = 1, TM_EPI_NONE = 2 };

@@ -11,6 +11,7 @@
 // A "group" is one (net, element): rows [rowmeta[2e], +rowmeta[2e+1]) of the row space (padded to
 // TM_ROW_TILE), so tiles never straddle elements and row counts stay on the device.
 #include "tm_internal.h"
+#include <algorithm>
 
 #define FULL 0xffffffffu
 
@@ -161,15 +162,18 @@ int tm_launch_gemm(tm_ctx* c, const GemmGroup* groups, int ngroups, const int* r
   return TM_OK;
 }
 
+
 // ------------------------------------------------------------------------------------------------
-// output layer (H_last -> 1) and its backward seed
+// output layer (H_last -> 1), its backward seed, and the hi/lo split used by the tcgen05 path
 // ------------------------------------------------------------------------------------------------
 struct OutTbl {
   const float* w[2][TM_MAX_ELE];
   float b[2][TM_MAX_ELE];
-  const float* h[2];   // last hidden activation [nrows][ld]
-  float* y[2];         // [nrows]
-  float* delta[2];     // [nrows][ld]
+  const float* h[2];      // last hidden activation [nrows][ld] (hi plane in split mode)
+  const float* h_lo[2];   // lo plane (split mode) or nullptr
+  float* y[2];            // [nrows]
+  float* delta[2];        // [nrows][ld]
+  float* delta_lo[2];
   int ld, H;
 };
 
@@ -181,9 +185,15 @@ __device__ __forceinline__ int row_element(const int32_t* rowmeta, int64_t row, 
   return -1;
 }
 
+__device__ __forceinline__ float tf32_round(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
 // one warp per (row, net): y = h . w + b ; delta = w * a'(h)
 __global__ void k_out_layer(const __grid_constant__ OutTbl T, const int32_t* __restrict__ rowmeta, int64_t nrows, int n_ele, int act_kind,
-                            float act_alpha, int want_delta) {
+                            float act_alpha, int split) {
   int64_t wid = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   int lane = threadIdx.x & 31;
   int net = (int)(wid & 1);
@@ -192,16 +202,26 @@ __global__ void k_out_layer(const __grid_constant__ OutTbl T, const int32_t* __r
   int e = row_element(rowmeta, row, n_ele);
   if (e < 0) { if (lane == 0) T.y[net][row] = 0.f; return; }
   const float* h = T.h[net] + row * T.ld;
+  const float* hl = split ? T.h_lo[net] + row * T.ld : nullptr;
   const float* w = T.w[net][e];
   float* d = T.delta[net] + row * T.ld;
+  float* dl = split ? T.delta_lo[net] + row * T.ld : nullptr;
   float s = 0.f;
   for (int i = lane * 4; i < T.ld; i += 128) {
     float4 hv = *reinterpret_cast<const float4*>(h + i);
+    if (split) {
+      float4 h2 = *reinterpret_cast<const float4*>(hl + i);
+      hv.x += h2.x; hv.y += h2.y; hv.z += h2.z; hv.w += h2.w;
+    }
     float4 wv = *reinterpret_cast<const float4*>(w + i);
     s += hv.x * wv.x + hv.y * wv.y + hv.z * wv.z + hv.w * wv.w;
-    if (want_delta) {
-      float4 dv = make_float4(wv.x * act_bwd_from_h(hv.x, act_kind, act_alpha), wv.y * act_bwd_from_h(hv.y, act_kind, act_alpha),
-                              wv.z * act_bwd_from_h(hv.z, act_kind, act_alpha), wv.w * act_bwd_from_h(hv.w, act_kind, act_alpha));
+    float4 dv = make_float4(wv.x * act_bwd_from_h(hv.x, act_kind, act_alpha), wv.y * act_bwd_from_h(hv.y, act_kind, act_alpha),
+                            wv.z * act_bwd_from_h(hv.z, act_kind, act_alpha), wv.w * act_bwd_from_h(hv.w, act_kind, act_alpha));
+    if (split) {
+      float4 dh = make_float4(tf32_round(dv.x), tf32_round(dv.y), tf32_round(dv.z), tf32_round(dv.w));
+      *reinterpret_cast<float4*>(d + i) = dh;
+      *reinterpret_cast<float4*>(dl + i) = make_float4(dv.x - dh.x, dv.y - dh.y, dv.z - dh.z, dv.w - dh.w);
+    } else {
       *reinterpret_cast<float4*>(d + i) = dv;
     }
   }
@@ -210,27 +230,53 @@ __global__ void k_out_layer(const __grid_constant__ OutTbl T, const int32_t* __r
   if (lane == 0) T.y[net][row] = s + T.b[net][e];
 }
 
+// x -> (hi, lo) planes
+__global__ void k_split_planes(const float* __restrict__ x, float* __restrict__ hi, float* __restrict__ lo, int64_t n4) {
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n4; t += (int64_t)gridDim.x * blockDim.x) {
+    float4 v = reinterpret_cast<const float4*>(x)[t];
+    float4 h = make_float4(tf32_round(v.x), tf32_round(v.y), tf32_round(v.z), tf32_round(v.w));
+    reinterpret_cast<float4*>(hi)[t] = h;
+    reinterpret_cast<float4*>(lo)[t] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+  }
+}
+
+// Buffer planes: every activation / delta buffer is allocated with two planes [hi | lo]; the fp32 mode uses plane 0 only.
 static int ensure_mlp_bufs(tm_ctx* c, const SysView& s) {
   int rc;
   int nh = c->desc.n_hidden;
   for (int net = 0; net < 2; net++) {
     for (int l = 0; l < nh; l++)
-      if ((rc = tm_buf(c, c->b_act[net][l], (size_t)s.nrows * c->Hp[l] * 4))) return rc;
+      if ((rc = tm_buf(c, c->b_act[net][l], (size_t)2 * s.nrows * c->Hp[l] * 4))) return rc;
     if ((rc = tm_buf(c, c->b_y[net], (size_t)s.nrows * 4))) return rc;
     if ((rc = tm_buf(c, c->b_dG[net], (size_t)s.nrows * c->hp.Dp * 4))) return rc;
   }
-  if ((rc = tm_buf(c, c->b_delta0, (size_t)2 * s.nrows * c->Hmax * 4))) return rc;
-  if ((rc = tm_buf(c, c->b_delta1, (size_t)2 * s.nrows * c->Hmax * 4))) return rc;
+  if ((rc = tm_buf(c, c->b_delta0, (size_t)4 * s.nrows * c->Hmax * 4))) return rc;   // [plane][net][nrows*Hmax]
+  if ((rc = tm_buf(c, c->b_delta1, (size_t)4 * s.nrows * c->Hmax * 4))) return rc;
+  if (c->gemm_mode != TM_GEMM_FP32)
+    if ((rc = tm_buf(c, c->b_Gs, (size_t)2 * s.nrows * c->hp.Dp * 4))) return rc;
   return TM_OK;
+}
+
+// delta for hidden layer l (net, plane): buffers alternate with l
+static float* delta_ptr(tm_ctx* c, const SysView& s, int l, int net, int plane) {
+  void* base = (l & 1) ? c->b_delta1.p : c->b_delta0.p;
+  return (float*)base + ((size_t)plane * 2 + net) * s.nrows * c->Hmax;
 }
 
 int tm_launch_mlp_forward(tm_ctx* c, const SysView& s) {
   int rc;
   if ((rc = ensure_mlp_bufs(c, s))) return rc;
+  const bool tc = c->gemm_mode != TM_GEMM_FP32;
   int nh = c->desc.n_hidden, ne = c->hp.n_ele;
-  int max_tiles = (int)((s.ncent_max + TM_ROW_TILE - 1) / TM_ROW_TILE);
-  if (max_tiles < 1) max_tiles = 1;
+  int max_tiles = (int)((s.ncent_max + TM_ROW_TILE - 1) / TM_ROW_TILE) + 1;
   const int* rowmeta = (const int*)c->b_rowmeta.p;
+  const size_t gplane = (size_t)s.nrows * c->hp.Dp;
+  if (tc) {
+    int64_t n4 = (int64_t)gplane / 4;
+    int blocks = (int)std::min<int64_t>((n4 + 255) / 256, 148 * 16);
+    k_split_planes<<<blocks, 256, 0, c->stream>>>((const float*)c->b_G.p, (float*)c->b_Gs.p, (float*)c->b_Gs.p + gplane, n4);
+    c->launches++;
+  }
   for (int l = 0; l < nh; l++) {
     GemmGroup gg[2 * TM_MAX_ELE];
     int ng = 0;
@@ -238,11 +284,21 @@ int tm_launch_mlp_forward(tm_ctx* c, const SysView& s) {
       for (int e = 0; e < ne; e++) {
         const Layer& L = c->nets[net][e].layers[l];
         GemmGroup& g = gg[ng++];
-        g.A = (l == 0) ? (const float*)c->b_G.p : (const float*)c->b_act[net][l - 1].p;
-        g.lda = (l == 0) ? c->hp.Dp : c->Hp[l - 1];
-        g.B = L.W; g.ldb = L.Np; g.bias = L.b; g.Hmul = nullptr;
-        g.C = (float*)c->b_act[net][l].p; g.ldc = L.Np;
-        g.K = L.Kp; g.N = L.Np; g.ele = e;
+        g = GemmGroup();
+        int lda = (l == 0) ? c->hp.Dp : c->Hp[l - 1];
+        size_t aplane = (size_t)s.nrows * lda, cplane = (size_t)s.nrows * L.Np;
+        if (tc) {
+          g.A = (l == 0) ? (const float*)c->b_Gs.p : (const float*)c->b_act[net][l - 1].p;
+          g.A2 = g.A + aplane;
+          g.B = L.WTs; g.B2 = L.WTs + (size_t)L.Np * L.Kp; g.ldb = L.Kp;
+        } else {
+          g.A = (l == 0) ? (const float*)c->b_G.p : (const float*)c->b_act[net][l - 1].p;
+          g.B = L.W; g.ldb = L.Np;
+        }
+        g.lda = lda;
+        g.bias = L.b; g.Hmul = nullptr;
+        g.C = (float*)c->b_act[net][l].p; g.C2 = g.C + cplane; g.ldc = L.Np;
+        g.K = L.Kp; g.N = L.Np; g.ele = e; g.rows_alloc = s.nrows;
       }
     if ((rc = tm_launch_gemm(c, gg, ng, rowmeta, max_tiles, TM_EPI_ACT))) return rc;
   }
@@ -253,32 +309,27 @@ int tm_launch_mlp_forward(tm_ctx* c, const SysView& s) {
       T.b[net][e] = (e < ne) ? c->nets[net][e].b_out : 0.f;
     }
     T.h[net] = (const float*)c->b_act[net][nh - 1].p;
+    T.h_lo[net] = T.h[net] + (size_t)s.nrows * c->Hp[nh - 1];
     T.y[net] = (float*)c->b_y[net].p;
-    T.delta[net] = (float*)((nh % 2) ? c->b_delta0.p : c->b_delta1.p) + (size_t)net * s.nrows * c->Hmax;
+    T.delta[net] = delta_ptr(c, s, nh - 1, net, 0);
+    T.delta_lo[net] = delta_ptr(c, s, nh - 1, net, 1);
   }
   T.ld = c->Hp[nh - 1];
   T.H = c->desc.hidden[nh - 1];
   int64_t nw = s.nrows * 2;
   int blocks = (int)((nw * 32 + 255) / 256);
-  k_out_layer<<<blocks, 256, 0, c->stream>>>(T, (const int32_t*)c->b_rowmeta.p, s.nrows, ne, c->hp.activation, c->hp.act_alpha, 1);
+  k_out_layer<<<blocks, 256, 0, c->stream>>>(T, (const int32_t*)c->b_rowmeta.p, s.nrows, ne, c->hp.activation, c->hp.act_alpha, tc ? 1 : 0);
   c->launches++;
   TM_CUDA(cudaGetLastError());
   return TM_OK;
 }
 
-// delta buffers ping-pong: delta for hidden layer l lives in (l odd ? delta1 : delta0) ... chosen so that
-// the seed written by k_out_layer (layer nh-1) is in buffer ((nh-1) & 1).
 int tm_launch_mlp_backward(tm_ctx* c, const SysView& s) {
   int rc;
+  const bool tc = c->gemm_mode != TM_GEMM_FP32;
   int nh = c->desc.n_hidden, ne = c->hp.n_ele;
-  int max_tiles = (int)((s.ncent_max + TM_ROW_TILE - 1) / TM_ROW_TILE);
-  if (max_tiles < 1) max_tiles = 1;
+  int max_tiles = (int)((s.ncent_max + TM_ROW_TILE - 1) / TM_ROW_TILE) + 1;
   const int* rowmeta = (const int*)c->b_rowmeta.p;
-  auto dbuf = [&](int l, int net) -> float* {
-    // layer l's delta buffer; must match the seed placement in tm_launch_mlp_forward
-    void* base = (((nh - 1 - l) % 2) == 0) ? ((nh % 2) ? c->b_delta0.p : c->b_delta1.p) : ((nh % 2) ? c->b_delta1.p : c->b_delta0.p);
-    return (float*)base + (size_t)net * s.nrows * c->Hmax;
-  };
   for (int l = nh - 1; l >= 0; l--) {
     GemmGroup gg[2 * TM_MAX_ELE];
     int ng = 0;
@@ -286,12 +337,16 @@ int tm_launch_mlp_backward(tm_ctx* c, const SysView& s) {
       for (int e = 0; e < ne; e++) {
         const Layer& L = c->nets[net][e].layers[l];
         GemmGroup& g = gg[ng++];
-        g.A = dbuf(l, net); g.lda = c->Hp[l];
-        g.B = L.WT; g.ldb = L.Kp; g.bias = nullptr;
-        g.K = L.Np; g.N = L.Kp; g.ele = e;
+        g = GemmGroup();
+        g.A = delta_ptr(c, s, l, net, 0); g.A2 = delta_ptr(c, s, l, net, 1); g.lda = c->Hp[l];
+        if (tc) { g.B = L.Ws; g.B2 = L.Ws + (size_t)L.Kp * L.Np; g.ldb = L.Np; }   // [N'=Kp][K'=Np], K-major
+        else { g.B = L.WT; g.ldb = L.Kp; }
+        g.bias = nullptr;
+        g.K = L.Np; g.N = L.Kp; g.ele = e; g.rows_alloc = s.nrows;
         if (l > 0) {
           g.Hmul = (const float*)c->b_act[net][l - 1].p;
-          g.C = dbuf(l - 1, net); g.ldc = c->Hp[l - 1];
+          g.Hmul2 = g.Hmul + (size_t)s.nrows * c->Hp[l - 1];
+          g.C = delta_ptr(c, s, l - 1, net, 0); g.C2 = delta_ptr(c, s, l - 1, net, 1); g.ldc = c->Hp[l - 1];
         } else {
           g.Hmul = nullptr;
           g.C = (float*)c->b_dG[net].p; g.ldc = c->hp.Dp;

@@ -120,10 +120,14 @@ def test_pairs_triples_ele_tables(name):
 
 
 # ---------------------------------------------------------------------------------------- fused evaluation
+GEMM_MODES = [0, 1]    # 0 = fp32 FFMA tiles, 1 = tcgen05 3xTF32 (library default)
+
+
+@pytest.mark.parametrize("mode", GEMM_MODES)
 @pytest.mark.parametrize("name", ["h2o_cluster", "morphine"])
-def test_eval_aperiodic_golden(name):
+def test_eval_aperiodic_golden(name, mode):
     g = load_golden(name)
-    eng, _, _ = _engine(g["eles"], list(g["hidden"]), int(g["seed"]))
+    eng, _, _ = _engine(g["eles"], list(g["hidden"]), int(g["seed"]), gemm_mode=mode)
     N = len(g["Z"])
     r = eng.evaluate(g["xyz"][None], g["Z"][None], np.array([N]), descriptors=True)
     _check_desc(r["descriptors"][0], g["ref_sym"])             # reference-native pin (MolEmb.Make_ANI1_Sym)
@@ -136,10 +140,11 @@ def test_eval_aperiodic_golden(name):
     _check_grad(r["gradient"], g["oracle_gradient"])
 
 
-def test_eval_periodic_golden_images_and_lattice():
+@pytest.mark.parametrize("mode", GEMM_MODES)
+def test_eval_periodic_golden_images_and_lattice(mode):
     from oracle import oracle_np as onp
     g = load_golden("water_tiny_periodic")
-    eng, _, P = _engine(g["eles"], list(g["hidden"]), int(g["seed"]))
+    eng, _, P = _engine(g["eles"], list(g["hidden"]), int(g["seed"]), gemm_mode=mode)
     nreal = len(g["Z"])
     Zt, Xt = onp.tess_lattice(g["lattice"], g["Z"].astype(np.uint8), g["xyz"], P["EECutoffOff"])
     r1 = eng.evaluate_images(Xt, Zt.astype(np.int32), nreal, descriptors=True)
@@ -160,7 +165,7 @@ def test_eval_set_of_molecules_vs_oracle():
     from oracle import oracle_graph as og
     g = load_golden("morphine")
     hidden = [64, 64]
-    eng, W, P = _engine(g["eles"], hidden, 5)
+    eng, W, P = _engine(g["eles"], hidden, 5, gemm_mode=1)
     N = len(g["Z"])
     rng = np.random.default_rng(7)
     nmol = 5
@@ -179,13 +184,13 @@ def test_eval_set_of_molecules_vs_oracle():
     _check_grad(r["gradient"], o["gradient"])
 
 
-def test_eval_water_box_periodic_vs_oracle():
+@pytest.mark.parametrize("mode,hidden", [(0, [128, 96, 64]), (1, [128, 96, 64]), (1, [500, 500, 500])])
+def test_eval_water_box_periodic_vs_oracle(mode, hidden):
     """216-water periodic box (648 atoms, L=18.6 A > 15 A so ntess=1, 27 images)."""
     from oracle import oracle_graph as og
     from oracle import oracle_np as onp
     Z, X, lat = water_box(6)
-    hidden = [128, 96, 64]
-    eng, W, P = _engine([1, 8], hidden, 11)
+    eng, W, P = _engine([1, 8], hidden, 11, gemm_mode=mode)
     Xw = onp.modulo_lattice(lat, X)
     r = eng.evaluate_lattice(Xw, Z, lat, 1, descriptors=True)
     Zt, Xt = onp.tess_lattice(lat, Z.astype(np.uint8), Xw, P["EECutoffOff"])
