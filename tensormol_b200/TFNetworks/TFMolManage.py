@@ -1,0 +1,251 @@
+"""The manager the drivers' closures call (reference: TFNetworks/TFMolManage.py:33-63, 1260-1465).
+
+`TFMolManage(Name_, TData_, Train_, NetType_, RandomTData_, Trainable_)` keeps the reference's constructor and the
+`EvalBPDirectEE*` methods with their return tuples; the TensorFlow instance behind them is replaced by one
+tensormol_b200.engine.Engine (CUDA).  Pair/triple tables are NOT built on the host for these calls -- the fused
+library call does neighbour search, descriptors, nets, electrostatics and forces on the device.
+
+Weights: the reference restores a TensorFlow checkpoint (TFMolInstanceDirect.py:5765), which cannot be read here.
+Extensions: `InitRandom(seed)`, `SetWeights(dict)`, `SaveWeights(path)` / `LoadWeights(path)` (npz), and automatic
+loading of  PARAMS["networks_directory"]/<Name_>.npz  when Name_ is given.
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+
+from ..Containers.Mol import Mol
+from ..Containers.Sets import MSet
+from ..Util import *   # noqa: F401,F403
+from ..engine import Engine, element_pairs, random_weights
+
+SUPPORTED_NETTYPES = ("fc_sqdiff_BP_Direct_EE_ChargeEncode_Update_vdw_DSF_elu_Normalize_Dropout",
+                      "fc_sqdiff_BP_Direct_EE_ChargeEncode_Update_vdw_DSF_elu_Normalize",
+                      "fc_sqdiff_BP_Direct_EE_ChargeEncode_Update_vdw_DSF_elu",
+                      "fc_sqdiff_BP_Direct_EE_SymFunction",
+                      "fc_sqdiff_BP_Direct_EandG_SymFunction")
+
+
+class BPInstance:
+    """What `manager.Instances` exposes to scripts (eles_np, eles_pairs_np, ...) plus the CUDA engine."""
+
+    def __init__(self, TData_, NetType_):
+        self.TData = TData_
+        self.NetType = NetType_
+        self.eles, pairs = element_pairs(TData_.eles)
+        self.n_eles = len(self.eles)
+        self.eles_np = np.asarray(self.eles).reshape((self.n_eles, 1))
+        self.eles_pairs = pairs
+        self.eles_pairs_np = np.asarray(pairs)
+        self.HiddenLayers = list(PARAMS["HiddenLayers"])
+        self.Rr_cut = PARAMS["AN1_r_Rc"]
+        self.Ra_cut = PARAMS["AN1_a_Rc"]
+        self.Ree_on = PARAMS["EECutoffOn"]
+        self.Ree_off = PARAMS["EECutoffOff"]
+        self.DSFAlpha = PARAMS["DSFAlpha"]
+        self.elu_width = PARAMS["Elu_Width"]
+        self.inshape = int(self.n_eles * PARAMS["AN1_num_r_Rs"] + len(pairs) * PARAMS["AN1_num_a_Rs"] * PARAMS["AN1_num_a_As"])
+        if self.Ree_on != 0.0:
+            raise Exception("EECutoffOn should equal to zero in DSF_elu")
+        self.engine = Engine(self.eles, self.HiddenLayers, self._params(), device=int(PARAMS.get("B200Device", 0)))
+        self.engine.set_gemm_mode(int(PARAMS.get("B200GemmMode", 1)))
+        self.elu_shift, self.elu_alpha = self.engine.elu_shift, self.engine.elu_alpha
+        self.weights = None
+        self.name = "Mol_" + str(TData_.name) + "_" + str(getattr(TData_.dig, "name", "")) + "_" + NetType_
+
+    @staticmethod
+    def _params():
+        keys = ("AN1_r_Rc", "AN1_a_Rc", "AN1_eta", "AN1_zeta", "AN1_num_r_Rs", "AN1_num_a_Rs", "AN1_num_a_As", "EECutoffOn", "EECutoffOff",
+                "Elu_Width", "Poly_Width", "DSFAlpha", "AddEcc", "sigmoid_alpha", "NeuronType")
+        return {k: PARAMS[k] for k in keys}
+
+    def refresh(self):
+        """The reference re-reads NeuronType / AddEcc / EECutoffOff / Poly_Width from PARAMS at evaluate time."""
+        self.engine.update_params({k: PARAMS[k] for k in ("NeuronType", "AddEcc", "EECutoffOff", "Poly_Width", "sigmoid_alpha")})
+
+    def set_weights(self, w):
+        self.engine.set_weights(w)
+        self.weights = w
+
+
+class TFMolManage:
+    def __init__(self, Name_="", TData_=None, Train_=True, NetType_="fc_sqdiff", RandomTData_=True, Trainable_=True):
+        self.path = PARAMS["networks_directory"]
+        self.TData = TData_
+        self.NetType = NetType_
+        self.n_train = PARAMS.get("max_steps", 0)
+        self.Instances = None
+        self.Trainable = Trainable_
+        self.name = Name_
+        if NetType_ not in SUPPORTED_NETTYPES:
+            raise Exception("Unknown / unsupported Network Type on the B200 path: " + str(NetType_) + "  (supported: " + ", ".join(SUPPORTED_NETTYPES) + ")")
+        if TData_ is None:
+            raise Exception("TFMolManage needs a TensorMolData (element list, MaxNAtoms)")
+        if Train_:
+            raise NotImplementedError("training is outside the B200 hot path (SURVEY.md section 8f, N2); build the manager with Train_=False")
+        self.Instances = BPInstance(TData_, NetType_)
+        self.energy_only = NetType_.endswith("EandG_SymFunction")
+        if Name_:
+            f = os.path.join(self.path, Name_ + ".npz")
+            if os.path.exists(f):
+                self.LoadWeights(f)
+            else:
+                LOGGER.info("No %s; call manager.InitRandom(seed) / SetWeights(...) / LoadWeights(path) before evaluating "
+                            "(TensorFlow checkpoints of the reference cannot be read)", f)
+
+    # ---- weights (extension) -------------------------------------------------------------------
+    def InitRandom(self, seed=0):
+        """Random-init weights with the reference's initialiser statistics (TFInstance.py:277-297)."""
+        I = self.Instances
+        w = random_weights(I.eles, I.inshape, I.HiddenLayers, seed)
+        I.set_weights(w)
+        return w
+
+    def SetWeights(self, weights):
+        """weights = {"charge": {Z: [(W,b), ...]}, "energy": {Z: [(W,b), ...]}}; y = a(xW+b), last layer linear."""
+        self.Instances.set_weights(weights)
+
+    def SaveWeights(self, path=None):
+        path = os.path.join(self.path, self.name + ".npz") if path is None else path
+        os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
+        out = {}
+        for net, d in self.Instances.weights.items():
+            for z, layers in d.items():
+                for l, (W, b) in enumerate(layers):
+                    out[f"{net}/{z}/{l}/W"] = W
+                    out[f"{net}/{z}/{l}/b"] = b
+        np.savez_compressed(path, **out)
+        return path
+
+    def LoadWeights(self, path):
+        d = np.load(path)
+        w = {"charge": {}, "energy": {}}
+        for key in d.files:
+            net, z, l, kind = key.split("/")
+            w[net].setdefault(int(z), {}).setdefault(int(l), {})[kind] = d[key]
+        w = {net: {z: [(ls[l]["W"], ls[l]["b"]) for l in sorted(ls)] for z, ls in dz.items()} for net, dz in w.items()}
+        self.SetWeights(w)
+
+    # ---- marshalling -----------------------------------------------------------------------------
+    def _pad_set(self, mols):
+        nmols = len(mols)
+        maxn = max(m.NAtoms() for m in mols)
+        self.TData.MaxNAtoms = maxn
+        xyzs = np.zeros((nmols, maxn, 3), dtype=np.float64)
+        Zs = np.zeros((nmols, maxn), dtype=np.int32)
+        natom = np.zeros((nmols), dtype=np.int32)
+        for i, mol in enumerate(mols):
+            xyzs[i][:mol.NAtoms()] = mol.coords
+            Zs[i][:mol.NAtoms()] = mol.atoms
+            natom[i] = mol.NAtoms()
+        return xyzs, Zs, natom
+
+    def _check_cutoffs(self, Rr_cut, Ra_cut, Ree_cut=None):
+        I = self.Instances
+        if abs(Rr_cut - I.Rr_cut) > 1e-12 or abs(Ra_cut - I.Ra_cut) > 1e-12:
+            raise Exception("cutoffs passed to Eval* must equal the instance's AN1_r_Rc / AN1_a_Rc")
+        if Ree_cut is not None and abs(Ree_cut - PARAMS["EECutoffOff"]) > 1e-12:
+            raise Exception("Ree_cut must equal PARAMS['EECutoffOff']")
+
+    def _eval_set(self, mols, Rr_cut, Ra_cut, Ree_cut, do_force=True, has_vdw=True):
+        self._check_cutoffs(Rr_cut, Ra_cut, Ree_cut)
+        self.Instances.refresh()
+        xyzs, Zs, natom = self._pad_set(mols)
+        return self.Instances.engine.evaluate(xyzs, Zs, natom, do_force=do_force, has_vdw=has_vdw)
+
+    # ---- aperiodic (TFMolManage.py:1260-1321, 1410-1439) ---------------------------------------------
+    def EvalBPDirectEEUpdateSet(self, mol_set, Rr_cut, Ra_cut, Ree_cut, HasVdw=False):
+        """Returns Etotal, Ebp, [Ebp_atom,] Ecc, [Evdw,] mol_dipole, atom_charge, force (J/mol/A, = -JOULEPERHARTREE * dE/dx)."""
+        r = self._eval_set(mol_set.mols, Rr_cut, Ra_cut, Ree_cut)
+        F = -JOULEPERHARTREE * r["gradient"]   # noqa: F405
+        if not HasVdw:
+            return r["Etotal"], r["Ebp"], r["Ecc"], r["dipole"], r["charge"], F
+        return r["Etotal"], r["Ebp"], r["Ebp_atom"], r["Ecc"], r["Evdw"], r["dipole"], r["charge"], F
+
+    @TMTiming("EvalBPDirectEEUpdateSingle")
+    def EvalBPDirectEEUpdateSingle(self, mol, Rr_cut, Ra_cut, Ree_cut, HasVdw=False):
+        s = MSet()
+        s.mols.append(mol)
+        return self.EvalBPDirectEEUpdateSet(s, Rr_cut, Ra_cut, Ree_cut, HasVdw)
+
+    def EvalBPDirectEELinearSingle(self, mol, Rr_cut, Ra_cut, Ree_cut, HasVdw=False):
+        return self.EvalBPDirectEEUpdateSingle(mol, Rr_cut, Ra_cut, Ree_cut, HasVdw)
+
+    def EvalBPDirectEESingle(self, mol, Rr_cut, Ra_cut, Ree_cut):
+        return self.EvalBPDirectEEUpdateSingle(mol, Rr_cut, Ra_cut, Ree_cut, False)
+
+    def EvalBPDirectEESet(self, mol_set, Rr_cut=None, Ra_cut=None, Ree_cut=None):
+        Rr_cut = PARAMS["AN1_r_Rc"] if Rr_cut is None else Rr_cut
+        Ra_cut = PARAMS["AN1_a_Rc"] if Ra_cut is None else Ra_cut
+        Ree_cut = PARAMS["EECutoffOff"] if Ree_cut is None else Ree_cut
+        return self.EvalBPDirectEEUpdateSet(mol_set, Rr_cut, Ra_cut, Ree_cut, False)
+
+    def EvalBPDirectChargeSingle(self, mol, Rr_cut, Ra_cut, Ree_cut, HasVdw=False):
+        r = self._eval_set([mol], Rr_cut, Ra_cut, Ree_cut, do_force=False)
+        return r["dipole"], r["charge"]
+
+    def EvalBPDirectEandGLinearSingle(self, mol, Rr_cut, Ra_cut):
+        """BP energy and gradient only (no electrostatics): Etotal, Ebp, Ebp_atom, force."""
+        self._check_cutoffs(Rr_cut, Ra_cut)
+        old = PARAMS["AddEcc"]
+        PARAMS["AddEcc"] = False
+        try:
+            r = self._eval_set([mol], Rr_cut, Ra_cut, None, has_vdw=False)
+        finally:
+            PARAMS["AddEcc"] = old
+        return r["Etotal"], r["Ebp"], r["Ebp_atom"], -JOULEPERHARTREE * r["gradient"]   # noqa: F405
+
+    # ---- periodic (TFMolManage.py:1323-1358, 1441-1442) ---------------------------------------------
+    @TMTiming("EvalBPDirectEEUpdateSinglePeriodic")
+    def EvalBPDirectEEUpdateSinglePeriodic(self, mol, Rr_cut, Ra_cut, Ree_cut, nreal, HasVdw=True, DoForce=True, DoCharge=False):
+        """mol holds the real atoms first and then their periodic images (PeriodicForce tessellation)."""
+        self._check_cutoffs(Rr_cut, Ra_cut, Ree_cut)
+        self.Instances.refresh()
+        self.TData.MaxNAtoms = mol.NAtoms()
+        r = self.Instances.engine.evaluate_images(mol.coords, np.asarray(mol.atoms, np.int32), int(nreal), do_force=DoForce, has_vdw=True)
+        if not DoForce:
+            return r["Etotal"]
+        F = -JOULEPERHARTREE * r["gradient"][0][:nreal].reshape(1, nreal, 3)   # noqa: F405
+        if not DoCharge:
+            return r["Etotal"], F
+        return r["Etotal"], F, r["charge"][0][:nreal].reshape(1, nreal)
+
+    def EvalBPDirectEELinearSinglePeriodic(self, mol, Rr_cut, Ra_cut, Ree_cut, nreal, HasVdw=True, DoForce=True, DoCharge=False):
+        return self.EvalBPDirectEEUpdateSinglePeriodic(mol, Rr_cut, Ra_cut, Ree_cut, nreal, HasVdw, DoForce, DoCharge)
+
+    def EvalBPDirectEandGLinearSinglePeriodic(self, mol, Rr_cut, Ra_cut, nreal, DoForce=True):
+        self._check_cutoffs(Rr_cut, Ra_cut)
+        old = PARAMS["AddEcc"]
+        PARAMS["AddEcc"] = False
+        try:
+            self.Instances.refresh()
+            r = self.Instances.engine.evaluate_images(mol.coords, np.asarray(mol.atoms, np.int32), int(nreal), do_force=DoForce, has_vdw=False)
+        finally:
+            PARAMS["AddEcc"] = old
+        if not DoForce:
+            return r["Etotal"]
+        return r["Etotal"], r["Ebp"], r["Ebp_atom"], -JOULEPERHARTREE * r["gradient"]   # noqa: F405
+
+    # ---- periodic, images made on the device (B200 extension) ------------------------------------------
+    def EvalBPDirectEEUpdateSingleLattice(self, atoms, coords_wrapped, lattice, ntess, DoForce=True, DoCharge=False):
+        """Same results as EvalBPDirectEEUpdateSinglePeriodic on Lattice.TessLattice(atoms, coords, rng) but the
+        (2 ntess+1)^3 image blocks are generated on the GPU (tm_eval_lattice)."""
+        self.Instances.refresh()
+        nreal = len(atoms)
+        r = self.Instances.engine.evaluate_lattice(coords_wrapped, np.asarray(atoms, np.int32), lattice, int(ntess), do_force=DoForce, has_vdw=True)
+        if not DoForce:
+            return r["Etotal"]
+        F = -JOULEPERHARTREE * r["gradient"][0].reshape(1, nreal, 3)   # noqa: F405
+        if not DoCharge:
+            return r["Etotal"], F
+        return r["Etotal"], F, r["charge"][0][:nreal].reshape(1, nreal)
+
+    def LatticeForce(self):
+        """A callback for PeriodicForce.BindLatticeForce: f(z, x, lattice, ntess, DoForce) -> (E, F[nreal,3])."""
+        def f(z, x, lattice, ntess, DoForce=True):
+            if DoForce:
+                e, frc = self.EvalBPDirectEEUpdateSingleLattice(z, x, lattice, ntess, True)
+                return e[0], frc[0]
+            return self.EvalBPDirectEEUpdateSingleLattice(z, x, lattice, ntess, False)[0]
+        return f

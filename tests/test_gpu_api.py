@@ -1,0 +1,205 @@
+"""GPU tests of the reference-facing Python surface (TFMolManage Eval* methods, NeighborListSet, MolEmb shim,
+PeriodicForce callbacks, drivers) against the oracle."""
+import numpy as np
+import pytest
+
+from common import ENERGY_RTOL, FORCE_ATOL_HA_BOHR, water_box
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+NET = "fc_sqdiff_BP_Direct_EE_ChargeEncode_Update_vdw_DSF_elu_Normalize_Dropout"
+
+
+def _setup_params(hidden):
+    from tensormol_b200 import PARAMS
+    PARAMS["NeuronType"] = "sigmoid_with_param"
+    PARAMS["sigmoid_alpha"] = 100.0
+    PARAMS["HiddenLayers"] = list(hidden)
+    PARAMS["EECutoffOn"] = 0
+    PARAMS["Elu_Width"] = 4.6
+    PARAMS["EECutoffOff"] = 15.0
+    PARAMS["DSFAlpha"] = 0.18
+    PARAMS["AddEcc"] = True
+    PARAMS["KeepProb"] = [1.0, 1.0, 1.0, 1.0]
+    PARAMS["MDLogTrajectory"] = False
+    return PARAMS
+
+
+def _manager(mols, hidden, seed):
+    from tensormol_b200 import MolDigester, MSet, TensorMolData_BP_Direct_EE_WithEle, TFMolManage
+    _setup_params(hidden)
+    a = MSet("t", center_=False)
+    a.mols = list(mols)
+    d = MolDigester(a.AtomTypes(), name_="ANI1_Sym_Direct", OType_="EnergyAndDipole")
+    tset = TensorMolData_BP_Direct_EE_WithEle(a, d, order_=1, num_indis_=1, type_="mol", WithGrad_=True)
+    manager = TFMolManage("", tset, False, NET, False, False)
+    W = manager.InitRandom(seed)
+    return manager, W
+
+
+def _oracle(eles, W):
+    from oracle import oracle_graph as og
+    return og.Oracle(eles, W, og.default_params())
+
+
+def test_manager_single_matches_oracle_and_units():
+    from tensormol_b200 import PARAMS, Mol
+    from tensormol_b200.PhysicalData import BOHRPERA, JOULEPERHARTREE
+    g = load_golden("h2o_cluster")
+    m = Mol(g["Z"].astype(np.uint8), g["xyz"])
+    manager, W = _manager([m], list(g["hidden"]), int(g["seed"]))
+    out = manager.EvalBPDirectEEUpdateSingle(m, PARAMS["AN1_r_Rc"], PARAMS["AN1_a_Rc"], PARAMS["EECutoffOff"], True)
+    Etotal, Ebp, Ebp_atom, Ecc, Evdw, mol_dipole, atom_charge, force = out
+    assert Etotal.shape == (1,) and force.shape == (1, len(g["Z"]), 3) and atom_charge.shape == (1, len(g["Z"]))
+    assert abs(Etotal[0] - g["oracle_Etotal"][0]) <= ENERGY_RTOL * abs(g["oracle_Etotal"][0])
+    assert abs(Ecc[0] - g["oracle_Ecc"][0]) <= ENERGY_RTOL * max(abs(g["oracle_Ecc"][0]), 1e-3)
+    # force = -JOULEPERHARTREE * dE/dx (J/mol/A)
+    grad = -force / JOULEPERHARTREE
+    assert np.abs(grad - g["oracle_gradient"]).max() / BOHRPERA <= FORCE_ATOL_HA_BOHR
+    assert np.abs(grad - g["oracle_gradient"]).max() <= 2e-4 * np.abs(g["oracle_gradient"]).max()
+    six = manager.EvalBPDirectEEUpdateSingle(m, PARAMS["AN1_r_Rc"], PARAMS["AN1_a_Rc"], PARAMS["EECutoffOff"], False)
+    assert len(six) == 6 and six[0][0] == Etotal[0]
+    dip, q = manager.EvalBPDirectChargeSingle(m, PARAMS["AN1_r_Rc"], PARAMS["AN1_a_Rc"], PARAMS["EECutoffOff"])
+    assert np.allclose(q, atom_charge) and np.abs(dip - g["oracle_dipole"]).max() < 1e-5
+    assert manager.Instances.eles_np.reshape(-1).tolist() == [1, 8]
+    assert manager.Instances.eles_pairs_np.tolist() == [[1, 1], [1, 8], [8, 8]]
+
+
+def test_manager_weights_save_load_round_trip(tmp_path):
+    from tensormol_b200 import PARAMS, Mol
+    g = load_golden("h2o_cluster")
+    m = Mol(g["Z"].astype(np.uint8), g["xyz"])
+    manager, W = _manager([m], [32, 16], 4)
+    e1 = manager.EvalBPDirectEEUpdateSingle(m, PARAMS["AN1_r_Rc"], PARAMS["AN1_a_Rc"], PARAMS["EECutoffOff"], True)[0][0]
+    p = manager.SaveWeights(str(tmp_path / "w.npz"))
+    manager2, _ = _manager([m], [32, 16], 99)
+    manager2.LoadWeights(p)
+    e2 = manager2.EvalBPDirectEEUpdateSingle(m, PARAMS["AN1_r_Rc"], PARAMS["AN1_a_Rc"], PARAMS["EECutoffOff"], True)[0][0]
+    assert e1 == e2
+
+
+def test_manager_periodic_callbacks_match_oracle():
+    from oracle import oracle_np as onp
+    from tensormol_b200 import PARAMS, Mol, PeriodicForce
+    from tensormol_b200.PhysicalData import BOHRPERA, JOULEPERHARTREE
+    g = load_golden("water_tiny_periodic")
+    nreal = len(g["Z"])
+    m = Mol(g["Z"].astype(np.uint8), g["xyz"])
+    manager, W = _manager([m], list(g["hidden"]), int(g["seed"]))
+
+    def EnAndForce(z_, x_, nreal_, DoForce=True):      # the closure of samples/test_h2o.py:1661-1671
+        mtmp = Mol(z_, x_)
+        if DoForce:
+            en, f = manager.EvalBPDirectEEUpdateSinglePeriodic(mtmp, PARAMS["AN1_r_Rc"], PARAMS["AN1_a_Rc"], PARAMS["EECutoffOff"], nreal_, True)
+            return en[0], f[0]
+        return manager.EvalBPDirectEEUpdateSinglePeriodic(mtmp, PARAMS["AN1_r_Rc"], PARAMS["AN1_a_Rc"], PARAMS["EECutoffOff"], nreal_, True, DoForce)[0]
+
+    pf = PeriodicForce(m, g["lattice"])
+    pf.BindForce(EnAndForce, 15.0)
+    x0 = g["xyz"]          # already wrapped
+    e, f = pf(x0)
+    assert abs(e - g["oracle_Etotal"][0]) <= ENERGY_RTOL * abs(g["oracle_Etotal"][0])
+    grad = -f / JOULEPERHARTREE
+    assert np.abs(grad - g["oracle_gradient"][0]).max() / BOHRPERA <= FORCE_ATOL_HA_BOHR
+    assert np.abs(grad - g["oracle_gradient"][0]).max() <= 2e-4 * np.abs(g["oracle_gradient"]).max()
+    e_only, _ = pf(x0, False)
+    assert abs(e_only - e) < 1e-12 * abs(e) + 1e-9
+    # B200 extension: images generated on the device give the same numbers
+    pf2 = PeriodicForce(m, g["lattice"])
+    pf2.BindLatticeForce(manager.LatticeForce(), 15.0)
+    e2, f2 = pf2(x0)
+    assert abs(e2 - e) <= 1e-9 * abs(e) and np.abs(f2 - f).max() <= 1e-6 * np.abs(f).max()
+    out = manager.EvalBPDirectEEUpdateSinglePeriodic(Mol(*pf.lattice.TessLattice(pf.atoms, x0, 15.0)), PARAMS["AN1_r_Rc"], PARAMS["AN1_a_Rc"],
+                                                     PARAMS["EECutoffOff"], nreal, True, True, True)
+    assert out[2].shape == (1, nreal) and np.abs(out[2] - g["oracle_charge"]).max() < 1e-5
+
+
+def test_neighbor_list_set_tables_match_oracle():
+    from oracle import oracle_graph as og
+    from oracle import oracle_np as onp
+    from tensormol_b200 import MolEmb, NeighborListSet, NeighborListSetWithImages
+    g = load_golden("morphine")
+    N = len(g["Z"])
+    xyzs = np.zeros((2, N, 3))
+    Zs = np.zeros((2, N), np.int32)
+    nat = np.array([N, N - 5])
+    xyzs[0], Zs[0] = g["xyz"], g["Z"]
+    xyzs[1, :N - 5], Zs[1, :N - 5] = g["xyz"][:N - 5] + 0.01, g["Z"][:N - 5]
+    eles_np, elep_np = og.elements_and_pairs(g["eles"])
+    NL = NeighborListSet(xyzs, nat, True, True, Zs, sort_=True)
+    rad, ang, mil_jk, jk_max = NL.buildPairsAndTriplesWithEleIndex(4.6, 3.1, eles_np, elep_np)
+    o = onp.build_pairs_and_triples_with_ele_index(xyzs, nat, nat, Zs, 4.6, 3.1, eles_np, elep_np)
+    assert rad.dtype == np.float64
+    assert np.array_equal(rad, o[0]) and np.array_equal(ang, o[1]) and np.array_equal(mil_jk, o[2]) and jk_max == o[3]
+    rad2, ang2, mil_j, mil_jk2 = NL.buildPairsAndTriplesWithEleIndexLinear(4.6, 3.1, eles_np, elep_np)
+    o2 = onp.build_pairs_and_triples_with_ele_index_periodic(xyzs, nat, nat, Zs, 4.6, 3.1, eles_np, elep_np)
+    assert np.array_equal(mil_j, o2[2])
+    NLEE = NeighborListSet(xyzs, nat, False, False, None)
+    ree = NLEE.buildPairs(15.0)
+    o_ree = onp.set_build_pairs(xyzs, nat, nat, 15.0, False)
+    assert ree.dtype == np.uint64
+    key = lambda a: a[np.lexsort((a[:, 2], a[:, 1], a[:, 0]))]   # noqa: E731
+    assert np.array_equal(key(ree.astype(np.int64)), key(o_ree.astype(np.int64)))
+    p, t = NL.buildPairsAndTriples(4.6, 3.1)
+    op, ot = onp.set_build_pairs_and_triples(xyzs, nat, nat, Zs, 4.6, 3.1, True)
+    key4 = lambda a: a[np.lexsort((a[:, 3], a[:, 2], a[:, 1], a[:, 0]))]   # noqa: E731
+    assert np.array_equal(key(p.astype(np.int64)), key(op.astype(np.int64)))
+    assert np.array_equal(key4(t.astype(np.int64)), key4(ot.astype(np.int64)))
+    # images form
+    NLI = NeighborListSetWithImages(xyzs[:1], np.array([N]), np.array([10]), False, True, Zs[:1])
+    both = NLI.buildPairsWithBothEleIndex(15.0, eles_np)
+    ob = onp.build_pairs_with_both_ele_index(xyzs[:1], np.array([N]), np.array([10]), Zs[:1], 15.0, eles_np, True)
+    key5 = lambda a: a[np.lexsort((a[:, 2], a[:, 1]))]   # noqa: E731
+    assert np.array_equal(key5(both), key5(ob))
+    # MolEmb shim returns list-of-lists like the C extension
+    ll = MolEmb.Make_NListNaive(g["xyz"], 4.6, N, 1)
+    off, idx = g["ref_nl_rr_off"], g["ref_nl_rr_idx"]
+    assert [sorted(r) for r in ll] == [idx[off[i]:off[i + 1]].tolist() for i in range(N)]
+    assert [sorted(r) for r in MolEmb.Make_NListLinear(g["xyz"], 4.6, N, 1)] == [sorted(r) for r in ll]
+
+
+def test_nve_md_on_gpu_forces_conserves_energy():
+    """3x3x3 water box, 40 velocity-Verlet steps through PeriodicVelocityVerlet with the device-tessellated force."""
+    from tensormol_b200 import PARAMS, Mol, PeriodicForce, PeriodicVelocityVerlet
+    from tensormol_b200.PhysicalData import JOULEPERHARTREE
+    Z, X, lat = water_box(3, jitter=0.0)
+    m = Mol(Z.astype(np.uint8), X)
+    manager, W = _manager([m], [64, 64], 7)
+    pf = PeriodicForce(m, lat)
+    pf.BindLatticeForce(manager.LatticeForce(), 15.0)
+    PARAMS["MDMaxStep"] = 40
+    PARAMS["MDdt"] = 0.2
+    PARAMS["MDV0"] = None
+    PARAMS["MDThermostat"] = None
+    md = PeriodicVelocityVerlet(pf, "gpu_nve")
+    md.Prop()
+    ke = md.md_log[:, 4] * len(Z)                       # J/mol total (KE is per atom), logged one step behind EPot
+    etot = ke[1:] + md.md_log[:-1, 5] * JOULEPERHARTREE
+    drift = np.ptp(etot[2:])
+    scale = np.ptp(md.md_log[:, 5] * JOULEPERHARTREE) + 1.0
+    assert np.all(np.isfinite(md.md_log)) and drift < 0.05 * scale + 1e-3 * abs(etot[2])
+
+
+def test_geometry_optimizer_lowers_energy_on_gpu_potential():
+    from tensormol_b200 import PARAMS, GeomOptimizer, Mol
+    g = load_golden("h2o_cluster")
+    m = Mol(g["Z"].astype(np.uint8), g["xyz"])
+    manager, W = _manager([m], [32, 32], 9)
+
+    def EnAndForce(x_, DoForce=True):
+        out = manager.EvalBPDirectEEUpdateSingle(Mol(m.atoms, x_), PARAMS["AN1_r_Rc"], PARAMS["AN1_a_Rc"], PARAMS["EECutoffOff"], True)
+        return (out[0][0], out[-1][0]) if DoForce else out[0][0]
+    PARAMS["OptMaxCycles"] = 8
+    e0 = EnAndForce(m.coords, False)
+    out = GeomOptimizer(EnAndForce).Opt(m, "gpuopt")
+    assert EnAndForce(out.coords, False) < e0
+
+
+@pytest.fixture(autouse=True)
+def _tmp_results(tmp_path):
+    from tensormol_b200 import PARAMS
+    old = PARAMS["results_dir"]
+    PARAMS["results_dir"] = str(tmp_path) + "/"
+    yield
+    PARAMS["results_dir"] = old

@@ -1,0 +1,211 @@
+"""CPU tests of the host-side mirror of the reference interface (containers, lattice, drivers, math) on
+analytic potentials -- no GPU, no oracle needed except for the lattice cross-check."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle_np as onp
+from tensormol_b200 import (PARAMS, ConjGradient, GeomOptimizer, Lattice, Mol, MSet, NudgedElasticBand, PeriodicForce,
+                            PeriodicVelocityVerlet, RemoveInvariantForce, VelocityVerlet, HarmonicSpectra, FdiffGradient, KineticEnergy)
+from tensormol_b200.PhysicalData import ATOMICMASSES, IDEALGASR, JOULEPERHARTREE
+
+
+@pytest.fixture(autouse=True)
+def _results_dir(tmp_path):
+    old = PARAMS["results_dir"]
+    PARAMS["results_dir"] = str(tmp_path) + "/"
+    PARAMS["MDLogTrajectory"] = False
+    yield
+    PARAMS["results_dir"] = old
+
+
+def _water():
+    return Mol(np.array([1, 1, 8], np.uint8), np.array([[0.757, 0.586, 0.0], [-0.757, 0.586, 0.0], [0.0, 0.0, 0.0]]))
+
+
+def _spring_potential(pairs, r0, k=0.5):
+    """E (Hartree) = sum k (r-r0)^2 ; force returned in J/mol/A like the manager's callbacks."""
+    def f(x, DoForce=True):
+        E, F = 0.0, np.zeros_like(x)
+        for (i, j), r in zip(pairs, r0):
+            d = x[i] - x[j]
+            n = np.linalg.norm(d)
+            E += k * (n - r) ** 2
+            g = 2 * k * (n - r) * d / n
+            F[i] -= g
+            F[j] += g
+        if DoForce:
+            return E, F * JOULEPERHARTREE
+        return E
+    return f
+
+
+def test_mol_xyz_round_trip(tmp_path):
+    m = _water()
+    m.properties["energy"] = -76.4
+    m.properties["Lattice"] = np.eye(3) * 9.3215
+    m.WriteXYZfile(str(tmp_path), "w", "w", True)
+    m.WriteXYZfile(str(tmp_path), "w", "a", True)
+    s = MSet("w", str(tmp_path) + "/", center_=False)
+    s.ReadXYZ()
+    assert len(s.mols) == 2 and s.MaxNAtoms() == 3 and s.NAtoms() == 6
+    assert np.array_equal(s.mols[1].atoms, m.atoms) and np.allclose(s.mols[1].coords, m.coords)
+    assert abs(s.mols[0].properties["energy"] + 76.4) < 1e-12
+    assert np.allclose(s.mols[0].properties["Lattice"], np.eye(3) * 9.3215)
+    assert s.AtomTypes().tolist() == [1, 8]
+    s.OnlyAtoms([8])
+    assert s.mols[0].NAtoms() == 1
+
+
+def test_lattice_matches_oracle_restatement():
+    lat = np.array([[9.0, 0, 0], [0.5, 8.0, 0], [0, 0.3, 7.0]])
+    L = Lattice(lat)
+    rng = np.random.default_rng(0)
+    x = rng.uniform(-12, 20, (17, 3))
+    assert np.allclose(L.ModuloLattice(x), onp.modulo_lattice(lat, x), atol=1e-12)
+    assert abs(L.latticeMinDiameter - onp.lattice_min_diameter(lat)) < 1e-12
+    z = rng.integers(1, 9, 17).astype(np.uint8)
+    w = L.ModuloLattice(x)
+    for r in (3.0, 15.0):
+        Za, Xa = L.TessLattice(z, w, r)
+        Zb, Xb = onp.tess_lattice(lat, z, w, r)
+        assert np.array_equal(Za, Zb) and np.array_equal(Xa, Xb)
+    assert L.NTess(15.0) == int(15.0 / L.latticeMinDiameter) + 1
+    Zt, Xt = L.TessNTimes(z, w, 2)
+    assert len(Zt) == 8 * 17 and np.allclose(Xt[17:34], w + lat[2])
+
+
+def test_remove_invariant_force():
+    rng = np.random.default_rng(1)
+    x = rng.normal(size=(6, 3))
+    f = rng.normal(size=(6, 3))
+    m = np.array([1, 1, 8, 6, 7, 1.0])
+    x = x - np.einsum("a,ax->x", m, x) / m.sum()          # centre of mass at the origin
+    g = RemoveInvariantForce(x, f, m)
+    assert np.abs(g.sum(0)).max() < 1e-12                 # no net force
+    assert np.abs(np.cross(x, g).sum(0)).max() < 1e-10    # no net torque
+    # angular part: mass-weighted torque removed
+    PARAMS["RemoveInvariant"] = False
+    assert RemoveInvariantForce(x, f, m) is f
+    PARAMS["RemoveInvariant"] = True
+
+
+def test_geom_optimizer_on_springs():
+    m = _water()
+    pairs, r0 = [(0, 2), (1, 2), (0, 1)], [0.96, 0.96, 1.52]
+    f = _spring_potential(pairs, r0)
+    PARAMS["OptMaxCycles"] = 200
+    PARAMS["OptThresh"] = 1e-5
+    out = GeomOptimizer(f).Opt(m, "springs")
+    d = [np.linalg.norm(out.coords[i] - out.coords[j]) for i, j in pairs]
+    assert np.allclose(d, r0, atol=2e-3)
+    assert f(out.coords, False) < 1e-5
+
+
+def test_velocity_verlet_conserves_energy():
+    m = _water()
+    f = _spring_potential([(0, 2), (1, 2), (0, 1)], [0.96, 0.96, 1.52], k=0.3)
+    PARAMS["MDMaxStep"] = 400
+    PARAMS["MDdt"] = 0.2
+    PARAMS["MDV0"] = None
+    PARAMS["MDThermostat"] = None
+    md = VelocityVerlet(None, m, "nve", f)
+    md.Prop()
+    etot = md.md_log[5:, 4] * 3 + (md.md_log[5:, 5]) * JOULEPERHARTREE      # KE is per atom
+    assert np.ptp(etot) < 2e-3 * np.abs(md.md_log[5:, 5] * JOULEPERHARTREE).max() + 50.0
+    assert md.md_log[-1, 0] == pytest.approx(399 * 0.2)
+
+
+def test_nose_thermostat_reaches_temperature():
+    np.random.seed(3)
+    n = 24
+    atoms = np.array([8] * n, np.uint8)
+    x = np.random.normal(size=(n, 3)) * 3
+    f = lambda y, DoForce=True: (0.0, -0.002 * JOULEPERHARTREE * y) if DoForce else 0.0   # noqa: E731
+    PARAMS["MDMaxStep"] = 300
+    PARAMS["MDdt"] = 0.5
+    PARAMS["MDV0"] = "Random"
+    PARAMS["MDTemp"] = 300.0
+    PARAMS["MDThermostat"] = "Nose"
+    md = VelocityVerlet(None, Mol(atoms, x), "nvt", f)
+    T0 = (2. / 3.) * KineticEnergy(md.v, md.m) / IDEALGASR
+    assert T0 == pytest.approx(300.0, rel=1e-6)          # per-atom rescale at start
+    md.Prop()
+    assert md.Tstat.name == "Nose" and np.isfinite(md.KE)
+    PARAMS["MDThermostat"] = None
+    PARAMS["MDV0"] = None
+
+
+def test_neb_finds_barrier_on_double_well():
+    # one "atom" moving in a 2D double well E = (x^2-1)^2 + 2 y^2, plus a spectator far away
+    def f(x, DoForce=True):
+        a, b = x[0, 0], x[0, 1]
+        E = (a * a - 1) ** 2 + 2 * b * b
+        F = np.zeros_like(x)
+        F[0, 0] = -4 * a * (a * a - 1)
+        F[0, 1] = -4 * b
+        return (E, F * JOULEPERHARTREE) if DoForce else E
+    PARAMS["NebSolver"] = "Verlet"
+    PARAMS["NebNumBeads"] = 9
+    PARAMS["OptMaxCycles"] = 200
+    PARAMS["RemoveInvariant"] = False
+    g0 = Mol(np.array([1], np.uint8), np.array([[-1.0, 0.3, 0.0]]))
+    g1 = Mol(np.array([1], np.uint8), np.array([[1.0, 0.3, 0.0]]))
+    neb = NudgedElasticBand(f, g0, g1, "dw", thresh_=1e-3)
+    neb.Opt("dw")
+    PARAMS["RemoveInvariant"] = True
+    assert np.max(neb.Es) == pytest.approx(1.0, abs=0.15)            # barrier height of the double well
+    assert abs(neb.beads[4, 0, 0]) < 0.15                            # middle bead sits near the saddle
+
+
+def test_conj_gradient_and_fdiff():
+    f = lambda x, DoForce=True: ((np.sum((x - 1.0) ** 2)), -2 * (x - 1.0)) if DoForce else np.sum((x - 1.0) ** 2)   # noqa: E731
+    x = np.zeros((2, 3))
+    CG = ConjGradient(f, x)
+    for _ in range(30):
+        x, e, g = CG(x)
+    assert np.allclose(x, 1.0, atol=1e-3)
+    g = FdiffGradient(lambda y: np.sum(y ** 3), np.ones((2, 3)))
+    assert np.allclose(g, 3.0, atol=1e-6)
+
+
+def test_harmonic_spectra_diatomic():
+    k = 0.5    # Hartree/A^2 on the bond
+    at = np.array([1, 1], np.uint8)
+    x0 = np.array([[0.0, 0, 0], [0.74, 0, 0]])
+    E = lambda x: k * (np.linalg.norm(x[0] - x[1]) - 0.74) ** 2   # noqa: E731
+    w, v = HarmonicSpectra(E, x0, at)
+    assert np.sum(np.abs(w) > 100.0) == 1      # one stretch, five zero modes
+    assert w[-1] > 1000.0
+
+
+def test_periodic_force_wrapper_and_md():
+    # LJ-like soft pair force on the tessellated images, computed in numpy
+    def lf(z, x, nreal, DoForce=True):
+        E, F = 0.0, np.zeros((nreal, 3))
+        for i in range(nreal):
+            d = x[i] - x
+            r = np.linalg.norm(d, axis=1)
+            m = (r > 1e-9) & (r < 4.0)
+            w = np.where(np.arange(len(x))[m] < nreal, 1.0, 0.5)
+            E += 0.5 * np.sum(0.01 * (4.0 - r[m]) ** 2)
+            F[i] += np.sum((w * 0.02 * (4.0 - r[m]) / r[m])[:, None] * d[m], axis=0)
+        return (E, F * JOULEPERHARTREE) if DoForce else E
+    rng = np.random.default_rng(2)
+    atoms = np.array([8] * 8, np.uint8)
+    x = rng.uniform(0, 6, (8, 3))
+    pf = PeriodicForce(Mol(atoms, x), np.eye(3) * 6.0)
+    pf.BindForce(lf, 4.0)
+    e, f = pf(pf.mol0.coords)
+    assert f.shape == (8, 3) and np.isfinite(e)
+    e2, _ = pf(pf.mol0.coords + np.array([6.0, 0, 0]))        # invariance under a lattice translation
+    assert e2 == pytest.approx(e, rel=1e-10)
+    assert 0.9 < pf.Density() / (8 * 15.9994 / 6.02214086e23 / (216e-24)) < 1.1
+    PARAMS["MDMaxStep"] = 5
+    PARAMS["MDThermostat"] = None
+    PARAMS["MDV0"] = None
+    md = PeriodicVelocityVerlet(pf, "pmd")
+    md.Prop()
+    assert md.md_log.shape == (5, 7) and np.all(np.isfinite(md.x))
+    assert np.all(pf.lattice.InLat(md.x) >= -1e-9) and np.all(pf.lattice.InLat(md.x) < 1 + 1e-9)
