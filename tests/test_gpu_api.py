@@ -203,3 +203,52 @@ def _tmp_results(tmp_path):
     PARAMS["results_dir"] = str(tmp_path) + "/"
     yield
     PARAMS["results_dir"] = old
+
+
+@pytest.mark.parametrize("world", [1, 2, 3])
+def test_slab_phases_emulated_ranks_match_single_call(world):
+    """The three slab phases of `world` ranks, run one after the other on ONE GPU with the all-reduces emulated by
+    sums, must reproduce tm_eval_lattice (energies 1e-9 relative, gradients to fp32 atomics noise)."""
+    import torch
+    from oracle import oracle_graph as og
+    from tensormol_b200.engine import Engine, random_weights
+    from tensormol_b200.parallel import EngineSlabBackend
+    from tensormol_b200._lib import TM_F_FORCE, TM_F_VDW
+    from tensormol_b200.SystemBuilders import wrap_into_cell
+    Z, X, lat = water_box(5, jitter=0.03)
+    X = wrap_into_cell(X, lat)
+    n = len(Z)
+    P = og.default_params()
+    hidden = [64, 48]
+    W = random_weights([1, 8], 256, hidden, 3)
+    ref_eng = Engine([1, 8], hidden, P)
+    ref_eng.set_weights(W)
+    ref = ref_eng.evaluate_lattice(X, Z, lat, 1)
+    dev = torch.device("cuda", 0)
+    xt = torch.tensor(X, dtype=torch.float64, device=dev)
+    zt = torch.tensor(Z, dtype=torch.int32, device=dev)
+    engines = []
+    for r in range(world):
+        e = Engine([1, 8], hidden, P)
+        e.set_weights(W)
+        engines.append(EngineSlabBackend(e))
+    qraw = [torch.zeros(n, dtype=torch.float64, device=dev) for _ in range(world)]
+    for r, b in enumerate(engines):
+        b.slab_phase_a(xt, zt, n, lat, 1, r, world, qraw[r])
+        b.eng.sync()
+    qsum = torch.stack(qraw).sum(0)
+    es = [torch.zeros(6, dtype=torch.float64, device=dev) for _ in range(world)]
+    for r, b in enumerate(engines):
+        b.slab_phase_b(qsum, es[r])
+        b.eng.sync()
+    esum = torch.stack(es).sum(0)
+    grads = [torch.zeros(n, 3, dtype=torch.float64, device=dev) for _ in range(world)]
+    for r, b in enumerate(engines):
+        b.slab_phase_c(esum, TM_F_FORCE | TM_F_VDW, grads[r])
+        b.eng.sync()
+    g = torch.stack(grads).sum(0).cpu().numpy()
+    e = esum.cpu().numpy()
+    etot = e[1] + e[2] + e[3]
+    assert abs(etot - ref["Etotal"][0]) <= 1e-8 * abs(ref["Etotal"][0])
+    assert abs(e[2] - ref["Ecc"][0]) <= 1e-7 * max(abs(ref["Ecc"][0]), 1e-3)
+    assert np.abs(g - ref["gradient"][0]).max() <= 2e-6 * np.abs(ref["gradient"]).max() + 1e-9
