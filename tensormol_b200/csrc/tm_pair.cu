@@ -83,14 +83,18 @@ __global__ void k_neutralise(const double* __restrict__ qraw_slot, double* __res
   }
 }
 
-// charge per cell-sorted atom (images inherit the charge of slot % nreal, TFMolInstanceDirect.py:5892-5893)
+// Candidate record of the pair kernel, one float4 per cell-sorted atom: position relative to the grid origin in
+// fp32 (only used for the in/out-of-cutoff test, where the kernel vanishes) and the charge (images inherit the
+// charge of slot % nreal, TFMolInstanceDirect.py:5892-5893).
 __global__ void k_q_sorted(const SAtom* __restrict__ sat, const int32_t* __restrict__ cstart, const GridParams* __restrict__ gp,
-                           const double* __restrict__ q_slot, int64_t nreal, int periodic, float* __restrict__ qs) {
-  int ntot = cstart[gp->ncells];
+                           const double* __restrict__ q_slot, int64_t nreal, int periodic, float4* __restrict__ pq) {
+  GridParams g = *gp;
+  int ntot = cstart[g.ncells];
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ntot; i += gridDim.x * blockDim.x) {
-    int s = sat[i].slot;
+    SAtom a = sat[i];
+    int s = a.slot;
     if (periodic) s = (int)(s % nreal);
-    qs[i] = (float)q_slot[s];
+    pq[i] = make_float4((float)(a.x - g.ox), (float)(a.y - g.oy), (float)(a.z - g.oz), (float)q_slot[s]);
   }
 }
 
@@ -99,7 +103,7 @@ int tm_launch_charges(tm_ctx* c, const SysView& s) {
   int64_t nq = s.periodic ? s.nreal : s.nslots;           // slots that carry an own charge
   int64_t nq_per_mol = s.periodic ? s.nreal : s.maxnatom;
   if ((rc = tm_buf(c, c->b_q, (size_t)nq * 8 * 2))) return rc;  // [qraw_slot | q_slot]
-  if ((rc = tm_buf(c, c->b_qs, (size_t)s.nslots * 4))) return rc;
+  if ((rc = tm_buf(c, c->b_qs, (size_t)s.nslots * 16))) return rc;
   double* qraw = (double*)c->b_q.p;
   double* q = qraw + nq;
   // molacc (zeroed by the caller at the start of the evaluation), stride 16 doubles per molecule:
@@ -118,7 +122,7 @@ int tm_launch_charges(tm_ctx* c, const SysView& s) {
                                          s.maxnatom, nq_per_mol, s.nmol, q);
   int b2 = (int)std::min<int64_t>((s.nslots + 255) / 256, 148 * 8);
   k_q_sorted<<<b2, 256, 0, c->stream>>>((const SAtom*)c->b_satom.p, (const int32_t*)c->b_cstart.p, (const GridParams*)c->b_grid.p, q, s.nreal,
-                                        s.periodic, (float*)c->b_qs.p);
+                                        s.periodic, (float4*)c->b_qs.p);
   c->launches += 3;
   TM_CUDA(cudaGetLastError());
   return TM_OK;
@@ -182,12 +186,11 @@ __device__ __forceinline__ void pair_eval(const DevParams& P, float r, float dx,
 }
 
 __global__ void __launch_bounds__(PAIR_WARPS * 32)
-k_pair(const SAtom* __restrict__ sat, const float* __restrict__ qs, const int32_t* __restrict__ cstart, const GridParams* __restrict__ gp,
+k_pair(const SAtom* __restrict__ sat, const float4* __restrict__ pq, const int32_t* __restrict__ cstart, const GridParams* __restrict__ gp,
        const int32_t* __restrict__ rowsidx, const int32_t* __restrict__ rowslot, int64_t nrows, int64_t maxnatom, int64_t nreal_slots,
        const __grid_constant__ DevParams P, int do_vdw, int do_force, float cutoff_A, double* __restrict__ dedq_slot, float* __restrict__ F,
        double* __restrict__ molacc) {
-  __shared__ float q_r[PAIR_WARPS][QCAP], q_q[PAIR_WARPS][QCAP], q_dx[PAIR_WARPS][QCAP], q_dy[PAIR_WARPS][QCAP], q_dz[PAIR_WARPS][QCAP];
-  __shared__ int q_info[PAIR_WARPS][QCAP];
+  __shared__ int q_j[PAIR_WARPS][QCAP];
   int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int64_t row = (int64_t)blockIdx.x * PAIR_WARPS + warp;
   if (row >= nrows) return;
@@ -196,74 +199,56 @@ k_pair(const SAtom* __restrict__ sat, const float* __restrict__ qs, const int32_
   GridParams g = *gp;
   int si = rowsidx[row];
   SAtom ci = sat[si];
-  float qi = qs[si];
+  float4 pi = pq[si];
+  float qi = pi.w;
   int ei = ci.e;
   int m = (int)(slot / maxnatom);
-  int cx = cell_coord(ci.x, g.ox, g.inv_cell, g.gx);
-  int cy = cell_coord(ci.y, g.oy, g.inv_cell, g.gy);
-  int cz = cell_coord(ci.z, g.oz, g.inv_cell, g.gz);
-  float cell = (float)g.cell;
+  float cell = (float)g.cell, icell = (float)g.inv_cell;
   float rc2 = cutoff_A * cutoff_A;
-  int nrange = (int)ceilf(cutoff_A / cell);
+  // cell columns that can hold a partner, from the centre's actual position (not its cell): |dx| <= rc
+  int x0 = max(0, (int)floorf((pi.x - cutoff_A) * icell)), x1 = min(g.gx - 1, (int)floorf((pi.x + cutoff_A) * icell));
+  int y0 = max(0, (int)floorf((pi.y - cutoff_A) * icell)), y1 = min(g.gy - 1, (int)floorf((pi.y + cutoff_A) * icell));
   PairAcc A = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   int qn = 0;
-  for (int dx = -nrange; dx <= nrange; dx++) {
-    int x = cx + dx;
-    if (x < 0 || x >= g.gx) continue;
-    float mx = fmaxf(0.f, (float)(abs(dx) - 1)) * cell;
-    for (int dy = -nrange; dy <= nrange; dy++) {
-      int y = cy + dy;
-      if (y < 0 || y >= g.gy) continue;
-      float my = fmaxf(0.f, (float)(abs(dy) - 1)) * cell;
-      float rem = rc2 - mx * mx - my * my;
-      if (rem < 0.f) continue;
-      int nz = (int)floorf(sqrtf(rem) / cell) + 1;
-      int z0 = max(cz - nz, 0), z1 = min(cz + nz, g.gz - 1);
+  auto eval = [&](int j) {
+    SAtom a = sat[j];
+    float ddx = (float)(a.x - ci.x), ddy = (float)(a.y - ci.y), ddz = (float)(a.z - ci.z);
+    float r = sqrtf(ddx * ddx + ddy * ddy + ddz * ddz);
+    pair_eval(P, r, ddx, ddy, ddz, qi, pq[j].w, ei, a.e, (a.slot < nreal_slots) ? 1.0f : 0.5f, do_vdw, A);
+  };
+  for (int x = x0; x <= x1; x++) {
+    // distance from the centre to the column's slab in x, then the same in y
+    float lx = fmaxf(0.f, fmaxf(x * cell - pi.x, pi.x - (x + 1) * cell));
+    for (int y = y0; y <= y1; y++) {
+      float ly = fmaxf(0.f, fmaxf(y * cell - pi.y, pi.y - (y + 1) * cell));
+      float rem = rc2 - lx * lx - ly * ly;
+      if (rem <= 0.f) continue;
+      float zr = sqrtf(rem);
+      int z0 = max(0, (int)floorf((pi.z - zr) * icell)), z1 = min(g.gz - 1, (int)floorf((pi.z + zr) * icell));
+      if (z1 < z0) continue;
       int cbase = m * g.ncell_mol + (x * g.gy + y) * g.gz;
       int b = cstart[cbase + z0], e = cstart[cbase + z1 + 1];
       for (int j0 = b; j0 < e; j0 += 32) {
         int j = j0 + lane;
         bool ok = false;
-        float ddx = 0.f, ddy = 0.f, ddz = 0.f, d2 = 0.f, qj = 0.f;
-        int info = 0;
         if (j < e && j != si) {
-          SAtom a = sat[j];
-          ddx = (float)(a.x - ci.x);
-          ddy = (float)(a.y - ci.y);
-          ddz = (float)(a.z - ci.z);
-          d2 = ddx * ddx + ddy * ddy + ddz * ddz;
-          ok = d2 < rc2;
-          if (ok) {
-            qj = qs[j];
-            info = a.e | ((a.slot < nreal_slots) ? 256 : 0);
-          }
+          float4 pj = pq[j];
+          float ddx = pj.x - pi.x, ddy = pj.y - pi.y, ddz = pj.z - pi.z;
+          ok = (ddx * ddx + ddy * ddy + ddz * ddz) < rc2;
         }
         unsigned mk = __ballot_sync(FULL, ok);
-        if (ok) {
-          int pos = qn + __popc(mk & ((1u << lane) - 1));
-          q_r[warp][pos] = sqrtf(d2);
-          q_q[warp][pos] = qj;
-          q_dx[warp][pos] = ddx; q_dy[warp][pos] = ddy; q_dz[warp][pos] = ddz;
-          q_info[warp][pos] = info;
-        }
+        if (ok) q_j[warp][qn + __popc(mk & ((1u << lane) - 1))] = j;
         qn += __popc(mk);
         __syncwarp();
         if (qn >= 32) {
-          int k = qn - 32 + lane;
-          int inf = q_info[warp][k];
-          pair_eval(P, q_r[warp][k], q_dx[warp][k], q_dy[warp][k], q_dz[warp][k], qi, q_q[warp][k], ei, inf & 255, (inf & 256) ? 1.0f : 0.5f,
-                    do_vdw, A);
+          eval(q_j[warp][qn - 32 + lane]);
           qn -= 32;
           __syncwarp();
         }
       }
     }
   }
-  if (lane < qn) {
-    int inf = q_info[warp][lane];
-    pair_eval(P, q_r[warp][lane], q_dx[warp][lane], q_dy[warp][lane], q_dz[warp][lane], qi, q_q[warp][lane], ei, inf & 255,
-              (inf & 256) ? 1.0f : 0.5f, do_vdw, A);
-  }
+  if (lane < qn) eval(q_j[warp][lane]);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     A.ecc += __shfl_xor_sync(FULL, A.ecc, o);
@@ -292,7 +277,7 @@ int tm_launch_pair(tm_ctx* c, const SysView& s, int flags) {
   if ((rc = tm_buf(c, c->b_dedq, (size_t)nq * 8))) return rc;
   TM_CUDA(cudaMemsetAsync(c->b_dedq.p, 0, (size_t)nq * 8, c->stream));
   int blocks = (int)((s.nrows + PAIR_WARPS - 1) / PAIR_WARPS);
-  k_pair<<<blocks, PAIR_WARPS * 32, 0, c->stream>>>((const SAtom*)c->b_satom.p, (const float*)c->b_qs.p, (const int32_t*)c->b_cstart.p,
+  k_pair<<<blocks, PAIR_WARPS * 32, 0, c->stream>>>((const SAtom*)c->b_satom.p, (const float4*)c->b_qs.p, (const int32_t*)c->b_cstart.p,
                                                    (const GridParams*)c->b_grid.p, (const int32_t*)c->b_rowsidx.p, (const int32_t*)c->b_rowslot.p,
                                                    s.nrows, s.maxnatom, nq, c->hp, (flags & TM_F_VDW) ? 1 : 0,
                                                    (flags & TM_F_FORCE) ? 1 : 0, (float)c->params.ee_cutoff_off, (double*)c->b_dedq.p,
