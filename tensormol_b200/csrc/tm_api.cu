@@ -99,6 +99,41 @@ static int build_dev_params(tm_ctx* c) {
   P.Zc = (float)ZZ; P.ZoverR_plus_Y = (float)(ZZ / Rl + YY);
   P.elu_a = (float)p.elu_alpha; P.elu_shift = (float)p.elu_shift;
   P.poly_width_b = (float)(p.poly_width * B);
+  P.inv_poly_width_b = (float)(1.0 / (p.poly_width * B));
+  {
+    // Chebyshev fit (degree 11) of erfcx(x) = exp(x^2) erfc(x) on the LR branch's range, converted to monomials in u
+    const int n = 12;
+    double lo = std::max(0.0, alpha * p.elu_width * B - 0.05), hi = alpha * Rl + 0.05;
+    double mid = 0.5 * (lo + hi), half = 0.5 * (hi - lo);
+    double a[n], fx[n];
+    for (int k = 0; k < n; k++) {
+      double u = cos(M_PI * (k + 0.5) / n), x = mid + half * u;
+      fx[k] = exp(x * x) * erfc(x);
+    }
+    for (int j = 0; j < n; j++) {
+      double sacc = 0;
+      for (int k = 0; k < n; k++) sacc += fx[k] * cos(M_PI * j * (k + 0.5) / n);
+      a[j] = 2.0 * sacc / n;
+    }
+    a[0] *= 0.5;
+    double T0[n] = {0}, T1[n] = {0}, mono[n] = {0}, Tn[n];
+    T0[0] = 1.0; T1[1] = 1.0;
+    for (int i = 0; i < n; i++) mono[i] += a[0] * T0[i] + a[1] * T1[i];
+    for (int j = 2; j < n; j++) {
+      for (int i = 0; i < n; i++) Tn[i] = (i > 0 ? 2.0 * T1[i - 1] : 0.0) - T0[i];
+      for (int i = 0; i < n; i++) { mono[i] += a[j] * Tn[i]; T0[i] = T1[i]; T1[i] = Tn[i]; }
+    }
+    double err = 0;
+    for (int k = 0; k <= 200; k++) {
+      double x = lo + (hi - lo) * k / 200.0, u = (x - mid) / half, pz = mono[n - 1];
+      for (int i = n - 2; i >= 0; i--) pz = pz * u + mono[i];
+      double ref = exp(x * x) * erfc(x);
+      err = std::max(err, fabs(pz - ref) / ref);
+    }
+    for (int i = 0; i < n; i++) P.erfc_c[i] = (float)mono[i];
+    P.erfc_mid = (float)mid; P.erfc_ihalf = (float)(1.0 / half); P.erfc_fit_err = (float)err;
+    if (err > 1e-7) { tm_set_error("erfc fit error %.3e too large for this DSFAlpha / cutoff range", err); return TM_EINVAL; }
+  }
   for (int i = 0; i < d.n_ele; i++) { P.sqrtC6[i] = (float)sqrt(p.C6[i]); P.Rvdw[i] = (float)p.Rvdw[i]; }
   P.add_ecc = p.add_ecc; P.activation = p.activation; P.act_alpha = (float)p.sigmoid_alpha;
   P.rr_exact = p.r_Rc; P.ra_exact = p.a_Rc;

@@ -13,14 +13,17 @@
 // per-element MLP batch).  Neighbour records (32 B) are fetched coalesced from the cell-sorted
 // copy; position differences are formed in float64 and rounded once to fp32.
 //   radial : lane = Rs channel, neighbours broadcast by warp shuffle, register accumulators per element
-//   angular: phase 1 lanes = triples (geometry, 8 angular and 8 radial factors into shared tiles),
-//            phase 2 lanes = output channels (rank-1 update of the 64-wide block of the pair channel).
+//   angular: phase 1 lanes = triples (geometry, nAs angular and nRs_a radial factors into shared tiles),
+//            phase 2 lanes = output channels, register accumulators per element-pair channel
+// The kernel is instruction-issue bound (ncu r01: 79 % issue-active), not HBM bound, so the template
+// parameters exist to cut instructions: NE = number of elements (selects per neighbour), OPLT = outputs
+// per lane of one pair channel (2 for the default 8x8 angular grid).  Exponentials use ex2.approx
+// (__expf): relative error < 1e-6 on every term that is not itself < 1e-10 of the row scale.
 #include "tm_internal.h"
 
 #define FULL 0xffffffffu
 #define DESC_WARPS 8
 #define RPL 2   // radial channels per lane (num_r_Rs <= 64)
-#define OPL 8   // angular outputs per lane (nAs*nRs_a <= 256)
 
 __device__ __forceinline__ void tri_inv(int t, int& j, int& k) {
   // t = k(k-1)/2 + j with 0 <= j < k
@@ -39,13 +42,15 @@ __device__ __forceinline__ float pow_zeta(float b, const DevParams& P) {
 }
 
 size_t tm_desc_smem_floats_per_warp(const DevParams& P) {
-  return 5 * TM_ANG_CAP + TM_ANG_CAP + 32 * (P.nAs + 1) + 32 * (P.nRs_a + 1) + 32 + (size_t)P.n_elep * P.nsym;
+  return 5 * TM_ANG_CAP + TM_ANG_CAP + 32 * (P.nAs + 1) + 32 * (P.nRs_a + 1) + 32;
 }
 
+template <int NE, int OPLT>
 __global__ void __launch_bounds__(DESC_WARPS * 32)
 k_desc(const SAtom* __restrict__ sat, const int32_t* __restrict__ rowsidx, const int32_t* __restrict__ rowslot,
        const int32_t* __restrict__ nboff, const uint32_t* __restrict__ nbr, int64_t nrows, const __grid_constant__ DevParams P,
        float* __restrict__ G, int32_t* __restrict__ flags, int wfloats) {
+  constexpr int NELEP = NE * (NE + 1) / 2;
   extern __shared__ float smem[];
   int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int64_t row = (int64_t)blockIdx.x * DESC_WARPS + warp;
@@ -67,20 +72,18 @@ k_desc(const SAtom* __restrict__ sat, const int32_t* __restrict__ rowsidx, const
   const int tstr = P.nAs + 1, estr = P.nRs_a + 1;
   float* Et = Tt + 32 * tstr;
   int* chan = (int*)(Et + 32 * estr);
-  float* Gs = (float*)(chan + 32);
-  const int nang_out = P.n_elep * P.nsym;
-  for (int i = lane; i < nang_out; i += 32) Gs[i] = 0.f;
 
   SAtom ci = sat[rowsidx[row]];
   int b = nboff[row], e = nboff[row + 1];
-  float acc[RPL][TM_MAX_ELE];
+  float acc[RPL][NE];
   float rs[RPL];
 #pragma unroll
   for (int k = 0; k < RPL; k++) {
     rs[k] = (lane + 32 * k < P.nRs_r) ? P.Rs_r[lane + 32 * k] : 0.f;
 #pragma unroll
-    for (int q = 0; q < TM_MAX_ELE; q++) acc[k][q] = 0.f;
+    for (int q = 0; q < NE; q++) acc[k][q] = 0.f;
   }
+  const float neg_eta = -P.eta;
   int nang = 0;
   for (int j0 = b; j0 < e; j0 += 32) {
     int j = j0 + lane;
@@ -96,14 +99,14 @@ k_desc(const SAtom* __restrict__ sat, const int32_t* __restrict__ rowsidx, const
       dz = (float)(a.z - ci.z);
       r = sqrtf(dx * dx + dy * dy + dz * dz);
       ej = a.e;
-      fc = 0.5f * (cosf(P.pi_over_rRc * r) + 1.0f);
+      fc = 0.5f * (__cosf(P.pi_over_rRc * r) + 1.0f);
     }
     unsigned mk = __ballot_sync(FULL, isang);
     if (isang) {
       int pos = nang + __popc(mk & ((1u << lane) - 1));
       if (pos < TM_ANG_CAP) {
         ax[pos] = dx; ay[pos] = dy; az[pos] = dz; ar[pos] = r;
-        afc[pos] = 0.5f * (cosf(P.pi_over_aRc * r) + 1.0f);
+        afc[pos] = 0.5f * (__cosf(P.pi_over_aRc * r) + 1.0f);
         ae[pos] = ej;
       } else {
         atomicOr(flags, 4);
@@ -118,9 +121,9 @@ k_desc(const SAtom* __restrict__ sat, const int32_t* __restrict__ rowsidx, const
       for (int k = 0; k < RPL; k++) {
         if (k == 0 || P.nRs_r > 32) {
           float d = rr - rs[k];
-          float v = expf(-P.eta * d * d) * ff;
+          float v = __expf(neg_eta * d * d) * ff;
 #pragma unroll
-          for (int q = 0; q < TM_MAX_ELE; q++) acc[k][q] += (ee == q) ? v : 0.f;
+          for (int q = 0; q < NE; q++) acc[k][q] += (ee == q) ? v : 0.f;
         }
       }
     }
@@ -128,13 +131,28 @@ k_desc(const SAtom* __restrict__ sat, const int32_t* __restrict__ rowsidx, const
   nang = min(nang, TM_ANG_CAP);
   __syncwarp();
 
-  // per-lane output coordinates for phase 2
-  int oa[OPL], os[OPL];
+  // write the radial block now (frees registers for the angular accumulators)
 #pragma unroll
-  for (int k = 0; k < OPL; k++) {
+  for (int k = 0; k < RPL; k++) {
+    int s = lane + 32 * k;
+    if (s < P.nRs_r) {
+#pragma unroll
+      for (int q = 0; q < NE; q++)
+        if (q < P.n_ele) Grow[q * P.nRs_r + s] = acc[k][q];
+    }
+  }
+
+  // per-lane output coordinates for phase 2
+  int oa[OPLT], os[OPLT];
+  float ga[NELEP][OPLT];
+#pragma unroll
+  for (int k = 0; k < OPLT; k++) {
     int idx = lane + 32 * k;
-    oa[k] = idx / P.nRs_a;
-    os[k] = idx - oa[k] * P.nRs_a;
+    int a_ = idx / P.nRs_a;
+    oa[k] = (idx < P.nsym) ? a_ : 0;
+    os[k] = (idx < P.nsym) ? idx - a_ * P.nRs_a : 0;
+#pragma unroll
+    for (int q = 0; q < NELEP; q++) ga[q][k] = 0.f;
   }
   int ntrip = nang * (nang - 1) / 2;
   for (int t0 = 0; t0 < ntrip; t0 += 32) {
@@ -144,7 +162,7 @@ k_desc(const SAtom* __restrict__ sat, const int32_t* __restrict__ rowsidx, const
       tri_inv(t, j, k);
       float ajx = ax[j], ajy = ay[j], ajz = az[j], akx = ax[k], aky = ay[k], akz = az[k];
       float ra = ar[j], rb = ar[k];
-      float inv = 1.0f / (ra * rb);
+      float inv = __frcp_rn(ra * rb);
       float c = (ajx * akx + ajy * aky + ajz * akz) * inv;
       float nx = ajy * akz - ajz * aky, ny = ajz * akx - ajx * akz, nz = ajx * aky - ajy * akx;
       float s = sqrtf(nx * nx + ny * ny + nz * nz) * inv;
@@ -157,7 +175,7 @@ k_desc(const SAtom* __restrict__ sat, const int32_t* __restrict__ rowsidx, const
       }
       for (int q = 0; q < P.nRs_a; q++) {
         float d = rho - P.Rs_a[q];
-        Et[lane * estr + q] = expf(-P.eta * d * d) * f;
+        Et[lane * estr + q] = __expf(neg_eta * d * d) * f;
       }
       chan[lane] = P.pair_index[ae[j]][ae[k]];
     }
@@ -167,47 +185,67 @@ k_desc(const SAtom* __restrict__ sat, const int32_t* __restrict__ rowsidx, const
       int p = chan[tt];
       const float* Tr = Tt + tt * tstr;
       const float* Er = Et + tt * estr;
-      float* Gp = Gs + p * P.nsym;
+      float v[OPLT];
 #pragma unroll
-      for (int k = 0; k < OPL; k++) {
-        int idx = lane + 32 * k;
-        if (idx < P.nsym) Gp[idx] += Tr[oa[k]] * Er[os[k]];
+      for (int k = 0; k < OPLT; k++) v[k] = Tr[oa[k]] * Er[os[k]];
+#pragma unroll
+      for (int q = 0; q < NELEP; q++) {
+        if (p == q) {
+#pragma unroll
+          for (int k = 0; k < OPLT; k++) ga[q][k] += v[k];
+        }
       }
     }
     __syncwarp();
   }
 
-  // write the row: radial block, angular block, zero padding
+  // angular block, zero padding
+  int off = P.n_ele * P.nRs_r;
 #pragma unroll
-  for (int k = 0; k < RPL; k++) {
-    int s = lane + 32 * k;
-    if (s < P.nRs_r) {
+  for (int q = 0; q < NELEP; q++) {
+    if (q < P.n_elep) {
 #pragma unroll
-      for (int q = 0; q < TM_MAX_ELE; q++)
-        if (q < P.n_ele) Grow[q * P.nRs_r + s] = acc[k][q];
+      for (int k = 0; k < OPLT; k++) {
+        int idx = lane + 32 * k;
+        if (idx < P.nsym) Grow[off + q * P.nsym + idx] = ga[q][k];
+      }
     }
   }
-  int off = P.n_ele * P.nRs_r;
-  for (int i = lane; i < nang_out; i += 32) Grow[off + i] = Gs[i];
   for (int i = P.D + lane; i < P.Dp; i += 32) Grow[i] = 0.f;
+}
+
+template <int NE, int OPLT>
+static int launch_desc(tm_ctx* c, const SysView& s) {
+  const DevParams& P = c->hp;
+  size_t wf = tm_desc_smem_floats_per_warp(P);
+  size_t smem = wf * 4 * DESC_WARPS;
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    TM_CUDA(cudaFuncSetAttribute(k_desc<NE, OPLT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  int blocks = (int)((s.nrows + DESC_WARPS - 1) / DESC_WARPS);
+  k_desc<NE, OPLT><<<blocks, DESC_WARPS * 32, smem, c->stream>>>((const SAtom*)c->b_satom.p, (const int32_t*)c->b_rowsidx.p,
+                                                                (const int32_t*)c->b_rowslot.p, (const int32_t*)c->b_nboff.p,
+                                                                (const uint32_t*)c->b_nbr.p, s.nrows, P, (float*)c->b_G.p,
+                                                                (int32_t*)c->b_flags.p, (int)wf);
+  c->launches++;
+  TM_CUDA(cudaGetLastError());
+  return TM_OK;
 }
 
 int tm_launch_desc(tm_ctx* c, const SysView& s) {
   int rc;
   const DevParams& P = c->hp;
   if ((rc = tm_buf(c, c->b_G, (size_t)s.nrows * P.Dp * 4))) return rc;
-  size_t wf = tm_desc_smem_floats_per_warp(P);
-  size_t smem = wf * 4 * DESC_WARPS;
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    TM_CUDA(cudaFuncSetAttribute(k_desc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
-  int blocks = (int)((s.nrows + DESC_WARPS - 1) / DESC_WARPS);
-  k_desc<<<blocks, DESC_WARPS * 32, smem, c->stream>>>((const SAtom*)c->b_satom.p, (const int32_t*)c->b_rowsidx.p, (const int32_t*)c->b_rowslot.p,
-                                                      (const int32_t*)c->b_nboff.p, (const uint32_t*)c->b_nbr.p, s.nrows, P, (float*)c->b_G.p,
-                                                      (int32_t*)c->b_flags.p, (int)wf);
-  c->launches++;
-  TM_CUDA(cudaGetLastError());
-  return TM_OK;
+  bool small = P.nsym <= 64;
+  if (small && P.n_ele == 1) return launch_desc<1, 2>(c, s);
+  if (small && P.n_ele == 2) return launch_desc<2, 2>(c, s);
+  if (small && P.n_ele == 3) return launch_desc<3, 2>(c, s);
+  if (small && P.n_ele == 4) return launch_desc<4, 2>(c, s);
+  if (P.n_ele <= 4) return launch_desc<4, 8>(c, s);
+  if (small) return launch_desc<TM_MAX_ELE, 2>(c, s);
+  // 8 elements x 256 angular functions would need 36 x 8 register accumulators per lane: not supported
+  tm_set_error("more than 4 elements together with more than 64 angular functions per pair channel is not supported");
+  return TM_EINVAL;
 }

@@ -15,6 +15,7 @@
 // TMEM: 2 accumulator buffers of BN columns (double buffered so the epilogue of tile i overlaps the MMAs of i+1).
 #include "tm_internal.h"
 #include <cuda.h>
+#include <cstdlib>
 #include <map>
 #include <tuple>
 
@@ -25,6 +26,9 @@
 #define TC_NACC 4                 // TMEM accumulator buffers (4 x 128 columns = all 512)
 #define TC_CHUNK 1                // k-blocks accumulated inside TMEM before the fp32 register add
 #define TC_MAX_GROUPS (2 * TM_MAX_ELE)
+// 32x32 fp32 transpose tile, 16-byte chunks XOR-swizzled by the row so that both the row-wise (thread = row) and the
+// slab-wise (8 lanes per row) 128-bit accesses are bank-conflict free without padding
+#define TB_OFF(r, c4) ((r) * 32 + ((((c4) ^ ((r) & 7))) << 2))
 
 struct alignas(64) TcGroup {
   CUtensorMap mapA_hi, mapA_lo, mapB_hi, mapB_lo;
@@ -39,6 +43,7 @@ struct alignas(64) TcParams {
   TcGroup g[TC_MAX_GROUPS];
   int ngroups, epilogue, act_kind;
   float act_alpha;
+  int dbg;   // development switches (TM_TC_DBG): 1 = skip the output phase, 2 = skip the TMA loads
 };
 
 // ------------------------------------------------------------------------------------------------ PTX helpers
@@ -158,7 +163,7 @@ k_gemm_tc(const __grid_constant__ TcParams P, const int32_t* __restrict__ rowmet
   uint32_t* tmem_slot = (uint32_t*)(tempty_bar + TC_NACC);
   int* tile_base = (int*)(tmem_slot + 4);       // [TC_MAX_GROUPS+1]
   int* row_first = tile_base + TC_MAX_GROUPS + 1;   // [TC_MAX_GROUPS]
-  float* tbuf = (float*)(row_first + TC_MAX_GROUPS);  // TC_EPI_WARPS x [32][33] transpose tiles
+  float* tbuf = (float*)(((uintptr_t)(row_first + TC_MAX_GROUPS) + 15) & ~(uintptr_t)15);  // TC_EPI_WARPS x [32][32] XOR-swizzled transpose tiles (16-byte aligned)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -212,6 +217,7 @@ k_gemm_tc(const __grid_constant__ TcParams P, const int32_t* __restrict__ rowmet
         for (int kb = 0; kb < nkb; kb++) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* st = smem + stage * STAGE_BYTES;
+          if (P.dbg & 2) { mbar_arrive(&full_bar[stage]); if (++stage == STAGES) { stage = 0; phase ^= 1; } continue; }
           mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
           tma_load_2d(&G.mapA_hi, &full_bar[stage], st, kb * TC_BK, row0);
           tma_load_2d(&G.mapA_lo, &full_bar[stage], st + A_BYTES, kb * TC_BK, row0);
@@ -279,7 +285,7 @@ k_gemm_tc(const __grid_constant__ TcParams P, const int32_t* __restrict__ rowmet
     constexpr int NC = BN / 2;                     // columns per thread
     const int act_kind = (ACTK >= 0) ? ACTK : P.act_kind;
     const float act_alpha = P.act_alpha;
-    float* tb = tbuf + (warp - 2) * (32 * 33);
+    float* tb = tbuf + (warp - 2) * (32 * 32);
     uint32_t chunk_it = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       int g, rt, ct;
@@ -305,28 +311,38 @@ k_gemm_tc(const __grid_constant__ TcParams P, const int32_t* __restrict__ rowmet
 #pragma unroll
         for (int i = 0; i < NC; i++) accr[i] += __uint_as_float(v[i]);
       }
-      // Output: thread = row of the warp's 32-row band.  Each 32x32 block goes through a padded shared tile so that
-      // global accesses are 128-byte coalesced row segments (thread-per-row stores cost 32 L1 wavefronts each).
+      // Output: thread = row of the warp's 32-row band.  Each 32x32 block goes through a shared tile (XOR-swizzled,
+      // 128-bit accesses, conflict-free per quarter warp) so that every global access is a 128-bit piece of a
+      // full 128-byte row segment: one warp instruction moves 4 rows x 128 B.
+      if (P.dbg & 1) continue;
       int64_t wrow0 = (int64_t)row_first[g] + (int64_t)rt * TC_BM + q * 32;
       int n0 = ct * BN + half * NC;
+      const int trow = lane >> 3, tcol = (lane & 7) * 4;     // coordinates of this lane inside a 4-row slab
 #pragma unroll
       for (int c = 0; c < NC / 32; c++) {   // unrolled: accr[] indices must be static
         int64_t off0 = wrow0 * G.ldc + n0 + c * 32;
         float x[32];
         if (EPI == TM_EPI_DACT) {
-          // all 64 coalesced row-segment loads in flight at once (latency, not bandwidth, is the cost here)
-          float h1[32], h2[32];
+          float4 h1[8], h2[8];
 #pragma unroll
-          for (int r = 0; r < 32; r++) {
-            int64_t o = off0 + (int64_t)r * G.ldc + lane;
-            h1[r] = __ldg(G.Hmul_hi + o);
-            h2[r] = __ldg(G.Hmul_lo + o);
+          for (int it = 0; it < 8; it++) {
+            int64_t o = off0 + (int64_t)(it * 4 + trow) * G.ldc + tcol;
+            h1[it] = __ldg(reinterpret_cast<const float4*>(G.Hmul_hi + o));
+            h2[it] = __ldg(reinterpret_cast<const float4*>(G.Hmul_lo + o));
           }
 #pragma unroll
-          for (int r = 0; r < 32; r++) tb[r * 33 + lane] = h1[r] + h2[r];
+          for (int it = 0; it < 8; it++)
+            *reinterpret_cast<float4*>(tb + TB_OFF(it * 4 + trow, tcol >> 2)) =
+                make_float4(h1[it].x + h2[it].x, h1[it].y + h2[it].y, h1[it].z + h2[it].z, h1[it].w + h2[it].w);
           __syncwarp();
 #pragma unroll
-          for (int i = 0; i < 32; i++) x[i] = accr[c * 32 + i] * tc_act_bwd(tb[lane * 33 + i], act_kind, act_alpha);
+          for (int i = 0; i < 8; i++) {
+            float4 hv = *reinterpret_cast<const float4*>(tb + TB_OFF(lane, i));
+            x[4 * i + 0] = accr[c * 32 + 4 * i + 0] * tc_act_bwd(hv.x, act_kind, act_alpha);
+            x[4 * i + 1] = accr[c * 32 + 4 * i + 1] * tc_act_bwd(hv.y, act_kind, act_alpha);
+            x[4 * i + 2] = accr[c * 32 + 4 * i + 2] * tc_act_bwd(hv.z, act_kind, act_alpha);
+            x[4 * i + 3] = accr[c * 32 + 4 * i + 3] * tc_act_bwd(hv.w, act_kind, act_alpha);
+          }
           __syncwarp();
         } else if (EPI == TM_EPI_ACT) {
           float bl = G.bias[n0 + c * 32 + lane];
@@ -337,17 +353,23 @@ k_gemm_tc(const __grid_constant__ TcParams P, const int32_t* __restrict__ rowmet
           for (int i = 0; i < 32; i++) x[i] = accr[c * 32 + i];
         }
 #pragma unroll
-        for (int i = 0; i < 32; i++) tb[lane * 33 + i] = (EPI == TM_EPI_NONE) ? x[i] : tf32_hi(x[i]);
-        __syncwarp();
-#pragma unroll 4
-        for (int r = 0; r < 32; r++) G.C_hi[off0 + (int64_t)r * G.ldc + lane] = tb[r * 33 + lane];
-        __syncwarp();
-        if (EPI != TM_EPI_NONE) {
+        for (int plane = 0; plane < ((EPI == TM_EPI_NONE) ? 1 : 2); plane++) {
+          float* Cp = plane ? G.C_lo : G.C_hi;
 #pragma unroll
-          for (int i = 0; i < 32; i++) tb[lane * 33 + i] = x[i] - tf32_hi(x[i]);
+          for (int i = 0; i < 8; i++) {
+            float4 v;
+            if (EPI == TM_EPI_NONE) v = make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
+            else if (plane == 0) v = make_float4(tf32_hi(x[4 * i]), tf32_hi(x[4 * i + 1]), tf32_hi(x[4 * i + 2]), tf32_hi(x[4 * i + 3]));
+            else v = make_float4(x[4 * i] - tf32_hi(x[4 * i]), x[4 * i + 1] - tf32_hi(x[4 * i + 1]), x[4 * i + 2] - tf32_hi(x[4 * i + 2]),
+                                 x[4 * i + 3] - tf32_hi(x[4 * i + 3]));
+            *reinterpret_cast<float4*>(tb + TB_OFF(lane, i)) = v;
+          }
           __syncwarp();
-#pragma unroll 4
-          for (int r = 0; r < 32; r++) G.C_lo[off0 + (int64_t)r * G.ldc + lane] = tb[r * 33 + lane];
+#pragma unroll
+          for (int it = 0; it < 8; it++) {
+            float4 v = *reinterpret_cast<const float4*>(tb + TB_OFF(it * 4 + trow, tcol >> 2));
+            *reinterpret_cast<float4*>(Cp + off0 + (int64_t)(it * 4 + trow) * G.ldc + tcol) = v;
+          }
           __syncwarp();
         }
       }
@@ -402,7 +424,7 @@ static int make_map(CUtensorMap* m, const float* base, int64_t rows, int64_t col
 
 template <int BN, int STAGES, int EPI, int ACTK>
 static int launch_tc(tm_ctx* c, const TcParams& P, const int* rowmeta_dev, int total_tiles_bound) {
-  constexpr size_t smem = (size_t)STAGES * (2 * TC_BM * TC_BK * 4 + 2 * BN * TC_BK * 4) + 1024 + 512 + TC_EPI_WARPS * 32 * 33 * 4;
+  constexpr size_t smem = (size_t)STAGES * (2 * TC_BM * TC_BK * 4 + 2 * BN * TC_BK * 4) + 1024 + 512 + TC_EPI_WARPS * 32 * 32 * 4;
   static bool configured = false;
   if (!configured) {
     TM_CUDA(cudaFuncSetAttribute(k_gemm_tc<BN, STAGES, EPI, ACTK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -431,6 +453,7 @@ int tm_gemm_tc_launch(tm_ctx* c, const GemmGroup* groups, int ngroups, const int
   if ((rc = get_encode())) return rc;
   if (ngroups > TC_MAX_GROUPS) { tm_set_error("too many GEMM groups"); return TM_EINVAL; }
   static TcParams P;   // large; filled per launch (calls on one ctx are serialised by contract)
+  { const char* d = getenv("TM_TC_DBG"); P.dbg = d ? atoi(d) : 0; }
   P.ngroups = ngroups; P.epilogue = epilogue; P.act_kind = c->hp.activation; P.act_alpha = c->hp.act_alpha;
   bool all256 = true;
   int64_t tiles = 0;

@@ -58,6 +58,9 @@ struct DevParams {
   float Zc, ZoverR_plus_Y;        // erfc(a R_lr)/R_lr ; Zc/R_lr + Yc
   float elu_a, elu_shift;
   float poly_width_b;             // Poly_Width*B
+  float inv_poly_width_b;
+  float erfc_c[12];               // erfcx(x) ~ sum_k c_k u^k, u = (x - erfc_mid)*erfc_ihalf, on [alpha R_sr, alpha R_lr]
+  float erfc_mid, erfc_ihalf, erfc_fit_err;
   float sqrtC6[TM_MAX_ELE], Rvdw[TM_MAX_ELE];
   int add_ecc;
   int activation;

@@ -90,12 +90,20 @@ __global__ void k_bbox(const double* __restrict__ pos, const int32_t* __restrict
       mx[d] = fmax(mx[d], __shfl_xor_sync(FULL, mx[d], o));
     }
   }
+  // block-level combine in shared memory, then 6 atomics per block (per-warp atomics on 6 addresses serialised: 42 us)
+  __shared__ double smn[8][3], smx[8][3];
+  int w = threadIdx.x >> 5;
   if ((threadIdx.x & 31) == 0) {
 #pragma unroll
-    for (int d = 0; d < 3; d++) {
-      if (mn[d] < 1e299) atomicMin(&bb[d], enc_d(mn[d]));
-      if (mx[d] > -1e299) atomicMax(&bb[3 + d], enc_d(mx[d]));
-    }
+    for (int d = 0; d < 3; d++) { smn[w][d] = mn[d]; smx[w][d] = mx[d]; }
+  }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    int d = threadIdx.x;
+    double a = smn[0][d], b = smx[0][d];
+    for (int k = 1; k < (int)(blockDim.x >> 5); k++) { a = fmin(a, smn[k][d]); b = fmax(b, smx[k][d]); }
+    if (a < 1e299) atomicMin(&bb[d], enc_d(a));
+    if (b > -1e299) atomicMax(&bb[3 + d], enc_d(b));
   }
 }
 
@@ -238,21 +246,38 @@ __global__ void k_scatter(const int32_t* __restrict__ cellid, const int32_t* __r
   }
 }
 
-// one thread per cell: order the cell's slots ascending (removes the atomic-arrival nondeterminism),
-// then write the 32-byte SAtom records in sorted order.
+// One warp per cell: order the cell's slots ascending (removes the atomic-arrival nondeterminism) by rank counting
+// across lanes, then write the 32-byte SAtom records in sorted order (lane = record: coalesced).  Cells holding more
+// than 32 atoms fall back to a serial insertion sort by lane 0.
 __global__ void k_cell_sort_gather(const GridParams* __restrict__ gp, const int32_t* __restrict__ cstart, int32_t* __restrict__ sorted,
                                    const double* __restrict__ pos, const int32_t* __restrict__ Z, const __grid_constant__ DevParams P,
                                    SAtom* __restrict__ sat, int32_t* __restrict__ sidx_of_slot) {
   int ncells = gp->ncells;
-  for (int cid = blockIdx.x * blockDim.x + threadIdx.x; cid < ncells; cid += gridDim.x * blockDim.x) {
-    int b = cstart[cid], e = cstart[cid + 1];
-    for (int i = b + 1; i < e; i++) {
-      int32_t v = sorted[i];
-      int j = i - 1;
-      while (j >= b && sorted[j] > v) { sorted[j + 1] = sorted[j]; j--; }
-      sorted[j + 1] = v;
+  int lane = threadIdx.x & 31;
+  int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int cid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; cid < ncells; cid += warps) {
+    int b = cstart[cid], e = cstart[cid + 1], n = e - b;
+    if (n <= 0) continue;
+    if (n <= 32) {
+      int32_t mine = (lane < n) ? sorted[b + lane] : 0x7fffffff;
+      int rank = 0;
+      for (int k = 0; k < n; k++) {
+        int32_t other = __shfl_sync(FULL, mine, k);
+        rank += (other < mine) ? 1 : 0;
+      }
+      __syncwarp();
+      if (lane < n) sorted[b + rank] = mine;
+      __syncwarp();
+    } else if (lane == 0) {
+      for (int i = b + 1; i < e; i++) {
+        int32_t v = sorted[i];
+        int j = i - 1;
+        while (j >= b && sorted[j] > v) { sorted[j + 1] = sorted[j]; j--; }
+        sorted[j + 1] = v;
+      }
     }
-    for (int i = b; i < e; i++) {
+    __syncwarp();
+    for (int i = b + lane; i < e; i += 32) {
       int32_t s = sorted[i];
       SAtom a;
       a.x = pos[3 * (int64_t)s]; a.y = pos[3 * (int64_t)s + 1]; a.z = pos[3 * (int64_t)s + 2];
@@ -295,9 +320,9 @@ int tm_launch_nlist_build(tm_ctx* c, const SysView& s, double rc_grid) {
   if ((rc = scan_exclusive(c, (const int32_t*)c->b_count.p, (int32_t*)c->b_cstart.p, s.ncells_cap, (int32_t*)c->b_scan_tmp.p))) return rc;
   k_scatter<<<blocks, 256, 0, c->stream>>>((const int32_t*)c->b_cellid.p, (const int32_t*)c->b_rank.p, (const int32_t*)c->b_cstart.p, n,
                                            (int32_t*)c->b_sorted.p);
-  int cblocks = (int)((s.ncells_cap + 127) / 128);
-  if (cblocks > 148 * 16) cblocks = 148 * 16;
-  k_cell_sort_gather<<<cblocks, 128, 0, c->stream>>>(gp, (const int32_t*)c->b_cstart.p, (int32_t*)c->b_sorted.p, (const double*)c->b_pos.p,
+  int cblocks = (int)((s.ncells_cap * 32 + 255) / 256);
+  if (cblocks > 148 * 32) cblocks = 148 * 32;
+  k_cell_sort_gather<<<cblocks, 256, 0, c->stream>>>(gp, (const int32_t*)c->b_cstart.p, (int32_t*)c->b_sorted.p, (const double*)c->b_pos.p,
                                                      (const int32_t*)c->b_Z.p, c->hp, (SAtom*)c->b_satom.p, (int32_t*)c->b_rank.p);
   c->launches += 2;
   TM_CUDA(cudaGetLastError());

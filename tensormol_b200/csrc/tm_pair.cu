@@ -37,7 +37,7 @@ __global__ void k_qraw_scatter(const float* __restrict__ y, const int32_t* __res
 __global__ void k_mol_sum(const double* __restrict__ v, const int32_t* __restrict__ Z, int64_t maxnatom, int64_t nvalid_per_mol, double* __restrict__ molacc, int field) {
   int m = blockIdx.x;
   double s = 0.0;
-  for (int64_t a = threadIdx.x; a < nvalid_per_mol; a += blockDim.x) {
+  for (int64_t a = blockIdx.y * (int64_t)blockDim.x + threadIdx.x; a < nvalid_per_mol; a += (int64_t)gridDim.y * blockDim.x) {
     int64_t slot = (int64_t)m * maxnatom + a;
     if (Z[slot] > 0) s += v[slot];
   }
@@ -50,7 +50,7 @@ __global__ void k_mol_sum(const double* __restrict__ v, const int32_t* __restric
     s = (threadIdx.x < (blockDim.x >> 5)) ? sh[threadIdx.x] : 0.0;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
-    if (threadIdx.x == 0) molacc[16 * m + field] = s;
+    if (threadIdx.x == 0) atomicAdd(&molacc[16 * m + field], s);   // molacc is zeroed at the start of the evaluation
   }
 }
 
@@ -116,7 +116,8 @@ int tm_launch_charges(tm_ctx* c, const SysView& s) {
     k_qraw_scatter<<<blocks, 256, 0, c->stream>>>((const float*)c->b_y[TM_NET_CHARGE].p, (const int32_t*)c->b_rowslot.p, s.nrows, qraw);
     c->launches++;
   }
-  k_mol_sum<<<(int)s.nmol, 256, 0, c->stream>>>(qraw, (const int32_t*)c->b_Z.p, s.maxnatom, nq_per_mol, molacc, 4);
+  dim3 gms((unsigned)s.nmol, (unsigned)std::max<int64_t>(1, std::min<int64_t>((nq_per_mol + 2047) / 2048, 64)));
+  k_mol_sum<<<gms, 256, 0, c->stream>>>(qraw, (const int32_t*)c->b_Z.p, s.maxnatom, nq_per_mol, molacc, 4);
   dim3 g((unsigned)std::min<int64_t>((nq_per_mol + 255) / 256, 148 * 4), (unsigned)s.nmol);
   k_neutralise<<<g, 256, 0, c->stream>>>(qraw, molacc, (const double*)c->b_natom.p, (const double*)c->b_pos.p, (const int32_t*)c->b_Z.p,
                                          s.maxnatom, nq_per_mol, s.nmol, q);
@@ -133,10 +134,16 @@ struct PairAcc {
   float ecc, evdw, dedq, gx, gy, gz;
 };
 
-__device__ __forceinline__ void pair_eval(const DevParams& P, float r, float dx, float dy, float dz, float qi, float qj, int ei, int ej,
+// erfc(x) = exp(-x^2) * erfcx(x); erfcx is smooth on the LR branch's range [alpha R_sr, alpha R_lr] and is evaluated as a
+// degree-11 polynomial in u in [-1,1] fitted on the host (tm_api.cu, max relative error stored in DevParams and < 1e-7),
+// sharing the exp(-x^2) that the derivative needs anyway.
+__device__ __forceinline__ void pair_eval(const DevParams& P, float d2, float dx, float dy, float dz, float qi, float qj, int ei, int ej,
                                           float wj, int do_vdw, PairAcc& A) {
   const float B = (float)TM_BOHRPERA;
+  float ir = rsqrtf(d2);          // 1/r (Angstrom^-1)
+  float r = d2 * ir;
   float R = B * r;
+  float iR = ir * (1.0f / B);
   float dEdR = 0.f;   // d e_ij / dR (Bohr)
   if (P.add_ecc) {
     float kap, dkap;
@@ -145,8 +152,12 @@ __device__ __forceinline__ void pair_eval(const DevParams& P, float r, float dx,
         kap = 0.f; dkap = 0.f;
       } else {
         float aR = P.alpha_b * R;
-        float er = erfcf(aR), ex = expf(-aR * aR);
-        float iR = 1.0f / R;
+        float ex = expf(-aR * aR);
+        float u = (aR - P.erfc_mid) * P.erfc_ihalf;
+        float pz = P.erfc_c[11];
+#pragma unroll
+        for (int k = 10; k >= 0; k--) pz = fmaf(pz, u, P.erfc_c[k]);
+        float er = pz * ex;
         kap = er * iR - P.Zc + (R - P.R_lr) * P.ZoverR_plus_Y;
         dkap = -er * iR * iR - 1.1283791671f * P.alpha_b * ex * iR + P.ZoverR_plus_Y;
       }
@@ -155,33 +166,34 @@ __device__ __forceinline__ void pair_eval(const DevParams& P, float r, float dx,
       kap = P.elu_a * (ex - 1.0f) + P.elu_shift;
       dkap = P.elu_a * ex;
     }
-    A.ecc += qi * qj * kap;
+    float qq = qi * qj;
+    A.ecc += qq * kap;
     A.dedq += qj * kap;
-    dEdR += qi * qj * dkap;
+    dEdR += qq * dkap;
   }
   if (do_vdw) {
     float Rp = B * R;                       // second Bohr scaling (RawSymFunc.py:1377)
-    float t = Rp / P.poly_width_b;
+    float iRp = iR * (1.0f / B);
+    float t = Rp * P.inv_poly_width_b;
     float S, dS;
     if (t > 1.0f) { S = 1.0f; dS = 0.f; }
-    else { S = -t * t * (2.0f * t - 3.0f); dS = (6.0f * t - 6.0f * t * t) / P.poly_width_b; }
+    else { S = -t * t * (2.0f * t - 3.0f); dS = (6.0f * t - 6.0f * t * t) * P.inv_poly_width_b; }
     float c6 = P.sqrtC6[ei] * P.sqrtC6[ej];
     float Rs = P.Rvdw[ei] + P.Rvdw[ej];
-    float iRp = 1.0f / Rp;
     float iRp2 = iRp * iRp;
     float Rp6i = iRp2 * iRp2 * iRp2;
     float xi = Rs * iRp;                    // 1/x
     float xi2 = xi * xi, xi6 = xi2 * xi2 * xi2;
     float xm12 = xi6 * xi6;                 // x^-12
-    float damp = 1.0f / (1.0f + 6.0f * xm12);
+    float damp = __frcp_rn(1.0f + 6.0f * xm12);
     float w = -S * c6 * Rp6i * damp;
     float ddamp = 72.0f * xm12 * iRp * damp * damp;
-    float dw = -c6 * (dS * Rp6i * damp - 6.0f * S * Rp6i * iRp * damp + S * Rp6i * ddamp);
+    float dw = -c6 * Rp6i * (dS * damp - 6.0f * S * iRp * damp + S * ddamp);
     A.evdw += w;
     dEdR += B * dw;
   }
   // d e_ij / d x_i = dEdR * B * (x_i - x_j)/r ; (dx,dy,dz) = x_j - x_i
-  float sc = -wj * dEdR * B / r;
+  float sc = -wj * dEdR * B * ir;
   A.gx += sc * dx; A.gy += sc * dy; A.gz += sc * dz;
 }
 
@@ -213,8 +225,8 @@ k_pair(const SAtom* __restrict__ sat, const float4* __restrict__ pq, const int32
   auto eval = [&](int j) {
     SAtom a = sat[j];
     float ddx = (float)(a.x - ci.x), ddy = (float)(a.y - ci.y), ddz = (float)(a.z - ci.z);
-    float r = sqrtf(ddx * ddx + ddy * ddy + ddz * ddz);
-    pair_eval(P, r, ddx, ddy, ddz, qi, pq[j].w, ei, a.e, (a.slot < nreal_slots) ? 1.0f : 0.5f, do_vdw, A);
+    float d2 = ddx * ddx + ddy * ddy + ddz * ddz;
+    pair_eval(P, d2, ddx, ddy, ddz, qi, pq[j].w, ei, a.e, (a.slot < nreal_slots) ? 1.0f : 0.5f, do_vdw, A);
   };
   for (int x = x0; x <= x1; x++) {
     // distance from the centre to the column's slab in x, then the same in y
