@@ -407,6 +407,7 @@ static SysView make_view(tm_ctx* c, int64_t nslots, int64_t nmol, int64_t maxnat
   s.ncells_cap = nslots + 1024;
   s.slab_rank = 0; s.slab_world = 1;
   s.slab_g[0] = s.slab_g[1] = s.slab_g[2] = 0.0;
+  s.window_on = 0; s.win_lo = 0.0; s.win_hi = 0.0;
   return s;
 }
 
@@ -753,6 +754,12 @@ extern "C" int tm_slab_phase_a(tm_ctx* c, const double* xyz_dev, const int32_t* 
   if (world > 1) {
     s.ncent_max = std::min<int64_t>(nreal, nreal / world + nreal / (2 * world) + 4096);
     s.nrows = s.ncent_max + (int64_t)TM_ROW_TILE * c->hp.n_ele;
+    // bin only the slab and its halo: everything an owned centre can interact with lies within the largest cutoff
+    double gn = sqrt(s.slab_g[0] * s.slab_g[0] + s.slab_g[1] * s.slab_g[1] + s.slab_g[2] * s.slab_g[2]);   // 1 / plane spacing
+    double halo = (std::max(c->params.ee_cutoff_off, c->params.r_Rc) + 0.05) * gn + 1e-6;
+    s.window_on = 1;
+    s.win_lo = (rank == 0) ? -halo - 1e-3 : (double)rank / world - halo;
+    s.win_hi = (rank == world - 1) ? 1.0 + halo + 1e-3 : (double)(rank + 1) / world + halo;
   }
   c->slab_view = s;
   if ((rc = stage_a(c, s))) return rc;

@@ -24,7 +24,7 @@
 #define TC_THREADS 320           // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quarter)
 #define TC_EPI_WARPS 8
 #define TC_NACC 4                 // TMEM accumulator buffers (4 x 128 columns = all 512)
-#define TC_CHUNK 1                // k-blocks accumulated inside TMEM before the fp32 register add
+#define TC_CHUNK 2                // k-blocks accumulated inside TMEM before the fp32 register add
 #define TC_MAX_GROUPS (2 * TM_MAX_ELE)
 // 32x32 fp32 transpose tile, 16-byte chunks XOR-swizzled by the row so that both the row-wise (thread = row) and the
 // slab-wise (8 lanes per row) 128-bit accesses are bank-conflict free without padding

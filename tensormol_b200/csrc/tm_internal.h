@@ -103,6 +103,9 @@ struct SysView {
   // slab ownership filter on centres (fraction of x-range), world==1 -> everything
   int slab_rank, slab_world;
   double slab_g[3];     // first row of the inverse lattice: frac = pos . slab_g
+  // slab runs only: slots whose fractional coordinate lies outside [win_lo, win_hi] (slab + interaction halo) are not binned
+  int window_on;
+  double win_lo, win_hi;
 };
 
 struct tm_ctx {

@@ -66,15 +66,23 @@ int tm_launch_tessellate(tm_ctx* c, const double* xyz_real, const int32_t* Z_rea
 }
 
 // ---------------------------------------------------------------- bbox
+// Slab runs bin only the slots inside the owned slab plus the interaction halo (fractional coordinate window along the
+// first lattice vector); everything else never enters the cell list of this rank.
+struct Window { int on; double gx, gy, gz, lo, hi; };
+__device__ __forceinline__ bool slot_in_window(const double* __restrict__ pos, int64_t t, const Window& w) {
+  if (!w.on) return true;
+  double f = pos[3 * t] * w.gx + pos[3 * t + 1] * w.gy + pos[3 * t + 2] * w.gz;
+  return f >= w.lo && f <= w.hi;
+}
 __global__ void k_bbox_init(unsigned long long* bb) {
   if (threadIdx.x < 3) bb[threadIdx.x] = 0xffffffffffffffffull;   // mins
   else if (threadIdx.x < 6) bb[threadIdx.x] = 0ull;               // maxs
 }
 
-__global__ void k_bbox(const double* __restrict__ pos, const int32_t* __restrict__ Z, int64_t n, unsigned long long* bb) {
+__global__ void k_bbox(const double* __restrict__ pos, const int32_t* __restrict__ Z, int64_t n, Window win, unsigned long long* bb) {
   double mn[3] = {1e300, 1e300, 1e300}, mx[3] = {-1e300, -1e300, -1e300};
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
-    if (Z[t] <= 0) continue;
+    if (Z[t] <= 0 || !slot_in_window(pos, t, win)) continue;
 #pragma unroll
     for (int d = 0; d < 3; d++) {
       double v = pos[3 * t + d];
@@ -136,11 +144,11 @@ __global__ void k_grid_params(const unsigned long long* bb, double rc, int64_t n
 
 // per slot: cell id and arrival rank inside the cell
 __global__ void k_cell_count(const double* __restrict__ pos, const int32_t* __restrict__ Z, int64_t n, int64_t maxnatom,
-                             const GridParams* __restrict__ gp, int32_t* __restrict__ cellid, int32_t* __restrict__ rank,
+                             const GridParams* __restrict__ gp, Window win, int32_t* __restrict__ cellid, int32_t* __restrict__ rank,
                              int32_t* __restrict__ count) {
   GridParams g = *gp;
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
-    if (Z[t] <= 0) { cellid[t] = -1; rank[t] = -1; continue; }   // rank[] is reused as sidx_of_slot (-1 = absent)
+    if (Z[t] <= 0 || !slot_in_window(pos, t, win)) { cellid[t] = -1; rank[t] = -1; continue; }   // rank[] is reused as sidx_of_slot (-1 = absent)
     int cx = cell_coord(pos[3 * t], g.ox, g.inv_cell, g.gx);
     int cy = cell_coord(pos[3 * t + 1], g.oy, g.inv_cell, g.gy);
     int cz = cell_coord(pos[3 * t + 2], g.oz, g.inv_cell, g.gz);
@@ -311,10 +319,11 @@ int tm_launch_nlist_build(tm_ctx* c, const SysView& s, double rc_grid) {
   unsigned long long* bb = (unsigned long long*)c->b_bbox.p;
   GridParams* gp = (GridParams*)c->b_grid.p;
   k_bbox_init<<<1, 32, 0, c->stream>>>(bb);
-  k_bbox<<<blocks, 256, 0, c->stream>>>((const double*)c->b_pos.p, (const int32_t*)c->b_Z.p, n, bb);
+  Window win{s.window_on, s.slab_g[0], s.slab_g[1], s.slab_g[2], s.win_lo, s.win_hi};
+  k_bbox<<<blocks, 256, 0, c->stream>>>((const double*)c->b_pos.p, (const int32_t*)c->b_Z.p, n, win, bb);
   k_grid_params<<<1, 1, 0, c->stream>>>(bb, rc_grid, s.nmol, s.ncells_cap, gp);
   TM_CUDA(cudaMemsetAsync(c->b_count.p, 0, (s.ncells_cap + 8) * 4, c->stream));
-  k_cell_count<<<blocks, 256, 0, c->stream>>>((const double*)c->b_pos.p, (const int32_t*)c->b_Z.p, n, s.maxnatom, gp,
+  k_cell_count<<<blocks, 256, 0, c->stream>>>((const double*)c->b_pos.p, (const int32_t*)c->b_Z.p, n, s.maxnatom, gp, win,
                                               (int32_t*)c->b_cellid.p, (int32_t*)c->b_rank.p, (int32_t*)c->b_count.p);
   c->launches += 4;
   if ((rc = scan_exclusive(c, (const int32_t*)c->b_count.p, (int32_t*)c->b_cstart.p, s.ncells_cap, (int32_t*)c->b_scan_tmp.p))) return rc;
