@@ -162,7 +162,8 @@ int tm_eval_images(tm_ctx* ctx, const double* xyz_tess, const int32_t* Z_tess, i
 
 /* Periodic from the primitive cell: wraps (Lattice.ModuloLattice must already be applied by
  * the caller), tessellates on the device exactly like Lattice.TessLattice (Periodic.py:131-168)
- * with the given ntess, then evaluates like tm_eval_images.  lattice [9] row vectors. */
+ * with the given ntess, then evaluates like tm_eval_images, except that out->charge is [nreal]
+ * (the image blocks would be copies).  lattice [9] row vectors. */
 int tm_eval_lattice(tm_ctx* ctx, const double* xyz, const int32_t* Z, int64_t nreal, const double* lattice, int ntess,
                     int flags, tm_outputs* out);
 

@@ -679,7 +679,7 @@ extern "C" int tm_eval_lattice(tm_ctx* c, const double* xyz, const int32_t* Z, i
   if ((rc = prepare_lattice(c, (const double*)c->b_acc.p, (const int32_t*)((char*)c->b_acc.p + bx), nreal, lattice, ntess, &s))) return rc;
   OutLayout o = out_layout(1, nreal);
   if ((rc = run_all(c, s, flags, o))) return rc;
-  rc = deliver(c, s, flags, o, out, s.nslots);
+  rc = deliver(c, s, flags, o, out, nreal);   // charges of the real atoms only: the image blocks are copies
   c->last.n_centres = nreal;
   return rc;
 }

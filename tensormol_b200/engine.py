@@ -246,8 +246,7 @@ class Engine:
         Z = np.ascontiguousarray(Z, np.int32)
         lat = np.ascontiguousarray(lattice, np.float64).reshape(9)
         n = xyz.shape[0]
-        nt = n * (2 * int(ntess) + 1) ** 3
-        res, out = self._periodic_result(n, nt, descriptors)
+        res, out = self._periodic_result(n, n, descriptors)   # charges of the real atoms only
         check(self.lib.tm_eval_lattice(self.ctx, _ptr(xyz), _ptr(Z), n, _ptr(lat), int(ntess), self._flags(do_force, has_vdw, descriptors, fold), C.byref(out)),
               "tm_eval_lattice")
         return res
