@@ -245,7 +245,7 @@ def run_b200(args, rank, world, local_rank):
     line = {"metric": "atom-steps/s (energy+force)", "value": value, "unit": "atom-steps/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "strong" if world > 1 else "weak", "vs_baseline": None,
-            "dtype": {0: "f32", 1: "tf32x3", 2: "bf16"}[args.gemm_mode], "data": "synthetic",
+            "dtype": {0: "f32", 1: "f16x2-split (fp32 accumulate)"}[args.gemm_mode], "data": "synthetic",
             "config": {"workload": f"{natom}-atom periodic water box (C4: {args.nx}^3 waters, L={lat[0, 0]:.3f} A, 27 images), BP+EE single-point energy+force, nets {HIDDEN}, random-init weights seed 0",
                        "l2": "flushed between timed iterations (512 MiB write)", "parallelism": f"slab{world}" if world > 1 else "single",
                        "gemm_mode": args.gemm_mode},

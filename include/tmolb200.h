@@ -53,8 +53,8 @@ enum { TM_ACT_SIGMOID_WITH_PARAM = 0, TM_ACT_RELU = 1, TM_ACT_SOFTPLUS = 2, TM_A
 /* GEMM arithmetic of the per-element MLPs */
 enum {
   TM_GEMM_FP32 = 0,      /* fp32 FFMA tiles (parity reference mode of the library) */
-  TM_GEMM_TC_3XTF32 = 1, /* tcgen05 kind::tf32, 3-term split, fp32 accumulate in TMEM (default when available) */
-  TM_GEMM_TC_BF16 = 2    /* tcgen05 kind::f16 bf16 single pass (throughput mode; outside the 1e-5 energy tolerance) */
+  TM_GEMM_TC_SPLIT = 1   /* tcgen05 kind::f16 on split operands x = hi + lo/2048 (two fp16 planes, 22 significant bits),
+                            3 MMAs per K-step, fp32 accumulation in TMEM + registers (default) */
 };
 
 /* evaluation flags */

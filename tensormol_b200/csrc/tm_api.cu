@@ -1,6 +1,7 @@
 // C-ABI of libtmolb200.so (see include/tmolb200.h): context, weights, evaluation pipelines and the
 // MolEmb / Neighbors.py compatible neighbour-table entry points.
 #include "tm_internal.h"
+#include <cuda_fp16.h>
 #include <algorithm>
 #include <cmath>
 #include <cstdarg>
@@ -215,7 +216,7 @@ extern "C" int tm_set_stream(tm_ctx* c, void* s) {
   return TM_OK;
 }
 extern "C" int tm_set_gemm_mode(tm_ctx* c, int mode) {
-  if (!c || mode < 0 || mode > 2) { tm_set_error("bad gemm mode"); return TM_EINVAL; }
+  if (!c || mode < 0 || mode > 1) { tm_set_error("bad gemm mode %d (0 = fp32, 1 = tcgen05 split fp16)", mode); return TM_EINVAL; }
   c->gemm_mode = mode;
   return TM_OK;
 }
@@ -269,28 +270,26 @@ extern "C" int tm_set_weights(tm_ctx* c, int net, int ele_index, int layer, cons
   TM_CUDA(cudaMemcpy(L.W, w.data(), w.size() * 4, cudaMemcpyHostToDevice));
   TM_CUDA(cudaMemcpy(L.WT, wt.data(), wt.size() * 4, cudaMemcpyHostToDevice));
   TM_CUDA(cudaMemcpy(L.b, bb.data(), bb.size() * 4, cudaMemcpyHostToDevice));
-  // hi/lo tf32 planes for the tcgen05 3xTF32 path: hi = rna_tf32(x) (13 low mantissa bits cleared after
-  // rounding to nearest, ties away), lo = x - hi (exact in fp32)
-  auto split = [](const std::vector<float>& src, std::vector<float>& dst) {
+  // split-fp16 planes for the tcgen05 path: hi = rn_f16(x), lo = rn_f16((x - hi) * 2048)   (tm_gemm_tc.cu)
+  bool range_ok = true;
+  auto split = [&range_ok](const std::vector<float>& src, std::vector<__half>& dst) {
     size_t n = src.size();
     dst.resize(2 * n);
     for (size_t i = 0; i < n; i++) {
-      uint32_t u;
-      memcpy(&u, &src[i], 4);
-      u = (u + 0x1000u) & 0xffffe000u;
-      float hi;
-      memcpy(&hi, &u, 4);
+      if (!(fabsf(src[i]) <= 65000.f)) range_ok = false;
+      __half hi = __float2half_rn(src[i]);
       dst[i] = hi;
-      dst[n + i] = src[i] - hi;
+      dst[n + i] = __float2half_rn((src[i] - __half2float(hi)) * 2048.0f);
     }
   };
-  std::vector<float> ws, wts;
+  std::vector<__half> ws, wts;
   split(w, ws);
   split(wt, wts);
-  if (!L.Ws) TM_CUDA(cudaMalloc(&L.Ws, ws.size() * 4));
-  if (!L.WTs) TM_CUDA(cudaMalloc(&L.WTs, wts.size() * 4));
-  TM_CUDA(cudaMemcpy(L.Ws, ws.data(), ws.size() * 4, cudaMemcpyHostToDevice));
-  TM_CUDA(cudaMemcpy(L.WTs, wts.data(), wts.size() * 4, cudaMemcpyHostToDevice));
+  if (!range_ok) { tm_set_error("tm_set_weights: a weight is outside the fp16 range of the tensor-core path"); return TM_EINVAL; }
+  if (!L.Ws) TM_CUDA(cudaMalloc(&L.Ws, ws.size() * 2));
+  if (!L.WTs) TM_CUDA(cudaMalloc(&L.WTs, wts.size() * 2));
+  TM_CUDA(cudaMemcpy(L.Ws, ws.data(), ws.size() * 2, cudaMemcpyHostToDevice));
+  TM_CUDA(cudaMemcpy(L.WTs, wts.data(), wts.size() * 2, cudaMemcpyHostToDevice));
   N.set[layer] = true;
   return TM_OK;
 }
@@ -494,6 +493,7 @@ static int check_flags(tm_ctx* c) {
   TM_CUDA(cudaStreamSynchronize(c->stream));
   if (f[0] & 2) { tm_set_error("neighbour table capacity exceeded (>256 radial neighbours per centre on average)"); return TM_ECAP; }
   if (f[0] & 4) { tm_set_error("more than %d neighbours inside the angular cutoff of one centre", TM_ANG_CAP); return TM_ECAP; }
+  if (f[0] & 16) { tm_set_error("an MLP activation left the fp16 range of the tensor-core path (use gemm mode 0)"); return TM_ECAP; }
   return TM_OK;
 }
 

@@ -1,49 +1,66 @@
-// tcgen05 grouped GEMM for the per-element MLPs (sm_100a): 3xTF32 split precision, fp32 accumulate in TMEM.
+// tcgen05 grouped GEMM for the per-element MLPs (sm_100a): split-fp16 operands, fp32 accumulation.
 //
 //   C[rows,N] = epi( A[rows,K] * B^T ),  A row-major (K contiguous), B given K-major as [N][K]
 //
-// Why 3xTF32: the reference is float64 and the parity bar is 1e-5 relative on the energy
-// (BASELINE.json north_star); single-pass tf32/bf16 misses it (weight rounding is systematic over atoms).
-// Operands are stored pre-split in HBM as two fp32 planes  x = hi + lo,  hi = rna_tf32(x), lo = x - hi
-// (weights once at tm_set_weights, activations by the producing epilogue), and every K-step issues
-//   D += A_hi*B_hi + A_lo*B_hi + A_hi*B_lo            (the dropped lo*lo term is ~2^-22 relative)
+// Why split precision: the reference is float64 and the parity bar is 1e-5 relative on the energy
+// (BASELINE.json north_star); a single fp16/bf16/tf32 pass misses it (weight rounding is systematic over atoms).
+// Every operand lives in HBM as two fp16 planes
+//     x = hi + lo / 2048 ,   hi = rn_f16(x) ,   lo = rn_f16((x - hi) * 2048)
+// (weights once at tm_set_weights, activations by the producing epilogue).  hi carries 11 significant bits, the
+// scaled lo the next 11 (the 2^11 scale keeps it out of the fp16 subnormal range: absolute floor 1.5e-11), which
+// is the same 22 bits as a 3xTF32 split but on the kind::f16 pipe: twice the MMA rate and half the operand bytes.
+// Every K-step issues
+//     D_main  += A_hi*B_hi                      D_cross += A_lo*B_hi + A_hi*B_lo      (the lo*lo term is ~2^-22)
+// into two TMEM accumulators and the result is  D_main + D_cross / 2048.
+//
+// The tensor core adds into its accumulator with truncation: over a long K loop that is a systematic bias
+// (measured 1.6e-5 relative on the energy for K=512 in one accumulator).  The K loop is therefore cut into chunks
+// of TC_CHUNK k-blocks; each chunk accumulates into a fresh TMEM pair which the epilogue warps drain into fp32
+// REGISTER accumulators with round-to-nearest adds.
 //
 // Structure (one CTA per SM, persistent over a device-side tile list so row counts never visit the host):
 //   warp 0      TMA producer   cp.async.bulk.tensor.2d, 128B swizzle, mbarrier expect_tx       (1 lane)
-//   warp 1      MMA issuer     tcgen05.mma.cta_group::1.kind::tf32, 128 x BN x 8, commit->mbarrier (1 lane)
-//   warps 2..5  epilogue       tcgen05.ld 32x32b.x32 -> bias/activation (or act' product) -> hi/lo split -> global
-// TMEM: 2 accumulator buffers of BN columns (double buffered so the epilogue of tile i overlaps the MMAs of i+1).
+//   warp 1      MMA issuer     tcgen05.mma.cta_group::1.kind::f16, 128 x 128 x 16, commit->mbarrier (1 lane)
+//   warps 2..9  epilogue       tcgen05.ld 32x32b.x32 -> register accumulators -> bias/activation (or act' product)
+//                              -> hi/lo split -> swizzled smem transpose -> 128-bit coalesced global stores
+// TMEM: TC_NPAIR pairs of (main, cross) accumulators, 128 columns each (all 512 columns).
 #include "tm_internal.h"
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <cstdlib>
 #include <map>
 #include <tuple>
 
 #define TC_BM 128
-#define TC_BK 32                 // 32 fp32 = 128 bytes = one swizzle row
+#define TC_BN 128
+#define TC_BK 64                 // 64 fp16 = 128 bytes = one swizzle row
+#define TC_STAGES 3
 #define TC_THREADS 320           // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quarter)
 #define TC_EPI_WARPS 8
-#define TC_NACC 4                 // TMEM accumulator buffers (4 x 128 columns = all 512)
-#define TC_CHUNK 2                // k-blocks accumulated inside TMEM before the fp32 register add
+#define TC_NPAIR 2               // (main, cross) accumulator pairs in flight: 2 x 2 x 128 columns = all 512
+#define TC_CHUNK 2               // k-blocks (of 64) accumulated inside TMEM before the fp32 register add
 #define TC_MAX_GROUPS (2 * TM_MAX_ELE)
-// 32x32 fp32 transpose tile, 16-byte chunks XOR-swizzled by the row so that both the row-wise (thread = row) and the
-// slab-wise (8 lanes per row) 128-bit accesses are bank-conflict free without padding
+#define TC_LO_SCALE 2048.0f
+#define TC_LO_INV (1.0f / 2048.0f)
+// 32 rows x 128 bytes transpose tile, 16-byte chunks XOR-swizzled by the row so that both the row-wise (thread = row)
+// and the slab-wise (several lanes per row) 128-bit accesses are bank-conflict free without padding.  Float index.
 #define TB_OFF(r, c4) ((r) * 32 + ((((c4) ^ ((r) & 7))) << 2))
 
 struct alignas(64) TcGroup {
   CUtensorMap mapA_hi, mapA_lo, mapB_hi, mapB_lo;
   const float* bias;
-  const float* Hmul_hi;
-  const float* Hmul_lo;
-  float* C_hi;
-  float* C_lo;
+  const __half* Hmul_hi;
+  const __half* Hmul_lo;
+  __half* C_hi;
+  __half* C_lo;
+  float* C32;      // TM_EPI_NONE: single fp32 plane
   int ldc, K, N, ele;
 };
 struct alignas(64) TcParams {
   TcGroup g[TC_MAX_GROUPS];
-  int ngroups, epilogue, act_kind;
+  int ngroups, act_kind;
   float act_alpha;
-  int dbg;   // development switches (TM_TC_DBG): 1 = skip the output phase, 2 = skip the TMA loads
+  int32_t* flags;   // bit 4 (16): a value left the fp16 range
 };
 
 // ------------------------------------------------------------------------------------------------ PTX helpers
@@ -97,12 +114,12 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
   d |= (uint64_t)2 << 61;                   // SWIZZLE_128B
   return d;
 }
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
       "}" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
@@ -116,28 +133,36 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
         "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
       : "r"(taddr));
 }
-__device__ __forceinline__ float tf32_hi(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
+__device__ __forceinline__ float ex2_approx(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float lg2_approx(float x) {
+  float r;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
 }
 
-__device__ __forceinline__ float tc_act_fwd(float z, int kind, float alpha) {
+// activation with the bias folded in.  The sigmoid_with_param (softplus(alpha z)/alpha) branch works in base 2:
+//   t2 = alpha*log2e*(z+b);  h = (max(t2,0) + lg2(1 + 2^-|t2|)) * ln2/alpha      (2 MUFU + 5 FP32 per element;
+//   absolute error of lg2.approx near 1 is ~1e-7, i.e. <= 1e-9 on h after the 1/alpha)
+__device__ __forceinline__ float tc_act_fwd(float z, float b, int kind, float alpha) {
   switch (kind) {
     case TM_ACT_SIGMOID_WITH_PARAM: {
-      // fast intrinsics: absolute error of log(1+e) <= ~1e-7, i.e. <= 1e-9 on h after the 1/alpha (alpha = 100)
-      float t = alpha * z;
-      return (fmaxf(t, 0.f) + __logf(1.0f + __expf(-fabsf(t)))) * __frcp_rn(alpha);
+      const float a2 = alpha * 1.4426950408889634f;
+      float t2 = fmaf(a2, z, a2 * b);
+      return (fmaxf(t2, 0.f) + lg2_approx(1.0f + ex2_approx(-fabsf(t2)))) * (0.6931471805599453f / alpha);
     }
-    case TM_ACT_RELU: return fmaxf(z, 0.f);
-    case TM_ACT_SOFTPLUS: return fmaxf(z, 0.f) + log1pf(expf(-fabsf(z)));
-    case TM_ACT_TANH: return tanhf(z);
-    default: return 1.0f / (1.0f + expf(-z));
+    case TM_ACT_RELU: return fmaxf(z + b, 0.f);
+    case TM_ACT_SOFTPLUS: return fmaxf(z + b, 0.f) + log1pf(expf(-fabsf(z + b)));
+    case TM_ACT_TANH: return tanhf(z + b);
+    default: return 1.0f / (1.0f + expf(-(z + b)));
   }
 }
 __device__ __forceinline__ float tc_act_bwd(float h, int kind, float alpha) {
   switch (kind) {
-    case TM_ACT_SIGMOID_WITH_PARAM: return 1.0f - __expf(-alpha * h);
+    case TM_ACT_SIGMOID_WITH_PARAM: return 1.0f - ex2_approx(-alpha * 1.4426950408889634f * h);
     case TM_ACT_RELU: return h > 0.f ? 1.f : 0.f;
     case TM_ACT_SOFTPLUS: return -expm1f(-h);
     case TM_ACT_TANH: return 1.0f - h * h;
@@ -145,25 +170,40 @@ __device__ __forceinline__ float tc_act_bwd(float h, int kind, float alpha) {
   }
 }
 
+// x0,x1 -> packed hi halves and packed scaled-lo halves
+__device__ __forceinline__ void split2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  __half2 h = __floats2half2_rn(x0, x1);
+  float2 hf = __half22float2(h);
+  __half2 l = __floats2half2_rn((x0 - hf.x) * TC_LO_SCALE, (x1 - hf.y) * TC_LO_SCALE);
+  hi = *reinterpret_cast<uint32_t*>(&h);
+  lo = *reinterpret_cast<uint32_t*>(&l);
+}
+__device__ __forceinline__ float2 join2(uint32_t hi, uint32_t lo) {
+  float2 a = __half22float2(*reinterpret_cast<__half2*>(&hi));
+  float2 b = __half22float2(*reinterpret_cast<__half2*>(&lo));
+  return make_float2(fmaf(b.x, TC_LO_INV, a.x), fmaf(b.y, TC_LO_INV, a.y));
+}
+
 // ------------------------------------------------------------------------------------------------ kernel
-// EPI: TM_EPI_* (compile time, so each instantiation carries ONE epilogue: the runtime-switched version was
+// EPI: TM_EPI_* (compile time, so each instantiation carries ONE epilogue: a runtime-switched version was
 // 30k SASS instructions and stalled on instruction fetch); ACTK: activation kind or -1 for a runtime switch.
-template <int BN, int STAGES, int EPI, int ACTK>
+template <int EPI, int ACTK>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_gemm_tc(const __grid_constant__ TcParams P, const int32_t* __restrict__ rowmeta) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  constexpr uint32_t A_BYTES = TC_BM * TC_BK * 4;    // 16 KB per plane
-  constexpr uint32_t B_BYTES = BN * TC_BK * 4;
+  constexpr int BN = TC_BN, STAGES = TC_STAGES;
+  constexpr uint32_t A_BYTES = TC_BM * TC_BK * 2;    // 16 KB per plane
+  constexpr uint32_t B_BYTES = BN * TC_BK * 2;
   constexpr uint32_t STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint64_t* full_bar = (uint64_t*)(smem + STAGES * STAGE_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tfull_bar = empty_bar + STAGES;     // [TC_NACC]
-  uint64_t* tempty_bar = tfull_bar + TC_NACC;   // [TC_NACC]
-  uint32_t* tmem_slot = (uint32_t*)(tempty_bar + TC_NACC);
+  uint64_t* tfull_bar = empty_bar + STAGES;      // [TC_NPAIR]
+  uint64_t* tempty_bar = tfull_bar + TC_NPAIR;   // [TC_NPAIR]
+  uint32_t* tmem_slot = (uint32_t*)(tempty_bar + TC_NPAIR);
   int* tile_base = (int*)(tmem_slot + 4);       // [TC_MAX_GROUPS+1]
   int* row_first = tile_base + TC_MAX_GROUPS + 1;   // [TC_MAX_GROUPS]
-  float* tbuf = (float*)(((uintptr_t)(row_first + TC_MAX_GROUPS) + 15) & ~(uintptr_t)15);  // TC_EPI_WARPS x [32][32] XOR-swizzled transpose tiles (16-byte aligned)
+  float* tbuf = (float*)(((uintptr_t)(row_first + TC_MAX_GROUPS) + 15) & ~(uintptr_t)15);  // TC_EPI_WARPS x 4 KB transpose tiles
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -177,11 +217,11 @@ k_gemm_tc(const __grid_constant__ TcParams P, const int32_t* __restrict__ rowmet
     }
     tile_base[P.ngroups] = acc;
     for (int s = 0; s < STAGES; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int a = 0; a < TC_NACC; a++) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], TC_EPI_WARPS); }
+    for (int a = 0; a < TC_NPAIR; a++) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], TC_EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) {   // TMEM allocation by one warp: 2 accumulators of BN fp32 columns
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)(TC_NACC * BN)));
+  if (warp == 1) {   // TMEM allocation by one warp
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)(TC_NPAIR * 2 * BN)));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -217,7 +257,6 @@ k_gemm_tc(const __grid_constant__ TcParams P, const int32_t* __restrict__ rowmet
         for (int kb = 0; kb < nkb; kb++) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* st = smem + stage * STAGE_BYTES;
-          if (P.dbg & 2) { mbar_arrive(&full_bar[stage]); if (++stage == STAGES) { stage = 0; phase ^= 1; } continue; }
           mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
           tma_load_2d(&G.mapA_hi, &full_bar[stage], st, kb * TC_BK, row0);
           tma_load_2d(&G.mapA_lo, &full_bar[stage], st + A_BYTES, kb * TC_BK, row0);
@@ -229,14 +268,9 @@ k_gemm_tc(const __grid_constant__ TcParams P, const int32_t* __restrict__ rowmet
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    // The K loop is cut into chunks of TC_CHUNK k-blocks; each chunk accumulates into a fresh TMEM buffer
-    // (ping-pong) that the epilogue warps drain into fp32 REGISTER accumulators with round-to-nearest adds.
-    // Reason: the tensor core adds into its accumulator with truncation, and over a K=512 loop (192 MMA
-    // accumulations per output) that is a systematic ~1.6e-5 relative bias on the energy (measured); 24
-    // accumulations per chunk keep it below 1e-6.
     if (elect_one()) {
-      // instruction descriptor: D=f32, A=B=tf32, both K-major, N=BN, M=128
-      constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      // instruction descriptor: D=f32, A=B=f16, both K-major, N=BN, M=128
+      constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
       int stage = 0;
       uint32_t phase = 0;
       uint32_t chunk_it = 0;
@@ -245,11 +279,12 @@ k_gemm_tc(const __grid_constant__ TcParams P, const int32_t* __restrict__ rowmet
         decode(t, g, rt, ct);
         int nkb = P.g[g].K / TC_BK;
         for (int kb0 = 0; kb0 < nkb; kb0 += TC_CHUNK, chunk_it++) {
-          int acc = chunk_it % TC_NACC;
-          uint32_t acc_phase = (chunk_it / TC_NACC) & 1;
-          mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+          int pair = chunk_it % TC_NPAIR;
+          uint32_t pair_phase = (chunk_it / TC_NPAIR) & 1;
+          mbar_wait(&tempty_bar[pair], pair_phase ^ 1);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+          uint32_t d_main = tmem_base + (uint32_t)(pair * 2 * BN);
+          uint32_t d_cross = d_main + BN;
           int kb1 = min(kb0 + TC_CHUNK, nkb);
           for (int kb = kb0; kb < kb1; kb++) {
             mbar_wait(&full_bar[stage], phase);
@@ -257,23 +292,18 @@ k_gemm_tc(const __grid_constant__ TcParams P, const int32_t* __restrict__ rowmet
             uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
             uint64_t a_hi = umma_desc(sa), a_lo = umma_desc(sa + A_BYTES);
             uint64_t b_hi = umma_desc(sa + 2 * A_BYTES), b_lo = umma_desc(sa + 2 * A_BYTES + B_BYTES);
-            // small correction terms first (accumulator still small, so its truncating adds cost nothing),
-            // then the hi*hi terms: only TC_BK/8 full-magnitude accumulations per chunk
 #pragma unroll
-            for (int k = 0; k < TC_BK / 8; k++) {
-              uint64_t koff = (uint64_t)((k * 8 * 4) >> 4);   // 32 bytes per K=8 step inside the 128B swizzle row
-              umma_tf32(d_tmem, a_lo + koff, b_hi + koff, idesc, ((kb - kb0) | k) ? 1u : 0u);
-              umma_tf32(d_tmem, a_hi + koff, b_lo + koff, idesc, 1u);
-            }
-#pragma unroll
-            for (int k = 0; k < TC_BK / 8; k++) {
-              uint64_t koff = (uint64_t)((k * 8 * 4) >> 4);
-              umma_tf32(d_tmem, a_hi + koff, b_hi + koff, idesc, 1u);
+            for (int k = 0; k < TC_BK / 16; k++) {
+              uint64_t koff = (uint64_t)((k * 16 * 2) >> 4);   // 32 bytes per K=16 step inside the 128B swizzle row
+              uint32_t acc = ((kb - kb0) | k) ? 1u : 0u;
+              umma_f16(d_main, a_hi + koff, b_hi + koff, idesc, acc);
+              umma_f16(d_cross, a_lo + koff, b_hi + koff, idesc, acc);
+              umma_f16(d_cross, a_hi + koff, b_lo + koff, idesc, 1u);
             }
             umma_commit(&empty_bar[stage]);          // frees the smem stage once these MMAs have read it
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
-          umma_commit(&tfull_bar[acc]);              // chunk complete -> epilogue drains it
+          umma_commit(&tfull_bar[pair]);             // chunk complete -> epilogue drains it
         }
       }
     }
@@ -282,11 +312,12 @@ k_gemm_tc(const __grid_constant__ TcParams P, const int32_t* __restrict__ rowmet
     // warp%4 selects the TMEM lane quarter (hardware rule); the two warps of a quarter split the BN columns.
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;
-    constexpr int NC = BN / 2;                     // columns per thread
+    constexpr int NC = BN / 2;                     // columns per thread (64)
     const int act_kind = (ACTK >= 0) ? ACTK : P.act_kind;
     const float act_alpha = P.act_alpha;
     float* tb = tbuf + (warp - 2) * (32 * 32);
     uint32_t chunk_it = 0;
+    float vmax = 0.f;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       int g, rt, ct;
       decode(t, g, rt, ct);
@@ -296,90 +327,128 @@ k_gemm_tc(const __grid_constant__ TcParams P, const int32_t* __restrict__ rowmet
 #pragma unroll
       for (int i = 0; i < NC; i++) accr[i] = 0.f;
       for (int kb0 = 0; kb0 < nkb; kb0 += TC_CHUNK, chunk_it++) {
-        int acc = chunk_it % TC_NACC;
-        uint32_t acc_phase = (chunk_it / TC_NACC) & 1;
-        mbar_wait(&tfull_bar[acc], acc_phase);
+        int pair = chunk_it % TC_NPAIR;
+        uint32_t pair_phase = (chunk_it / TC_NPAIR) & 1;
+        mbar_wait(&tfull_bar[pair], pair_phase);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        uint32_t taddr = tmem_base + (uint32_t)(pair * 2 * BN + half * NC) + ((uint32_t)(q * 32) << 16);
         uint32_t v[NC];
 #pragma unroll
-        for (int c = 0; c < NC / 32; c++)
-          tmem_ld32(tmem_base + (uint32_t)(acc * BN + half * NC + c * 32) + ((uint32_t)(q * 32) << 16), v + c * 32);
+        for (int c = 0; c < NC / 32; c++) tmem_ld32(taddr + c * 32, v + c * 32);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int i = 0; i < NC; i++) accr[i] += __uint_as_float(v[i]);
+#pragma unroll
+        for (int c = 0; c < NC / 32; c++) tmem_ld32(taddr + BN + c * 32, v + c * 32);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty_bar[acc]);   // TMEM buffer is free again; the adds below overlap the next MMAs
+        if (lane == 0) mbar_arrive(&tempty_bar[pair]);   // TMEM pair is free again; the adds below overlap the next MMAs
 #pragma unroll
-        for (int i = 0; i < NC; i++) accr[i] += __uint_as_float(v[i]);
+        for (int i = 0; i < NC; i++) accr[i] = fmaf(__uint_as_float(v[i]), TC_LO_INV, accr[i]);
       }
-      // Output: thread = row of the warp's 32-row band.  Each 32x32 block goes through a shared tile (XOR-swizzled,
-      // 128-bit accesses, conflict-free per quarter warp) so that every global access is a 128-bit piece of a
-      // full 128-byte row segment: one warp instruction moves 4 rows x 128 B.
-      if (P.dbg & 1) continue;
-      int64_t wrow0 = (int64_t)row_first[g] + (int64_t)rt * TC_BM + q * 32;
-      int n0 = ct * BN + half * NC;
-      const int trow = lane >> 3, tcol = (lane & 7) * 4;     // coordinates of this lane inside a 4-row slab
+      // ---- output phase: thread = row of the warp's 32-row band, NC = 64 consecutive columns
+      const int64_t wrow0 = (int64_t)row_first[g] + (int64_t)rt * TC_BM + q * 32;
+      const int n0 = ct * BN + half * NC;
+      if (EPI == TM_EPI_DACT) {
+        // act'(h) for the band: lanes work slab-wise (4 lanes per row, 8 rows per instruction) on 32-column passes,
+        // join hi/lo, evaluate act', and hand the fp32 values to the row threads through the swizzled tile
 #pragma unroll
-      for (int c = 0; c < NC / 32; c++) {   // unrolled: accr[] indices must be static
-        int64_t off0 = wrow0 * G.ldc + n0 + c * 32;
-        float x[32];
-        if (EPI == TM_EPI_DACT) {
-          float4 h1[8], h2[8];
+        for (int p = 0; p < 2; p++) {
+          const int srow = lane >> 2, sc = lane & 3;
+          uint4 hh[4], ll[4];
 #pragma unroll
-          for (int it = 0; it < 8; it++) {
-            int64_t o = off0 + (int64_t)(it * 4 + trow) * G.ldc + tcol;
-            h1[it] = __ldg(reinterpret_cast<const float4*>(G.Hmul_hi + o));
-            h2[it] = __ldg(reinterpret_cast<const float4*>(G.Hmul_lo + o));
+          for (int it = 0; it < 4; it++) {
+            int64_t o = (wrow0 + it * 8 + srow) * G.ldc + n0 + p * 32 + sc * 8;
+            hh[it] = __ldg(reinterpret_cast<const uint4*>(G.Hmul_hi + o));
+            ll[it] = __ldg(reinterpret_cast<const uint4*>(G.Hmul_lo + o));
           }
 #pragma unroll
-          for (int it = 0; it < 8; it++)
-            *reinterpret_cast<float4*>(tb + TB_OFF(it * 4 + trow, tcol >> 2)) =
-                make_float4(h1[it].x + h2[it].x, h1[it].y + h2[it].y, h1[it].z + h2[it].z, h1[it].w + h2[it].w);
+          for (int it = 0; it < 4; it++) {
+            float2 a = join2(hh[it].x, ll[it].x), b = join2(hh[it].y, ll[it].y), c2 = join2(hh[it].z, ll[it].z), d = join2(hh[it].w, ll[it].w);
+            int r = it * 8 + srow;
+            *reinterpret_cast<float4*>(tb + TB_OFF(r, 2 * sc)) =
+                make_float4(tc_act_bwd(a.x, act_kind, act_alpha), tc_act_bwd(a.y, act_kind, act_alpha), tc_act_bwd(b.x, act_kind, act_alpha),
+                            tc_act_bwd(b.y, act_kind, act_alpha));
+            *reinterpret_cast<float4*>(tb + TB_OFF(r, 2 * sc + 1)) =
+                make_float4(tc_act_bwd(c2.x, act_kind, act_alpha), tc_act_bwd(c2.y, act_kind, act_alpha), tc_act_bwd(d.x, act_kind, act_alpha),
+                            tc_act_bwd(d.y, act_kind, act_alpha));
+          }
           __syncwarp();
 #pragma unroll
           for (int i = 0; i < 8; i++) {
-            float4 hv = *reinterpret_cast<const float4*>(tb + TB_OFF(lane, i));
-            x[4 * i + 0] = accr[c * 32 + 4 * i + 0] * tc_act_bwd(hv.x, act_kind, act_alpha);
-            x[4 * i + 1] = accr[c * 32 + 4 * i + 1] * tc_act_bwd(hv.y, act_kind, act_alpha);
-            x[4 * i + 2] = accr[c * 32 + 4 * i + 2] * tc_act_bwd(hv.z, act_kind, act_alpha);
-            x[4 * i + 3] = accr[c * 32 + 4 * i + 3] * tc_act_bwd(hv.w, act_kind, act_alpha);
+            float4 dv = *reinterpret_cast<const float4*>(tb + TB_OFF(lane, i));
+            accr[p * 32 + 4 * i + 0] *= dv.x;
+            accr[p * 32 + 4 * i + 1] *= dv.y;
+            accr[p * 32 + 4 * i + 2] *= dv.z;
+            accr[p * 32 + 4 * i + 3] *= dv.w;
           }
           __syncwarp();
-        } else if (EPI == TM_EPI_ACT) {
-          float bl = G.bias[n0 + c * 32 + lane];
+        }
+      } else if (EPI == TM_EPI_ACT) {
 #pragma unroll
-          for (int i = 0; i < 32; i++) x[i] = tc_act_fwd(accr[c * 32 + i] + __shfl_sync(0xffffffffu, bl, i), act_kind, act_alpha);
-        } else {
+        for (int i = 0; i < NC / 4; i++) {
+          float4 b4 = __ldg(reinterpret_cast<const float4*>(G.bias + n0) + i);   // uniform address: one broadcast load
+          accr[4 * i + 0] = tc_act_fwd(accr[4 * i + 0], b4.x, act_kind, act_alpha);
+          accr[4 * i + 1] = tc_act_fwd(accr[4 * i + 1], b4.y, act_kind, act_alpha);
+          accr[4 * i + 2] = tc_act_fwd(accr[4 * i + 2], b4.z, act_kind, act_alpha);
+          accr[4 * i + 3] = tc_act_fwd(accr[4 * i + 3], b4.w, act_kind, act_alpha);
+        }
+      }
+      const int trow = lane >> 3, tc16 = lane & 7;     // coordinates of this lane inside a 4-row x 128-byte slab
+      if (EPI == TM_EPI_NONE) {
+        // fp32 plane: two 32-column blocks, each a [32][32] fp32 tile
 #pragma unroll
-          for (int i = 0; i < 32; i++) x[i] = accr[c * 32 + i];
+        for (int c = 0; c < NC / 32; c++) {
+#pragma unroll
+          for (int i = 0; i < 8; i++)
+            *reinterpret_cast<float4*>(tb + TB_OFF(lane, i)) =
+                make_float4(accr[c * 32 + 4 * i], accr[c * 32 + 4 * i + 1], accr[c * 32 + 4 * i + 2], accr[c * 32 + 4 * i + 3]);
+          __syncwarp();
+#pragma unroll
+          for (int it = 0; it < 8; it++) {
+            float4 v4 = *reinterpret_cast<const float4*>(tb + TB_OFF(it * 4 + trow, tc16));
+            *reinterpret_cast<float4*>(G.C32 + (wrow0 + it * 4 + trow) * G.ldc + n0 + c * 32 + tc16 * 4) = v4;
+          }
+          __syncwarp();
+        }
+      } else {
+        // fp16 hi / scaled-lo planes: 64 columns = 128 bytes per row per plane = one tile per plane
+        uint32_t hp[NC / 2], lp[NC / 2];
+#pragma unroll
+        for (int i = 0; i < NC / 2; i++) {
+          vmax = fmaxf(vmax, fmaxf(fabsf(accr[2 * i]), fabsf(accr[2 * i + 1])));
+          split2(accr[2 * i], accr[2 * i + 1], hp[i], lp[i]);
         }
 #pragma unroll
-        for (int plane = 0; plane < ((EPI == TM_EPI_NONE) ? 1 : 2); plane++) {
-          float* Cp = plane ? G.C_lo : G.C_hi;
+        for (int plane = 0; plane < 2; plane++) {
+          __half* Cp = plane ? G.C_lo : G.C_hi;
 #pragma unroll
           for (int i = 0; i < 8; i++) {
-            float4 v;
-            if (EPI == TM_EPI_NONE) v = make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
-            else if (plane == 0) v = make_float4(tf32_hi(x[4 * i]), tf32_hi(x[4 * i + 1]), tf32_hi(x[4 * i + 2]), tf32_hi(x[4 * i + 3]));
-            else v = make_float4(x[4 * i] - tf32_hi(x[4 * i]), x[4 * i + 1] - tf32_hi(x[4 * i + 1]), x[4 * i + 2] - tf32_hi(x[4 * i + 2]),
-                                 x[4 * i + 3] - tf32_hi(x[4 * i + 3]));
-            *reinterpret_cast<float4*>(tb + TB_OFF(lane, i)) = v;
+            uint4 u = plane ? make_uint4(lp[4 * i], lp[4 * i + 1], lp[4 * i + 2], lp[4 * i + 3])
+                            : make_uint4(hp[4 * i], hp[4 * i + 1], hp[4 * i + 2], hp[4 * i + 3]);
+            *reinterpret_cast<uint4*>(tb + TB_OFF(lane, i)) = u;
           }
           __syncwarp();
 #pragma unroll
           for (int it = 0; it < 8; it++) {
-            float4 v = *reinterpret_cast<const float4*>(tb + TB_OFF(it * 4 + trow, tcol >> 2));
-            *reinterpret_cast<float4*>(Cp + off0 + (int64_t)(it * 4 + trow) * G.ldc + tcol) = v;
+            uint4 u = *reinterpret_cast<const uint4*>(tb + TB_OFF(it * 4 + trow, tc16));
+            *reinterpret_cast<uint4*>(Cp + (wrow0 + it * 4 + trow) * G.ldc + n0 + tc16 * 8) = u;
           }
           __syncwarp();
         }
       }
+    }
+    if (EPI != TM_EPI_NONE) {
+      bool bad = !(vmax <= 65000.f);   // also catches NaN
+      if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(P.flags, 16);
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(TC_NACC * BN)));
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(TC_NPAIR * 2 * BN)));
   }
 }
 
@@ -401,17 +470,17 @@ static int get_encode() {
   return TM_OK;
 }
 
-// 2D fp32 tensor [rows][cols] with row pitch ld (elements); box = 32 x box_rows, 128B swizzle
-static int make_map(CUtensorMap* m, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+// 2D fp16 tensor [rows][cols] with row pitch ld (elements); box = 64 x box_rows (128 bytes wide), 128B swizzle
+static int make_map(CUtensorMap* m, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
   static std::map<std::tuple<const void*, int64_t, int64_t, int64_t, int>, CUtensorMap> cache;
-  auto key = std::make_tuple((const void*)base, rows, cols, ld, box_rows);
+  auto key = std::make_tuple(base, rows, cols, ld, box_rows);
   auto it = cache.find(key);
   if (it != cache.end()) { *m = it->second; return TM_OK; }
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
   cuuint32_t box[2] = {TC_BK, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     tm_set_error("cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld ld=%lld", (int)r, (long long)rows, (long long)cols, (long long)ld);
@@ -422,19 +491,19 @@ static int make_map(CUtensorMap* m, const float* base, int64_t rows, int64_t col
   return TM_OK;
 }
 
-template <int BN, int STAGES, int EPI, int ACTK>
+template <int EPI, int ACTK>
 static int launch_tc(tm_ctx* c, const TcParams& P, const int* rowmeta_dev, int total_tiles_bound) {
-  constexpr size_t smem = (size_t)STAGES * (2 * TC_BM * TC_BK * 4 + 2 * BN * TC_BK * 4) + 1024 + 512 + TC_EPI_WARPS * 32 * 32 * 4;
+  constexpr size_t smem = (size_t)TC_STAGES * (2 * TC_BM * TC_BK * 2 + 2 * TC_BN * TC_BK * 2) + 1024 + 512 + TC_EPI_WARPS * 32 * 32 * 4;
   static bool configured = false;
   if (!configured) {
-    TM_CUDA(cudaFuncSetAttribute(k_gemm_tc<BN, STAGES, EPI, ACTK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TM_CUDA(cudaFuncSetAttribute(k_gemm_tc<EPI, ACTK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
   int grid = total_tiles_bound < sms ? total_tiles_bound : sms;
   if (grid < 1) grid = 1;
-  k_gemm_tc<BN, STAGES, EPI, ACTK><<<grid, TC_THREADS, smem, c->stream>>>(P, rowmeta_dev);
+  k_gemm_tc<EPI, ACTK><<<grid, TC_THREADS, smem, c->stream>>>(P, rowmeta_dev);
   c->launches++;
   TM_CUDA(cudaGetLastError());
   return TM_OK;
@@ -442,36 +511,33 @@ static int launch_tc(tm_ctx* c, const TcParams& P, const int* rowmeta_dev, int t
 
 template <int EPI>
 static int launch_tc_act(tm_ctx* c, const TcParams& P, const int* rowmeta_dev, int bound) {
-  if (EPI == TM_EPI_NONE) return launch_tc<128, 3, EPI, 0>(c, P, rowmeta_dev, bound);
-  if (P.act_kind == TM_ACT_SIGMOID_WITH_PARAM) return launch_tc<128, 3, EPI, TM_ACT_SIGMOID_WITH_PARAM>(c, P, rowmeta_dev, bound);
-  return launch_tc<128, 3, EPI, -1>(c, P, rowmeta_dev, bound);
+  if (EPI == TM_EPI_NONE) return launch_tc<EPI, 0>(c, P, rowmeta_dev, bound);
+  if (P.act_kind == TM_ACT_SIGMOID_WITH_PARAM) return launch_tc<EPI, TM_ACT_SIGMOID_WITH_PARAM>(c, P, rowmeta_dev, bound);
+  return launch_tc<EPI, -1>(c, P, rowmeta_dev, bound);
 }
 
+// In this mode every GemmGroup pointer except bias (and C for TM_EPI_NONE) addresses fp16 planes.
 int tm_gemm_tc_launch(tm_ctx* c, const GemmGroup* groups, int ngroups, const int* rowmeta_dev, int max_row_tiles, int epilogue) {
   int rc;
-  if (c->gemm_mode != TM_GEMM_TC_3XTF32) { tm_set_error("gemm mode %d is not implemented (use 0 = fp32 or 1 = tcgen05 3xTF32)", c->gemm_mode); return TM_ESTATE; }
+  if (c->gemm_mode != TM_GEMM_TC_SPLIT) { tm_set_error("gemm mode %d is not implemented (use 0 = fp32 or 1 = tcgen05 split fp16)", c->gemm_mode); return TM_ESTATE; }
   if ((rc = get_encode())) return rc;
   if (ngroups > TC_MAX_GROUPS) { tm_set_error("too many GEMM groups"); return TM_EINVAL; }
   static TcParams P;   // large; filled per launch (calls on one ctx are serialised by contract)
-  { const char* d = getenv("TM_TC_DBG"); P.dbg = d ? atoi(d) : 0; }
-  P.ngroups = ngroups; P.epilogue = epilogue; P.act_kind = c->hp.activation; P.act_alpha = c->hp.act_alpha;
-  bool all256 = true;
+  P.ngroups = ngroups; P.act_kind = c->hp.activation; P.act_alpha = c->hp.act_alpha;
+  P.flags = (int32_t*)c->b_flags.p;
   int64_t tiles = 0;
-  for (int i = 0; i < ngroups; i++)
-    if (groups[i].N % 256) all256 = false;
-  (void)all256;
-  int BN = 128;   // register accumulators of the epilogue hold 128 columns per thread
   for (int i = 0; i < ngroups; i++) {
     const GemmGroup& g = groups[i];
-    if (g.K % TC_BK || g.N % BN || !g.A2 || !g.B2) { tm_set_error("tc gemm: bad group (K=%d N=%d)", g.K, g.N); return TM_EINVAL; }
+    if (g.K % TC_BK || g.N % TC_BN || !g.A2 || !g.B2) { tm_set_error("tc gemm: bad group (K=%d N=%d)", g.K, g.N); return TM_EINVAL; }
     TcGroup& T = P.g[i];
     if ((rc = make_map(&T.mapA_hi, g.A, g.rows_alloc, g.K, g.lda, TC_BM))) return rc;
     if ((rc = make_map(&T.mapA_lo, g.A2, g.rows_alloc, g.K, g.lda, TC_BM))) return rc;
-    if ((rc = make_map(&T.mapB_hi, g.B, g.N, g.K, g.ldb, BN))) return rc;
-    if ((rc = make_map(&T.mapB_lo, g.B2, g.N, g.K, g.ldb, BN))) return rc;
-    T.bias = g.bias; T.Hmul_hi = g.Hmul; T.Hmul_lo = g.Hmul2; T.C_hi = g.C; T.C_lo = g.C2;
+    if ((rc = make_map(&T.mapB_hi, g.B, g.N, g.K, g.ldb, TC_BN))) return rc;
+    if ((rc = make_map(&T.mapB_lo, g.B2, g.N, g.K, g.ldb, TC_BN))) return rc;
+    T.bias = g.bias; T.Hmul_hi = (const __half*)g.Hmul; T.Hmul_lo = (const __half*)g.Hmul2;
+    T.C_hi = (__half*)g.C; T.C_lo = (__half*)g.C2; T.C32 = (float*)g.C;
     T.ldc = g.ldc; T.K = g.K; T.N = g.N; T.ele = g.ele;
-    tiles += (int64_t)max_row_tiles * (g.N / BN);
+    tiles += (int64_t)max_row_tiles * (g.N / TC_BN);
   }
   int bound = tiles > 100000 ? 100000 : (int)tiles;
   if (epilogue == TM_EPI_ACT) return launch_tc_act<TM_EPI_ACT>(c, P, rowmeta_dev, bound);

@@ -73,9 +73,9 @@ struct Layer {
   float* W = nullptr;    // [Kp][Np] row-major fp32 (zero padded)
   float* WT = nullptr;   // [Np][Kp] (for the backward-data GEMM)
   float* b = nullptr;    // [Np]
-  // hi/lo tf32 split planes for the tcgen05 path: Ws = [W_hi | W_lo] each [Kp][Np]; WTs = [WT_hi | WT_lo] each [Np][Kp]
-  float* Ws = nullptr;
-  float* WTs = nullptr;
+  // split-fp16 planes for the tcgen05 path (x = hi + lo/2048): Ws = [W_hi | W_lo] each [Kp][Np]; WTs = [WT_hi | WT_lo] each [Np][Kp]
+  uint16_t* Ws = nullptr;
+  uint16_t* WTs = nullptr;
 };
 
 struct Net {
@@ -117,7 +117,7 @@ struct tm_ctx {
   DevParams hp;                  // host copy
   DevParams* dp = nullptr;       // device copy
   Net nets[2][TM_MAX_ELE];
-  int gemm_mode = TM_GEMM_TC_3XTF32;   // parity-preserving tensor-core path is the default
+  int gemm_mode = TM_GEMM_TC_SPLIT;   // parity-preserving tensor-core path is the default
   int Hp[TM_MAX_HIDDEN];         // padded hidden widths
   int Hmax = 0;
 
@@ -173,19 +173,20 @@ int tm_launch_finalize(tm_ctx* c, const SysView& s, int flags);
 int tm_launch_nlist_csr(tm_ctx* c, const SysView& s, double rc, int do_perms, int64_t* total_out);
 
 // GEMM back-ends (tm_gemm.cu): C[g] = act(A[g] * B[g] + bias) or the backward variant, grouped over row tiles
+// fp32 mode: every pointer is float.  Tensor-core mode: A, B, Hmul and C (except the fp32 C of TM_EPI_NONE) address
+// fp16 planes, the *2 members are the scaled "lo" planes, and B is given K-major as [N][K].
 struct GemmGroup {
-  const float* A;      // [rows][lda]
-  const float* B;      // [K][ldb]  (K-major rows)
+  const void* A;       // [rows][lda]
+  const void* B;       // [K][ldb]  (K-major rows)
   const float* bias;   // [N] or nullptr
-  const float* Hmul;   // backward: multiply result by act'(h) computed from Hmul [rows][ldc], or nullptr
-  float* C;            // [rows][ldc]
+  const void* Hmul;    // backward: multiply result by act'(h) computed from Hmul [rows][ldc], or nullptr
+  void* C;             // [rows][ldc]
   int lda, ldb, ldc, K, N;
   int ele;             // element whose row range this group covers
-  // tensor-core (3xTF32) mode only: the "lo" planes of the hi/lo split operands, B given K-major as [N][K]
-  const float* A2 = nullptr;
-  const float* B2 = nullptr;
-  const float* Hmul2 = nullptr;
-  float* C2 = nullptr;
+  const void* A2 = nullptr;
+  const void* B2 = nullptr;
+  const void* Hmul2 = nullptr;
+  void* C2 = nullptr;
   int64_t rows_alloc = 0;
 };
 int tm_launch_gemm(tm_ctx* c, const GemmGroup* groups, int ngroups, const int* rowmeta_dev, int max_row_tiles, int epilogue);

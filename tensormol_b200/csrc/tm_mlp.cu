@@ -11,6 +11,7 @@
 // A "group" is one (net, element): rows [rowmeta[2e], +rowmeta[2e+1]) of the row space (padded to
 // TM_ROW_TILE), so tiles never straddle elements and row counts stay on the device.
 #include "tm_internal.h"
+#include <cuda_fp16.h>
 #include <algorithm>
 
 #define FULL 0xffffffffu
@@ -60,8 +61,8 @@ k_gemm_simt(const __grid_constant__ GemmGroupTbl tbl, const int32_t* __restrict_
   int nt = blockIdx.y;
   if (nt * BN >= G.N) return;
   int64_t row0 = (int64_t)rowmeta[2 * G.ele] + (int64_t)rt * BM;
-  const float* A = G.A + row0 * G.lda;
-  const float* B = G.B + nt * BN;
+  const float* A = (const float*)G.A + row0 * G.lda;
+  const float* B = (const float*)G.B + nt * BN;
   __shared__ __align__(16) float As[2][BK][BM + APAD];
   __shared__ __align__(16) float Bs[2][BK][BN];
   int tid = threadIdx.x;
@@ -130,13 +131,13 @@ k_gemm_simt(const __grid_constant__ GemmGroupTbl tbl, const int32_t* __restrict_
         v[2] = act_fwd(v[2] + bb.z, act_kind, act_alpha);
         v[3] = act_fwd(v[3] + bb.w, act_kind, act_alpha);
       } else if (epilogue == TM_EPI_DACT) {
-        float4 hh = *reinterpret_cast<const float4*>(G.Hmul + grow * G.ldc + cn);
+        float4 hh = *reinterpret_cast<const float4*>((const float*)G.Hmul + grow * G.ldc + cn);
         v[0] *= act_bwd_from_h(hh.x, act_kind, act_alpha);
         v[1] *= act_bwd_from_h(hh.y, act_kind, act_alpha);
         v[2] *= act_bwd_from_h(hh.z, act_kind, act_alpha);
         v[3] *= act_bwd_from_h(hh.w, act_kind, act_alpha);
       }
-      *reinterpret_cast<float4*>(G.C + grow * G.ldc + cn) = make_float4(v[0], v[1], v[2], v[3]);
+      *reinterpret_cast<float4*>((float*)G.C + grow * G.ldc + cn) = make_float4(v[0], v[1], v[2], v[3]);
     }
   }
 }
@@ -169,11 +170,11 @@ int tm_launch_gemm(tm_ctx* c, const GemmGroup* groups, int ngroups, const int* r
 struct OutTbl {
   const float* w[2][TM_MAX_ELE];
   float b[2][TM_MAX_ELE];
-  const float* h[2];      // last hidden activation [nrows][ld] (hi plane in split mode)
-  const float* h_lo[2];   // lo plane (split mode) or nullptr
+  const void* h[2];       // last hidden activation [nrows][ld]: fp32, or the fp16 hi plane in split mode
+  const void* h_lo[2];    // fp16 scaled-lo plane (split mode) or nullptr
   float* y[2];            // [nrows]
-  float* delta[2];        // [nrows][ld]
-  float* delta_lo[2];
+  void* delta[2];         // [nrows][ld]
+  void* delta_lo[2];
   int ld, H;
 };
 
@@ -185,10 +186,21 @@ __device__ __forceinline__ int row_element(const int32_t* rowmeta, int64_t row, 
   return -1;
 }
 
-__device__ __forceinline__ float tf32_round(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
+// split-fp16 operand format of the tcgen05 path (tm_gemm_tc.cu): x = hi + lo / 2048
+#define LO_SCALE 2048.0f
+#define LO_INV (1.0f / 2048.0f)
+__device__ __forceinline__ void split4(float4 v, uint2& hi, uint2& lo) {
+  __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
+  float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+  __half2 l0 = __floats2half2_rn((v.x - f0.x) * LO_SCALE, (v.y - f0.y) * LO_SCALE);
+  __half2 l1 = __floats2half2_rn((v.z - f1.x) * LO_SCALE, (v.w - f1.y) * LO_SCALE);
+  hi = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+  lo = make_uint2(*reinterpret_cast<uint32_t*>(&l0), *reinterpret_cast<uint32_t*>(&l1));
+}
+__device__ __forceinline__ float4 join4(uint2 hi, uint2 lo) {
+  float2 a0 = __half22float2(*reinterpret_cast<__half2*>(&hi.x)), a1 = __half22float2(*reinterpret_cast<__half2*>(&hi.y));
+  float2 b0 = __half22float2(*reinterpret_cast<__half2*>(&lo.x)), b1 = __half22float2(*reinterpret_cast<__half2*>(&lo.y));
+  return make_float4(fmaf(b0.x, LO_INV, a0.x), fmaf(b0.y, LO_INV, a0.y), fmaf(b1.x, LO_INV, a1.x), fmaf(b1.y, LO_INV, a1.y));
 }
 
 // one warp per (row, net): y = h . w + b ; delta = w * a'(h)
@@ -201,28 +213,24 @@ __global__ void k_out_layer(const __grid_constant__ OutTbl T, const int32_t* __r
   if (row >= nrows) return;
   int e = row_element(rowmeta, row, n_ele);
   if (e < 0) { if (lane == 0) T.y[net][row] = 0.f; return; }
-  const float* h = T.h[net] + row * T.ld;
-  const float* hl = split ? T.h_lo[net] + row * T.ld : nullptr;
   const float* w = T.w[net][e];
-  float* d = T.delta[net] + row * T.ld;
-  float* dl = split ? T.delta_lo[net] + row * T.ld : nullptr;
   float s = 0.f;
   for (int i = lane * 4; i < T.ld; i += 128) {
-    float4 hv = *reinterpret_cast<const float4*>(h + i);
-    if (split) {
-      float4 h2 = *reinterpret_cast<const float4*>(hl + i);
-      hv.x += h2.x; hv.y += h2.y; hv.z += h2.z; hv.w += h2.w;
-    }
+    float4 hv;
+    if (split) hv = join4(*reinterpret_cast<const uint2*>((const __half*)T.h[net] + row * T.ld + i),
+                          *reinterpret_cast<const uint2*>((const __half*)T.h_lo[net] + row * T.ld + i));
+    else hv = *reinterpret_cast<const float4*>((const float*)T.h[net] + row * T.ld + i);
     float4 wv = *reinterpret_cast<const float4*>(w + i);
     s += hv.x * wv.x + hv.y * wv.y + hv.z * wv.z + hv.w * wv.w;
     float4 dv = make_float4(wv.x * act_bwd_from_h(hv.x, act_kind, act_alpha), wv.y * act_bwd_from_h(hv.y, act_kind, act_alpha),
                             wv.z * act_bwd_from_h(hv.z, act_kind, act_alpha), wv.w * act_bwd_from_h(hv.w, act_kind, act_alpha));
     if (split) {
-      float4 dh = make_float4(tf32_round(dv.x), tf32_round(dv.y), tf32_round(dv.z), tf32_round(dv.w));
-      *reinterpret_cast<float4*>(d + i) = dh;
-      *reinterpret_cast<float4*>(dl + i) = make_float4(dv.x - dh.x, dv.y - dh.y, dv.z - dh.z, dv.w - dh.w);
+      uint2 dh, dl;
+      split4(dv, dh, dl);
+      *reinterpret_cast<uint2*>((__half*)T.delta[net] + row * T.ld + i) = dh;
+      *reinterpret_cast<uint2*>((__half*)T.delta_lo[net] + row * T.ld + i) = dl;
     } else {
-      *reinterpret_cast<float4*>(d + i) = dv;
+      *reinterpret_cast<float4*>((float*)T.delta[net] + row * T.ld + i) = dv;
     }
   }
 #pragma unroll
@@ -230,37 +238,40 @@ __global__ void k_out_layer(const __grid_constant__ OutTbl T, const int32_t* __r
   if (lane == 0) T.y[net][row] = s + T.b[net][e];
 }
 
-// x -> (hi, lo) planes
-__global__ void k_split_planes(const float* __restrict__ x, float* __restrict__ hi, float* __restrict__ lo, int64_t n4) {
+// x (fp32) -> (hi, scaled lo) fp16 planes
+__global__ void k_split_planes(const float* __restrict__ x, __half* __restrict__ hi, __half* __restrict__ lo, int64_t n4) {
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n4; t += (int64_t)gridDim.x * blockDim.x) {
     float4 v = reinterpret_cast<const float4*>(x)[t];
-    float4 h = make_float4(tf32_round(v.x), tf32_round(v.y), tf32_round(v.z), tf32_round(v.w));
-    reinterpret_cast<float4*>(hi)[t] = h;
-    reinterpret_cast<float4*>(lo)[t] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+    uint2 h, l;
+    split4(v, h, l);
+    reinterpret_cast<uint2*>(hi)[t] = h;
+    reinterpret_cast<uint2*>(lo)[t] = l;
   }
 }
 
-// Buffer planes: every activation / delta buffer is allocated with two planes [hi | lo]; the fp32 mode uses plane 0 only.
+// Buffer planes: every activation / delta buffer holds either one fp32 plane (fp32 mode) or two fp16 planes [hi | lo]
+// (tensor-core mode); both need the same bytes.
 static int ensure_mlp_bufs(tm_ctx* c, const SysView& s) {
   int rc;
   int nh = c->desc.n_hidden;
   for (int net = 0; net < 2; net++) {
     for (int l = 0; l < nh; l++)
-      if ((rc = tm_buf(c, c->b_act[net][l], (size_t)2 * s.nrows * c->Hp[l] * 4))) return rc;
+      if ((rc = tm_buf(c, c->b_act[net][l], (size_t)s.nrows * c->Hp[l] * 4))) return rc;
     if ((rc = tm_buf(c, c->b_y[net], (size_t)s.nrows * 4))) return rc;
     if ((rc = tm_buf(c, c->b_dG[net], (size_t)s.nrows * c->hp.Dp * 4))) return rc;
   }
-  if ((rc = tm_buf(c, c->b_delta0, (size_t)4 * s.nrows * c->Hmax * 4))) return rc;   // [plane][net][nrows*Hmax]
-  if ((rc = tm_buf(c, c->b_delta1, (size_t)4 * s.nrows * c->Hmax * 4))) return rc;
+  if ((rc = tm_buf(c, c->b_delta0, (size_t)2 * s.nrows * c->Hmax * 4))) return rc;   // [plane][net][nrows*Hmax] fp16, or [net][nrows*Hmax] fp32
+  if ((rc = tm_buf(c, c->b_delta1, (size_t)2 * s.nrows * c->Hmax * 4))) return rc;
   if (c->gemm_mode != TM_GEMM_FP32)
-    if ((rc = tm_buf(c, c->b_Gs, (size_t)2 * s.nrows * c->hp.Dp * 4))) return rc;
+    if ((rc = tm_buf(c, c->b_Gs, (size_t)2 * s.nrows * c->hp.Dp * 2))) return rc;
   return TM_OK;
 }
 
 // delta for hidden layer l (net, plane): buffers alternate with l
-static float* delta_ptr(tm_ctx* c, const SysView& s, int l, int net, int plane) {
-  void* base = (l & 1) ? c->b_delta1.p : c->b_delta0.p;
-  return (float*)base + ((size_t)plane * 2 + net) * s.nrows * c->Hmax;
+static void* delta_ptr(tm_ctx* c, const SysView& s, int l, int net, int plane) {
+  char* base = (char*)((l & 1) ? c->b_delta1.p : c->b_delta0.p);
+  size_t esz = (c->gemm_mode != TM_GEMM_FP32) ? 2 : 4;
+  return base + ((size_t)plane * 2 + net) * s.nrows * c->Hmax * esz;
 }
 
 int tm_launch_mlp_forward(tm_ctx* c, const SysView& s) {
@@ -274,7 +285,7 @@ int tm_launch_mlp_forward(tm_ctx* c, const SysView& s) {
   if (tc) {
     int64_t n4 = (int64_t)gplane / 4;
     int blocks = (int)std::min<int64_t>((n4 + 255) / 256, 148 * 16);
-    k_split_planes<<<blocks, 256, 0, c->stream>>>((const float*)c->b_G.p, (float*)c->b_Gs.p, (float*)c->b_Gs.p + gplane, n4);
+    k_split_planes<<<blocks, 256, 0, c->stream>>>((const float*)c->b_G.p, (__half*)c->b_Gs.p, (__half*)c->b_Gs.p + gplane, n4);
     c->launches++;
   }
   for (int l = 0; l < nh; l++) {
@@ -288,8 +299,8 @@ int tm_launch_mlp_forward(tm_ctx* c, const SysView& s) {
         int lda = (l == 0) ? c->hp.Dp : c->Hp[l - 1];
         size_t aplane = (size_t)s.nrows * lda, cplane = (size_t)s.nrows * L.Np;
         if (tc) {
-          g.A = (l == 0) ? (const float*)c->b_Gs.p : (const float*)c->b_act[net][l - 1].p;
-          g.A2 = g.A + aplane;
+          const uint16_t* a = (l == 0) ? (const uint16_t*)c->b_Gs.p : (const uint16_t*)c->b_act[net][l - 1].p;
+          g.A = a; g.A2 = a + aplane;
           g.B = L.WTs; g.B2 = L.WTs + (size_t)L.Np * L.Kp; g.ldb = L.Kp;
         } else {
           g.A = (l == 0) ? (const float*)c->b_G.p : (const float*)c->b_act[net][l - 1].p;
@@ -297,7 +308,7 @@ int tm_launch_mlp_forward(tm_ctx* c, const SysView& s) {
         }
         g.lda = lda;
         g.bias = L.b; g.Hmul = nullptr;
-        g.C = (float*)c->b_act[net][l].p; g.C2 = g.C + cplane; g.ldc = L.Np;
+        g.C = c->b_act[net][l].p; g.C2 = tc ? (void*)((uint16_t*)g.C + cplane) : nullptr; g.ldc = L.Np;
         g.K = L.Kp; g.N = L.Np; g.ele = e; g.rows_alloc = s.nrows;
       }
     if ((rc = tm_launch_gemm(c, gg, ng, rowmeta, max_tiles, TM_EPI_ACT))) return rc;
@@ -308,8 +319,8 @@ int tm_launch_mlp_forward(tm_ctx* c, const SysView& s) {
       T.w[net][e] = (e < ne) ? c->nets[net][e].w_out : nullptr;
       T.b[net][e] = (e < ne) ? c->nets[net][e].b_out : 0.f;
     }
-    T.h[net] = (const float*)c->b_act[net][nh - 1].p;
-    T.h_lo[net] = T.h[net] + (size_t)s.nrows * c->Hp[nh - 1];
+    T.h[net] = c->b_act[net][nh - 1].p;
+    T.h_lo[net] = (const uint16_t*)T.h[net] + (size_t)s.nrows * c->Hp[nh - 1];
     T.y[net] = (float*)c->b_y[net].p;
     T.delta[net] = delta_ptr(c, s, nh - 1, net, 0);
     T.delta_lo[net] = delta_ptr(c, s, nh - 1, net, 1);
@@ -344,12 +355,12 @@ int tm_launch_mlp_backward(tm_ctx* c, const SysView& s) {
         g.bias = nullptr;
         g.K = L.Np; g.N = L.Kp; g.ele = e; g.rows_alloc = s.nrows;
         if (l > 0) {
-          g.Hmul = (const float*)c->b_act[net][l - 1].p;
-          g.Hmul2 = g.Hmul + (size_t)s.nrows * c->Hp[l - 1];
+          g.Hmul = c->b_act[net][l - 1].p;
+          g.Hmul2 = (const uint16_t*)g.Hmul + (size_t)s.nrows * c->Hp[l - 1];
           g.C = delta_ptr(c, s, l - 1, net, 0); g.C2 = delta_ptr(c, s, l - 1, net, 1); g.ldc = c->Hp[l - 1];
         } else {
           g.Hmul = nullptr;
-          g.C = (float*)c->b_dG[net].p; g.ldc = c->hp.Dp;
+          g.C = c->b_dG[net].p; g.ldc = c->hp.Dp;
         }
       }
     if ((rc = tm_launch_gemm(c, gg, ng, rowmeta, max_tiles, l > 0 ? TM_EPI_DACT : TM_EPI_NONE))) return rc;

@@ -11,7 +11,7 @@ import math
 import numpy as np
 
 from . import _lib
-from ._lib import (TM_ACT, TM_F_DESCRIPTORS, TM_F_FOLD_IMAGES, TM_F_FORCE, TM_F_VDW, TM_GEMM_FP32, TM_GEMM_TC_3XTF32, TM_GEMM_TC_BF16,
+from ._lib import (TM_ACT, TM_F_DESCRIPTORS, TM_F_FOLD_IMAGES, TM_F_FORCE, TM_F_VDW, TM_GEMM_FP32, TM_GEMM_TC_3XTF32, TM_GEMM_TC_SPLIT,
                    TM_NET_CHARGE, TM_NET_ENERGY, check, tm_model_desc, tm_outputs, tm_params, tm_timings)
 
 BOHRPERA = 1.889725989
