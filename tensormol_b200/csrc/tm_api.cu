@@ -493,7 +493,6 @@ static int check_flags(tm_ctx* c) {
   TM_CUDA(cudaStreamSynchronize(c->stream));
   if (f[0] & 2) { tm_set_error("neighbour table capacity exceeded (>256 radial neighbours per centre on average)"); return TM_ECAP; }
   if (f[0] & 4) { tm_set_error("more than %d neighbours inside the angular cutoff of one centre", TM_ANG_CAP); return TM_ECAP; }
-  if (f[0] & 16) { tm_set_error("an MLP activation left the fp16 range of the tensor-core path (use gemm mode 0)"); return TM_ECAP; }
   return TM_OK;
 }
 
@@ -525,6 +524,12 @@ static int deliver(tm_ctx* c, const SysView& s, int flags, const OutLayout& o, t
   if ((rc = check_flags(c))) return rc;   // synchronises
   const double* h = (const double*)c->h_stage;
   int64_t nm = o.nmol;
+  for (int64_t m = 0; m < nm; m++)
+    if (!std::isfinite(h[m])) {
+      tm_set_error("non-finite energy for molecule %lld (bad input%s)", (long long)m,
+                   c->gemm_mode != TM_GEMM_FP32 ? ", or an MLP activation outside the fp16 range of gemm mode 1: use mode 0" : "");
+      return TM_ECAP;
+    }
   if (out->Etotal) memcpy(out->Etotal, h, nm * 8);
   if (out->Ebp) memcpy(out->Ebp, h + nm, nm * 8);
   if (out->Ecc) memcpy(out->Ecc, h + 2 * nm, nm * 8);

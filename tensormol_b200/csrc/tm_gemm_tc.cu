@@ -38,7 +38,7 @@
 #define TC_THREADS 320           // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quarter)
 #define TC_EPI_WARPS 8
 #define TC_NPAIR 2               // (main, cross) accumulator pairs in flight: 2 x 2 x 128 columns = all 512
-#define TC_CHUNK 2               // k-blocks (of 64) accumulated inside TMEM before the fp32 register add
+#define TC_CHUNK 4               // k-blocks (of 64) accumulated inside TMEM before the fp32 register add (16 truncating adds)
 #define TC_MAX_GROUPS (2 * TM_MAX_ELE)
 #define TC_LO_SCALE 2048.0f
 #define TC_LO_INV (1.0f / 2048.0f)
@@ -60,7 +60,6 @@ struct alignas(64) TcParams {
   TcGroup g[TC_MAX_GROUPS];
   int ngroups, act_kind;
   float act_alpha;
-  int32_t* flags;   // bit 4 (16): a value left the fp16 range
 };
 
 // ------------------------------------------------------------------------------------------------ PTX helpers
@@ -142,6 +141,18 @@ __device__ __forceinline__ float lg2_approx(float x) {
   float r;
   asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;
+}
+
+__device__ __forceinline__ void sts128(uint32_t a, uint4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void sts128f(uint32_t a, float x, float y, float z, float w) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+  return v;
 }
 
 // activation with the bias folded in.  The sigmoid_with_param (softplus(alpha z)/alpha) branch works in base 2:
@@ -315,14 +326,22 @@ k_gemm_tc(const __grid_constant__ TcParams P, const int32_t* __restrict__ rowmet
     constexpr int NC = BN / 2;                     // columns per thread (64)
     const int act_kind = (ACTK >= 0) ? ACTK : P.act_kind;
     const float act_alpha = P.act_alpha;
-    float* tb = tbuf + (warp - 2) * (32 * 32);
+    const uint32_t tb = smem_u32(tbuf) + (uint32_t)(warp - 2) * 4096u;   // this warp's transpose tile (shared-space address)
     uint32_t chunk_it = 0;
-    float vmax = 0.f;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       int g, rt, ct;
       decode(t, g, rt, ct);
-      const TcGroup& G = P.g[g];
-      int nkb = G.K / TC_BK;
+      // group fields into registers once per tile (indexed constant loads are long-scoreboard operations)
+      const int nkb = P.g[g].K / TC_BK;
+      const int64_t ldc = P.g[g].ldc;
+      const int64_t wrow0 = (int64_t)row_first[g] + (int64_t)rt * TC_BM + q * 32;
+      const int n0 = ct * BN + half * NC;
+      float bias_a = 0.f, bias_b = 0.f;
+      if (EPI == TM_EPI_ACT) {   // issued now, consumed after the K loop: the latency hides behind the MMAs
+        const float* bp = P.g[g].bias + n0;
+        bias_a = __ldg(bp + lane);
+        bias_b = __ldg(bp + 32 + lane);
+      }
       float accr[NC];
 #pragma unroll
       for (int i = 0; i < NC; i++) accr[i] = 0.f;
@@ -348,100 +367,103 @@ k_gemm_tc(const __grid_constant__ TcParams P, const int32_t* __restrict__ rowmet
         for (int i = 0; i < NC; i++) accr[i] = fmaf(__uint_as_float(v[i]), TC_LO_INV, accr[i]);
       }
       // ---- output phase: thread = row of the warp's 32-row band, NC = 64 consecutive columns
-      const int64_t wrow0 = (int64_t)row_first[g] + (int64_t)rt * TC_BM + q * 32;
-      const int n0 = ct * BN + half * NC;
       if (EPI == TM_EPI_DACT) {
-        // act'(h) for the band: lanes work slab-wise (4 lanes per row, 8 rows per instruction) on 32-column passes,
-        // join hi/lo, evaluate act', and hand the fp32 values to the row threads through the swizzled tile
+        // act'(h) for the band: lanes work slab-wise (4 lanes per row, 8 rows per instruction) on two 32-column passes,
+        // join hi/lo, evaluate act', and hand the fp32 values to the row threads through the swizzled tile.
+        // All 16 loads are issued up front (one exposed memory latency per tile, not two).
+        const __half* Hh = P.g[g].Hmul_hi;
+        const __half* Hl = P.g[g].Hmul_lo;
+        const int srow = lane >> 2, sc = lane & 3;
+        uint4 hh[2][4], ll[2][4];
 #pragma unroll
-        for (int p = 0; p < 2; p++) {
-          const int srow = lane >> 2, sc = lane & 3;
-          uint4 hh[4], ll[4];
+        for (int p = 0; p < 2; p++)
 #pragma unroll
           for (int it = 0; it < 4; it++) {
-            int64_t o = (wrow0 + it * 8 + srow) * G.ldc + n0 + p * 32 + sc * 8;
-            hh[it] = __ldg(reinterpret_cast<const uint4*>(G.Hmul_hi + o));
-            ll[it] = __ldg(reinterpret_cast<const uint4*>(G.Hmul_lo + o));
+            int64_t o = (wrow0 + it * 8 + srow) * ldc + n0 + p * 32 + sc * 8;
+            hh[p][it] = __ldg(reinterpret_cast<const uint4*>(Hh + o));
+            ll[p][it] = __ldg(reinterpret_cast<const uint4*>(Hl + o));
           }
 #pragma unroll
+        for (int p = 0; p < 2; p++) {
+#pragma unroll
           for (int it = 0; it < 4; it++) {
-            float2 a = join2(hh[it].x, ll[it].x), b = join2(hh[it].y, ll[it].y), c2 = join2(hh[it].z, ll[it].z), d = join2(hh[it].w, ll[it].w);
+            float2 a = join2(hh[p][it].x, ll[p][it].x), b = join2(hh[p][it].y, ll[p][it].y);
+            float2 c2 = join2(hh[p][it].z, ll[p][it].z), d = join2(hh[p][it].w, ll[p][it].w);
             int r = it * 8 + srow;
-            *reinterpret_cast<float4*>(tb + TB_OFF(r, 2 * sc)) =
-                make_float4(tc_act_bwd(a.x, act_kind, act_alpha), tc_act_bwd(a.y, act_kind, act_alpha), tc_act_bwd(b.x, act_kind, act_alpha),
-                            tc_act_bwd(b.y, act_kind, act_alpha));
-            *reinterpret_cast<float4*>(tb + TB_OFF(r, 2 * sc + 1)) =
-                make_float4(tc_act_bwd(c2.x, act_kind, act_alpha), tc_act_bwd(c2.y, act_kind, act_alpha), tc_act_bwd(d.x, act_kind, act_alpha),
-                            tc_act_bwd(d.y, act_kind, act_alpha));
+            sts128f(tb + 4u * TB_OFF(r, 2 * sc), tc_act_bwd(a.x, act_kind, act_alpha), tc_act_bwd(a.y, act_kind, act_alpha),
+                    tc_act_bwd(b.x, act_kind, act_alpha), tc_act_bwd(b.y, act_kind, act_alpha));
+            sts128f(tb + 4u * TB_OFF(r, 2 * sc + 1), tc_act_bwd(c2.x, act_kind, act_alpha), tc_act_bwd(c2.y, act_kind, act_alpha),
+                    tc_act_bwd(d.x, act_kind, act_alpha), tc_act_bwd(d.y, act_kind, act_alpha));
           }
           __syncwarp();
 #pragma unroll
           for (int i = 0; i < 8; i++) {
-            float4 dv = *reinterpret_cast<const float4*>(tb + TB_OFF(lane, i));
-            accr[p * 32 + 4 * i + 0] *= dv.x;
-            accr[p * 32 + 4 * i + 1] *= dv.y;
-            accr[p * 32 + 4 * i + 2] *= dv.z;
-            accr[p * 32 + 4 * i + 3] *= dv.w;
+            uint4 dv = lds128(tb + 4u * TB_OFF(lane, i));
+            accr[p * 32 + 4 * i + 0] *= __uint_as_float(dv.x);
+            accr[p * 32 + 4 * i + 1] *= __uint_as_float(dv.y);
+            accr[p * 32 + 4 * i + 2] *= __uint_as_float(dv.z);
+            accr[p * 32 + 4 * i + 3] *= __uint_as_float(dv.w);
           }
           __syncwarp();
         }
       } else if (EPI == TM_EPI_ACT) {
+        // bias through the tile: 64 floats, read back with uniform-address (broadcast) 128-bit loads
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(tb + 4u * lane), "f"(bias_a) : "memory");
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(tb + 128u + 4u * lane), "f"(bias_b) : "memory");
+        __syncwarp();
 #pragma unroll
         for (int i = 0; i < NC / 4; i++) {
-          float4 b4 = __ldg(reinterpret_cast<const float4*>(G.bias + n0) + i);   // uniform address: one broadcast load
-          accr[4 * i + 0] = tc_act_fwd(accr[4 * i + 0], b4.x, act_kind, act_alpha);
-          accr[4 * i + 1] = tc_act_fwd(accr[4 * i + 1], b4.y, act_kind, act_alpha);
-          accr[4 * i + 2] = tc_act_fwd(accr[4 * i + 2], b4.z, act_kind, act_alpha);
-          accr[4 * i + 3] = tc_act_fwd(accr[4 * i + 3], b4.w, act_kind, act_alpha);
+          uint4 b4 = lds128(tb + 16u * i);
+          accr[4 * i + 0] = tc_act_fwd(accr[4 * i + 0], __uint_as_float(b4.x), act_kind, act_alpha);
+          accr[4 * i + 1] = tc_act_fwd(accr[4 * i + 1], __uint_as_float(b4.y), act_kind, act_alpha);
+          accr[4 * i + 2] = tc_act_fwd(accr[4 * i + 2], __uint_as_float(b4.z), act_kind, act_alpha);
+          accr[4 * i + 3] = tc_act_fwd(accr[4 * i + 3], __uint_as_float(b4.w), act_kind, act_alpha);
         }
+        __syncwarp();
       }
       const int trow = lane >> 3, tc16 = lane & 7;     // coordinates of this lane inside a 4-row x 128-byte slab
       if (EPI == TM_EPI_NONE) {
         // fp32 plane: two 32-column blocks, each a [32][32] fp32 tile
+        float* C32 = P.g[g].C32;
 #pragma unroll
         for (int c = 0; c < NC / 32; c++) {
 #pragma unroll
           for (int i = 0; i < 8; i++)
-            *reinterpret_cast<float4*>(tb + TB_OFF(lane, i)) =
-                make_float4(accr[c * 32 + 4 * i], accr[c * 32 + 4 * i + 1], accr[c * 32 + 4 * i + 2], accr[c * 32 + 4 * i + 3]);
+            sts128f(tb + 4u * TB_OFF(lane, i), accr[c * 32 + 4 * i], accr[c * 32 + 4 * i + 1], accr[c * 32 + 4 * i + 2], accr[c * 32 + 4 * i + 3]);
           __syncwarp();
 #pragma unroll
           for (int it = 0; it < 8; it++) {
-            float4 v4 = *reinterpret_cast<const float4*>(tb + TB_OFF(it * 4 + trow, tc16));
-            *reinterpret_cast<float4*>(G.C32 + (wrow0 + it * 4 + trow) * G.ldc + n0 + c * 32 + tc16 * 4) = v4;
+            uint4 v4 = lds128(tb + 4u * TB_OFF(it * 4 + trow, tc16));
+            *reinterpret_cast<uint4*>(C32 + (wrow0 + it * 4 + trow) * ldc + n0 + c * 32 + tc16 * 4) = v4;
           }
           __syncwarp();
         }
       } else {
-        // fp16 hi / scaled-lo planes: 64 columns = 128 bytes per row per plane = one tile per plane
+        // fp16 hi / scaled-lo planes: 64 columns = 128 bytes per row per plane = one tile per plane.
+        // A value outside the fp16 range becomes inf here and NaN downstream: the host checks the energies.
+        __half* Ch = P.g[g].C_hi;
+        __half* Cl = P.g[g].C_lo;
         uint32_t hp[NC / 2], lp[NC / 2];
 #pragma unroll
-        for (int i = 0; i < NC / 2; i++) {
-          vmax = fmaxf(vmax, fmaxf(fabsf(accr[2 * i]), fabsf(accr[2 * i + 1])));
-          split2(accr[2 * i], accr[2 * i + 1], hp[i], lp[i]);
-        }
+        for (int i = 0; i < NC / 2; i++) split2(accr[2 * i], accr[2 * i + 1], hp[i], lp[i]);
 #pragma unroll
         for (int plane = 0; plane < 2; plane++) {
-          __half* Cp = plane ? G.C_lo : G.C_hi;
+          __half* Cp = plane ? Cl : Ch;
 #pragma unroll
           for (int i = 0; i < 8; i++) {
             uint4 u = plane ? make_uint4(lp[4 * i], lp[4 * i + 1], lp[4 * i + 2], lp[4 * i + 3])
                             : make_uint4(hp[4 * i], hp[4 * i + 1], hp[4 * i + 2], hp[4 * i + 3]);
-            *reinterpret_cast<uint4*>(tb + TB_OFF(lane, i)) = u;
+            sts128(tb + 4u * TB_OFF(lane, i), u);
           }
           __syncwarp();
 #pragma unroll
           for (int it = 0; it < 8; it++) {
-            uint4 u = *reinterpret_cast<const uint4*>(tb + TB_OFF(it * 4 + trow, tc16));
-            *reinterpret_cast<uint4*>(Cp + (wrow0 + it * 4 + trow) * G.ldc + n0 + tc16 * 8) = u;
+            uint4 u = lds128(tb + 4u * TB_OFF(it * 4 + trow, tc16));
+            *reinterpret_cast<uint4*>(Cp + (wrow0 + it * 4 + trow) * ldc + n0 + tc16 * 8) = u;
           }
           __syncwarp();
         }
       }
-    }
-    if (EPI != TM_EPI_NONE) {
-      bool bad = !(vmax <= 65000.f);   // also catches NaN
-      if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(P.flags, 16);
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -524,7 +546,6 @@ int tm_gemm_tc_launch(tm_ctx* c, const GemmGroup* groups, int ngroups, const int
   if (ngroups > TC_MAX_GROUPS) { tm_set_error("too many GEMM groups"); return TM_EINVAL; }
   static TcParams P;   // large; filled per launch (calls on one ctx are serialised by contract)
   P.ngroups = ngroups; P.act_kind = c->hp.activation; P.act_alpha = c->hp.act_alpha;
-  P.flags = (int32_t*)c->b_flags.p;
   int64_t tiles = 0;
   for (int i = 0; i < ngroups; i++) {
     const GemmGroup& g = groups[i];
