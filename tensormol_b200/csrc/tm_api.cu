@@ -222,10 +222,12 @@ extern "C" int tm_set_gemm_mode(tm_ctx* c, int mode) {
 }
 extern "C" int tm_get_gemm_mode(tm_ctx* c) { return c ? c->gemm_mode : TM_EINVAL; }
 extern "C" int tm_descriptor_width(tm_ctx* c) { return c ? c->hp.D : TM_EINVAL; }
+static int check_flags(tm_ctx* c);
 extern "C" int tm_sync(tm_ctx* c) {
   if (!c) return TM_EINVAL;
   TM_CUDA(cudaSetDevice(c->device));
   TM_CUDA(cudaStreamSynchronize(c->stream));
+  if (c->b_flags.p) return check_flags(c);   // the device-pointer entry points do not synchronise: their capacity / input flags surface here
   return TM_OK;
 }
 
@@ -407,6 +409,8 @@ static SysView make_view(tm_ctx* c, int64_t nslots, int64_t nmol, int64_t maxnat
   s.slab_rank = 0; s.slab_world = 1;
   s.slab_g[0] = s.slab_g[1] = s.slab_g[2] = 0.0;
   s.window_on = 0; s.win_lo = 0.0; s.win_hi = 0.0;
+  s.grid_host = 0;
+  memset(&s.hgrid, 0, sizeof(s.hgrid));
   return s;
 }
 
@@ -491,7 +495,8 @@ static int check_flags(tm_ctx* c) {
   int32_t f[2] = {0, 0};
   TM_CUDA(cudaMemcpyAsync(f, c->b_flags.p, 8, cudaMemcpyDeviceToHost, c->stream));
   TM_CUDA(cudaStreamSynchronize(c->stream));
-  if (f[0] & 2) { tm_set_error("neighbour table capacity exceeded (>256 radial neighbours per centre on average)"); return TM_ECAP; }
+  if (f[0] & 2) { tm_set_error("more than %d radial neighbours of one centre", TM_NB_STRIDE); return TM_ECAP; }
+  if (f[0] & 8) { tm_set_error("coordinates are not wrapped into the cell (apply Lattice.ModuloLattice before tm_eval_lattice)"); return TM_EINVAL; }
   if (f[0] & 4) { tm_set_error("more than %d neighbours inside the angular cutoff of one centre", TM_ANG_CAP); return TM_ECAP; }
   return TM_OK;
 }
@@ -664,6 +669,42 @@ static int prepare_lattice(tm_ctx* c, const double* xyz_dev, const int32_t* Z_de
   return TM_OK;
 }
 
+// Lattice path: the binned atoms (all images, or the slab window of them) fill a parallelepiped that is known on the
+// host, so the cell grid is laid out here instead of by a bounding-box pass over the slots (same rules as
+// k_grid_params).  Atoms outside it (unwrapped input) raise flag 8 in k_cell_count.
+static void host_grid(tm_ctx* c, SysView* sv, const double* L, int ntess) {
+  double flo = -(double)ntess, fhi = (double)ntess + 1.0;
+  double alo = flo, ahi = fhi;
+  if (sv->window_on) { alo = std::max(alo, sv->win_lo); ahi = std::min(ahi, sv->win_hi); }
+  double mn[3] = {1e300, 1e300, 1e300}, mx[3] = {-1e300, -1e300, -1e300};
+  for (int k = 0; k < 8; k++) {
+    double fa = (k & 1) ? ahi : alo, fb = (k & 2) ? fhi : flo, fc = (k & 4) ? fhi : flo;
+    for (int d = 0; d < 3; d++) {
+      double v = fa * L[d] + fb * L[3 + d] + fc * L[6 + d];
+      mn[d] = std::min(mn[d], v);
+      mx[d] = std::max(mx[d], v);
+    }
+  }
+  GridParams g;
+  double cell = c->params.r_Rc * (1.0 + 1e-6);
+  int gx = 1, gy = 1, gz = 1;
+  for (int d = 0; d < 3; d++) { double pad = 1e-6 * (1.0 + fabs(mn[d]) + fabs(mx[d])); mn[d] -= pad; mx[d] += pad; }
+  for (int it = 0; it < 200; it++) {
+    gx = (int)floor((mx[0] - mn[0]) / cell) + 1;
+    gy = (int)floor((mx[1] - mn[1]) / cell) + 1;
+    gz = (int)floor((mx[2] - mn[2]) / cell) + 1;
+    if ((double)gx * gy * gz <= (double)sv->ncells_cap) break;
+    cell *= 1.2599210498948732;
+  }
+  g.ox = mn[0]; g.oy = mn[1]; g.oz = mn[2];
+  g.cell = cell; g.inv_cell = 1.0 / cell;
+  g.gx = gx; g.gy = gy; g.gz = gz;
+  g.ncell_mol = gx * gy * gz;
+  g.ncells = g.ncell_mol;
+  sv->hgrid = g;
+  sv->grid_host = 1;
+}
+
 extern "C" int tm_eval_lattice(tm_ctx* c, const double* xyz, const int32_t* Z, int64_t nreal, const double* lattice, int ntess, int flags,
                                tm_outputs* out) {
   if (!c || !xyz || !Z || !lattice || !out || nreal < 1) { tm_set_error("tm_eval_lattice: bad argument"); return TM_EINVAL; }
@@ -682,6 +723,23 @@ extern "C" int tm_eval_lattice(tm_ctx* c, const double* xyz, const int32_t* Z, i
   TM_CUDA(cudaMemcpyAsync(c->b_acc.p, hs, bx + bz, cudaMemcpyHostToDevice, c->stream));
   SysView s;
   if ((rc = prepare_lattice(c, (const double*)c->b_acc.p, (const int32_t*)((char*)c->b_acc.p + bx), nreal, lattice, ntess, &s))) return rc;
+  // (checked here, after the copy and the tessellation were queued, so the device is busy meanwhile)
+  // host-laid grid only for wrapped input (fractional coordinates in [0,1]); anything else takes the bounding-box pass
+  bool wrapped = true;
+  {
+    const double* L = lattice;
+    double det = L[0] * (L[4] * L[8] - L[5] * L[7]) - L[1] * (L[3] * L[8] - L[5] * L[6]) + L[2] * (L[3] * L[7] - L[4] * L[6]);
+    double inv[9] = {(L[4] * L[8] - L[5] * L[7]) / det, (L[2] * L[7] - L[1] * L[8]) / det, (L[1] * L[5] - L[2] * L[4]) / det,
+                     (L[5] * L[6] - L[3] * L[8]) / det, (L[0] * L[8] - L[2] * L[6]) / det, (L[2] * L[3] - L[0] * L[5]) / det,
+                     (L[3] * L[7] - L[4] * L[6]) / det, (L[1] * L[6] - L[0] * L[7]) / det, (L[0] * L[4] - L[1] * L[3]) / det};
+    for (int64_t i = 0; i < nreal && wrapped; i++)
+      for (int d = 0; d < 3; d++) {
+        double f = xyz[3 * i] * inv[d] + xyz[3 * i + 1] * inv[3 + d] + xyz[3 * i + 2] * inv[6 + d];   // f = x inv(L)
+        if (!(f >= -1e-9 && f <= 1.0 + 1e-9)) { wrapped = false; break; }
+      }
+  }
+
+  if (wrapped) host_grid(c, &s, lattice, ntess);
   OutLayout o = out_layout(1, nreal);
   if ((rc = run_all(c, s, flags, o))) return rc;
   rc = deliver(c, s, flags, o, out, nreal);   // charges of the real atoms only: the image blocks are copies
@@ -699,6 +757,7 @@ extern "C" int tm_eval_lattice_dev(tm_ctx* c, const double* xyz_dev, const int32
   cudaEventRecord(c->ev[0], c->stream);
   SysView s;
   if ((rc = prepare_lattice(c, xyz_dev, Z_dev, nreal, lattice, ntess, &s))) return rc;
+  host_grid(c, &s, lattice, ntess);
   OutLayout o = out_layout(1, nreal);
   if ((rc = run_all(c, s, flags, o))) return rc;
   const double* out = (const double*)c->b_out.p;
@@ -766,6 +825,7 @@ extern "C" int tm_slab_phase_a(tm_ctx* c, const double* xyz_dev, const int32_t* 
     s.win_lo = (rank == 0) ? -halo - 1e-3 : (double)rank / world - halo;
     s.win_hi = (rank == world - 1) ? 1.0 + halo + 1e-3 : (double)(rank + 1) / world + halo;
   }
+  host_grid(c, &s, lattice, ntess);
   c->slab_view = s;
   if ((rc = stage_a(c, s))) return rc;
   if ((rc = tm_launch_mlp_backward(c, s))) return rc;

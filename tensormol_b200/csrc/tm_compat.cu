@@ -36,6 +36,7 @@ extern "C" int tm_nlist(tm_ctx* c, const double* xyz, int64_t n, int64_t nreal, 
   if ((r = tm_buf(c, c->b_pos, (size_t)n * 24))) return r;
   if ((r = tm_buf(c, c->b_Z, (size_t)n * 4))) return r;
   if ((r = tm_buf(c, c->b_flags, 64))) return r;
+  TM_CUDA(cudaMemsetAsync(c->b_flags.p, 0, 64, c->stream));
   TM_CUDA(cudaMemcpyAsync(c->b_pos.p, xyz, (size_t)n * 24, cudaMemcpyHostToDevice, c->stream));
   int blocks = (int)std::min<int64_t>((n + 255) / 256, 148 * 8);
   k_fill_const_i32<<<blocks, 256, 0, c->stream>>>((int32_t*)c->b_Z.p, n, 1);
@@ -85,6 +86,7 @@ extern "C" int tm_pairs_triples_ele(tm_ctx* c, const double* xyzs, const int32_t
   if ((r = tm_buf(c, c->b_pos, (size_t)nslots * 24))) return r;
   if ((r = tm_buf(c, c->b_Z, (size_t)nslots * 4))) return r;
   if ((r = tm_buf(c, c->b_flags, 64))) return r;
+  TM_CUDA(cudaMemsetAsync(c->b_flags.p, 0, 64, c->stream));
   TM_CUDA(cudaMemcpyAsync(c->b_pos.p, xyzs, (size_t)nslots * 24, cudaMemcpyHostToDevice, c->stream));
   TM_CUDA(cudaMemcpyAsync(c->b_Z.p, hz.data(), (size_t)nslots * 4, cudaMemcpyHostToDevice, c->stream));
   TM_CUDA(cudaStreamSynchronize(c->stream));

@@ -48,7 +48,7 @@ size_t tm_desc_smem_floats_per_warp(const DevParams& P) {
 template <int NE, int OPLT>
 __global__ void __launch_bounds__(DESC_WARPS * 32)
 k_desc(const SAtom* __restrict__ sat, const int32_t* __restrict__ rowsidx, const int32_t* __restrict__ rowslot,
-       const int32_t* __restrict__ nboff, const uint32_t* __restrict__ nbr, int64_t nrows, const __grid_constant__ DevParams P,
+       const int32_t* __restrict__ nbcnt, const uint32_t* __restrict__ nbr, int64_t nrows, const __grid_constant__ DevParams P,
        float* __restrict__ G, int32_t* __restrict__ flags, int wfloats) {
   constexpr int NELEP = NE * (NE + 1) / 2;
   extern __shared__ float smem[];
@@ -74,7 +74,7 @@ k_desc(const SAtom* __restrict__ sat, const int32_t* __restrict__ rowsidx, const
   int* chan = (int*)(Et + 32 * estr);
 
   SAtom ci = sat[rowsidx[row]];
-  int b = nboff[row], e = nboff[row + 1];
+  int b = (int)row * TM_NB_STRIDE, e = b + nbcnt[row];
   float acc[RPL][NE];
   float rs[RPL];
 #pragma unroll
@@ -226,7 +226,7 @@ static int launch_desc(tm_ctx* c, const SysView& s) {
   }
   int blocks = (int)((s.nrows + DESC_WARPS - 1) / DESC_WARPS);
   k_desc<NE, OPLT><<<blocks, DESC_WARPS * 32, smem, c->stream>>>((const SAtom*)c->b_satom.p, (const int32_t*)c->b_rowsidx.p,
-                                                                (const int32_t*)c->b_rowslot.p, (const int32_t*)c->b_nboff.p,
+                                                                (const int32_t*)c->b_rowslot.p, (const int32_t*)c->b_nbcnt.p,
                                                                 (const uint32_t*)c->b_nbr.p, s.nrows, P, (float*)c->b_G.p,
                                                                 (int32_t*)c->b_flags.p, (int)wf);
   c->launches++;

@@ -31,7 +31,7 @@ size_t tm_force_smem_floats_per_warp(const DevParams& P) {
 template <int NAS_MAX, int NRS_MAX>
 __global__ void __launch_bounds__(FORCE_WARPS * 32)
 k_force(const SAtom* __restrict__ sat, const int32_t* __restrict__ rowsidx, const int32_t* __restrict__ rowslot,
-        const int32_t* __restrict__ nboff, const uint32_t* __restrict__ nbr, int64_t nrows, const __grid_constant__ DevParams P,
+        const int32_t* __restrict__ nbcnt, const uint32_t* __restrict__ nbr, int64_t nrows, const __grid_constant__ DevParams P,
         const float* __restrict__ dGe, const float* __restrict__ dGq, const float* __restrict__ u, int64_t nreal_slots, int fold,
         float* __restrict__ F, int wfloats) {
   extern __shared__ float smem[];
@@ -73,7 +73,7 @@ k_force(const SAtom* __restrict__ sat, const int32_t* __restrict__ rowsidx, cons
   __syncwarp();
 
   SAtom ci = sat[rowsidx[row]];
-  int b = nboff[row], e = nboff[row + 1];
+  int b = (int)row * TM_NB_STRIDE, e = b + nbcnt[row];
   float gix = 0.f, giy = 0.f, giz = 0.f;   // dE/dx_i accumulated by this lane
   int nang = 0;
   for (int j0 = b; j0 < e; j0 += 32) {
@@ -252,7 +252,7 @@ int tm_launch_force(tm_ctx* c, const SysView& s, int flags) {
       conf_small = smem;
     }
     k_force<8, 8><<<blocks, FORCE_WARPS * 32, smem, c->stream>>>(
-        (const SAtom*)c->b_satom.p, (const int32_t*)c->b_rowsidx.p, (const int32_t*)c->b_rowslot.p, (const int32_t*)c->b_nboff.p,
+        (const SAtom*)c->b_satom.p, (const int32_t*)c->b_rowsidx.p, (const int32_t*)c->b_rowslot.p, (const int32_t*)c->b_nbcnt.p,
         (const uint32_t*)c->b_nbr.p, s.nrows, P, (const float*)c->b_dG[TM_NET_ENERGY].p, (const float*)c->b_dG[TM_NET_CHARGE].p,
         (const float*)c->b_u.p, nreal_slots, fold, (float*)c->b_F.p, (int)wf);
   } else {
@@ -261,7 +261,7 @@ int tm_launch_force(tm_ctx* c, const SysView& s, int flags) {
       conf_big = smem;
     }
     k_force<TM_MAX_SYM, TM_MAX_SYM><<<blocks, FORCE_WARPS * 32, smem, c->stream>>>(
-        (const SAtom*)c->b_satom.p, (const int32_t*)c->b_rowsidx.p, (const int32_t*)c->b_rowslot.p, (const int32_t*)c->b_nboff.p,
+        (const SAtom*)c->b_satom.p, (const int32_t*)c->b_rowsidx.p, (const int32_t*)c->b_rowslot.p, (const int32_t*)c->b_nbcnt.p,
         (const uint32_t*)c->b_nbr.p, s.nrows, P, (const float*)c->b_dG[TM_NET_ENERGY].p, (const float*)c->b_dG[TM_NET_CHARGE].p,
         (const float*)c->b_u.p, nreal_slots, fold, (float*)c->b_F.p, (int)wf);
   }

@@ -8,6 +8,7 @@
 
 #define TM_ROW_TILE 128          // GEMM row tile; element row groups are padded to this
 #define TM_ANG_CAP 64            // angular neighbours per centre held in shared memory
+#define TM_NB_STRIDE 256         // radial neighbour slots per centre row (liquid water: 48 max)
 #define TM_MAX_ELEP (TM_MAX_ELE * (TM_MAX_ELE + 1) / 2)
 #define TM_MAX_SYM 16            // max num_a_As / num_a_Rs
 #define TM_BOHRPERA 1.889725989  // PhysicalData.py:30
@@ -29,7 +30,8 @@ struct __align__(32) SAtom {
   int32_t e;      // element index into eles, -1 never stored
 };
 
-// Grid geometry, produced ON THE DEVICE from the bounding box (no host round trip).
+// Grid geometry: produced ON THE DEVICE from the bounding box (no host round trip), or laid out by the host from the
+// lattice in the periodic-lattice path.
 struct GridParams {
   double ox, oy, oz;   // origin
   double inv_cell;     // 1/cell edge
@@ -106,6 +108,9 @@ struct SysView {
   // slab runs only: slots whose fractional coordinate lies outside [win_lo, win_hi] (slab + interaction halo) are not binned
   int window_on;
   double win_lo, win_hi;
+  // lattice path: the cell grid is laid out on the host from the lattice (no bounding-box pass); grid_host = 1
+  int grid_host;
+  GridParams hgrid;
 };
 
 struct tm_ctx {

@@ -11,6 +11,7 @@
 //   -> centre rows sorted by (element, cell order) -> neighbour count -> scan -> fill.
 #include "tm_internal.h"
 #include <cstdio>
+#include <algorithm>
 
 #define FULL 0xffffffffu
 
@@ -143,12 +144,18 @@ __global__ void k_grid_params(const unsigned long long* bb, double rc, int64_t n
 
 
 // per slot: cell id and arrival rank inside the cell
+// check_inside: the grid was laid out by the host from the lattice; an atom outside it means the caller did not wrap
+// the coordinates into the cell (flag 8).  It is still binned (clamped), so nothing reads out of bounds.
 __global__ void k_cell_count(const double* __restrict__ pos, const int32_t* __restrict__ Z, int64_t n, int64_t maxnatom,
-                             const GridParams* __restrict__ gp, Window win, int32_t* __restrict__ cellid, int32_t* __restrict__ rank,
-                             int32_t* __restrict__ count) {
+                             const GridParams* __restrict__ gp, Window win, int check_inside, int32_t* __restrict__ cellid,
+                             int32_t* __restrict__ rank, int32_t* __restrict__ count, int32_t* __restrict__ flags) {
   GridParams g = *gp;
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
     if (Z[t] <= 0 || !slot_in_window(pos, t, win)) { cellid[t] = -1; rank[t] = -1; continue; }   // rank[] is reused as sidx_of_slot (-1 = absent)
+    if (check_inside) {
+      double fx = (pos[3 * t] - g.ox) * g.inv_cell, fy = (pos[3 * t + 1] - g.oy) * g.inv_cell, fz = (pos[3 * t + 2] - g.oz) * g.inv_cell;
+      if (fx < 0.0 || fy < 0.0 || fz < 0.0 || fx > (double)g.gx || fy > (double)g.gy || fz > (double)g.gz) atomicOr(flags, 8);
+    }
     int cx = cell_coord(pos[3 * t], g.ox, g.inv_cell, g.gx);
     int cy = cell_coord(pos[3 * t + 1], g.oy, g.inv_cell, g.gy);
     int cz = cell_coord(pos[3 * t + 2], g.oz, g.inv_cell, g.gz);
@@ -299,6 +306,8 @@ __global__ void k_cell_sort_gather(const GridParams* __restrict__ gp, const int3
   }
 }
 
+__global__ void k_set_grid(GridParams v, GridParams* g) { *g = v; }
+
 // ---------------------------------------------------------------- build launcher
 int tm_launch_nlist_build(tm_ctx* c, const SysView& s, double rc_grid) {
   int64_t n = s.nslots;
@@ -318,18 +327,26 @@ int tm_launch_nlist_build(tm_ctx* c, const SysView& s, double rc_grid) {
   if (blocks < 1) blocks = 1;
   unsigned long long* bb = (unsigned long long*)c->b_bbox.p;
   GridParams* gp = (GridParams*)c->b_grid.p;
-  k_bbox_init<<<1, 32, 0, c->stream>>>(bb);
   Window win{s.window_on, s.slab_g[0], s.slab_g[1], s.slab_g[2], s.win_lo, s.win_hi};
-  k_bbox<<<blocks, 256, 0, c->stream>>>((const double*)c->b_pos.p, (const int32_t*)c->b_Z.p, n, win, bb);
-  k_grid_params<<<1, 1, 0, c->stream>>>(bb, rc_grid, s.nmol, s.ncells_cap, gp);
-  TM_CUDA(cudaMemsetAsync(c->b_count.p, 0, (s.ncells_cap + 8) * 4, c->stream));
-  k_cell_count<<<blocks, 256, 0, c->stream>>>((const double*)c->b_pos.p, (const int32_t*)c->b_Z.p, n, s.maxnatom, gp, win,
-                                              (int32_t*)c->b_cellid.p, (int32_t*)c->b_rank.p, (int32_t*)c->b_count.p);
-  c->launches += 4;
-  if ((rc = scan_exclusive(c, (const int32_t*)c->b_count.p, (int32_t*)c->b_cstart.p, s.ncells_cap, (int32_t*)c->b_scan_tmp.p))) return rc;
+  int64_t ncs = s.ncells_cap;   // cells the count / scan passes have to cover
+  if (s.grid_host) {
+    k_set_grid<<<1, 1, 0, c->stream>>>(s.hgrid, gp);
+    ncs = s.hgrid.ncells;
+    c->launches += 1;
+  } else {
+    k_bbox_init<<<1, 32, 0, c->stream>>>(bb);
+    k_bbox<<<blocks, 256, 0, c->stream>>>((const double*)c->b_pos.p, (const int32_t*)c->b_Z.p, n, win, bb);
+    k_grid_params<<<1, 1, 0, c->stream>>>(bb, rc_grid, s.nmol, s.ncells_cap, gp);
+    c->launches += 3;
+  }
+  TM_CUDA(cudaMemsetAsync(c->b_count.p, 0, (ncs + 8) * 4, c->stream));
+  k_cell_count<<<blocks, 256, 0, c->stream>>>((const double*)c->b_pos.p, (const int32_t*)c->b_Z.p, n, s.maxnatom, gp, win, s.grid_host,
+                                              (int32_t*)c->b_cellid.p, (int32_t*)c->b_rank.p, (int32_t*)c->b_count.p, (int32_t*)c->b_flags.p);
+  c->launches += 1;
+  if ((rc = scan_exclusive(c, (const int32_t*)c->b_count.p, (int32_t*)c->b_cstart.p, ncs, (int32_t*)c->b_scan_tmp.p))) return rc;
   k_scatter<<<blocks, 256, 0, c->stream>>>((const int32_t*)c->b_cellid.p, (const int32_t*)c->b_rank.p, (const int32_t*)c->b_cstart.p, n,
                                            (int32_t*)c->b_sorted.p);
-  int cblocks = (int)((s.ncells_cap * 32 + 255) / 256);
+  int cblocks = (int)((ncs * 32 + 255) / 256);
   if (cblocks > 148 * 32) cblocks = 148 * 32;
   k_cell_sort_gather<<<cblocks, 256, 0, c->stream>>>(gp, (const int32_t*)c->b_cstart.p, (int32_t*)c->b_sorted.p, (const double*)c->b_pos.p,
                                                      (const int32_t*)c->b_Z.p, c->hp, (SAtom*)c->b_satom.p, (int32_t*)c->b_rank.p);
@@ -366,6 +383,7 @@ __global__ void k_rows_count(const SAtom* __restrict__ sat, const int32_t* __res
   __syncthreads();
   GridParams g = *gp;
   int ntot = cstart[g.ncells];
+  if (blockIdx.x * ROWS_BLOCK >= ntot) return;   // k_rows_scan only visits the blocks below ntot
   int i = blockIdx.x * ROWS_BLOCK + threadIdx.x;
   if (i < ntot) {
     SAtom a = sat[i];
@@ -376,8 +394,10 @@ __global__ void k_rows_count(const SAtom* __restrict__ sat, const int32_t* __res
 }
 
 // single block: per element exclusive scan over blocks; element bases padded to TM_ROW_TILE
-__global__ void k_rows_scan(int32_t* __restrict__ blkcnt, int nblk, int n_ele, int32_t* __restrict__ rowmeta) {
+__global__ void k_rows_scan(int32_t* __restrict__ blkcnt, int nblk, int n_ele, const int32_t* __restrict__ cstart,
+                            const GridParams* __restrict__ gp, int32_t* __restrict__ rowmeta) {
   __shared__ int32_t tot[TM_MAX_ELE];
+  nblk = min(nblk, (cstart[gp->ncells] + ROWS_BLOCK - 1) / ROWS_BLOCK);
   int e = threadIdx.x >> 5, lane = threadIdx.x & 31;   // one warp per element
   if (e < TM_MAX_ELE) {
     int32_t carry = 0;
@@ -417,6 +437,7 @@ __global__ void k_rows_fill(const SAtom* __restrict__ sat, const int32_t* __rest
   __shared__ int32_t wcnt[32][TM_MAX_ELE];
   GridParams g = *gp;
   int ntot = cstart[g.ncells];
+  if (blockIdx.x * ROWS_BLOCK >= ntot) return;
   int i = blockIdx.x * ROWS_BLOCK + threadIdx.x;
   int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   int e = -1, slot = -1;
@@ -444,8 +465,11 @@ __global__ void k_rows_fill(const SAtom* __restrict__ sat, const int32_t* __rest
   }
 }
 
-__global__ void k_fill_i32(int32_t* p, int64_t n, int32_t v) {
-  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) p[t] = v;
+__global__ void k_fill2_i32(int32_t* a, int64_t na, int32_t* b, int64_t nb, int32_t v) {
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < na + nb; t += (int64_t)gridDim.x * blockDim.x) {
+    if (t < na) a[t] = v;
+    else b[t - na] = v;
+  }
 }
 
 int tm_launch_rows(tm_ctx* c, const SysView& s) {
@@ -456,21 +480,21 @@ int tm_launch_rows(tm_ctx* c, const SysView& s) {
   if ((rc = tm_buf(c, c->b_rowmeta, (2 * TM_MAX_ELE + 2) * 4))) return rc;
   if ((rc = tm_buf(c, c->b_rowslot, s.nrows * 4))) return rc;
   if ((rc = tm_buf(c, c->b_rowsidx, s.nrows * 4))) return rc;
-  int fb = (int)((s.nrows + 255) / 256);
-  k_fill_i32<<<fb, 256, 0, c->stream>>>((int32_t*)c->b_rowslot.p, s.nrows, -1);
-  int fb2 = (int)((s.nslots + 255) / 256);
-  if (fb2 > 148 * 8) fb2 = 148 * 8;
-  k_fill_i32<<<fb2, 256, 0, c->stream>>>((int32_t*)c->b_rowofslot.p, s.nslots, -1);
+  // rowofslot is only read for slots that can be centres (the descriptor output), i.e. the real block in images mode
+  int64_t nq = s.periodic ? s.nreal : s.nslots;
+  int fb = (int)std::min<int64_t>((s.nrows + nq + 255) / 256, 148 * 8);
+  k_fill2_i32<<<fb, 256, 0, c->stream>>>((int32_t*)c->b_rowslot.p, s.nrows, (int32_t*)c->b_rowofslot.p, nq, -1);
   const SAtom* sat = (const SAtom*)c->b_satom.p;
   const GridParams* gp = (const GridParams*)c->b_grid.p;
   SlabFilter sf{s.slab_rank, s.slab_world, s.slab_g[0], s.slab_g[1], s.slab_g[2]};
   k_rows_count<<<nblk, ROWS_BLOCK, 0, c->stream>>>(sat, (const int32_t*)c->b_cstart.p, gp, s.nreal, s.periodic, sf,
                                                    (int32_t*)c->b_blkcnt.p);
-  k_rows_scan<<<1, 32 * TM_MAX_ELE, 0, c->stream>>>((int32_t*)c->b_blkcnt.p, nblk, c->hp.n_ele, (int32_t*)c->b_rowmeta.p);
+  k_rows_scan<<<1, 32 * TM_MAX_ELE, 0, c->stream>>>((int32_t*)c->b_blkcnt.p, nblk, c->hp.n_ele, (const int32_t*)c->b_cstart.p, gp,
+                                                    (int32_t*)c->b_rowmeta.p);
   k_rows_fill<<<nblk, ROWS_BLOCK, 0, c->stream>>>(sat, (const int32_t*)c->b_cstart.p, gp, s.nreal, s.periodic, sf,
                                                   (const int32_t*)c->b_blkcnt.p, (const int32_t*)c->b_rowmeta.p, (int32_t*)c->b_rowslot.p,
                                                   (int32_t*)c->b_rowsidx.p, (int32_t*)c->b_rowofslot.p);
-  c->launches += 5;
+  c->launches += 4;
   TM_CUDA(cudaGetLastError());
   return TM_OK;
 }
@@ -479,23 +503,23 @@ int tm_launch_rows(tm_ctx* c, const SysView& s) {
 // One warp per centre row.  The 27 neighbour cells are visited as 9 (x,y) columns whose +-1 z-run
 // is contiguous in the cell-sorted array; lanes stride over the run (coalesced 32-byte records),
 // the accept test runs in float64, survivors are compacted with __ballot_sync / __popc.
-// Entry = cell-sorted index of j, bit 31 set when j is also inside the angular cutoff.
 __device__ __forceinline__ double ref_dist(const SAtom& a, double xi, double yi, double zi) {
   double dx = __dsub_rn(xi, a.x), dy = __dsub_rn(yi, a.y), dz = __dsub_rn(zi, a.z);
   double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
   return __dadd_rn(__dsqrt_rn(d2), 0.0000000000001);
 }
 
-template <bool FILL>
+// Entry = cell-sorted index of j, bit 31 set when j is also inside the angular cutoff.
+// One pass: row r owns the TM_NB_STRIDE slots nbr[r*TM_NB_STRIDE ...]; nbcnt[r] = number written.  More than
+// TM_NB_STRIDE radial neighbours of one centre raises flag 2 (TM_ECAP).
 __global__ void k_neighbours(const SAtom* __restrict__ sat, const int32_t* __restrict__ cstart, const GridParams* __restrict__ gp,
                              const int32_t* __restrict__ rowsidx, const int32_t* __restrict__ rowslot, int64_t nrows, int64_t maxnatom,
-                             double rr, double ra, int32_t* __restrict__ nbcnt, const int32_t* __restrict__ nboff,
-                             uint32_t* __restrict__ nbr, int64_t nbr_cap, int32_t* __restrict__ flags) {
+                             double rr, double ra, int32_t* __restrict__ nbcnt, uint32_t* __restrict__ nbr, int32_t* __restrict__ flags) {
   int64_t row = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   int lane = threadIdx.x & 31;
   if (row >= nrows) return;
   int slot = rowslot[row];
-  if (slot < 0) { if (!FILL && lane == 0) nbcnt[row] = 0; return; }
+  if (slot < 0) { if (lane == 0) nbcnt[row] = 0; return; }
   GridParams g = *gp;
   int si = rowsidx[row];
   SAtom ci = sat[si];
@@ -505,7 +529,7 @@ __global__ void k_neighbours(const SAtom* __restrict__ sat, const int32_t* __res
   int cz = cell_coord(ci.z, g.oz, g.inv_cell, g.gz);
   int z0 = max(cz - 1, 0), z1 = min(cz + 1, g.gz - 1);
   int total = 0;
-  int wbase = FILL ? nboff[row] : 0;
+  uint32_t* out = nbr + row * TM_NB_STRIDE;
   for (int dx = -1; dx <= 1; dx++) {
     int x = cx + dx;
     if (x < 0 || x >= g.gx) continue;
@@ -524,37 +548,29 @@ __global__ void k_neighbours(const SAtom* __restrict__ sat, const int32_t* __res
           ang = d < ra;
         }
         unsigned mk = __ballot_sync(FULL, ok);
-        if (FILL && ok) {
-          int64_t w = (int64_t)wbase + total + __popc(mk & ((1u << lane) - 1));
-          if (w < nbr_cap) nbr[w] = (uint32_t)j | (ang ? 0x80000000u : 0u);
-          else atomicOr(flags, 2);
+        if (ok) {
+          int w = total + __popc(mk & ((1u << lane) - 1));
+          if (w < TM_NB_STRIDE) out[w] = (uint32_t)j | (ang ? 0x80000000u : 0u);
         }
         total += __popc(mk);
       }
     }
   }
-  if (!FILL && lane == 0) nbcnt[row] = total;
+  if (lane == 0) {
+    if (total > TM_NB_STRIDE) { atomicOr(flags, 2); total = TM_NB_STRIDE; }
+    nbcnt[row] = total;
+  }
 }
 
 int tm_launch_neighbours(tm_ctx* c, const SysView& s) {
   int rc;
   if ((rc = tm_buf(c, c->b_nbcnt, (s.nrows + 8) * 4))) return rc;
-  if ((rc = tm_buf(c, c->b_nboff, (s.nrows + 8) * 4))) return rc;
-  const SAtom* sat = (const SAtom*)c->b_satom.p;
-  const GridParams* gp = (const GridParams*)c->b_grid.p;
+  if ((rc = tm_buf(c, c->b_nbr, (size_t)s.nrows * TM_NB_STRIDE * 4))) return rc;
   int blocks = (int)((s.nrows * 32 + 255) / 256);
-  k_neighbours<false><<<blocks, 256, 0, c->stream>>>(sat, (const int32_t*)c->b_cstart.p, gp, (const int32_t*)c->b_rowsidx.p,
-                                                     (const int32_t*)c->b_rowslot.p, s.nrows, s.maxnatom, c->hp.rr_exact, c->hp.ra_exact,
-                                                     (int32_t*)c->b_nbcnt.p, nullptr, nullptr, 0, (int32_t*)c->b_flags.p);
-  c->launches++;
-  if ((rc = scan_exclusive(c, (const int32_t*)c->b_nbcnt.p, (int32_t*)c->b_nboff.p, s.nrows, (int32_t*)c->b_scan_tmp.p))) return rc;
-  // capacity: a host bound so that no device->host round trip is needed.  256 radial neighbours per
-  // centre is ~5x liquid water (48 max measured); overflow raises TM_ECAP in finalize.
-  size_t cap = (size_t)s.ncent_max * 256 + 1024;
-  if ((rc = tm_buf(c, c->b_nbr, cap * 4))) return rc;
-  k_neighbours<true><<<blocks, 256, 0, c->stream>>>(sat, (const int32_t*)c->b_cstart.p, gp, (const int32_t*)c->b_rowsidx.p,
-                                                    (const int32_t*)c->b_rowslot.p, s.nrows, s.maxnatom, c->hp.rr_exact, c->hp.ra_exact,
-                                                    nullptr, (const int32_t*)c->b_nboff.p, (uint32_t*)c->b_nbr.p, (int64_t)cap, (int32_t*)c->b_flags.p);
+  k_neighbours<<<blocks, 256, 0, c->stream>>>((const SAtom*)c->b_satom.p, (const int32_t*)c->b_cstart.p, (const GridParams*)c->b_grid.p,
+                                              (const int32_t*)c->b_rowsidx.p, (const int32_t*)c->b_rowslot.p, s.nrows, s.maxnatom,
+                                              c->hp.rr_exact, c->hp.ra_exact, (int32_t*)c->b_nbcnt.p, (uint32_t*)c->b_nbr.p,
+                                              (int32_t*)c->b_flags.p);
   c->launches++;
   TM_CUDA(cudaGetLastError());
   return TM_OK;

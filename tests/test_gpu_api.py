@@ -109,7 +109,8 @@ def test_manager_periodic_callbacks_match_oracle():
     pf2 = PeriodicForce(m, g["lattice"])
     pf2.BindLatticeForce(manager.LatticeForce(), 15.0)
     e2, f2 = pf2(x0)
-    assert abs(e2 - e) <= 1e-9 * abs(e) and np.abs(f2 - f).max() <= 1e-6 * np.abs(f).max()
+    # (a different cell grid, hence a different fp32 summation order: equal to rounding, not bit for bit)
+    assert abs(e2 - e) <= 1e-6 * abs(e) and np.abs(f2 - f).max() <= 1e-5 * np.abs(f).max()
     out = manager.EvalBPDirectEEUpdateSinglePeriodic(Mol(*pf.lattice.TessLattice(pf.atoms, x0, 15.0)), PARAMS["AN1_r_Rc"], PARAMS["AN1_a_Rc"],
                                                      PARAMS["EECutoffOff"], nreal, True, True, True)
     assert out[2].shape == (1, nreal) and np.abs(out[2] - g["oracle_charge"]).max() < 1e-5
