@@ -186,7 +186,7 @@ extern "C" void tm_destroy(tm_ctx* c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   DevBuf* all[] = {&c->b_pos, &c->b_Z, &c->b_cellid, &c->b_rank, &c->b_count, &c->b_cstart, &c->b_sorted, &c->b_satom, &c->b_scan_tmp,
-                   &c->b_rowslot, &c->b_rowsidx, &c->b_rowofslot, &c->b_blkcnt, &c->b_rowmeta, &c->b_nbcnt, &c->b_nboff, &c->b_nbr, &c->b_G, &c->b_Gs,
+                   &c->b_rowslot, &c->b_rowsidx, &c->b_rowofslot, &c->b_blkcnt, &c->b_rowmeta, &c->b_nbcnt, &c->b_nboff, &c->b_nbr, &c->b_G, &c->b_Gs, &c->b_ypart,
                    &c->b_delta0, &c->b_delta1, &c->b_dG[0], &c->b_dG[1], &c->b_y[0], &c->b_y[1], &c->b_q, &c->b_qs, &c->b_dedq, &c->b_u, &c->b_F,
                    &c->b_Fpair, &c->b_acc, &c->b_bbox, &c->b_grid, &c->b_flags, &c->b_out, &c->b_molacc, &c->b_natom, &c->b_lattice};
   for (DevBuf* b : all) free_buf(*b);
@@ -495,6 +495,7 @@ static int check_flags(tm_ctx* c) {
   int32_t f[2] = {0, 0};
   TM_CUDA(cudaMemcpyAsync(f, c->b_flags.p, 8, cudaMemcpyDeviceToHost, c->stream));
   TM_CUDA(cudaStreamSynchronize(c->stream));
+  c->last_flags = f[0];
   if (f[0] & 2) { tm_set_error("more than %d radial neighbours of one centre", TM_NB_STRIDE); return TM_ECAP; }
   if (f[0] & 8) { tm_set_error("coordinates are not wrapped into the cell (apply Lattice.ModuloLattice before tm_eval_lattice)"); return TM_EINVAL; }
   if (f[0] & 4) { tm_set_error("more than %d neighbours inside the angular cutoff of one centre", TM_ANG_CAP); return TM_ECAP; }
@@ -705,13 +706,9 @@ static void host_grid(tm_ctx* c, SysView* sv, const double* L, int ntess) {
   sv->grid_host = 1;
 }
 
-extern "C" int tm_eval_lattice(tm_ctx* c, const double* xyz, const int32_t* Z, int64_t nreal, const double* lattice, int ntess, int flags,
-                               tm_outputs* out) {
-  if (!c || !xyz || !Z || !lattice || !out || nreal < 1) { tm_set_error("tm_eval_lattice: bad argument"); return TM_EINVAL; }
+static int eval_lattice_impl(tm_ctx* c, const double* xyz, const int32_t* Z, int64_t nreal, const double* lattice, int ntess, int flags,
+                             tm_outputs* out, bool use_host_grid) {
   int rc;
-  TM_CUDA(cudaSetDevice(c->device));
-  if ((rc = check_weights(c))) return rc;
-  if ((rc = validate_Z(c, Z, nreal))) return rc;
   c->launches = 0;
   size_t bx = (size_t)nreal * 24, bz = (size_t)nreal * 4;
   if ((rc = tm_host_stage(c, bx + bz + 64))) return rc;
@@ -723,27 +720,25 @@ extern "C" int tm_eval_lattice(tm_ctx* c, const double* xyz, const int32_t* Z, i
   TM_CUDA(cudaMemcpyAsync(c->b_acc.p, hs, bx + bz, cudaMemcpyHostToDevice, c->stream));
   SysView s;
   if ((rc = prepare_lattice(c, (const double*)c->b_acc.p, (const int32_t*)((char*)c->b_acc.p + bx), nreal, lattice, ntess, &s))) return rc;
-  // (checked here, after the copy and the tessellation were queued, so the device is busy meanwhile)
-  // host-laid grid only for wrapped input (fractional coordinates in [0,1]); anything else takes the bounding-box pass
-  bool wrapped = true;
-  {
-    const double* L = lattice;
-    double det = L[0] * (L[4] * L[8] - L[5] * L[7]) - L[1] * (L[3] * L[8] - L[5] * L[6]) + L[2] * (L[3] * L[7] - L[4] * L[6]);
-    double inv[9] = {(L[4] * L[8] - L[5] * L[7]) / det, (L[2] * L[7] - L[1] * L[8]) / det, (L[1] * L[5] - L[2] * L[4]) / det,
-                     (L[5] * L[6] - L[3] * L[8]) / det, (L[0] * L[8] - L[2] * L[6]) / det, (L[2] * L[3] - L[0] * L[5]) / det,
-                     (L[3] * L[7] - L[4] * L[6]) / det, (L[1] * L[6] - L[0] * L[7]) / det, (L[0] * L[4] - L[1] * L[3]) / det};
-    for (int64_t i = 0; i < nreal && wrapped; i++)
-      for (int d = 0; d < 3; d++) {
-        double f = xyz[3 * i] * inv[d] + xyz[3 * i + 1] * inv[3 + d] + xyz[3 * i + 2] * inv[6 + d];   // f = x inv(L)
-        if (!(f >= -1e-9 && f <= 1.0 + 1e-9)) { wrapped = false; break; }
-      }
-  }
-
-  if (wrapped) host_grid(c, &s, lattice, ntess);
+  if (use_host_grid) host_grid(c, &s, lattice, ntess);
   OutLayout o = out_layout(1, nreal);
   if ((rc = run_all(c, s, flags, o))) return rc;
   rc = deliver(c, s, flags, o, out, nreal);   // charges of the real atoms only: the image blocks are copies
   c->last.n_centres = nreal;
+  return rc;
+}
+
+extern "C" int tm_eval_lattice(tm_ctx* c, const double* xyz, const int32_t* Z, int64_t nreal, const double* lattice, int ntess, int flags,
+                               tm_outputs* out) {
+  if (!c || !xyz || !Z || !lattice || !out || nreal < 1) { tm_set_error("tm_eval_lattice: bad argument"); return TM_EINVAL; }
+  int rc;
+  TM_CUDA(cudaSetDevice(c->device));
+  if ((rc = check_weights(c))) return rc;
+  if ((rc = validate_Z(c, Z, nreal))) return rc;
+  c->last_flags = 0;
+  rc = eval_lattice_impl(c, xyz, Z, nreal, lattice, ntess, flags, out, true);
+  // input not wrapped into the cell: the host-laid grid does not cover it, redo with the bounding-box pass
+  if (rc == TM_EINVAL && (c->last_flags & 8)) rc = eval_lattice_impl(c, xyz, Z, nreal, lattice, ntess, flags, out, false);
   return rc;
 }
 

@@ -54,6 +54,9 @@ struct alignas(64) TcGroup {
   __half* C_hi;
   __half* C_lo;
   float* C32;      // TM_EPI_NONE: single fp32 plane
+  const float* wout;   // TM_EPI_ACT_OUT
+  float* ypart;
+  int64_t ystride;
   int ldc, K, N, ele;
 };
 struct alignas(64) TcParams {
@@ -336,11 +339,16 @@ k_gemm_tc(const __grid_constant__ TcParams P, const int32_t* __restrict__ rowmet
       const int64_t ldc = P.g[g].ldc;
       const int64_t wrow0 = (int64_t)row_first[g] + (int64_t)rt * TC_BM + q * 32;
       const int n0 = ct * BN + half * NC;
-      float bias_a = 0.f, bias_b = 0.f;
-      if (EPI == TM_EPI_ACT) {   // issued now, consumed after the K loop: the latency hides behind the MMAs
+      float bias_a = 0.f, bias_b = 0.f, wout_a = 0.f, wout_b = 0.f;
+      if (EPI == TM_EPI_ACT || EPI == TM_EPI_ACT_OUT) {   // issued now, consumed after the K loop: the latency hides behind the MMAs
         const float* bp = P.g[g].bias + n0;
         bias_a = __ldg(bp + lane);
         bias_b = __ldg(bp + 32 + lane);
+        if (EPI == TM_EPI_ACT_OUT) {
+          const float* wp = P.g[g].wout + n0;
+          wout_a = __ldg(wp + lane);
+          wout_b = __ldg(wp + 32 + lane);
+        }
       }
       float accr[NC];
 #pragma unroll
@@ -406,6 +414,30 @@ k_gemm_tc(const __grid_constant__ TcParams P, const int32_t* __restrict__ rowmet
           }
           __syncwarp();
         }
+      } else if (EPI == TM_EPI_ACT_OUT) {
+        // last hidden layer fused with the output layer: y_partial = sum_cols h * w_out (this thread's row, its 64 columns),
+        // and the stored value becomes the backward seed w_out * act'(h) instead of h
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(tb + 4u * lane), "f"(bias_a) : "memory");
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(tb + 128u + 4u * lane), "f"(bias_b) : "memory");
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(tb + 256u + 4u * lane), "f"(wout_a) : "memory");
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(tb + 384u + 4u * lane), "f"(wout_b) : "memory");
+        __syncwarp();
+        float part = 0.f;
+#pragma unroll
+        for (int i = 0; i < NC / 4; i++) {
+          uint4 b4 = lds128(tb + 16u * i);
+          uint4 w4 = lds128(tb + 256u + 16u * i);
+          const float bb[4] = {__uint_as_float(b4.x), __uint_as_float(b4.y), __uint_as_float(b4.z), __uint_as_float(b4.w)};
+          const float ww[4] = {__uint_as_float(w4.x), __uint_as_float(w4.y), __uint_as_float(w4.z), __uint_as_float(w4.w)};
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            float h = tc_act_fwd(accr[4 * i + k], bb[k], act_kind, act_alpha);
+            part = fmaf(h, ww[k], part);
+            accr[4 * i + k] = ww[k] * tc_act_bwd(h, act_kind, act_alpha);
+          }
+        }
+        P.g[g].ypart[(int64_t)(ct * 2 + half) * P.g[g].ystride + wrow0 + lane] = part;
+        __syncwarp();
       } else if (EPI == TM_EPI_ACT) {
         // bias through the tile: 64 floats, read back with uniform-address (broadcast) 128-bit loads
         asm volatile("st.shared.f32 [%0], %1;" ::"r"(tb + 4u * lane), "f"(bias_a) : "memory");
@@ -557,11 +589,14 @@ int tm_gemm_tc_launch(tm_ctx* c, const GemmGroup* groups, int ngroups, const int
     if ((rc = make_map(&T.mapB_lo, g.B2, g.N, g.K, g.ldb, TC_BN))) return rc;
     T.bias = g.bias; T.Hmul_hi = (const __half*)g.Hmul; T.Hmul_lo = (const __half*)g.Hmul2;
     T.C_hi = (__half*)g.C; T.C_lo = (__half*)g.C2; T.C32 = (float*)g.C;
+    T.wout = g.wout; T.ypart = g.ypart; T.ystride = g.rows_alloc;
+    if (epilogue == TM_EPI_ACT_OUT && (!g.wout || !g.ypart)) { tm_set_error("tc gemm: output-layer epilogue without w_out / ypart"); return TM_EINVAL; }
     T.ldc = g.ldc; T.K = g.K; T.N = g.N; T.ele = g.ele;
     tiles += (int64_t)max_row_tiles * (g.N / TC_BN);
   }
   int bound = tiles > 100000 ? 100000 : (int)tiles;
   if (epilogue == TM_EPI_ACT) return launch_tc_act<TM_EPI_ACT>(c, P, rowmeta_dev, bound);
+  if (epilogue == TM_EPI_ACT_OUT) return launch_tc_act<TM_EPI_ACT_OUT>(c, P, rowmeta_dev, bound);
   if (epilogue == TM_EPI_DACT) return launch_tc_act<TM_EPI_DACT>(c, P, rowmeta_dev, bound);
   return launch_tc_act<TM_EPI_NONE>(c, P, rowmeta_dev, bound);
 }

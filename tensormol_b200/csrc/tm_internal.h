@@ -122,14 +122,15 @@ struct tm_ctx {
   DevParams hp;                  // host copy
   DevParams* dp = nullptr;       // device copy
   Net nets[2][TM_MAX_ELE];
-  int gemm_mode = TM_GEMM_TC_SPLIT;   // parity-preserving tensor-core path is the default
+  int gemm_mode = TM_GEMM_TC_SPLIT;
+  int last_flags = 0;                  // device flag word read by the last check_flags   // parity-preserving tensor-core path is the default
   int Hp[TM_MAX_HIDDEN];         // padded hidden widths
   int Hmax = 0;
 
   // ---- per-evaluation workspace (grow-only) ----
   DevBuf b_pos, b_Z, b_cellid, b_rank, b_count, b_cstart, b_sorted, b_satom, b_scan_tmp;
   DevBuf b_rowslot, b_rowsidx, b_rowofslot, b_blkcnt, b_rowmeta;
-  DevBuf b_nbcnt, b_nboff, b_nbr, b_G, b_Gs, b_act[2][TM_MAX_HIDDEN], b_delta0, b_delta1, b_dG[2], b_y[2];
+  DevBuf b_nbcnt, b_nboff, b_nbr, b_G, b_Gs, b_ypart, b_act[2][TM_MAX_HIDDEN], b_delta0, b_delta1, b_dG[2], b_y[2];
   DevBuf b_q, b_qs, b_dedq, b_u, b_F, b_Fpair, b_acc, b_bbox, b_grid, b_flags, b_out, b_molacc;
   DevBuf b_natom, b_lattice;
   // host staging (pinned)
@@ -193,6 +194,11 @@ struct GemmGroup {
   const void* Hmul2 = nullptr;
   void* C2 = nullptr;
   int64_t rows_alloc = 0;
+  const float* wout = nullptr;   // TM_EPI_ACT_OUT: output-layer weights [N] and partial sums [2*N/128][rows_alloc]
+  float* ypart = nullptr;
 };
 int tm_launch_gemm(tm_ctx* c, const GemmGroup* groups, int ngroups, const int* rowmeta_dev, int max_row_tiles, int epilogue);
-enum { TM_EPI_ACT = 0, TM_EPI_DACT = 1, TM_EPI_NONE = 2 };
+// TM_EPI_ACT_OUT (tensor-core mode, last hidden layer): h = act(z + b) is not stored; the epilogue emits the output layer's
+// partial dot products  ypart[p][row] = sum_cols h*w_out  (p = 128-column half-tile index) and C = w_out * act'(h), the
+// backward seed.
+enum { TM_EPI_ACT = 0, TM_EPI_DACT = 1, TM_EPI_NONE = 2, TM_EPI_ACT_OUT = 3 };

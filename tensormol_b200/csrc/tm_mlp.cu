@@ -249,6 +249,26 @@ __global__ void k_split_planes(const float* __restrict__ x, __half* __restrict__
   }
 }
 
+// y[net][row] = b_out + sum of the np partial dot products left by the TM_EPI_ACT_OUT epilogue (fixed order: deterministic)
+struct YTbl {
+  float b[2][TM_MAX_ELE];
+  const float* part[2];
+  float* y[2];
+};
+__global__ void k_y_reduce(const __grid_constant__ YTbl T, const int32_t* __restrict__ rowmeta, int64_t nrows, int n_ele, int np) {
+  int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t >= 2 * nrows) return;
+  int net = (int)(t / nrows);
+  int64_t row = t - (int64_t)net * nrows;
+  int e = row_element(rowmeta, row, n_ele);
+  float s = 0.f;
+  if (e >= 0) {
+    s = T.b[net][e];
+    for (int p = 0; p < np; p++) s += T.part[net][(int64_t)p * nrows + row];
+  }
+  T.y[net][row] = s;
+}
+
 // Buffer planes: every activation / delta buffer holds either one fp32 plane (fp32 mode) or two fp16 planes [hi | lo]
 // (tensor-core mode); both need the same bytes.
 static int ensure_mlp_bufs(tm_ctx* c, const SysView& s) {
@@ -262,8 +282,10 @@ static int ensure_mlp_bufs(tm_ctx* c, const SysView& s) {
   }
   if ((rc = tm_buf(c, c->b_delta0, (size_t)2 * s.nrows * c->Hmax * 4))) return rc;   // [plane][net][nrows*Hmax] fp16, or [net][nrows*Hmax] fp32
   if ((rc = tm_buf(c, c->b_delta1, (size_t)2 * s.nrows * c->Hmax * 4))) return rc;
-  if (c->gemm_mode != TM_GEMM_FP32)
+  if (c->gemm_mode != TM_GEMM_FP32) {
     if ((rc = tm_buf(c, c->b_Gs, (size_t)2 * s.nrows * c->hp.Dp * 2))) return rc;
+    if ((rc = tm_buf(c, c->b_ypart, (size_t)2 * (2 * c->Hmax / 128) * s.nrows * 4))) return rc;   // [net][2*N/128][nrows]
+  }
   return TM_OK;
 }
 
@@ -310,8 +332,26 @@ int tm_launch_mlp_forward(tm_ctx* c, const SysView& s) {
         g.bias = L.b; g.Hmul = nullptr;
         g.C = c->b_act[net][l].p; g.C2 = tc ? (void*)((uint16_t*)g.C + cplane) : nullptr; g.ldc = L.Np;
         g.K = L.Kp; g.N = L.Np; g.ele = e; g.rows_alloc = s.nrows;
+        if (tc && l == nh - 1) {   // fused output layer: the seed of the backward pass replaces the stored activation
+          g.C = delta_ptr(c, s, l, net, 0); g.C2 = delta_ptr(c, s, l, net, 1);
+          g.wout = c->nets[net][e].w_out;
+          g.ypart = (float*)c->b_ypart.p + (size_t)net * (2 * c->Hmax / 128) * s.nrows;
+        }
       }
-    if ((rc = tm_launch_gemm(c, gg, ng, rowmeta, max_tiles, TM_EPI_ACT))) return rc;
+    if ((rc = tm_launch_gemm(c, gg, ng, rowmeta, max_tiles, (tc && l == nh - 1) ? TM_EPI_ACT_OUT : TM_EPI_ACT))) return rc;
+  }
+  if (tc) {
+    YTbl Y;
+    for (int net = 0; net < 2; net++) {
+      for (int e = 0; e < TM_MAX_ELE; e++) Y.b[net][e] = (e < ne) ? c->nets[net][e].b_out : 0.f;
+      Y.part[net] = (const float*)c->b_ypart.p + (size_t)net * (2 * c->Hmax / 128) * s.nrows;
+      Y.y[net] = (float*)c->b_y[net].p;
+    }
+    int np = 2 * c->Hp[nh - 1] / 128;
+    k_y_reduce<<<(unsigned)((2 * s.nrows + 255) / 256), 256, 0, c->stream>>>(Y, (const int32_t*)c->b_rowmeta.p, s.nrows, ne, np);
+    c->launches++;
+    TM_CUDA(cudaGetLastError());
+    return TM_OK;
   }
   OutTbl T;
   for (int net = 0; net < 2; net++) {

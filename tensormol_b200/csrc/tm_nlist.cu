@@ -398,22 +398,25 @@ __global__ void k_rows_scan(int32_t* __restrict__ blkcnt, int nblk, int n_ele, c
                             const GridParams* __restrict__ gp, int32_t* __restrict__ rowmeta) {
   __shared__ int32_t tot[TM_MAX_ELE];
   nblk = min(nblk, (cstart[gp->ncells] + ROWS_BLOCK - 1) / ROWS_BLOCK);
-  int e = threadIdx.x >> 5, lane = threadIdx.x & 31;   // one warp per element
+  int e = threadIdx.x >> 5, lane = threadIdx.x & 31;   // one warp per element, each lane a contiguous run of blocks
   if (e < TM_MAX_ELE) {
-    int32_t carry = 0;
-    for (int base = 0; base < nblk; base += 32) {
-      int i = base + lane;
-      int32_t v = (i < nblk) ? blkcnt[i * TM_MAX_ELE + e] : 0;
-      int32_t inc = v;
+    int per = (nblk + 31) / 32;
+    int b0 = lane * per, b1 = min(nblk, b0 + per);
+    int32_t sum = 0;
+    for (int i = b0; i < b1; i++) sum += blkcnt[i * TM_MAX_ELE + e];
+    int32_t inc = sum;
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        int32_t t = __shfl_up_sync(FULL, inc, o);
-        if (lane >= o) inc += t;
-      }
-      if (i < nblk) blkcnt[i * TM_MAX_ELE + e] = carry + inc - v;
-      carry += __shfl_sync(FULL, inc, 31);
+    for (int o = 1; o < 32; o <<= 1) {
+      int32_t t = __shfl_up_sync(FULL, inc, o);
+      if (lane >= o) inc += t;
     }
-    if (lane == 0) tot[e] = carry;
+    int32_t run = inc - sum;
+    for (int i = b0; i < b1; i++) {
+      int32_t v = blkcnt[i * TM_MAX_ELE + e];
+      blkcnt[i * TM_MAX_ELE + e] = run;
+      run += v;
+    }
+    if (lane == 31) tot[e] = inc;
   }
   __syncthreads();
   if (threadIdx.x == 0) {

@@ -228,3 +228,24 @@ def test_unknown_element_and_missing_weights_fail_loudly():
     eng2, _, _ = _engine([1, 8], [16], 0)
     with pytest.raises(TMolB200Error):
         eng2.evaluate(x, np.array([[1, 6]], np.int32), np.array([2]))         # carbon is not in eles
+
+
+def test_eval_lattice_unwrapped_input_falls_back_to_bbox_grid():
+    """tm_eval_lattice lays the cell grid out from the lattice (wrapped input); coordinates outside the cell must still give
+    the images-mode answer for the same (unwrapped) tessellation, through the bounding-box grid."""
+    from oracle import oracle_np as onp
+    g = load_golden("water_tiny_periodic")
+    eng, _, P = _engine(g["eles"], list(g["hidden"]), int(g["seed"]))
+    X = g["xyz"].copy()
+    X[::3] += g["lattice"][1]            # every third atom one cell over
+    X[1::7] -= 0.4 * g["lattice"][0]
+    nreal = len(g["Z"])
+    Zt, Xt = onp.tess_lattice(g["lattice"], g["Z"].astype(np.uint8), X, P["EECutoffOff"])
+    r1 = eng.evaluate_images(Xt, Zt.astype(np.int32), nreal)
+    r2 = eng.evaluate_lattice(X, g["Z"], g["lattice"], int(g["ntess"]))
+    for k in ("Etotal", "Ebp", "Ecc", "Evdw"):
+        _check_energy(r2[k], r1[k], k)
+    assert np.abs(r2["gradient"] - r1["gradient"]).max() <= 1e-5 * np.abs(r1["gradient"]).max()
+    # and the wrapped call still works on the same context afterwards
+    r3 = eng.evaluate_lattice(g["xyz"], g["Z"], g["lattice"], int(g["ntess"]))
+    _check_energy(r3["Etotal"], g["oracle_Etotal"], "Etotal")
