@@ -136,6 +136,34 @@ static int build_dev_params(tm_ctx* c) {
     if (err > 1e-7) { tm_set_error("erfc fit error %.3e too large for this DSFAlpha / cutoff range", err); return TM_EINVAL; }
   }
   for (int i = 0; i < d.n_ele; i++) { P.sqrtC6[i] = (float)sqrt(p.C6[i]); P.Rvdw[i] = (float)p.Rvdw[i]; }
+  {
+    // pair-kernel constants in Angstrom (see DevParams); every product is formed in double and rounded once
+    const double LOG2E = 1.4426950408889634;
+    double Rs = p.elu_width * B, ZY = (double)ZZ / Rl + YY;
+    double lo = std::max(0.0, alpha * p.elu_width * B - 0.05), hi = alpha * Rl + 0.05;
+    double mid = 0.5 * (lo + hi), half = 0.5 * (hi - lo);
+    P.pk_rsr2 = (float)(p.elu_width * p.elu_width);
+    P.pk_rlr2 = (float)(p.ee_cutoff_off * p.ee_cutoff_off);
+    P.pk_cex = (float)(-(alpha * B) * (alpha * B) * LOG2E);
+    P.pk_ua = (float)(alpha * B / half);
+    P.pk_ub = (float)(-mid / half);
+    for (int k = 0; k < 12; k++) P.pk_pc[k] = (float)((double)P.erfc_c[k] / B);
+    P.pk_ka = (float)(B * ZY);
+    P.pk_kb = (float)(-ZZ - Rl * ZY);
+    P.pk_c2 = (float)(1.1283791671 * alpha);
+    P.pk_BZY = (float)(B * ZY);
+    P.pk_ea = (float)(B * LOG2E);
+    P.pk_eb = (float)(-Rs * LOG2E);
+    P.pk_ec = (float)(p.elu_shift - p.elu_alpha);
+    P.pk_ta = (float)(B * B / (p.poly_width * B));
+    for (int i = 0; i < TM_MAX_ELE; i++)
+      for (int j = 0; j < TM_MAX_ELE; j++) {
+        double c6 = (i < d.n_ele && j < d.n_ele) ? sqrt(p.C6[i]) * sqrt(p.C6[j]) : 0.0;
+        double rs = (i < d.n_ele && j < d.n_ele) ? p.Rvdw[i] + p.Rvdw[j] : 0.0;
+        P.pk_c6[i][j] = (float)(c6 / pow(B, 12.0));
+        P.pk_rs12[i][j] = (float)(6.0 * pow(rs, 12.0) / pow(B, 24.0));
+      }
+  }
   P.add_ecc = p.add_ecc; P.activation = p.activation; P.act_alpha = (float)p.sigmoid_alpha;
   P.rr_exact = p.r_Rc; P.ra_exact = p.a_Rc;
   return TM_OK;

@@ -135,74 +135,70 @@ struct PairAcc {
 };
 
 // erfc(x) = exp(-x^2) * erfcx(x); erfcx is smooth on the LR branch's range [alpha R_sr, alpha R_lr] and is evaluated as a
-// degree-11 polynomial in u in [-1,1] fitted on the host (tm_api.cu, max relative error stored in DevParams and < 1e-7),
-// sharing the exp(-x^2) that the derivative needs anyway.
-__device__ __forceinline__ void pair_eval(const DevParams& P, float d2, float dx, float dy, float dz, float qi, float qj, int ei, int ej,
+// degree-11 polynomial in u in [-1,1] fitted on the host (tm_api.cu, max relative error < 1e-7), sharing the exp(-x^2)
+// that the derivative needs anyway.  All unit factors (Bohr/Angstrom, log2 e, 1/B in erfc(aR)/R, the double Bohr scaling
+// of the vdW term) are folded into the DevParams pk_* constants; MUFU: rsqrt, ex2, rcp.
+//   d2, (dx,dy,dz) = x_j - x_i in Angstrom; c6r / rs12r = this centre's rows of pk_c6 / pk_rs12 (shared memory);
+//   accumulates e_ij pieces and  d e_ij / d x_i = -(dE/dr) (x_j - x_i)/r  weighted by wj.
+__device__ __forceinline__ float ex2f(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ void pair_eval(const DevParams& P, float d2, float dx, float dy, float dz, float qi, float qj, float c6, float rs12,
                                           float wj, int do_vdw, PairAcc& A) {
-  const float B = (float)TM_BOHRPERA;
-  float ir = rsqrtf(d2);          // 1/r (Angstrom^-1)
+  float ir = rsqrtf(d2);          // 1/r
   float r = d2 * ir;
-  float R = B * r;
-  float iR = ir * (1.0f / B);
-  float dEdR = 0.f;   // d e_ij / dR (Bohr)
+  float de = 0.f;                 // dE/dr (Hartree / Angstrom)
   if (P.add_ecc) {
-    float kap, dkap;
-    if (R > P.R_sr) {
-      if (R > P.R_lr) {
-        kap = 0.f; dkap = 0.f;
-      } else {
-        float aR = P.alpha_b * R;
-        float ex = expf(-aR * aR);
-        float u = (aR - P.erfc_mid) * P.erfc_ihalf;
-        float pz = P.erfc_c[11];
+    float kap = 0.f, bdk = 0.f;   // kappa and B dkappa/dR
+    if (d2 > P.pk_rsr2) {
+      if (d2 <= P.pk_rlr2) {
+        float ex = ex2f(P.pk_cex * d2);
+        float u = fmaf(r, P.pk_ua, P.pk_ub);
+        float pz = P.pk_pc[11];
 #pragma unroll
-        for (int k = 10; k >= 0; k--) pz = fmaf(pz, u, P.erfc_c[k]);
-        float er = pz * ex;
-        kap = er * iR - P.Zc + (R - P.R_lr) * P.ZoverR_plus_Y;
-        dkap = -er * iR * iR - 1.1283791671f * P.alpha_b * ex * iR + P.ZoverR_plus_Y;
+        for (int k = 10; k >= 0; k--) pz = fmaf(pz, u, P.pk_pc[k]);
+        float eir = pz * ex * ir;                       // erfc(aR)/R
+        kap = eir + fmaf(r, P.pk_ka, P.pk_kb);
+        bdk = fmaf(-ir, fmaf(P.pk_c2, ex, eir), P.pk_BZY);
       }
     } else {
-      float ex = expf(R - P.R_sr);
-      kap = P.elu_a * (ex - 1.0f) + P.elu_shift;
-      dkap = P.elu_a * ex;
+      float ex = ex2f(fmaf(r, P.pk_ea, P.pk_eb));
+      kap = fmaf(P.elu_a, ex, P.pk_ec);
+      bdk = (float)TM_BOHRPERA * P.elu_a * ex;
     }
     float qq = qi * qj;
-    A.ecc += qq * kap;
-    A.dedq += qj * kap;
-    dEdR += qq * dkap;
+    A.ecc = fmaf(qq, kap, A.ecc);
+    A.dedq = fmaf(qj, kap, A.dedq);
+    de = qq * bdk;
   }
   if (do_vdw) {
-    float Rp = B * R;                       // second Bohr scaling (RawSymFunc.py:1377)
-    float iRp = iR * (1.0f / B);
-    float t = Rp * P.inv_poly_width_b;
-    float S, dS;
-    if (t > 1.0f) { S = 1.0f; dS = 0.f; }
-    else { S = -t * t * (2.0f * t - 3.0f); dS = (6.0f * t - 6.0f * t * t) * P.inv_poly_width_b; }
-    float c6 = P.sqrtC6[ei] * P.sqrtC6[ej];
-    float Rs = P.Rvdw[ei] + P.Rvdw[ej];
-    float iRp2 = iRp * iRp;
-    float Rp6i = iRp2 * iRp2 * iRp2;
-    float xi = Rs * iRp;                    // 1/x
-    float xi2 = xi * xi, xi6 = xi2 * xi2 * xi2;
-    float xm12 = xi6 * xi6;                 // x^-12
-    float damp = __frcp_rn(1.0f + 6.0f * xm12);
-    float w = -S * c6 * Rp6i * damp;
-    float ddamp = 72.0f * xm12 * iRp * damp * damp;
-    float dw = -c6 * Rp6i * (dS * damp - 6.0f * S * iRp * damp + S * ddamp);
-    A.evdw += w;
-    dEdR += B * dw;
+    float id2 = ir * ir;
+    float id6 = id2 * id2 * id2;
+    float X = rs12 * id6 * id6;                         // 6 x^-12
+    float damp = __frcp_rn(1.0f + X);
+    float fd = c6 * id6 * damp;                         // C6 / R'^6 * damp
+    float t = fminf(r * P.pk_ta, 1.0f);                 // switch argument, clamped: S(1) = 1, S'(1) = 0
+    float S = t * t * fmaf(-2.0f, t, 3.0f);
+    float bds = 6.0f * t * (1.0f - t) * P.pk_ta;        // B^2 dS/dR'
+    A.evdw = fmaf(-S, fd, A.evdw);
+    de -= fd * fmaf(S * ir, fmaf(12.0f * X, damp, -6.0f), bds);
   }
-  // d e_ij / d x_i = dEdR * B * (x_i - x_j)/r ; (dx,dy,dz) = x_j - x_i
-  float sc = -wj * dEdR * B * ir;
-  A.gx += sc * dx; A.gy += sc * dy; A.gz += sc * dz;
+  float sc = -wj * de * ir;
+  A.gx = fmaf(sc, dx, A.gx); A.gy = fmaf(sc, dy, A.gy); A.gz = fmaf(sc, dz, A.gz);
 }
 
+// One warp per centre.  The cell columns (x, y) that can hold a partner are resolved 32 at a time, one column per lane
+// (its z-range from the centre's actual position: contiguous run [b, e) of the cell-sorted copy), then the warp walks
+// the runs; candidates inside the cutoff are compacted into the shared queue and evaluated 32 at a time.
 __global__ void __launch_bounds__(PAIR_WARPS * 32)
 k_pair(const SAtom* __restrict__ sat, const float4* __restrict__ pq, const int32_t* __restrict__ cstart, const GridParams* __restrict__ gp,
        const int32_t* __restrict__ rowsidx, const int32_t* __restrict__ rowslot, int64_t nrows, int64_t maxnatom, int64_t nreal_slots,
        const __grid_constant__ DevParams P, int do_vdw, int do_force, float cutoff_A, double* __restrict__ dedq_slot, float* __restrict__ F,
        double* __restrict__ molacc) {
   __shared__ int q_j[PAIR_WARPS][QCAP];
+  __shared__ float s_c6[PAIR_WARPS][TM_MAX_ELE], s_rs12[PAIR_WARPS][TM_MAX_ELE];
   int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int64_t row = (int64_t)blockIdx.x * PAIR_WARPS + warp;
   if (row >= nrows) return;
@@ -214,42 +210,59 @@ k_pair(const SAtom* __restrict__ sat, const float4* __restrict__ pq, const int32
   float4 pi = pq[si];
   float qi = pi.w;
   int ei = ci.e;
+  if (lane < TM_MAX_ELE) { s_c6[warp][lane] = P.pk_c6[ei][lane]; s_rs12[warp][lane] = P.pk_rs12[ei][lane]; }
+  __syncwarp();
   int m = (int)(slot / maxnatom);
   float cell = (float)g.cell, icell = (float)g.inv_cell;
   float rc2 = cutoff_A * cutoff_A;
+  const unsigned lt_mask = (1u << lane) - 1u;
   // cell columns that can hold a partner, from the centre's actual position (not its cell): |dx| <= rc
   int x0 = max(0, (int)floorf((pi.x - cutoff_A) * icell)), x1 = min(g.gx - 1, (int)floorf((pi.x + cutoff_A) * icell));
   int y0 = max(0, (int)floorf((pi.y - cutoff_A) * icell)), y1 = min(g.gy - 1, (int)floorf((pi.y + cutoff_A) * icell));
+  int ny = y1 - y0 + 1, ncol = (x1 - x0 + 1) * ny;
   PairAcc A = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   int qn = 0;
   auto eval = [&](int j) {
     SAtom a = sat[j];
     float ddx = (float)(a.x - ci.x), ddy = (float)(a.y - ci.y), ddz = (float)(a.z - ci.z);
     float d2 = ddx * ddx + ddy * ddy + ddz * ddz;
-    pair_eval(P, d2, ddx, ddy, ddz, qi, pq[j].w, ei, a.e, (a.slot < nreal_slots) ? 1.0f : 0.5f, do_vdw, A);
+    pair_eval(P, d2, ddx, ddy, ddz, qi, pq[j].w, s_c6[warp][a.e], s_rs12[warp][a.e], (a.slot < nreal_slots) ? 1.0f : 0.5f, do_vdw, A);
   };
-  for (int x = x0; x <= x1; x++) {
-    // distance from the centre to the column's slab in x, then the same in y
-    float lx = fmaxf(0.f, fmaxf(x * cell - pi.x, pi.x - (x + 1) * cell));
-    for (int y = y0; y <= y1; y++) {
+  for (int c0 = 0; c0 < ncol; c0 += 32) {
+    // lane -> column c0+lane: run [cb, ce) or empty
+    int cb = 0, ce = 0;
+    int cidx = c0 + lane;
+    if (cidx < ncol) {
+      int x = x0 + cidx / ny, y = y0 + cidx % ny;
+      float lx = fmaxf(0.f, fmaxf(x * cell - pi.x, pi.x - (x + 1) * cell));   // distance from the centre to the column's slab in x
       float ly = fmaxf(0.f, fmaxf(y * cell - pi.y, pi.y - (y + 1) * cell));
       float rem = rc2 - lx * lx - ly * ly;
-      if (rem <= 0.f) continue;
-      float zr = sqrtf(rem);
-      int z0 = max(0, (int)floorf((pi.z - zr) * icell)), z1 = min(g.gz - 1, (int)floorf((pi.z + zr) * icell));
-      if (z1 < z0) continue;
-      int cbase = m * g.ncell_mol + (x * g.gy + y) * g.gz;
-      int b = cstart[cbase + z0], e = cstart[cbase + z1 + 1];
+      if (rem > 0.f) {
+        float zr = sqrtf(rem);
+        int z0 = max(0, (int)floorf((pi.z - zr) * icell)), z1 = min(g.gz - 1, (int)floorf((pi.z + zr) * icell));
+        if (z1 >= z0) {
+          int cbase = m * g.ncell_mol + (x * g.gy + y) * g.gz;
+          cb = cstart[cbase + z0];
+          ce = cstart[cbase + z1 + 1];
+        }
+      }
+    }
+    unsigned live = __ballot_sync(FULL, ce > cb);
+    while (live) {
+      int k = __ffs(live) - 1;
+      live &= live - 1;
+      int b = __shfl_sync(FULL, cb, k), e = __shfl_sync(FULL, ce, k);
       for (int j0 = b; j0 < e; j0 += 32) {
         int j = j0 + lane;
-        bool ok = false;
-        if (j < e && j != si) {
+        float d2 = 3.0e38f;
+        if (j < e) {
           float4 pj = pq[j];
           float ddx = pj.x - pi.x, ddy = pj.y - pi.y, ddz = pj.z - pi.z;
-          ok = (ddx * ddx + ddy * ddy + ddz * ddz) < rc2;
+          d2 = ddx * ddx + ddy * ddy + ddz * ddz;
         }
+        bool ok = (d2 < rc2) && (j != si);
         unsigned mk = __ballot_sync(FULL, ok);
-        if (ok) q_j[warp][qn + __popc(mk & ((1u << lane) - 1))] = j;
+        if (ok) q_j[warp][qn + __popc(mk & lt_mask)] = j;
         qn += __popc(mk);
         __syncwarp();
         if (qn >= 32) {
