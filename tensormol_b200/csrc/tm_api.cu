@@ -155,6 +155,7 @@ static int build_dev_params(tm_ctx* c) {
     P.pk_ea = (float)(B * LOG2E);
     P.pk_eb = (float)(-Rs * LOG2E);
     P.pk_ec = (float)(p.elu_shift - p.elu_alpha);
+    P.pk_belu = (float)(B * p.elu_alpha);
     P.pk_ta = (float)(B * B / (p.poly_width * B));
     for (int i = 0; i < TM_MAX_ELE; i++)
       for (int j = 0; j < TM_MAX_ELE; j++) {

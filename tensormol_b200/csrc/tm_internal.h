@@ -67,9 +67,9 @@ struct DevParams {
   // the same pair potentials with every unit factor folded in, as the pair kernel evaluates them (r in Angstrom):
   //   LR   ex = 2^(pk_cex r^2), u = pk_ua r + pk_ub, erfc(aR)/R = (sum pk_pc[k] u^k) ex / r,
   //        kappa = erfc(aR)/R + pk_ka r + pk_kb,  B dkappa/dR = pk_BZY - (erfc(aR)/R + pk_c2 ex) / r
-  //   ELU  ex = 2^(pk_ea r + pk_eb), kappa = elu_a ex + pk_ec
+  //   ELU  ex = 2^(pk_ea r + pk_eb), kappa = elu_a ex + pk_ec, B dkappa/dR = pk_belu ex
   //   vdW  f0 = pk_c6[i][j] / r^6, X = pk_rs12[i][j] / r^12 (= 6 x^-12), t = pk_ta r
-  float pk_rsr2, pk_rlr2, pk_cex, pk_ua, pk_ub, pk_pc[12], pk_ka, pk_kb, pk_c2, pk_BZY, pk_ea, pk_eb, pk_ec, pk_ta;
+  float pk_rsr2, pk_rlr2, pk_cex, pk_ua, pk_ub, pk_pc[12], pk_ka, pk_kb, pk_c2, pk_BZY, pk_ea, pk_eb, pk_ec, pk_belu, pk_ta;
   float pk_c6[TM_MAX_ELE][TM_MAX_ELE], pk_rs12[TM_MAX_ELE][TM_MAX_ELE];
   int add_ecc;
   int activation;

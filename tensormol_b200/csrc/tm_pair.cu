@@ -145,12 +145,23 @@ __device__ __forceinline__ float ex2f(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;
 }
+__device__ __forceinline__ float rsqrt_approx(float x) {
+  float r;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+template <bool ECC, bool VDW>
 __device__ __forceinline__ void pair_eval(const DevParams& P, float d2, float dx, float dy, float dz, float qi, float qj, float c6, float rs12,
-                                          float wj, int do_vdw, PairAcc& A) {
-  float ir = rsqrtf(d2);          // 1/r
+                                          float wj, PairAcc& A) {
+  float ir = rsqrt_approx(d2);    // 1/r (2 ulp: d2 is never denormal for distinct atoms)
   float r = d2 * ir;
   float de = 0.f;                 // dE/dr (Hartree / Angstrom)
-  if (P.add_ecc) {
+  if (ECC) {
     float kap = 0.f, bdk = 0.f;   // kappa and B dkappa/dR
     if (d2 > P.pk_rsr2) {
       if (d2 <= P.pk_rlr2) {
@@ -166,18 +177,18 @@ __device__ __forceinline__ void pair_eval(const DevParams& P, float d2, float dx
     } else {
       float ex = ex2f(fmaf(r, P.pk_ea, P.pk_eb));
       kap = fmaf(P.elu_a, ex, P.pk_ec);
-      bdk = (float)TM_BOHRPERA * P.elu_a * ex;
+      bdk = P.pk_belu * ex;
     }
     float qq = qi * qj;
     A.ecc = fmaf(qq, kap, A.ecc);
     A.dedq = fmaf(qj, kap, A.dedq);
     de = qq * bdk;
   }
-  if (do_vdw) {
+  if (VDW) {
     float id2 = ir * ir;
     float id6 = id2 * id2 * id2;
     float X = rs12 * id6 * id6;                         // 6 x^-12
-    float damp = __frcp_rn(1.0f + X);
+    float damp = rcp_approx(1.0f + X);
     float fd = c6 * id6 * damp;                         // C6 / R'^6 * damp
     float t = fminf(r * P.pk_ta, 1.0f);                 // switch argument, clamped: S(1) = 1, S'(1) = 0
     float S = t * t * fmaf(-2.0f, t, 3.0f);
@@ -192,10 +203,11 @@ __device__ __forceinline__ void pair_eval(const DevParams& P, float d2, float dx
 // One warp per centre.  The cell columns (x, y) that can hold a partner are resolved 32 at a time, one column per lane
 // (its z-range from the centre's actual position: contiguous run [b, e) of the cell-sorted copy), then the warp walks
 // the runs; candidates inside the cutoff are compacted into the shared queue and evaluated 32 at a time.
+template <bool ECC, bool VDW>
 __global__ void __launch_bounds__(PAIR_WARPS * 32)
 k_pair(const SAtom* __restrict__ sat, const float4* __restrict__ pq, const int32_t* __restrict__ cstart, const GridParams* __restrict__ gp,
-       const int32_t* __restrict__ rowsidx, const int32_t* __restrict__ rowslot, int64_t nrows, int64_t maxnatom, int64_t nreal_slots,
-       const __grid_constant__ DevParams P, int do_vdw, int do_force, float cutoff_A, double* __restrict__ dedq_slot, float* __restrict__ F,
+       const int32_t* __restrict__ rowsidx, const int32_t* __restrict__ rowslot, int64_t nrows, int64_t maxnatom, int nreal_slots,
+       const __grid_constant__ DevParams P, int do_force, float cutoff_A, double* __restrict__ dedq_slot, float* __restrict__ F,
        double* __restrict__ molacc) {
   __shared__ int q_j[PAIR_WARPS][QCAP];
   __shared__ float s_c6[PAIR_WARPS][TM_MAX_ELE], s_rs12[PAIR_WARPS][TM_MAX_ELE];
@@ -226,7 +238,7 @@ k_pair(const SAtom* __restrict__ sat, const float4* __restrict__ pq, const int32
     SAtom a = sat[j];
     float ddx = (float)(a.x - ci.x), ddy = (float)(a.y - ci.y), ddz = (float)(a.z - ci.z);
     float d2 = ddx * ddx + ddy * ddy + ddz * ddz;
-    pair_eval(P, d2, ddx, ddy, ddz, qi, pq[j].w, s_c6[warp][a.e], s_rs12[warp][a.e], (a.slot < nreal_slots) ? 1.0f : 0.5f, do_vdw, A);
+    pair_eval<ECC, VDW>(P, d2, ddx, ddy, ddz, qi, pq[j].w, s_c6[warp][a.e], s_rs12[warp][a.e], (a.slot < nreal_slots) ? 1.0f : 0.5f, A);
   };
   for (int c0 = 0; c0 < ncol; c0 += 32) {
     // lane -> column c0+lane: run [cb, ce) or empty
@@ -302,11 +314,18 @@ int tm_launch_pair(tm_ctx* c, const SysView& s, int flags) {
   if ((rc = tm_buf(c, c->b_dedq, (size_t)nq * 8))) return rc;
   TM_CUDA(cudaMemsetAsync(c->b_dedq.p, 0, (size_t)nq * 8, c->stream));
   int blocks = (int)((s.nrows + PAIR_WARPS - 1) / PAIR_WARPS);
-  k_pair<<<blocks, PAIR_WARPS * 32, 0, c->stream>>>((const SAtom*)c->b_satom.p, (const float4*)c->b_qs.p, (const int32_t*)c->b_cstart.p,
-                                                   (const GridParams*)c->b_grid.p, (const int32_t*)c->b_rowsidx.p, (const int32_t*)c->b_rowslot.p,
-                                                   s.nrows, s.maxnatom, nq, c->hp, (flags & TM_F_VDW) ? 1 : 0,
-                                                   (flags & TM_F_FORCE) ? 1 : 0, (float)c->params.ee_cutoff_off, (double*)c->b_dedq.p,
-                                                   (float*)c->b_F.p, (double*)c->b_molacc.p);
+  if (nq > 0x7fffffff) { tm_set_error("too many slots"); return TM_EINVAL; }
+  auto launch = [&](auto kern) {
+    kern<<<blocks, PAIR_WARPS * 32, 0, c->stream>>>((const SAtom*)c->b_satom.p, (const float4*)c->b_qs.p, (const int32_t*)c->b_cstart.p,
+                                                    (const GridParams*)c->b_grid.p, (const int32_t*)c->b_rowsidx.p, (const int32_t*)c->b_rowslot.p,
+                                                    s.nrows, s.maxnatom, (int)nq, c->hp, (flags & TM_F_FORCE) ? 1 : 0,
+                                                    (float)c->params.ee_cutoff_off, (double*)c->b_dedq.p, (float*)c->b_F.p, (double*)c->b_molacc.p);
+  };
+  bool ecc = c->hp.add_ecc != 0, vdw = (flags & TM_F_VDW) != 0;
+  if (ecc && vdw) launch(k_pair<true, true>);
+  else if (ecc) launch(k_pair<true, false>);
+  else if (vdw) launch(k_pair<false, true>);
+  else launch(k_pair<false, false>);
   c->launches++;
   TM_CUDA(cudaGetLastError());
   return TM_OK;
