@@ -177,25 +177,44 @@ def run_b200(args, rank, world, local_rank):
     for _ in range(max(args.warmup, 3)):
         step_resident()
     barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    # stage timings and the launch count come from one kernel-by-kernel pass (events inside a graph cannot be read back)
     stage = {"mlp": 0.0, "desc": 0.0, "force": 0.0, "pair": 0.0, "nlist": 0.0}
     launches = 0
-    barrier()
-    for a, b in evs:
-        flush.zero_()                      # L2 flush between timed iterations (not timed)
-        a.record()
-        step_resident()
-        b.record()
-        if slab is None:
-            t = eng.timings()              # synchronises AFTER the end event was recorded
+    nstage = 5
+    if slab is None:
+        for _ in range(nstage):
+            flush.zero_()
+            step_resident()
+            t = eng.timings()
             stage["mlp"] += t["mlp_fwd"] + t["mlp_bwd"]
             stage["desc"] += t["desc"]
             stage["force"] += t["force"]
             stage["pair"] += t["pair"]
             stage["nlist"] += t["nlist"]
             launches = t["launches"]
+    else:
+        torch.cuda.synchronize()
+        launches = eng.timings()["launches"]      # kernels of the three phases of this rank's last step
+    step_timed = step_resident
+    if args.graph:
+        from tensormol_b200.engine import GraphedCall
+        if slab is None:
+            step_timed = GraphedCall(step_resident, stream, warmup=1)
+        else:                              # three graphs, the NCCL all-reduces between them stay eager
+            slab.capture(xyz_t, Z_t, lat, 1, stream)
+            step_timed = slab.step_replay
+        for _ in range(3):
+            step_timed()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    for a, b in evs:
+        flush.zero_()                      # L2 flush between timed iterations (not timed)
+        a.record()
+        step_timed()
+        b.record()
     barrier()
     ms = sum(a.elapsed_time(b) for a, b in evs)
     tms = torch.tensor([ms], dtype=torch.float64, device=dev)
@@ -226,9 +245,9 @@ def run_b200(args, rank, world, local_rank):
         t0 = time.perf_counter()
         for _ in range(args.steps):
             xyz_t.copy_(xh, non_blocking=True)
-            e, g = slab.step(xyz_t, Z_t, lat, 1)
-            gh.copy_(g, non_blocking=True)
-            e_tot = float(e[0].item())
+            step_timed()
+            gh.copy_(slab.grad, non_blocking=True)
+            e_tot = float(slab.e[0].item())
         barrier()
         e2e_s = time.perf_counter() - t0
         te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
@@ -248,13 +267,13 @@ def run_b200(args, rank, world, local_rank):
             "dtype": {0: "f32", 1: "f16x2-split (fp32 accumulate)"}[args.gemm_mode], "data": "synthetic",
             "config": {"workload": f"{natom}-atom periodic water box (C4: {args.nx}^3 waters, L={lat[0, 0]:.3f} A, 27 images), BP+EE single-point energy+force, nets {HIDDEN}, random-init weights seed 0",
                        "l2": "flushed between timed iterations (512 MiB write)", "parallelism": f"slab{world}" if world > 1 else "single",
-                       "gemm_mode": args.gemm_mode},
+                       "gemm_mode": args.gemm_mode, "launch": ("CUDA graph replay of the step" if world == 1 else "one CUDA graph per phase, eager NCCL all-reduces between") if args.graph else "kernel by kernel"},
             "e2e": {"value": e2e_val, "unit": "atom-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches) * args.steps if launches else None,
             "clocks": sampler.summary(), "Etotal": e_tot}
     if slab is None:
-        mlp_ms = stage["mlp"] / args.steps
-        df_ms = (stage["desc"] + stage["force"]) / args.steps
+        mlp_ms = stage["mlp"] / nstage
+        df_ms = (stage["desc"] + stage["force"]) / nstage
         ach = flops / (mlp_ms * 1e-3) / 1e12
         line["roofline"] = {"bound": "tensor", "achieved": ach, "peak": tc_peak, "unit": "TFLOP/s", "frac": ach / tc_peak, "traffic": None,
                             "kernel": "grouped per-element MLP GEMMs (fwd + bwd-data, both nets)", "peak_source": which,
@@ -263,7 +282,7 @@ def run_b200(args, rank, world, local_rank):
         line["descriptor_roofline"] = {"bound": "hbm", "achieved": bytes_df / (df_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                                        "frac": bytes_df / (df_ms * 1e-3) / 1e9 / hbm_peak, "ms_per_step": df_ms,
                                        "kernels": "k_desc + k_force", "algorithmic_bytes_per_step": bytes_df}
-        line["stage_ms"] = {k: v / args.steps for k, v in stage.items()}
+        line["stage_ms"] = {k: v / nstage for k, v in stage.items()}
         try:
             n, ts, cores, desc = cpu_sample_run(2, os.cpu_count())
             line["cpu_baseline"] = {"value": n * len(ts) / sum(ts), "unit": "atom-steps/s", "cores": cores, "kind": "port", "sample": desc}
@@ -281,7 +300,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--nx", type=int, default=20, help="waters per box edge (20 -> 24,000 atoms)")
-    ap.add_argument("--gemm-mode", type=int, default=1, help="0 = fp32 FFMA, 1 = tcgen05 3xTF32 (default)")
+    ap.add_argument("--gemm-mode", type=int, default=1, help="0 = fp32 FFMA, 1 = tcgen05 split-fp16 (default)")
+    ap.add_argument("--graph", type=int, default=1, help="1 = the resident step is replayed from a CUDA graph (default), 0 = launched kernel by kernel")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -674,6 +674,12 @@ static int64_t tess_count(int64_t nreal, int ntess) {
 }
 
 // device-side tessellation; xyz_dev / Z_dev are DEVICE pointers to the primitive cell
+struct LatArgs { double v[10]; };
+__global__ void k_set_lattice(LatArgs a, double* __restrict__ lat, double* __restrict__ inv_n) {
+  if (threadIdx.x < 10) lat[threadIdx.x] = a.v[threadIdx.x];
+  if (threadIdx.x == 0) inv_n[0] = a.v[9];
+}
+
 static int prepare_lattice(tm_ctx* c, const double* xyz_dev, const int32_t* Z_dev, int64_t nreal, const double* lattice, int ntess, SysView* sv) {
   int rc;
   if (ntess < 1 || ntess > 8) { tm_set_error("ntess must be 1..8"); return TM_EINVAL; }
@@ -681,12 +687,13 @@ static int prepare_lattice(tm_ctx* c, const double* xyz_dev, const int32_t* Z_de
   if ((rc = tm_buf(c, c->b_pos, (size_t)nslots * 24))) return rc;
   if ((rc = tm_buf(c, c->b_Z, (size_t)nslots * 4))) return rc;
   if ((rc = tm_buf(c, c->b_lattice, 16 * 8))) return rc;
-  double hl[10];
-  memcpy(hl, lattice, 72);
-  hl[9] = 1.0 / (double)nreal;
-  TM_CUDA(cudaMemcpyAsync(c->b_lattice.p, hl, 80, cudaMemcpyHostToDevice, c->stream));
   if ((rc = tm_buf(c, c->b_natom, 8))) return rc;
-  TM_CUDA(cudaMemcpyAsync(c->b_natom.p, (const double*)c->b_lattice.p + 9, 8, cudaMemcpyDeviceToDevice, c->stream));
+  // lattice and 1/natom travel as kernel arguments (no pageable copy: the call sequence stays CUDA-graph capturable)
+  LatArgs la;
+  memcpy(la.v, lattice, 72);
+  la.v[9] = 1.0 / (double)nreal;
+  k_set_lattice<<<1, 32, 0, c->stream>>>(la, (double*)c->b_lattice.p, (double*)c->b_natom.p);
+  c->launches++;
   if ((rc = tm_launch_tessellate(c, xyz_dev, Z_dev, nreal, (const double*)c->b_lattice.p, ntess))) return rc;
   *sv = make_view(c, nslots, 1, nslots, nreal, 1, nreal);
   // inverse lattice first row (for slab ownership): frac_a = pos . g

@@ -207,12 +207,15 @@ template <bool ECC, bool VDW>
 __global__ void __launch_bounds__(PAIR_WARPS * 32)
 k_pair(const SAtom* __restrict__ sat, const float4* __restrict__ pq, const int32_t* __restrict__ cstart, const GridParams* __restrict__ gp,
        const int32_t* __restrict__ rowsidx, const int32_t* __restrict__ rowslot, int64_t nrows, int64_t maxnatom, int nreal_slots,
-       const __grid_constant__ DevParams P, int do_force, float cutoff_A, double* __restrict__ dedq_slot, float* __restrict__ F,
+       const __grid_constant__ DevParams P, int do_force, float cutoff_A, int split, double* __restrict__ dedq_slot, float* __restrict__ F,
        double* __restrict__ molacc) {
   __shared__ int q_j[PAIR_WARPS][QCAP];
   __shared__ float s_c6[PAIR_WARPS][TM_MAX_ELE], s_rs12[PAIR_WARPS][TM_MAX_ELE];
   int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  int64_t row = (int64_t)blockIdx.x * PAIR_WARPS + warp;
+  // `split` warps share one centre (few centres: slab runs, small systems); warp `sub` takes every split-th column
+  int64_t gw = (int64_t)blockIdx.x * PAIR_WARPS + warp;
+  int64_t row = gw / split;
+  int sub = (int)(gw - row * split);
   if (row >= nrows) return;
   int slot = rowslot[row];
   if (slot < 0) return;
@@ -240,10 +243,10 @@ k_pair(const SAtom* __restrict__ sat, const float4* __restrict__ pq, const int32
     float d2 = ddx * ddx + ddy * ddy + ddz * ddz;
     pair_eval<ECC, VDW>(P, d2, ddx, ddy, ddz, qi, pq[j].w, s_c6[warp][a.e], s_rs12[warp][a.e], (a.slot < nreal_slots) ? 1.0f : 0.5f, A);
   };
-  for (int c0 = 0; c0 < ncol; c0 += 32) {
-    // lane -> column c0+lane: run [cb, ce) or empty
+  for (int c0 = 0; c0 * split < ncol; c0 += 32) {
+    // lane -> column (c0+lane)*split + sub: run [cb, ce) or empty
     int cb = 0, ce = 0;
-    int cidx = c0 + lane;
+    int cidx = (c0 + lane) * split + sub;
     if (cidx < ncol) {
       int x = x0 + cidx / ny, y = y0 + cidx % ny;
       float lx = fmaxf(0.f, fmaxf(x * cell - pi.x, pi.x - (x + 1) * cell));   // distance from the centre to the column's slab in x
@@ -296,7 +299,8 @@ k_pair(const SAtom* __restrict__ sat, const float4* __restrict__ pq, const int32
     A.gz += __shfl_xor_sync(FULL, A.gz, o);
   }
   if (lane == 0) {
-    dedq_slot[slot] = (double)A.dedq;
+    if (split == 1) dedq_slot[slot] = (double)A.dedq;
+    else atomicAdd(&dedq_slot[slot], (double)A.dedq);   // zeroed by the launcher
     if (do_force) {
       atomicAdd(F + 3 * (int64_t)slot, A.gx);
       atomicAdd(F + 3 * (int64_t)slot + 1, A.gy);
@@ -313,13 +317,17 @@ int tm_launch_pair(tm_ctx* c, const SysView& s, int flags) {
   int64_t nq = s.periodic ? s.nreal : s.nslots;
   if ((rc = tm_buf(c, c->b_dedq, (size_t)nq * 8))) return rc;
   TM_CUDA(cudaMemsetAsync(c->b_dedq.p, 0, (size_t)nq * 8, c->stream));
-  int blocks = (int)((s.nrows + PAIR_WARPS - 1) / PAIR_WARPS);
+  // enough warps to fill the machine: one per centre for large systems, up to 8 per centre for small ones / slabs
+  int64_t expect = std::max<int64_t>(1, s.slab_world > 1 ? (s.periodic ? s.nreal : s.nslots) / s.slab_world : s.ncent_max);
+  int split = 1;
+  while (split < 8 && expect * split < 148 * 48) split *= 2;
+  int blocks = (int)((s.nrows * split + PAIR_WARPS - 1) / PAIR_WARPS);
   if (nq > 0x7fffffff) { tm_set_error("too many slots"); return TM_EINVAL; }
   auto launch = [&](auto kern) {
     kern<<<blocks, PAIR_WARPS * 32, 0, c->stream>>>((const SAtom*)c->b_satom.p, (const float4*)c->b_qs.p, (const int32_t*)c->b_cstart.p,
                                                     (const GridParams*)c->b_grid.p, (const int32_t*)c->b_rowsidx.p, (const int32_t*)c->b_rowslot.p,
                                                     s.nrows, s.maxnatom, (int)nq, c->hp, (flags & TM_F_FORCE) ? 1 : 0,
-                                                    (float)c->params.ee_cutoff_off, (double*)c->b_dedq.p, (float*)c->b_F.p, (double*)c->b_molacc.p);
+                                                    (float)c->params.ee_cutoff_off, split, (double*)c->b_dedq.p, (float*)c->b_F.p, (double*)c->b_molacc.p);
   };
   bool ecc = c->hp.add_ecc != 0, vdw = (flags & TM_F_VDW) != 0;
   if (ecc && vdw) launch(k_pair<true, true>);

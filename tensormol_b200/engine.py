@@ -86,6 +86,28 @@ def _ptr(a):
     return a.ctypes.data_as(C.c_void_p) if a is not None else None
 
 
+class GraphedCall:
+    """Captures `fn()` -- device-pointer calls of this library (tm_eval_lattice_dev, the slab phases) and torch ops,
+    all issued on `stream` -- into a CUDA graph and replays it: one launch per step instead of ~40, no host work
+    between kernels.  The buffers `fn` touches must stay allocated and keep their addresses; new positions are
+    written into the captured input tensor in place.  `fn` is run `warmup` times first so that every library buffer
+    has its final size (allocation is not capturable)."""
+
+    def __init__(self, fn, stream, warmup=3):
+        import torch
+        self.stream = stream
+        with torch.cuda.stream(stream):
+            for _ in range(max(1, warmup)):
+                fn()
+        stream.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph, stream=stream):
+            fn()
+
+    def __call__(self):
+        self.graph.replay()
+
+
 class Engine:
     """One CUDA context of the BP+EE evaluator."""
 
