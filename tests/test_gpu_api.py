@@ -182,6 +182,42 @@ def test_nve_md_on_gpu_forces_conserves_energy():
     assert np.all(np.isfinite(md.md_log)) and drift < 0.05 * scale + 1e-3 * abs(etot[2])
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("thermostat,graph", [(None, True), (None, False), ("Nose", True)])
+def test_device_md_matches_host_driver(thermostat, graph):
+    """the on-device integrator (state on the GPU, CUDA-graph replay) follows the host driver
+    (PeriodicVelocityVerlet / PeriodicNoseThermostat on numpy arrays, same device forces) step for step."""
+    from tensormol_b200 import PARAMS, Mol, PeriodicForce, PeriodicVelocityVerlet
+    from tensormol_b200.Simulations.DeviceMD import DevicePeriodicVelocityVerlet
+    Z, X, lat = water_box(3, jitter=0.02)
+    m = Mol(Z.astype(np.uint8), X)
+    manager, W = _manager([m], [64, 64], 7)
+    nstep = 12
+    PARAMS["MDMaxStep"] = nstep
+    PARAMS["MDdt"] = 0.2
+    PARAMS["MDV0"] = None
+    PARAMS["MDTemp"] = 300.0
+    PARAMS["MDThermostat"] = thermostat
+    rs = np.random.RandomState(5)
+    v0 = 1e-3 * rs.randn(len(Z), 3)
+    pf = PeriodicForce(m, lat)
+    pf.BindLatticeForce(manager.LatticeForce(), 15.0)
+    host = PeriodicVelocityVerlet(pf, "host_md", v0_=v0.copy())
+    v_start = host.v.copy()                       # the Nose constructor rescales v0 to MDTemp
+    host.Prop()
+    dev = DevicePeriodicVelocityVerlet(manager, m, lat, "dev_md", v0_=v0.copy(), graph_=graph, sync_every_=5)
+    log = dev.Prop()
+    if thermostat is None:
+        assert np.allclose(v_start, v0)
+    xh = pf.lattice.ModuloLattice(host.x)
+    d = dev.x - xh
+    d -= np.round(d @ np.linalg.inv(lat)) @ lat   # same point modulo the lattice
+    assert np.abs(d).max() < 1e-7
+    assert np.abs(dev.v - host.v).max() < 1e-7 * max(1.0, np.abs(host.v).max() / 1e-3)
+    assert abs(dev.EPot - host.EPot) < 1e-6 * abs(host.EPot)
+    assert np.all(np.isfinite(log)) and log[nstep - 1, 5] == dev.EPot
+
+
 def test_geometry_optimizer_lowers_energy_on_gpu_potential():
     from tensormol_b200 import PARAMS, GeomOptimizer, Mol
     g = load_golden("h2o_cluster")
