@@ -25,7 +25,18 @@ __device__ __forceinline__ void tri_inv_f(int t, int& j, int& k) {
 }
 
 size_t tm_force_smem_floats_per_warp(const DevParams& P) {
-  return (size_t)P.n_ele * (P.nRs_r + 1) + (size_t)P.n_elep * (P.nsym + 1) + 5 * TM_ANG_CAP + 2 * TM_ANG_CAP + 3 * TM_ANG_CAP;
+  return (size_t)P.n_ele * (P.nRs_r + 1) + (size_t)P.n_elep * (P.nsym + 1) + 6 * TM_ANG_CAP + 2 * TM_ANG_CAP + 3 * TM_ANG_CAP;
+}
+
+__device__ __forceinline__ float f_ex2(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float f_rcp(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
 }
 
 template <int NAS_MAX, int NRS_MAX>
@@ -49,7 +60,8 @@ k_force(const SAtom* __restrict__ sat, const int32_t* __restrict__ rowsidx, cons
   float* az = ay + TM_ANG_CAP;
   float* ar = az + TM_ANG_CAP;
   float* afc = ar + TM_ANG_CAP;
-  int* ae = (int*)(afc + TM_ANG_CAP);
+  float* adfc = afc + TM_ANG_CAP;
+  int* ae = (int*)(adfc + TM_ANG_CAP);
   int* aslot = ae + TM_ANG_CAP;                  // destination slot for the force, -1 = dropped
   float* Ft = (float*)(aslot + TM_ANG_CAP);      // [ANG_CAP][3]
 
@@ -74,6 +86,7 @@ k_force(const SAtom* __restrict__ sat, const int32_t* __restrict__ rowsidx, cons
 
   SAtom ci = sat[rowsidx[row]];
   int b = (int)row * TM_NB_STRIDE, e = b + nbcnt[row];
+  const float nel2 = -P.eta * 1.4426950408889634f;   // exp(-eta x) = 2^(nel2 x)
   float gix = 0.f, giy = 0.f, giz = 0.f;   // dE/dx_i accumulated by this lane
   int nang = 0;
   for (int j0 = b; j0 < e; j0 += 32) {
@@ -94,17 +107,18 @@ k_force(const SAtom* __restrict__ sat, const int32_t* __restrict__ rowsidx, cons
       // radial: dE/dr = sum_s A[e_j][s] * d/dr [ exp(-eta (r-Rs)^2) fc(r) ]
       float arg = P.pi_over_rRc * r;
       float sn, cs;
-      sincosf(arg, &sn, &cs);
+      __sincosf(arg, &sn, &cs);                     // arg in [0, pi]: absolute error < 5e-7
       float fc = 0.5f * (cs + 1.0f);
       float dfc = -0.5f * sn * P.pi_over_rRc;
       const float* Arow = Ar + ej * rstr;
       float dEdr = 0.f;
+      const float m2ef = -2.0f * P.eta * fc;
       for (int s = 0; s < P.nRs_r; s++) {
         float d = r - P.Rs_r[s];
-        float g = expf(-P.eta * d * d);
-        dEdr += Arow[s] * g * (dfc - 2.0f * P.eta * d * fc);
+        float g = f_ex2(nel2 * d * d);               // exp(-eta d^2)
+        dEdr = fmaf(Arow[s] * g, fmaf(m2ef, d, dfc), dEdr);
       }
-      float sc = dEdr / r;
+      float sc = dEdr * f_rcp(r);
       float gx = sc * dx, gy = sc * dy, gz = sc * dz;   // dE/dx_j  (d = x_j - x_i)
       gix -= gx; giy -= gy; giz -= gz;
       if (dst >= 0) {
@@ -118,7 +132,10 @@ k_force(const SAtom* __restrict__ sat, const int32_t* __restrict__ rowsidx, cons
       int pos = nang + __popc(mk & ((1u << lane) - 1));
       if (pos < TM_ANG_CAP) {
         ax[pos] = dx; ay[pos] = dy; az[pos] = dz; ar[pos] = r;
-        afc[pos] = P.pi_over_aRc * r;   // the angle; fc and fc' are formed per triple
+        float sa_, ca_;
+        __sincosf(P.pi_over_aRc * r, &sa_, &ca_);
+        afc[pos] = 0.5f * (ca_ + 1.0f);              // fc(r, Ra) and its derivative, once per neighbour
+        adfc[pos] = -0.5f * sa_ * P.pi_over_aRc;
         ae[pos] = ej;
         aslot[pos] = dst;
       }
@@ -136,7 +153,7 @@ k_force(const SAtom* __restrict__ sat, const int32_t* __restrict__ rowsidx, cons
       tri_inv_f(t, j, k);
       float ajx = ax[j], ajy = ay[j], ajz = az[j], akx = ax[k], aky = ay[k], akz = az[k];
       float ra = ar[j], rb = ar[k];
-      float ira = 1.0f / ra, irb = 1.0f / rb;
+      float ira = f_rcp(ra), irb = f_rcp(rb);
       // unit vectors
       float uax = ajx * ira, uay = ajy * ira, uaz = ajz * ira;
       float ubx = akx * irb, uby = aky * irb, ubz = akz * irb;
@@ -144,18 +161,15 @@ k_force(const SAtom* __restrict__ sat, const int32_t* __restrict__ rowsidx, cons
       float nx = uay * ubz - uaz * uby, ny = uaz * ubx - uax * ubz, nz = uax * uby - uay * ubx;
       float s = sqrtf(nx * nx + ny * ny + nz * nz);
       c = fminf(1.0f, fmaxf(-1.0f, c));
-      float sj, cj, sk, ck;
-      sincosf(afc[j], &sj, &cj);
-      sincosf(afc[k], &sk, &ck);
-      float fa = 0.5f * (cj + 1.0f), fb = 0.5f * (ck + 1.0f);
-      float dfa = -0.5f * sj * P.pi_over_aRc, dfb = -0.5f * sk * P.pi_over_aRc;
+      float fa = afc[j], fb = afc[k];
+      float dfa = adfc[j], dfb = adfc[k];
       float rho = 0.5f * (ra + rb);
       float E[NRS_MAX], dE[NRS_MAX];
 #pragma unroll
       for (int q = 0; q < NRS_MAX; q++) {
         if (q < P.nRs_a) {
           float d = rho - P.Rs_a[q];
-          float g = expf(-P.eta * d * d);
+          float g = f_ex2(nel2 * d * d);
           E[q] = g;
           dE[q] = -2.0f * P.eta * d * g;
         } else {
@@ -201,7 +215,7 @@ k_force(const SAtom* __restrict__ sat, const int32_t* __restrict__ rowsidx, cons
       float dVdt = Wt * ff;
       float dVda_r = 0.5f * Wr * ff + W * dfa * fb;   // along a_hat
       float dVdb_r = 0.5f * Wr * ff + W * fa * dfb;   // along b_hat
-      float is = (s > 1e-6f) ? 1.0f / s : 0.f;
+      float is = (s > 1e-6f) ? f_rcp(s) : 0.f;
       // dtheta/da = -(b_hat - c a_hat)/(|a| s) ; dtheta/db = -(a_hat - c b_hat)/(|b| s)
       float ta = -dVdt * is * ira, tb = -dVdt * is * irb;
       float gax = ta * (ubx - c * uax) + dVda_r * uax;
