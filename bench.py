@@ -275,7 +275,10 @@ def run_b200(args, rank, world, local_rank):
         mlp_ms = stage["mlp"] / nstage
         df_ms = (stage["desc"] + stage["force"]) / nstage
         ach = flops / (mlp_ms * 1e-3) / 1e12
-        line["roofline"] = {"bound": "tensor", "achieved": ach, "peak": tc_peak, "unit": "TFLOP/s", "frac": ach / tc_peak, "traffic": None,
+        # traffic: dram__bytes_read.sum + dram__bytes_write.sum of the six k_gemm_tc launches of one 24k-atom step
+        # (profiles/r02_ncu_hot_kernels.csv, ncu --set full), only meaningful for that workload
+        traffic = 1.04e9 if (args.nx == 20 and args.gemm_mode == 1) else None
+        line["roofline"] = {"bound": "tensor", "achieved": ach, "peak": tc_peak, "unit": "TFLOP/s", "frac": ach / tc_peak, "traffic": traffic,
                             "kernel": "grouped per-element MLP GEMMs (fwd + bwd-data, both nets)", "peak_source": which,
                             "ms_per_step": mlp_ms, "algorithmic_flops_per_step": flops}
         bytes_df = (44 + 8 * (40.3 + 10.4) + 8 * eng.D) * natom

@@ -249,3 +249,41 @@ def test_eval_lattice_unwrapped_input_falls_back_to_bbox_grid():
     # and the wrapped call still works on the same context afterwards
     r3 = eng.evaluate_lattice(g["xyz"], g["Z"], g["lattice"], int(g["ntess"]))
     _check_energy(r3["Etotal"], g["oracle_Etotal"], "Etotal")
+
+
+def test_graph_replay_equals_eager_device_call():
+    """engine.GraphedCall: the captured tm_eval_lattice_dev step, replayed after the positions were changed in place,
+    gives the numbers of an eager call on the new positions."""
+    import ctypes as C
+    import torch
+    from tensormol_b200.engine import GraphedCall
+    Z, X, lat = water_box(4)
+    from oracle import oracle_np as onp
+    X = onp.modulo_lattice(lat, X)
+    eng, _, _ = _engine([1, 8], [128, 128], 3)
+    dev = torch.device("cuda", 0)
+    stream = torch.cuda.Stream(device=dev)
+    eng.set_stream(C.c_void_p(stream.cuda_stream))
+    n = len(Z)
+    with torch.cuda.stream(stream):
+        x = torch.tensor(X, dtype=torch.float64, device=dev)
+        z = torch.tensor(Z, dtype=torch.int32, device=dev)
+        e = torch.zeros(6, dtype=torch.float64, device=dev)
+        g = torch.zeros(n, 3, dtype=torch.float64, device=dev)
+
+        def step():
+            eng.evaluate_lattice_dev(C.c_void_p(x.data_ptr()), C.c_void_p(z.data_ptr()), n, lat, 1, C.c_void_p(e.data_ptr()), C.c_void_p(g.data_ptr()))
+
+        gc = GraphedCall(step, stream)
+        X2 = onp.modulo_lattice(lat, X + 0.05 * np.random.RandomState(2).randn(*X.shape))
+        x.copy_(torch.tensor(X2, dtype=torch.float64))
+        gc()
+        stream.synchronize()
+        e_graph, g_graph = e.cpu().numpy().copy(), g.cpu().numpy().copy()
+        step()
+        stream.synchronize()
+    eng.sync()   # surfaces device flags of the pointer API
+    assert np.array_equal(e_graph[:4], e.cpu().numpy()[:4]) or np.allclose(e_graph[:4], e.cpu().numpy()[:4], rtol=1e-7, atol=1e-9)
+    assert np.abs(g_graph - g.cpu().numpy()).max() <= 1e-6 * np.abs(g_graph).max()
+    r = eng.evaluate_lattice(X2, Z, lat, 1)
+    _check_energy(e_graph[0:1], r["Etotal"], "Etotal")
