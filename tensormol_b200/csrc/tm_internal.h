@@ -138,7 +138,7 @@ struct tm_ctx {
   DevBuf b_pos, b_Z, b_cellid, b_rank, b_count, b_cstart, b_sorted, b_satom, b_scan_tmp;
   DevBuf b_rowslot, b_rowsidx, b_rowofslot, b_blkcnt, b_rowmeta;
   DevBuf b_nbcnt, b_nboff, b_nbr, b_G, b_Gs, b_ypart, b_act[2][TM_MAX_HIDDEN], b_delta0, b_delta1, b_dG[2], b_y[2];
-  DevBuf b_q, b_qs, b_dedq, b_u, b_F, b_Fpair, b_acc, b_bbox, b_grid, b_flags, b_out, b_molacc;
+  DevBuf b_q, b_qs, b_dedq, b_u, b_F, b_acc, b_bbox, b_grid, b_flags, b_out, b_molacc;
   DevBuf b_natom, b_lattice;
   // host staging (pinned)
   void* h_stage = nullptr;
@@ -180,7 +180,6 @@ int tm_launch_mlp_backward(tm_ctx* c, const SysView& s);
 int tm_launch_charges(tm_ctx* c, const SysView& s);
 int tm_launch_pair(tm_ctx* c, const SysView& s, int flags);
 int tm_launch_force(tm_ctx* c, const SysView& s, int flags);
-int tm_launch_finalize(tm_ctx* c, const SysView& s, int flags);
 
 // generic CSR neighbour list for the MolEmb-compatible API
 int tm_launch_nlist_csr(tm_ctx* c, const SysView& s, double rc, int do_perms, int64_t* total_out);

@@ -165,16 +165,14 @@ int tm_launch_gemm(tm_ctx* c, const GemmGroup* groups, int ngroups, const int* r
 
 
 // ------------------------------------------------------------------------------------------------
-// output layer (H_last -> 1), its backward seed, and the hi/lo split used by the tcgen05 path
+// output layer (H_last -> 1) and its backward seed (fp32 mode), and the hi/lo split used by the tcgen05 path
 // ------------------------------------------------------------------------------------------------
 struct OutTbl {
   const float* w[2][TM_MAX_ELE];
   float b[2][TM_MAX_ELE];
-  const void* h[2];       // last hidden activation [nrows][ld]: fp32, or the fp16 hi plane in split mode
-  const void* h_lo[2];    // fp16 scaled-lo plane (split mode) or nullptr
+  const float* h[2];      // last hidden activation [nrows][ld]
   float* y[2];            // [nrows]
-  void* delta[2];         // [nrows][ld]
-  void* delta_lo[2];
+  float* delta[2];        // [nrows][ld]
   int ld, H;
 };
 
@@ -186,26 +184,10 @@ __device__ __forceinline__ int row_element(const int32_t* rowmeta, int64_t row, 
   return -1;
 }
 
-// split-fp16 operand format of the tcgen05 path (tm_gemm_tc.cu): x = hi + lo / 2048
-#define LO_SCALE 2048.0f
-#define LO_INV (1.0f / 2048.0f)
-__device__ __forceinline__ void split4(float4 v, uint2& hi, uint2& lo) {
-  __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
-  float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
-  __half2 l0 = __floats2half2_rn((v.x - f0.x) * LO_SCALE, (v.y - f0.y) * LO_SCALE);
-  __half2 l1 = __floats2half2_rn((v.z - f1.x) * LO_SCALE, (v.w - f1.y) * LO_SCALE);
-  hi = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
-  lo = make_uint2(*reinterpret_cast<uint32_t*>(&l0), *reinterpret_cast<uint32_t*>(&l1));
-}
-__device__ __forceinline__ float4 join4(uint2 hi, uint2 lo) {
-  float2 a0 = __half22float2(*reinterpret_cast<__half2*>(&hi.x)), a1 = __half22float2(*reinterpret_cast<__half2*>(&hi.y));
-  float2 b0 = __half22float2(*reinterpret_cast<__half2*>(&lo.x)), b1 = __half22float2(*reinterpret_cast<__half2*>(&lo.y));
-  return make_float4(fmaf(b0.x, LO_INV, a0.x), fmaf(b0.y, LO_INV, a0.y), fmaf(b1.x, LO_INV, a1.x), fmaf(b1.y, LO_INV, a1.y));
-}
-
+// fp32 mode only (the tensor-core path fuses this into the last hidden layer's GEMM epilogue, TM_EPI_ACT_OUT):
 // one warp per (row, net): y = h . w + b ; delta = w * a'(h)
 __global__ void k_out_layer(const __grid_constant__ OutTbl T, const int32_t* __restrict__ rowmeta, int64_t nrows, int n_ele, int act_kind,
-                            float act_alpha, int split) {
+                            float act_alpha) {
   int64_t wid = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   int lane = threadIdx.x & 31;
   int net = (int)(wid & 1);
@@ -216,26 +198,27 @@ __global__ void k_out_layer(const __grid_constant__ OutTbl T, const int32_t* __r
   const float* w = T.w[net][e];
   float s = 0.f;
   for (int i = lane * 4; i < T.ld; i += 128) {
-    float4 hv;
-    if (split) hv = join4(*reinterpret_cast<const uint2*>((const __half*)T.h[net] + row * T.ld + i),
-                          *reinterpret_cast<const uint2*>((const __half*)T.h_lo[net] + row * T.ld + i));
-    else hv = *reinterpret_cast<const float4*>((const float*)T.h[net] + row * T.ld + i);
+    float4 hv = *reinterpret_cast<const float4*>(T.h[net] + row * T.ld + i);
     float4 wv = *reinterpret_cast<const float4*>(w + i);
     s += hv.x * wv.x + hv.y * wv.y + hv.z * wv.z + hv.w * wv.w;
-    float4 dv = make_float4(wv.x * act_bwd_from_h(hv.x, act_kind, act_alpha), wv.y * act_bwd_from_h(hv.y, act_kind, act_alpha),
-                            wv.z * act_bwd_from_h(hv.z, act_kind, act_alpha), wv.w * act_bwd_from_h(hv.w, act_kind, act_alpha));
-    if (split) {
-      uint2 dh, dl;
-      split4(dv, dh, dl);
-      *reinterpret_cast<uint2*>((__half*)T.delta[net] + row * T.ld + i) = dh;
-      *reinterpret_cast<uint2*>((__half*)T.delta_lo[net] + row * T.ld + i) = dl;
-    } else {
-      *reinterpret_cast<float4*>((float*)T.delta[net] + row * T.ld + i) = dv;
-    }
+    *reinterpret_cast<float4*>(T.delta[net] + row * T.ld + i) =
+        make_float4(wv.x * act_bwd_from_h(hv.x, act_kind, act_alpha), wv.y * act_bwd_from_h(hv.y, act_kind, act_alpha),
+                    wv.z * act_bwd_from_h(hv.z, act_kind, act_alpha), wv.w * act_bwd_from_h(hv.w, act_kind, act_alpha));
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
   if (lane == 0) T.y[net][row] = s + T.b[net][e];
+}
+
+// split-fp16 operand format of the tcgen05 path (tm_gemm_tc.cu): x = hi + lo / 2048
+#define LO_SCALE 2048.0f
+__device__ __forceinline__ void split4(float4 v, uint2& hi, uint2& lo) {
+  __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
+  float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+  __half2 l0 = __floats2half2_rn((v.x - f0.x) * LO_SCALE, (v.y - f0.y) * LO_SCALE);
+  __half2 l1 = __floats2half2_rn((v.z - f1.x) * LO_SCALE, (v.w - f1.y) * LO_SCALE);
+  hi = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+  lo = make_uint2(*reinterpret_cast<uint32_t*>(&l0), *reinterpret_cast<uint32_t*>(&l1));
 }
 
 // x (fp32) -> (hi, scaled lo) fp16 planes
@@ -359,17 +342,15 @@ int tm_launch_mlp_forward(tm_ctx* c, const SysView& s) {
       T.w[net][e] = (e < ne) ? c->nets[net][e].w_out : nullptr;
       T.b[net][e] = (e < ne) ? c->nets[net][e].b_out : 0.f;
     }
-    T.h[net] = c->b_act[net][nh - 1].p;
-    T.h_lo[net] = (const uint16_t*)T.h[net] + (size_t)s.nrows * c->Hp[nh - 1];
+    T.h[net] = (const float*)c->b_act[net][nh - 1].p;
     T.y[net] = (float*)c->b_y[net].p;
-    T.delta[net] = delta_ptr(c, s, nh - 1, net, 0);
-    T.delta_lo[net] = delta_ptr(c, s, nh - 1, net, 1);
+    T.delta[net] = (float*)delta_ptr(c, s, nh - 1, net, 0);
   }
   T.ld = c->Hp[nh - 1];
   T.H = c->desc.hidden[nh - 1];
   int64_t nw = s.nrows * 2;
   int blocks = (int)((nw * 32 + 255) / 256);
-  k_out_layer<<<blocks, 256, 0, c->stream>>>(T, (const int32_t*)c->b_rowmeta.p, s.nrows, ne, c->hp.activation, c->hp.act_alpha, tc ? 1 : 0);
+  k_out_layer<<<blocks, 256, 0, c->stream>>>(T, (const int32_t*)c->b_rowmeta.p, s.nrows, ne, c->hp.activation, c->hp.act_alpha);
   c->launches++;
   TM_CUDA(cudaGetLastError());
   return TM_OK;
