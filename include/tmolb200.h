@@ -53,8 +53,10 @@ enum { TM_ACT_SIGMOID_WITH_PARAM = 0, TM_ACT_RELU = 1, TM_ACT_SOFTPLUS = 2, TM_A
 /* GEMM arithmetic of the per-element MLPs */
 enum {
   TM_GEMM_FP32 = 0,      /* fp32 FFMA tiles (parity reference mode of the library) */
-  TM_GEMM_TC_SPLIT = 1   /* tcgen05 kind::f16 on split operands x = hi + lo/2048 (two fp16 planes, 22 significant bits),
+  TM_GEMM_TC_SPLIT = 1,  /* tcgen05 kind::f16 on split operands x = hi + lo/2048 (two fp16 planes, 22 significant bits),
                             3 MMAs per K-step, fp32 accumulation in TMEM + registers (default) */
+  TM_GEMM_TC_SPLIT_PAIR = 2 /* same arithmetic on CTA pairs: cta_group::2 MMAs of M = 256 over a cluster of two SMs,
+                            each CTA stages its 128 A rows and half of the B rows (fewer L2 bytes per SM) */
 };
 
 /* evaluation flags */

@@ -19,6 +19,7 @@ LIB = os.path.join(PKG, "libtmolb200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
          "--expt-relaxed-constexpr", "-Xptxas", "-v"]
+FLAGS += os.environ.get("TM_EXTRA_NVCC_FLAGS", "").split()   # e.g. -DTC_PROFILE for the GEMM warp-role cycle counters
 
 
 def _digest() -> str:

@@ -245,7 +245,7 @@ extern "C" int tm_set_stream(tm_ctx* c, void* s) {
   return TM_OK;
 }
 extern "C" int tm_set_gemm_mode(tm_ctx* c, int mode) {
-  if (!c || mode < 0 || mode > 1) { tm_set_error("bad gemm mode %d (0 = fp32, 1 = tcgen05 split fp16)", mode); return TM_EINVAL; }
+  if (!c || mode < 0 || mode > 2) { tm_set_error("bad gemm mode %d (0 = fp32, 1 = tcgen05 split fp16, 2 = same on CTA pairs)", mode); return TM_EINVAL; }
   c->gemm_mode = mode;
   return TM_OK;
 }

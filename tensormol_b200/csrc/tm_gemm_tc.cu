@@ -28,6 +28,7 @@
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <cstdlib>
+#include <cstdio>
 #include <map>
 #include <tuple>
 
@@ -44,6 +45,13 @@
 #define TC_LO_INV (1.0f / 2048.0f)
 // 32 rows x 128 bytes transpose tile, 16-byte chunks XOR-swizzled by the row so that both the row-wise (thread = row)
 // and the slab-wise (several lanes per row) 128-bit accesses are bank-conflict free without padding.  Float index.
+#ifdef TC_PROFILE
+#define PROF_T(x) long long x = clock64()
+#define PROF_ADD(slot, t0) do { if (P.prof) atomicAdd(&P.prof[slot], (unsigned long long)(clock64() - (t0))); } while (0)
+#else
+#define PROF_T(x)
+#define PROF_ADD(slot, t0)
+#endif
 #define TB_OFF(r, c4) ((r) * 32 + ((((c4) ^ ((r) & 7))) << 2))
 
 struct alignas(64) TcGroup {
@@ -63,6 +71,7 @@ struct alignas(64) TcParams {
   TcGroup g[TC_MAX_GROUPS];
   int ngroups, act_kind;
   float act_alpha;
+  unsigned long long* prof;   // TC_PROFILE builds: per-CTA cycle counters
 };
 
 // ------------------------------------------------------------------------------------------------ PTX helpers
@@ -127,6 +136,43 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t da, uint64_t 
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// ---- CTA-pair (cta_group::2) variants: one MMA spans two SMs (M = 256), each CTA stages its own 128 A rows and half of
+// the B rows, so the operand bytes an SM pulls from L2 per k-block drop from 64 KB to 48 KB
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {   // same smem offset in CTA `rank` of the cluster
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// the mbarrier (cluster address) may live in the peer CTA: both CTAs of the pair signal the leader's barrier
+__device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* map, uint32_t bar_cluster, void* dst, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(bar_cluster), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+// arrives on the barrier at this smem offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster) : "memory");
+}
+
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
@@ -201,13 +247,15 @@ __device__ __forceinline__ float2 join2(uint32_t hi, uint32_t lo) {
 // ------------------------------------------------------------------------------------------------ kernel
 // EPI: TM_EPI_* (compile time, so each instantiation carries ONE epilogue: a runtime-switched version was
 // 30k SASS instructions and stalled on instruction fetch); ACTK: activation kind or -1 for a runtime switch.
-template <int EPI, int ACTK>
+// NCTA: 1 = one CTA per 128x128 tile; 2 = CTA pair (cluster of 2, cta_group::2) per 256x128 tile: CTA `rank` owns row tile
+// 2*rt2 + rank and stages rows [64*rank, +64) of the B tile; the leader (rank 0) issues the MMAs for both.
+template <int EPI, int ACTK, int NCTA>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_gemm_tc(const __grid_constant__ TcParams P, const int32_t* __restrict__ rowmeta) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  constexpr int BN = TC_BN, STAGES = TC_STAGES;
+  constexpr int BN = TC_BN, STAGES = (NCTA == 2) ? 4 : TC_STAGES;
   constexpr uint32_t A_BYTES = TC_BM * TC_BK * 2;    // 16 KB per plane
-  constexpr uint32_t B_BYTES = BN * TC_BK * 2;
+  constexpr uint32_t B_BYTES = (BN / NCTA) * TC_BK * 2;
   constexpr uint32_t STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint64_t* full_bar = (uint64_t*)(smem + STAGES * STAGE_BYTES);
@@ -217,9 +265,12 @@ k_gemm_tc(const __grid_constant__ TcParams P, const int32_t* __restrict__ rowmet
   uint32_t* tmem_slot = (uint32_t*)(tempty_bar + TC_NPAIR);
   int* tile_base = (int*)(tmem_slot + 4);       // [TC_MAX_GROUPS+1]
   int* row_first = tile_base + TC_MAX_GROUPS + 1;   // [TC_MAX_GROUPS]
-  float* tbuf = (float*)(((uintptr_t)(row_first + TC_MAX_GROUPS) + 15) & ~(uintptr_t)15);  // TC_EPI_WARPS x 4 KB transpose tiles
+  int* row_tiles = row_first + TC_MAX_GROUPS;       // [TC_MAX_GROUPS]
+  float* tbuf = (float*)(((uintptr_t)(row_tiles + TC_MAX_GROUPS) + 15) & ~(uintptr_t)15);  // TC_EPI_WARPS x 4 KB transpose tiles
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = (NCTA == 2) ? cluster_ctarank() : 0u;
+  const int unit = blockIdx.x / NCTA, nunits = gridDim.x / NCTA;   // persistent loop over tiles (NCTA = 1) or tile pairs
 
   if (threadIdx.x == 0) {
     int acc = 0;
@@ -227,19 +278,26 @@ k_gemm_tc(const __grid_constant__ TcParams P, const int32_t* __restrict__ rowmet
       tile_base[g] = acc;
       int rows = rowmeta[2 * P.g[g].ele + 1];
       row_first[g] = rowmeta[2 * P.g[g].ele];
-      acc += ((rows + TC_BM - 1) / TC_BM) * (P.g[g].N / BN);
+      row_tiles[g] = (rows + TC_BM - 1) / TC_BM;
+      acc += ((row_tiles[g] + NCTA - 1) / NCTA) * (P.g[g].N / BN);
     }
     tile_base[P.ngroups] = acc;
     for (int s = 0; s < STAGES; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int a = 0; a < TC_NPAIR; a++) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], TC_EPI_WARPS); }
+    for (int a = 0; a < TC_NPAIR; a++) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], NCTA * TC_EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) {   // TMEM allocation by one warp
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)(TC_NPAIR * 2 * BN)));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  if (warp == 1) {   // TMEM allocation by one warp (the same warp in both CTAs of a pair)
+    if (NCTA == 2) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)(TC_NPAIR * 2 * BN)));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)(TC_NPAIR * 2 * BN)));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
+  if (NCTA == 2) cluster_sync_all();   // barrier initialisation must be visible to the peer before any remote arrive
+  else __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
   const int total_tiles = tile_base[P.ngroups];
@@ -249,7 +307,7 @@ k_gemm_tc(const __grid_constant__ TcParams P, const int32_t* __restrict__ rowmet
     while (g + 1 < P.ngroups && t >= tile_base[g + 1]) g++;
     int local = t - tile_base[g];
     int nct = P.g[g].N / BN;
-    rt = local / nct;
+    rt = local / nct;          // NCTA == 2: index of the row-tile PAIR
     ct = local - rt * nct;
   };
 
@@ -262,46 +320,61 @@ k_gemm_tc(const __grid_constant__ TcParams P, const int32_t* __restrict__ rowmet
       }
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      for (int t = unit; t < total_tiles; t += nunits) {
         int g, rt, ct;
         decode(t, g, rt, ct);
         const TcGroup& G = P.g[g];
-        int row0 = row_first[g] + rt * TC_BM, n0 = ct * BN;
+        // a pair's second CTA may own a row tile past the element's rows (odd tile count): it still stages it (the TMA
+        // zero-fills rows outside the tensor) so that the pair's MMAs and barriers stay uniform; its output is dropped
+        int row0 = row_first[g] + (rt * NCTA + (int)rank) * TC_BM, n0 = ct * BN + (int)rank * (BN / NCTA);
         int nkb = G.K / TC_BK;
         for (int kb = 0; kb < nkb; kb++) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* st = smem + stage * STAGE_BYTES;
-          mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
-          tma_load_2d(&G.mapA_hi, &full_bar[stage], st, kb * TC_BK, row0);
-          tma_load_2d(&G.mapA_lo, &full_bar[stage], st + A_BYTES, kb * TC_BK, row0);
-          tma_load_2d(&G.mapB_hi, &full_bar[stage], st + 2 * A_BYTES, kb * TC_BK, n0);
-          tma_load_2d(&G.mapB_lo, &full_bar[stage], st + 2 * A_BYTES + B_BYTES, kb * TC_BK, n0);
+          if (NCTA == 2) {
+            uint32_t fb = mapa_u32(smem_u32(&full_bar[stage]), 0);     // the leader's barrier collects both CTAs' bytes
+            if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * STAGE_BYTES);
+            tma_load_2d_pair(&G.mapA_hi, fb, st, kb * TC_BK, row0);
+            tma_load_2d_pair(&G.mapA_lo, fb, st + A_BYTES, kb * TC_BK, row0);
+            tma_load_2d_pair(&G.mapB_hi, fb, st + 2 * A_BYTES, kb * TC_BK, n0);
+            tma_load_2d_pair(&G.mapB_lo, fb, st + 2 * A_BYTES + B_BYTES, kb * TC_BK, n0);
+          } else {
+            mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+            tma_load_2d(&G.mapA_hi, &full_bar[stage], st, kb * TC_BK, row0);
+            tma_load_2d(&G.mapA_lo, &full_bar[stage], st + A_BYTES, kb * TC_BK, row0);
+            tma_load_2d(&G.mapB_hi, &full_bar[stage], st + 2 * A_BYTES, kb * TC_BK, n0);
+            tma_load_2d(&G.mapB_lo, &full_bar[stage], st + 2 * A_BYTES + B_BYTES, kb * TC_BK, n0);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (elect_one()) {
-      // instruction descriptor: D=f32, A=B=f16, both K-major, N=BN, M=128
-      constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+    if (rank == 0 && elect_one()) {
+      // instruction descriptor: D=f32, A=B=f16, both K-major, N=BN, M=128 (256 across a CTA pair)
+      constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((TC_BM * NCTA) >> 4) << 24);
       int stage = 0;
       uint32_t phase = 0;
       uint32_t chunk_it = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      for (int t = unit; t < total_tiles; t += nunits) {
         int g, rt, ct;
         decode(t, g, rt, ct);
         int nkb = P.g[g].K / TC_BK;
         for (int kb0 = 0; kb0 < nkb; kb0 += TC_CHUNK, chunk_it++) {
           int pair = chunk_it % TC_NPAIR;
           uint32_t pair_phase = (chunk_it / TC_NPAIR) & 1;
+          PROF_T(t_te);
           mbar_wait(&tempty_bar[pair], pair_phase ^ 1);
+          PROF_ADD(0, t_te);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           uint32_t d_main = tmem_base + (uint32_t)(pair * 2 * BN);
           uint32_t d_cross = d_main + BN;
           int kb1 = min(kb0 + TC_CHUNK, nkb);
           for (int kb = kb0; kb < kb1; kb++) {
+            PROF_T(t_fu);
             mbar_wait(&full_bar[stage], phase);
+            PROF_ADD(1, t_fu);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
             uint64_t a_hi = umma_desc(sa), a_lo = umma_desc(sa + A_BYTES);
@@ -310,14 +383,22 @@ k_gemm_tc(const __grid_constant__ TcParams P, const int32_t* __restrict__ rowmet
             for (int k = 0; k < TC_BK / 16; k++) {
               uint64_t koff = (uint64_t)((k * 16 * 2) >> 4);   // 32 bytes per K=16 step inside the 128B swizzle row
               uint32_t acc = ((kb - kb0) | k) ? 1u : 0u;
-              umma_f16(d_main, a_hi + koff, b_hi + koff, idesc, acc);
-              umma_f16(d_cross, a_lo + koff, b_hi + koff, idesc, acc);
-              umma_f16(d_cross, a_hi + koff, b_lo + koff, idesc, 1u);
+              if (NCTA == 2) {
+                umma_f16_pair(d_main, a_hi + koff, b_hi + koff, idesc, acc);
+                umma_f16_pair(d_cross, a_lo + koff, b_hi + koff, idesc, acc);
+                umma_f16_pair(d_cross, a_hi + koff, b_lo + koff, idesc, 1u);
+              } else {
+                umma_f16(d_main, a_hi + koff, b_hi + koff, idesc, acc);
+                umma_f16(d_cross, a_lo + koff, b_hi + koff, idesc, acc);
+                umma_f16(d_cross, a_hi + koff, b_lo + koff, idesc, 1u);
+              }
             }
-            umma_commit(&empty_bar[stage]);          // frees the smem stage once these MMAs have read it
+            // frees the smem stage (in both CTAs of a pair) once these MMAs have read it
+            if (NCTA == 2) umma_commit_pair(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
-          umma_commit(&tfull_bar[pair]);             // chunk complete -> epilogue drains it
+          // chunk complete -> the epilogue warps (of both CTAs) drain it
+          if (NCTA == 2) umma_commit_pair(&tfull_bar[pair]); else umma_commit(&tfull_bar[pair]);
         }
       }
     }
@@ -331,9 +412,11 @@ k_gemm_tc(const __grid_constant__ TcParams P, const int32_t* __restrict__ rowmet
     const float act_alpha = P.act_alpha;
     const uint32_t tb = smem_u32(tbuf) + (uint32_t)(warp - 2) * 4096u;   // this warp's transpose tile (shared-space address)
     uint32_t chunk_it = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+    for (int t = unit; t < total_tiles; t += nunits) {
       int g, rt, ct;
       decode(t, g, rt, ct);
+      rt = rt * NCTA + (int)rank;
+      const bool live = rt < row_tiles[g];           // false only for the padding tile of an odd pair
       // group fields into registers once per tile (indexed constant loads are long-scoreboard operations)
       const int nkb = P.g[g].K / TC_BK;
       const int64_t ldc = P.g[g].ldc;
@@ -356,7 +439,10 @@ k_gemm_tc(const __grid_constant__ TcParams P, const int32_t* __restrict__ rowmet
       for (int kb0 = 0; kb0 < nkb; kb0 += TC_CHUNK, chunk_it++) {
         int pair = chunk_it % TC_NPAIR;
         uint32_t pair_phase = (chunk_it / TC_NPAIR) & 1;
+        PROF_T(t_tf);
         mbar_wait(&tfull_bar[pair], pair_phase);
+        if (warp == 2 && lane == 0) PROF_ADD(2, t_tf);
+        PROF_T(t_dr);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         uint32_t taddr = tmem_base + (uint32_t)(pair * 2 * BN + half * NC) + ((uint32_t)(q * 32) << 16);
         uint32_t v[NC];
@@ -370,11 +456,18 @@ k_gemm_tc(const __grid_constant__ TcParams P, const int32_t* __restrict__ rowmet
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty_bar[pair]);   // TMEM pair is free again; the adds below overlap the next MMAs
+        // TMEM pair is free again (the leader's barrier counts the warps of both CTAs); the adds below overlap the next MMAs
+        if (lane == 0) {
+          if (NCTA == 2) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[pair]), 0));
+          else mbar_arrive(&tempty_bar[pair]);
+        }
 #pragma unroll
         for (int i = 0; i < NC; i++) accr[i] = fmaf(__uint_as_float(v[i]), TC_LO_INV, accr[i]);
+        if (warp == 2 && lane == 0) PROF_ADD(3, t_dr);
       }
+      PROF_T(t_out);
       // ---- output phase: thread = row of the warp's 32-row band, NC = 64 consecutive columns
+      if (!live) continue;
       if (EPI == TM_EPI_DACT) {
         // act'(h) for the band: lanes work slab-wise (4 lanes per row, 8 rows per instruction) on two 32-column passes,
         // join hi/lo, evaluate act', and hand the fp32 values to the row threads through the swizzled tile.
@@ -496,13 +589,16 @@ k_gemm_tc(const __grid_constant__ TcParams P, const int32_t* __restrict__ rowmet
           __syncwarp();
         }
       }
+      if (warp == 2 && lane == 0) { PROF_ADD(4, t_out); if (P.prof) atomicAdd(&P.prof[5], 1ull); }
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
+  if (NCTA == 2) cluster_sync_all();   // the peer's smem / TMEM stay alive until both CTAs are done
+  else __syncthreads();
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(TC_NPAIR * 2 * BN)));
+    if (NCTA == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(TC_NPAIR * 2 * BN)));
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(TC_NPAIR * 2 * BN)));
   }
 }
 
@@ -545,39 +641,84 @@ static int make_map(CUtensorMap* m, const void* base, int64_t rows, int64_t cols
   return TM_OK;
 }
 
-template <int EPI, int ACTK>
-static int launch_tc(tm_ctx* c, const TcParams& P, const int* rowmeta_dev, int total_tiles_bound) {
+template <int EPI, int ACTK, int NCTA>
+static int launch_tc(tm_ctx* c, const TcParams& P, const int* rowmeta_dev, int total_units_bound) {
+  // NCTA = 1: 3 stages x 64 KB; NCTA = 2: 4 stages x 48 KB -- the same 192 KB
   constexpr size_t smem = (size_t)TC_STAGES * (2 * TC_BM * TC_BK * 2 + 2 * TC_BN * TC_BK * 2) + 1024 + 512 + TC_EPI_WARPS * 32 * 32 * 4;
   static bool configured = false;
   if (!configured) {
-    TM_CUDA(cudaFuncSetAttribute(k_gemm_tc<EPI, ACTK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TM_CUDA(cudaFuncSetAttribute(k_gemm_tc<EPI, ACTK, NCTA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
-  int grid = total_tiles_bound < sms ? total_tiles_bound : sms;
-  if (grid < 1) grid = 1;
-  k_gemm_tc<EPI, ACTK><<<grid, TC_THREADS, smem, c->stream>>>(P, rowmeta_dev);
+  int units = sms / NCTA;
+  if (total_units_bound < units) units = total_units_bound;
+  if (units < 1) units = 1;
+  if (NCTA == 1) {
+    k_gemm_tc<EPI, ACTK, NCTA><<<units, TC_THREADS, smem, c->stream>>>(P, rowmeta_dev);
+  } else {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(units * NCTA));
+    cfg.blockDim = dim3(TC_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = c->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = NCTA; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    TM_CUDA(cudaLaunchKernelEx(&cfg, k_gemm_tc<EPI, ACTK, NCTA>, P, rowmeta_dev));
+  }
   c->launches++;
   TM_CUDA(cudaGetLastError());
   return TM_OK;
 }
 
-template <int EPI>
+template <int EPI, int NCTA>
 static int launch_tc_act(tm_ctx* c, const TcParams& P, const int* rowmeta_dev, int bound) {
-  if (EPI == TM_EPI_NONE) return launch_tc<EPI, 0>(c, P, rowmeta_dev, bound);
-  if (P.act_kind == TM_ACT_SIGMOID_WITH_PARAM) return launch_tc<EPI, TM_ACT_SIGMOID_WITH_PARAM>(c, P, rowmeta_dev, bound);
-  return launch_tc<EPI, -1>(c, P, rowmeta_dev, bound);
+  if (EPI == TM_EPI_NONE) return launch_tc<EPI, 0, NCTA>(c, P, rowmeta_dev, bound);
+  if (P.act_kind == TM_ACT_SIGMOID_WITH_PARAM) return launch_tc<EPI, TM_ACT_SIGMOID_WITH_PARAM, NCTA>(c, P, rowmeta_dev, bound);
+  return launch_tc<EPI, -1, NCTA>(c, P, rowmeta_dev, bound);
+}
+
+template <int NCTA>
+static int launch_tc_epi(tm_ctx* c, const TcParams& P, const int* rowmeta_dev, int bound, int epilogue) {
+  if (epilogue == TM_EPI_ACT) return launch_tc_act<TM_EPI_ACT, NCTA>(c, P, rowmeta_dev, bound);
+  if (epilogue == TM_EPI_ACT_OUT) return launch_tc_act<TM_EPI_ACT_OUT, NCTA>(c, P, rowmeta_dev, bound);
+  if (epilogue == TM_EPI_DACT) return launch_tc_act<TM_EPI_DACT, NCTA>(c, P, rowmeta_dev, bound);
+  return launch_tc_act<TM_EPI_NONE, NCTA>(c, P, rowmeta_dev, bound);
 }
 
 // In this mode every GemmGroup pointer except bias (and C for TM_EPI_NONE) addresses fp16 planes.
 int tm_gemm_tc_launch(tm_ctx* c, const GemmGroup* groups, int ngroups, const int* rowmeta_dev, int max_row_tiles, int epilogue) {
   int rc;
-  if (c->gemm_mode != TM_GEMM_TC_SPLIT) { tm_set_error("gemm mode %d is not implemented (use 0 = fp32 or 1 = tcgen05 split fp16)", c->gemm_mode); return TM_ESTATE; }
+  if (c->gemm_mode != TM_GEMM_TC_SPLIT && c->gemm_mode != TM_GEMM_TC_SPLIT_PAIR) { tm_set_error("gemm mode %d is not implemented", c->gemm_mode); return TM_ESTATE; }
+  const int ncta = (c->gemm_mode == TM_GEMM_TC_SPLIT_PAIR) ? 2 : 1;
   if ((rc = get_encode())) return rc;
   if (ngroups > TC_MAX_GROUPS) { tm_set_error("too many GEMM groups"); return TM_EINVAL; }
   static TcParams P;   // large; filled per launch (calls on one ctx are serialised by contract)
   P.ngroups = ngroups; P.act_kind = c->hp.activation; P.act_alpha = c->hp.act_alpha;
+  P.prof = nullptr;
+#ifdef TC_PROFILE
+  {
+    static unsigned long long* dprof = nullptr;
+    static int call = 0;
+    if (!dprof) cudaMalloc(&dprof, 64 * 8 * 16);
+    P.prof = dprof + 8 * (call % 6);        // one slot set per GEMM launch of a step (3 forward + 3 backward)
+    if (call % 6 == 0 && call > 0) {
+      unsigned long long h[56];
+      cudaMemcpy(h, dprof, sizeof(h), cudaMemcpyDeviceToHost);
+      if (getenv("TC_PROFILE_PRINT"))
+        for (int k = 0; k < 6; k++)
+          fprintf(stderr, "gemm %d: tiles(warp2) %llu  mma wait tempty %.0f full %.0f | epi wait tfull %.0f drain %.0f output %.0f  (cycles per tile)\n", k, h[8 * k + 5],
+                  (double)h[8 * k + 0] / h[8 * k + 5], (double)h[8 * k + 1] / h[8 * k + 5], (double)h[8 * k + 2] / h[8 * k + 5], (double)h[8 * k + 3] / h[8 * k + 5],
+                  (double)h[8 * k + 4] / h[8 * k + 5]);
+      cudaMemset(dprof, 0, 64 * 8 * 16);
+    }
+    call++;
+  }
+#endif
   int64_t tiles = 0;
   for (int i = 0; i < ngroups; i++) {
     const GemmGroup& g = groups[i];
@@ -585,18 +726,15 @@ int tm_gemm_tc_launch(tm_ctx* c, const GemmGroup* groups, int ngroups, const int
     TcGroup& T = P.g[i];
     if ((rc = make_map(&T.mapA_hi, g.A, g.rows_alloc, g.K, g.lda, TC_BM))) return rc;
     if ((rc = make_map(&T.mapA_lo, g.A2, g.rows_alloc, g.K, g.lda, TC_BM))) return rc;
-    if ((rc = make_map(&T.mapB_hi, g.B, g.N, g.K, g.ldb, TC_BN))) return rc;
-    if ((rc = make_map(&T.mapB_lo, g.B2, g.N, g.K, g.ldb, TC_BN))) return rc;
+    if ((rc = make_map(&T.mapB_hi, g.B, g.N, g.K, g.ldb, TC_BN / ncta))) return rc;   // a CTA of a pair stages half of the B rows
+    if ((rc = make_map(&T.mapB_lo, g.B2, g.N, g.K, g.ldb, TC_BN / ncta))) return rc;
     T.bias = g.bias; T.Hmul_hi = (const __half*)g.Hmul; T.Hmul_lo = (const __half*)g.Hmul2;
     T.C_hi = (__half*)g.C; T.C_lo = (__half*)g.C2; T.C32 = (float*)g.C;
     T.wout = g.wout; T.ypart = g.ypart; T.ystride = g.rows_alloc;
     if (epilogue == TM_EPI_ACT_OUT && (!g.wout || !g.ypart)) { tm_set_error("tc gemm: output-layer epilogue without w_out / ypart"); return TM_EINVAL; }
     T.ldc = g.ldc; T.K = g.K; T.N = g.N; T.ele = g.ele;
-    tiles += (int64_t)max_row_tiles * (g.N / TC_BN);
+    tiles += (int64_t)((max_row_tiles + ncta - 1) / ncta) * (g.N / TC_BN);
   }
   int bound = tiles > 100000 ? 100000 : (int)tiles;
-  if (epilogue == TM_EPI_ACT) return launch_tc_act<TM_EPI_ACT>(c, P, rowmeta_dev, bound);
-  if (epilogue == TM_EPI_ACT_OUT) return launch_tc_act<TM_EPI_ACT_OUT>(c, P, rowmeta_dev, bound);
-  if (epilogue == TM_EPI_DACT) return launch_tc_act<TM_EPI_DACT>(c, P, rowmeta_dev, bound);
-  return launch_tc_act<TM_EPI_NONE>(c, P, rowmeta_dev, bound);
+  return ncta == 2 ? launch_tc_epi<2>(c, P, rowmeta_dev, bound, epilogue) : launch_tc_epi<1>(c, P, rowmeta_dev, bound, epilogue);
 }
