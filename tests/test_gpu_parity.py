@@ -287,3 +287,25 @@ def test_graph_replay_equals_eager_device_call():
     assert np.abs(g_graph - g.cpu().numpy()).max() <= 1e-6 * np.abs(g_graph).max()
     r = eng.evaluate_lattice(X2, Z, lat, 1)
     _check_energy(e_graph[0:1], r["Etotal"], "Etotal")
+
+
+def test_molecule_batch_members_equal_single_evaluations():
+    """Config C2 shape (many geometries of one C,H,N,O molecule in one padded set): a size-independent property at a size
+    the oracle cannot reach -- a molecule evaluated inside the batch equals the same molecule evaluated alone, and the
+    batch is invariant under a permutation of its members."""
+    from tensormol_b200.SystemBuilders import perturbed_molecule_batch
+    g = load_golden("morphine")
+    eng, _, _ = _engine(g["eles"], [128, 128, 128], 4)
+    nmol = 3000
+    Zs, xyzs = perturbed_molecule_batch(g["Z"], g["xyz"], nmol, sigma=0.05, seed=3)
+    nat = np.full(nmol, Zs.shape[1], np.int64)
+    r = eng.evaluate(xyzs, Zs, nat)
+    assert np.all(np.isfinite(r["Etotal"])) and np.all(np.isfinite(r["gradient"]))
+    for m in (0, 1234, nmol - 1):
+        r1 = eng.evaluate(xyzs[m:m + 1], Zs[m:m + 1], nat[m:m + 1])
+        assert abs(r1["Etotal"][0] - r["Etotal"][m]) <= 2e-6 * abs(r["Etotal"][m])
+        assert np.abs(r1["gradient"][0] - r["gradient"][m]).max() <= 1e-6
+    perm = np.random.default_rng(0).permutation(nmol)
+    rp = eng.evaluate(xyzs[perm], Zs[perm], nat[perm])
+    assert np.abs(rp["Etotal"] - r["Etotal"][perm]).max() <= 2e-6 * np.abs(r["Etotal"]).max()
+    assert np.abs(rp["gradient"] - r["gradient"][perm]).max() <= 1e-6
