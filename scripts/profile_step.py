@@ -1,4 +1,6 @@
 """One 24k-atom periodic step in a given GEMM mode, for ncu launch lists / captures."""
+import os
+os.environ.setdefault("TM_NO_GRAPH", "1")   # per-stage timings need the kernel-by-kernel path
 import sys
 import numpy as np
 sys.path.insert(0, '.')

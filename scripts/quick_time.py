@@ -1,4 +1,6 @@
 """Stage timings of the 24k-atom step (dev helper)."""
+import os
+os.environ.setdefault("TM_NO_GRAPH", "1")   # per-stage timings need the kernel-by-kernel path
 import sys
 sys.path.insert(0, '.')
 from bench import hot_params, HIDDEN

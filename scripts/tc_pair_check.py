@@ -1,4 +1,6 @@
 """Dev check: CTA-pair GEMM mode (2) against modes 0 and 1."""
+import os
+os.environ.setdefault("TM_NO_GRAPH", "1")   # per-stage timings need the kernel-by-kernel path
 import sys, time
 import numpy as np
 sys.path.insert(0, '.'); sys.path.insert(0, 'tests')

@@ -1,6 +1,7 @@
 // C-ABI of libtmolb200.so (see include/tmolb200.h): context, weights, evaluation pipelines and the
 // MolEmb / Neighbors.py compatible neighbour-table entry points.
 #include "tm_internal.h"
+#include <cstdlib>
 #include <cuda_fp16.h>
 #include <algorithm>
 #include <cmath>
@@ -35,6 +36,7 @@ int tm_buf(tm_ctx* c, DevBuf& b, size_t bytes) {
     b.p = nullptr; b.cap = 0;
   }
   size_t want = bytes + bytes / 8;
+  c->alloc_gen++;
   TM_CUDA(cudaMalloc(&b.p, want));
   TM_CUDA(cudaMemsetAsync(b.p, 0, want, c->stream));
   b.cap = want;
@@ -45,6 +47,7 @@ int tm_host_stage(tm_ctx* c, size_t bytes) {
   if (c->h_cap >= bytes) return TM_OK;
   if (c->h_stage) { TM_CUDA(cudaStreamSynchronize(c->stream)); TM_CUDA(cudaFreeHost(c->h_stage)); c->h_stage = nullptr; c->h_cap = 0; }
   size_t want = bytes + bytes / 4 + 4096;
+  c->alloc_gen++;
   TM_CUDA(cudaMallocHost(&c->h_stage, want));
   c->h_cap = want;
   return TM_OK;
@@ -173,6 +176,7 @@ static int build_dev_params(tm_ctx* c) {
 extern "C" int tm_set_params(tm_ctx* c, const tm_params* params) {
   if (!c || !params) { tm_set_error("null argument"); return TM_EINVAL; }
   tm_params old = c->params;
+  c->cfg_gen++;
   c->params = *params;
   int rc = build_dev_params(c);
   if (rc) { c->params = old; build_dev_params(c); return rc; }
@@ -203,6 +207,7 @@ extern "C" tm_ctx* tm_create(int device, const tm_model_desc* desc, const tm_par
   if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) { tm_set_error("stream create failed"); delete c; return nullptr; }
   c->stream = c->own_stream;
   for (int i = 0; i < 12; i++) cudaEventCreate(&c->ev[i]);
+  c->graphs_on = getenv("TM_NO_GRAPH") ? 0 : 1;
   c->ev_ok = true;
   memset(&c->last, 0, sizeof(c->last));
   return c;
@@ -214,6 +219,7 @@ extern "C" void tm_destroy(tm_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
+  if (c->lg.exec) cudaGraphExecDestroy(c->lg.exec);
   DevBuf* all[] = {&c->b_pos, &c->b_Z, &c->b_cellid, &c->b_rank, &c->b_count, &c->b_cstart, &c->b_sorted, &c->b_satom, &c->b_scan_tmp,
                    &c->b_rowslot, &c->b_rowsidx, &c->b_rowofslot, &c->b_blkcnt, &c->b_rowmeta, &c->b_nbcnt, &c->b_nboff, &c->b_nbr, &c->b_G, &c->b_Gs, &c->b_ypart,
                    &c->b_delta0, &c->b_delta1, &c->b_dG[0], &c->b_dG[1], &c->b_y[0], &c->b_y[1], &c->b_q, &c->b_qs, &c->b_dedq, &c->b_u, &c->b_F,
@@ -242,11 +248,13 @@ extern "C" void tm_destroy(tm_ctx* c) {
 extern "C" int tm_set_stream(tm_ctx* c, void* s) {
   if (!c) return TM_EINVAL;
   c->stream = s ? (cudaStream_t)s : c->own_stream;
+  c->cfg_gen++;
   return TM_OK;
 }
 extern "C" int tm_set_gemm_mode(tm_ctx* c, int mode) {
   if (!c || mode < 0 || mode > 2) { tm_set_error("bad gemm mode %d (0 = fp32, 1 = tcgen05 split fp16, 2 = same on CTA pairs)", mode); return TM_EINVAL; }
   c->gemm_mode = mode;
+  c->cfg_gen++;
   return TM_OK;
 }
 extern "C" int tm_get_gemm_mode(tm_ctx* c) { return c ? c->gemm_mode : TM_EINVAL; }
@@ -268,6 +276,7 @@ extern "C" int tm_set_weights(tm_ctx* c, int net, int ele_index, int layer, cons
     return TM_EINVAL;
   }
   TM_CUDA(cudaSetDevice(c->device));
+  c->cfg_gen++;
   int nh = c->desc.n_hidden;
   Net& N = c->nets[net][ele_index];
   if (layer == nh) {
@@ -542,6 +551,8 @@ static int validate_Z(tm_ctx* c, const int32_t* Z, int64_t n) {
   return TM_OK;
 }
 
+static int copy_out(tm_ctx* c, int flags, const OutLayout& o, tm_outputs* out, int64_t charge_tile_to, size_t bytes, size_t dbytes);
+
 // copy the packed device outputs to the user's arrays
 static int deliver(tm_ctx* c, const SysView& s, int flags, const OutLayout& o, tm_outputs* out, int64_t charge_tile_to) {
   int rc;
@@ -557,6 +568,12 @@ static int deliver(tm_ctx* c, const SysView& s, int flags, const OutLayout& o, t
   }
   cudaEventRecord(c->ev[8], c->stream);
   if ((rc = check_flags(c))) return rc;   // synchronises
+  if ((rc = copy_out(c, flags, o, out, charge_tile_to, bytes, dbytes))) return rc;
+  return finish_timings(c, s);
+}
+
+// host side of a delivery: the packed outputs are in the pinned staging buffer
+static int copy_out(tm_ctx* c, int flags, const OutLayout& o, tm_outputs* out, int64_t charge_tile_to, size_t bytes, size_t dbytes) {
   const double* h = (const double*)c->h_stage;
   int64_t nm = o.nmol;
   for (int64_t m = 0; m < nm; m++)
@@ -581,7 +598,7 @@ static int deliver(tm_ctx* c, const SysView& s, int flags, const OutLayout& o, t
   }
   if (out->gradient && (flags & TM_F_FORCE)) memcpy(out->gradient, h + o.off_grad, 3 * o.nq * 8);
   if (dbytes) memcpy(out->descriptors, (const char*)c->h_stage + bytes, dbytes);
-  return finish_timings(c, s);
+  return TM_OK;
 }
 
 static int upload_inv_n(tm_ctx* c, const double* inv_n, int64_t nmol) {
@@ -627,6 +644,7 @@ extern "C" int tm_eval(tm_ctx* c, const double* xyzs, const int32_t* Zs, int64_t
   }
   if ((rc = tm_buf(c, c->b_pos, bx))) return rc;
   if ((rc = tm_buf(c, c->b_Z, bz))) return rc;
+  c->timings_final = false;
   cudaEventRecord(c->ev[0], c->stream);
   TM_CUDA(cudaMemcpyAsync(c->b_pos.p, hs, bx, cudaMemcpyHostToDevice, c->stream));
   TM_CUDA(cudaMemcpyAsync(c->b_Z.p, hz, bz, cudaMemcpyHostToDevice, c->stream));
@@ -656,6 +674,7 @@ extern "C" int tm_eval_images(tm_ctx* c, const double* xyz_tess, const int32_t* 
   memcpy(hs + bx + bz, &inv, 8);
   if ((rc = tm_buf(c, c->b_pos, bx))) return rc;
   if ((rc = tm_buf(c, c->b_Z, bz))) return rc;
+  c->timings_final = false;
   cudaEventRecord(c->ev[0], c->stream);
   TM_CUDA(cudaMemcpyAsync(c->b_pos.p, hs, bx, cudaMemcpyHostToDevice, c->stream));
   TM_CUDA(cudaMemcpyAsync(c->b_Z.p, hs + bx, bz, cudaMemcpyHostToDevice, c->stream));
@@ -752,6 +771,7 @@ static int eval_lattice_impl(tm_ctx* c, const double* xyz, const int32_t* Z, int
   memcpy(hs, xyz, bx);
   memcpy(hs + bx, Z, bz);
   if ((rc = tm_buf(c, c->b_acc, bx + bz + 64))) return rc;
+  c->timings_final = false;
   cudaEventRecord(c->ev[0], c->stream);
   TM_CUDA(cudaMemcpyAsync(c->b_acc.p, hs, bx + bz, cudaMemcpyHostToDevice, c->stream));
   SysView s;
@@ -764,6 +784,78 @@ static int eval_lattice_impl(tm_ctx* c, const double* xyz, const int32_t* Z, int
   return rc;
 }
 
+// The same evaluation replayed from a CUDA graph (H2D copy of the staged input, tessellation, every kernel of the step,
+// D2H copy of the packed outputs and of the flag word).  Captured on the third consecutive call with the same shape;
+// any (re)allocation, parameter / weight / stream change, or a different lattice or atom count falls back to the eager
+// path and restarts the count.  Returns TM_OK, an error, or +1 = "use the eager path" (nothing was delivered).
+static int lattice_graph_call(tm_ctx* c, const double* xyz, const int32_t* Z, int64_t nreal, const double* lattice, int ntess, int flags,
+                              tm_outputs* out) {
+  tm_ctx::LatGraph& G = c->lg;
+  bool same = G.nreal == nreal && G.ntess == ntess && G.flags == flags && G.cfg_gen == c->cfg_gen && G.alloc_gen == c->alloc_gen &&
+              memcmp(G.lat, lattice, 72) == 0;
+  if (!same) {
+    if (G.exec) { cudaGraphExecDestroy(G.exec); G.exec = nullptr; }
+    G.nreal = nreal; G.ntess = ntess; G.flags = flags; G.cfg_gen = c->cfg_gen; G.alloc_gen = c->alloc_gen;
+    memcpy(G.lat, lattice, 72);
+    G.streak = 1; G.failed = false;
+    return 1;
+  }
+  if (G.failed) return 1;
+  if (!G.exec && ++G.streak < 3) return 1;
+  int rc;
+  OutLayout o = out_layout(1, nreal);
+  size_t bx = (size_t)nreal * 24, bz = (size_t)nreal * 4, bytes = (size_t)o.total * 8;
+  if (c->h_cap < std::max(bx + bz, bytes) + 64 || c->b_acc.cap < bx + bz + 64) return 1;   // the eager calls size these
+  char* hs = (char*)c->h_stage;
+  memcpy(hs, xyz, bx);
+  memcpy(hs + bx, Z, bz);
+  if (!G.exec) {
+    cudaGraph_t graph = nullptr;
+    if (cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); G.failed = true; return 1; }
+    c->launches = 0;
+    SysView s;
+    rc = (cudaMemcpyAsync(c->b_acc.p, hs, bx + bz, cudaMemcpyHostToDevice, c->stream) == cudaSuccess) ? TM_OK : TM_ECUDA;
+    if (!rc) rc = prepare_lattice(c, (const double*)c->b_acc.p, (const int32_t*)((char*)c->b_acc.p + bx), nreal, lattice, ntess, &s);
+    if (!rc) { host_grid(c, &s, lattice, ntess); rc = run_all(c, s, flags, o); }
+    if (!rc && cudaMemcpyAsync(hs, c->b_out.p, bytes, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) rc = TM_ECUDA;
+    if (!rc && cudaMemcpyAsync(hs + bytes, c->b_flags.p, 8, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) rc = TM_ECUDA;
+    cudaError_t ce = cudaStreamEndCapture(c->stream, &graph);
+    if (rc || ce != cudaSuccess || !graph || c->alloc_gen != G.alloc_gen) {
+      if (graph) cudaGraphDestroy(graph);
+      cudaGetLastError();
+      G.failed = true;
+      G.alloc_gen = c->alloc_gen;
+      return 1;
+    }
+    ce = cudaGraphInstantiate(&G.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ce != cudaSuccess) { cudaGetLastError(); G.exec = nullptr; G.failed = true; return 1; }
+    G.launches = c->launches;
+  }
+  cudaEventRecord(c->ev[9], c->stream);
+  TM_CUDA(cudaGraphLaunch(G.exec, c->stream));
+  cudaEventRecord(c->ev[10], c->stream);
+  TM_CUDA(cudaStreamSynchronize(c->stream));
+  int32_t f0 = *(const int32_t*)(hs + bytes);
+  c->last_flags = f0;
+  if (f0 & 8) return 1;   // unwrapped input: the eager path redoes it with the bounding-box grid
+  if (f0 & 2) { tm_set_error("more than %d radial neighbours of one centre", TM_NB_STRIDE); return TM_ECAP; }
+  if (f0 & 4) { tm_set_error("more than %d neighbours inside the angular cutoff of one centre", TM_ANG_CAP); return TM_ECAP; }
+  if ((rc = copy_out(c, flags, o, out, nreal, bytes, 0))) return rc;
+  tm_timings& t = c->last;
+  memset(&t, 0, sizeof(t));
+  c->timings_final = true;
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, c->ev[9], c->ev[10]);
+  t.total = ms;
+  t.n_slots = tess_count(nreal, ntess);
+  t.n_centres = nreal;
+  t.launches = G.launches;
+  c->launches = G.launches;
+  c->cur_nslots = 0;
+  return TM_OK;
+}
+
 extern "C" int tm_eval_lattice(tm_ctx* c, const double* xyz, const int32_t* Z, int64_t nreal, const double* lattice, int ntess, int flags,
                                tm_outputs* out) {
   if (!c || !xyz || !Z || !lattice || !out || nreal < 1) { tm_set_error("tm_eval_lattice: bad argument"); return TM_EINVAL; }
@@ -772,7 +864,13 @@ extern "C" int tm_eval_lattice(tm_ctx* c, const double* xyz, const int32_t* Z, i
   if ((rc = check_weights(c))) return rc;
   if ((rc = validate_Z(c, Z, nreal))) return rc;
   c->last_flags = 0;
+  if (c->graphs_on && !(flags & TM_F_DESCRIPTORS)) {
+    rc = lattice_graph_call(c, xyz, Z, nreal, lattice, ntess, flags, out);
+    if (rc <= 0) return rc;                     // delivered from the graph, or failed
+    if (c->last_flags & 8) return eval_lattice_impl(c, xyz, Z, nreal, lattice, ntess, flags, out, false);
+  }
   rc = eval_lattice_impl(c, xyz, Z, nreal, lattice, ntess, flags, out, true);
+  c->lg.alloc_gen = c->alloc_gen;              // allocations made by this eager call are part of the key
   // input not wrapped into the cell: the host-laid grid does not cover it, redo with the bounding-box pass
   if (rc == TM_EINVAL && (c->last_flags & 8)) rc = eval_lattice_impl(c, xyz, Z, nreal, lattice, ntess, flags, out, false);
   return rc;
@@ -785,6 +883,7 @@ extern "C" int tm_eval_lattice_dev(tm_ctx* c, const double* xyz_dev, const int32
   TM_CUDA(cudaSetDevice(c->device));
   if ((rc = check_weights(c))) return rc;
   c->launches = 0;
+  c->timings_final = false;
   cudaEventRecord(c->ev[0], c->stream);
   SysView s;
   if ((rc = prepare_lattice(c, xyz_dev, Z_dev, nreal, lattice, ntess, &s))) return rc;
@@ -804,12 +903,14 @@ extern "C" int tm_get_timings(tm_ctx* c, tm_timings* t) {
   if (!c || !t) return TM_EINVAL;
   TM_CUDA(cudaSetDevice(c->device));
   TM_CUDA(cudaStreamSynchronize(c->stream));
-  SysView s;
-  memset(&s, 0, sizeof(s));
-  s.nslots = c->cur_nslots ? c->cur_nslots : c->last.n_slots;
-  int64_t nc = c->last.n_centres;
-  finish_timings(c, s);
-  c->last.n_centres = nc;
+  if (!c->timings_final) {      // (a graph replay has no per-stage events: its totals were stored by the call itself)
+    SysView s;
+    memset(&s, 0, sizeof(s));
+    s.nslots = c->cur_nslots ? c->cur_nslots : c->last.n_slots;
+    int64_t nc = c->last.n_centres;
+    finish_timings(c, s);
+    c->last.n_centres = nc;
+  }
   *t = c->last;
   return TM_OK;
 }
@@ -841,6 +942,7 @@ extern "C" int tm_slab_phase_a(tm_ctx* c, const double* xyz_dev, const int32_t* 
   TM_CUDA(cudaSetDevice(c->device));
   if ((rc = check_weights(c))) return rc;
   c->launches = 0;
+  c->timings_final = false;
   cudaEventRecord(c->ev[0], c->stream);
   SysView s;
   if ((rc = prepare_lattice(c, xyz_dev, Z_dev, nreal, lattice, ntess, &s))) return rc;

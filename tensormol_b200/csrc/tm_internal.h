@@ -151,6 +151,21 @@ struct tm_ctx {
   tm_timings last;
   int launches = 0;
 
+  // tm_eval_lattice replays its device work from a CUDA graph once the same call shape (atom count, lattice, flags,
+  // configuration, buffer allocations) has been seen twice in a row; see lattice_graph_call in tm_api.cu
+  uint64_t alloc_gen = 0;        // bumped by every (re)allocation of a workspace buffer
+  uint64_t cfg_gen = 0;          // bumped by set_weights / set_params / set_gemm_mode / set_stream
+  struct LatGraph {
+    cudaGraphExec_t exec = nullptr;
+    int64_t nreal = -1;
+    int ntess = 0, flags = 0, streak = 0, launches = 0;
+    double lat[9];
+    uint64_t alloc_gen = 0, cfg_gen = 0;
+    bool failed = false;         // capture failed for this key: stay eager
+  } lg;
+  int graphs_on = 1;             // TM_NO_GRAPH=1 in the environment disables the replay
+  bool timings_final = false;    // c->last already holds the timings of the last call (graph replay)
+
   // slab state
   int slab_rank = 0, slab_world = 1;
   int64_t cur_nslots = 0, cur_nreal = 0, cur_nmol = 0, cur_maxnatom = 0, cur_ncent = 0, cur_nrows = 0;

@@ -309,3 +309,32 @@ def test_molecule_batch_members_equal_single_evaluations():
     rp = eng.evaluate(xyzs[perm], Zs[perm], nat[perm])
     assert np.abs(rp["Etotal"] - r["Etotal"][perm]).max() <= 2e-6 * np.abs(r["Etotal"]).max()
     assert np.abs(rp["gradient"] - r["gradient"][perm]).max() <= 1e-6
+
+
+def test_host_call_graph_replay_equals_eager(monkeypatch):
+    """tm_eval_lattice replays its device work from a CUDA graph from the third same-shaped call on: the replayed
+    results on new positions equal those of a context that never uses the graph (TM_NO_GRAPH=1), and a change of the
+    call shape (other lattice) drops back to the eager path."""
+    from oracle import oracle_np as onp
+    Z, X, lat = water_box(4)
+    X = onp.modulo_lattice(lat, X)
+    eng_g, _, _ = _engine([1, 8], [128, 128], 3)
+    monkeypatch.setenv("TM_NO_GRAPH", "1")
+    eng_e, _, _ = _engine([1, 8], [128, 128], 3)
+    monkeypatch.delenv("TM_NO_GRAPH")
+    rs = np.random.RandomState(9)
+    for it in range(6):
+        Xi = onp.modulo_lattice(lat, X + 0.03 * rs.randn(*X.shape))
+        rg = eng_g.evaluate_lattice(Xi, Z, lat, 1)
+        re = eng_e.evaluate_lattice(Xi, Z, lat, 1)
+        for k in ("Etotal", "Ebp", "Ecc", "Evdw"):
+            assert abs(rg[k][0] - re[k][0]) <= 1e-7 * abs(re[k][0]) + 1e-10, (it, k)
+        assert np.abs(rg["gradient"] - re["gradient"]).max() <= 1e-6 * np.abs(re["gradient"]).max()
+        assert np.abs(rg["charge"] - re["charge"]).max() <= 1e-6
+    assert eng_g.timings()["launches"] > 20 and eng_g.timings()["nlist"] == 0.0     # last call came from the graph
+    lat2 = lat * 1.01
+    X2 = onp.modulo_lattice(lat2, X)
+    rg = eng_g.evaluate_lattice(X2, Z, lat2, 1)
+    re = eng_e.evaluate_lattice(X2, Z, lat2, 1)
+    assert abs(rg["Etotal"][0] - re["Etotal"][0]) <= 1e-7 * abs(re["Etotal"][0])
+    assert eng_g.timings()["nlist"] > 0.0                                            # eager again
