@@ -8,7 +8,9 @@ Each fixture holds (a) a geometry taken from the reference's datasets/ directory
 the REFERENCE'S OWN native code: neighbour lists (MolEmb.Make_NListNaive, C_API/MolEmb.cpp:1180-1247),
 descriptors (MolEmb.Make_ANI1_Sym, :1913-1988) and, for the small cases, descriptor Jacobians
 (MolEmb.Make_ANI1_Sym_deri, :1844-1911); (c) outputs of the float64 restatement oracle/oracle_graph.py
-with seeded random-init weights (tensormol_b200.engine.random_weights(seed)).
+with seeded random-init weights (tensormol_b200.engine.random_weights(seed)); plus ref_python_pins.npz = outputs of the
+reference's own Python for the table builders, the lattice tessellation, the DSF constants and PhysicalData
+(oracle/ref_py.py).
 """
 from __future__ import annotations
 
@@ -126,8 +128,60 @@ def periodic_case(name, Z, X, L, hidden, seed):
     print(name, "ntess", ntess, "E", res["Etotal"], "n_ee", res["n_ee"], "sym pin err", np.abs(out["ref_sym"] - res["descriptors"][0]).max())
 
 
+def reference_python_pins():
+    """Outputs of the reference's OWN Python (Neighbors.py, Periodic.py Lattice, Util.py DSF, PhysicalData.py) executed
+    in place by oracle/ref_py.py on top of the reference's own MolEmb build -> tests/golden/ref_python_pins.npz."""
+    import hashlib
+    from oracle import ref_py
+    out = {}
+    for k, v in ref_py.constants().items():
+        out["const_" + k] = np.asarray(v)
+    ns = ref_py.namespace()
+    B = float(ns["BOHRPERA"])
+    dsf_in = np.array([[4.6 * B, 15.0 * B, 0.18 / B], [4.4 * B, 15.0 * B, 0.18 / B], [5.0 * B, 12.0 * B, 0.2 / B], [3.0, 25.0, 0.1]])
+    out["dsf_in"] = dsf_in
+    out["dsf"] = np.array([ns["DSF"](*r) for r in dsf_in])
+    out["dsf_gradient"] = np.array([ns["DSF_Gradient"](*r) for r in dsf_in])
+    for name, fn in (("h2o_cluster", "H2O_cluster.xyz"), ("morphine", "morphine.xyz")):
+        Z, X, _ = read_xyz_frames(os.path.join(REF, "datasets", fn))[0]
+        rad, ang, mil_jk, jk_max = ref_py.tables_aperiodic(X, Z, 4.6, 3.1)
+        out[name + "_rad"] = rad.astype(np.int32)
+        out[name + "_ang"] = ang.astype(np.int32)
+        out[name + "_mil_jk"] = mil_jk.astype(np.int32)
+        out[name + "_jk_max"] = np.int64(jk_max)
+    Z, X, _ = read_xyz_frames(os.path.join(REF, "datasets", "water_tiny.xyz"))[0]
+    lat = 9.3215 * np.eye(3)
+    L = ref_py.lattice(lat)
+    out["lat"] = lat
+    out["lat_min_diameter"] = np.float64(L.latticeMinDiameter)
+    Xu = X + 3.0 * np.random.RandomState(0).randn(*X.shape)          # far outside the cell
+    out["modulo_in"] = Xu
+    out["modulo_out"] = L.ModuloLattice(Xu)
+    Xw = L.ModuloLattice(X)
+    zt, xt = L.TessLattice(Z.astype(np.uint8), Xw, 15.0)
+    out["tess_in"] = Xw
+    out["tess_Z"] = np.asarray(zt, np.int32)
+    out["tess_xyz_sha256"] = np.frombuffer(hashlib.sha256(np.ascontiguousarray(xt, np.float64).tobytes()).digest(), np.uint8)
+    out["tess_xyz_head"] = np.asarray(xt)[: 3 * len(Z)]
+    out["tess_n"] = np.int64(len(zt))
+    rad, ang, mil_j, mil_jk = ref_py.tables_periodic(xt, zt, len(Z), 4.6, 3.1, [1, 8])
+    out["periodic_rad"] = rad.astype(np.int32)
+    out["periodic_ang"] = ang.astype(np.int32)
+    out["periodic_mil_j"] = mil_j.astype(np.int32)
+    out["periodic_mil_jk"] = mil_jk.astype(np.int32)
+    NLEE = ns["NeighborListSetWithImages"](np.asarray(xt)[None].copy(), np.array([len(zt)]), np.array([len(Z)]), False, True,
+                                           np.asarray(zt, np.int32)[None].copy())
+    ree = np.asarray(NLEE.buildPairsWithBothEleIndex(15.0, np.array([[1], [8]]))).astype(np.int32)
+    ree = ree[np.lexsort(ree.T[::-1])]                                # the reference's order is the sweep order: pin the SET
+    out["periodic_ee_n"] = np.int64(len(ree))
+    out["periodic_ee_sorted_sha256"] = np.frombuffer(hashlib.sha256(np.ascontiguousarray(ree).tobytes()).digest(), np.uint8)
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "ref_python_pins.npz"), **out)
+    print("ref_python_pins:", {k: np.asarray(v).shape for k, v in out.items() if np.asarray(v).size > 8})
+
+
 def main():
     os.makedirs(os.path.join(ROOT, "tests", "golden"), exist_ok=True)
+    reference_python_pins()
     Z, X, _ = read_xyz_frames(os.path.join(REF, "datasets", "H2O_cluster.xyz"))[0]
     aperiodic_case("h2o_cluster", Z, X, [64, 48, 32], 0, True)
     Z, X, _ = read_xyz_frames(os.path.join(REF, "datasets", "morphine.xyz"))[0]

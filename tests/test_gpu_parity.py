@@ -117,10 +117,15 @@ def test_pairs_triples_ele_tables(name):
     # first molecule against the golden oracle tables
     assert np.array_equal(rad[rad[:, 0] == 0], g["oracle_rad_p_ele"])
     assert np.array_equal(ang[ang[:, 0] == 0], g["oracle_ang_t_elep"])
+    # ... and against the tables the reference's own Python builds for it (Neighbors.py executed in place, ref_python_pins)
+    pins = load_golden("ref_python_pins")
+    assert np.array_equal(rad[rad[:, 0] == 0], pins[name + "_rad"])
+    assert np.array_equal(ang[ang[:, 0] == 0], pins[name + "_ang"])
+    assert np.array_equal(mil_jk[mil_jk[:, 0] == 0], pins[name + "_mil_jk"])
 
 
 # ---------------------------------------------------------------------------------------- fused evaluation
-GEMM_MODES = [0, 1]    # 0 = fp32 FFMA tiles, 1 = tcgen05 3xTF32 (library default)
+GEMM_MODES = [0, 1]    # 0 = fp32 FFMA tiles, 1 = tcgen05 split-fp16 (library default)
 
 
 @pytest.mark.parametrize("mode", GEMM_MODES)

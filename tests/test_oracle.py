@@ -201,3 +201,74 @@ def test_tessellation_order_and_modulo():
     # first image block is (i,j,k) = (-1,-1,-1)
     assert np.allclose(Xt[3:6], w - lat[0] - lat[1] - lat[2])
     assert np.array_equal(Zt[3:6], [1, 1, 8])
+
+
+# ---- pins produced by the reference's OWN Python (oracle/ref_py.py executes Neighbors.py, Periodic.py Lattice, Util.py DSF
+# and PhysicalData.py where they lie, on the reference's own MolEmb build; oracle/make_golden.py stores the outputs) ----
+def _pins():
+    return load_golden("ref_python_pins")
+
+
+@pytest.mark.parametrize("name", ["h2o_cluster", "morphine"])
+def test_oracle_tables_equal_reference_python_aperiodic(name):
+    """NeighborListSet(...).buildPairsAndTriplesWithEleIndex (Neighbors.py:344-391, TFMolManage.py:1309-1310): bit-exact."""
+    p, g = _pins(), load_golden(name)
+    Z, X = g["Z"].astype(np.int32), g["xyz"]
+    eles = sorted(set(int(z) for z in Z))
+    eles_np = np.asarray(eles).reshape(-1, 1)
+    elep_np = np.asarray([[eles[i], eles[j]] for i in range(len(eles)) for j in range(i, len(eles))])
+    rad, ang, mil_jk, jk_max = onp.build_pairs_and_triples_with_ele_index(X[None], np.array([len(Z)]), np.array([len(Z)]), Z[None], 4.6, 3.1,
+                                                                          eles_np, elep_np)
+    assert np.array_equal(np.asarray(rad), p[name + "_rad"])
+    assert np.array_equal(np.asarray(ang), p[name + "_ang"])
+    assert np.array_equal(np.asarray(mil_jk), p[name + "_mil_jk"])
+    assert int(jk_max) == int(p[name + "_jk_max"])
+
+
+def test_oracle_lattice_and_periodic_tables_equal_reference_python():
+    """Lattice.ModuloLattice / TessLattice (Periodic.py:87-168) and buildPairsAndTriplesWithEleIndexPeriodic /
+    buildPairsWithBothEleIndex (Neighbors.py:393-470): coordinates bit-exact (sha256 of the float64 bytes), tables bit-exact,
+    the 15 A pair list as a set (the reference keeps MolEmb's sweep order)."""
+    import hashlib
+    p, g = _pins(), load_golden("water_tiny_periodic")
+    lat = p["lat"]
+    assert np.array_equal(onp.modulo_lattice(lat, p["modulo_in"]), p["modulo_out"])
+    assert abs(onp.lattice_min_diameter(lat) - float(p["lat_min_diameter"])) < 1e-9
+    Z = g["Z"]
+    zt, xt = onp.tess_lattice(lat, Z.astype(np.uint8), p["tess_in"], 15.0)
+    assert len(zt) == int(p["tess_n"]) and np.array_equal(np.asarray(zt, np.int32), p["tess_Z"])
+    assert np.array_equal(xt[: len(p["tess_xyz_head"])], p["tess_xyz_head"])
+    assert hashlib.sha256(np.ascontiguousarray(xt, np.float64).tobytes()).digest() == p["tess_xyz_sha256"].tobytes()
+    nreal = len(Z)
+    eles_np, elep_np = np.array([[1], [8]]), np.array([[1, 1], [1, 8], [8, 8]])
+    o = onp.build_pairs_and_triples_with_ele_index_periodic(xt[None], np.array([len(zt)]), np.array([nreal]), zt.astype(np.int32)[None], 4.6, 3.1,
+                                                            eles_np, elep_np)
+    for got, key in zip(o, ("periodic_rad", "periodic_ang", "periodic_mil_j", "periodic_mil_jk")):
+        assert np.array_equal(np.asarray(got), p[key]), key
+    ee = np.asarray(onp.build_pairs_with_both_ele_index(xt[None], np.array([len(zt)]), np.array([nreal]), zt.astype(np.int32)[None], 15.0, eles_np,
+                                                        True)).astype(np.int32)
+    ee = ee[np.lexsort(ee.T[::-1])]
+    assert len(ee) == int(p["periodic_ee_n"])
+    assert hashlib.sha256(np.ascontiguousarray(ee).tobytes()).digest() == p["periodic_ee_sorted_sha256"].tobytes()
+
+
+def test_constants_and_dsf_equal_reference_python():
+    """PhysicalData.py tables and Util.py DSF / DSF_Gradient (the ELU shift / slope of the Coulomb kernel) as the host
+    layer and the oracle use them."""
+    from tensormol_b200 import PhysicalData as PD
+    from tensormol_b200.engine import DSF, DSF_Gradient
+    p = _pins()
+    for k in ("BOHRPERA", "JOULEPERHARTREE", "KCALPERHARTREE", "KJPERHARTREE", "IDEALGASR", "AVOCONST", "AUPERDEBYE"):
+        assert getattr(PD, k) == float(p["const_" + k]), k
+    for z, c6, rv in zip(p["const_vdw_Z"], p["const_C6_coff"], p["const_atomic_vdw_radius"]):
+        assert PD.C6_coff[int(z)] == c6 and PD.atomic_vdw_radius[int(z)] == rv
+    mine = np.asarray(PD.ATOMICMASSES, np.float64)      # H..Kr here, the first 100 elements in the reference
+    assert len(mine) >= 36 and np.array_equal(mine, p["const_ATOMICMASSES"][: len(mine)])
+    for (R, Rc, a), v, dv in zip(p["dsf_in"], p["dsf"], p["dsf_gradient"]):
+        assert abs(DSF(R, Rc, a) - v) <= 1e-15 * max(1.0, abs(v))
+        assert abs(DSF_Gradient(R, Rc, a) - dv) <= 1e-15 * max(1.0, abs(dv))
+    P = og.default_params()
+    B = float(p["const_BOHRPERA"])
+    sh, al = og.elu_constants(P) if hasattr(og, "elu_constants") else (None, None)
+    if sh is not None:
+        assert abs(sh - p["dsf"][0]) < 1e-14 and abs(al - p["dsf_gradient"][0]) < 1e-14 and P["Elu_Width"] * B == p["dsf_in"][0][0]
