@@ -175,6 +175,27 @@ def reference_python_pins():
     ree = ree[np.lexsort(ree.T[::-1])]                                # the reference's order is the sweep order: pin the SET
     out["periodic_ee_n"] = np.int64(len(ree))
     out["periodic_ee_sorted_sha256"] = np.frombuffer(hashlib.sha256(np.ascontiguousarray(ree).tobytes()).digest(), np.uint8)
+    # electrostatics: the reference's TensorFlow functions (RawSymFunc.py TFCoulombEluSRDSFLR / TFVdwPolyLR / ...WithEle)
+    # executed on the numpy stand-in oracle/tf_shim.py, for seeded neutral charge vectors
+    P = og.default_params()
+    for name, fn in (("h2o_cluster", "H2O_cluster.xyz"), ("morphine", "morphine.xyz")):
+        Z, X, _ = read_xyz_frames(os.path.join(REF, "datasets", fn))[0]
+        q = 0.3 * np.random.RandomState(3).randn(len(Z))
+        q -= q.mean()
+        ecc, evdw, ree = ref_py.electrostatics_aperiodic(X, Z, q, P)
+        out[name + "_q"] = q
+        out[name + "_Ecc"] = np.float64(ecc)
+        out[name + "_Evdw"] = np.float64(evdw)
+        out[name + "_n_ee"] = np.int64(len(ree))
+    q = 0.3 * np.random.RandomState(4).randn(len(Z0 := read_xyz_frames(os.path.join(REF, "datasets", "water_tiny.xyz"))[0][0]))
+    q -= q.mean()
+    ecc, evdw = ref_py.electrostatics_periodic(xt, zt, len(Z0), q, [1, 8], P)
+    out["periodic_q"] = q
+    out["periodic_Ecc"] = np.float64(ecc)
+    out["periodic_Evdw"] = np.float64(evdw)
+    tfn = ref_py.tf_namespace({"sigmoid_alpha": P["sigmoid_alpha"], "EECutoffOff": P["EECutoffOff"], "Poly_Width": P["Poly_Width"]})
+    out["act_in"] = np.linspace(-2.0, 2.0, 81)
+    out["act_out"] = tfn["sigmoid_with_param"](out["act_in"])
     np.savez_compressed(os.path.join(ROOT, "tests", "golden", "ref_python_pins.npz"), **out)
     print("ref_python_pins:", {k: np.asarray(v).shape for k, v in out.items() if np.asarray(v).size > 8})
 

@@ -43,7 +43,9 @@ def _load_molemb():
 def _defs(path, names=None):
     """Source of the top-level class / function definitions (and plain assignments when names is None) of a reference file,
     imports removed."""
-    with open(os.path.join(REF, path)) as fh:
+    import warnings
+    with open(os.path.join(REF, path)) as fh, warnings.catch_warnings():
+        warnings.simplefilter("ignore")          # invalid escape sequences in the reference's docstrings
         tree = ast.parse(fh.read())
     body = []
     for node in tree.body:
@@ -55,7 +57,10 @@ def _defs(path, names=None):
         elif isinstance(node, (ast.FunctionDef, ast.ClassDef)) and node.name in names:
             body.append(node)
     mod = ast.Module(body=body, type_ignores=[])
-    return compile(ast.fix_missing_locations(mod), os.path.join(REF, path), "exec")
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        return compile(ast.fix_missing_locations(mod), os.path.join(REF, path), "exec")
 
 
 def _tmtiming(_name):
@@ -135,6 +140,75 @@ def tables_periodic(xyz_tess, Z_tess, nreal, Rr, Ra, eles):
     NL = ns["NeighborListSetWithImages"](xyzs, np.array([len(Z_tess)]), np.array([nreal]), True, True, Zs, sort_=True)
     rad, ang, mil_j, mil_jk = NL.buildPairsAndTriplesWithEleIndexPeriodic(Rr, Ra, eles_np, elep_np)
     return np.asarray(rad), np.asarray(ang), np.asarray(mil_j), np.asarray(mil_jk)
+
+
+_TFNS = None
+
+
+def tf_namespace(params):
+    """The reference's TensorFlow electrostatics functions (RawSymFunc.py:63-79, 123-134, 1307-1465), executed unmodified on
+    the numpy stand-in oracle/tf_shim.py.  `params` supplies PARAMS["EECutoffOff"], PARAMS["Poly_Width"]."""
+    global _TFNS
+    from oracle import tf_shim
+    if _TFNS is None:
+        ns = {"tf": tf_shim, "np": np, "BOHRPERA": float(namespace()["BOHRPERA"]), "PARAMS": {}}
+        exec(_defs("TensorMol/TFDescriptors/RawSymFunc.py",
+                   {"AllDoublesSet", "DifferenceVectorsLinear", "TFCoulombEluSRDSFLR", "TFVdwPolyLR", "TFVdwPolyLRWithEle"}), ns)
+        exec(_defs("TensorMol/Util.py", {"sigmoid_with_param"}), ns)             # Util.py:200-201
+        _TFNS = ns
+    _TFNS["PARAMS"].clear()
+    _TFNS["PARAMS"].update(params)
+    return _TFNS
+
+
+def vdw_parameters(eles):
+    """self.C6 / self.vdw_R of the instance (TFMolInstanceDirect.py:3763-3767)."""
+    ns = namespace()
+    B, JPH = float(ns["BOHRPERA"]), float(ns["JOULEPERHARTREE"])
+    c6 = np.array([ns["C6_coff"][int(e)] * (B * 10.0) ** 6.0 / JPH for e in eles])
+    rv = np.array([ns["atomic_vdw_radius"][int(e)] * B for e in eles])
+    return c6, rv
+
+
+def electrostatics_aperiodic(xyz, Z, q, P):
+    """Ecc and Evdw of one molecule exactly as energy_inference / dipole_inference call the TF functions
+    (TFMolInstanceDirect.py:5214, 5281; pair list of TFMolManage.py:1311-1312), for given atomic charges q [N]."""
+    ns = namespace()
+    B = float(ns["BOHRPERA"])
+    tfn = tf_namespace({"EECutoffOff": P["EECutoffOff"], "Poly_Width": P["Poly_Width"]})
+    N = len(Z)
+    X = np.asarray(xyz, np.float64)
+    NLEE = ns["NeighborListSet"](X[None].copy(), np.array([N], np.int32), False, False, None)
+    ree = np.asarray(NLEE.buildPairs(P["EECutoffOff"])).astype(np.int64)
+    elu_a = ns["DSF_Gradient"](P["Elu_Width"] * B, P["EECutoffOff"] * B, P["DSFAlpha"] / B)
+    elu_s = ns["DSF"](P["Elu_Width"] * B, P["EECutoffOff"] * B, P["DSFAlpha"] / B)
+    eles = sorted(set(int(z) for z in Z))
+    c6, rv = vdw_parameters(eles)
+    xb = X[None] * B                                                        # xyzsInBohr
+    Ecc = tfn["TFCoulombEluSRDSFLR"](xb, np.asarray(q, np.float64)[None], P["Elu_Width"] * B, ree, P["DSFAlpha"], elu_a, elu_s)
+    Evdw = tfn["TFVdwPolyLR"](xb, np.asarray(Z, np.int64)[None], np.array(eles, np.int64), c6, rv, P["EECutoffOn"] * B, ree)
+    return float(Ecc[0]), float(Evdw[0]), ree
+
+
+def electrostatics_periodic(xyz_tess, Z_tess, nreal, q_real, eles, P):
+    """The periodic forms (TFMolInstanceDirect.py:5824, 5892-5896; pair list of TFMolManage.py:1345-1346): charges tiled
+    over the image blocks, both energies halved."""
+    ns = namespace()
+    B = float(ns["BOHRPERA"])
+    tfn = tf_namespace({"EECutoffOff": P["EECutoffOff"], "Poly_Width": P["Poly_Width"]})
+    X = np.asarray(xyz_tess, np.float64)
+    Zt = np.asarray(Z_tess, np.int32)
+    eles = sorted(int(e) for e in eles)
+    NLEE = ns["NeighborListSetWithImages"](X[None].copy(), np.array([len(Zt)]), np.array([nreal]), False, True, Zt[None].copy())
+    ree = np.asarray(NLEE.buildPairsWithBothEleIndex(P["EECutoffOff"], np.asarray(eles).reshape(-1, 1))).astype(np.int64)
+    elu_a = ns["DSF_Gradient"](P["Elu_Width"] * B, P["EECutoffOff"] * B, P["DSFAlpha"] / B)
+    elu_s = ns["DSF"](P["Elu_Width"] * B, P["EECutoffOff"] * B, P["DSFAlpha"] / B)
+    c6, rv = vdw_parameters(eles)
+    xb = X[None] * B
+    q_all = np.tile(np.asarray(q_real, np.float64)[None], (1, len(Zt) // nreal))
+    Ecc = tfn["TFCoulombEluSRDSFLR"](xb, q_all, P["Elu_Width"] * B, ree[:, :3], P["DSFAlpha"], elu_a, elu_s) / 2.0
+    Evdw = tfn["TFVdwPolyLRWithEle"](xb, Zt[None].astype(np.int64), np.array(eles, np.int64), c6, rv, P["EECutoffOn"] * B, ree) / 2.0
+    return float(Ecc[0]), float(Evdw[0])
 
 
 def lattice(latvec):

@@ -272,3 +272,67 @@ def test_constants_and_dsf_equal_reference_python():
     sh, al = og.elu_constants(P) if hasattr(og, "elu_constants") else (None, None)
     if sh is not None:
         assert abs(sh - p["dsf"][0]) < 1e-14 and abs(al - p["dsf_gradient"][0]) < 1e-14 and P["Elu_Width"] * B == p["dsf_in"][0][0]
+
+
+@pytest.mark.parametrize("name", ["h2o_cluster", "morphine"])
+def test_oracle_electrostatics_equal_reference_tf_functions(name):
+    """TFCoulombEluSRDSFLR and TFVdwPolyLR (RawSymFunc.py:1307-1414), executed unmodified on the numpy TF stand-in for a
+    seeded neutral charge vector and the manager's i<j pair list: the oracle's restatements agree to rounding."""
+    from oracle.oracle_graph import BOHRPERA, coulomb_elu_sr_dsf_lr, vdw_poly_lr
+    from tensormol_b200.engine import DSF, DSF_Gradient
+    p, g = _pins(), load_golden(name)
+    P = og.default_params()
+    Z, X = g["Z"].astype(np.int32), g["xyz"]
+    N = len(Z)
+    q = p[name + "_q"]
+    ree = np.asarray(onp.build_pairs(X, P["EECutoffOff"], N, False))
+    ree = np.concatenate([np.zeros((len(ree), 1), np.int64), ree.astype(np.int64)], axis=1) if ree.shape[1] == 2 else ree.astype(np.int64)
+    assert len(ree) == int(p[name + "_n_ee"])
+    elu_a = DSF_Gradient(P["Elu_Width"] * BOHRPERA, P["EECutoffOff"] * BOHRPERA, P["DSFAlpha"] / BOHRPERA)
+    elu_s = DSF(P["Elu_Width"] * BOHRPERA, P["EECutoffOff"] * BOHRPERA, P["DSFAlpha"] / BOHRPERA)
+    Rb = torch.tensor(X[None] * BOHRPERA)
+    pr = torch.tensor(ree)
+    Ecc = coulomb_elu_sr_dsf_lr(Rb, torch.tensor(q[None]), P["Elu_Width"] * BOHRPERA, pr, P["DSFAlpha"], elu_a, elu_s, P)
+    assert abs(float(Ecc[0]) - float(p[name + "_Ecc"])) <= 1e-13 * abs(float(p[name + "_Ecc"]))
+    eles = sorted(set(Z.tolist()))
+    C6, vdw_R = og.vdw_constants(eles)
+    ei = np.array([eles.index(z) for z in Z[ree[:, 1]]])
+    ej = np.array([eles.index(z) for z in Z[ree[:, 2]]])
+    Evdw = vdw_poly_lr(Rb, torch.as_tensor(C6[ei]), torch.as_tensor(C6[ej]), torch.as_tensor(vdw_R[ei]), torch.as_tensor(vdw_R[ej]),
+                       P["EECutoffOn"] * BOHRPERA, pr, P)
+    assert abs(float(Evdw[0]) - float(p[name + "_Evdw"])) <= 1e-13 * abs(float(p[name + "_Evdw"]))
+
+
+def test_oracle_periodic_electrostatics_equal_reference_tf_functions():
+    """The periodic forms (TFMolInstanceDirect.py:5824, 5892-5896): charges tiled over the image blocks, TFVdwPolyLRWithEle
+    and TFCoulombEluSRDSFLR over the real-centre pair list, both halved."""
+    from oracle.oracle_graph import BOHRPERA, coulomb_elu_sr_dsf_lr, vdw_poly_lr
+    from tensormol_b200.engine import DSF, DSF_Gradient
+    p, g = _pins(), load_golden("water_tiny_periodic")
+    P = og.default_params()
+    Z = g["Z"]
+    nreal = len(Z)
+    zt, xt = onp.tess_lattice(p["lat"], Z.astype(np.uint8), p["tess_in"], P["EECutoffOff"])
+    eles_np = np.array([[1], [8]])
+    ree = np.asarray(onp.build_pairs_with_both_ele_index(xt[None], np.array([len(zt)]), np.array([nreal]), zt.astype(np.int32)[None],
+                                                         P["EECutoffOff"], eles_np, True)).astype(np.int64)
+    q_all = np.tile(p["periodic_q"][None], (1, len(zt) // nreal))
+    elu_a = DSF_Gradient(P["Elu_Width"] * BOHRPERA, P["EECutoffOff"] * BOHRPERA, P["DSFAlpha"] / BOHRPERA)
+    elu_s = DSF(P["Elu_Width"] * BOHRPERA, P["EECutoffOff"] * BOHRPERA, P["DSFAlpha"] / BOHRPERA)
+    Rb = torch.tensor(xt[None] * BOHRPERA)
+    pr = torch.tensor(ree[:, :3])
+    Ecc = coulomb_elu_sr_dsf_lr(Rb, torch.tensor(q_all), P["Elu_Width"] * BOHRPERA, pr, P["DSFAlpha"], elu_a, elu_s, P) / 2.0
+    assert abs(float(Ecc[0]) - float(p["periodic_Ecc"])) <= 1e-11 * abs(float(p["periodic_Ecc"]))
+    C6, vdw_R = og.vdw_constants([1, 8])
+    ei, ej = ree[:, 3], ree[:, 4]
+    Evdw = vdw_poly_lr(Rb, torch.as_tensor(C6[ei]), torch.as_tensor(C6[ej]), torch.as_tensor(vdw_R[ei]), torch.as_tensor(vdw_R[ej]),
+                       P["EECutoffOn"] * BOHRPERA, pr, P) / 2.0
+    assert abs(float(Evdw[0]) - float(p["periodic_Evdw"])) <= 1e-11 * abs(float(p["periodic_Evdw"]))
+
+
+def test_oracle_activation_equals_reference_sigmoid_with_param():
+    """Util.py:200-201 executed on the numpy TF stand-in (alpha = 100, |x| <= 2 stays inside float64 range)."""
+    p = _pins()
+    P = og.default_params()
+    got = og.activation(torch.tensor(p["act_in"]), P).numpy()
+    assert np.abs(got - p["act_out"]).max() <= 1e-15 + 1e-14 * np.abs(p["act_out"]).max()
