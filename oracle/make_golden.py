@@ -193,6 +193,22 @@ def reference_python_pins():
     out["periodic_q"] = q
     out["periodic_Ecc"] = np.float64(ecc)
     out["periodic_Evdw"] = np.float64(evdw)
+    # the whole evaluation graph of the reference instance (symmetry functions, dipole_inference, energy_inference,
+    # tf.gradients) executed on the torch stand-in with the same seeded weights as the oracle fixtures
+    for name, fn, hidden, seed in (("h2o_cluster", "H2O_cluster.xyz", [64, 48, 32], 0), ("morphine", "morphine.xyz", [96, 64, 64], 1)):
+        Z, X, _ = read_xyz_frames(os.path.join(REF, "datasets", fn))[0]
+        eles = sorted(set(int(z) for z in Z))
+        W = ref_py.weights_with_biases(random_weights(eles, descriptor_width(len(eles), P), hidden, seed), 100 + seed)
+        r = ref_py.full_graph_aperiodic(X, Z, hidden, W, P)
+        for k in ("Etotal", "Ebp", "Ecc", "Evdw", "Ebp_atom", "dipole", "charge", "gradient", "descriptors"):
+            out["graph_" + name + "_" + k] = np.asarray(r[k])
+    W = ref_py.weights_with_biases(random_weights([1, 8], descriptor_width(2, P), [64, 48, 32], 2), 102)
+    r = ref_py.full_graph_periodic(xt, zt, len(Z0), [1, 8], [64, 48, 32], W, P)
+    for k in ("Etotal", "Ebp", "Ecc", "Evdw", "dipole"):
+        out["graph_periodic_" + k] = np.asarray(r[k])
+    out["graph_periodic_Ebp_atom"] = np.asarray(r["Ebp_atom"])[:, : len(Z0)]
+    out["graph_periodic_charge"] = np.asarray(r["charge"])[:, : len(Z0)]
+    out["graph_periodic_gradient"] = np.asarray(r["gradient"])[:, : len(Z0)]       # the rows the manager keeps (TFMolManage.py:1353)
     tfn = ref_py.tf_namespace({"sigmoid_alpha": P["sigmoid_alpha"], "EECutoffOff": P["EECutoffOff"], "Poly_Width": P["Poly_Width"]})
     out["act_in"] = np.linspace(-2.0, 2.0, 81)
     out["act_out"] = tfn["sigmoid_with_param"](out["act_in"])

@@ -185,8 +185,10 @@ def electrostatics_aperiodic(xyz, Z, q, P):
     eles = sorted(set(int(z) for z in Z))
     c6, rv = vdw_parameters(eles)
     xb = X[None] * B                                                        # xyzsInBohr
-    Ecc = tfn["TFCoulombEluSRDSFLR"](xb, np.asarray(q, np.float64)[None], P["Elu_Width"] * B, ree, P["DSFAlpha"], elu_a, elu_s)
-    Evdw = tfn["TFVdwPolyLR"](xb, np.asarray(Z, np.int64)[None], np.array(eles, np.int64), c6, rv, P["EECutoffOn"] * B, ree)
+    import torch
+    T = torch.as_tensor
+    Ecc = tfn["TFCoulombEluSRDSFLR"](T(xb), T(np.asarray(q, np.float64)[None]), P["Elu_Width"] * B, T(ree), P["DSFAlpha"], elu_a, elu_s)
+    Evdw = tfn["TFVdwPolyLR"](T(xb), T(np.asarray(Z, np.int64)[None]), T(np.array(eles, np.int64)), T(c6), T(rv), P["EECutoffOn"] * B, T(ree))
     return float(Ecc[0]), float(Evdw[0]), ree
 
 
@@ -206,9 +208,187 @@ def electrostatics_periodic(xyz_tess, Z_tess, nreal, q_real, eles, P):
     c6, rv = vdw_parameters(eles)
     xb = X[None] * B
     q_all = np.tile(np.asarray(q_real, np.float64)[None], (1, len(Zt) // nreal))
-    Ecc = tfn["TFCoulombEluSRDSFLR"](xb, q_all, P["Elu_Width"] * B, ree[:, :3], P["DSFAlpha"], elu_a, elu_s) / 2.0
-    Evdw = tfn["TFVdwPolyLRWithEle"](xb, Zt[None].astype(np.int64), np.array(eles, np.int64), c6, rv, P["EECutoffOn"] * B, ree) / 2.0
+    import torch
+    T = torch.as_tensor
+    Ecc = tfn["TFCoulombEluSRDSFLR"](T(xb), T(q_all), P["Elu_Width"] * B, T(ree[:, :3].copy()), P["DSFAlpha"], elu_a, elu_s) / 2.0
+    Evdw = tfn["TFVdwPolyLRWithEle"](T(xb), T(Zt[None].astype(np.int64)), T(np.array(eles, np.int64)), T(c6), T(rv), P["EECutoffOn"] * B, T(ree)) / 2.0
     return float(Ecc[0]), float(Evdw[0])
+
+
+def _method_defs(path, names, class_name=None):
+    """Methods taken out of their class (first class defining them, or `class_name`) as plain functions f(self, ...)."""
+    import warnings
+    with open(os.path.join(REF, path)) as fh, warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        tree = ast.parse(fh.read())
+    found = {}
+    for node in tree.body:
+        if isinstance(node, ast.ClassDef) and (class_name is None or node.name == class_name):
+            for sub in node.body:
+                if isinstance(sub, ast.FunctionDef) and sub.name in names and sub.name not in found:
+                    found[sub.name] = sub
+    mod = ast.Module(body=[found[n] for n in names if n in found], type_ignores=[])
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        return compile(ast.fix_missing_locations(mod), os.path.join(REF, path), "exec")
+
+
+INSTANCE_CLASS = "MolInstance_DirectBP_EE_ChargeEncode_Update_vdw_DSF_elu_Normalize_Dropout"
+_GNS = None
+
+
+def graph_namespace(P):
+    """Everything the instance's EvalPrepare wires together (TFMolInstanceDirect.py:5713-5761), executed on the torch
+    stand-in: the symmetry-function graph (RawSymFunc.py), the electrostatics, and the methods energy_inference /
+    dipole_inference (+ periodic forms) of the instance class, taken out of the class as plain functions."""
+    global _GNS
+    from oracle import tf_shim
+    if _GNS is None:
+        import math
+        base = namespace()
+        ns = {"tf": tf_shim, "np": np, "math": math, "Pi": math.pi, "BOHRPERA": float(base["BOHRPERA"]), "PARAMS": {},
+              "TMTiming": _tmtiming, "print": lambda *a, **k: None}
+        exec(_defs("TensorMol/TFDescriptors/RawSymFunc.py",
+                   {"AllSinglesSet", "AllDoublesSet", "DifferenceVectorsLinear", "TFSymRSet_Linear_WithEle", "TFSymASet_Linear_WithEle",
+                    "TFSymSet_Scattered_Linear_WithEle", "TFSymRSet_Linear_WithElePeriodic", "TFSymASet_Linear_WithElePeriodic",
+                    "TFSymSet_Scattered_Linear_WithEle_Periodic", "TFCoulombEluSRDSFLR", "TFVdwPolyLR", "TFVdwPolyLRWithEle"}), ns)
+        exec(_defs("TensorMol/Util.py", {"sigmoid_with_param"}), ns)
+        exec(_method_defs("TensorMol/TFNetworks/TFMolInstanceDirect.py",
+                          ["energy_inference", "dipole_inference", "energy_inference_periodic", "dipole_inference_periodic"], INSTANCE_CLASS), ns)
+        exec(_method_defs("TensorMol/TFNetworks/TFMolInstanceDirect.py", ["SetANI1Param"]), ns)
+        _GNS = ns
+    _GNS["PARAMS"].clear()
+    _GNS["PARAMS"].update(P)
+    return _GNS
+
+
+class _FakeInstance:
+    """The attributes of the reference instance that the extracted methods read (TFMolInstanceDirect.py:4969-4984, 3755-3767)."""
+
+    def __init__(self, ns, eles, hidden, P, nmol, maxnatom, weights):
+        from oracle import tf_shim
+        base = namespace()
+        B = float(base["BOHRPERA"])
+        self.eles = list(eles)
+        self.eles_np = np.asarray(self.eles).reshape(-1, 1)
+        self.eles_pairs = [[self.eles[i], self.eles[j]] for i in range(len(self.eles)) for j in range(i, len(self.eles))]
+        self.eles_pairs_np = np.asarray(self.eles_pairs)
+        self.HiddenLayers = list(hidden)
+        self.batch_size, self.MaxNAtoms = nmol, maxnatom
+        self.tf_prec = tf_shim.float64
+        self.activation_function = ns["sigmoid_with_param"]
+        self.DSFAlpha = P["DSFAlpha"]
+        self.elu_shift = base["DSF"](P["Elu_Width"] * B, P["EECutoffOff"] * B, P["DSFAlpha"] / B)          # :4371
+        self.elu_alpha = base["DSF_Gradient"](P["Elu_Width"] * B, P["EECutoffOff"] * B, P["DSFAlpha"] / B)
+        self.C6, self.vdw_R = vdw_parameters(self.eles)
+        ns["SetANI1Param"](self)
+        self._weights = weights
+        self._queue = []
+
+    def load(self, net):
+        """Queue this net's variables in the order the inference method creates them: per element, per hidden layer
+        (weights, biases), then the linear output layer."""
+        from oracle import tf_shim
+        assert not self._queue and not tf_shim._bias_queue, "the previous inference did not consume all its variables"
+        self._queue = []
+        biases = []
+        for z in self.eles:
+            for W, b in self._weights[net][int(z)]:
+                self._queue.append(np.asarray(W, np.float64))
+                biases.append(np.asarray(b, np.float64))
+        tf_shim.push_biases(biases)
+
+    def _variable_with_weight_decay(self, var_name, var_shape, var_stddev, var_wd):
+        import torch
+        W = self._queue.pop(0)
+        assert list(W.shape) == [int(v) for v in var_shape], (W.shape, var_shape)
+        return torch.as_tensor(W)
+
+
+def weights_with_biases(weights, seed):
+    """random_weights() keeps the reference's zero bias initialisation; the pins use seeded non-zero biases so that the
+    bias wiring is exercised as well."""
+    rng = np.random.default_rng(seed)
+    return {net: {z: [(W, 0.05 * rng.standard_normal(b.shape)) for W, b in layers] for z, layers in d.items()} for net, d in weights.items()}
+
+
+def full_graph_aperiodic(xyz, Z, hidden, weights, P):
+    """One molecule through the reference's own graph code in the order of EvalPrepare / evaluate
+    (TFMolInstanceDirect.py:5748-5761, 5684-5711; feed of TFMolManage.py:1300-1317): returns Etotal, Ebp, Ecc, Evdw,
+    Ebp_atom, dipole, charge, gradient dE/dx (Hartree / Angstrom)."""
+    import torch
+    from oracle import tf_shim as tf
+    ns = graph_namespace(P)
+    X = np.asarray(xyz, np.float64)
+    Zs = np.asarray(Z, np.int64)[None]
+    N = Zs.shape[1]
+    eles = sorted(set(int(z) for z in Z))
+    inst = _FakeInstance(ns, eles, hidden, P, 1, N, weights)
+    rad, ang, mil_jk, _ = tables_aperiodic(X, Z, P["AN1_r_Rc"], P["AN1_a_Rc"])
+    base = namespace()
+    NLEE = base["NeighborListSet"](X[None].copy(), np.array([N], np.int32), False, False, None)
+    reep = np.asarray(NLEE.buildPairs(P["EECutoffOff"])).astype(np.int64)
+    xyzs = torch.tensor(X[None], dtype=torch.float64, requires_grad=True)
+    Zt = torch.as_tensor(Zs)
+    natom = torch.tensor([1.0 / N], dtype=torch.float64)
+    keep = torch.ones(len(hidden) + 1, dtype=torch.float64)
+    Ele, Elep = torch.as_tensor(inst.eles_np), torch.as_tensor(inst.eles_pairs_np)
+    SFPa2, SFPr2 = torch.as_tensor(inst.SFPa2), torch.as_tensor(inst.SFPr2)
+    sym, idx = ns["TFSymSet_Scattered_Linear_WithEle"](xyzs, Zt, Ele, SFPr2, inst.Rr_cut, Elep, SFPa2, inst.zeta, inst.eta, inst.Ra_cut,
+                                                       torch.as_tensor(rad.astype(np.int64)), torch.as_tensor(ang.astype(np.int64)),
+                                                       torch.as_tensor(mil_jk.astype(np.int64)))
+    inst.load("charge")
+    Ecc, dipole, charge, _ = ns["dipole_inference"](inst, sym, idx, xyzs, natom, P["Elu_Width"], P["EECutoffOff"], torch.as_tensor(reep), True, keep)
+    inst.load("energy")
+    Etotal, Ebp, Evdw, _, Ebp_atom = ns["energy_inference"](inst, sym, idx, Ecc, xyzs, Zt, Ele, torch.as_tensor(inst.C6), torch.as_tensor(inst.vdw_R),
+                                                            torch.as_tensor(reep), P["EECutoffOn"], P["EECutoffOff"], keep)
+    grad = tf.gradients(Etotal, xyzs)[0]
+    D = torch.cat([torch.zeros(0)]).numpy()   # placeholder to keep numpy import obvious
+    desc = np.zeros((N, int(inst.inshape)))
+    for e in range(len(eles)):
+        rows = idx[e][:, 1].numpy()
+        desc[rows] = sym[e].detach().numpy()
+    del D
+    return dict(Etotal=Etotal.detach().numpy(), Ebp=Ebp.detach().numpy(), Ecc=Ecc.detach().numpy(), Evdw=Evdw.detach().numpy(),
+                Ebp_atom=Ebp_atom.detach().numpy(), dipole=dipole.detach().numpy(), charge=charge.detach().numpy(),
+                gradient=grad.detach().numpy(), descriptors=desc)
+
+
+def full_graph_periodic(xyz_tess, Z_tess, nreal, eles, hidden, weights, P):
+    """The periodic form: EvalPrepare_Periodic / evaluate_periodic (TFMolInstanceDirect.py:5919-6003) fed as
+    TFMolManage.py:1335-1351 does.  Returns the reference's outputs; gradient rows beyond nreal are the image rows the
+    manager discards."""
+    import torch
+    from oracle import tf_shim as tf
+    ns = graph_namespace(P)
+    X = np.asarray(xyz_tess, np.float64)
+    Zt_np = np.asarray(Z_tess, np.int32)
+    NT = len(Zt_np)
+    eles = sorted(int(e) for e in eles)
+    inst = _FakeInstance(ns, eles, hidden, P, 1, NT, weights)
+    inst.nreal = int(nreal)
+    rad, ang, mil_j, mil_jk = tables_periodic(X, Zt_np, nreal, P["AN1_r_Rc"], P["AN1_a_Rc"], eles)
+    base = namespace()
+    NLEE = base["NeighborListSetWithImages"](X[None].copy(), np.array([NT]), np.array([nreal]), False, True, Zt_np[None].copy())
+    ree = np.asarray(NLEE.buildPairsWithBothEleIndex(P["EECutoffOff"], np.asarray(eles).reshape(-1, 1))).astype(np.int64)
+    T = torch.as_tensor
+    xyzs = torch.tensor(X[None], dtype=torch.float64, requires_grad=True)
+    Zt = T(Zt_np.astype(np.int64)[None])
+    natom = torch.tensor([1.0 / nreal], dtype=torch.float64)
+    keep = torch.ones(len(hidden) + 1, dtype=torch.float64)
+    Ele, Elep = T(inst.eles_np), T(inst.eles_pairs_np)
+    sym, idx = ns["TFSymSet_Scattered_Linear_WithEle_Periodic"](xyzs, Zt, Ele, T(inst.SFPr2), inst.Rr_cut, Elep, T(inst.SFPa2), inst.zeta, inst.eta,
+                                                                inst.Ra_cut, T(rad.astype(np.int64)), T(ang.astype(np.int64)), T(mil_j.astype(np.int64)),
+                                                                T(mil_jk.astype(np.int64)), int(nreal))
+    inst.load("charge")
+    Ecc, dipole, charge, _ = ns["dipole_inference_periodic"](inst, sym, idx, xyzs, natom, P["Elu_Width"], P["EECutoffOff"], T(ree[:, :3].copy()), True, keep)
+    inst.load("energy")
+    Etotal, Ebp, Evdw, _, Ebp_atom = ns["energy_inference_periodic"](inst, sym, idx, Ecc, xyzs, Zt, Ele, T(inst.C6), T(inst.vdw_R), T(ree),
+                                                                     P["EECutoffOn"], P["EECutoffOff"], keep)
+    grad = tf.gradients(Etotal, xyzs)[0]
+    return dict(Etotal=Etotal.detach().numpy(), Ebp=Ebp.detach().numpy(), Ecc=Ecc.detach().numpy(), Evdw=Evdw.detach().numpy(),
+                Ebp_atom=Ebp_atom.detach().numpy(), dipole=dipole.detach().numpy(), charge=charge.detach().numpy(),
+                gradient=grad.detach().numpy())
 
 
 def lattice(latvec):

@@ -1,123 +1,262 @@
-"""TEST INFRASTRUCTURE ONLY.  A numpy stand-in for the handful of TensorFlow-1 ops that the reference's electrostatics
-functions use (RawSymFunc.py: DifferenceVectorsLinear, AllDoublesSet, TFCoulombEluSRDSFLR, TFVdwPolyLR,
-TFVdwPolyLRWithEle), so that oracle/ref_py.py can execute those functions unmodified, in float64, without TensorFlow.
-Eager semantics: every "tensor" is a numpy array.  Only what those functions call is implemented."""
-import numpy as np
-from scipy.special import erfc as _erfc
+"""TEST INFRASTRUCTURE ONLY.  An eager, torch-float64-backed stand-in for the TensorFlow-1 ops that the reference's
+energy/force graph uses on this path (RawSymFunc.py symmetry functions and electrostatics, TFMolInstanceDirect.py
+energy_inference / dipole_inference), so that oracle/ref_py.py can execute those functions unmodified without
+TensorFlow.  Every "tensor" is a torch tensor; tf.gradients is torch.autograd.  Only what those functions call exists.
 
-float64, float32, int64, int32 = np.float64, np.float32, np.int64, np.int32
+Variables: the reference creates its weights with self._variable_with_weight_decay (supplied by the caller) and its
+biases with tf.Variable(tf.zeros(...), name='biases'); a caller can queue values for the latter with push_biases()."""
+import contextlib
+
+import numpy as np
+import torch
+
+float64, float32, int64, int32, bool = torch.float64, torch.float32, torch.int64, torch.int32, torch.bool   # noqa: A001
+
+_bias_queue = []
+
+
+def push_biases(values):
+    _bias_queue.extend(values)
+
+
+def _t(x, dtype=None):
+    if isinstance(x, torch.Tensor):
+        return x if dtype is None else x.to(dtype)
+    if isinstance(x, (list, tuple)) and any(isinstance(v, torch.Tensor) for v in x):
+        x = [int(v) if isinstance(v, torch.Tensor) else v for v in x]
+    return torch.as_tensor(np.asarray(x), dtype=dtype)
+
+
+def _ints(shp):
+    if isinstance(shp, torch.Tensor):
+        return [int(v) for v in shp.reshape(-1)]
+    return [int(v) for v in shp]
+
+
+class _Shape(tuple):
+    def as_list(self):
+        return list(self)
+
+
+torch.Tensor.get_shape = lambda self: _Shape(self.shape)   # tensor.get_shape().as_list() (RawSymFunc.py:2250)
 
 
 def shape(x):
-    return np.array(np.shape(x), dtype=np.int64)
+    return _Shape(_t(x).shape)
 
 
-def cast(x, dtype):
-    return np.asarray(x).astype(dtype)
+def cast(x, dtype=None, name=None):
+    return _t(x).to(dtype)
 
 
 def constant(v, dtype=None):
-    return np.asarray(v, dtype=dtype)
+    return _t(v, dtype)
 
 
-def reshape(x, shp):
-    return np.reshape(x, [int(s) for s in np.asarray(shp).ravel()] if not isinstance(shp, (list, tuple)) else [int(s) for s in shp])
+def convert_to_tensor(v, dtype=None):
+    return _t(v, dtype)
 
 
-def sqrt(x):
-    return np.sqrt(x)
+def identity(x, name=None):
+    return x
 
 
-def exp(x):
-    return np.exp(x)
+def Variable(init, trainable=True, dtype=None, name=None):
+    if name is not None and name.startswith("biases") and _bias_queue:   # 'biases' / 'biaseslayer<i>' (TFMolInstanceDirect.py:5189)
+        return _t(_bias_queue.pop(0), float64)
+    return _t(init, dtype)
 
 
-def log(x):
-    return np.log(x)
+def zeros(shp, dtype=float64):
+    return torch.zeros(_ints(shp), dtype=dtype)
 
 
-def erfc(x):
-    return _erfc(x)
+def zeros_like(x, dtype=None):
+    return torch.zeros_like(_t(x), dtype=dtype)
 
 
-def pow(x, y):   # noqa: A001
-    return np.power(x, y)
+def ones_like(x, dtype=None):
+    return torch.ones_like(_t(x), dtype=dtype)
 
 
-def multiply(a, b):
-    return np.multiply(a, b)
+def reshape(x, shp, name=None):
+    return _t(x).reshape(_ints(shp))
 
 
-def reduce_sum(x, axis=None):
-    return np.sum(x, axis=axis)
+def expand_dims(x, axis):
+    return _t(x).unsqueeze(axis)
 
 
-def greater(a, b):
-    return np.greater(a, b)
+def tile(x, reps):
+    return _t(x).repeat(*_ints(reps))
 
 
-def equal(a, b):
-    return np.equal(a, b)
+def transpose(x, perm):
+    return _t(x).permute(*perm)
 
 
-def is_nan(x):
-    return np.isnan(x)
+def concat(xs, axis, name=None):
+    return torch.cat([_t(a) for a in xs], dim=axis)
 
 
-def zeros_like(x):
-    return np.zeros_like(x)
+def stack(xs, axis=0):
+    return torch.stack([_t(a) for a in xs], dim=axis)
 
 
-def ones_like(x):
-    return np.ones_like(x)
+def range(n, dtype=int32):   # noqa: A001
+    return torch.arange(int(n), dtype=dtype)
 
 
-def where(cond, x=None, y=None):
-    if x is None:
-        return np.argwhere(cond).astype(np.int64)
-    return np.where(cond, x, y)
-
-
-def range(n, dtype=np.int32):   # noqa: A001
-    return np.arange(int(n), dtype=dtype)
-
-
-def slice(x, begin, size):   # noqa: A001
-    x = np.asarray(x)
+def slice(x, begin, size, name=None):   # noqa: A001
+    x = _t(x)
     idx = []
-    for d, (b, s) in enumerate(zip(begin, size)):
-        b, s = int(b), int(s)
+    for b, s in zip(_ints(begin), _ints(size)):
         idx.append(np.s_[b:] if s < 0 else np.s_[b:b + s])
     return x[tuple(idx)]
 
 
-def concat(xs, axis):
-    return np.concatenate([np.asarray(a) for a in xs], axis=axis)
+def sqrt(x):
+    return torch.sqrt(_t(x))
 
 
-def stack(xs, axis=0):
-    return np.stack([np.asarray(a) for a in xs], axis=axis)
+def exp(x):
+    return torch.exp(_t(x))
 
 
-def tile(x, reps):
-    return np.tile(x, [int(r) for r in reps])
+def log(x):
+    return torch.log(_t(x))
 
 
-def transpose(x, perm):
-    return np.transpose(x, perm)
+def cos(x):
+    return torch.cos(_t(x))
+
+
+def acos(x):
+    return torch.acos(_t(x))
+
+
+def erfc(x):
+    return torch.erfc(_t(x))
+
+
+def pow(x, y):   # noqa: A001
+    return torch.pow(_t(x, float64) if not isinstance(x, torch.Tensor) else x, y)
+
+
+def multiply(a, b):
+    return _t(a) * _t(b)
+
+
+def add(a, b):
+    return _t(a) + _t(b)
+
+
+def subtract(a, b):
+    return _t(a) - _t(b)
+
+
+def div(a, b):
+    if isinstance(a, int) and isinstance(b, int):
+        return a // b
+    return _t(a) / _t(b)
+
+
+def matmul(a, b):
+    return _t(a) @ _t(b)
+
+
+def reduce_sum(x, axis=None):
+    return torch.sum(_t(x)) if axis is None else torch.sum(_t(x), dim=axis)
+
+
+def reduce_max(x):
+    return torch.max(_t(x))
+
+
+def greater(a, b):
+    return _t(a) > b
+
+
+def greater_equal(a, b):
+    return _t(a) >= b
+
+
+def less_equal(a, b):
+    return _t(a) <= b
+
+
+def equal(a, b, name=None):
+    return _t(a) == _t(b)
+
+
+def is_nan(x):
+    return torch.isnan(_t(x))
+
+
+def where(cond, x=None, y=None):
+    if x is None:
+        return torch.nonzero(cond)
+    return torch.where(cond, _t(x), _t(y))
+
+
+def boolean_mask(x, mask):
+    return _t(x)[mask]
 
 
 def gather_nd(params, indices):
-    params, indices = np.asarray(params), np.asarray(indices).astype(np.int64)
+    params, indices = _t(params), _t(indices).long()
     k = indices.shape[-1]
     return params[tuple(indices[..., i] for i in np.arange(k))]
 
 
+def scatter_nd(indices, updates, shp):
+    indices = _t(indices).long()
+    out = torch.zeros(_ints(shp), dtype=_t(updates).dtype)
+    return out.index_put(tuple(indices[:, i] for i in np.arange(indices.shape[1])), _t(updates), accumulate=True)
+
+
 class SparseTensor:
     def __init__(self, indices, values, dense_shape):
-        self.indices, self.values, self.dense_shape = np.asarray(indices), np.asarray(values), [int(s) for s in dense_shape]
+        self.indices, self.values, self.dense_shape = _t(indices).long(), _t(values), _ints(dense_shape)
 
 
 def sparse_reduce_sum(sp, axis):
     assert axis == 1
-    return np.bincount(sp.indices[:, 0], weights=sp.values, minlength=sp.dense_shape[0])
+    return torch.zeros(sp.dense_shape[0], dtype=sp.values.dtype).index_add(0, sp.indices[:, 0], sp.values)
+
+
+def cond(pred, f1, f2):
+    return f1() if builtins_bool(pred) else f2()
+
+
+def builtins_bool(v):
+    return (v.item() if isinstance(v, torch.Tensor) else v) not in (0, False)
+
+
+def verify_tensor_all_finite(x, msg):
+    return x
+
+
+def get_collection(key, scope=None):
+    return []
+
+
+class GraphKeys:
+    TRAINABLE_VARIABLES = "trainable_variables"
+
+
+@contextlib.contextmanager
+def name_scope(name):
+    yield
+
+
+class nn:   # noqa: N801
+    @staticmethod
+    def dropout(x, keep_prob):
+        kp = float(keep_prob)
+        assert kp == 1.0, "evaluation runs with keep_prob = 1"
+        return x
+
+
+def gradients(y, x, name=None):
+    return list(torch.autograd.grad(y.sum(), x, retain_graph=True))

@@ -343,3 +343,53 @@ def test_host_call_graph_replay_equals_eager(monkeypatch):
     re = eng_e.evaluate_lattice(X2, Z, lat2, 1)
     assert abs(rg["Etotal"][0] - re["Etotal"][0]) <= 1e-7 * abs(re["Etotal"][0])
     assert eng_g.timings()["nlist"] > 0.0                                            # eager again
+
+
+# ---- the CUDA path against outputs of the REFERENCE'S OWN evaluation graph (RawSymFunc.py symmetry functions,
+# dipole_inference, energy_inference, tf.gradients executed unmodified on the torch TF stand-in by oracle/ref_py.py;
+# seeded weights with non-zero biases; tests/golden/ref_python_pins.npz) ----
+@pytest.mark.parametrize("mode", GEMM_MODES)
+@pytest.mark.parametrize("name,hidden,seed", [("h2o_cluster", [64, 48, 32], 0), ("morphine", [96, 64, 64], 1)])
+def test_eval_vs_reference_graph_aperiodic(name, hidden, seed, mode):
+    from oracle import oracle_graph as og
+    from oracle.ref_py import weights_with_biases
+    from tensormol_b200.engine import Engine, descriptor_width, random_weights
+    p, g = load_golden("ref_python_pins"), load_golden(name)
+    P = og.default_params()
+    Z, X = g["Z"], g["xyz"]
+    eles = sorted(set(int(z) for z in Z))
+    W = weights_with_biases(random_weights(eles, descriptor_width(len(eles), P), hidden, seed), 100 + seed)
+    eng = Engine(eles, hidden, P)
+    eng.set_weights(W)
+    eng.set_gemm_mode(mode)
+    r = eng.evaluate(X[None], Z[None].astype(np.int32), np.array([len(Z)]), descriptors=True)
+    pre = "graph_" + name + "_"
+    _check_desc(r["descriptors"][0], p[pre + "descriptors"])
+    for k in ("Etotal", "Ebp", "Ecc", "Evdw"):
+        _check_energy(r[k], p[pre + k], k)
+    _check_grad(r["gradient"], p[pre + "gradient"])
+    assert np.abs(r["charge"] - p[pre + "charge"]).max() <= 1e-5 * max(np.abs(p[pre + "charge"]).max(), 1e-3)
+    assert np.abs(r["Ebp_atom"] - p[pre + "Ebp_atom"]).max() <= 1e-5 * np.abs(p[pre + "Ebp_atom"]).max()
+    assert np.abs(r["dipole"] - p[pre + "dipole"]).max() <= 1e-5 * max(np.abs(p[pre + "dipole"]).max(), 1e-3)
+
+
+@pytest.mark.parametrize("mode", GEMM_MODES)
+def test_eval_vs_reference_graph_periodic(mode):
+    from oracle import oracle_graph as og
+    from oracle.ref_py import weights_with_biases
+    from tensormol_b200.engine import Engine, descriptor_width, random_weights
+    p, g = load_golden("ref_python_pins"), load_golden("water_tiny_periodic")
+    P = og.default_params()
+    Z = g["Z"]
+    nreal = len(Z)
+    hidden = [64, 48, 32]
+    W = weights_with_biases(random_weights([1, 8], descriptor_width(2, P), hidden, 2), 102)
+    eng = Engine([1, 8], hidden, P)
+    eng.set_weights(W)
+    eng.set_gemm_mode(mode)
+    r = eng.evaluate_lattice(p["tess_in"], Z, p["lat"], int(g["ntess"]))
+    for k in ("Etotal", "Ebp", "Ecc", "Evdw"):
+        _check_energy(r[k], p["graph_periodic_" + k], k)
+    _check_grad(r["gradient"], p["graph_periodic_gradient"])
+    assert np.abs(r["charge"][:, :nreal] - p["graph_periodic_charge"]).max() <= 1e-5 * max(np.abs(p["graph_periodic_charge"]).max(), 1e-3)
+    assert np.abs(r["Ebp_atom"] - p["graph_periodic_Ebp_atom"]).max() <= 1e-5 * np.abs(p["graph_periodic_Ebp_atom"]).max()

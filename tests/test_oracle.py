@@ -336,3 +336,43 @@ def test_oracle_activation_equals_reference_sigmoid_with_param():
     P = og.default_params()
     got = og.activation(torch.tensor(p["act_in"]), P).numpy()
     assert np.abs(got - p["act_out"]).max() <= 1e-15 + 1e-14 * np.abs(p["act_out"]).max()
+
+
+# ---- the whole evaluation graph of the reference (its TF symmetry functions, dipole_inference, energy_inference and
+# tf.gradients, executed by oracle/ref_py.py on the torch stand-in with seeded weights AND non-zero biases) ----
+_GRAPH_CASES = {"h2o_cluster": ([64, 48, 32], 0), "morphine": ([96, 64, 64], 1)}
+
+
+@pytest.mark.parametrize("name", ["h2o_cluster", "morphine"])
+def test_oracle_equals_reference_graph_aperiodic(name):
+    from oracle.ref_py import weights_with_biases
+    p, g = _pins(), load_golden(name)
+    hidden, seed = _GRAPH_CASES[name]
+    P = og.default_params()
+    Z, X = g["Z"], g["xyz"]
+    eles = sorted(set(int(z) for z in Z))
+    W = weights_with_biases(random_weights(eles, descriptor_width(len(eles), P), hidden, seed), 100 + seed)
+    o = og.Oracle(eles, W, P).evaluate(X[None], Z[None].astype(np.int32), np.array([len(Z)]))
+    pre = "graph_" + name + "_"
+    for k in ("Etotal", "Ebp", "Ecc", "Evdw"):
+        assert abs(o[k][0] - p[pre + k][0]) <= 1e-12 * max(abs(p[pre + k][0]), 1e-6), k
+    assert np.abs(o["gradient"] - p[pre + "gradient"]).max() <= 1e-13
+    assert np.abs(o["charge"] - p[pre + "charge"]).max() <= 1e-14
+    assert np.abs(o["Ebp_atom"] - p[pre + "Ebp_atom"]).max() <= 1e-13
+    assert np.abs(o["dipole"] - p[pre + "dipole"]).max() <= 1e-12
+    assert np.abs(o["descriptors"][0] - p[pre + "descriptors"]).max() <= 1e-12
+
+
+def test_oracle_equals_reference_graph_periodic():
+    from oracle.ref_py import weights_with_biases
+    p, g = _pins(), load_golden("water_tiny_periodic")
+    P = og.default_params()
+    Z = g["Z"]
+    nreal = len(Z)
+    W = weights_with_biases(random_weights([1, 8], descriptor_width(2, P), [64, 48, 32], 2), 102)
+    zt, xt = onp.tess_lattice(p["lat"], Z.astype(np.uint8), p["tess_in"], P["EECutoffOff"])
+    o = og.Oracle([1, 8], W, P).evaluate_periodic(xt, zt, nreal)
+    for k in ("Etotal", "Ebp", "Ecc", "Evdw"):
+        assert abs(o[k][0] - p["graph_periodic_" + k][0]) <= 1e-11 * max(abs(p["graph_periodic_" + k][0]), 1e-6), k
+    assert np.abs(o["gradient"][0][:nreal] - p["graph_periodic_gradient"][0]).max() <= 1e-13
+    assert np.abs(np.asarray(o["charge"])[0][:nreal] - p["graph_periodic_charge"][0]).max() <= 1e-14
