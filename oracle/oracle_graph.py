@@ -4,13 +4,16 @@ the reference builds for the BP+EE energy/force evaluation.
 
 Nothing in the product package may import this module (see oracle/oracle_np.py header).
 
-Parity pinning: "parity unpinned" by the reference's tests (it has none) and
-TensorFlow is not installable here.  What IS pinned, by executable reference code compiled from
-/root/reference (oracle/_ref/MolEmb): descriptor values (`MolEmb.Make_ANI1_Sym`,
-C_API/MolEmb.cpp:1913-1988) and descriptor Jacobians (`Make_ANI1_Sym_deri`, :1844-1911) -- see
-tests/test_oracle.py.  The MLP / electrostatics / gradient-assembly part is a hand restatement,
-cross-checked by central finite differences of its own energy and by the closed-form constants
-of SURVEY.md §8 a11/a13.
+Parity pinning: PINNED by executing the reference's own code in the build container (the reference's tests hold no
+golden vectors for this path, SURVEY.md §4, and TensorFlow is not installable):
+  * oracle/ref_py.py runs the reference's evaluation graph itself -- RSF symmetry functions and electrostatics, the
+    instance methods dipole_inference / energy_inference (+ periodic forms), tf.gradients -- unmodified on the eager
+    torch stand-in oracle/tf_shim.py, with seeded weights and non-zero biases; the outputs are stored in
+    tests/golden/ref_python_pins.npz (oracle/make_golden.py) and this module reproduces them to 1e-12 relative
+    (tests/test_oracle.py: test_oracle_equals_reference_graph_*);
+  * descriptor values and Jacobians against the reference's C implementation compiled from /root/reference
+    (oracle/_ref/MolEmb: Make_ANI1_Sym, C_API/MolEmb.cpp:1913-1988; Make_ANI1_Sym_deri, :1844-1911);
+  * central finite differences of its own energy and the closed-form constants of SURVEY.md §8 a11/a13.
 
 Abbreviations: RSF = TensorMol/TFDescriptors/RawSymFunc.py, TMD =
 TensorMol/TFNetworks/TFMolInstanceDirect.py, MGR = TensorMol/TFNetworks/TFMolManage.py.
