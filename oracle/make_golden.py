@@ -209,6 +209,13 @@ def reference_python_pins():
     out["graph_periodic_Ebp_atom"] = np.asarray(r["Ebp_atom"])[:, : len(Z0)]
     out["graph_periodic_charge"] = np.asarray(r["charge"])[:, : len(Z0)]
     out["graph_periodic_gradient"] = np.asarray(r["gradient"])[:, : len(Z0)]       # the rows the manager keeps (TFMolManage.py:1353)
+    # integrators: PeriodicVelocityVerletStep / PeriodicNoseThermostat.step (Simulations/PeriodicMD.py:21-60) on a toy force
+    rs = np.random.RandomState(0)
+    md_lat = np.array([[6.0, 0, 0], [0.5, 6.5, 0], [0, 0.3, 7.0]])
+    md_x0, md_m, md_v0 = rs.rand(9, 3) * 5.0, np.array([0.016, 0.001, 0.001] * 3), 1e-3 * rs.randn(9, 3)
+    md = ref_py.md_pins(md_lat, md_x0, md_m, md_v0, 0.2, 8, {"MDTemp": 300.0, "MDdt": 0.2, "MDThermostat": "Nose"})
+    out.update({"md_lat": md_lat, "md_x0": md_x0, "md_m": md_m, "md_v0": md_v0, "md_nve": md["nve"], "md_nose": md["nose"],
+                "md_nose_v0": md["nose_v0"], "md_ke": md["ke"]})
     tfn = ref_py.tf_namespace({"sigmoid_alpha": P["sigmoid_alpha"], "EECutoffOff": P["EECutoffOff"], "Poly_Width": P["Poly_Width"]})
     out["act_in"] = np.linspace(-2.0, 2.0, 81)
     out["act_out"] = tfn["sigmoid_with_param"](out["act_in"])

@@ -391,5 +391,54 @@ def full_graph_periodic(xyz_tess, Z_tess, nreal, eles, hidden, weights, P):
                 gradient=grad.detach().numpy())
 
 
+def md_namespace(P):
+    """The reference's integrator functions (Simulations/SimpleMD.py:14-129, PeriodicMD.py:21-60), plain numpy."""
+    base = namespace()
+    ns = {"np": np, "PARAMS": dict(P), "IDEALGASR": base["IDEALGASR"], "KineticEnergy": None, "LOGGER": base["LOGGER"]}
+    exec(_defs("TensorMol/Simulations/SimpleMD.py", {"VelocityVerletStep", "KineticEnergy", "Thermostat", "NoseThermostat"}), ns)
+    exec(_defs("TensorMol/Simulations/PeriodicMD.py", {"PeriodicVelocityVerletStep", "PeriodicNoseThermostat"}), ns)
+    return ns
+
+
+class _ToyPeriodicForce:
+    """A PeriodicForce stand-in for the integrator pins: the reference Lattice plus a smooth analytic energy / force
+    (harmonic tethers to the initial positions and a soft pair term), returned in the callback's units
+    (energy Hartree-like scalar, force in J/mol/Angstrom)."""
+
+    def __init__(self, lat, x0):
+        self.lattice = lattice(lat)
+        self.x0 = np.array(x0)
+
+    def __call__(self, x, DoForce=True):
+        d = x - self.x0
+        e = 0.5 * 3.0e5 * float(np.sum(d * d)) + 1.0e4 * float(np.sum(np.sin(x)))
+        f = -(3.0e5 * d + 1.0e4 * np.cos(x))
+        return e, f
+
+
+def md_pins(lat, x0, m, v0, dt, nsteps, P):
+    """nsteps of PeriodicVelocityVerletStep and of PeriodicNoseThermostat.step on the toy force."""
+    ns = md_namespace(P)
+    pf = _ToyPeriodicForce(lat, x0)
+    out = {}
+    x, v, a = np.array(x0), np.array(v0), np.zeros_like(x0)
+    traj = []
+    for _ in range(nsteps):
+        x, v, a, e = ns["PeriodicVelocityVerletStep"](pf, a, x, v, m, dt)
+        traj.append(np.concatenate([x.ravel(), v.ravel(), [e]]))
+    out["nve"] = np.array(traj)
+    vv = np.array(v0)
+    th = ns["PeriodicNoseThermostat"](m, vv)          # rescales vv in place (SimpleMD.py:90-100)
+    out["nose_v0"] = vv.copy()
+    x, v, a = np.array(x0), vv, np.zeros_like(x0)
+    traj = []
+    for _ in range(nsteps):
+        x, v, a, e = th.step(pf, a, x, v, m, dt)
+        traj.append(np.concatenate([x.ravel(), v.ravel(), [e, th.eta]]))
+    out["nose"] = np.array(traj)
+    out["ke"] = np.float64(ns["KineticEnergy"](np.array(v0), m))
+    return out
+
+
 def lattice(latvec):
     return namespace()["Lattice"](np.asarray(latvec, np.float64))

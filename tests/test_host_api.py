@@ -209,3 +209,40 @@ def test_periodic_force_wrapper_and_md():
     md.Prop()
     assert md.md_log.shape == (5, 7) and np.all(np.isfinite(md.x))
     assert np.all(pf.lattice.InLat(md.x) >= -1e-9) and np.all(pf.lattice.InLat(md.x) < 1 + 1e-9)
+
+
+def test_integrators_equal_reference_python():
+    """PeriodicVelocityVerletStep, PeriodicNoseThermostat.step and KineticEnergy of this package against the reference's own
+    functions (Simulations/PeriodicMD.py:21-60, SimpleMD.py:42-129) executed by oracle/ref_py.py on a toy analytic force
+    (pins in tests/golden/ref_python_pins.npz)."""
+    from conftest import load_golden
+    from tensormol_b200 import PARAMS
+    from tensormol_b200.ForceModifiers.Periodic import Lattice
+    from tensormol_b200.Simulations.PeriodicMD import PeriodicNoseThermostat, PeriodicVelocityVerletStep
+    from tensormol_b200.Simulations.SimpleMD import KineticEnergy
+    p = load_golden("ref_python_pins")
+    lat, x0, m, v0 = p["md_lat"], p["md_x0"], p["md_m"], p["md_v0"]
+
+    class Toy:
+        def __init__(self):
+            self.lattice = Lattice(lat)
+
+        def __call__(self, x, DoForce=True):
+            d = x - x0
+            return 0.5 * 3.0e5 * float(np.sum(d * d)) + 1.0e4 * float(np.sum(np.sin(x))), -(3.0e5 * d + 1.0e4 * np.cos(x))
+
+    pf = Toy()
+    assert abs(KineticEnergy(v0, m) - float(p["md_ke"])) <= 1e-12 * float(p["md_ke"])
+    x, v, a = x0.copy(), v0.copy(), np.zeros_like(x0)
+    for row in p["md_nve"]:
+        x, v, a, e = PeriodicVelocityVerletStep(pf, a, x, v, m, 0.2)
+        assert np.abs(x.ravel() - row[:27]).max() <= 1e-12 and np.abs(v.ravel() - row[27:54]).max() <= 1e-14 and abs(e - row[54]) <= 1e-9 * abs(row[54])
+    PARAMS["MDTemp"], PARAMS["MDdt"] = 300.0, 0.2
+    vv = v0.copy()
+    th = PeriodicNoseThermostat(m, vv)
+    assert np.abs(vv - p["md_nose_v0"]).max() <= 1e-15
+    x, v, a = x0.copy(), vv, np.zeros_like(x0)
+    for row in p["md_nose"]:
+        x, v, a, e = th.step(pf, a, x, v, m, 0.2)
+        assert np.abs(x.ravel() - row[:27]).max() <= 1e-12 and np.abs(v.ravel() - row[27:54]).max() <= 1e-14
+        assert abs(th.eta - row[55]) <= 1e-12 * max(1.0, abs(row[55]))
