@@ -20,6 +20,7 @@
 // per lane of one pair channel (2 for the default 8x8 angular grid).  Exponentials use ex2.approx
 // (__expf): relative error < 1e-6 on every term that is not itself < 1e-10 of the row scale.
 #include "tm_internal.h"
+#include <cuda_fp16.h>
 
 #define FULL 0xffffffffu
 #define DESC_WARPS 8
@@ -49,16 +50,26 @@ template <int NE, int OPLT>
 __global__ void __launch_bounds__(DESC_WARPS * 32)
 k_desc(const SAtom* __restrict__ sat, const int32_t* __restrict__ rowsidx, const int32_t* __restrict__ rowslot,
        const int32_t* __restrict__ nbcnt, const uint32_t* __restrict__ nbr, int64_t nrows, const __grid_constant__ DevParams P,
-       float* __restrict__ G, int32_t* __restrict__ flags, int wfloats) {
+       float* __restrict__ G, __half* __restrict__ Ghi, __half* __restrict__ Glo, int32_t* __restrict__ flags, int wfloats) {
   constexpr int NELEP = NE * (NE + 1) / 2;
   extern __shared__ float smem[];
   int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int64_t row = (int64_t)blockIdx.x * DESC_WARPS + warp;
   if (row >= nrows) return;
   float* Grow = G + row * P.Dp;
+  // the tensor-core MLP path takes the descriptor row as two fp16 planes x = hi + lo/2048 (tm_gemm_tc.cu): written here
+  // together with the fp32 row, which saves a separate split pass over G
+  auto put = [&](int i, float v) {
+    Grow[i] = v;
+    if (Ghi) {
+      __half h = __float2half_rn(v);
+      Ghi[row * P.Dp + i] = h;
+      Glo[row * P.Dp + i] = __float2half_rn((v - __half2float(h)) * 2048.0f);
+    }
+  };
   int slot = rowslot[row];
   if (slot < 0) {
-    for (int i = lane; i < P.Dp; i += 32) Grow[i] = 0.f;
+    for (int i = lane; i < P.Dp; i += 32) put(i, 0.f);
     return;
   }
   float* ws = smem + (size_t)warp * wfloats;
@@ -138,7 +149,7 @@ k_desc(const SAtom* __restrict__ sat, const int32_t* __restrict__ rowsidx, const
     if (s < P.nRs_r) {
 #pragma unroll
       for (int q = 0; q < NE; q++)
-        if (q < P.n_ele) Grow[q * P.nRs_r + s] = acc[k][q];
+        if (q < P.n_ele) put(q * P.nRs_r + s, acc[k][q]);
     }
   }
 
@@ -207,11 +218,11 @@ k_desc(const SAtom* __restrict__ sat, const int32_t* __restrict__ rowsidx, const
 #pragma unroll
       for (int k = 0; k < OPLT; k++) {
         int idx = lane + 32 * k;
-        if (idx < P.nsym) Grow[off + q * P.nsym + idx] = ga[q][k];
+        if (idx < P.nsym) put(off + q * P.nsym + idx, ga[q][k]);
       }
     }
   }
-  for (int i = P.D + lane; i < P.Dp; i += 32) Grow[i] = 0.f;
+  for (int i = P.D + lane; i < P.Dp; i += 32) put(i, 0.f);
 }
 
 template <int NE, int OPLT>
@@ -225,9 +236,12 @@ static int launch_desc(tm_ctx* c, const SysView& s) {
     configured = smem;
   }
   int blocks = (int)((s.nrows + DESC_WARPS - 1) / DESC_WARPS);
+  const bool split = c->gemm_mode != TM_GEMM_FP32;
   k_desc<NE, OPLT><<<blocks, DESC_WARPS * 32, smem, c->stream>>>((const SAtom*)c->b_satom.p, (const int32_t*)c->b_rowsidx.p,
                                                                 (const int32_t*)c->b_rowslot.p, (const int32_t*)c->b_nbcnt.p,
                                                                 (const uint32_t*)c->b_nbr.p, s.nrows, P, (float*)c->b_G.p,
+                                                                split ? (__half*)c->b_Gs.p : nullptr,
+                                                                split ? (__half*)c->b_Gs.p + (size_t)s.nrows * P.Dp : nullptr,
                                                                 (int32_t*)c->b_flags.p, (int)wf);
   c->launches++;
   TM_CUDA(cudaGetLastError());
@@ -238,6 +252,8 @@ int tm_launch_desc(tm_ctx* c, const SysView& s) {
   int rc;
   const DevParams& P = c->hp;
   if ((rc = tm_buf(c, c->b_G, (size_t)s.nrows * P.Dp * 4))) return rc;
+  if (c->gemm_mode != TM_GEMM_FP32)
+    if ((rc = tm_buf(c, c->b_Gs, (size_t)2 * s.nrows * P.Dp * 2))) return rc;   // [hi | lo] fp16 planes
   bool small = P.nsym <= 64;
   if (small && P.n_ele == 1) return launch_desc<1, 2>(c, s);
   if (small && P.n_ele == 2) return launch_desc<2, 2>(c, s);

@@ -165,7 +165,7 @@ int tm_launch_gemm(tm_ctx* c, const GemmGroup* groups, int ngroups, const int* r
 
 
 // ------------------------------------------------------------------------------------------------
-// output layer (H_last -> 1) and its backward seed (fp32 mode), and the hi/lo split used by the tcgen05 path
+// output layer (H_last -> 1) and its backward seed (fp32 mode), and the reduction of the fused output layer's partial sums (tensor-core mode)
 // ------------------------------------------------------------------------------------------------
 struct OutTbl {
   const float* w[2][TM_MAX_ELE];
@@ -208,28 +208,6 @@ __global__ void k_out_layer(const __grid_constant__ OutTbl T, const int32_t* __r
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
   if (lane == 0) T.y[net][row] = s + T.b[net][e];
-}
-
-// split-fp16 operand format of the tcgen05 path (tm_gemm_tc.cu): x = hi + lo / 2048
-#define LO_SCALE 2048.0f
-__device__ __forceinline__ void split4(float4 v, uint2& hi, uint2& lo) {
-  __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
-  float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
-  __half2 l0 = __floats2half2_rn((v.x - f0.x) * LO_SCALE, (v.y - f0.y) * LO_SCALE);
-  __half2 l1 = __floats2half2_rn((v.z - f1.x) * LO_SCALE, (v.w - f1.y) * LO_SCALE);
-  hi = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
-  lo = make_uint2(*reinterpret_cast<uint32_t*>(&l0), *reinterpret_cast<uint32_t*>(&l1));
-}
-
-// x (fp32) -> (hi, scaled lo) fp16 planes
-__global__ void k_split_planes(const float* __restrict__ x, __half* __restrict__ hi, __half* __restrict__ lo, int64_t n4) {
-  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n4; t += (int64_t)gridDim.x * blockDim.x) {
-    float4 v = reinterpret_cast<const float4*>(x)[t];
-    uint2 h, l;
-    split4(v, h, l);
-    reinterpret_cast<uint2*>(hi)[t] = h;
-    reinterpret_cast<uint2*>(lo)[t] = l;
-  }
 }
 
 // y[net][row] = b_out + sum of the np partial dot products left by the TM_EPI_ACT_OUT epilogue (fixed order: deterministic)
@@ -286,13 +264,7 @@ int tm_launch_mlp_forward(tm_ctx* c, const SysView& s) {
   int nh = c->desc.n_hidden, ne = c->hp.n_ele;
   int max_tiles = (int)((s.ncent_max + TM_ROW_TILE - 1) / TM_ROW_TILE) + 1;
   const int* rowmeta = (const int*)c->b_rowmeta.p;
-  const size_t gplane = (size_t)s.nrows * c->hp.Dp;
-  if (tc) {
-    int64_t n4 = (int64_t)gplane / 4;
-    int blocks = (int)std::min<int64_t>((n4 + 255) / 256, 148 * 16);
-    k_split_planes<<<blocks, 256, 0, c->stream>>>((const float*)c->b_G.p, (__half*)c->b_Gs.p, (__half*)c->b_Gs.p + gplane, n4);
-    c->launches++;
-  }
+  // (tensor-core mode: k_desc already wrote the descriptor rows as fp16 hi/lo planes into b_Gs)
   for (int l = 0; l < nh; l++) {
     GemmGroup gg[2 * TM_MAX_ELE];
     int ng = 0;

@@ -398,25 +398,34 @@ __global__ void k_rows_scan(int32_t* __restrict__ blkcnt, int nblk, int n_ele, c
                             const GridParams* __restrict__ gp, int32_t* __restrict__ rowmeta) {
   __shared__ int32_t tot[TM_MAX_ELE];
   nblk = min(nblk, (cstart[gp->ncells] + ROWS_BLOCK - 1) / ROWS_BLOCK);
-  int e = threadIdx.x >> 5, lane = threadIdx.x & 31;   // one warp per element, each lane a contiguous run of blocks
+  int e = threadIdx.x >> 5, lane = threadIdx.x & 31;   // one warp per element; a lane owns 32 consecutive blocks of a 1024-block chunk
   if (e < TM_MAX_ELE) {
-    int per = (nblk + 31) / 32;
-    int b0 = lane * per, b1 = min(nblk, b0 + per);
-    int32_t sum = 0;
-    for (int i = b0; i < b1; i++) sum += blkcnt[i * TM_MAX_ELE + e];
-    int32_t inc = sum;
+    int32_t carry = 0;
+    for (int base = 0; base < nblk; base += 1024) {
+      int32_t v[32];
+      int32_t sum = 0;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      int32_t t = __shfl_up_sync(FULL, inc, o);
-      if (lane >= o) inc += t;
+      for (int k = 0; k < 32; k++) {   // all 32 loads in flight (the serial version waited one L2 round trip per block)
+        int i = base + lane * 32 + k;
+        v[k] = (i < nblk) ? blkcnt[i * TM_MAX_ELE + e] : 0;
+        sum += v[k];
+      }
+      int32_t inc = sum;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        int32_t t = __shfl_up_sync(FULL, inc, o);
+        if (lane >= o) inc += t;
+      }
+      int32_t run = carry + inc - sum;
+#pragma unroll
+      for (int k = 0; k < 32; k++) {
+        int i = base + lane * 32 + k;
+        if (i < nblk) blkcnt[i * TM_MAX_ELE + e] = run;
+        run += v[k];
+      }
+      carry += __shfl_sync(FULL, inc, 31);
     }
-    int32_t run = inc - sum;
-    for (int i = b0; i < b1; i++) {
-      int32_t v = blkcnt[i * TM_MAX_ELE + e];
-      blkcnt[i * TM_MAX_ELE + e] = run;
-      run += v;
-    }
-    if (lane == 31) tot[e] = inc;
+    if (lane == 0) tot[e] = carry;
   }
   __syncthreads();
   if (threadIdx.x == 0) {
