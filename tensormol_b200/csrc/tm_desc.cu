@@ -230,10 +230,11 @@ static int launch_desc(tm_ctx* c, const SysView& s) {
   const DevParams& P = c->hp;
   size_t wf = tm_desc_smem_floats_per_warp(P);
   size_t smem = wf * 4 * DESC_WARPS;
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
+  static size_t configured[64] = {};            // per device
+  const int dv = (c->device >= 0 && c->device < 64) ? c->device : 0;
+  if (smem > 48 * 1024 && smem > configured[dv]) {
     TM_CUDA(cudaFuncSetAttribute(k_desc<NE, OPLT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
+    configured[dv] = smem;
   }
   int blocks = (int)((s.nrows + DESC_WARPS - 1) / DESC_WARPS);
   const bool split = c->gemm_mode != TM_GEMM_FP32;

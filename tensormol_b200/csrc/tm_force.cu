@@ -259,7 +259,10 @@ int tm_launch_force(tm_ctx* c, const SysView& s, int flags) {
   int fold = (flags & TM_F_FOLD_IMAGES) ? 1 : 0;
   int blocks = (int)((s.nrows + FORCE_WARPS - 1) / FORCE_WARPS);
   bool small = (P.nAs <= 8 && P.nRs_a <= 8);
-  static size_t conf_small = 0, conf_big = 0;
+  static size_t conf_small_d[64] = {}, conf_big_d[64] = {};   // per device
+  const int dv = (c->device >= 0 && c->device < 64) ? c->device : 0;
+  size_t& conf_small = conf_small_d[dv];
+  size_t& conf_big = conf_big_d[dv];
   if (small) {
     if (smem > 48 * 1024 && smem > conf_small) {
       TM_CUDA(cudaFuncSetAttribute(k_force<8, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -621,8 +621,11 @@ static int get_encode() {
 }
 
 // 2D fp16 tensor [rows][cols] with row pitch ld (elements); box = 64 x box_rows (128 bytes wide), 128B swizzle
-static int make_map(CUtensorMap* m, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
-  static std::map<std::tuple<const void*, int64_t, int64_t, int64_t, int>, CUtensorMap> cache;
+typedef std::map<std::tuple<const void*, int64_t, int64_t, int64_t, int>, CUtensorMap> MapCache;
+
+static int make_map(tm_ctx* c, CUtensorMap* m, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+  if (!c->tc_maps) c->tc_maps = new MapCache();
+  MapCache& cache = *(MapCache*)c->tc_maps;    // per context: buffers (and so the keys) belong to the context
   auto key = std::make_tuple(base, rows, cols, ld, box_rows);
   auto it = cache.find(key);
   if (it != cache.end()) { *m = it->second; return TM_OK; }
@@ -645,10 +648,10 @@ template <int EPI, int ACTK, int NCTA>
 static int launch_tc(tm_ctx* c, const TcParams& P, const int* rowmeta_dev, int total_units_bound) {
   // NCTA = 1: 3 stages x 64 KB; NCTA = 2: 4 stages x 48 KB -- the same 192 KB
   constexpr size_t smem = (size_t)TC_STAGES * (2 * TC_BM * TC_BK * 2 + 2 * TC_BN * TC_BK * 2) + 1024 + 512 + TC_EPI_WARPS * 32 * 32 * 4;
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[64] = {};              // the attribute is per device
+  if (c->device < 0 || c->device >= 64 || !configured[c->device]) {
     TM_CUDA(cudaFuncSetAttribute(k_gemm_tc<EPI, ACTK, NCTA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
+    if (c->device >= 0 && c->device < 64) configured[c->device] = true;
   }
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
@@ -697,7 +700,8 @@ int tm_gemm_tc_launch(tm_ctx* c, const GemmGroup* groups, int ngroups, const int
   const int ncta = (c->gemm_mode == TM_GEMM_TC_SPLIT_PAIR) ? 2 : 1;
   if ((rc = get_encode())) return rc;
   if (ngroups > TC_MAX_GROUPS) { tm_set_error("too many GEMM groups"); return TM_EINVAL; }
-  static TcParams P;   // large; filled per launch (calls on one ctx are serialised by contract)
+  if (!c->tc_params) c->tc_params = new TcParams();
+  TcParams& P = *(TcParams*)c->tc_params;   // large (16 groups x 4 tensor maps); filled per launch, calls on one ctx are serialised by contract
   P.ngroups = ngroups; P.act_kind = c->hp.activation; P.act_alpha = c->hp.act_alpha;
   P.prof = nullptr;
 #ifdef TC_PROFILE
@@ -724,10 +728,10 @@ int tm_gemm_tc_launch(tm_ctx* c, const GemmGroup* groups, int ngroups, const int
     const GemmGroup& g = groups[i];
     if (g.K % TC_BK || g.N % TC_BN || !g.A2 || !g.B2) { tm_set_error("tc gemm: bad group (K=%d N=%d)", g.K, g.N); return TM_EINVAL; }
     TcGroup& T = P.g[i];
-    if ((rc = make_map(&T.mapA_hi, g.A, g.rows_alloc, g.K, g.lda, TC_BM))) return rc;
-    if ((rc = make_map(&T.mapA_lo, g.A2, g.rows_alloc, g.K, g.lda, TC_BM))) return rc;
-    if ((rc = make_map(&T.mapB_hi, g.B, g.N, g.K, g.ldb, TC_BN / ncta))) return rc;   // a CTA of a pair stages half of the B rows
-    if ((rc = make_map(&T.mapB_lo, g.B2, g.N, g.K, g.ldb, TC_BN / ncta))) return rc;
+    if ((rc = make_map(c, &T.mapA_hi, g.A, g.rows_alloc, g.K, g.lda, TC_BM))) return rc;
+    if ((rc = make_map(c, &T.mapA_lo, g.A2, g.rows_alloc, g.K, g.lda, TC_BM))) return rc;
+    if ((rc = make_map(c, &T.mapB_hi, g.B, g.N, g.K, g.ldb, TC_BN / ncta))) return rc;   // a CTA of a pair stages half of the B rows
+    if ((rc = make_map(c, &T.mapB_lo, g.B2, g.N, g.K, g.ldb, TC_BN / ncta))) return rc;
     T.bias = g.bias; T.Hmul_hi = (const __half*)g.Hmul; T.Hmul_lo = (const __half*)g.Hmul2;
     T.C_hi = (__half*)g.C; T.C_lo = (__half*)g.C2; T.C32 = (float*)g.C;
     T.wout = g.wout; T.ypart = g.ypart; T.ystride = g.rows_alloc;
@@ -737,4 +741,11 @@ int tm_gemm_tc_launch(tm_ctx* c, const GemmGroup* groups, int ngroups, const int
   }
   int bound = tiles > 100000 ? 100000 : (int)tiles;
   return ncta == 2 ? launch_tc_epi<2>(c, P, rowmeta_dev, bound, epilogue) : launch_tc_epi<1>(c, P, rowmeta_dev, bound, epilogue);
+}
+
+void tm_gemm_tc_release(tm_ctx* c) {
+  delete (TcParams*)c->tc_params;
+  delete (MapCache*)c->tc_maps;
+  c->tc_params = nullptr;
+  c->tc_maps = nullptr;
 }

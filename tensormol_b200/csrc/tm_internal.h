@@ -163,6 +163,8 @@ struct tm_ctx {
     uint64_t alloc_gen = 0, cfg_gen = 0;
     bool failed = false;         // capture failed for this key: stay eager
   } lg;
+  void* tc_params = nullptr;     // TcParams scratch of tm_gemm_tc.cu (kernel argument block, one per context)
+  void* tc_maps = nullptr;       // tensor-map cache of tm_gemm_tc.cu
   int graphs_on = 1;             // TM_NO_GRAPH=1 in the environment disables the replay
   bool timings_final = false;    // c->last already holds the timings of the last call (graph replay)
 
@@ -218,6 +220,7 @@ struct GemmGroup {
   const float* wout = nullptr;   // TM_EPI_ACT_OUT: output-layer weights [N] and partial sums [2*N/128][rows_alloc]
   float* ypart = nullptr;
 };
+void tm_gemm_tc_release(tm_ctx* c);
 int tm_launch_gemm(tm_ctx* c, const GemmGroup* groups, int ngroups, const int* rowmeta_dev, int max_row_tiles, int epilogue);
 // TM_EPI_ACT_OUT (tensor-core mode, last hidden layer): h = act(z + b) is not stored; the epilogue emits the output layer's
 // partial dot products  ypart[p][row] = sum_cols h*w_out  (p = 128-column half-tile index) and C = w_out * act'(h), the
