@@ -393,3 +393,35 @@ def test_eval_vs_reference_graph_periodic(mode):
     _check_grad(r["gradient"], p["graph_periodic_gradient"])
     assert np.abs(r["charge"][:, :nreal] - p["graph_periodic_charge"]).max() <= 1e-5 * max(np.abs(p["graph_periodic_charge"]).max(), 1e-3)
     assert np.abs(r["Ebp_atom"] - p["graph_periodic_Ebp_atom"]).max() <= 1e-5 * np.abs(p["graph_periodic_Ebp_atom"]).max()
+
+
+def test_edge_cases_empty_single_atom_and_capacity():
+    """Ragged / degenerate input and the capacity errors: an empty molecule and a lone atom inside a padded set evaluate
+    (lone atom = net(0 descriptor), zero force) and agree with the oracle; more than TM_ANG_CAP = 64 atoms inside the
+    angular cutoff of one centre fails loudly with TM_ECAP instead of truncating."""
+    from oracle import oracle_graph as og
+    from tensormol_b200._lib import TMolB200Error
+    eng, W, P = _engine([1, 8], [32, 32], 2)
+    xyzs = np.zeros((3, 4, 3))
+    Zs = np.zeros((3, 4), np.int32)
+    nat = np.array([0, 1, 3])
+    Zs[1, 0] = 8
+    xyzs[2, :3] = [[0.0, 0.0, 0.0], [0.96, 0.0, 0.0], [-0.24, 0.93, 0.0]]
+    Zs[2, :3] = [8, 1, 1]
+    r = eng.evaluate(xyzs, Zs, nat)
+    o = og.Oracle([1, 8], W, P).evaluate(xyzs, Zs, nat)
+    for k in ("Etotal", "Ebp", "Ecc", "Evdw"):
+        _check_energy(r[k], o[k], k)
+    assert r["Etotal"][0] == 0.0 and np.all(r["gradient"][0] == 0.0) and np.all(r["gradient"][1] == 0.0)
+    _check_grad(r["gradient"], o["gradient"])
+    # 80 hydrogens inside a 1.2 A ball around an oxygen: > 64 angular neighbours
+    rs = np.random.RandomState(0)
+    pts = rs.randn(80, 3)
+    pts *= (1.2 * rs.rand(80, 1) ** (1 / 3)) / np.linalg.norm(pts, axis=1, keepdims=True)
+    X = np.concatenate([[[0.0, 0.0, 0.0]], pts])[None]
+    Z = np.array([[8] + [1] * 80], np.int32)
+    with pytest.raises(TMolB200Error, match="angular"):
+        eng.evaluate(X, Z, np.array([81]))
+    # the context stays usable afterwards
+    r2 = eng.evaluate(xyzs, Zs, nat)
+    assert np.array_equal(r2["Etotal"], r["Etotal"])
