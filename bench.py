@@ -160,6 +160,7 @@ def run_b200(args, rank, world, local_rank):
     g_t = torch.zeros(natom, 3, dtype=torch.float64, device=dev)
     flush = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
     slab = SlabEvaluator(EngineSlabBackend(eng), natom, rank, world, dev, dist) if world > 1 else None
+    p2p = bool(slab is not None and args.p2p and slab.enable_p2p())
 
     def step_resident():
         if slab is None:
@@ -266,8 +267,8 @@ def run_b200(args, rank, world, local_rank):
             "scaling": "strong" if world > 1 else "weak", "vs_baseline": None,
             "dtype": {0: "f32", 1: "f16x2-split (fp32 accumulate)"}[args.gemm_mode], "data": "synthetic",
             "config": {"workload": f"{natom}-atom periodic water box (C4: {args.nx}^3 waters, L={lat[0, 0]:.3f} A, 27 images), BP+EE single-point energy+force, nets {HIDDEN}, random-init weights seed 0",
-                       "l2": "flushed between timed iterations (512 MiB write)", "parallelism": f"slab{world}" if world > 1 else "single",
-                       "gemm_mode": args.gemm_mode, "launch": ("CUDA graph replay of the step" if world == 1 else "one CUDA graph per phase, eager NCCL all-reduces between") if args.graph else "kernel by kernel"},
+                       "l2": "flushed between timed iterations (512 MiB write)", "parallelism": f"slab{world}" if world > 1 else "single", "exchange": ("peer-memory stores + device flags" if p2p else "3 NCCL all-reduces" + (f" (peer memory unavailable: {getattr(slab, 'p2p_error', '')[:120]})" if args.p2p and not p2p else "")) if world > 1 else None,
+                       "gemm_mode": args.gemm_mode, "launch": ("CUDA graph replay of the step" if (world == 1 or p2p) else "one CUDA graph per phase, eager NCCL all-reduces between") if args.graph else "kernel by kernel"},
             "e2e": {"value": e2e_val, "unit": "atom-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches) * args.steps if launches else None,
             "clocks": sampler.summary(), "Etotal": e_tot}
@@ -304,6 +305,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--nx", type=int, default=20, help="waters per box edge (20 -> 24,000 atoms)")
     ap.add_argument("--gemm-mode", type=int, default=1, help="0 = fp32 FFMA, 1 = tcgen05 split-fp16 (default)")
+    ap.add_argument("--p2p", type=int, default=1, help="N > 1: 1 = exchange between the slab phases by peer-memory stores over NVLink (default), 0 = NCCL all-reduces")
     ap.add_argument("--graph", type=int, default=1, help="1 = the resident step is replayed from a CUDA graph (default), 0 = launched kernel by kernel")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -188,6 +188,17 @@ int tm_slab_phase_a(tm_ctx* ctx, const double* xyz_dev, const int32_t* Z_dev, in
 int tm_slab_phase_b(tm_ctx* ctx, const double* qraw_dev, double* e_dev /* [6]: Etot,Ebp,Ecc,Evdw,sum_dedq,unused */);
 int tm_slab_phase_c(tm_ctx* ctx, const double* e_dev, int flags, double* grad_dev);
 
+/* Peer-memory exchange for the slab phases (one process per GPU of an NVLink/NVSwitch box; no reference counterpart).
+ * Every rank owns a "symmetric" device buffer of tm_slab_p2p_bytes(world, nreal) bytes, ZERO-FILLED, that all peers can
+ * address (CUDA IPC / torch symmetric memory); peer_base[r] is rank r's buffer as seen from this process.  Once set, the
+ * three phases no longer need host collectives between them: the kernels that produce q_raw, the energy partials and
+ * the force partials store them straight into every peer's buffer over NVLink, signal a per-peer flag, and the
+ * consuming phase starts with a device-side wait on the local flag (bounded spin: a peer that never arrives raises
+ * device flag 32, reported by tm_sync).  qraw_dev of phase A/B is then ignored, e_dev / grad_dev of phase C receive the
+ * fully reduced energies [6] and dE/dx [nreal*3].  world <= 16.  tm_slab_p2p_setup(ctx, 0, ...) switches it off. */
+int64_t tm_slab_p2p_bytes(int world, int64_t nreal);
+int tm_slab_p2p_setup(tm_ctx* ctx, int world, int rank, int64_t nreal, void* const* peer_base);
+
 int tm_get_timings(tm_ctx* ctx, tm_timings* t);
 /* synchronise ctx's stream (for the _dev entry points) */
 int tm_sync(tm_ctx* ctx);

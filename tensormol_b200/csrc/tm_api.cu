@@ -536,6 +536,7 @@ static int check_flags(tm_ctx* c) {
   TM_CUDA(cudaStreamSynchronize(c->stream));
   c->last_flags = f[0];
   if (f[0] & 2) { tm_set_error("more than %d radial neighbours of one centre", TM_NB_STRIDE); return TM_ECAP; }
+  if (f[0] & 32) { tm_set_error("slab exchange: a peer rank never signalled (timed out after ~2 s)"); return TM_ECUDA; }
   if (f[0] & 8) { tm_set_error("coordinates are not wrapped into the cell (apply Lattice.ModuloLattice before tm_eval_lattice)"); return TM_EINVAL; }
   if (f[0] & 4) { tm_set_error("more than %d neighbours inside the angular cutoff of one centre", TM_ANG_CAP); return TM_ECAP; }
   return TM_OK;
@@ -936,9 +937,134 @@ __global__ void k_slab_e(const double* __restrict__ molacc, double* __restrict__
 }
 __global__ void k_slab_set_dedq(double* __restrict__ molacc, const double* __restrict__ e) { molacc[5] = e[4]; }
 
+// ---- peer-memory exchange (see include/tmolb200.h) ---------------------------------------------------------------------
+// symmetric buffer layout: [ q_raw f64[nreal] | e partials f64[16][8] | force partials f32[world][3 nreal] | flags ]
+// flags (uint32, 64 B apart): [0..2] arrival counters of the three exchanges, [4..6] the epochs this rank has waited for.
+struct PeerPtrs { char* p[16]; };
+
+static void p2p_layout(int world, int64_t nreal, int64_t* off_q, int64_t* off_e, int64_t* off_g, int64_t* off_flag, int64_t* total) {
+  auto up = [](int64_t v) { return (v + 255) / 256 * 256; };
+  int64_t o = 0;
+  *off_q = o; o += up(nreal * 8);
+  *off_e = o; o += up(16 * 8 * 8);
+  *off_g = o; o += up((int64_t)world * ((3 * nreal + 3) / 4 * 4) * 4);   // per-rank stride padded to 16 bytes
+  *off_flag = o; o += 1024;
+  *total = o;
+}
+
+extern "C" int64_t tm_slab_p2p_bytes(int world, int64_t nreal) {
+  int64_t a, b, c2, d, t;
+  p2p_layout(world, nreal, &a, &b, &c2, &d, &t);
+  return t;
+}
+
+static int p2p_preload(tm_ctx* c);
+
+extern "C" int tm_slab_p2p_setup(tm_ctx* c, int world, int rank, int64_t nreal, void* const* peer_base) {
+  if (!c) { tm_set_error("tm_slab_p2p_setup: null context"); return TM_EINVAL; }
+  c->cfg_gen++;
+  if (world <= 1 || !peer_base) { c->p2p = tm_ctx::P2P(); return TM_OK; }
+  if (world > 16 || rank < 0 || rank >= world || nreal < 1) { tm_set_error("tm_slab_p2p_setup: bad argument"); return TM_EINVAL; }
+  tm_ctx::P2P q;
+  q.on = 1; q.world = world; q.rank = rank; q.nreal = nreal;
+  for (int r = 0; r < world; r++) {
+    if (!peer_base[r]) { tm_set_error("tm_slab_p2p_setup: null peer buffer %d", r); return TM_EINVAL; }
+    q.base[r] = (char*)peer_base[r];
+  }
+  int64_t total;
+  p2p_layout(world, nreal, &q.off_q, &q.off_e, &q.off_g, &q.off_flag, &total);
+  c->p2p = q;
+  return p2p_preload(c);
+}
+
+static PeerPtrs peer_ptrs(const tm_ctx* c, int64_t off) {
+  PeerPtrs pp;
+  for (int r = 0; r < 16; r++) pp.p[r] = (r < c->p2p.world) ? c->p2p.base[r] + off : nullptr;
+  return pp;
+}
+
+// q_raw of the owned centres, stored into every peer's copy (each slot has exactly one owner: no reduction needed)
+__global__ void k_owned_qraw_p2p(const float* __restrict__ y, const int32_t* __restrict__ rowslot, int64_t nrows, PeerPtrs q, int world) {
+  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < nrows; r += (int64_t)gridDim.x * blockDim.x) {
+    int s = rowslot[r];
+    if (s < 0) continue;
+    double v = (double)y[r];
+    for (int p = 0; p < world; p++) ((double*)q.p[p])[s] = v;
+  }
+}
+// this rank's energy partials into slot [rank] of every peer
+__global__ void k_slab_e_p2p(const double* __restrict__ molacc, int add_ecc, PeerPtrs e, int world, int rank) {
+  int p = threadIdx.x;
+  if (p >= world) return;
+  double* d = (double*)e.p[p] + 8 * rank;
+  d[0] = 0.0; d[1] = molacc[1]; d[2] = add_ecc ? molacc[2] : 0.0; d[3] = molacc[3]; d[4] = molacc[5]; d[5] = 0.0;
+}
+// this rank's force partial (fp32, every atom: zeros outside its slab + halo) into slot [rank] of every peer
+__global__ void k_push_grad_p2p(const float* __restrict__ F, int64_t n3, int64_t stride, PeerPtrs g, int world, int rank) {
+  int64_t n4 = n3 / 4;     // 3*nreal floats, float4 body + scalar tail; stride = n3 rounded up to 4 floats
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n4; t += (int64_t)gridDim.x * blockDim.x) {
+    float4 v = reinterpret_cast<const float4*>(F)[t];
+    for (int p = 0; p < world; p++) reinterpret_cast<float4*>((float*)g.p[p] + (int64_t)rank * stride)[t] = v;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n3 & 3)) {
+    int64_t t = n4 * 4 + threadIdx.x;
+    for (int p = 0; p < world; p++) ((float*)g.p[p] + (int64_t)rank * stride)[t] = F[t];
+  }
+}
+// all of this device's earlier stores are out: bump arrival counter `which` on every peer (one thread per peer)
+__global__ void k_p2p_signal(PeerPtrs f, int world, int which) {
+  __threadfence_system();
+  int p = threadIdx.x;
+  if (p < world) atomicAdd_system((unsigned int*)(f.p[p]) + 16 * which, 1u);
+}
+// wait until every rank has signalled the next epoch of exchange `which` (epoch kept on the device: graph replayable)
+__global__ void k_p2p_wait(char* flags, int world, int which, int32_t* errflags) {
+  volatile unsigned int* cnt = (volatile unsigned int*)flags + 16 * which;
+  unsigned int* epoch = (unsigned int*)flags + 16 * (4 + which);
+  unsigned int target = (*epoch + 1u) * (unsigned int)world;
+  long long t0 = clock64();
+  while ((int)(*cnt - target) < 0) {
+    if (clock64() - t0 > 4000000000ll) { atomicOr(errflags, 32); break; }   // ~2 s: a peer never arrived
+    __nanosleep(200);
+  }
+  *epoch += 1u;
+  __threadfence_system();
+}
+// sum of the energy partials -> molacc[5] (sum dE/dq over all ranks) and the reduced energies
+__global__ void k_slab_reduce_e(const double* __restrict__ eparts, int world, double* __restrict__ molacc, double* __restrict__ e_out) {
+  double s[6] = {0, 0, 0, 0, 0, 0};
+  for (int r = 0; r < world; r++)
+    for (int k = 0; k < 6; k++) s[k] += eparts[8 * r + k];
+  molacc[5] = s[4];
+  s[0] = s[1] + s[2] + s[3];
+  for (int k = 0; k < 6; k++) e_out[k] = s[k];
+}
+__global__ void k_sum_grad_p2p(const float* __restrict__ gparts, int world, int64_t n3, int64_t stride, double* __restrict__ out) {
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n3; t += (int64_t)gridDim.x * blockDim.x) {
+    double s = 0.0;
+    for (int r = 0; r < world; r++) s += (double)gparts[(int64_t)r * stride + t];
+    out[t] = s;
+  }
+}
+
+static int p2p_preload(tm_ctx* c) {
+  // load the exchange kernels now: with lazy module loading the FIRST launch of a kernel can wait for the device to
+  // drain, and a device that is spinning in k_p2p_wait only drains when its peers make progress
+  cudaFuncAttributes fa;
+  TM_CUDA(cudaSetDevice(c->device));
+  TM_CUDA(cudaFuncGetAttributes(&fa, k_owned_qraw_p2p));
+  TM_CUDA(cudaFuncGetAttributes(&fa, k_slab_e_p2p));
+  TM_CUDA(cudaFuncGetAttributes(&fa, k_push_grad_p2p));
+  TM_CUDA(cudaFuncGetAttributes(&fa, k_p2p_signal));
+  TM_CUDA(cudaFuncGetAttributes(&fa, k_p2p_wait));
+  TM_CUDA(cudaFuncGetAttributes(&fa, k_slab_reduce_e));
+  TM_CUDA(cudaFuncGetAttributes(&fa, k_sum_grad_p2p));
+  return TM_OK;
+}
+
 extern "C" int tm_slab_phase_a(tm_ctx* c, const double* xyz_dev, const int32_t* Z_dev, int64_t nreal, const double* lattice, int ntess,
                                int rank, int world, double* qraw_dev) {
-  if (!c || !xyz_dev || !Z_dev || !lattice || !qraw_dev || world < 1 || rank < 0 || rank >= world) { tm_set_error("tm_slab_phase_a: bad argument"); return TM_EINVAL; }
+  if (!c || !xyz_dev || !Z_dev || !lattice || (!qraw_dev && !c->p2p.on) || world < 1 || rank < 0 || rank >= world) { tm_set_error("tm_slab_phase_a: bad argument"); return TM_EINVAL; }
   int rc;
   TM_CUDA(cudaSetDevice(c->device));
   if ((rc = check_weights(c))) return rc;
@@ -964,20 +1090,34 @@ extern "C" int tm_slab_phase_a(tm_ctx* c, const double* xyz_dev, const int32_t* 
   if ((rc = stage_a(c, s))) return rc;
   if ((rc = tm_launch_mlp_backward(c, s))) return rc;
   cudaEventRecord(c->ev[6], c->stream);
-  TM_CUDA(cudaMemsetAsync(qraw_dev, 0, (size_t)nreal * 8, c->stream));
-  k_owned_qraw<<<nblk(s.nrows), 256, 0, c->stream>>>((const float*)c->b_y[TM_NET_CHARGE].p, (const int32_t*)c->b_rowslot.p, s.nrows, qraw_dev);
-  c->launches++;
+  if (c->p2p.on) {
+    if (c->p2p.world != world || c->p2p.rank != rank || c->p2p.nreal != nreal) { tm_set_error("tm_slab_phase_a: does not match tm_slab_p2p_setup"); return TM_EINVAL; }
+    k_owned_qraw_p2p<<<nblk(s.nrows), 256, 0, c->stream>>>((const float*)c->b_y[TM_NET_CHARGE].p, (const int32_t*)c->b_rowslot.p, s.nrows,
+                                                          peer_ptrs(c, c->p2p.off_q), world);
+    k_p2p_signal<<<1, 32, 0, c->stream>>>(peer_ptrs(c, c->p2p.off_flag), world, 0);
+    c->launches += 2;
+  } else {
+    TM_CUDA(cudaMemsetAsync(qraw_dev, 0, (size_t)nreal * 8, c->stream));
+    k_owned_qraw<<<nblk(s.nrows), 256, 0, c->stream>>>((const float*)c->b_y[TM_NET_CHARGE].p, (const int32_t*)c->b_rowslot.p, s.nrows, qraw_dev);
+    c->launches++;
+  }
   TM_CUDA(cudaGetLastError());
   return TM_OK;
 }
 
 extern "C" int tm_slab_phase_b(tm_ctx* c, const double* qraw_dev, double* e_dev) {
-  if (!c || !qraw_dev || !e_dev) { tm_set_error("tm_slab_phase_b: bad argument"); return TM_EINVAL; }
+  if (!c || ((!qraw_dev || !e_dev) && !c->p2p.on)) { tm_set_error("tm_slab_phase_b: bad argument"); return TM_EINVAL; }
   int rc;
   TM_CUDA(cudaSetDevice(c->device));
   SysView s = c->slab_view;
   int64_t nq = s.nreal;
   if ((rc = tm_buf(c, c->b_q, (size_t)nq * 8 * 2))) return rc;
+  if (c->p2p.on) {   // every owner has stored its charges into this rank's copy once all ranks have signalled
+    char* mine = c->p2p.base[c->p2p.rank];
+    k_p2p_wait<<<1, 1, 0, c->stream>>>(mine + c->p2p.off_flag, c->p2p.world, 0, (int32_t*)c->b_flags.p);
+    c->launches++;
+    qraw_dev = (const double*)(mine + c->p2p.off_q);
+  }
   TM_CUDA(cudaMemcpyAsync(c->b_q.p, qraw_dev, (size_t)nq * 8, cudaMemcpyDeviceToDevice, c->stream));
   SysView s2 = s;
   s2.slab_world = 2;   // any value > 1: tm_launch_charges then takes qraw from b_q instead of scattering its own rows
@@ -985,7 +1125,13 @@ extern "C" int tm_slab_phase_b(tm_ctx* c, const double* qraw_dev, double* e_dev)
   if ((rc = tm_launch_pair(c, s, TM_F_FORCE | TM_F_VDW))) return rc;
   k_ebp<<<(int)((s.nrows + 255) / 256), 256, 0, c->stream>>>((const float*)c->b_y[TM_NET_ENERGY].p, (const int32_t*)c->b_rowslot.p, s.nrows, s.maxnatom,
                                                             nullptr, (double*)c->b_molacc.p);
-  k_slab_e<<<1, 1, 0, c->stream>>>((const double*)c->b_molacc.p, e_dev, c->hp.add_ecc);
+  if (c->p2p.on) {
+    k_slab_e_p2p<<<1, 32, 0, c->stream>>>((const double*)c->b_molacc.p, c->hp.add_ecc, peer_ptrs(c, c->p2p.off_e), c->p2p.world, c->p2p.rank);
+    k_p2p_signal<<<1, 32, 0, c->stream>>>(peer_ptrs(c, c->p2p.off_flag), c->p2p.world, 1);
+    c->launches++;
+  } else {
+    k_slab_e<<<1, 1, 0, c->stream>>>((const double*)c->b_molacc.p, e_dev, c->hp.add_ecc);
+  }
   c->launches += 2;
   cudaEventRecord(c->ev[5], c->stream);
   TM_CUDA(cudaGetLastError());
@@ -997,12 +1143,28 @@ extern "C" int tm_slab_phase_c(tm_ctx* c, const double* e_dev, int flags, double
   int rc;
   TM_CUDA(cudaSetDevice(c->device));
   SysView s = c->slab_view;
+  if (c->p2p.on) {
+    char* mine = c->p2p.base[c->p2p.rank];
+    k_p2p_wait<<<1, 1, 0, c->stream>>>(mine + c->p2p.off_flag, c->p2p.world, 1, (int32_t*)c->b_flags.p);
+    k_slab_reduce_e<<<1, 1, 0, c->stream>>>((const double*)(mine + c->p2p.off_e), c->p2p.world, (double*)c->b_molacc.p, (double*)e_dev);
+    c->launches += 2;
+  } else
   k_slab_set_dedq<<<1, 1, 0, c->stream>>>((double*)c->b_molacc.p, e_dev);
   k_u<<<nblk(s.nrows), 256, 0, c->stream>>>((const double*)c->b_dedq.p, (const double*)c->b_molacc.p, (const double*)c->b_natom.p,
                                             (const int32_t*)c->b_rowslot.p, s.nrows, s.maxnatom, c->hp.add_ecc, (float*)c->b_u.p);
   c->launches += 2;
   if ((rc = tm_launch_force(c, s, flags))) return rc;
-  k_f2d<<<nblk(3 * s.nreal), 256, 0, c->stream>>>((const float*)c->b_F.p, grad_dev, 3 * s.nreal);
+  if (c->p2p.on) {
+    char* mine = c->p2p.base[c->p2p.rank];
+    int64_t n3 = 3 * s.nreal, stride = (n3 + 3) / 4 * 4;
+    k_push_grad_p2p<<<nblk(n3 / 4 + 1), 256, 0, c->stream>>>((const float*)c->b_F.p, n3, stride, peer_ptrs(c, c->p2p.off_g), c->p2p.world, c->p2p.rank);
+    k_p2p_signal<<<1, 32, 0, c->stream>>>(peer_ptrs(c, c->p2p.off_flag), c->p2p.world, 2);
+    k_p2p_wait<<<1, 1, 0, c->stream>>>(mine + c->p2p.off_flag, c->p2p.world, 2, (int32_t*)c->b_flags.p);
+    k_sum_grad_p2p<<<nblk(n3), 256, 0, c->stream>>>((const float*)(mine + c->p2p.off_g), c->p2p.world, n3, stride, grad_dev);
+    c->launches += 3;
+  } else {
+    k_f2d<<<nblk(3 * s.nreal), 256, 0, c->stream>>>((const float*)c->b_F.p, grad_dev, 3 * s.nreal);
+  }
   c->launches++;
   cudaEventRecord(c->ev[7], c->stream);
   cudaEventRecord(c->ev[8], c->stream);

@@ -168,6 +168,14 @@ struct tm_ctx {
   int graphs_on = 1;             // TM_NO_GRAPH=1 in the environment disables the replay
   bool timings_final = false;    // c->last already holds the timings of the last call (graph replay)
 
+  // peer-memory exchange of the slab phases (tm_slab_p2p_setup)
+  struct P2P {
+    int on = 0, world = 1, rank = 0;
+    int64_t nreal = 0;
+    char* base[16] = {};          // every rank's symmetric buffer as addressable from this device
+    int64_t off_q = 0, off_e = 0, off_g = 0, off_flag = 0;
+  } p2p;
+
   // slab state
   int slab_rank = 0, slab_world = 1;
   int64_t cur_nslots = 0, cur_nreal = 0, cur_nmol = 0, cur_maxnatom = 0, cur_ncent = 0, cur_nrows = 0;

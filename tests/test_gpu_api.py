@@ -290,3 +290,76 @@ def test_slab_phases_emulated_ranks_match_single_call(world):
     assert abs(etot - ref["Etotal"][0]) <= 5e-7 * abs(ref["Etotal"][0])
     assert abs(e[2] - ref["Ecc"][0]) <= 1e-6 * max(abs(ref["Ecc"][0]), 1e-3)
     assert np.abs(g - ref["gradient"][0]).max() <= 2e-6 * np.abs(ref["gradient"]).max() + 1e-9
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_slab_peer_memory_exchange_on_one_gpu(world):
+    """The peer-memory form of the slab phases (tm_slab_p2p_setup): `world` contexts on ONE GPU, each on its own stream,
+    exchange q_raw / energy partials / force partials through each other's "symmetric" buffers with device-side
+    signal/wait flags, no host collective.  Two consecutive steps (the flag epochs advance) reproduce tm_eval_lattice."""
+    import ctypes as C
+    import torch
+    from oracle import oracle_graph as og
+    from tensormol_b200.engine import Engine, random_weights
+    from tensormol_b200.parallel import EngineSlabBackend
+    from tensormol_b200._lib import TM_F_FORCE, TM_F_VDW
+    from tensormol_b200.SystemBuilders import wrap_into_cell
+    Z, X, lat = water_box(5, jitter=0.03)
+    n = len(Z)
+    P = og.default_params()
+    hidden = [64, 48]
+    W = random_weights([1, 8], 256, hidden, 3)
+    ref_eng = Engine([1, 8], hidden, P)
+    ref_eng.set_weights(W)
+    dev = torch.device("cuda", 0)
+    backs, streams, bufs = [], [], []
+    for r in range(world):
+        e = Engine([1, 8], hidden, P)
+        e.set_weights(W)
+        st = torch.cuda.Stream(device=dev)
+        e.set_stream(C.c_void_p(st.cuda_stream))
+        backs.append(EngineSlabBackend(e))
+        streams.append(st)
+    zt = torch.tensor(Z, dtype=torch.int32, device=dev)
+    es = [torch.zeros(6, dtype=torch.float64, device=dev) for _ in range(world)]
+    gs = [torch.zeros(n, 3, dtype=torch.float64, device=dev) for _ in range(world)]
+    # one ordinary (host-collective form) pass per context first, so that every workspace buffer exists: an allocation
+    # may wait for the device, and in this ONE-host-thread emulation that would wait for a peer whose work is not
+    # enqueued yet.  Real ranks are separate processes on separate GPUs.
+    xt = torch.tensor(wrap_into_cell(X, lat), dtype=torch.float64, device=dev)
+    qtmp = torch.zeros(n, dtype=torch.float64, device=dev)
+    for r, b in enumerate(backs):
+        b.slab_phase_a(xt, zt, n, lat, 1, r, world, qtmp)
+        b.slab_phase_b(qtmp, es[r])
+        b.slab_phase_c(es[r], TM_F_FORCE | TM_F_VDW, gs[r])
+        b.eng.sync()
+    nbytes = backs[0].p2p_bytes(world, n)
+    bufs = [torch.zeros(nbytes, dtype=torch.uint8, device=dev) for _ in range(world)]
+    torch.cuda.synchronize()
+    for r, b in enumerate(backs):
+        b.p2p_setup(world, r, n, [t.data_ptr() for t in bufs])
+    rs = np.random.RandomState(1)
+    for step in range(3):
+        Xs = wrap_into_cell(X + 0.02 * step * rs.randn(*X.shape), lat)
+        ref = ref_eng.evaluate_lattice(Xs, Z, lat, 1)
+        xt = torch.tensor(Xs, dtype=torch.float64, device=dev)
+        torch.cuda.synchronize()
+        # launch order: phase by phase over the ranks, everything asynchronous; the waits resolve on the device
+        for r, b in enumerate(backs):
+            b.slab_phase_a(xt, zt, n, lat, 1, r, world, es[r])        # qraw argument unused in this mode
+        for r, b in enumerate(backs):
+            b.slab_phase_b(es[r], es[r])
+        for r, b in enumerate(backs):
+            b.slab_phase_c(es[r], TM_F_FORCE | TM_F_VDW, gs[r])
+        for r, b in enumerate(backs):
+            try:
+                b.eng.sync()                                          # also surfaces a wait time-out (flag 32)
+            except Exception as ex:
+                raise AssertionError(f"step {step} rank {r}: {ex}")
+        for r in range(world):
+            e = es[r].cpu().numpy()
+            assert abs(e[0] - ref["Etotal"][0]) <= 5e-7 * abs(ref["Etotal"][0]), (step, r)
+            assert abs(e[1] - ref["Ebp"][0]) <= 5e-7 * abs(ref["Ebp"][0])
+            assert abs(e[2] - ref["Ecc"][0]) <= 1e-6 * abs(ref["Ecc"][0]) + 1e-9
+            assert abs(e[3] - ref["Evdw"][0]) <= 5e-7 * abs(ref["Evdw"][0])
+            assert np.abs(gs[r].cpu().numpy() - ref["gradient"][0]).max() <= 2e-6 * np.abs(ref["gradient"]).max()
