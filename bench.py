@@ -217,6 +217,7 @@ def run_b200(args, rank, world, local_rank):
         step_timed()
         b.record()
     barrier()
+    eng.sync()                             # raises if a device flag was set (capacity, unwrapped input, exchange time-out)
     ms = sum(a.elapsed_time(b) for a, b in evs)
     tms = torch.tensor([ms], dtype=torch.float64, device=dev)
     if dist is not None:

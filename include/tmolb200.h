@@ -193,7 +193,7 @@ int tm_slab_phase_c(tm_ctx* ctx, const double* e_dev, int flags, double* grad_de
  * address (CUDA IPC / torch symmetric memory); peer_base[r] is rank r's buffer as seen from this process.  Once set, the
  * three phases no longer need host collectives between them: the kernels that produce q_raw, the energy partials and
  * the force partials store them straight into every peer's buffer over NVLink, signal a per-peer flag, and the
- * consuming phase starts with a device-side wait on the local flag (bounded spin: a peer that never arrives raises
+ * consuming phase starts with a device-side wait on the local flag (bounded spin of about 8 s: a peer that never arrives raises
  * device flag 32, reported by tm_sync).  qraw_dev of phase A/B is then ignored, e_dev / grad_dev of phase C receive the
  * fully reduced energies [6] and dE/dx [nreal*3].  world <= 16.  tm_slab_p2p_setup(ctx, 0, ...) switches it off. */
 int64_t tm_slab_p2p_bytes(int world, int64_t nreal);

@@ -536,7 +536,7 @@ static int check_flags(tm_ctx* c) {
   TM_CUDA(cudaStreamSynchronize(c->stream));
   c->last_flags = f[0];
   if (f[0] & 2) { tm_set_error("more than %d radial neighbours of one centre", TM_NB_STRIDE); return TM_ECAP; }
-  if (f[0] & 32) { tm_set_error("slab exchange: a peer rank never signalled (timed out after ~2 s)"); return TM_ECUDA; }
+  if (f[0] & 32) { tm_set_error("slab exchange: a peer rank never signalled (timed out after ~8 s)"); return TM_ECUDA; }
   if (f[0] & 8) { tm_set_error("coordinates are not wrapped into the cell (apply Lattice.ModuloLattice before tm_eval_lattice)"); return TM_EINVAL; }
   if (f[0] & 4) { tm_set_error("more than %d neighbours inside the angular cutoff of one centre", TM_ANG_CAP); return TM_ECAP; }
   return TM_OK;
@@ -1024,7 +1024,7 @@ __global__ void k_p2p_wait(char* flags, int world, int which, int32_t* errflags)
   unsigned int target = (*epoch + 1u) * (unsigned int)world;
   long long t0 = clock64();
   while ((int)(*cnt - target) < 0) {
-    if (clock64() - t0 > 4000000000ll) { atomicOr(errflags, 32); break; }   // ~2 s: a peer never arrived
+    if (clock64() - t0 > 16000000000ll) { atomicOr(errflags, 32); break; }   // ~8 s: a peer never arrived
     __nanosleep(200);
   }
   *epoch += 1u;
