@@ -448,6 +448,7 @@ static SysView make_view(tm_ctx* c, int64_t nslots, int64_t nmol, int64_t maxnat
   s.slab_rank = 0; s.slab_world = 1;
   s.slab_g[0] = s.slab_g[1] = s.slab_g[2] = 0.0;
   s.window_on = 0; s.win_lo = 0.0; s.win_hi = 0.0;
+  s.win_ntess = 0; s.win_ilo = -1000; s.win_ihi = 1000;
   s.grid_host = 0;
   memset(&s.hgrid, 0, sizeof(s.hgrid));
   return s;
@@ -701,7 +702,8 @@ __global__ void k_set_lattice(LatArgs a, double* __restrict__ lat, double* __res
   if (threadIdx.x == 0) inv_n[0] = a.v[9];
 }
 
-static int prepare_lattice(tm_ctx* c, const double* xyz_dev, const int32_t* Z_dev, int64_t nreal, const double* lattice, int ntess, SysView* sv) {
+static int prepare_lattice(tm_ctx* c, const double* xyz_dev, const int32_t* Z_dev, int64_t nreal, const double* lattice, int ntess, SysView* sv,
+                           int ilo = -1000, int ihi = 1000) {
   int rc;
   if (ntess < 1 || ntess > 8) { tm_set_error("ntess must be 1..8"); return TM_EINVAL; }
   int64_t nslots = tess_count(nreal, ntess);
@@ -715,7 +717,7 @@ static int prepare_lattice(tm_ctx* c, const double* xyz_dev, const int32_t* Z_de
   la.v[9] = 1.0 / (double)nreal;
   k_set_lattice<<<1, 32, 0, c->stream>>>(la, (double*)c->b_lattice.p, (double*)c->b_natom.p);
   c->launches++;
-  if ((rc = tm_launch_tessellate(c, xyz_dev, Z_dev, nreal, (const double*)c->b_lattice.p, ntess))) return rc;
+  if ((rc = tm_launch_tessellate(c, xyz_dev, Z_dev, nreal, (const double*)c->b_lattice.p, ntess, ilo, ihi))) return rc;
   *sv = make_view(c, nslots, 1, nslots, nreal, 1, nreal);
   // inverse lattice first row (for slab ownership): frac_a = pos . g
   const double* L = lattice;
@@ -1072,18 +1074,32 @@ extern "C" int tm_slab_phase_a(tm_ctx* c, const double* xyz_dev, const int32_t* 
   c->timings_final = false;
   cudaEventRecord(c->ev[0], c->stream);
   SysView s;
-  if ((rc = prepare_lattice(c, xyz_dev, Z_dev, nreal, lattice, ntess, &s))) return rc;
+  // the slab window along the first lattice vector: the owned slab plus the largest interaction range on both sides.
+  // Everything an owned centre can interact with lies inside; slots outside are not binned, and image blocks whose
+  // whole range [i, i+1) misses the window are not even tessellated (the input must be wrapped into the cell).
+  int ilo = -1000, ihi = 1000;
+  double win_lo = 0.0, win_hi = 0.0;
+  if (world > 1) {
+    const double* L = lattice;
+    double det = L[0] * (L[4] * L[8] - L[5] * L[7]) - L[1] * (L[3] * L[8] - L[5] * L[6]) + L[2] * (L[3] * L[7] - L[4] * L[6]);
+    if (fabs(det) < 1e-12) { tm_set_error("singular lattice"); return TM_EINVAL; }
+    double g0 = (L[4] * L[8] - L[5] * L[7]) / det, g1 = -(L[3] * L[8] - L[5] * L[6]) / det, g2 = (L[3] * L[7] - L[4] * L[6]) / det;
+    double gn = sqrt(g0 * g0 + g1 * g1 + g2 * g2);   // 1 / plane spacing
+    double halo = (std::max(c->params.ee_cutoff_off, c->params.r_Rc) + 0.05) * gn + 1e-6;
+    win_lo = (rank == 0) ? -halo - 1e-3 : (double)rank / world - halo;
+    win_hi = (rank == world - 1) ? 1.0 + halo + 1e-3 : (double)(rank + 1) / world + halo;
+    ilo = std::max(-ntess, (int)floor(win_lo - 1.0 - 1e-6) + 1);
+    ihi = std::min(ntess, (int)ceil(win_hi + 1e-6) - 1);
+  }
+  if ((rc = prepare_lattice(c, xyz_dev, Z_dev, nreal, lattice, ntess, &s, ilo, ihi))) return rc;
   s.slab_rank = rank; s.slab_world = world;
   // a slab holds ~nreal/world centres; keep head-room for density fluctuations without a host round trip
   if (world > 1) {
     s.ncent_max = std::min<int64_t>(nreal, nreal / world + nreal / (2 * world) + 4096);
     s.nrows = s.ncent_max + (int64_t)TM_ROW_TILE * c->hp.n_ele;
-    // bin only the slab and its halo: everything an owned centre can interact with lies within the largest cutoff
-    double gn = sqrt(s.slab_g[0] * s.slab_g[0] + s.slab_g[1] * s.slab_g[1] + s.slab_g[2] * s.slab_g[2]);   // 1 / plane spacing
-    double halo = (std::max(c->params.ee_cutoff_off, c->params.r_Rc) + 0.05) * gn + 1e-6;
     s.window_on = 1;
-    s.win_lo = (rank == 0) ? -halo - 1e-3 : (double)rank / world - halo;
-    s.win_hi = (rank == world - 1) ? 1.0 + halo + 1e-3 : (double)(rank + 1) / world + halo;
+    s.win_lo = win_lo; s.win_hi = win_hi;
+    s.win_ntess = ntess; s.win_ilo = ilo; s.win_ihi = ihi;
   }
   host_grid(c, &s, lattice, ntess);
   c->slab_view = s;

@@ -115,6 +115,7 @@ struct SysView {
   // slab runs only: slots whose fractional coordinate lies outside [win_lo, win_hi] (slab + interaction halo) are not binned
   int window_on;
   double win_lo, win_hi;
+  int win_ntess, win_ilo, win_ihi;   // image indices along the first lattice vector whose blocks can reach the window
   // lattice path: the cell grid is laid out on the host from the lattice (no bounding-box pass); grid_host = 1
   int grid_host;
   GridParams hgrid;
@@ -195,7 +196,7 @@ int tm_buf(tm_ctx* c, DevBuf& b, size_t bytes);
 int tm_host_stage(tm_ctx* c, size_t bytes);
 
 // ---- launchers (each returns TM_OK / error) ----
-int tm_launch_tessellate(tm_ctx* c, const double* xyz_real, const int32_t* Z_real, int64_t nreal, const double* lattice9_dev, int ntess);
+int tm_launch_tessellate(tm_ctx* c, const double* xyz_real, const int32_t* Z_real, int64_t nreal, const double* lattice9_dev, int ntess, int ilo, int ihi);
 int tm_launch_nlist_build(tm_ctx* c, const SysView& s, double rc_grid);
 int tm_launch_rows(tm_ctx* c, const SysView& s);
 int tm_launch_neighbours(tm_ctx* c, const SysView& s);

@@ -28,14 +28,18 @@ __device__ __forceinline__ double dec_d(unsigned long long b) {
 // ---------------------------------------------------------------- tessellation (Periodic.py:131-168)
 // slot = b*nreal + a ; block 0 = real atoms, then images for i,j,k in [-ntess..ntess]^3 skipping (0,0,0).
 // coords_ + i*L0 + j*L1 + k*L2 is evaluated left to right with separate roundings like numpy does.
+// ilo..ihi: image indices along the first lattice vector that can reach a slab rank's window (all of them otherwise);
+// the other blocks are never binned (image_block_skipped below) and are not written.
 __global__ void k_tessellate(const double* __restrict__ xyz, const int32_t* __restrict__ Z, int64_t nreal,
-                             const double* __restrict__ lat, int ntess, double* __restrict__ pos, int32_t* __restrict__ Zo) {
+                             const double* __restrict__ lat, int ntess, int ilo, int ihi, double* __restrict__ pos, int32_t* __restrict__ Zo) {
   int side = 2 * ntess + 1;
   int64_t nimg = (int64_t)side * side * side;
   int64_t total = nimg * nreal;
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
     int64_t b = t / nreal, a = t - b * nreal;
-    double x = xyz[3 * a], y = xyz[3 * a + 1], z = xyz[3 * a + 2];
+    if (b == 0 && (0 < ilo || 0 > ihi)) continue;
+    double x, y, z;
+    if (b == 0) { x = xyz[3 * a]; y = xyz[3 * a + 1]; z = xyz[3 * a + 2]; }
     if (b > 0) {
       // block index b>0 enumerates (i,j,k) in loop order with the centre cell skipped
       int64_t centre = ((int64_t)ntess * side + ntess) * side + ntess;
@@ -43,6 +47,8 @@ __global__ void k_tessellate(const double* __restrict__ xyz, const int32_t* __re
       int k = (int)(lin % side) - ntess;
       int j = (int)((lin / side) % side) - ntess;
       int i = (int)(lin / ((int64_t)side * side)) - ntess;
+      if (i < ilo || i > ihi) continue;
+      x = xyz[3 * a]; y = xyz[3 * a + 1]; z = xyz[3 * a + 2];
       double di = (double)i, dj = (double)j, dk = (double)k;
       x = __dadd_rn(__dadd_rn(__dadd_rn(x, __dmul_rn(di, lat[0])), __dmul_rn(dj, lat[3])), __dmul_rn(dk, lat[6]));
       y = __dadd_rn(__dadd_rn(__dadd_rn(y, __dmul_rn(di, lat[1])), __dmul_rn(dj, lat[4])), __dmul_rn(dk, lat[7]));
@@ -55,12 +61,12 @@ __global__ void k_tessellate(const double* __restrict__ xyz, const int32_t* __re
   }
 }
 
-int tm_launch_tessellate(tm_ctx* c, const double* xyz_real, const int32_t* Z_real, int64_t nreal, const double* lat_dev, int ntess) {
+int tm_launch_tessellate(tm_ctx* c, const double* xyz_real, const int32_t* Z_real, int64_t nreal, const double* lat_dev, int ntess, int ilo, int ihi) {
   int side = 2 * ntess + 1;
   int64_t total = (int64_t)side * side * side * nreal;
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
-  k_tessellate<<<blocks, 256, 0, c->stream>>>(xyz_real, Z_real, nreal, lat_dev, ntess, (double*)c->b_pos.p, (int32_t*)c->b_Z.p);
+  k_tessellate<<<blocks, 256, 0, c->stream>>>(xyz_real, Z_real, nreal, lat_dev, ntess, ilo, ihi, (double*)c->b_pos.p, (int32_t*)c->b_Z.p);
   c->launches++;
   TM_CUDA(cudaGetLastError());
   return TM_OK;
@@ -69,9 +75,23 @@ int tm_launch_tessellate(tm_ctx* c, const double* xyz_real, const int32_t* Z_rea
 // ---------------------------------------------------------------- bbox
 // Slab runs bin only the slots inside the owned slab plus the interaction halo (fractional coordinate window along the
 // first lattice vector); everything else never enters the cell list of this rank.
-struct Window { int on; double gx, gy, gz, lo, hi; };
+struct Window { int on; double gx, gy, gz, lo, hi; int64_t nreal; int ntess, ilo, ihi; };
+// image block of slot t along the first lattice vector outside [ilo, ihi]: the slot was not even tessellated
+__device__ __forceinline__ bool image_block_skipped(int64_t t, const Window& w) {
+  if (!w.on) return false;
+  int64_t b = t / w.nreal;
+  int i = 0;
+  if (b > 0) {
+    int side = 2 * w.ntess + 1;
+    int64_t centre = ((int64_t)w.ntess * side + w.ntess) * side + w.ntess;
+    int64_t lin = (b - 1 < centre) ? (b - 1) : b;
+    i = (int)(lin / ((int64_t)side * side)) - w.ntess;
+  }
+  return i < w.ilo || i > w.ihi;
+}
 __device__ __forceinline__ bool slot_in_window(const double* __restrict__ pos, int64_t t, const Window& w) {
   if (!w.on) return true;
+  if (image_block_skipped(t, w)) return false;
   double f = pos[3 * t] * w.gx + pos[3 * t + 1] * w.gy + pos[3 * t + 2] * w.gz;
   return f >= w.lo && f <= w.hi;
 }
@@ -83,7 +103,7 @@ __global__ void k_bbox_init(unsigned long long* bb) {
 __global__ void k_bbox(const double* __restrict__ pos, const int32_t* __restrict__ Z, int64_t n, Window win, unsigned long long* bb) {
   double mn[3] = {1e300, 1e300, 1e300}, mx[3] = {-1e300, -1e300, -1e300};
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
-    if (Z[t] <= 0 || !slot_in_window(pos, t, win)) continue;
+    if (image_block_skipped(t, win) || Z[t] <= 0 || !slot_in_window(pos, t, win)) continue;
 #pragma unroll
     for (int d = 0; d < 3; d++) {
       double v = pos[3 * t + d];
@@ -151,6 +171,7 @@ __global__ void k_cell_count(const double* __restrict__ pos, const int32_t* __re
                              int32_t* __restrict__ rank, int32_t* __restrict__ count, int32_t* __restrict__ flags) {
   GridParams g = *gp;
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+    if (image_block_skipped(t, win)) continue;   // k_scatter applies the same test: cellid / rank of these slots are never read
     if (Z[t] <= 0 || !slot_in_window(pos, t, win)) { cellid[t] = -1; rank[t] = -1; continue; }   // rank[] is reused as sidx_of_slot (-1 = absent)
     if (check_inside) {
       double fx = (pos[3 * t] - g.ox) * g.inv_cell, fy = (pos[3 * t + 1] - g.oy) * g.inv_cell, fz = (pos[3 * t + 2] - g.oz) * g.inv_cell;
@@ -254,8 +275,9 @@ static int scan_exclusive(tm_ctx* c, const int32_t* in, int32_t* out, int64_t n,
 }
 
 __global__ void k_scatter(const int32_t* __restrict__ cellid, const int32_t* __restrict__ rank, const int32_t* __restrict__ cstart,
-                          int64_t n, int32_t* __restrict__ sorted) {
+                          int64_t n, Window win, int32_t* __restrict__ sorted) {
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+    if (image_block_skipped(t, win)) continue;
     int cid = cellid[t];
     if (cid >= 0) sorted[cstart[cid] + rank[t]] = (int32_t)t;
   }
@@ -327,7 +349,7 @@ int tm_launch_nlist_build(tm_ctx* c, const SysView& s, double rc_grid) {
   if (blocks < 1) blocks = 1;
   unsigned long long* bb = (unsigned long long*)c->b_bbox.p;
   GridParams* gp = (GridParams*)c->b_grid.p;
-  Window win{s.window_on, s.slab_g[0], s.slab_g[1], s.slab_g[2], s.win_lo, s.win_hi};
+  Window win{s.window_on, s.slab_g[0], s.slab_g[1], s.slab_g[2], s.win_lo, s.win_hi, s.nreal > 0 ? s.nreal : 1, s.win_ntess, s.win_ilo, s.win_ihi};
   int64_t ncs = s.ncells_cap;   // cells the count / scan passes have to cover
   if (s.grid_host) {
     k_set_grid<<<1, 1, 0, c->stream>>>(s.hgrid, gp);
@@ -344,7 +366,7 @@ int tm_launch_nlist_build(tm_ctx* c, const SysView& s, double rc_grid) {
                                               (int32_t*)c->b_cellid.p, (int32_t*)c->b_rank.p, (int32_t*)c->b_count.p, (int32_t*)c->b_flags.p);
   c->launches += 1;
   if ((rc = scan_exclusive(c, (const int32_t*)c->b_count.p, (int32_t*)c->b_cstart.p, ncs, (int32_t*)c->b_scan_tmp.p))) return rc;
-  k_scatter<<<blocks, 256, 0, c->stream>>>((const int32_t*)c->b_cellid.p, (const int32_t*)c->b_rank.p, (const int32_t*)c->b_cstart.p, n,
+  k_scatter<<<blocks, 256, 0, c->stream>>>((const int32_t*)c->b_cellid.p, (const int32_t*)c->b_rank.p, (const int32_t*)c->b_cstart.p, n, win,
                                            (int32_t*)c->b_sorted.p);
   int cblocks = (int)((ncs * 32 + 255) / 256);
   if (cblocks > 148 * 32) cblocks = 148 * 32;
