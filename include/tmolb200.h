@@ -55,8 +55,11 @@ enum {
   TM_GEMM_FP32 = 0,      /* fp32 FFMA tiles (parity reference mode of the library) */
   TM_GEMM_TC_SPLIT = 1,  /* tcgen05 kind::f16 on split operands x = hi + lo/2048 (two fp16 planes, 22 significant bits),
                             3 MMAs per K-step, fp32 accumulation in TMEM + registers (default) */
-  TM_GEMM_TC_SPLIT_PAIR = 2 /* same arithmetic on CTA pairs: cta_group::2 MMAs of M = 256 over a cluster of two SMs,
+  TM_GEMM_TC_SPLIT_PAIR = 2, /* same arithmetic on CTA pairs: cta_group::2 MMAs of M = 256 over a cluster of two SMs,
                             each CTA stages its 128 A rows and half of the B rows (fewer L2 bytes per SM) */
+  TM_GEMM_TC_SPLIT_N64 = 3, /* mode 1 with the 128 x 64 tile forced; mode 1 picks that tile by itself for launches with few
+                            row tiles (slab ranks, small systems), this mode exists for tests and measurements */
+  TM_GEMM_TC_SPLIT_N128 = 4 /* mode 1 with the 128 x 128 tile forced (tests and measurements) */
 };
 
 /* evaluation flags */

@@ -253,7 +253,7 @@ extern "C" int tm_set_stream(tm_ctx* c, void* s) {
   return TM_OK;
 }
 extern "C" int tm_set_gemm_mode(tm_ctx* c, int mode) {
-  if (!c || mode < 0 || mode > 2) { tm_set_error("bad gemm mode %d (0 = fp32, 1 = tcgen05 split fp16, 2 = same on CTA pairs)", mode); return TM_EINVAL; }
+  if (!c || mode < 0 || mode > 4) { tm_set_error("bad gemm mode %d (0 = fp32, 1 = tcgen05 split fp16, 2 = same on CTA pairs, 3 / 4 = mode 1 with 64- / 128-column tiles forced)", mode); return TM_EINVAL; }
   c->gemm_mode = mode;
   c->cfg_gen++;
   return TM_OK;

@@ -249,20 +249,27 @@ __device__ __forceinline__ float2 join2(uint32_t hi, uint32_t lo) {
 // 30k SASS instructions and stalled on instruction fetch); ACTK: activation kind or -1 for a runtime switch.
 // NCTA: 1 = one CTA per 128x128 tile; 2 = CTA pair (cluster of 2, cta_group::2) per 256x128 tile: CTA `rank` owns row tile
 // 2*rt2 + rank and stages rows [64*rank, +64) of the B tile; the leader (rank 0) issues the MMAs for both.
-template <int EPI, int ACTK, int NCTA>
+template <int EPI, int ACTK, int NCTA, int BN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_gemm_tc(const __grid_constant__ TcParams P, const int32_t* __restrict__ rowmeta) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  constexpr int BN = TC_BN, STAGES = (NCTA == 2) ? 4 : TC_STAGES;
+  // BN = 128, or 64 (NCTA = 1 only) for launches with few row tiles (slab ranks, small systems): twice the tiles of half
+  // the width fill the 148 SMs more evenly (208 tiles of 128 columns = 2 waves for 1.4 waves of work).  With BN = 64 a
+  // (main, cross) accumulator pair takes 128 TMEM columns, so four pairs are in flight, and the two epilogue warps of a
+  // lane quarter take alternate TILES (all 64 columns each) instead of the two column halves of every tile.
+  static_assert(BN == 128 || (BN == 64 && NCTA == 1), "BN = 64 is a single-CTA variant");
+  constexpr int STAGES = (NCTA == 2 || BN == 64) ? 4 : TC_STAGES;
+  constexpr int NPAIR = 512 / (2 * BN);
+  constexpr int DRAIN_WARPS = (BN == 64) ? TC_EPI_WARPS / 2 : TC_EPI_WARPS;   // warps that drain one chunk
   constexpr uint32_t A_BYTES = TC_BM * TC_BK * 2;    // 16 KB per plane
   constexpr uint32_t B_BYTES = (BN / NCTA) * TC_BK * 2;
   constexpr uint32_t STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint64_t* full_bar = (uint64_t*)(smem + STAGES * STAGE_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tfull_bar = empty_bar + STAGES;      // [TC_NPAIR]
-  uint64_t* tempty_bar = tfull_bar + TC_NPAIR;   // [TC_NPAIR]
-  uint32_t* tmem_slot = (uint32_t*)(tempty_bar + TC_NPAIR);
+  uint64_t* tfull_bar = empty_bar + STAGES;      // [NPAIR]
+  uint64_t* tempty_bar = tfull_bar + NPAIR;      // [NPAIR]
+  uint32_t* tmem_slot = (uint32_t*)(tempty_bar + NPAIR);
   int* tile_base = (int*)(tmem_slot + 4);       // [TC_MAX_GROUPS+1]
   int* row_first = tile_base + TC_MAX_GROUPS + 1;   // [TC_MAX_GROUPS]
   int* row_tiles = row_first + TC_MAX_GROUPS;       // [TC_MAX_GROUPS]
@@ -283,15 +290,15 @@ k_gemm_tc(const __grid_constant__ TcParams P, const int32_t* __restrict__ rowmet
     }
     tile_base[P.ngroups] = acc;
     for (int s = 0; s < STAGES; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int a = 0; a < TC_NPAIR; a++) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], NCTA * TC_EPI_WARPS); }
+    for (int a = 0; a < NPAIR; a++) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], NCTA * DRAIN_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {   // TMEM allocation by one warp (the same warp in both CTAs of a pair)
     if (NCTA == 2) {
-      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)(TC_NPAIR * 2 * BN)));
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)(NPAIR * 2 * BN)));
       asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
     } else {
-      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)(TC_NPAIR * 2 * BN)));
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)(NPAIR * 2 * BN)));
       asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
   }
@@ -362,8 +369,8 @@ k_gemm_tc(const __grid_constant__ TcParams P, const int32_t* __restrict__ rowmet
         decode(t, g, rt, ct);
         int nkb = P.g[g].K / TC_BK;
         for (int kb0 = 0; kb0 < nkb; kb0 += TC_CHUNK, chunk_it++) {
-          int pair = chunk_it % TC_NPAIR;
-          uint32_t pair_phase = (chunk_it / TC_NPAIR) & 1;
+          int pair = chunk_it % NPAIR;
+          uint32_t pair_phase = (chunk_it / NPAIR) & 1;
           PROF_T(t_te);
           mbar_wait(&tempty_bar[pair], pair_phase ^ 1);
           PROF_ADD(0, t_te);
@@ -404,24 +411,31 @@ k_gemm_tc(const __grid_constant__ TcParams P, const int32_t* __restrict__ rowmet
     }
   } else {
     // ===================== epilogue (warps 2..9) =====================
-    // warp%4 selects the TMEM lane quarter (hardware rule); the two warps of a quarter split the BN columns.
+    // warp%4 selects the TMEM lane quarter (hardware rule); the two warps of a quarter split the 128 columns of a tile
+    // (BN = 128) or take alternate tiles (BN = 64).
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;
-    constexpr int NC = BN / 2;                     // columns per thread (64)
+    const int chalf = (BN == 128) ? half : 0;      // column half of the tile this warp owns
+    constexpr int NC = 64;                         // columns per thread
     const int act_kind = (ACTK >= 0) ? ACTK : P.act_kind;
     const float act_alpha = P.act_alpha;
     const uint32_t tb = smem_u32(tbuf) + (uint32_t)(warp - 2) * 4096u;   // this warp's transpose tile (shared-space address)
     uint32_t chunk_it = 0;
-    for (int t = unit; t < total_tiles; t += nunits) {
+    int titer = 0;
+    for (int t = unit; t < total_tiles; t += nunits, titer++) {
       int g, rt, ct;
       decode(t, g, rt, ct);
+      if (BN == 64 && (titer & 1) != half) {        // the other warp of this lane quarter drains this tile
+        chunk_it += (uint32_t)((P.g[g].K / TC_BK + TC_CHUNK - 1) / TC_CHUNK);
+        continue;
+      }
       rt = rt * NCTA + (int)rank;
       const bool live = rt < row_tiles[g];           // false only for the padding tile of an odd pair
       // group fields into registers once per tile (indexed constant loads are long-scoreboard operations)
       const int nkb = P.g[g].K / TC_BK;
       const int64_t ldc = P.g[g].ldc;
       const int64_t wrow0 = (int64_t)row_first[g] + (int64_t)rt * TC_BM + q * 32;
-      const int n0 = ct * BN + half * NC;
+      const int n0 = ct * BN + chalf * NC;
       float bias_a = 0.f, bias_b = 0.f, wout_a = 0.f, wout_b = 0.f;
       if (EPI == TM_EPI_ACT || EPI == TM_EPI_ACT_OUT) {   // issued now, consumed after the K loop: the latency hides behind the MMAs
         const float* bp = P.g[g].bias + n0;
@@ -437,14 +451,14 @@ k_gemm_tc(const __grid_constant__ TcParams P, const int32_t* __restrict__ rowmet
 #pragma unroll
       for (int i = 0; i < NC; i++) accr[i] = 0.f;
       for (int kb0 = 0; kb0 < nkb; kb0 += TC_CHUNK, chunk_it++) {
-        int pair = chunk_it % TC_NPAIR;
-        uint32_t pair_phase = (chunk_it / TC_NPAIR) & 1;
+        int pair = chunk_it % NPAIR;
+        uint32_t pair_phase = (chunk_it / NPAIR) & 1;
         PROF_T(t_tf);
         mbar_wait(&tfull_bar[pair], pair_phase);
         if (warp == 2 && lane == 0) PROF_ADD(2, t_tf);
         PROF_T(t_dr);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        uint32_t taddr = tmem_base + (uint32_t)(pair * 2 * BN + half * NC) + ((uint32_t)(q * 32) << 16);
+        uint32_t taddr = tmem_base + (uint32_t)(pair * 2 * BN + chalf * NC) + ((uint32_t)(q * 32) << 16);
         uint32_t v[NC];
 #pragma unroll
         for (int c = 0; c < NC / 32; c++) tmem_ld32(taddr + c * 32, v + c * 32);
@@ -529,7 +543,7 @@ k_gemm_tc(const __grid_constant__ TcParams P, const int32_t* __restrict__ rowmet
             accr[4 * i + k] = ww[k] * tc_act_bwd(h, act_kind, act_alpha);
           }
         }
-        P.g[g].ypart[(int64_t)(ct * 2 + half) * P.g[g].ystride + wrow0 + lane] = part;
+        P.g[g].ypart[(int64_t)((BN == 128) ? ct * 2 + half : ct) * P.g[g].ystride + wrow0 + lane] = part;   // one plane per 64 columns
         __syncwarp();
       } else if (EPI == TM_EPI_ACT) {
         // bias through the tile: 64 floats, read back with uniform-address (broadcast) 128-bit loads
@@ -597,8 +611,8 @@ k_gemm_tc(const __grid_constant__ TcParams P, const int32_t* __restrict__ rowmet
   else __syncthreads();
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    if (NCTA == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(TC_NPAIR * 2 * BN)));
-    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(TC_NPAIR * 2 * BN)));
+    if (NCTA == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(NPAIR * 2 * BN)));
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(NPAIR * 2 * BN)));
   }
 }
 
@@ -644,13 +658,13 @@ static int make_map(tm_ctx* c, CUtensorMap* m, const void* base, int64_t rows, i
   return TM_OK;
 }
 
-template <int EPI, int ACTK, int NCTA>
+template <int EPI, int ACTK, int NCTA, int BN>
 static int launch_tc(tm_ctx* c, const TcParams& P, const int* rowmeta_dev, int total_units_bound) {
-  // NCTA = 1: 3 stages x 64 KB; NCTA = 2: 4 stages x 48 KB -- the same 192 KB
+  // NCTA = 1, BN = 128: 3 stages x 64 KB; CTA pair or BN = 64: 4 stages x 48 KB -- the same 192 KB
   constexpr size_t smem = (size_t)TC_STAGES * (2 * TC_BM * TC_BK * 2 + 2 * TC_BN * TC_BK * 2) + 1024 + 512 + TC_EPI_WARPS * 32 * 32 * 4;
   static bool configured[64] = {};              // the attribute is per device
   if (c->device < 0 || c->device >= 64 || !configured[c->device]) {
-    TM_CUDA(cudaFuncSetAttribute(k_gemm_tc<EPI, ACTK, NCTA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TM_CUDA(cudaFuncSetAttribute(k_gemm_tc<EPI, ACTK, NCTA, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (c->device >= 0 && c->device < 64) configured[c->device] = true;
   }
   int sms = 148;
@@ -659,7 +673,7 @@ static int launch_tc(tm_ctx* c, const TcParams& P, const int* rowmeta_dev, int t
   if (total_units_bound < units) units = total_units_bound;
   if (units < 1) units = 1;
   if (NCTA == 1) {
-    k_gemm_tc<EPI, ACTK, NCTA><<<units, TC_THREADS, smem, c->stream>>>(P, rowmeta_dev);
+    k_gemm_tc<EPI, ACTK, NCTA, BN><<<units, TC_THREADS, smem, c->stream>>>(P, rowmeta_dev);
   } else {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(units * NCTA));
@@ -671,32 +685,49 @@ static int launch_tc(tm_ctx* c, const TcParams& P, const int* rowmeta_dev, int t
     attr[0].val.clusterDim.x = NCTA; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    TM_CUDA(cudaLaunchKernelEx(&cfg, k_gemm_tc<EPI, ACTK, NCTA>, P, rowmeta_dev));
+    TM_CUDA(cudaLaunchKernelEx(&cfg, k_gemm_tc<EPI, ACTK, NCTA, BN>, P, rowmeta_dev));
   }
   c->launches++;
   TM_CUDA(cudaGetLastError());
   return TM_OK;
 }
 
-template <int EPI, int NCTA>
+template <int EPI, int NCTA, int BN>
 static int launch_tc_act(tm_ctx* c, const TcParams& P, const int* rowmeta_dev, int bound) {
-  if (EPI == TM_EPI_NONE) return launch_tc<EPI, 0, NCTA>(c, P, rowmeta_dev, bound);
-  if (P.act_kind == TM_ACT_SIGMOID_WITH_PARAM) return launch_tc<EPI, TM_ACT_SIGMOID_WITH_PARAM, NCTA>(c, P, rowmeta_dev, bound);
-  return launch_tc<EPI, -1, NCTA>(c, P, rowmeta_dev, bound);
+  if (EPI == TM_EPI_NONE) return launch_tc<EPI, 0, NCTA, BN>(c, P, rowmeta_dev, bound);
+  if (P.act_kind == TM_ACT_SIGMOID_WITH_PARAM) return launch_tc<EPI, TM_ACT_SIGMOID_WITH_PARAM, NCTA, BN>(c, P, rowmeta_dev, bound);
+  return launch_tc<EPI, -1, NCTA, BN>(c, P, rowmeta_dev, bound);
 }
 
-template <int NCTA>
+template <int NCTA, int BN>
 static int launch_tc_epi(tm_ctx* c, const TcParams& P, const int* rowmeta_dev, int bound, int epilogue) {
-  if (epilogue == TM_EPI_ACT) return launch_tc_act<TM_EPI_ACT, NCTA>(c, P, rowmeta_dev, bound);
-  if (epilogue == TM_EPI_ACT_OUT) return launch_tc_act<TM_EPI_ACT_OUT, NCTA>(c, P, rowmeta_dev, bound);
-  if (epilogue == TM_EPI_DACT) return launch_tc_act<TM_EPI_DACT, NCTA>(c, P, rowmeta_dev, bound);
-  return launch_tc_act<TM_EPI_NONE, NCTA>(c, P, rowmeta_dev, bound);
+  if (epilogue == TM_EPI_ACT) return launch_tc_act<TM_EPI_ACT, NCTA, BN>(c, P, rowmeta_dev, bound);
+  if (epilogue == TM_EPI_ACT_OUT) return launch_tc_act<TM_EPI_ACT_OUT, NCTA, BN>(c, P, rowmeta_dev, bound);
+  if (epilogue == TM_EPI_DACT) return launch_tc_act<TM_EPI_DACT, NCTA, BN>(c, P, rowmeta_dev, bound);
+  return launch_tc_act<TM_EPI_NONE, NCTA, BN>(c, P, rowmeta_dev, bound);
+}
+
+// Column-tile width for a launch whose groups hold about `expect_rows` rows in total (the exact counts live on the
+// device): 64 when the persistent grid would otherwise idle through a large part of its last wave.  Half-width tiles
+// cost ~1.5x the shared-memory operand reads per flop and re-read the A tiles twice as often, so they must buy at
+// least 15 % of occupancy.  TM_GEMM_BN=64|128 overrides (measurements).
+static int choose_bn(const GemmGroup* groups, int ngroups, int64_t expect_rows, int n_ele, int sms) {
+  static int forced = -1;
+  if (forced < 0) { const char* e = getenv("TM_GEMM_BN"); forced = e ? atoi(e) : 0; }
+  if (forced == 64 || forced == 128) return forced;
+  if (ngroups < 1 || n_ele < 1) return TC_BN;
+  // groups = nets x elements; the rows are shared out over the elements, each element ending in a partial tile
+  int nets = (ngroups + n_ele - 1) / n_ele;
+  int64_t row_tiles = (expect_rows + TC_BM - 1) / TC_BM + n_ele / 2;
+  int64_t t128 = row_tiles * nets * (groups[0].N / TC_BN), t64 = 2 * t128;
+  auto eff = [&](int64_t t) { int64_t w = (t + sms - 1) / sms; return w ? (double)t / (double)(w * sms) : 1.0; };
+  return eff(t64) > 1.15 * eff(t128) ? 64 : TC_BN;
 }
 
 // In this mode every GemmGroup pointer except bias (and C for TM_EPI_NONE) addresses fp16 planes.
-int tm_gemm_tc_launch(tm_ctx* c, const GemmGroup* groups, int ngroups, const int* rowmeta_dev, int max_row_tiles, int epilogue) {
+int tm_gemm_tc_launch(tm_ctx* c, const GemmGroup* groups, int ngroups, const int* rowmeta_dev, int max_row_tiles, int64_t expect_rows, int epilogue) {
   int rc;
-  if (c->gemm_mode != TM_GEMM_TC_SPLIT && c->gemm_mode != TM_GEMM_TC_SPLIT_PAIR) { tm_set_error("gemm mode %d is not implemented", c->gemm_mode); return TM_ESTATE; }
+  if (c->gemm_mode != TM_GEMM_TC_SPLIT && c->gemm_mode != TM_GEMM_TC_SPLIT_PAIR && c->gemm_mode != TM_GEMM_TC_SPLIT_N64 && c->gemm_mode != TM_GEMM_TC_SPLIT_N128) { tm_set_error("gemm mode %d is not implemented", c->gemm_mode); return TM_ESTATE; }
   const int ncta = (c->gemm_mode == TM_GEMM_TC_SPLIT_PAIR) ? 2 : 1;
   if ((rc = get_encode())) return rc;
   if (ngroups > TC_MAX_GROUPS) { tm_set_error("too many GEMM groups"); return TM_EINVAL; }
@@ -723,6 +754,9 @@ int tm_gemm_tc_launch(tm_ctx* c, const GemmGroup* groups, int ngroups, const int
     call++;
   }
 #endif
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
+  const int bn = (c->gemm_mode == TM_GEMM_TC_SPLIT_N64) ? 64 : (c->gemm_mode == TM_GEMM_TC_SPLIT_N128) ? TC_BN : (ncta == 1) ? choose_bn(groups, ngroups, expect_rows, c->hp.n_ele, sms) : TC_BN;
   int64_t tiles = 0;
   for (int i = 0; i < ngroups; i++) {
     const GemmGroup& g = groups[i];
@@ -730,17 +764,18 @@ int tm_gemm_tc_launch(tm_ctx* c, const GemmGroup* groups, int ngroups, const int
     TcGroup& T = P.g[i];
     if ((rc = make_map(c, &T.mapA_hi, g.A, g.rows_alloc, g.K, g.lda, TC_BM))) return rc;
     if ((rc = make_map(c, &T.mapA_lo, g.A2, g.rows_alloc, g.K, g.lda, TC_BM))) return rc;
-    if ((rc = make_map(c, &T.mapB_hi, g.B, g.N, g.K, g.ldb, TC_BN / ncta))) return rc;   // a CTA of a pair stages half of the B rows
-    if ((rc = make_map(c, &T.mapB_lo, g.B2, g.N, g.K, g.ldb, TC_BN / ncta))) return rc;
+    if ((rc = make_map(c, &T.mapB_hi, g.B, g.N, g.K, g.ldb, bn / ncta))) return rc;   // a CTA of a pair stages half of the B rows
+    if ((rc = make_map(c, &T.mapB_lo, g.B2, g.N, g.K, g.ldb, bn / ncta))) return rc;
     T.bias = g.bias; T.Hmul_hi = (const __half*)g.Hmul; T.Hmul_lo = (const __half*)g.Hmul2;
     T.C_hi = (__half*)g.C; T.C_lo = (__half*)g.C2; T.C32 = (float*)g.C;
     T.wout = g.wout; T.ypart = g.ypart; T.ystride = g.rows_alloc;
     if (epilogue == TM_EPI_ACT_OUT && (!g.wout || !g.ypart)) { tm_set_error("tc gemm: output-layer epilogue without w_out / ypart"); return TM_EINVAL; }
     T.ldc = g.ldc; T.K = g.K; T.N = g.N; T.ele = g.ele;
-    tiles += (int64_t)((max_row_tiles + ncta - 1) / ncta) * (g.N / TC_BN);
+    tiles += (int64_t)((max_row_tiles + ncta - 1) / ncta) * (g.N / bn);
   }
   int bound = tiles > 100000 ? 100000 : (int)tiles;
-  return ncta == 2 ? launch_tc_epi<2>(c, P, rowmeta_dev, bound, epilogue) : launch_tc_epi<1>(c, P, rowmeta_dev, bound, epilogue);
+  if (ncta == 2) return launch_tc_epi<2, TC_BN>(c, P, rowmeta_dev, bound, epilogue);
+  return bn == 64 ? launch_tc_epi<1, 64>(c, P, rowmeta_dev, bound, epilogue) : launch_tc_epi<1, TC_BN>(c, P, rowmeta_dev, bound, epilogue);
 }
 
 void tm_gemm_tc_release(tm_ctx* c) {

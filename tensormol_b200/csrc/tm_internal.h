@@ -230,7 +230,7 @@ struct GemmGroup {
   float* ypart = nullptr;
 };
 void tm_gemm_tc_release(tm_ctx* c);
-int tm_launch_gemm(tm_ctx* c, const GemmGroup* groups, int ngroups, const int* rowmeta_dev, int max_row_tiles, int epilogue);
+int tm_launch_gemm(tm_ctx* c, const GemmGroup* groups, int ngroups, const int* rowmeta_dev, int max_row_tiles, int64_t expect_rows, int epilogue);
 // TM_EPI_ACT_OUT (tensor-core mode, last hidden layer): h = act(z + b) is not stored; the epilogue emits the output layer's
 // partial dot products  ypart[p][row] = sum_cols h*w_out  (p = 128-column half-tile index) and C = w_out * act'(h), the
 // backward seed.

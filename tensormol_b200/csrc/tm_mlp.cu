@@ -142,10 +142,10 @@ k_gemm_simt(const __grid_constant__ GemmGroupTbl tbl, const int32_t* __restrict_
   }
 }
 
-int tm_gemm_tc_launch(tm_ctx* c, const GemmGroup* groups, int ngroups, const int* rowmeta_dev, int max_row_tiles, int epilogue);
+int tm_gemm_tc_launch(tm_ctx* c, const GemmGroup* groups, int ngroups, const int* rowmeta_dev, int max_row_tiles, int64_t expect_rows, int epilogue);
 
-int tm_launch_gemm(tm_ctx* c, const GemmGroup* groups, int ngroups, const int* rowmeta_dev, int max_row_tiles, int epilogue) {
-  if (c->gemm_mode != TM_GEMM_FP32) return tm_gemm_tc_launch(c, groups, ngroups, rowmeta_dev, max_row_tiles, epilogue);
+int tm_launch_gemm(tm_ctx* c, const GemmGroup* groups, int ngroups, const int* rowmeta_dev, int max_row_tiles, int64_t expect_rows, int epilogue) {
+  if (c->gemm_mode != TM_GEMM_FP32) return tm_gemm_tc_launch(c, groups, ngroups, rowmeta_dev, max_row_tiles, expect_rows, epilogue);
   GemmGroupTbl tbl;
   int maxN = 0;
   for (int i = 0; i < ngroups; i++) {
@@ -257,6 +257,11 @@ static void* delta_ptr(tm_ctx* c, const SysView& s, int l, int net, int plane) {
   return base + ((size_t)plane * 2 + net) * s.nrows * c->Hmax * esz;
 }
 
+// centres this rank is likely to own (the exact count lives on the device): sizes the GEMM column tiles
+static int64_t expect_rows(const SysView& s) {
+  return std::max<int64_t>(1, s.slab_world > 1 ? (s.periodic ? s.nreal : s.nslots) / s.slab_world : s.ncent_max);
+}
+
 int tm_launch_mlp_forward(tm_ctx* c, const SysView& s) {
   int rc;
   if ((rc = ensure_mlp_bufs(c, s))) return rc;
@@ -293,7 +298,7 @@ int tm_launch_mlp_forward(tm_ctx* c, const SysView& s) {
           g.ypart = (float*)c->b_ypart.p + (size_t)net * (2 * c->Hmax / 128) * s.nrows;
         }
       }
-    if ((rc = tm_launch_gemm(c, gg, ng, rowmeta, max_tiles, (tc && l == nh - 1) ? TM_EPI_ACT_OUT : TM_EPI_ACT))) return rc;
+    if ((rc = tm_launch_gemm(c, gg, ng, rowmeta, max_tiles, expect_rows(s), (tc && l == nh - 1) ? TM_EPI_ACT_OUT : TM_EPI_ACT))) return rc;
   }
   if (tc) {
     YTbl Y;
@@ -356,7 +361,7 @@ int tm_launch_mlp_backward(tm_ctx* c, const SysView& s) {
           g.C = c->b_dG[net].p; g.ldc = c->hp.Dp;
         }
       }
-    if ((rc = tm_launch_gemm(c, gg, ng, rowmeta, max_tiles, l > 0 ? TM_EPI_DACT : TM_EPI_NONE))) return rc;
+    if ((rc = tm_launch_gemm(c, gg, ng, rowmeta, max_tiles, expect_rows(s), l > 0 ? TM_EPI_DACT : TM_EPI_NONE))) return rc;
   }
   return TM_OK;
 }

@@ -125,7 +125,7 @@ def test_pairs_triples_ele_tables(name):
 
 
 # ---------------------------------------------------------------------------------------- fused evaluation
-GEMM_MODES = [0, 1]    # 0 = fp32 FFMA tiles, 1 = tcgen05 split-fp16 (library default)
+GEMM_MODES = [0, 1, 3, 4]    # 0 = fp32 FFMA tiles, 1 = tcgen05 split-fp16 (library default: tile width by size), 3 / 4 = 64- / 128-column tiles forced
 
 
 @pytest.mark.parametrize("mode", GEMM_MODES)
@@ -189,7 +189,7 @@ def test_eval_set_of_molecules_vs_oracle():
     _check_grad(r["gradient"], o["gradient"])
 
 
-@pytest.mark.parametrize("mode,hidden", [(0, [128, 96, 64]), (1, [128, 96, 64]), (1, [500, 500, 500])])
+@pytest.mark.parametrize("mode,hidden", [(0, [128, 96, 64]), (1, [128, 96, 64]), (1, [500, 500, 500]), (3, [500, 500, 500]), (4, [500, 500, 500])])
 def test_eval_water_box_periodic_vs_oracle(mode, hidden):
     """216-water periodic box (648 atoms, L=18.6 A > 15 A so ntess=1, 27 images)."""
     from oracle import oracle_graph as og
