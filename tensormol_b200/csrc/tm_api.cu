@@ -223,8 +223,8 @@ extern "C" void tm_destroy(tm_ctx* c) {
   tm_gemm_tc_release(c);
   DevBuf* all[] = {&c->b_pos, &c->b_Z, &c->b_cellid, &c->b_rank, &c->b_count, &c->b_cstart, &c->b_sorted, &c->b_satom, &c->b_scan_tmp,
                    &c->b_rowslot, &c->b_rowsidx, &c->b_rowofslot, &c->b_blkcnt, &c->b_rowmeta, &c->b_nbcnt, &c->b_nboff, &c->b_nbr, &c->b_G, &c->b_Gs, &c->b_ypart,
-                   &c->b_delta0, &c->b_delta1, &c->b_dG[0], &c->b_dG[1], &c->b_y[0], &c->b_y[1], &c->b_q, &c->b_qs, &c->b_dedq, &c->b_u, &c->b_F,
-                   &c->b_acc, &c->b_bbox, &c->b_grid, &c->b_flags, &c->b_out, &c->b_molacc, &c->b_natom, &c->b_lattice};
+                   &c->b_delta0, &c->b_delta1, &c->b_dG[0], &c->b_dG[1], &c->b_y[0], &c->b_y[1], &c->b_q, &c->b_qs, &c->b_dedq, &c->b_F,
+                   &c->b_acc, &c->b_bbox, &c->b_grid, &c->b_flags, &c->b_out, &c->b_molacc, &c->b_natom};
   for (DevBuf* b : all) free_buf(*b);
   for (int n = 0; n < 2; n++)
     for (int l = 0; l < TM_MAX_HIDDEN; l++) free_buf(c->b_act[n][l]);
@@ -347,9 +347,9 @@ static int check_weights(tm_ctx* c) {
 }
 
 // ------------------------------------------------------------------------------------------------ small kernels
-// per row: Ebp_atom (slot order, double) and per-molecule Ebp
+// per-molecule Ebp (fp32 GEMM mode only: the tensor-core forward pass sums it in k_y_reduce)
 __global__ void k_ebp(const float* __restrict__ y, const int32_t* __restrict__ rowslot, int64_t nrows, int64_t maxnatom,
-                      double* __restrict__ ebp_slot, double* __restrict__ molacc) {
+                      double* __restrict__ molacc) {
   int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   int slot = (r < nrows) ? rowslot[r] : -1;
   double v = 0.0;
@@ -357,7 +357,6 @@ __global__ void k_ebp(const float* __restrict__ y, const int32_t* __restrict__ r
   if (slot >= 0) {
     v = (double)y[r];
     m = (int)(slot / maxnatom);
-    if (ebp_slot) ebp_slot[slot] = v;
   }
   // warp-aggregate when the whole warp belongs to one molecule
   int m0 = __shfl_sync(FULL, m, 0);
@@ -375,23 +374,13 @@ __global__ void k_ebp(const float* __restrict__ y, const int32_t* __restrict__ r
   }
 }
 
-// u[row] = dE/dq_raw = dE/dq_slot - mean_mol(dE/dq)   (backward of the neutralisation, TFMolInstanceDirect.py:5274-5277)
-__global__ void k_u(const double* __restrict__ dedq_slot, const double* __restrict__ molacc, const double* __restrict__ inv_n,
-                    const int32_t* __restrict__ rowslot, int64_t nrows, int64_t maxnatom, int add_ecc, float* __restrict__ u) {
-  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < nrows; r += (int64_t)gridDim.x * blockDim.x) {
-    int slot = rowslot[r];
-    float v = 0.f;
-    if (slot >= 0 && add_ecc) {
-      int m = (int)(slot / maxnatom);
-      v = (float)(dedq_slot[slot] - molacc[16 * m + 5] * inv_n[m]);
-    }
-    u[r] = v;
-  }
-}
-
 // pack the outputs as doubles: [Etot nmol][Ebp][Ecc][Evdw][dipole 3nmol][Ebp_atom nq][charge nq][grad 3nq]
-__global__ void k_pack(const double* __restrict__ molacc, int64_t nmol, int add_ecc, double* __restrict__ out) {
-  for (int64_t m = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; m < nmol; m += (int64_t)gridDim.x * blockDim.x) {
+// (one launch: the molecule sums are complete, Ebp_atom comes from the energy net's rows through rowofslot)
+__global__ void k_pack_all(const double* __restrict__ molacc, int64_t nmol, int add_ecc, const float* __restrict__ y_e,
+                           const int32_t* __restrict__ rowofslot, const double* __restrict__ q_slot, const float* __restrict__ F, int64_t nq,
+                           int do_force, double* __restrict__ out) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x, t0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  for (int64_t m = t0; m < nmol; m += stride) {
     double ebp = molacc[16 * m + 1], ecc = add_ecc ? molacc[16 * m + 2] : 0.0, evdw = molacc[16 * m + 3];
     out[m] = ebp + ecc + evdw;                 // TFMolInstanceDirect.py:5213-5215
     out[nmol + m] = ebp;
@@ -401,12 +390,19 @@ __global__ void k_pack(const double* __restrict__ molacc, int64_t nmol, int add_
     out[4 * nmol + 3 * m + 1] = molacc[16 * m + 7];
     out[4 * nmol + 3 * m + 2] = molacc[16 * m + 8];
   }
+  double* ebp_atom = out + 7 * nmol;
+  double* charge = ebp_atom + nq;
+  double* grad = charge + nq;
+  for (int64_t t = t0; t < nq; t += stride) {
+    int row = rowofslot[t];
+    ebp_atom[t] = (row >= 0) ? (double)y_e[row] : 0.0;
+    charge[t] = q_slot[t];
+  }
+  if (do_force)
+    for (int64_t t = t0; t < 3 * nq; t += stride) grad[t] = (double)F[t];
 }
 __global__ void k_f2d(const float* __restrict__ in, double* __restrict__ out, int64_t n) {
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) out[t] = (double)in[t];
-}
-__global__ void k_d2d(const double* __restrict__ in, double* __restrict__ out, int64_t n) {
-  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) out[t] = in[t];
 }
 __global__ void k_desc_out(const float* __restrict__ G, const int32_t* __restrict__ rowofslot, int64_t nq, int D, int Dp, float* __restrict__ out) {
   int64_t slot = blockIdx.x;
@@ -445,7 +441,7 @@ static SysView make_view(tm_ctx* c, int64_t nslots, int64_t nmol, int64_t maxnat
   s.ncent_max = ncent_max;
   s.nrows = ncent_max + (int64_t)TM_ROW_TILE * c->hp.n_ele;
   s.ncells_cap = nslots + 1024;
-  s.slab_rank = 0; s.slab_world = 1;
+  s.slab_rank = 0; s.slab_world = 1; s.slab_api = 0;
   s.slab_g[0] = s.slab_g[1] = s.slab_g[2] = 0.0;
   s.window_on = 0; s.win_lo = 0.0; s.win_hi = 0.0;
   s.win_ntess = 0; s.win_ilo = -1000; s.win_ihi = 1000;
@@ -461,7 +457,6 @@ static int stage_a(tm_ctx* c, const SysView& s) {
   if ((rc = tm_buf(c, c->b_flags, 64))) return rc;
   if ((rc = tm_buf(c, c->b_molacc, (size_t)s.nmol * 16 * 8))) return rc;
   if ((rc = tm_buf(c, c->b_F, (size_t)nq * 3 * 4))) return rc;
-  if ((rc = tm_buf(c, c->b_u, (size_t)s.nrows * 4))) return rc;
   TM_CUDA(cudaMemsetAsync(c->b_flags.p, 0, 64, c->stream));
   TM_CUDA(cudaMemsetAsync(c->b_molacc.p, 0, (size_t)s.nmol * 16 * 8, c->stream));
   TM_CUDA(cudaMemsetAsync(c->b_F.p, 0, (size_t)nq * 3 * 4, c->stream));
@@ -490,9 +485,6 @@ static int stage_c(tm_ctx* c, const SysView& s, int flags) {
   if (flags & TM_F_FORCE) {
     if ((rc = tm_launch_mlp_backward(c, s))) return rc;
     cudaEventRecord(c->ev[6], c->stream);
-    k_u<<<nblk(s.nrows), 256, 0, c->stream>>>((const double*)c->b_dedq.p, (const double*)c->b_molacc.p, (const double*)c->b_natom.p,
-                                              (const int32_t*)c->b_rowslot.p, s.nrows, s.maxnatom, c->hp.add_ecc, (float*)c->b_u.p);
-    c->launches++;
     if ((rc = tm_launch_force(c, s, flags))) return rc;
   } else {
     cudaEventRecord(c->ev[6], c->stream);
@@ -506,16 +498,16 @@ static int stage_pack(tm_ctx* c, const SysView& s, int flags, const OutLayout& o
   int rc;
   if ((rc = tm_buf(c, c->b_out, (size_t)o.total * 8))) return rc;
   double* out = (double*)c->b_out.p;
-  TM_CUDA(cudaMemsetAsync(out + o.off_ebp_atom, 0, (size_t)o.nq * 8, c->stream));
-  k_ebp<<<(int)((s.nrows + 255) / 256), 256, 0, c->stream>>>((const float*)c->b_y[TM_NET_ENERGY].p, (const int32_t*)c->b_rowslot.p, s.nrows, s.maxnatom,
-                                                            out + o.off_ebp_atom, (double*)c->b_molacc.p);
-  k_pack<<<nblk(s.nmol), 256, 0, c->stream>>>((const double*)c->b_molacc.p, s.nmol, c->hp.add_ecc, out);
-  k_d2d<<<nblk(o.nq), 256, 0, c->stream>>>((const double*)c->b_q.p + o.nq, out + o.off_charge, o.nq);
-  c->launches += 3;
-  if (flags & TM_F_FORCE) {
-    k_f2d<<<nblk(3 * o.nq), 256, 0, c->stream>>>((const float*)c->b_F.p, out + o.off_grad, 3 * o.nq);
+  if (!c->y_fused) {
+    k_ebp<<<(int)((s.nrows + 255) / 256), 256, 0, c->stream>>>((const float*)c->b_y[TM_NET_ENERGY].p, (const int32_t*)c->b_rowslot.p, s.nrows, s.maxnatom,
+                                                              (double*)c->b_molacc.p);
     c->launches++;
   }
+  const int do_force = (flags & TM_F_FORCE) ? 1 : 0;
+  k_pack_all<<<nblk(std::max<int64_t>(s.nmol, (do_force ? 3 : 1) * o.nq)), 256, 0, c->stream>>>(
+      (const double*)c->b_molacc.p, s.nmol, c->hp.add_ecc, (const float*)c->b_y[TM_NET_ENERGY].p, (const int32_t*)c->b_rowofslot.p,
+      (const double*)c->b_q.p + o.nq, (const float*)c->b_F.p, o.nq, do_force, out);
+  c->launches++;
   TM_CUDA(cudaGetLastError());
   return TM_OK;
 }
@@ -696,11 +688,6 @@ static int64_t tess_count(int64_t nreal, int ntess) {
 }
 
 // device-side tessellation; xyz_dev / Z_dev are DEVICE pointers to the primitive cell
-struct LatArgs { double v[10]; };
-__global__ void k_set_lattice(LatArgs a, double* __restrict__ lat, double* __restrict__ inv_n) {
-  if (threadIdx.x < 10) lat[threadIdx.x] = a.v[threadIdx.x];
-  if (threadIdx.x == 0) inv_n[0] = a.v[9];
-}
 
 static int prepare_lattice(tm_ctx* c, const double* xyz_dev, const int32_t* Z_dev, int64_t nreal, const double* lattice, int ntess, SysView* sv,
                            int ilo = -1000, int ihi = 1000) {
@@ -709,15 +696,13 @@ static int prepare_lattice(tm_ctx* c, const double* xyz_dev, const int32_t* Z_de
   int64_t nslots = tess_count(nreal, ntess);
   if ((rc = tm_buf(c, c->b_pos, (size_t)nslots * 24))) return rc;
   if ((rc = tm_buf(c, c->b_Z, (size_t)nslots * 4))) return rc;
-  if ((rc = tm_buf(c, c->b_lattice, 16 * 8))) return rc;
   if ((rc = tm_buf(c, c->b_natom, 8))) return rc;
-  // lattice and 1/natom travel as kernel arguments (no pageable copy: the call sequence stays CUDA-graph capturable)
+  // lattice and 1/natom travel as kernel arguments (no pageable copy: the call sequence stays CUDA-graph capturable);
+  // k_tessellate stores 1/natom into b_natom for the charge kernels
   LatArgs la;
   memcpy(la.v, lattice, 72);
   la.v[9] = 1.0 / (double)nreal;
-  k_set_lattice<<<1, 32, 0, c->stream>>>(la, (double*)c->b_lattice.p, (double*)c->b_natom.p);
-  c->launches++;
-  if ((rc = tm_launch_tessellate(c, xyz_dev, Z_dev, nreal, (const double*)c->b_lattice.p, ntess, ilo, ihi))) return rc;
+  if ((rc = tm_launch_tessellate(c, xyz_dev, Z_dev, nreal, la, ntess, ilo, ihi))) return rc;
   *sv = make_view(c, nslots, 1, nslots, nreal, 1, nreal);
   // inverse lattice first row (for slab ownership): frac_a = pos . g
   const double* L = lattice;
@@ -1032,11 +1017,24 @@ __global__ void k_p2p_wait(char* flags, int world, int which, int32_t* errflags)
   *epoch += 1u;
   __threadfence_system();
 }
-// sum of the energy partials -> molacc[5] (sum dE/dq over all ranks) and the reduced energies
-__global__ void k_slab_reduce_e(const double* __restrict__ eparts, int world, double* __restrict__ molacc, double* __restrict__ e_out) {
+// sum of the energy partials -> molacc[5] (sum dE/dq over all ranks) and the reduced energies, after the wait for
+// exchange `which` (same protocol as k_p2p_wait)
+__global__ void k_p2p_wait_reduce_e(char* flags, int world, int which, int32_t* errflags, const double* eparts, double* __restrict__ molacc,
+                                    double* __restrict__ e_out) {
+  volatile unsigned int* cnt = (volatile unsigned int*)flags + 16 * which;
+  unsigned int* epoch = (unsigned int*)flags + 16 * (4 + which);
+  unsigned int target = (*epoch + 1u) * (unsigned int)world;
+  long long t0 = clock64();
+  while ((int)(*cnt - target) < 0) {
+    if (clock64() - t0 > 16000000000ll) { atomicOr(errflags, 32); break; }   // ~8 s: a peer never arrived
+    __nanosleep(200);
+  }
+  *epoch += 1u;
+  __threadfence_system();
+  const volatile double* ep = (const volatile double*)eparts;   // written by the peers: no cached / hoisted reads
   double s[6] = {0, 0, 0, 0, 0, 0};
   for (int r = 0; r < world; r++)
-    for (int k = 0; k < 6; k++) s[k] += eparts[8 * r + k];
+    for (int k = 0; k < 6; k++) s[k] += ep[8 * r + k];
   molacc[5] = s[4];
   s[0] = s[1] + s[2] + s[3];
   for (int k = 0; k < 6; k++) e_out[k] = s[k];
@@ -1059,7 +1057,7 @@ static int p2p_preload(tm_ctx* c) {
   TM_CUDA(cudaFuncGetAttributes(&fa, k_push_grad_p2p));
   TM_CUDA(cudaFuncGetAttributes(&fa, k_p2p_signal));
   TM_CUDA(cudaFuncGetAttributes(&fa, k_p2p_wait));
-  TM_CUDA(cudaFuncGetAttributes(&fa, k_slab_reduce_e));
+  TM_CUDA(cudaFuncGetAttributes(&fa, k_p2p_wait_reduce_e));
   TM_CUDA(cudaFuncGetAttributes(&fa, k_sum_grad_p2p));
   return TM_OK;
 }
@@ -1092,7 +1090,7 @@ extern "C" int tm_slab_phase_a(tm_ctx* c, const double* xyz_dev, const int32_t* 
     ihi = std::min(ntess, (int)ceil(win_hi + 1e-6) - 1);
   }
   if ((rc = prepare_lattice(c, xyz_dev, Z_dev, nreal, lattice, ntess, &s, ilo, ihi))) return rc;
-  s.slab_rank = rank; s.slab_world = world;
+  s.slab_rank = rank; s.slab_world = world; s.slab_api = 1;
   // a slab holds ~nreal/world centres; keep head-room for density fluctuations without a host round trip
   if (world > 1) {
     s.ncent_max = std::min<int64_t>(nreal, nreal / world + nreal / (2 * world) + 4096);
@@ -1139,8 +1137,11 @@ extern "C" int tm_slab_phase_b(tm_ctx* c, const double* qraw_dev, double* e_dev)
   s2.slab_world = 2;   // any value > 1: tm_launch_charges then takes qraw from b_q instead of scattering its own rows
   if ((rc = tm_launch_charges(c, s2))) return rc;
   if ((rc = tm_launch_pair(c, s, TM_F_FORCE | TM_F_VDW))) return rc;
-  k_ebp<<<(int)((s.nrows + 255) / 256), 256, 0, c->stream>>>((const float*)c->b_y[TM_NET_ENERGY].p, (const int32_t*)c->b_rowslot.p, s.nrows, s.maxnatom,
-                                                            nullptr, (double*)c->b_molacc.p);
+  if (!c->y_fused) {
+    k_ebp<<<(int)((s.nrows + 255) / 256), 256, 0, c->stream>>>((const float*)c->b_y[TM_NET_ENERGY].p, (const int32_t*)c->b_rowslot.p, s.nrows, s.maxnatom,
+                                                              (double*)c->b_molacc.p);
+    c->launches++;
+  }
   if (c->p2p.on) {
     k_slab_e_p2p<<<1, 32, 0, c->stream>>>((const double*)c->b_molacc.p, c->hp.add_ecc, peer_ptrs(c, c->p2p.off_e), c->p2p.world, c->p2p.rank);
     k_p2p_signal<<<1, 32, 0, c->stream>>>(peer_ptrs(c, c->p2p.off_flag), c->p2p.world, 1);
@@ -1148,7 +1149,7 @@ extern "C" int tm_slab_phase_b(tm_ctx* c, const double* qraw_dev, double* e_dev)
   } else {
     k_slab_e<<<1, 1, 0, c->stream>>>((const double*)c->b_molacc.p, e_dev, c->hp.add_ecc);
   }
-  c->launches += 2;
+  c->launches++;
   cudaEventRecord(c->ev[5], c->stream);
   TM_CUDA(cudaGetLastError());
   return TM_OK;
@@ -1161,14 +1162,12 @@ extern "C" int tm_slab_phase_c(tm_ctx* c, const double* e_dev, int flags, double
   SysView s = c->slab_view;
   if (c->p2p.on) {
     char* mine = c->p2p.base[c->p2p.rank];
-    k_p2p_wait<<<1, 1, 0, c->stream>>>(mine + c->p2p.off_flag, c->p2p.world, 1, (int32_t*)c->b_flags.p);
-    k_slab_reduce_e<<<1, 1, 0, c->stream>>>((const double*)(mine + c->p2p.off_e), c->p2p.world, (double*)c->b_molacc.p, (double*)e_dev);
-    c->launches += 2;
-  } else
-  k_slab_set_dedq<<<1, 1, 0, c->stream>>>((double*)c->b_molacc.p, e_dev);
-  k_u<<<nblk(s.nrows), 256, 0, c->stream>>>((const double*)c->b_dedq.p, (const double*)c->b_molacc.p, (const double*)c->b_natom.p,
-                                            (const int32_t*)c->b_rowslot.p, s.nrows, s.maxnatom, c->hp.add_ecc, (float*)c->b_u.p);
-  c->launches += 2;
+    k_p2p_wait_reduce_e<<<1, 1, 0, c->stream>>>(mine + c->p2p.off_flag, c->p2p.world, 1, (int32_t*)c->b_flags.p, (const double*)(mine + c->p2p.off_e),
+                                                (double*)c->b_molacc.p, (double*)e_dev);
+  } else {
+    k_slab_set_dedq<<<1, 1, 0, c->stream>>>((double*)c->b_molacc.p, e_dev);
+  }
+  c->launches++;
   if ((rc = tm_launch_force(c, s, flags))) return rc;
   if (c->p2p.on) {
     char* mine = c->p2p.base[c->p2p.rank];

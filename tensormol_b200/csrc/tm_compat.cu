@@ -16,7 +16,7 @@ static SysView compat_view(int64_t nslots, int64_t nmol, int64_t maxnatom, int64
   s.ncent_max = periodic ? nreal : nslots;
   s.nrows = s.ncent_max;
   s.ncells_cap = nslots + 1024;
-  s.slab_rank = 0; s.slab_world = 1;
+  s.slab_rank = 0; s.slab_world = 1; s.slab_api = 0;
   return s;
 }
 

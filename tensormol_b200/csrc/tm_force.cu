@@ -43,8 +43,8 @@ template <int NAS_MAX, int NRS_MAX>
 __global__ void __launch_bounds__(FORCE_WARPS * 32)
 k_force(const SAtom* __restrict__ sat, const int32_t* __restrict__ rowsidx, const int32_t* __restrict__ rowslot,
         const int32_t* __restrict__ nbcnt, const uint32_t* __restrict__ nbr, int64_t nrows, const __grid_constant__ DevParams P,
-        const float* __restrict__ dGe, const float* __restrict__ dGq, const float* __restrict__ u, int64_t nreal_slots, int fold,
-        float* __restrict__ F, int wfloats) {
+        const float* __restrict__ dGe, const float* __restrict__ dGq, const double* __restrict__ dedq_slot, const double* __restrict__ molacc,
+        const double* __restrict__ inv_n, int64_t maxnatom, int64_t nreal_slots, int fold, float* __restrict__ F, int wfloats) {
   extern __shared__ float smem[];
   int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int64_t row = (int64_t)blockIdx.x * FORCE_WARPS + warp;
@@ -69,7 +69,12 @@ k_force(const SAtom* __restrict__ sat, const int32_t* __restrict__ rowsidx, cons
   {
     const float* ge = dGe + row * P.Dp;
     const float* gq = dGq + row * P.Dp;
-    float uu = u[row];
+    // u = dE/dq_raw = dE/dq_slot - mean_mol(dE/dq): backward of the neutralisation (TFMolInstanceDirect.py:5274-5277)
+    float uu = 0.f;
+    if (P.add_ecc) {
+      int m = (int)(slot / maxnatom);
+      uu = (float)(dedq_slot[slot] - molacc[16 * m + 5] * inv_n[m]);
+    }
     int nrad = P.n_ele * P.nRs_r;
     for (int i = lane; i < nrad; i += 32) {
       int q = i / P.nRs_r, s = i - q * P.nRs_r;
@@ -271,7 +276,8 @@ int tm_launch_force(tm_ctx* c, const SysView& s, int flags) {
     k_force<8, 8><<<blocks, FORCE_WARPS * 32, smem, c->stream>>>(
         (const SAtom*)c->b_satom.p, (const int32_t*)c->b_rowsidx.p, (const int32_t*)c->b_rowslot.p, (const int32_t*)c->b_nbcnt.p,
         (const uint32_t*)c->b_nbr.p, s.nrows, P, (const float*)c->b_dG[TM_NET_ENERGY].p, (const float*)c->b_dG[TM_NET_CHARGE].p,
-        (const float*)c->b_u.p, nreal_slots, fold, (float*)c->b_F.p, (int)wf);
+        (const double*)c->b_dedq.p, (const double*)c->b_molacc.p, (const double*)c->b_natom.p, s.maxnatom, nreal_slots, fold, (float*)c->b_F.p,
+        (int)wf);
   } else {
     if (smem > 48 * 1024 && smem > conf_big) {
       TM_CUDA(cudaFuncSetAttribute(k_force<TM_MAX_SYM, TM_MAX_SYM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -280,7 +286,8 @@ int tm_launch_force(tm_ctx* c, const SysView& s, int flags) {
     k_force<TM_MAX_SYM, TM_MAX_SYM><<<blocks, FORCE_WARPS * 32, smem, c->stream>>>(
         (const SAtom*)c->b_satom.p, (const int32_t*)c->b_rowsidx.p, (const int32_t*)c->b_rowslot.p, (const int32_t*)c->b_nbcnt.p,
         (const uint32_t*)c->b_nbr.p, s.nrows, P, (const float*)c->b_dG[TM_NET_ENERGY].p, (const float*)c->b_dG[TM_NET_CHARGE].p,
-        (const float*)c->b_u.p, nreal_slots, fold, (float*)c->b_F.p, (int)wf);
+        (const double*)c->b_dedq.p, (const double*)c->b_molacc.p, (const double*)c->b_natom.p, s.maxnatom, nreal_slots, fold, (float*)c->b_F.p,
+        (int)wf);
   }
   c->launches++;
   TM_CUDA(cudaGetLastError());

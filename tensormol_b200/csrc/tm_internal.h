@@ -32,6 +32,9 @@ struct __align__(32) SAtom {
 
 // Grid geometry: produced ON THE DEVICE from the bounding box (no host round trip), or laid out by the host from the
 // lattice in the periodic-lattice path.
+// lattice rows (9 doubles) + 1/natom, passed to k_tessellate by value
+struct LatArgs { double v[10]; };
+
 struct GridParams {
   double ox, oy, oz;   // origin
   double inv_cell;     // 1/cell edge
@@ -106,6 +109,7 @@ struct SysView {
   int64_t maxnatom;     // slots per molecule
   int64_t nreal;        // periodic-images mode: centres are slots < nreal; else 0
   int periodic;         // 1 = images mode
+  int slab_api;         // evaluated through tm_slab_phase_a/b/c (any world size): q_raw is combined over the ranks between the phases
   int64_t ncent_max;    // host upper bound on centre count
   int64_t nrows;        // ncent_max + TM_ROW_TILE*n_ele (allocated rows)
   int64_t ncells_cap;
@@ -131,6 +135,7 @@ struct tm_ctx {
   DevParams* dp = nullptr;       // device copy
   Net nets[2][TM_MAX_ELE];
   int gemm_mode = TM_GEMM_TC_SPLIT;
+  bool y_fused = false;   // the last forward pass already scattered q_raw and summed q_raw / Ebp per molecule (k_y_reduce)
   int last_flags = 0;                  // device flag word read by the last check_flags   // parity-preserving tensor-core path is the default
   int Hp[TM_MAX_HIDDEN];         // padded hidden widths
   int Hmax = 0;
@@ -139,8 +144,8 @@ struct tm_ctx {
   DevBuf b_pos, b_Z, b_cellid, b_rank, b_count, b_cstart, b_sorted, b_satom, b_scan_tmp;
   DevBuf b_rowslot, b_rowsidx, b_rowofslot, b_blkcnt, b_rowmeta;
   DevBuf b_nbcnt, b_nboff, b_nbr, b_G, b_Gs, b_ypart, b_act[2][TM_MAX_HIDDEN], b_delta0, b_delta1, b_dG[2], b_y[2];
-  DevBuf b_q, b_qs, b_dedq, b_u, b_F, b_acc, b_bbox, b_grid, b_flags, b_out, b_molacc;
-  DevBuf b_natom, b_lattice;
+  DevBuf b_q, b_qs, b_dedq, b_F, b_acc, b_bbox, b_grid, b_flags, b_out, b_molacc;
+  DevBuf b_natom;
   // host staging (pinned)
   void* h_stage = nullptr;
   size_t h_cap = 0;
@@ -196,7 +201,7 @@ int tm_buf(tm_ctx* c, DevBuf& b, size_t bytes);
 int tm_host_stage(tm_ctx* c, size_t bytes);
 
 // ---- launchers (each returns TM_OK / error) ----
-int tm_launch_tessellate(tm_ctx* c, const double* xyz_real, const int32_t* Z_real, int64_t nreal, const double* lattice9_dev, int ntess, int ilo, int ihi);
+int tm_launch_tessellate(tm_ctx* c, const double* xyz_real, const int32_t* Z_real, int64_t nreal, const LatArgs& lattice, int ntess, int ilo, int ihi);
 int tm_launch_nlist_build(tm_ctx* c, const SysView& s, double rc_grid);
 int tm_launch_rows(tm_ctx* c, const SysView& s);
 int tm_launch_neighbours(tm_ctx* c, const SysView& s);

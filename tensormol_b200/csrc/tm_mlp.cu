@@ -210,24 +210,78 @@ __global__ void k_out_layer(const __grid_constant__ OutTbl T, const int32_t* __r
   if (lane == 0) T.y[net][row] = s + T.b[net][e];
 }
 
-// y[net][row] = b_out + sum of the np partial dot products left by the TM_EPI_ACT_OUT epilogue (fixed order: deterministic)
+// y[net][row] = b_out + sum of the np partial dot products left by the TM_EPI_ACT_OUT epilogue (fixed order: deterministic).
+// The same pass hands the results on (these were three more launches): q_raw into slot order (qraw_slot != nullptr;
+// TFMolInstanceDirect.py:5274), its per-molecule sum for the neutralisation (molacc[16m+4], sum_q != 0) and the
+// per-molecule sum of the atomic energies (molacc[16m+1] = Ebp), one atomic per block and quantity when the block's
+// rows belong to one molecule.
 struct YTbl {
   float b[2][TM_MAX_ELE];
   const float* part[2];
   float* y[2];
 };
-__global__ void k_y_reduce(const __grid_constant__ YTbl T, const int32_t* __restrict__ rowmeta, int64_t nrows, int n_ele, int np) {
+__global__ void __launch_bounds__(256)
+k_y_reduce(const __grid_constant__ YTbl T, const int32_t* __restrict__ rowmeta, int64_t nrows, int n_ele, int np,
+           const int32_t* __restrict__ rowslot, int64_t maxnatom, double* __restrict__ qraw_slot, double* __restrict__ molacc, int sum_q) {
+  __shared__ int s_m[8];
+  __shared__ double s_q[8], s_e[8];
   int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (t >= 2 * nrows) return;
-  int net = (int)(t / nrows);
-  int64_t row = t - (int64_t)net * nrows;
-  int e = row_element(rowmeta, row, n_ele);
+  const bool live = t < 2 * nrows;
+  int net = live ? (int)(t / nrows) : 0;
+  int64_t row = live ? t - (int64_t)net * nrows : 0;
+  int e = live ? row_element(rowmeta, row, n_ele) : -1;
   float s = 0.f;
   if (e >= 0) {
     s = T.b[net][e];
     for (int p = 0; p < np; p++) s += T.part[net][(int64_t)p * nrows + row];
   }
-  T.y[net][row] = s;
+  if (live) T.y[net][row] = s;
+  int slot = (e >= 0) ? rowslot[row] : -1;
+  int m = -1;
+  double vq = 0.0, ve = 0.0;
+  if (slot >= 0) {
+    m = (int)(slot / maxnatom);
+    if (net == TM_NET_CHARGE) {
+      vq = (double)s;
+      if (qraw_slot) qraw_slot[slot] = vq;
+    } else {
+      ve = (double)s;
+    }
+  }
+  // warp, then block aggregation; a warp that straddles molecules falls back to one atomic per thread
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int mmax = m;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mmax = max(mmax, __shfl_xor_sync(FULL, mmax, o));
+  const bool uniform = __all_sync(FULL, m == mmax || m < 0);
+  if (uniform) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      vq += __shfl_xor_sync(FULL, vq, o);
+      ve += __shfl_xor_sync(FULL, ve, o);
+    }
+  } else if (m >= 0) {
+    if (net == TM_NET_CHARGE) { if (sum_q) atomicAdd(&molacc[16 * m + 4], vq); }
+    else atomicAdd(&molacc[16 * m + 1], ve);
+  }
+  if (lane == 0) { s_m[w] = uniform ? mmax : -1; s_q[w] = vq; s_e[w] = ve; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int cur = -1;
+    double aq = 0.0, ae = 0.0;
+    for (int k = 0; k <= 8; k++) {
+      int mk = (k < 8) ? s_m[k] : -2;
+      if (mk == -1) continue;
+      if (mk != cur) {
+        if (cur >= 0) {
+          if (sum_q) atomicAdd(&molacc[16 * cur + 4], aq);
+          atomicAdd(&molacc[16 * cur + 1], ae);
+        }
+        cur = mk; aq = 0.0; ae = 0.0;
+      }
+      if (k < 8) { aq += s_q[k]; ae += s_e[k]; }
+    }
+  }
 }
 
 // Buffer planes: every activation / delta buffer holds either one fp32 plane (fp32 mode) or two fp16 planes [hi | lo]
@@ -308,11 +362,23 @@ int tm_launch_mlp_forward(tm_ctx* c, const SysView& s) {
       Y.y[net] = (float*)c->b_y[net].p;
     }
     int np = 2 * c->Hp[nh - 1] / 128;
-    k_y_reduce<<<(unsigned)((2 * s.nrows + 255) / 256), 256, 0, c->stream>>>(Y, (const int32_t*)c->b_rowmeta.p, s.nrows, ne, np);
+    // single-device runs: q_raw goes straight into slot order (slab ranks exchange it first, tm_slab_phase_a)
+    double* qraw = nullptr;
+    if (!s.slab_api) {
+      int64_t nq = s.periodic ? s.nreal : s.nslots;           // slots that carry an own charge
+      if ((rc = tm_buf(c, c->b_q, (size_t)nq * 8 * 2))) return rc;   // [qraw_slot | q_slot]
+      qraw = (double*)c->b_q.p;
+      TM_CUDA(cudaMemsetAsync(qraw, 0, (size_t)nq * 8, c->stream));   // slots without a row (padding) stay 0
+    }
+    k_y_reduce<<<(unsigned)((2 * s.nrows + 255) / 256), 256, 0, c->stream>>>(Y, (const int32_t*)c->b_rowmeta.p, s.nrows, ne, np,
+                                                                           (const int32_t*)c->b_rowslot.p, s.maxnatom, qraw, (double*)c->b_molacc.p,
+                                                                           s.slab_api ? 0 : 1);
     c->launches++;
+    c->y_fused = true;
     TM_CUDA(cudaGetLastError());
     return TM_OK;
   }
+  c->y_fused = false;
   OutTbl T;
   for (int net = 0; net < 2; net++) {
     for (int e = 0; e < TM_MAX_ELE; e++) {

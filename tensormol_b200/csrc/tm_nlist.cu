@@ -30,8 +30,13 @@ __device__ __forceinline__ double dec_d(unsigned long long b) {
 // coords_ + i*L0 + j*L1 + k*L2 is evaluated left to right with separate roundings like numpy does.
 // ilo..ihi: image indices along the first lattice vector that can reach a slab rank's window (all of them otherwise);
 // the other blocks are never binned (image_block_skipped below) and are not written.
+// The lattice travels as a kernel argument (no pageable copy: the call sequence stays CUDA-graph capturable); the kernel
+// also publishes 1/natom (L.v[9]) for the charge kernels.
 __global__ void k_tessellate(const double* __restrict__ xyz, const int32_t* __restrict__ Z, int64_t nreal,
-                             const double* __restrict__ lat, int ntess, int ilo, int ihi, double* __restrict__ pos, int32_t* __restrict__ Zo) {
+                             const __grid_constant__ LatArgs L, int ntess, int ilo, int ihi, double* __restrict__ pos, int32_t* __restrict__ Zo,
+                             double* __restrict__ inv_n) {
+  const double* lat = L.v;
+  if (blockIdx.x == 0 && threadIdx.x == 0) inv_n[0] = L.v[9];
   int side = 2 * ntess + 1;
   int64_t nimg = (int64_t)side * side * side;
   int64_t total = nimg * nreal;
@@ -61,12 +66,12 @@ __global__ void k_tessellate(const double* __restrict__ xyz, const int32_t* __re
   }
 }
 
-int tm_launch_tessellate(tm_ctx* c, const double* xyz_real, const int32_t* Z_real, int64_t nreal, const double* lat_dev, int ntess, int ilo, int ihi) {
+int tm_launch_tessellate(tm_ctx* c, const double* xyz_real, const int32_t* Z_real, int64_t nreal, const LatArgs& lat, int ntess, int ilo, int ihi) {
   int side = 2 * ntess + 1;
   int64_t total = (int64_t)side * side * side * nreal;
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
-  k_tessellate<<<blocks, 256, 0, c->stream>>>(xyz_real, Z_real, nreal, lat_dev, ntess, ilo, ihi, (double*)c->b_pos.p, (int32_t*)c->b_Z.p);
+  k_tessellate<<<blocks, 256, 0, c->stream>>>(xyz_real, Z_real, nreal, lat, ntess, ilo, ihi, (double*)c->b_pos.p, (int32_t*)c->b_Z.p, (double*)c->b_natom.p);
   c->launches++;
   TM_CUDA(cudaGetLastError());
   return TM_OK;
@@ -165,11 +170,13 @@ __global__ void k_grid_params(const unsigned long long* bb, double rc, int64_t n
 
 // per slot: cell id and arrival rank inside the cell
 // check_inside: the grid was laid out by the host from the lattice; an atom outside it means the caller did not wrap
-// the coordinates into the cell (flag 8).  It is still binned (clamped), so nothing reads out of bounds.
+// the coordinates into the cell (flag 8).  It is still binned (clamped), so nothing reads out of bounds.  In that
+// case the grid arrives as the kernel argument `hg` and this kernel publishes it at *gp for the kernels that follow.
 __global__ void k_cell_count(const double* __restrict__ pos, const int32_t* __restrict__ Z, int64_t n, int64_t maxnatom,
-                             const GridParams* __restrict__ gp, Window win, int check_inside, int32_t* __restrict__ cellid,
+                             GridParams* gp, const __grid_constant__ GridParams hg, Window win, int check_inside, int32_t* __restrict__ cellid,
                              int32_t* __restrict__ rank, int32_t* __restrict__ count, int32_t* __restrict__ flags) {
-  GridParams g = *gp;
+  GridParams g = check_inside ? hg : *gp;
+  if (check_inside && blockIdx.x == 0 && threadIdx.x == 0) *gp = hg;
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
     if (image_block_skipped(t, win)) continue;   // k_scatter applies the same test: cellid / rank of these slots are never read
     if (Z[t] <= 0 || !slot_in_window(pos, t, win)) { cellid[t] = -1; rank[t] = -1; continue; }   // rank[] is reused as sidx_of_slot (-1 = absent)
@@ -262,11 +269,43 @@ __global__ void k_scan_add(int32_t* __restrict__ out, const int32_t* __restrict_
   if (blockIdx.x == 0 && threadIdx.x == 0) out[n] = blksum[nblk];   // total at out[n]
 }
 
+// k_scan_blocks + k_scan_add in one launch for moderate block counts: every block sums the (unscanned) totals of the
+// blocks before it by itself
+__global__ void k_scan_add_self(int32_t* __restrict__ out, const int32_t* __restrict__ blksum, int64_t n, int nblk) {
+  __shared__ int32_t wsum[8];
+  __shared__ int32_t off_s;
+  int32_t part = 0;
+  const int upto = (blockIdx.x == 0) ? nblk : (int)blockIdx.x;   // block 0 also needs the grand total
+  for (int i = threadIdx.x; i < upto; i += 256) part += blksum[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(FULL, part, o);
+  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = part;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int32_t t = 0;
+    for (int i = 0; i < 8; i++) t += wsum[i];
+    if (blockIdx.x == 0) { out[n] = t; t = 0; }   // total at out[n]
+    off_s = t;
+  }
+  __syncthreads();
+  int32_t off = off_s;
+  int64_t base = (int64_t)blockIdx.x * SCAN_TILE + threadIdx.x * 8;
+#pragma unroll
+  for (int i = 0; i < 8; i++)
+    if (base + i < n) out[base + i] += off;
+}
+
 // exclusive scan of in[0..n) into out[0..n], out[n] = total.  tmp needs (nblk+1) ints.
 static int scan_exclusive(tm_ctx* c, const int32_t* in, int32_t* out, int64_t n, int32_t* tmp) {
   int nblk = (int)((n + SCAN_TILE - 1) / SCAN_TILE);
   if (nblk < 1) nblk = 1;
   k_scan_local<<<nblk, 256, 0, c->stream>>>(in, out, tmp, n);
+  if (nblk <= 2048) {
+    k_scan_add_self<<<nblk, 256, 0, c->stream>>>(out, tmp, n, nblk);
+    c->launches += 2;
+    TM_CUDA(cudaGetLastError());
+    return TM_OK;
+  }
   k_scan_blocks<<<1, 1024, 0, c->stream>>>(tmp, nblk);
   k_scan_add<<<nblk, 256, 0, c->stream>>>(out, tmp, n, nblk);
   c->launches += 3;
@@ -328,8 +367,6 @@ __global__ void k_cell_sort_gather(const GridParams* __restrict__ gp, const int3
   }
 }
 
-__global__ void k_set_grid(GridParams v, GridParams* g) { *g = v; }
-
 // ---------------------------------------------------------------- build launcher
 int tm_launch_nlist_build(tm_ctx* c, const SysView& s, double rc_grid) {
   int64_t n = s.nslots;
@@ -352,9 +389,7 @@ int tm_launch_nlist_build(tm_ctx* c, const SysView& s, double rc_grid) {
   Window win{s.window_on, s.slab_g[0], s.slab_g[1], s.slab_g[2], s.win_lo, s.win_hi, s.nreal > 0 ? s.nreal : 1, s.win_ntess, s.win_ilo, s.win_ihi};
   int64_t ncs = s.ncells_cap;   // cells the count / scan passes have to cover
   if (s.grid_host) {
-    k_set_grid<<<1, 1, 0, c->stream>>>(s.hgrid, gp);
-    ncs = s.hgrid.ncells;
-    c->launches += 1;
+    ncs = s.hgrid.ncells;     // k_cell_count publishes the grid
   } else {
     k_bbox_init<<<1, 32, 0, c->stream>>>(bb);
     k_bbox<<<blocks, 256, 0, c->stream>>>((const double*)c->b_pos.p, (const int32_t*)c->b_Z.p, n, win, bb);
@@ -362,7 +397,7 @@ int tm_launch_nlist_build(tm_ctx* c, const SysView& s, double rc_grid) {
     c->launches += 3;
   }
   TM_CUDA(cudaMemsetAsync(c->b_count.p, 0, (ncs + 8) * 4, c->stream));
-  k_cell_count<<<blocks, 256, 0, c->stream>>>((const double*)c->b_pos.p, (const int32_t*)c->b_Z.p, n, s.maxnatom, gp, win, s.grid_host,
+  k_cell_count<<<blocks, 256, 0, c->stream>>>((const double*)c->b_pos.p, (const int32_t*)c->b_Z.p, n, s.maxnatom, gp, s.hgrid, win, s.grid_host,
                                               (int32_t*)c->b_cellid.p, (int32_t*)c->b_rank.p, (int32_t*)c->b_count.p, (int32_t*)c->b_flags.p);
   c->launches += 1;
   if ((rc = scan_exclusive(c, (const int32_t*)c->b_count.p, (int32_t*)c->b_cstart.p, ncs, (int32_t*)c->b_scan_tmp.p))) return rc;
@@ -398,9 +433,15 @@ __device__ __forceinline__ bool is_centre(const SAtom& a, int64_t nreal, int per
   return true;
 }
 
+// Also resets the row tables that k_rows_fill (the launch after next) fills in: rowslot[0..nrows) = rowofslot[0..nq) = -1.
 __global__ void k_rows_count(const SAtom* __restrict__ sat, const int32_t* __restrict__ cstart, const GridParams* __restrict__ gp,
-                             int64_t nreal, int periodic, SlabFilter sf, int32_t* __restrict__ blkcnt) {
+                             int64_t nreal, int periodic, SlabFilter sf, int32_t* __restrict__ blkcnt, int32_t* __restrict__ rowslot,
+                             int64_t nrows, int32_t* __restrict__ rowofslot, int64_t nq) {
   __shared__ int32_t cnt[TM_MAX_ELE];
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < nrows + nq; t += (int64_t)gridDim.x * blockDim.x) {
+    if (t < nrows) rowslot[t] = -1;
+    else rowofslot[t - nrows] = -1;
+  }
   if (threadIdx.x < TM_MAX_ELE) cnt[threadIdx.x] = 0;
   __syncthreads();
   GridParams g = *gp;
@@ -499,13 +540,6 @@ __global__ void k_rows_fill(const SAtom* __restrict__ sat, const int32_t* __rest
   }
 }
 
-__global__ void k_fill2_i32(int32_t* a, int64_t na, int32_t* b, int64_t nb, int32_t v) {
-  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < na + nb; t += (int64_t)gridDim.x * blockDim.x) {
-    if (t < na) a[t] = v;
-    else b[t - na] = v;
-  }
-}
-
 int tm_launch_rows(tm_ctx* c, const SysView& s) {
   int rc;
   int nblk = (int)((s.nslots + ROWS_BLOCK - 1) / ROWS_BLOCK);
@@ -516,19 +550,17 @@ int tm_launch_rows(tm_ctx* c, const SysView& s) {
   if ((rc = tm_buf(c, c->b_rowsidx, s.nrows * 4))) return rc;
   // rowofslot is only read for slots that can be centres (the descriptor output), i.e. the real block in images mode
   int64_t nq = s.periodic ? s.nreal : s.nslots;
-  int fb = (int)std::min<int64_t>((s.nrows + nq + 255) / 256, 148 * 8);
-  k_fill2_i32<<<fb, 256, 0, c->stream>>>((int32_t*)c->b_rowslot.p, s.nrows, (int32_t*)c->b_rowofslot.p, nq, -1);
   const SAtom* sat = (const SAtom*)c->b_satom.p;
   const GridParams* gp = (const GridParams*)c->b_grid.p;
   SlabFilter sf{s.slab_rank, s.slab_world, s.slab_g[0], s.slab_g[1], s.slab_g[2]};
   k_rows_count<<<nblk, ROWS_BLOCK, 0, c->stream>>>(sat, (const int32_t*)c->b_cstart.p, gp, s.nreal, s.periodic, sf,
-                                                   (int32_t*)c->b_blkcnt.p);
+                                                   (int32_t*)c->b_blkcnt.p, (int32_t*)c->b_rowslot.p, s.nrows, (int32_t*)c->b_rowofslot.p, nq);
   k_rows_scan<<<1, 32 * TM_MAX_ELE, 0, c->stream>>>((int32_t*)c->b_blkcnt.p, nblk, c->hp.n_ele, (const int32_t*)c->b_cstart.p, gp,
                                                     (int32_t*)c->b_rowmeta.p);
   k_rows_fill<<<nblk, ROWS_BLOCK, 0, c->stream>>>(sat, (const int32_t*)c->b_cstart.p, gp, s.nreal, s.periodic, sf,
                                                   (const int32_t*)c->b_blkcnt.p, (const int32_t*)c->b_rowmeta.p, (int32_t*)c->b_rowslot.p,
                                                   (int32_t*)c->b_rowsidx.p, (int32_t*)c->b_rowofslot.p);
-  c->launches += 4;
+  c->launches += 3;
   TM_CUDA(cudaGetLastError());
   return TM_OK;
 }

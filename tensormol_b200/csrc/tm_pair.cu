@@ -54,11 +54,16 @@ __global__ void k_mol_sum(const double* __restrict__ v, const int32_t* __restric
   }
 }
 
-// q_slot = qraw - molsum * inv_n[m]  for the first nq slots of each molecule (padding included, Q11);
-// dipole[m] += q * B * x   (TFMolInstanceDirect.py:5278-5279)
-__global__ void k_neutralise(const double* __restrict__ qraw_slot, double* __restrict__ molacc, const double* __restrict__ inv_n,
-                             const double* __restrict__ pos, const int32_t* __restrict__ Z, int64_t maxnatom, int64_t nq_per_mol, int64_t nmol,
-                             double* __restrict__ q_slot) {
+// One launch for the two consumers of the neutralised charges; block (x, m) works on molecule m.
+//  (1) q_slot = qraw - molsum * inv_n[m]  for the first nq slots of each molecule (padding included, Q11);
+//      dipole[m] += q * B * x   (TFMolInstanceDirect.py:5278-5279)
+//  (2) the candidate records of the pair kernel, one float4 per cell-sorted atom of the molecule: position relative to
+//      the grid origin in fp32 (only used for the in/out-of-cutoff test, where the kernel vanishes) and the charge
+//      (images inherit the charge of slot % nreal, TFMolInstanceDirect.py:5892-5893).
+__global__ void k_charges(const double* __restrict__ qraw_slot, double* __restrict__ molacc, const double* __restrict__ inv_n,
+                          const double* __restrict__ pos, const int32_t* __restrict__ Z, int64_t maxnatom, int64_t nq_per_mol,
+                          double* __restrict__ q_slot, const SAtom* __restrict__ sat, const int32_t* __restrict__ cstart,
+                          const GridParams* __restrict__ gp, int64_t nreal, int periodic, float4* __restrict__ pq) {
   int m = blockIdx.y;
   double mean = molacc[16 * m + 4] * inv_n[m];
   double d0 = 0, d1 = 0, d2 = 0;
@@ -76,25 +81,19 @@ __global__ void k_neutralise(const double* __restrict__ qraw_slot, double* __res
     d1 += __shfl_xor_sync(FULL, d1, o);
     d2 += __shfl_xor_sync(FULL, d2, o);
   }
-  if ((threadIdx.x & 31) == 0) {
+  if ((threadIdx.x & 31) == 0 && (d0 != 0.0 || d1 != 0.0 || d2 != 0.0)) {
     atomicAdd(&molacc[16 * m + 6], d0);
     atomicAdd(&molacc[16 * m + 7], d1);
     atomicAdd(&molacc[16 * m + 8], d2);
   }
-}
-
-// Candidate record of the pair kernel, one float4 per cell-sorted atom: position relative to the grid origin in
-// fp32 (only used for the in/out-of-cutoff test, where the kernel vanishes) and the charge (images inherit the
-// charge of slot % nreal, TFMolInstanceDirect.py:5892-5893).
-__global__ void k_q_sorted(const SAtom* __restrict__ sat, const int32_t* __restrict__ cstart, const GridParams* __restrict__ gp,
-                           const double* __restrict__ q_slot, int64_t nreal, int periodic, float4* __restrict__ pq) {
+  // (2): every binned atom has Z > 0, so its charge is qraw - mean (the value (1) stores for its slot)
   GridParams g = *gp;
-  int ntot = cstart[g.ncells];
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ntot; i += gridDim.x * blockDim.x) {
+  int ib = cstart[m * g.ncell_mol], ie = cstart[(m + 1) * g.ncell_mol];
+  for (int i = ib + blockIdx.x * blockDim.x + threadIdx.x; i < ie; i += gridDim.x * blockDim.x) {
     SAtom a = sat[i];
-    int s = a.slot;
-    if (periodic) s = (int)(s % nreal);
-    pq[i] = make_float4((float)(a.x - g.ox), (float)(a.y - g.oy), (float)(a.z - g.oz), (float)q_slot[s]);
+    int64_t s = a.slot;
+    if (periodic) s = s % nreal;
+    pq[i] = make_float4((float)(a.x - g.ox), (float)(a.y - g.oy), (float)(a.z - g.oz), (float)(qraw_slot[s] - mean));
   }
 }
 
@@ -109,22 +108,26 @@ int tm_launch_charges(tm_ctx* c, const SysView& s) {
   // molacc (zeroed by the caller at the start of the evaluation), stride 16 doubles per molecule:
   //   [0] Etotal [1] Ebp [2] Ecc [3] Evdw [4] sum q_raw [5] sum dE/dq [6..8] dipole
   double* molacc = (double*)c->b_molacc.p;
-  int blocks = (int)((s.nrows + 255) / 256);
-  // in slab mode qraw_slot was already all-reduced by the host and written into b_q
-  if (s.slab_world <= 1) {
-    TM_CUDA(cudaMemsetAsync(qraw, 0, (size_t)nq * 8, c->stream));
-    k_qraw_scatter<<<blocks, 256, 0, c->stream>>>((const float*)c->b_y[TM_NET_CHARGE].p, (const int32_t*)c->b_rowslot.p, s.nrows, qraw);
+  // slab mode: qraw_slot was already combined over the ranks and written into b_q; otherwise the tensor-core forward
+  // pass has scattered q_raw and summed it per molecule (k_y_reduce), and the fp32 mode does both here
+  const bool fused = c->y_fused && !s.slab_api;
+  if (!fused) {
+    if (!s.slab_api) {
+      int blocks = (int)((s.nrows + 255) / 256);
+      TM_CUDA(cudaMemsetAsync(qraw, 0, (size_t)nq * 8, c->stream));
+      k_qraw_scatter<<<blocks, 256, 0, c->stream>>>((const float*)c->b_y[TM_NET_CHARGE].p, (const int32_t*)c->b_rowslot.p, s.nrows, qraw);
+      c->launches++;
+    }
+    dim3 gms((unsigned)s.nmol, (unsigned)std::max<int64_t>(1, std::min<int64_t>((nq_per_mol + 2047) / 2048, 64)));
+    k_mol_sum<<<gms, 256, 0, c->stream>>>(qraw, (const int32_t*)c->b_Z.p, s.maxnatom, nq_per_mol, molacc, 4);
     c->launches++;
   }
-  dim3 gms((unsigned)s.nmol, (unsigned)std::max<int64_t>(1, std::min<int64_t>((nq_per_mol + 2047) / 2048, 64)));
-  k_mol_sum<<<gms, 256, 0, c->stream>>>(qraw, (const int32_t*)c->b_Z.p, s.maxnatom, nq_per_mol, molacc, 4);
-  dim3 g((unsigned)std::min<int64_t>((nq_per_mol + 255) / 256, 148 * 4), (unsigned)s.nmol);
-  k_neutralise<<<g, 256, 0, c->stream>>>(qraw, molacc, (const double*)c->b_natom.p, (const double*)c->b_pos.p, (const int32_t*)c->b_Z.p,
-                                         s.maxnatom, nq_per_mol, s.nmol, q);
-  int b2 = (int)std::min<int64_t>((s.nslots + 255) / 256, 148 * 8);
-  k_q_sorted<<<b2, 256, 0, c->stream>>>((const SAtom*)c->b_satom.p, (const int32_t*)c->b_cstart.p, (const GridParams*)c->b_grid.p, q, s.nreal,
-                                        s.periodic, (float4*)c->b_qs.p);
-  c->launches += 3;
+  int64_t per_mol = std::max<int64_t>(nq_per_mol, s.nslots / std::max<int64_t>(1, s.nmol));
+  dim3 g((unsigned)std::max<int64_t>(1, std::min<int64_t>((per_mol + 255) / 256, 148 * 8)), (unsigned)s.nmol);
+  k_charges<<<g, 256, 0, c->stream>>>(qraw, molacc, (const double*)c->b_natom.p, (const double*)c->b_pos.p, (const int32_t*)c->b_Z.p, s.maxnatom,
+                                      nq_per_mol, q, (const SAtom*)c->b_satom.p, (const int32_t*)c->b_cstart.p, (const GridParams*)c->b_grid.p, s.nreal,
+                                      s.periodic, (float4*)c->b_qs.p);
+  c->launches++;
   TM_CUDA(cudaGetLastError());
   return TM_OK;
 }
