@@ -25,3 +25,23 @@ for it in range(5):
     b.slab_phase_c(e, TM_F_FORCE | TM_F_VDW, g); eng.sync(); t3 = time.perf_counter()
 print("world", world, "rank", rank, "wall ms A,B,C:", round((t1-t0)*1e3,3), round((t2-t1)*1e3,3), round((t3-t2)*1e3,3))
 print({k: round(v, 3) for k, v in eng.timings().items() if isinstance(v, float)})
+# the same three phases replayed from one CUDA graph (what a rank executes per step, minus the exchange waits)
+if "--graph" in sys.argv:
+    import ctypes as C
+    from tensormol_b200.engine import GraphedCall
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    eng.set_stream(C.c_void_p(stream.cuda_stream))
+    def step():
+        b.slab_phase_a(xt, zt, n, lat, 1, rank, world, q)
+        b.slab_phase_b(q, e)
+        b.slab_phase_c(e, TM_F_FORCE | TM_F_VDW, g)
+    gc = GraphedCall(step, stream, warmup=2)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for _ in range(5): gc()
+    stream.synchronize()
+    ev0.record(stream)
+    for _ in range(50): gc()
+    ev1.record(stream)
+    stream.synchronize()
+    print("graph replay, ms per rank-step:", round(ev0.elapsed_time(ev1) / 50, 4))
