@@ -505,14 +505,53 @@ __global__ void k_rows_scan(int32_t* __restrict__ blkcnt, int nblk, int n_ele, c
   }
 }
 
+// self_scan != 0 (moderate block counts): blkcnt holds the raw per-block counts of k_rows_count and every block forms
+// its own prefix and the element totals from them (k_rows_scan is not launched; block 0 writes rowmeta).
 __global__ void k_rows_fill(const SAtom* __restrict__ sat, const int32_t* __restrict__ cstart, const GridParams* __restrict__ gp,
                             int64_t nreal, int periodic, SlabFilter sf, const int32_t* __restrict__ blkcnt,
-                            const int32_t* __restrict__ rowmeta, int32_t* __restrict__ rowslot, int32_t* __restrict__ rowsidx,
-                            int32_t* __restrict__ rowofslot) {
+                            int32_t* __restrict__ rowmeta, int32_t* __restrict__ rowslot, int32_t* __restrict__ rowsidx,
+                            int32_t* __restrict__ rowofslot, int self_scan, int nblk, int n_ele) {
   __shared__ int32_t wcnt[32][TM_MAX_ELE];
+  __shared__ int32_t s_pre[32][TM_MAX_ELE], s_tot[32][TM_MAX_ELE];
+  __shared__ int32_t s_base[TM_MAX_ELE], s_mine[TM_MAX_ELE];
   GridParams g = *gp;
   int ntot = cstart[g.ncells];
-  if (blockIdx.x * ROWS_BLOCK >= ntot) return;
+  if (blockIdx.x * ROWS_BLOCK >= ntot && !(self_scan && blockIdx.x == 0)) return;
+  if (self_scan) {
+    static_assert(TM_MAX_ELE == 8, "lane & 7 selects the element");
+    const int live = min(nblk, (ntot + ROWS_BLOCK - 1) / ROWS_BLOCK);   // blocks that counted anything
+    const int el = threadIdx.x & 7;
+    int32_t pre = 0, tot = 0;
+    for (int i = threadIdx.x >> 3; i < live; i += ROWS_BLOCK / 8) {
+      int32_t v = blkcnt[i * TM_MAX_ELE + el];
+      tot += v;
+      if (i < (int)blockIdx.x) pre += v;
+    }
+    pre += __shfl_xor_sync(FULL, pre, 8); tot += __shfl_xor_sync(FULL, tot, 8);
+    pre += __shfl_xor_sync(FULL, pre, 16); tot += __shfl_xor_sync(FULL, tot, 16);
+    if ((threadIdx.x & 31) < 8) { s_pre[threadIdx.x >> 5][el] = pre; s_tot[threadIdx.x >> 5][el] = tot; }
+    __syncthreads();
+    if (threadIdx.x < TM_MAX_ELE) {
+      int32_t p2 = 0, t2 = 0;
+      for (int w = 0; w < 32; w++) { p2 += s_pre[w][threadIdx.x]; t2 += s_tot[w][threadIdx.x]; }
+      s_mine[threadIdx.x] = p2;
+      s_tot[0][threadIdx.x] = (threadIdx.x < n_ele) ? t2 : 0;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int32_t base = 0, total = 0;
+      for (int k = 0; k < TM_MAX_ELE; k++) {
+        int32_t cnt = s_tot[0][k];
+        s_base[k] = base;
+        if (blockIdx.x == 0) { rowmeta[2 * k] = base; rowmeta[2 * k + 1] = cnt; }
+        base += ((cnt + TM_ROW_TILE - 1) / TM_ROW_TILE) * TM_ROW_TILE;
+        total += cnt;
+      }
+      if (blockIdx.x == 0) { rowmeta[2 * TM_MAX_ELE] = total; rowmeta[2 * TM_MAX_ELE + 1] = base; }
+    }
+    __syncthreads();
+    if (blockIdx.x * ROWS_BLOCK >= ntot) return;
+  }
   int i = blockIdx.x * ROWS_BLOCK + threadIdx.x;
   int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   int e = -1, slot = -1;
@@ -533,7 +572,7 @@ __global__ void k_rows_fill(const SAtom* __restrict__ sat, const int32_t* __rest
   if (e >= 0) {
     int off = 0;
     for (int ww = 0; ww < w; ww++) off += wcnt[ww][e];
-    int row = rowmeta[2 * e] + blkcnt[blockIdx.x * TM_MAX_ELE + e] + off + myrank;
+    int row = (self_scan ? s_base[e] + s_mine[e] : rowmeta[2 * e] + blkcnt[blockIdx.x * TM_MAX_ELE + e]) + off + myrank;
     rowslot[row] = slot;
     rowsidx[row] = i;
     rowofslot[slot] = row;
@@ -555,12 +594,16 @@ int tm_launch_rows(tm_ctx* c, const SysView& s) {
   SlabFilter sf{s.slab_rank, s.slab_world, s.slab_g[0], s.slab_g[1], s.slab_g[2]};
   k_rows_count<<<nblk, ROWS_BLOCK, 0, c->stream>>>(sat, (const int32_t*)c->b_cstart.p, gp, s.nreal, s.periodic, sf,
                                                    (int32_t*)c->b_blkcnt.p, (int32_t*)c->b_rowslot.p, s.nrows, (int32_t*)c->b_rowofslot.p, nq);
-  k_rows_scan<<<1, 32 * TM_MAX_ELE, 0, c->stream>>>((int32_t*)c->b_blkcnt.p, nblk, c->hp.n_ele, (const int32_t*)c->b_cstart.p, gp,
-                                                    (int32_t*)c->b_rowmeta.p);
+  const int self_scan = nblk <= 2048 ? 1 : 0;   // every fill block re-reads the nblk counts: only while that is cheap
+  if (!self_scan) {
+    k_rows_scan<<<1, 32 * TM_MAX_ELE, 0, c->stream>>>((int32_t*)c->b_blkcnt.p, nblk, c->hp.n_ele, (const int32_t*)c->b_cstart.p, gp,
+                                                      (int32_t*)c->b_rowmeta.p);
+    c->launches++;
+  }
   k_rows_fill<<<nblk, ROWS_BLOCK, 0, c->stream>>>(sat, (const int32_t*)c->b_cstart.p, gp, s.nreal, s.periodic, sf,
-                                                  (const int32_t*)c->b_blkcnt.p, (const int32_t*)c->b_rowmeta.p, (int32_t*)c->b_rowslot.p,
-                                                  (int32_t*)c->b_rowsidx.p, (int32_t*)c->b_rowofslot.p);
-  c->launches += 3;
+                                                  (const int32_t*)c->b_blkcnt.p, (int32_t*)c->b_rowmeta.p, (int32_t*)c->b_rowslot.p,
+                                                  (int32_t*)c->b_rowsidx.p, (int32_t*)c->b_rowofslot.p, self_scan, nblk, c->hp.n_ele);
+  c->launches += 2;
   TM_CUDA(cudaGetLastError());
   return TM_OK;
 }
@@ -578,6 +621,27 @@ __device__ __forceinline__ double ref_dist(const SAtom& a, double xi, double yi,
 // Entry = cell-sorted index of j, bit 31 set when j is also inside the angular cutoff.
 // One pass: row r owns the TM_NB_STRIDE slots nbr[r*TM_NB_STRIDE ...]; nbcnt[r] = number written.  More than
 // TM_NB_STRIDE radial neighbours of one centre raises flag 2 (TM_ECAP).
+// The accept test `sqrt(d2) + 1e-13 < rc` (MolEmb.cpp:1213-1218, one rounding per operation) decided from d2 alone
+// wherever that is safe: surely inside below (rc - 2e-13)^2 (1 - 1e-15), surely outside above rc^2 (1 + 1e-15); only the
+// band in between (relative width ~1e-13) takes the exact square-root path.
+struct AcceptBand { double lo, hi, rc; };
+__device__ __forceinline__ AcceptBand accept_band(double rc) {
+  AcceptBand a;
+  double t = rc - 2.0e-13;
+  a.lo = t > 0.0 ? t * t * (1.0 - 1.0e-15) : -1.0;
+  a.hi = rc * rc * (1.0 + 1.0e-15);
+  a.rc = rc;
+  return a;
+}
+__device__ __forceinline__ bool accept(double d2, const AcceptBand& a) {
+  if (d2 < a.lo) return true;
+  if (d2 > a.hi) return false;
+  return __dadd_rn(__dsqrt_rn(d2), 0.0000000000001) < a.rc;
+}
+
+// The nine (x, y) columns of a centre are resolved by nine lanes at once and their z-runs walked as ONE index space,
+// three 32-candidate passes at a time with the loads of all three issued first (the column-by-column version was a
+// chain of ~18 dependent L2 round trips per warp).  Order of a row = column order, then cell-sorted index: unchanged.
 __global__ void k_neighbours(const SAtom* __restrict__ sat, const int32_t* __restrict__ cstart, const GridParams* __restrict__ gp,
                              const int32_t* __restrict__ rowsidx, const int32_t* __restrict__ rowslot, int64_t nrows, int64_t maxnatom,
                              double rr, double ra, int32_t* __restrict__ nbcnt, uint32_t* __restrict__ nbr, int32_t* __restrict__ flags) {
@@ -594,32 +658,63 @@ __global__ void k_neighbours(const SAtom* __restrict__ sat, const int32_t* __res
   int cy = cell_coord(ci.y, g.oy, g.inv_cell, g.gy);
   int cz = cell_coord(ci.z, g.oz, g.inv_cell, g.gz);
   int z0 = max(cz - 1, 0), z1 = min(cz + 1, g.gz - 1);
+  // lane c < 9 owns column (dx, dy) = (c / 3 - 1, c % 3 - 1): run [cb, ce)
+  int cb = 0, ce = 0;
+  if (lane < 9) {
+    int x = cx + lane / 3 - 1, y = cy + lane % 3 - 1;
+    if (x >= 0 && x < g.gx && y >= 0 && y < g.gy) {
+      int cbase = m * g.ncell_mol + (x * g.gy + y) * g.gz;
+      cb = cstart[cbase + z0];
+      ce = cstart[cbase + z1 + 1];
+    }
+  }
+  int len = ce - cb, inc = len;
+#pragma unroll
+  for (int o = 1; o < 16; o <<= 1) {
+    int t = __shfl_up_sync(FULL, inc, o);
+    if (lane >= o) inc += t;
+  }
+  const int T = __shfl_sync(FULL, inc, 8);
+  // start[c] = first flat index of column c, off[c] = cb_c - start_c  (j = idx + off[c])
+  int start[9], off[9];
+#pragma unroll
+  for (int c = 0; c < 9; c++) {
+    start[c] = __shfl_sync(FULL, inc - len, c);
+    off[c] = __shfl_sync(FULL, cb - (inc - len), c);
+  }
+  const AcceptBand br = accept_band(rr), ba = accept_band(ra);
   int total = 0;
   uint32_t* out = nbr + row * TM_NB_STRIDE;
-  for (int dx = -1; dx <= 1; dx++) {
-    int x = cx + dx;
-    if (x < 0 || x >= g.gx) continue;
-    for (int dy = -1; dy <= 1; dy++) {
-      int y = cy + dy;
-      if (y < 0 || y >= g.gy) continue;
-      int cbase = m * g.ncell_mol + (x * g.gy + y) * g.gz;
-      int b = cstart[cbase + z0], e = cstart[cbase + z1 + 1];
-      for (int j0 = b; j0 < e; j0 += 32) {
-        int j = j0 + lane;
-        bool ok = false, ang = false;
-        if (j < e && j != si) {
-          SAtom aj = sat[j];
-          double d = ref_dist(aj, ci.x, ci.y, ci.z);
-          ok = d < rr;
-          ang = d < ra;
-        }
-        unsigned mk = __ballot_sync(FULL, ok);
-        if (ok) {
-          int w = total + __popc(mk & ((1u << lane) - 1));
-          if (w < TM_NB_STRIDE) out[w] = (uint32_t)j | (ang ? 0x80000000u : 0u);
-        }
-        total += __popc(mk);
+  for (int i0 = 0; i0 < T; i0 += 96) {
+    int jj[3];
+    bool live[3];
+    SAtom aj[3];
+#pragma unroll
+    for (int u = 0; u < 3; u++) {
+      int idx = i0 + 32 * u + lane;
+      int j = idx + off[0];
+#pragma unroll
+      for (int c = 1; c < 9; c++) j = (idx >= start[c]) ? idx + off[c] : j;
+      jj[u] = j;
+      live[u] = idx < T && j != si;
+      if (live[u]) aj[u] = sat[j];
+    }
+#pragma unroll
+    for (int u = 0; u < 3; u++) {
+      if (i0 + 32 * u >= T) break;
+      bool ok = false, ang = false;
+      if (live[u]) {
+        double dx = __dsub_rn(ci.x, aj[u].x), dy = __dsub_rn(ci.y, aj[u].y), dz = __dsub_rn(ci.z, aj[u].z);
+        double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+        ok = accept(d2, br);
+        ang = ok && accept(d2, ba);
       }
+      unsigned mk = __ballot_sync(FULL, ok);
+      if (ok) {
+        int w = total + __popc(mk & ((1u << lane) - 1));
+        if (w < TM_NB_STRIDE) out[w] = (uint32_t)jj[u] | (ang ? 0x80000000u : 0u);
+      }
+      total += __popc(mk);
     }
   }
   if (lane == 0) {

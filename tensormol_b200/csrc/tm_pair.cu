@@ -22,7 +22,7 @@
 
 #define FULL 0xffffffffu
 #define PAIR_WARPS 8
-#define QCAP 64
+#define QCAP 96
 
 // ---- charges -----------------------------------------------------------------------------------
 // y_charge[row] -> qraw_slot[slot]; per-molecule sums in double
@@ -270,7 +270,34 @@ k_pair(const SAtom* __restrict__ sat, const float4* __restrict__ pq, const int32
       int k = __ffs(live) - 1;
       live &= live - 1;
       int b = __shfl_sync(FULL, cb, k), e = __shfl_sync(FULL, ce, k);
-      for (int j0 = b; j0 < e; j0 += 32) {
+      int j0 = b;
+      // 64 candidates per pass while the run is long enough (two loads in flight, one set of loop / queue bookkeeping) ...
+      for (; j0 + 32 < e; j0 += 64) {
+        int ja = j0 + lane, jb = ja + 32;
+        float4 pa = pq[ja];
+        float d2b = 3.0e38f;
+        if (jb < e) {
+          float4 pb = pq[jb];
+          float bx = pb.x - pi.x, by = pb.y - pi.y, bz = pb.z - pi.z;
+          d2b = bx * bx + by * by + bz * bz;
+        }
+        float ddx = pa.x - pi.x, ddy = pa.y - pi.y, ddz = pa.z - pi.z;
+        float d2a = ddx * ddx + ddy * ddy + ddz * ddz;
+        bool oka = (d2a < rc2) && (ja != si), okb = (d2b < rc2) && (jb != si);
+        unsigned mka = __ballot_sync(FULL, oka), mkb = __ballot_sync(FULL, okb);
+        int na = __popc(mka);
+        if (oka) q_j[warp][qn + __popc(mka & lt_mask)] = ja;
+        if (okb) q_j[warp][qn + na + __popc(mkb & lt_mask)] = jb;
+        qn += na + __popc(mkb);
+        __syncwarp();
+        while (qn >= 32) {
+          eval(q_j[warp][qn - 32 + lane]);
+          qn -= 32;
+          __syncwarp();
+        }
+      }
+      // ... and a last pass of up to 32
+      if (j0 < e) {
         int j = j0 + lane;
         float d2 = 3.0e38f;
         if (j < e) {
