@@ -71,6 +71,7 @@ struct alignas(64) TcParams {
   TcGroup g[TC_MAX_GROUPS];
   int ngroups, act_kind;
   float act_alpha;
+  int fuse_n;                 // single-CTA tiles: A_hi x [B_hi | B_lo] as ONE MMA of N = 2 BN (see the MMA issuer)
   unsigned long long* prof;   // TC_PROFILE builds: per-CTA cycle counters
 };
 
@@ -361,6 +362,13 @@ k_gemm_tc(const __grid_constant__ TcParams P, const int32_t* __restrict__ rowmet
     if (rank == 0 && elect_one()) {
       // instruction descriptor: D=f32, A=B=f16, both K-major, N=BN, M=128 (256 across a CTA pair)
       constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((TC_BM * NCTA) >> 4) << 24);
+      // The B_hi and B_lo tiles of a stage are adjacent in shared memory and (main, cross) are adjacent in TMEM, so
+      // A_hi x [B_hi | B_lo] is one MMA of N = 2 BN writing [main | cross]; A_lo x B_hi then accumulates into cross.
+      // Same tensor-pipe time (N/2 cycles per MMA) but A_hi is fetched from shared memory once instead of twice: the
+      // operand reads of a k-step drop from 24 to 20 KB (the M = 128, N = 128 MMA needs 128 B/clk, all the shared-memory
+      // bandwidth there is, while the TMA is writing the next stage).
+      constexpr uint32_t idesc2 = (1u << 4) | ((uint32_t)((2 * BN) >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      const bool fuse = (NCTA == 1) && P.fuse_n != 0;
       int stage = 0;
       uint32_t phase = 0;
       uint32_t chunk_it = 0;
@@ -394,6 +402,9 @@ k_gemm_tc(const __grid_constant__ TcParams P, const int32_t* __restrict__ rowmet
                 umma_f16_pair(d_main, a_hi + koff, b_hi + koff, idesc, acc);
                 umma_f16_pair(d_cross, a_lo + koff, b_hi + koff, idesc, acc);
                 umma_f16_pair(d_cross, a_hi + koff, b_lo + koff, idesc, 1u);
+              } else if (fuse) {
+                umma_f16(d_main, a_hi + koff, b_hi + koff, idesc2, acc);
+                umma_f16(d_cross, a_lo + koff, b_hi + koff, idesc, 1u);
               } else {
                 umma_f16(d_main, a_hi + koff, b_hi + koff, idesc, acc);
                 umma_f16(d_cross, a_lo + koff, b_hi + koff, idesc, acc);
@@ -734,6 +745,9 @@ int tm_gemm_tc_launch(tm_ctx* c, const GemmGroup* groups, int ngroups, const int
   if (!c->tc_params) c->tc_params = new TcParams();
   TcParams& P = *(TcParams*)c->tc_params;   // large (16 groups x 4 tensor maps); filled per launch, calls on one ctx are serialised by contract
   P.ngroups = ngroups; P.act_kind = c->hp.activation; P.act_alpha = c->hp.act_alpha;
+  static int fuse_env = -1;     // TM_GEMM_FUSE=0 issues the three N = BN MMAs per k-step instead (measurements)
+  if (fuse_env < 0) { const char* e = getenv("TM_GEMM_FUSE"); fuse_env = (e && atoi(e) == 0) ? 0 : 1; }
+  P.fuse_n = fuse_env;
   P.prof = nullptr;
 #ifdef TC_PROFILE
   {
