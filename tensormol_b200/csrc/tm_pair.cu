@@ -240,11 +240,14 @@ k_pair(const SAtom* __restrict__ sat, const float4* __restrict__ pq, const int32
   int ny = y1 - y0 + 1, ncol = (x1 - x0 + 1) * ny;
   PairAcc A = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   int qn = 0;
+  // image partners: 1/2 under the reference's convention (header); 1 when the image rows are folded onto their real
+  // atom (TM_F_FOLD_IMAGES, do_force bit 1): then the row gradient is the derivative of the periodic energy
+  const float w_img = (do_force & 2) ? 1.0f : 0.5f;
   auto eval = [&](int j) {
     SAtom a = sat[j];
     float ddx = (float)(a.x - ci.x), ddy = (float)(a.y - ci.y), ddz = (float)(a.z - ci.z);
     float d2 = ddx * ddx + ddy * ddy + ddz * ddz;
-    pair_eval<ECC, VDW>(P, d2, ddx, ddy, ddz, qi, pq[j].w, s_c6[warp][a.e], s_rs12[warp][a.e], (a.slot < nreal_slots) ? 1.0f : 0.5f, A);
+    pair_eval<ECC, VDW>(P, d2, ddx, ddy, ddz, qi, pq[j].w, s_c6[warp][a.e], s_rs12[warp][a.e], (a.slot < nreal_slots) ? 1.0f : w_img, A);
   };
   for (int c0 = 0; c0 * split < ncol; c0 += 32) {
     // lane -> column (c0+lane)*split + sub: run [cb, ce) or empty
@@ -331,7 +334,7 @@ k_pair(const SAtom* __restrict__ sat, const float4* __restrict__ pq, const int32
   if (lane == 0) {
     if (split == 1) dedq_slot[slot] = (double)A.dedq;
     else atomicAdd(&dedq_slot[slot], (double)A.dedq);   // zeroed by the launcher
-    if (do_force) {
+    if (do_force & 1) {
       atomicAdd(F + 3 * (int64_t)slot, A.gx);
       atomicAdd(F + 3 * (int64_t)slot + 1, A.gy);
       atomicAdd(F + 3 * (int64_t)slot + 2, A.gz);
@@ -356,7 +359,7 @@ int tm_launch_pair(tm_ctx* c, const SysView& s, int flags) {
   auto launch = [&](auto kern) {
     kern<<<blocks, PAIR_WARPS * 32, 0, c->stream>>>((const SAtom*)c->b_satom.p, (const float4*)c->b_qs.p, (const int32_t*)c->b_cstart.p,
                                                     (const GridParams*)c->b_grid.p, (const int32_t*)c->b_rowsidx.p, (const int32_t*)c->b_rowslot.p,
-                                                    s.nrows, s.maxnatom, (int)nq, c->hp, (flags & TM_F_FORCE) ? 1 : 0,
+                                                    s.nrows, s.maxnatom, (int)nq, c->hp, ((flags & TM_F_FORCE) ? 1 : 0) | ((flags & TM_F_FOLD_IMAGES) ? 2 : 0),
                                                     (float)c->params.ee_cutoff_off, split, (double*)c->b_dedq.p, (float*)c->b_F.p, (double*)c->b_molacc.p);
   };
   bool ecc = c->hp.add_ecc != 0, vdw = (flags & TM_F_VDW) != 0;

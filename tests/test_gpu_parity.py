@@ -207,6 +207,25 @@ def test_eval_water_box_periodic_vs_oracle(mode, hidden):
     _check_grad(r["gradient"], o["gradient"][:, :len(Z)])
 
 
+def test_fold_images_gradient_is_the_oracles_gradient_summed_over_image_rows():
+    """TM_F_FOLD_IMAGES (non-reference option): the gradient rows the reference drops (image rows) are folded
+    onto slot % nreal -- descriptor terms by the force kernel, pair terms by full weight on image partners; the result is
+    the oracle's autograd gradient summed over each atom's 27 rows, i.e. the derivative of the periodic energy."""
+    from oracle import oracle_graph as og
+    from oracle import oracle_np as onp
+    Z, X, lat = water_box(6)
+    eng, W, P = _engine([1, 8], [128, 96, 64], 11)
+    Xw = onp.modulo_lattice(lat, X)
+    Zt, Xt = onp.tess_lattice(lat, Z.astype(np.uint8), Xw, P["EECutoffOff"])
+    o = og.Oracle([1, 8], W, P).evaluate_periodic(Xt, Zt, len(Z))
+    g_fold = o["gradient"][0].reshape(27, len(Z), 3).sum(0)
+    assert np.abs(g_fold.sum(0)).max() <= 1e-12                      # translation invariance of the oracle energy
+    for r in (eng.evaluate_lattice(Xw, Z, lat, 1, fold=True), eng.evaluate_images(Xt, Zt.astype(np.int32), len(Z), fold=True)):
+        _check_energy(r["Etotal"], o["Etotal"], "Etotal")
+        _check_grad(r["gradient"][0], g_fold)
+    assert np.abs(g_fold - o["gradient"][0, :len(Z)]).max() > 1e-3   # and it is not the reference-convention gradient
+
+
 def test_energy_only_and_no_ecc_flags():
     from oracle import oracle_graph as og
     g = load_golden("h2o_cluster")
