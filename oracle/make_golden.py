@@ -128,6 +128,41 @@ def periodic_case(name, Z, X, L, hidden, seed):
     print(name, "ntess", ntess, "E", res["Etotal"], "n_ee", res["n_ee"], "sym pin err", np.abs(out["ref_sym"] - res["descriptors"][0]).max())
 
 
+def protein_case(name, hidden, seed, nsample=48):
+    """Config C5: datasets/2evq.xyz -> OnlyAtoms([1, 6, 7, 8]) (1,568 atoms: the peptide in its explicit
+    water), shifted to the positive octant, cell = bounding box, as samples/test_neb.py:91-113 sets it up.  Pins: the
+    reference MolEmb's neighbour rows on the 27-image tessellation (4.6 / 3.1 A) and its ANI-1 descriptors for a sample of
+    rows (the full matrix is 9.6 MB), plus the float64 oracle's outputs with seeded random-init nets."""
+    import MolEmb
+    Z, X, _ = read_xyz_frames(os.path.join(REF, "datasets", "2evq.xyz"))[0]
+    keep = np.isin(Z, [1, 6, 7, 8])
+    Z, X = Z[keep], X[keep]
+    X = X - X.min(0)
+    lat = np.diag(X.max(0))
+    P = og.default_params()
+    eles = sorted(set(int(z) for z in Z))
+    W = random_weights(eles, descriptor_width(len(eles), P), hidden, seed)
+    Zt, Xt = onp.tess_lattice(lat, Z.astype(np.uint8), X, P["EECutoffOff"])      # atoms on the faces stay where they are
+    nreal = len(Z)
+    assert len(Zt) == 27 * nreal
+    res = og.Oracle(eles, W, P).evaluate_periodic(Xt, Zt, nreal)
+    out = dict(Z=Z, xyz=X, lattice=lat, ntess=1, eles=np.array(eles), hidden=np.array(hidden), seed=seed)
+    for rc, tag in ((P["AN1_r_Rc"], "rr"), (P["AN1_a_Rc"], "ra")):
+        off, idx = csr_from_lists(MolEmb.Make_NListNaive(np.ascontiguousarray(Xt), float(rc), nreal, 1))
+        out[f"ref_nl_{tag}_off"], out[f"ref_nl_{tag}_idx"] = off.astype(np.int32), idx.astype(np.int32)
+    rows = np.sort(np.random.default_rng(0).choice(nreal, nsample, replace=False))
+    near = np.unique(np.concatenate([np.arange(nreal), out["ref_nl_rr_idx"]]))
+    sub = MolEmb.Make_ANI1_Sym(symparams(P), np.ascontiguousarray(Xt[near]), Zt[near].astype(np.uint8), np.array(eles, np.uint8), -1)
+    out["sym_rows"] = rows
+    out["ref_sym"] = sub[:nreal][rows]
+    for k in ("Etotal", "Ebp", "Ebp_atom", "Ecc", "Evdw", "dipole"):
+        out["oracle_" + k] = res[k]
+    out["oracle_gradient"] = res["gradient"][:, :nreal]
+    out["oracle_charge"] = res["charge"][:, :nreal]
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", name + ".npz"), **out)
+    print(name, "atoms", nreal, "E", res["Etotal"], "n_ee", res["n_ee"], "sym pin err", np.abs(out["ref_sym"] - res["descriptors"][0][rows]).max())
+
+
 def reference_python_pins():
     """Outputs of the reference's OWN Python (Neighbors.py, Periodic.py Lattice, Util.py DSF, PhysicalData.py) executed
     in place by oracle/ref_py.py on top of the reference's own MolEmb build -> tests/golden/ref_python_pins.npz."""
@@ -225,6 +260,8 @@ def reference_python_pins():
 
 def main():
     os.makedirs(os.path.join(ROOT, "tests", "golden"), exist_ok=True)
+    if "--only-protein" in sys.argv:
+        return protein_case("evq2_periodic", [200, 200, 200], 5)
     reference_python_pins()
     Z, X, _ = read_xyz_frames(os.path.join(REF, "datasets", "H2O_cluster.xyz"))[0]
     aperiodic_case("h2o_cluster", Z, X, [64, 48, 32], 0, True)
@@ -232,6 +269,7 @@ def main():
     aperiodic_case("morphine", Z, X, [96, 64, 64], 1, False)
     Z, X, _ = read_xyz_frames(os.path.join(REF, "datasets", "water_tiny.xyz"))[0]
     periodic_case("water_tiny_periodic", Z, X, 9.3215, [64, 48, 32], 2)
+    protein_case("evq2_periodic", [200, 200, 200], 5)
 
 
 if __name__ == "__main__":

@@ -450,6 +450,22 @@ static SysView make_view(tm_ctx* c, int64_t nslots, int64_t nmol, int64_t maxnat
   return s;
 }
 
+// TM_TRACE=1 (debugging): synchronise after every stage and report it on stderr, so that a stage that never finishes or
+// faults is named.  Off by default (one getenv per process); never active during graph capture.
+void tm_trace(tm_ctx* c, const char* what) {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("TM_TRACE"); on = (e && atoi(e) != 0) ? 1 : 0; }
+  if (!on) return;
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(c->stream, &st);
+  if (st != cudaStreamCaptureStatusNone) return;
+  fprintf(stderr, "[tm_trace] %s ...", what);
+  fflush(stderr);
+  cudaError_t e = cudaStreamSynchronize(c->stream);
+  fprintf(stderr, " %s\n", e == cudaSuccess ? "ok" : cudaGetErrorString(e));
+  fflush(stderr);
+}
+
 // stages up to and including the nets' forward pass (pos/Z/inv_n already on the device)
 static int stage_a(tm_ctx* c, const SysView& s) {
   int rc;
@@ -461,13 +477,19 @@ static int stage_a(tm_ctx* c, const SysView& s) {
   TM_CUDA(cudaMemsetAsync(c->b_molacc.p, 0, (size_t)s.nmol * 16 * 8, c->stream));
   TM_CUDA(cudaMemsetAsync(c->b_F.p, 0, (size_t)nq * 3 * 4, c->stream));
   cudaEventRecord(c->ev[1], c->stream);
+  tm_trace(c, "inputs");
   if ((rc = tm_launch_nlist_build(c, s, c->params.r_Rc))) return rc;
+  tm_trace(c, "cell list");
   if ((rc = tm_launch_rows(c, s))) return rc;
+  tm_trace(c, "rows");
   if ((rc = tm_launch_neighbours(c, s))) return rc;
+  tm_trace(c, "neighbour rows");
   cudaEventRecord(c->ev[2], c->stream);
   if ((rc = tm_launch_desc(c, s))) return rc;
+  tm_trace(c, "descriptors");
   cudaEventRecord(c->ev[3], c->stream);
   if ((rc = tm_launch_mlp_forward(c, s))) return rc;
+  tm_trace(c, "nets forward");
   cudaEventRecord(c->ev[4], c->stream);
   return TM_OK;
 }
@@ -475,7 +497,9 @@ static int stage_a(tm_ctx* c, const SysView& s) {
 static int stage_b(tm_ctx* c, const SysView& s, int flags) {
   int rc;
   if ((rc = tm_launch_charges(c, s))) return rc;
+  tm_trace(c, "charges");
   if ((rc = tm_launch_pair(c, s, flags))) return rc;
+  tm_trace(c, "pair kernel");
   cudaEventRecord(c->ev[5], c->stream);
   return TM_OK;
 }
@@ -484,8 +508,10 @@ static int stage_c(tm_ctx* c, const SysView& s, int flags) {
   int rc;
   if (flags & TM_F_FORCE) {
     if ((rc = tm_launch_mlp_backward(c, s))) return rc;
+    tm_trace(c, "nets backward");
     cudaEventRecord(c->ev[6], c->stream);
     if ((rc = tm_launch_force(c, s, flags))) return rc;
+    tm_trace(c, "force kernel");
   } else {
     cudaEventRecord(c->ev[6], c->stream);
   }

@@ -436,7 +436,8 @@ k_gemm_tc(const __grid_constant__ TcParams P, const int32_t* __restrict__ rowmet
     for (int t = unit; t < total_tiles; t += nunits, titer++) {
       int g, rt, ct;
       decode(t, g, rt, ct);
-      if (BN == 64 && (titer & 1) != half) {        // the other warp of this lane quarter drains this tile
+      if (BN == 64 && (titer & 1) != half) {        // the other warp of this lane quarter drains this tile (the launcher keeps
+                                                    // BN = 64 to K loops of at most 3 chunks: see tm_gemm_tc_launch)
         chunk_it += (uint32_t)((P.g[g].K / TC_BK + TC_CHUNK - 1) / TC_CHUNK);
         continue;
       }
@@ -770,7 +771,15 @@ int tm_gemm_tc_launch(tm_ctx* c, const GemmGroup* groups, int ngroups, const int
 #endif
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
-  const int bn = (c->gemm_mode == TM_GEMM_TC_SPLIT_N64) ? 64 : (c->gemm_mode == TM_GEMM_TC_SPLIT_N128) ? TC_BN : (ncta == 1) ? choose_bn(groups, ngroups, expect_rows, c->hp.n_ele, sms) : TC_BN;
+  int bn = (c->gemm_mode == TM_GEMM_TC_SPLIT_N64) ? 64 : (c->gemm_mode == TM_GEMM_TC_SPLIT_N128) ? TC_BN : (ncta == 1) ? choose_bn(groups, ngroups, expect_rows, c->hp.n_ele, sms) : TC_BN;
+  // The BN = 64 kernel lets the two epilogue warps of a lane quarter take alternate tiles, so a warp does not observe the
+  // accumulator-full barriers of the tiles it skips.  Its parity wait on the first chunk of its next tile is only exact
+  // while the previous user of that TMEM pair (4 chunks earlier) lies at or before the last chunk the warp did observe,
+  // i.e. while a tile has fewer chunks than there are pairs: K <= 3 * TC_CHUNK * TC_BK = 768.  Longer K loops (hidden
+  // layers of 1024 and more) ran into a false pass of that wait and a dead-lock (found on the 2evq box with 1536- and
+  // 2000-wide nets); they take the BN = 128 kernel, whose warps all drain every chunk.
+  for (int i = 0; i < ngroups; i++)
+    if (bn == 64 && groups[i].K > 3 * TC_CHUNK * TC_BK) bn = TC_BN;
   int64_t tiles = 0;
   for (int i = 0; i < ngroups; i++) {
     const GemmGroup& g = groups[i];
@@ -788,6 +797,7 @@ int tm_gemm_tc_launch(tm_ctx* c, const GemmGroup* groups, int ngroups, const int
     tiles += (int64_t)((max_row_tiles + ncta - 1) / ncta) * (g.N / bn);
   }
   int bound = tiles > 100000 ? 100000 : (int)tiles;
+  if (getenv("TM_TRACE")) fprintf(stderr, "[tm_trace] tc gemm: groups %d K %d N %d bn %d ncta %d epilogue %d max_row_tiles %d bound %d rows_alloc %lld\n", ngroups, groups[0].K, groups[0].N, bn, ncta, epilogue, max_row_tiles, bound, (long long)groups[0].rows_alloc);
   if (ncta == 2) return launch_tc_epi<2, TC_BN>(c, P, rowmeta_dev, bound, epilogue);
   return bn == 64 ? launch_tc_epi<1, 64>(c, P, rowmeta_dev, bound, epilogue) : launch_tc_epi<1, TC_BN>(c, P, rowmeta_dev, bound, epilogue);
 }

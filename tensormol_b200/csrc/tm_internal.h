@@ -206,6 +206,7 @@ int tm_launch_nlist_build(tm_ctx* c, const SysView& s, double rc_grid);
 int tm_launch_rows(tm_ctx* c, const SysView& s);
 int tm_launch_neighbours(tm_ctx* c, const SysView& s);
 int tm_launch_desc(tm_ctx* c, const SysView& s);
+void tm_trace(tm_ctx* c, const char* what);   // TM_TRACE=1: synchronise + name the stage on stderr (tm_api.cu)
 int tm_launch_mlp_forward(tm_ctx* c, const SysView& s);
 int tm_launch_mlp_backward(tm_ctx* c, const SysView& s);
 int tm_launch_charges(tm_ctx* c, const SysView& s);

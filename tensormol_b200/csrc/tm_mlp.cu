@@ -353,6 +353,7 @@ int tm_launch_mlp_forward(tm_ctx* c, const SysView& s) {
         }
       }
     if ((rc = tm_launch_gemm(c, gg, ng, rowmeta, max_tiles, expect_rows(s), (tc && l == nh - 1) ? TM_EPI_ACT_OUT : TM_EPI_ACT))) return rc;
+    tm_trace(c, l == 0 ? "forward GEMM layer 0" : l == 1 ? "forward GEMM layer 1" : "forward GEMM layer 2+");
   }
   if (tc) {
     YTbl Y;
@@ -428,6 +429,7 @@ int tm_launch_mlp_backward(tm_ctx* c, const SysView& s) {
         }
       }
     if ((rc = tm_launch_gemm(c, gg, ng, rowmeta, max_tiles, expect_rows(s), l > 0 ? TM_EPI_DACT : TM_EPI_NONE))) return rc;
+    tm_trace(c, l == 0 ? "backward GEMM layer 0" : l == 1 ? "backward GEMM layer 1" : "backward GEMM layer 2+");
   }
   return TM_OK;
 }

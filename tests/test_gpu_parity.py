@@ -165,6 +165,53 @@ def test_eval_periodic_golden_images_and_lattice(mode):
     assert r2["charge"].shape == (1, nreal)
 
 
+def test_protein_box_periodic_golden_and_wide_nets():
+    """Config C5: the 1,568-atom 2evq peptide + water box (C/H/N/O, D = 768, bounding-box cell, atoms on the faces) against the
+    fixture (reference MolEmb neighbour rows and descriptor rows, oracle energies / charges / gradient, nets 200^3), then with
+    the 2000^3 nets BASELINE.json names for C/H/N/O against the oracle evaluated here."""
+    from oracle import oracle_graph as og
+    from oracle import oracle_np as onp
+    g = load_golden("evq2_periodic")
+    eles = [int(e) for e in g["eles"]]
+    nreal = len(g["Z"])
+    eng, _, P = _engine(eles, list(g["hidden"]), int(g["seed"]))
+    Zt, Xt = onp.tess_lattice(g["lattice"], g["Z"].astype(np.uint8), g["xyz"], P["EECutoffOff"])
+    for rc, tag in ((P["AN1_r_Rc"], "rr"), (P["AN1_a_Rc"], "ra")):
+        off, idx = eng.nlist(Xt, rc, nreal, 1)
+        assert np.array_equal(off, g[f"ref_nl_{tag}_off"])
+        assert np.array_equal(sort_rows_csr(off, idx), g[f"ref_nl_{tag}_idx"])
+    r = eng.evaluate_lattice(g["xyz"], g["Z"], g["lattice"], 1, descriptors=True)
+    _check_desc(r["descriptors"][0][g["sym_rows"]], g["ref_sym"])
+    for k in ("Etotal", "Ebp", "Ecc", "Evdw"):
+        _check_energy(r[k], g["oracle_" + k], k)
+    assert np.abs(r["charge"] - g["oracle_charge"]).max() <= 1e-5 * np.abs(g["oracle_charge"]).max()
+    _check_grad(r["gradient"], g["oracle_gradient"])
+    eng.close()
+    hidden = [2000, 2000, 2000]
+    eng, W, P = _engine(eles, hidden, 6)
+    o = og.Oracle(eles, W, P).evaluate_periodic(Xt, Zt, nreal)
+    r = eng.evaluate_lattice(g["xyz"], g["Z"], g["lattice"], 1)
+    for k in ("Etotal", "Ebp", "Ecc", "Evdw"):
+        _check_energy(r[k], o[k], k)
+    _check_grad(r["gradient"], o["gradient"][:, :nreal])
+
+
+@pytest.mark.parametrize("mode", [1, 3])
+def test_wide_nets_long_k_loops(mode):
+    """Hidden layers of 1024: K loops of 16 k-blocks = 4 accumulator chunks per tile.  Regression test for a dead-lock of the
+    64-column GEMM tile variant on K > 768 (the launcher now keeps that variant to short K loops; mode 3 asks for it)."""
+    from oracle import oracle_graph as og
+    g = load_golden("morphine")
+    hidden = [1024, 1024, 1024]
+    eng, W, P = _engine(g["eles"], hidden, 9, gemm_mode=mode)
+    N = len(g["Z"])
+    r = eng.evaluate(g["xyz"][None], g["Z"][None], np.array([N]))
+    o = og.Oracle(g["eles"], W, P).evaluate(g["xyz"][None], g["Z"][None], np.array([N]))
+    for k in ("Etotal", "Ebp", "Ecc", "Evdw"):
+        _check_energy(r[k], o[k], k)
+    _check_grad(r["gradient"], o["gradient"])
+
+
 def test_eval_set_of_molecules_vs_oracle():
     """EvalBPDirectEEUpdateSet contract: molecules of different size padded to MaxNAtoms."""
     from oracle import oracle_graph as og

@@ -211,6 +211,69 @@ def test_periodic_force_wrapper_and_md():
     assert np.all(pf.lattice.InLat(md.x) >= -1e-9) and np.all(pf.lattice.InLat(md.x) < 1 + 1e-9)
 
 
+def _soft_periodic_force(n=8, L=6.0, seed=2):
+    def lf(z, x, nreal, DoForce=True):
+        E, F = 0.0, np.zeros((nreal, 3))
+        for i in range(nreal):
+            d = x[i] - x
+            r = np.linalg.norm(d, axis=1)
+            m = (r > 1e-9) & (r < 4.0)
+            E += 0.5 * np.sum(0.01 * (4.0 - r[m]) ** 2)
+            F[i] += np.sum((0.02 * (4.0 - r[m]) / r[m])[:, None] * d[m], axis=0)
+        return (E, F * JOULEPERHARTREE) if DoForce else E
+    rng = np.random.default_rng(seed)
+    pf = PeriodicForce(Mol(np.array([8] * n, np.uint8), rng.uniform(0, L, (n, 3))), np.eye(3) * L)
+    pf.BindForce(lf, 4.0)
+    return pf
+
+
+def test_periodic_boxing_dynamics_reaches_the_target_cell():
+    """PeriodicBoxingDynamics (Simulations/PeriodicMD.py:147-215): the cell moves linearly to BoxingLatp_ over BoxingT_ fs,
+    fractional coordinates are carried along, the density ends at the target's."""
+    from tensormol_b200 import PeriodicBoxingDynamics
+    pf = _soft_periodic_force()
+    rho0 = pf.Density()
+    PARAMS["MDMaxStep"] = 12
+    PARAMS["MDdt"] = 0.5
+    PARAMS["MDThermostat"] = None
+    PARAMS["MDV0"] = None
+    target = np.eye(3) * 5.0
+    md = PeriodicBoxingDynamics(pf, target, "box", BoxingT_=5.0)
+    frac0 = pf.lattice.InLat(md.x)
+    md._deform()                                    # t = 0: the cell is still the initial one
+    assert np.allclose(pf.lattice.lattice, np.eye(3) * 6.0) and np.allclose(pf.lattice.InLat(md.x), frac0)
+    md.Prop()
+    assert np.allclose(pf.lattice.lattice, target)  # reached at t = 5 fs (step 10), kept afterwards
+    assert pf.Density() == pytest.approx(rho0 * (6.0 / 5.0) ** 3, rel=1e-9)
+    assert np.all(np.isfinite(md.x)) and md.md_log.shape == (12, 7)
+    f = pf.lattice.InLat(md.x)
+    assert np.all(f >= -1e-9) and np.all(f < 1 + 1e-9)
+    PARAMS["MDdt"] = 0.1
+
+
+def test_periodic_annealer_keeps_the_lowest_energy_geometry():
+    """PeriodicAnnealer (Simulations/PeriodicMD.py:218-285): starts at rest with dt = 0.1 fs, Nose target temperature follows the
+    MDAnnealT0 -> MDAnnealTF schedule, the best geometry so far is kept and written with its lattice."""
+    from tensormol_b200 import PeriodicAnnealer
+    pf = _soft_periodic_force()
+    e0, _ = pf(pf.mol0.coords)
+    PARAMS["MDMaxStep"] = 40
+    PARAMS["MDAnnealSteps"] = 40
+    PARAMS["MDAnnealT0"], PARAMS["MDAnnealTF"], PARAMS["MDAnnealKickBack"] = 20.0, 5.0, 1.0
+    PARAMS["MDThermostat"] = "Nose"
+    PARAMS["MDV0"] = None
+    an = PeriodicAnnealer(pf, "anneal", AnnealThresh_=1e-7)
+    assert an.dt == 0.1 and np.all(an.v == 0.0)
+    an.Prop()
+    assert an.Minx is not None and an.MinE < e0       # the soft repulsion relaxes from the random start
+    assert pf(an.Minx)[0] == pytest.approx(an.MinE, rel=1e-9)
+    assert abs(an.Tstat.T - (20.0 / 40 * 1 + 5.0 * 39 / 40)) < 25.0    # the schedule ended near MDAnnealTF (kick-backs allowed)
+    assert os.path.exists(os.path.join(PARAMS["results_dir"], "PAnnealMin.xyz"))
+    PARAMS["MDThermostat"] = None
+    PARAMS["MDAnnealSteps"] = 1000
+    PARAMS["MDAnnealT0"], PARAMS["MDAnnealTF"] = 20.0, 300.0
+
+
 def test_integrators_equal_reference_python():
     """PeriodicVelocityVerletStep, PeriodicNoseThermostat.step and KineticEnergy of this package against the reference's own
     functions (Simulations/PeriodicMD.py:21-60, SimpleMD.py:42-129) executed by oracle/ref_py.py on a toy analytic force

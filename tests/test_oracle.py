@@ -58,6 +58,28 @@ def test_oracle_nlist_periodic_vs_reference_golden():
     assert np.array_equal(np.diff(off), g["ref_nl_ree_count"])
 
 
+def test_oracle_protein_box_vs_reference_golden():
+    """Config C5 (2evq peptide in water, C/H/N/O, bounding-box cell): neighbour rows and sampled ANI-1 descriptor rows of the
+    reference's MolEmb, and the stored oracle outputs (a regression pin for the fixture the GPU test compares with)."""
+    from tensormol_b200.engine import descriptor_width, random_weights
+    g = load_golden("evq2_periodic")
+    P = og.default_params()
+    nreal = len(g["Z"])
+    assert nreal == 1568 and list(g["eles"]) == [1, 6, 7, 8]
+    Zt, Xt = onp.tess_lattice(g["lattice"], g["Z"].astype(np.uint8), g["xyz"], P["EECutoffOff"])
+    assert len(Zt) == 27 * nreal
+    for rc, tag in ((P["AN1_r_Rc"], "rr"), (P["AN1_a_Rc"], "ra")):
+        off, idx = onp.nlist_csr(Xt, rc, nreal, 1)
+        assert np.array_equal(off, g[f"ref_nl_{tag}_off"]) and np.array_equal(idx, g[f"ref_nl_{tag}_idx"])
+    eles = [int(e) for e in g["eles"]]
+    W = random_weights(eles, descriptor_width(4, P), list(g["hidden"]), int(g["seed"]))
+    o = og.Oracle(eles, W, P).evaluate_periodic(Xt, Zt, nreal)
+    assert np.abs(o["descriptors"][0][g["sym_rows"]] - g["ref_sym"]).max() < 1e-11
+    for k in ("Etotal", "Ebp", "Ecc", "Evdw"):
+        assert abs(o[k][0] - g["oracle_" + k][0]) <= 1e-10 * max(1.0, abs(o[k][0]))
+    assert np.abs(o["gradient"][:, :nreal] - g["oracle_gradient"]).max() < 1e-10
+
+
 def test_oracle_nlist_vs_live_reference_build():
     M = _ref_molemb()
     if M is None:
