@@ -5,9 +5,12 @@
 tensormol_b200.engine.Engine (CUDA).  Pair/triple tables are NOT built on the host for these calls -- the fused
 library call does neighbour search, descriptors, nets, electrostatics and forces on the device.
 
-Weights: the reference restores a TensorFlow checkpoint (TFMolInstanceDirect.py:5765), which cannot be read here.
-Extensions: `InitRandom(seed)`, `SetWeights(dict)`, `SaveWeights(path)` / `LoadWeights(path)` (npz), and automatic
-loading of  PARAMS["networks_directory"]/<Name_>.npz  when Name_ is given.
+Weights: the reference restores a TensorFlow checkpoint (TFMolInstanceDirect.py:5765).  `LoadCheckpoint(prefix)` reads
+such a checkpoint without TensorFlow (TFCheckpoint.py: the V2 tensor-bundle format and the reference's variable names),
+and a manager built with a Name_ follows the reference's `<Name_>.tfm` -> `<instance>.tfn` -> `chk_file` chain
+(TFMolManage.py:1468-1470, TFMolInstance.py:104-113).  Extensions: `InitRandom(seed)`, `SetWeights(dict)`,
+`SaveWeights(path)` / `LoadWeights(path)` (npz, looked for first as PARAMS["networks_directory"]/<Name_>.npz),
+`SaveCheckpoint(prefix)`.
 """
 from __future__ import annotations
 
@@ -91,8 +94,14 @@ class TFMolManage:
             if os.path.exists(f):
                 self.LoadWeights(f)
             else:
-                LOGGER.info("No %s; call manager.InitRandom(seed) / SetWeights(...) / LoadWeights(path) before evaluating "
-                            "(TensorFlow checkpoints of the reference cannot be read)", f)
+                from .TFCheckpoint import find_reference_network
+                chk, inst = find_reference_network(Name_, self.path)
+                if chk:
+                    self.TrainedNetworks = [os.path.basename(os.path.dirname(chk))]
+                    self.LoadCheckpoint(chk, inst)
+                else:
+                    LOGGER.info("No %s and no %s.tfm with a checkpoint; call manager.InitRandom(seed) / SetWeights(...) / "
+                                "LoadWeights(path) / LoadCheckpoint(prefix) before evaluating", f, Name_)
 
     # ---- weights (extension) -------------------------------------------------------------------
     def InitRandom(self, seed=0):
@@ -105,6 +114,33 @@ class TFMolManage:
     def SetWeights(self, weights):
         """weights = {"charge": {Z: [(W,b), ...]}, "energy": {Z: [(W,b), ...]}}; y = a(xW+b), last layer linear."""
         self.Instances.set_weights(weights)
+
+    def LoadCheckpoint(self, prefix, instance_state=None):
+        """Weights from a TensorFlow checkpoint of the reference (`<prefix>.index` + `.data-00000-of-00001`), read without
+        TensorFlow.  `instance_state` (the unpickled .tfn, optional) is checked against this manager's network shape."""
+        from .TFCheckpoint import CheckpointError, read_bundle, variable_names, weights_from_variables
+        I = self.Instances
+        if instance_state:
+            hl = instance_state.get("HiddenLayers")
+            if hl is not None and list(hl) != list(I.HiddenLayers):
+                raise CheckpointError(f"the stored network has HiddenLayers {list(hl)}, PARAMS asks for {list(I.HiddenLayers)}")
+            el = instance_state.get("eles")
+            if el is not None and sorted(int(e) for e in el) != sorted(I.eles):
+                raise CheckpointError(f"the stored network was trained for elements {sorted(int(e) for e in el)}, the set has {sorted(I.eles)}")
+        wanted = [n for pair in variable_names(I.eles, len(I.HiddenLayers)).values() for n in pair]
+        try:
+            variables = read_bundle(prefix, names=wanted)
+        except CheckpointError:
+            variables = read_bundle(prefix)          # names under an outer scope: let weights_from_variables resolve them
+        w = weights_from_variables(variables, I.eles, I.HiddenLayers, I.inshape)
+        I.set_weights(w)
+        return w
+
+    def SaveCheckpoint(self, prefix, dtype=np.float64):
+        """The current weights as a TensorFlow V2 checkpoint under the reference's variable names."""
+        from .TFCheckpoint import variables_from_weights, write_bundle
+        write_bundle(prefix, variables_from_weights(self.Instances.weights, dtype))
+        return prefix
 
     def SaveWeights(self, path=None):
         path = os.path.join(self.path, self.name + ".npz") if path is None else path

@@ -79,6 +79,44 @@ def test_manager_weights_save_load_round_trip(tmp_path):
     assert e1 == e2
 
 
+def test_manager_restores_a_reference_style_network_by_name(tmp_path):
+    """The reference's load chain (TFMolManage.py:1468-1470, TFMolInstance.py:104-113): <name>.tfm -> TrainedNetworks[0] ->
+    <instance>.tfn -> chk_file -> TensorFlow checkpoint, read without TensorFlow (TFNetworks/TFCheckpoint.py)."""
+    import pickle
+    from tensormol_b200 import PARAMS, Mol, MolDigester, MSet, TensorMolData_BP_Direct_EE_WithEle, TFMolManage
+    g = load_golden("h2o_cluster")
+    m = Mol(g["Z"].astype(np.uint8), g["xyz"])
+    manager, W = _manager([m], [32, 16, 24], 4)
+    for net in W:                                   # trained networks have biases
+        for z in W[net]:
+            W[net][z] = [(w, 0.01 * np.arange(len(b)) - 0.02) for w, b in W[net][z]]
+    manager.SetWeights(W)
+    args = (m, PARAMS["AN1_r_Rc"], PARAMS["AN1_a_Rc"], PARAMS["EECutoffOff"], True)
+    e1, f1 = manager.EvalBPDirectEEUpdateSingle(*args)[0][0], manager.EvalBPDirectEEUpdateSingle(*args)[7]
+    nets = str(tmp_path) + "/"
+    inst = "Mol_t_ANI1_Sym_Direct_" + NET
+    manager.SaveCheckpoint(nets + inst + "/" + inst + "-chk-7", np.float64)
+    with open(nets + inst + ".tfn", "wb") as fh:
+        pickle.dump(dict(name=inst, HiddenLayers=[32, 16, 24], eles=[1, 8], chk_file="./networks/" + inst + "/" + inst + "-chk-7"), fh, protocol=2)
+    with open(nets + "water_network.tfm", "wb") as fh:
+        pickle.dump(dict(name="water_network", NetType=NET, TrainedNetworks=[inst]), fh, protocol=2)
+    old = PARAMS["networks_directory"]
+    PARAMS["networks_directory"] = nets
+    try:
+        a = MSet("t", center_=False)
+        a.mols = [m]
+        tset = TensorMolData_BP_Direct_EE_WithEle(a, MolDigester(a.AtomTypes(), name_="ANI1_Sym_Direct", OType_="EnergyAndDipole"), order_=1,
+                                                  num_indis_=1, type_="mol", WithGrad_=True)
+        manager2 = TFMolManage("water_network", tset, False, NET, False, False)
+        out = manager2.EvalBPDirectEEUpdateSingle(*args)
+        assert out[0][0] == e1 and np.array_equal(out[7], f1)
+        PARAMS["HiddenLayers"] = [32, 16, 25]      # a network of another shape is refused, not silently mis-read
+        with pytest.raises(Exception, match="HiddenLayers"):
+            TFMolManage("water_network", tset, False, NET, False, False)
+    finally:
+        PARAMS["networks_directory"] = old
+
+
 def test_manager_periodic_callbacks_match_oracle():
     from oracle import oracle_np as onp
     from tensormol_b200 import PARAMS, Mol, PeriodicForce
