@@ -258,11 +258,70 @@ def reference_python_pins():
     print("ref_python_pins:", {k: np.asarray(v).shape for k, v in out.items() if np.asarray(v).size > 8})
 
 
+def host_pin_inputs():
+    """Seeded inputs of the host-driver pins (shared by the generator and tests/test_host_api.py)."""
+    atoms = np.array([8, 1, 1, 6, 1], np.uint8)
+    rs = np.random.RandomState(5)
+    x0 = np.cumsum(np.abs(rs.randn(5, 3)) * 0.7, axis=0)
+    x0[0, 0] = -1.05
+    x1 = x0.copy()
+    x1[0, 0] = 1.02
+    x1[1:] += 0.05 * rs.randn(4, 3)
+    return atoms, x0, x1
+
+
+HOST_PARAM_PREFIXES = ("Opt", "Neb", "GS", "Remove", "MaxBFGS", "Diis", "SDStep")
+
+
+def host_pins():
+    """Outputs of the reference's host drivers off the hot path, executed in place by oracle/ref_py.py:
+    ConjGradient, RemoveInvariantForce, GeomOptimizer.Opt, NudgedElasticBand with each solver (default windows and
+    windows of 3 so that the history roll-over is exercised), MolEmb.CountInRange / GetRDF_Bin of the reference build, and the
+    xyz text the reference's Mol writes -> tests/golden/ref_host_pins.npz."""
+    from oracle import ref_py
+    from tensormol_b200 import PARAMS
+    out = {}
+    P = {k: PARAMS[k] for k in PARAMS if k.startswith(HOST_PARAM_PREFIXES)}
+    atoms, x0, x1 = host_pin_inputs()
+    for k, v in ref_py.opt_pins(atoms, x0, x1, P, 6).items():
+        out["opt_" + k] = v
+    P3 = dict(P)
+    P3["MaxBFGS"], P3["DiisSize"] = 3, 3
+    for k, v in ref_py.opt_pins(atoms, x0, x1, P3, 9).items():
+        if k in ("neb_BFGS", "neb_DIIS"):
+            out["opt3_" + k] = v
+    M = ref_py.namespace()["MolEmb"]
+    rs = np.random.RandomState(11)
+    x = rs.uniform(0.0, 6.0, (30, 3))
+    z = np.array([1, 1, 8] * 10, np.uint8)
+    out["rdf_x"], out["rdf_z"] = x, z
+    out["rdf_bins_8_1"] = np.asarray(M.GetRDF_Bin(x, z, 7.0, 0.1, 6.0, 8, 1), np.int64)
+    out["rdf_bins_8_8"] = np.asarray(M.GetRDF_Bin(x, z, 5.0, 0.05, 6.0, 8, 8), np.int64)
+    xt = np.concatenate([x, x + 6.0, x - 6.0])
+    zt = np.concatenate([z, z, z])
+    out["count_8_8"] = M.CountInRange(zt, xt, 30, 8, 8, 5.0, 0.02)
+    out["count_8_1"] = M.CountInRange(zt, xt, 30, 8, 1, 6.0, 0.05)
+    RMol = ref_py.mol_class()
+    m = RMol(np.array([8, 1, 1], np.uint8), np.array([[0.1, 0.2, 0.3], [1.0, -0.25, 1e-7], [-0.75, 0.5, 2.5e-5]]))
+    m.properties = {"energy": -76.4, "Step": 3}
+    out["xyz_with_properties"] = np.array(m.__str__(True))
+    out["xyz_plain"] = np.array(str(m))
+    r = RMol()
+    r.FromXYZString("3\nComment: ;;;energy -1.5;;;foo bar\nO 0 0 0\nH 1.5*^-3 0 0\nH 0 12.25*^2 0\n")
+    out["xyz_parsed_coords"], out["xyz_parsed_atoms"] = r.coords, r.atoms
+    out["xyz_parsed_energy"] = np.float64(r.properties["energy"])
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "ref_host_pins.npz"), **out)
+    print("ref_host_pins:", {k: np.asarray(v).shape for k, v in out.items()})
+
+
 def main():
     os.makedirs(os.path.join(ROOT, "tests", "golden"), exist_ok=True)
+    if "--only-host" in sys.argv:
+        return host_pins()
     if "--only-protein" in sys.argv:
         return protein_case("evq2_periodic", [200, 200, 200], 5)
     reference_python_pins()
+    host_pins()
     Z, X, _ = read_xyz_frames(os.path.join(REF, "datasets", "H2O_cluster.xyz"))[0]
     aperiodic_case("h2o_cluster", Z, X, [64, 48, 32], 0, True)
     Z, X, _ = read_xyz_frames(os.path.join(REF, "datasets", "morphine.xyz"))[0]

@@ -442,3 +442,116 @@ def md_pins(lat, x0, m, v0, dt, nsteps, P):
 
 def lattice(latvec):
     return namespace()["Lattice"](np.asarray(latvec, np.float64))
+
+
+# ---- host drivers off the hot path: optimisers, NEB, xyz wire format -------------------------------
+
+class _NumpyCompat:
+    """numpy with the aliases the reference still uses (np.float, removed in NumPy 1.24); everything else is numpy's."""
+    float = float
+
+    def __getattr__(self, k):
+        return getattr(np, k)
+
+
+def mol_class():
+    """The reference's Mol class (Containers/Mol.py:7-...) executed in place; only the xyz reading / writing members are
+    exercised (FromXYZString, ParseProperties, PropertyString, __str__, WriteXYZfile)."""
+    base = namespace()
+    ns = {"np": _NumpyCompat(), "os": os, "errno": __import__("errno"), "atoi": base["atoi"], "PARAMS": {}, "LOGGER": base["LOGGER"],
+          "MolEmb": base["MolEmb"], "ELEHEATFORM": {}, "re": __import__("re")}
+    exec(_defs("TensorMol/Util.py", {"scitodeci", "AtomicNumber", "AtomicSymbol"}), ns)
+    exec(_defs("TensorMol/Containers/Mol.py", {"Mol"}), ns)
+    ns["Mol"].CalculateAtomization = lambda self: None      # needs the heat-of-formation tables; not part of the format
+    return ns["Mol"]
+
+
+class _QuietMol:
+    """Mol stand-in for the optimiser pins: the drivers only construct it, set properties and write trajectories."""
+
+    def __init__(self, atoms_, coords_):
+        self.atoms, self.coords, self.properties = np.array(atoms_), np.array(coords_), {}
+
+    def WriteXYZfile(self, *a, **k):
+        pass
+
+    def __str__(self):
+        return "Mol(%d atoms)" % len(self.atoms)
+
+
+def opt_namespace(P):
+    """ConjGradient / RemoveInvariantForce (Math/QuasiNewtonTools.py:10-25,350-465,551-577), the solvers of Math/BFGS.py
+    and Math/DIIS.py, GeomOptimizer (Simulations/Opt.py:17-75) and NudgedElasticBand (Simulations/Neb.py:17-220) executed
+    in place with the PARAMS given; prints silenced, trajectory files not written."""
+    base = namespace()
+    ns = {k: base[k] for k in ("JOULEPERHARTREE", "GOLDENRATIO", "BOHRPERA", "KCALPERHARTREE", "ATOMICMASSES", "ATOMICMASSESAMU",
+                               "IDEALGASR", "atoi", "LOGGER")}
+    ns.update({"np": np, "PARAMS": dict(P), "Mol": _QuietMol, "print": lambda *a, **k: None, "xrange": range,
+               "TMTiming": _tmtiming, "time": __import__("time"), "random": __import__("random")})
+    exec(_defs("TensorMol/Math/LinearOperations.py", {"PseudoInverse", "MatrixPower", "Normalize"}), ns)
+    exec(_defs("TensorMol/Math/QuasiNewtonTools.py", {"RmsForce", "CenterOfMass", "InertiaTensor", "FdiffGradient", "ConjGradient",
+                                                      "RemoveInvariantForce", "LineSearch"}), ns)
+    exec(_defs("TensorMol/Math/BFGS.py", {"SteepestDescent", "VerletOptimizer", "BFGS", "BFGS_WithLinesearch"}), ns)
+    exec(_defs("TensorMol/Math/DIIS.py", {"DIIS"}), ns)
+    exec(_defs("TensorMol/Simulations/Opt.py", {"GeomOptimizer"}), ns)
+    exec(_defs("TensorMol/Simulations/Neb.py", {"NudgedElasticBand"}), ns)
+    return ns
+
+
+def toy_surface(x, DoForce=True):
+    """Smooth analytic molecule-like surface for the optimiser / NEB pins, in the callback's convention
+    (E in Hartree, force in J/mol/Angstrom): harmonic bonds between consecutive atoms (r0 = 1.1), a weak 1-3 term and a
+    double well in the first atom's x coordinate."""
+    JPH = 2625499.638
+    d1 = x[1:] - x[:-1]
+    r1 = np.sqrt((d1 * d1).sum(1))
+    d2 = x[2:] - x[:-2]
+    r2 = np.sqrt((d2 * d2).sum(1))
+    w = x[0, 0]
+    e = 0.4 * np.sum((r1 - 1.1) ** 2) + 0.05 * np.sum((r2 - 1.9) ** 2) + 0.02 * (w * w - 1.0) ** 2
+    if not DoForce:
+        return float(e)
+    g = np.zeros_like(x)
+    c1 = (0.8 * (r1 - 1.1) / r1)[:, None] * d1
+    g[1:] += c1
+    g[:-1] -= c1
+    c2 = (0.1 * (r2 - 1.9) / r2)[:, None] * d2
+    g[2:] += c2
+    g[:-2] -= c2
+    g[0, 0] += 0.08 * w * (w * w - 1.0)
+    return float(e), -JPH * g
+
+
+def opt_pins(atoms, x0, x1, P, nsteps=6):
+    """Reference outputs on the toy surface: RemoveInvariantForce, `nsteps` ConjGradient iterations, GeomOptimizer.Opt, and
+    `nsteps` NudgedElasticBand solver iterations per solver (bead positions, Es, NEB forces)."""
+    out = {}
+    ns = opt_namespace(P)
+    e0, f0 = toy_surface(x0)
+    out["rif"] = ns["RemoveInvariantForce"](x0, f0, np.asarray(atoms, np.float64))
+    go = ns["GeomOptimizer"](toy_surface)
+    go.m = _QuietMol(atoms, x0)
+    cg = ns["ConjGradient"](go.WrappedEForce, x0)
+    x, tr = x0.copy(), []
+    for _ in range(nsteps):
+        x, e, g = cg(x)
+        tr.append(np.concatenate([x.ravel(), g.ravel(), [e, cg.alpha]]))
+    out["cg"] = np.array(tr)
+    m = ns["GeomOptimizer"](toy_surface).Opt(_QuietMol(atoms, x0))
+    out["opt_coords"] = m.coords
+    out["opt_energy"] = np.float64(m.properties["Energy"])
+    out["opt_step"] = np.int64(m.properties["Step"])
+    for solver in ("Verlet", "BFGS", "DIIS", "CG"):      # "SD" raises in the reference (Neb.py:51-62: an `if` where an `elif` is meant)
+        Ps = dict(P)
+        Ps["NebSolver"] = solver
+        nss = opt_namespace(Ps)
+        neb = nss["NudgedElasticBand"](toy_surface, _QuietMol(atoms, x0), _QuietMol(atoms, x1), nbeads_=7)
+        tr = []
+        for _ in range(nsteps):
+            neb.beads, e, neb.Fs = neb.Solver(neb.beads)
+            neb.IntegrateEnergy()
+            neb.TSI = np.argmax(neb.Es)
+            tr.append(np.concatenate([neb.beads.ravel(), neb.Fs.ravel(), neb.Es, neb.Esi, [e]]))
+            neb.step += 1
+        out["neb_" + solver] = np.array(tr)
+    return out

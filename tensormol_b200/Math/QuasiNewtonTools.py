@@ -169,5 +169,5 @@ class ConjGradient:
                 d = a + (b - a) / GOLDENRATIO   # noqa: F405
                 fa = fc
                 fc, fd = self.Energy(c), self.Energy(d)
-            rmsdist = np.sum(np.linalg.norm((a - b).reshape(-1, 3), axis=1)) / max(a.reshape(-1, 3).shape[0], 1)
+            rmsdist = np.sum(np.linalg.norm(a - b, axis=1)) / a.shape[0]     # axis 1 also for (bead, atom, 3) arrays, as the reference (:462)
         return (b + a) / 2

@@ -6,7 +6,7 @@ neighbour search runs on the B200 through libtmolb200 (tm_nlist); there is no CP
 
 `Make_NListLinear` deliberately returns the *Naive* semantics: the reference's Linear variant drops pairs in
 boxes larger than ~2 Rc^2, and both are meant to produce the same sets.
-The small helpers the periodic wrapper uses off the hot path (Make_DistMat, Make_DistMat_ForReal, CountInRange)
+The small helpers the periodic wrapper uses off the hot path (Make_DistMat, Make_DistMat_ForReal, CountInRange, GetRDF_Bin)
 are plain numpy.
 """
 from __future__ import annotations
@@ -56,16 +56,39 @@ def Make_DistMat_ForReal(xyz, nreal):
 
 
 def CountInRange(zt, xt, natoms, z1, z2, rng, dx):
-    """Cumulative pair-count histogram used by PeriodicForce.RDF (Periodic.py:425)."""
+    """Cumulative pair-count histogram used by PeriodicForce.RDF (MolEmb.cpp:1082-1119, caller Periodic.py:425):
+    out[k] = mean over the centres i < natoms of element z1 of the number of partners j != i of element z2 with
+    int(d_ij / dx) <= k, k < int(rng / dx)."""
     zt = np.asarray(zt)
     xt = np.asarray(xt, np.float64)
-    nbin = int(np.arange(0.0, rng, dx).shape[0])
+    nbin = int(float(rng) / float(dx))
     ni = np.zeros(nbin)
     centres = np.where(zt[:int(natoms)] == z1)[0]
     others = np.where(zt == z2)[0]
     for i in centres:
-        d = np.linalg.norm(xt[others] - xt[i], axis=1)
-        d = d[(others != i) & (d < rng)]
-        b = (d / dx).astype(int)
-        ni += np.cumsum(np.bincount(b, minlength=nbin)[:nbin])
-    return ni / max(len(centres), 1)
+        d = np.linalg.norm(xt[others] - xt[i], axis=1)[others != i]
+        b = (d / dx).astype(np.int64)
+        ni += np.cumsum(np.bincount(b[b < nbin], minlength=nbin)[:nbin])
+    with np.errstate(invalid="ignore", divide="ignore"):
+        return ni / float(len(centres))          # the reference divides by zero too when no centre matches
+
+
+def GetRDF_Bin(xyz, Zs, cut, dr, cellsize, ele1, ele2):
+    """Bin indices int(d / dr) of every (centre of element ele1, partner of element ele2 in the cubic cell of edge
+    `cellsize` or one of its images) distance with d + 1e-11 < cut (MolEmb.cpp:1121-1178; callers Periodic.py:452,
+    samples/test_h2o_peri.py:404). Order: centres ascending, partners by image block (cell first, then the blocks in
+    i, j, k order without (0,0,0)) and atom index, as the reference's list."""
+    x = np.asarray(xyz, np.float64)
+    z = np.asarray(Zs)
+    nat = x.shape[0]
+    ntess = int(float(cut) / float(cellsize)) + 1
+    r = range(-ntess, ntess + 1)
+    shifts = [(0, 0, 0)] + [(i, j, k) for i in r for j in r for k in r if (i, j, k) != (0, 0, 0)]
+    xp = (x[None, :, :] + float(cellsize) * np.asarray(shifts, np.float64)[:, None, :]).reshape(-1, 3)
+    partner = np.where(np.tile(z == ele2, len(shifts)))[0]
+    out = []
+    for i in np.where(z == ele1)[0]:
+        p = partner[partner != i]
+        d = np.sqrt(((x[i] - xp[p]) ** 2).sum(1)) + 0.00000000001
+        out.extend((d[d < cut] / dr).astype(np.int64).tolist())
+    return out

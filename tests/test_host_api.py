@@ -309,3 +309,92 @@ def test_integrators_equal_reference_python():
         x, v, a, e = th.step(pf, a, x, v, m, 0.2)
         assert np.abs(x.ravel() - row[:27]).max() <= 1e-12 and np.abs(v.ravel() - row[27:54]).max() <= 1e-14
         assert abs(th.eta - row[55]) <= 1e-12 * max(1.0, abs(row[55]))
+
+
+# ---- host drivers against the reference's own Python / MolEmb build executed in place (pins: tests/golden/ref_host_pins.npz,
+# ---- written by oracle/make_golden.py:host_pins through oracle/ref_py.py) ----------------------------------------------
+
+def _host_pin_setup():
+    from conftest import load_golden
+    from oracle.make_golden import host_pin_inputs
+    from oracle.ref_py import toy_surface
+    return load_golden("ref_host_pins"), toy_surface, host_pin_inputs()
+
+
+def test_conj_gradient_and_geom_optimizer_equal_reference_python():
+    """RemoveInvariantForce, six ConjGradient iterations (point, force, energy, line-search alpha) and a whole
+    GeomOptimizer.Opt run against Math/QuasiNewtonTools.py:350-465,551-577 and Simulations/Opt.py:17-75."""
+    p, ts, (atoms, x0, x1) = _host_pin_setup()
+    e0, f0 = ts(x0)
+    assert np.abs(RemoveInvariantForce(x0, f0, atoms.astype(np.float64)) - p["opt_rif"]).max() <= 1e-12 * np.abs(p["opt_rif"]).max()
+    go = GeomOptimizer(ts)
+    go.m = Mol(atoms, x0)
+    cg = ConjGradient(go.WrappedEForce, x0)
+    x = x0.copy()
+    for row in p["opt_cg"]:
+        x, e, g = cg(x)
+        assert np.abs(x.ravel() - row[:15]).max() <= 1e-12 and np.abs(g.ravel() - row[15:30]).max() <= 1e-12
+        assert abs(e - row[30]) <= 1e-13 and cg.alpha == row[31]
+    old = {k: PARAMS[k] for k in ("OptMaxCycles", "OptThresh")}
+    PARAMS["OptMaxCycles"], PARAMS["OptThresh"] = 50, 0.0001       # the package defaults the pins were written with
+    try:
+        m = GeomOptimizer(ts).Opt(Mol(atoms, x0))
+    finally:
+        PARAMS.update(old)
+    assert m.properties["Step"] == int(p["opt_opt_step"])
+    assert np.abs(m.coords - p["opt_opt_coords"]).max() <= 1e-6 and abs(m.properties["Energy"] - float(p["opt_opt_energy"])) <= 1e-9
+
+
+@pytest.mark.parametrize("solver,key,window", [("Verlet", "opt_neb_Verlet", None), ("CG", "opt_neb_CG", None), ("BFGS", "opt_neb_BFGS", None),
+                                               ("DIIS", "opt_neb_DIIS", None), ("BFGS", "opt3_neb_BFGS", 3), ("DIIS", "opt3_neb_DIIS", 3)])
+def test_neb_solvers_equal_reference_python(solver, key, window):
+    """NudgedElasticBand driven step by step with each of the reference's solvers (Simulations/Neb.py:17-220, Math/BFGS.py,
+    Math/DIIS.py): bead positions, NEB forces, bead energies and the integrated profile after every solver call. With
+    windows of 3 the quasi-Newton / DIIS histories roll over, including the reference's lagging DIIS overlap table."""
+    p, ts, (atoms, x0, x1) = _host_pin_setup()
+    old = {k: PARAMS[k] for k in ("NebSolver", "MaxBFGS", "DiisSize")}
+    try:
+        PARAMS["NebSolver"] = solver
+        if window:
+            PARAMS["MaxBFGS"] = PARAMS["DiisSize"] = window
+        neb = NudgedElasticBand(ts, Mol(atoms, x0), Mol(atoms, x1), nbeads_=7)
+        n = 7 * 15
+        for row in p[key]:
+            neb.beads, e, neb.Fs = neb.Solver(neb.beads)
+            neb.IntegrateEnergy()
+            neb.TSI = int(np.argmax(neb.Es))
+            neb.step += 1
+            assert np.abs(neb.beads.ravel() - row[:n]).max() <= 1e-9, solver
+            assert np.abs(neb.Fs.ravel() - row[n:2 * n]).max() <= 1e-9
+            assert np.abs(neb.Es - row[2 * n:2 * n + 7]).max() <= 1e-10 and np.abs(neb.Esi - row[2 * n + 7:2 * n + 14]).max() <= 1e-10
+            assert abs(e - row[-1]) <= 1e-10
+    finally:
+        PARAMS.update(old)
+
+
+def test_rdf_helpers_equal_reference_molemb():
+    """MolEmb.GetRDF_Bin / CountInRange (C_API/MolEmb.cpp:1082-1178) against the reference build's outputs, list order
+    included."""
+    from conftest import load_golden
+    from tensormol_b200 import MolEmb
+    p = load_golden("ref_host_pins")
+    x, z = p["rdf_x"], p["rdf_z"]
+    assert MolEmb.GetRDF_Bin(x, z, 7.0, 0.1, 6.0, 8, 1) == p["rdf_bins_8_1"].tolist()
+    assert MolEmb.GetRDF_Bin(x, z, 5.0, 0.05, 6.0, 8, 8) == p["rdf_bins_8_8"].tolist()
+    xt, zt = np.concatenate([x, x + 6.0, x - 6.0]), np.concatenate([z, z, z])
+    assert np.array_equal(MolEmb.CountInRange(zt, xt, 30, 8, 8, 5.0, 0.02), p["count_8_8"])
+    assert np.array_equal(MolEmb.CountInRange(zt, xt, 30, 8, 1, 6.0, 0.05), p["count_8_1"])
+
+
+def test_xyz_text_equals_reference_mol():
+    """The xyz text of Mol.__str__ / WriteXYZfile (';;;'-separated properties on the comment line) and FromXYZString with
+    Mathematica-style exponents against the reference's Mol class (Containers/Mol.py:268-359)."""
+    from conftest import load_golden
+    p = load_golden("ref_host_pins")
+    m = Mol(np.array([8, 1, 1], np.uint8), np.array([[0.1, 0.2, 0.3], [1.0, -0.25, 1e-7], [-0.75, 0.5, 2.5e-5]]))
+    m.properties = {"energy": -76.4, "Step": 3}
+    assert m.__str__(True) == str(p["xyz_with_properties"]) and str(m) == str(p["xyz_plain"])
+    r = Mol()
+    r.FromXYZString("3\nComment: ;;;energy -1.5;;;foo bar\nO 0 0 0\nH 1.5*^-3 0 0\nH 0 12.25*^2 0\n")
+    assert np.array_equal(r.coords, p["xyz_parsed_coords"]) and np.array_equal(r.atoms, p["xyz_parsed_atoms"])
+    assert r.properties["energy"] == float(p["xyz_parsed_energy"])
