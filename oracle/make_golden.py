@@ -276,7 +276,8 @@ HOST_PARAM_PREFIXES = ("Opt", "Neb", "GS", "Remove", "MaxBFGS", "Diis", "SDStep"
 def host_pins():
     """Outputs of the reference's host drivers off the hot path, executed in place by oracle/ref_py.py:
     ConjGradient, RemoveInvariantForce, GeomOptimizer.Opt, NudgedElasticBand with each solver (default windows and
-    windows of 3 so that the history roll-over is exercised), MolEmb.CountInRange / GetRDF_Bin of the reference build, and the
+    windows of 3 so that the history roll-over is exercised), the aperiodic integrator / thermostat steps of
+    Simulations/SimpleMD.py, MolEmb.CountInRange / GetRDF_Bin of the reference build, and the
     xyz text the reference's Mol writes -> tests/golden/ref_host_pins.npz."""
     from oracle import ref_py
     from tensormol_b200 import PARAMS
@@ -290,6 +291,14 @@ def host_pins():
     for k, v in ref_py.opt_pins(atoms, x0, x1, P3, 9).items():
         if k in ("neb_BFGS", "neb_DIIS"):
             out["opt3_" + k] = v
+    from tensormol_b200.PhysicalData import ATOMICMASSES
+    md_m = np.array([ATOMICMASSES[z - 1] for z in atoms])
+    md_v0 = 1e-3 * np.random.RandomState(3).randn(5, 3)
+    PM = {k: PARAMS[k] for k in PARAMS if k.startswith("MD")}
+    PM["MDTemp"], PM["MDdt"] = 300.0, 0.2
+    out["smd_m"], out["smd_v0"] = md_m, md_v0
+    for k, v in ref_py.simple_md_pins(x0, md_m, md_v0, 0.2, 8, PM).items():
+        out["smd_" + k] = v
     M = ref_py.namespace()["MolEmb"]
     rs = np.random.RandomState(11)
     x = rs.uniform(0.0, 6.0, (30, 3))

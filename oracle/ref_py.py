@@ -555,3 +555,40 @@ def opt_pins(atoms, x0, x1, P, nsteps=6):
             neb.step += 1
         out["neb_" + solver] = np.array(tr)
     return out
+
+
+def simple_md_pins(x0, m, v0, dt, nsteps, P):
+    """Aperiodic integrators of the reference (Simulations/SimpleMD.py:14-320): VelocityVerletStep and the step functions
+    of Thermostat (Rescaling), NoseThermostat, AndersenThermostat, LangevinThermostat on the toy
+    surface; the stochastic thermostats draw from numpy's global generator, seeded per run (np.random.seed(7))."""
+    base = namespace()
+    ns = {"np": np, "PARAMS": dict(P), "IDEALGASR": base["IDEALGASR"], "LOGGER": base["LOGGER"], "print": lambda *a, **k: None,
+          "KCONVERT": base.get("KCONVERT"), "time": __import__("time"), "random": __import__("random")}
+    exec(_defs("TensorMol/Simulations/SimpleMD.py", {"VelocityVerletStep", "KineticEnergy", "Thermostat", "NoseThermostat",
+                                                     "AndersenThermostat", "LangevinThermostat", "NoseChainThermostat"}), ns)
+    force = lambda x: toy_surface(x)[1]                     # noqa: E731  (the integrators take a force routine)
+    fande = lambda x: toy_surface(x)                        # noqa: E731
+    out = {}
+    x, v, a = np.array(x0), np.array(v0), np.zeros_like(x0)
+    tr = []
+    for _ in range(nsteps):
+        x, v, a, e = ns["VelocityVerletStep"](force, a, x, v, m, dt, fande)
+        tr.append(np.concatenate([x.ravel(), v.ravel(), a.ravel(), [e]]))
+    out["vv"] = np.array(tr)
+    # NoseChainThermostat cannot be constructed in the reference (PARAMS["MNHChain"] has no default, and its __init__ calls
+    # Rescale before any self.m exists, SimpleMD.py:220,250): nothing to pin. LangevinThermostat ("Not Working",
+    # :166) overflows within a few steps with masses in kg/mol: rows are kept while finite.
+    for name in ("Thermostat", "NoseThermostat", "AndersenThermostat", "LangevinThermostat"):
+        np.random.seed(7)
+        vv = np.array(v0)
+        th = ns[name](m, vv)
+        out[name + "_v0"] = vv.copy()
+        x, v, a = np.array(x0), vv, np.zeros_like(x0)
+        tr = []
+        for _ in range(nsteps):
+            x, v, a, e = th.step(force, a, x, v, m, dt, fande)[:4]      # some steps also return the force (frc_ = True)
+            if not (np.isfinite(x).all() and np.isfinite(v).all() and np.isfinite(a).all() and np.isfinite(e)):
+                break
+            tr.append(np.concatenate([x.ravel(), v.ravel(), a.ravel(), [e]]))
+        out[name] = np.array(tr)
+    return out

@@ -117,8 +117,11 @@ class AndersenThermostat(Thermostat):
         v = v_ + 0.5 * (a_ + a) * dt_
         self.kT = IDEALGASR * _ACC * self.T   # noqa: F405
         s = np.sqrt(2.0 * self.gamma * self.kT / self.m)
-        hit = np.random.random(x_.shape[0]) < self.gamma * dt_
-        v[hit] = np.random.normal(0.0, 1.0, size=(int(hit.sum()), 3)) * s[hit, None]
+        # collisions drawn atom by atom from numpy's global generator, in the reference's order (one uniform per atom,
+        # three normals right after a hit), so a seeded run reproduces the reference's trajectory (SimpleMD.py:157-159)
+        for i in range(x_.shape[0]):
+            if np.random.random() < self.gamma * dt_:
+                v[i] = np.random.normal(0.0, s[i], size=(3))
         if frc_:
             return x, v, a, e, f_x_
         return x, v, a, e

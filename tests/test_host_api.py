@@ -398,3 +398,35 @@ def test_xyz_text_equals_reference_mol():
     r.FromXYZString("3\nComment: ;;;energy -1.5;;;foo bar\nO 0 0 0\nH 1.5*^-3 0 0\nH 0 12.25*^2 0\n")
     assert np.array_equal(r.coords, p["xyz_parsed_coords"]) and np.array_equal(r.atoms, p["xyz_parsed_atoms"])
     assert r.properties["energy"] == float(p["xyz_parsed_energy"])
+
+
+def test_aperiodic_integrators_equal_reference_python():
+    """VelocityVerletStep and the step functions of the Rescaling, Nose, Andersen and Langevin thermostats against
+    Simulations/SimpleMD.py:14-204 executed in place on the toy surface (positions, velocities, accelerations, energy after
+    every step; the stochastic ones with numpy's global generator seeded as the generator did). The reference's Langevin
+    integrator overflows after a few steps (it is marked "Not Working"); its finite rows are compared."""
+    import tensormol_b200.Simulations.SimpleMD as S
+    p, ts, (atoms, x0, x1) = _host_pin_setup()
+    m, v0 = p["smd_m"], p["smd_v0"]
+    force = lambda x: ts(x)[1]      # noqa: E731
+    old = {k: PARAMS[k] for k in ("MDTemp", "MDdt")}
+    PARAMS["MDTemp"], PARAMS["MDdt"] = 300.0, 0.2
+    try:
+        x, v, a = x0.copy(), v0.copy(), np.zeros_like(x0)
+        for row in p["smd_vv"]:
+            x, v, a, e = S.VelocityVerletStep(force, a, x, v, m, 0.2, ts)
+            assert np.array_equal(np.concatenate([x.ravel(), v.ravel(), a.ravel(), [e]]), row)
+        for name in ("Thermostat", "NoseThermostat", "AndersenThermostat", "LangevinThermostat"):
+            np.random.seed(7)
+            vv = v0.copy()
+            th = getattr(S, name)(m, vv)
+            assert np.abs(vv - p["smd_" + name + "_v0"]).max() <= 1e-18, name
+            x, v, a = x0.copy(), vv, np.zeros_like(x0)
+            assert len(p["smd_" + name]) >= 3
+            for row in p["smd_" + name]:
+                with np.errstate(all="ignore"):
+                    x, v, a, e = th.step(force, a, x, v, m, 0.2, ts)[:4]
+                got = np.concatenate([x.ravel(), v.ravel(), a.ravel(), [e]])
+                assert np.abs(got - row).max() <= 1e-12 * max(1.0, np.abs(row).max()), name
+    finally:
+        PARAMS.update(old)
