@@ -13,9 +13,13 @@ from ..Util import *   # noqa: F401,F403
 
 
 class NudgedElasticBand:
-    def __init__(self, f_, g0_, g1_, name_="Neb", thresh_=None, nbeads_=None):
-        """f_(x, DoForce) -> (E [Hartree], F [J/mol/A]) or E; g0_, g1_: end-point molecules."""
+    def __init__(self, f_, g0_, g1_, name_="Neb", thresh_=None, nbeads_=None, fb_=None):
+        """f_(x, DoForce) -> (E [Hartree], F [J/mol/A]) or E; g0_, g1_: end-point molecules.
+        fb_ (B200 extension, optional): batched callback fb_(xs[B, N, 3], DoForce) -> (E[B], F[B, N, 3]) or E[B]
+        (TFMolManage.BatchForce); when given, every solver iteration evaluates ALL beads in one molecule-batch call
+        instead of one call per bead, with the same NEB arithmetic on the results."""
         self.name = name_
+        self.fb = fb_
         self.thresh = PARAMS["OptThresh"] if thresh_ is None else thresh_
         self.max_opt_step = PARAMS["OptMaxCycles"]
         self.nbeads = PARAMS["NebNumBeads"] if nbeads_ is None else nbeads_
@@ -87,7 +91,38 @@ class NudgedElasticBand:
             Fneb = self.Fs[i] - 2.0 * np.sum(self.Fs[i] * self.Ts[i]) * self.Ts[i]
         return self.Es[i], Fneb
 
+    def _evaluate_band(self, beads_, DoForce):
+        """All beads in one batched call: fills Es (every bead) and Fs (interior beads; the end beads keep zero force,
+        as in NebForce)."""
+        out = self.fb(np.asarray(beads_), DoForce)
+        if DoForce:
+            Es, Fs = out
+            self.Fs[1:-1] = np.asarray(Fs)[1:-1]
+            self.Fs[0] = 0.0
+            self.Fs[-1] = 0.0
+        else:
+            Es = out[0] if isinstance(out, tuple) else out
+        self.Es[:] = np.asarray(Es, np.float64).reshape(-1)
+
+    def _neb_force_from_stored(self, beads_, i):
+        t = self.Tangent(beads_, i)
+        self.Ts[i] = t
+        Spara = self.Parallel(-1.0 * self.SpringDeriv(beads_, i), t)
+        self.Ss[i] = Spara
+        Fneb = Spara + self.Perpendicular(self.Fs[i].copy(), t)
+        if PARAMS["NebClimbingImage"] and self.step > 10 and i == self.TSI:
+            Fneb = self.Fs[i] - 2.0 * np.sum(self.Fs[i] * self.Ts[i]) * self.Ts[i]
+        return Fneb
+
     def WrappedEForce(self, beads_, DoForce=True):
+        if self.fb is not None:
+            self._evaluate_band(beads_, DoForce)
+            if not DoForce:
+                return np.sum(self.Es) + self.SpringEnergy(beads_)
+            F = np.zeros(beads_.shape)
+            for i, bead in enumerate(beads_):
+                F[i] = RemoveInvariantForce(bead, self._neb_force_from_stored(beads_, i), self.atoms) / JOULEPERHARTREE   # noqa: F405
+            return np.sum(self.Es) + self.SpringEnergy(beads_), F
         if DoForce:
             F = np.zeros(beads_.shape)
             for i, bead in enumerate(beads_):

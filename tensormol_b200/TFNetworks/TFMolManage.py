@@ -208,6 +208,28 @@ class TFMolManage:
     def EvalBPDirectEELinearSingle(self, mol, Rr_cut, Ra_cut, Ree_cut, HasVdw=False):
         return self.EvalBPDirectEEUpdateSingle(mol, Rr_cut, Ra_cut, Ree_cut, HasVdw)
 
+    def BatchForce(self, atoms, HasVdw=True):
+        """B200 extension: an energy / force callback over MANY geometries of one molecule,
+        fb(xs[B, N, 3], DoForce=True) -> (E[B] Hartree, F[B, N, 3] J/mol/A) or E[B], evaluated as ONE molecule-batch call
+        of the C-ABI (tm_eval) -- the marshalling of EvalBPDirectEEUpdateSet without building Mol objects. Each member
+        equals EvalBPDirectEEUpdateSingle on that geometry. Used by NudgedElasticBand(fb_=...) to evaluate all beads of
+        a band per solver iteration in one launch sequence."""
+        Z = np.asarray(atoms, np.int32)
+        I = self.Instances
+
+        def fb(xs, DoForce=True):
+            xs = np.ascontiguousarray(xs, np.float64)
+            if xs.ndim != 3 or xs.shape[1] != len(Z) or xs.shape[2] != 3:
+                raise ValueError("BatchForce expects coordinates of shape (B, %d, 3)" % len(Z))
+            I.refresh()
+            B = xs.shape[0]
+            self.TData.MaxNAtoms = len(Z)
+            r = I.engine.evaluate(xs, np.tile(Z, (B, 1)), np.full(B, len(Z), np.int32), do_force=DoForce, has_vdw=HasVdw)
+            if not DoForce:
+                return r["Etotal"]
+            return r["Etotal"], -JOULEPERHARTREE * r["gradient"]   # noqa: F405
+        return fb
+
     def EvalBPDirectEESingle(self, mol, Rr_cut, Ra_cut, Ree_cut):
         return self.EvalBPDirectEEUpdateSingle(mol, Rr_cut, Ra_cut, Ree_cut, False)
 

@@ -430,3 +430,37 @@ def test_aperiodic_integrators_equal_reference_python():
                 assert np.abs(got - row).max() <= 1e-12 * max(1.0, np.abs(row).max()), name
     finally:
         PARAMS.update(old)
+
+
+@pytest.mark.parametrize("solver", ["Verlet", "CG", "BFGS"])
+def test_neb_batched_beads_equal_per_bead_path(solver):
+    """NudgedElasticBand(fb_=...) evaluates the whole band with one batched callback per solver iteration; with a
+    batched callback that returns what the per-geometry callback returns, every iterate equals the per-bead path's
+    (climbing image included: 14 iterations)."""
+    from oracle.make_golden import host_pin_inputs
+    from oracle.ref_py import toy_surface as ts
+    atoms, x0, x1 = host_pin_inputs()
+    calls = []
+
+    def fb(xs, DoForce=True):
+        calls.append(len(xs))
+        if DoForce:
+            out = [ts(x) for x in xs]
+            return np.array([o[0] for o in out]), np.array([o[1] for o in out])
+        return np.array([ts(x, False) for x in xs])
+
+    old = PARAMS["NebSolver"]
+    PARAMS["NebSolver"] = solver
+    try:
+        a = NudgedElasticBand(ts, Mol(atoms, x0), Mol(atoms, x1), nbeads_=6)
+        b = NudgedElasticBand(None, Mol(atoms, x0), Mol(atoms, x1), nbeads_=6, fb_=fb)
+        for it in range(14):
+            for neb in (a, b):
+                neb.beads, e, neb.Fs = neb.Solver(neb.beads)
+                neb.IntegrateEnergy()
+                neb.TSI = int(np.argmax(neb.Es))
+                neb.step += 1
+            assert np.array_equal(a.beads, b.beads) and np.array_equal(a.Es, b.Es) and np.array_equal(a.Fs, b.Fs), (solver, it)
+        assert set(calls) == {6}
+    finally:
+        PARAMS["NebSolver"] = old
