@@ -464,3 +464,96 @@ def test_neb_batched_beads_equal_per_bead_path(solver):
         assert set(calls) == {6}
     finally:
         PARAMS["NebSolver"] = old
+
+
+def test_ipi_client_serves_forces_over_a_socket():
+    """TMIPIManger (reference Interfaces/TMIPIinterface.py:7-61) against an in-process stand-in for the i-PI server
+    that speaks the driver protocol the reference's client implements (12-byte headers, POSDATA in atomic units, FORCEREADY
+    reply) and delivers its messages in small TCP fragments. Units: Bohr -> Angstrom into the callback, J/mol/Angstrom ->
+    Hartree/Bohr out."""
+    import socket
+    import threading
+    from tensormol_b200.PhysicalData import BOHRPERA
+    from TensorMol.Interfaces.TMIPIinterface import TMIPIManger        # the reference's import path
+
+    natom = 4
+    rs = np.random.RandomState(0)
+    pos_bohr = [rs.rand(natom, 3) * 5.0 for _ in range(3)]
+    seen, replies = [], []
+
+    def field(x):
+        seen.append(x.copy())
+        return -1.5 - 0.1 * len(seen), JOULEPERHARTREE * (x * 2.0 - 1.0)
+
+    srv = socket.socket(socket.AF_INET, socket.SOCK_STREAM)
+    srv.bind(("127.0.0.1", 0))
+    srv.listen(1)
+    port = srv.getsockname()[1]
+
+    def hdr(m):
+        return m.encode().ljust(12)
+
+    def recvn(c, n):
+        b = b""
+        while len(b) < n:
+            chunk = c.recv(n - len(b))
+            assert chunk
+            b += chunk
+        return b
+
+    def server():
+        c, _ = srv.accept()
+        c.sendall(hdr("STATUS"))
+        assert recvn(c, 12).strip() == b"READY"
+        c.sendall(hdr("INIT") + np.int32(0).tobytes() + np.int32(5).tobytes() + b"hello")
+        for p in pos_bohr:
+            cell = (np.eye(3) * 20.0).tobytes()
+            msg = hdr("POSDATA") + cell + cell + np.int32(natom).tobytes() + p.tobytes()
+            for k in range(0, len(msg), 37):        # fragments: the client must reassemble
+                c.sendall(msg[k:k + 37])
+            c.sendall(hdr("STATUS"))
+            assert recvn(c, 12).strip() == b"HAVEDATA"
+            c.sendall(hdr("GETFORCE"))
+            assert recvn(c, 12).strip() == b"FORCEREADY"
+            e = np.frombuffer(recvn(c, 8), np.float64)[0]
+            n = np.frombuffer(recvn(c, 4), np.int32)[0]
+            f = np.frombuffer(recvn(c, 3 * n * 8), np.float64).reshape(n, 3)
+            vir = np.frombuffer(recvn(c, 72), np.float64)
+            nx = np.frombuffer(recvn(c, 4), np.int32)[0]
+            extra = recvn(c, nx)
+            replies.append((e, n, f.copy(), vir.copy(), extra))
+            c.sendall(hdr("STATUS"))
+            assert recvn(c, 12).strip() == b"READY"
+        c.sendall(hdr("EXIT"))
+        c.close()
+
+    t = threading.Thread(target=server, daemon=True)
+    t.start()
+    client = TMIPIManger(field, "127.0.0.1", port)
+    assert client.md_run() == 3
+    t.join(10)
+    srv.close()
+    assert len(replies) == 3
+    for k, (e, n, f, vir, extra) in enumerate(replies):
+        x_ang = pos_bohr[k] / BOHRPERA
+        assert np.allclose(seen[k], x_ang, rtol=0, atol=1e-15)
+        assert e == -1.5 - 0.1 * (k + 1) and n == natom and extra == b"nothing" and not vir.any()
+        assert np.allclose(f, (x_ang * 2.0 - 1.0) / BOHRPERA, rtol=1e-14, atol=0)
+    with pytest.raises(OSError):
+        TMIPIManger(field, "127.0.0.1", port)      # nothing listens any more: a failed connection raises
+
+
+def test_reference_import_paths_resolve_to_the_same_modules():
+    """`from TensorMol.<sub>.<module> import *` and `import MolEmb`, as the reference's sample scripts write them, give the
+    modules of this package (one PARAMS, one engine)."""
+    import MolEmb as top
+    import TensorMol
+    import TensorMol.ForceModifiers.Neighbors as n1
+    import TensorMol.Simulations.SimpleMD as s1
+    import tensormol_b200
+    import tensormol_b200.ForceModifiers.Neighbors as n2
+    import tensormol_b200.Simulations.SimpleMD as s2
+    assert n1 is n2 and s1 is s2 and TensorMol.PARAMS is tensormol_b200.PARAMS
+    assert top.Make_NListNaive is tensormol_b200.MolEmb.Make_NListNaive
+    for f in ("Make_NListNaive", "Make_NListLinear", "Make_DistMat", "Make_DistMat_ForReal", "CountInRange", "GetRDF_Bin"):
+        assert callable(getattr(top, f))
