@@ -22,7 +22,6 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "oracle", "_ref"))
 
 from oracle import oracle_graph as og  # noqa: E402
 from oracle import oracle_np as onp  # noqa: E402
@@ -70,7 +69,8 @@ def csr_from_lists(ll):
 
 
 def aperiodic_case(name, Z, X, hidden, seed, with_jacobian):
-    import MolEmb
+    from oracle.ref_py import _load_molemb
+    MolEmb = _load_molemb()          # the reference build, loaded by path (a top-level `MolEmb` is this repo's drop-in)
     P = og.default_params()
     eles = sorted(set(int(z) for z in Z))
     D = descriptor_width(len(eles), P)
@@ -96,7 +96,8 @@ def aperiodic_case(name, Z, X, hidden, seed, with_jacobian):
 
 
 def periodic_case(name, Z, X, L, hidden, seed):
-    import MolEmb
+    from oracle.ref_py import _load_molemb
+    MolEmb = _load_molemb()          # the reference build, loaded by path (a top-level `MolEmb` is this repo's drop-in)
     P = og.default_params()
     eles = sorted(set(int(z) for z in Z))
     D = descriptor_width(len(eles), P)
@@ -133,7 +134,8 @@ def protein_case(name, hidden, seed, nsample=48):
     water), shifted to the positive octant, cell = bounding box, as samples/test_neb.py:91-113 sets it up.  Pins: the
     reference MolEmb's neighbour rows on the 27-image tessellation (4.6 / 3.1 A) and its ANI-1 descriptors for a sample of
     rows (the full matrix is 9.6 MB), plus the float64 oracle's outputs with seeded random-init nets."""
-    import MolEmb
+    from oracle.ref_py import _load_molemb
+    MolEmb = _load_molemb()          # the reference build, loaded by path (a top-level `MolEmb` is this repo's drop-in)
     Z, X, _ = read_xyz_frames(os.path.join(REF, "datasets", "2evq.xyz"))[0]
     keep = np.isin(Z, [1, 6, 7, 8])
     Z, X = Z[keep], X[keep]
@@ -258,16 +260,7 @@ def reference_python_pins():
     print("ref_python_pins:", {k: np.asarray(v).shape for k, v in out.items() if np.asarray(v).size > 8})
 
 
-def host_pin_inputs():
-    """Seeded inputs of the host-driver pins (shared by the generator and tests/test_host_api.py)."""
-    atoms = np.array([8, 1, 1, 6, 1], np.uint8)
-    rs = np.random.RandomState(5)
-    x0 = np.cumsum(np.abs(rs.randn(5, 3)) * 0.7, axis=0)
-    x0[0, 0] = -1.05
-    x1 = x0.copy()
-    x1[0, 0] = 1.02
-    x1[1:] += 0.05 * rs.randn(4, 3)
-    return atoms, x0, x1
+from oracle.ref_py import host_pin_inputs  # noqa: E402,F401
 
 
 HOST_PARAM_PREFIXES = ("Opt", "Neb", "GS", "Remove", "MaxBFGS", "Diis", "SDStep")
@@ -277,7 +270,8 @@ def host_pins():
     """Outputs of the reference's host drivers off the hot path, executed in place by oracle/ref_py.py:
     ConjGradient, RemoveInvariantForce, GeomOptimizer.Opt, NudgedElasticBand with each solver (default windows and
     windows of 3 so that the history roll-over is exercised), the aperiodic integrator / thermostat steps of
-    Simulations/SimpleMD.py, MolEmb.CountInRange / GetRDF_Bin of the reference build, and the
+    Simulations/SimpleMD.py, PeriodicForce (energy, force, RDF, RDF_inC, Density, LatticeStep), a seeded PeriodicMonteCarlo
+    chain and PeriodicGeomOptimizer.Opt on a toy local force, MolEmb.CountInRange / GetRDF_Bin of the reference build, and the
     xyz text the reference's Mol writes -> tests/golden/ref_host_pins.npz."""
     from oracle import ref_py
     from tensormol_b200 import PARAMS
@@ -299,6 +293,14 @@ def host_pins():
     out["smd_m"], out["smd_v0"] = md_m, md_v0
     for k, v in ref_py.simple_md_pins(x0, md_m, md_v0, 0.2, 8, PM).items():
         out["smd_" + k] = v
+    pd_atoms = np.array([1, 1, 8] * 3, np.uint8)
+    pd_x0 = np.random.RandomState(2).rand(9, 3) * 6.0
+    pd_lat = np.array([[6.0, 0, 0], [0.4, 6.2, 0], [0, 0.3, 6.5]])
+    PD = {k: PARAMS[k] for k in PARAMS if k.startswith(HOST_PARAM_PREFIXES + ("MD", "PrintTM"))}
+    PD["OptMaxCycles"], PD["MDV0"], PD["MDTemp"] = 12, None, 300.0     # MDV0 "Random" reseeds numpy from the OS (SimpleMD.py:367)
+    out["pd_atoms"], out["pd_x0"], out["pd_lat"] = pd_atoms, pd_x0, pd_lat
+    for k, v in ref_py.periodic_driver_pins(pd_atoms, pd_x0, pd_lat, PD, 6).items():
+        out["pd_" + k] = v
     M = ref_py.namespace()["MolEmb"]
     rs = np.random.RandomState(11)
     x = rs.uniform(0.0, 6.0, (30, 3))

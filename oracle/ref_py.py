@@ -92,6 +92,7 @@ def namespace():
             ns[k] = getattr(me, k)
     exec(_defs("TensorMol/ForceModifiers/Neighbors.py", {"NeighborList", "NeighborListSet", "NeighborListSetWithImages"}), ns)
     exec(_defs("TensorMol/ForceModifiers/Periodic.py", {"Lattice"}), ns)
+    ns["Mol"] = _PinMol                  # Lattice.CenteredInLattice builds one (Periodic.py:71)
     _NS = ns
     return ns
 
@@ -592,3 +593,111 @@ def simple_md_pins(x0, m, v0, dt, nsteps, P):
             tr.append(np.concatenate([x.ravel(), v.ravel(), a.ravel(), [e]]))
         out[name] = np.array(tr)
     return out
+
+
+class _PinMol(_QuietMol):
+    """_QuietMol with the members the periodic wrappers call."""
+
+    def __init__(self, atoms_=None, coords_=None):
+        _QuietMol.__init__(self, np.zeros(0, np.uint8) if atoms_ is None else atoms_, np.zeros((0, 3)) if coords_ is None else coords_)
+
+    def NAtoms(self):
+        return len(self.atoms)
+
+    def Center(self):
+        return np.average(self.coords, axis=0)          # Containers/Mol.py: Center
+
+
+def toy_local_force(z, x, nreal, DoForce=True):
+    """A smooth periodic `local force` for the PeriodicForce pins (callback of Periodic.py:368-400: tessellated atoms in,
+    energy [Hartree] and forces [J/mol/Angstrom] on the first nreal rows out): Gaussian pair repulsion between every real
+    atom and every other tessellated atom, weighted by the atomic numbers."""
+    JPH = 2625499.638
+    x = np.asarray(x, np.float64)
+    w = np.sqrt(np.asarray(z, np.float64))
+    d = x[:nreal, None, :] - x[None, :, :]
+    r2 = (d * d).sum(-1)
+    g = 0.004 * w[:nreal, None] * w[None, :] * np.exp(-r2 / 2.5)
+    g[np.arange(nreal), np.arange(nreal)] = 0.0
+    e = 0.5 * g.sum()
+    if not DoForce:
+        return e
+    f = (g[:, :, None] * d * (2.0 / 2.5)).sum(1)             # -dE/dx_i of the real atoms (pairs with images counted once per i)
+    return e, JPH * f
+
+
+def periodic_driver_namespace(P):
+    """LocalForce / PeriodicForce (ForceModifiers/Periodic.py:182-473), VelocityVerlet and the periodic drivers
+    (Simulations/PeriodicMD.py, PeriodicMC.py, OptPeriodic.py) executed in place."""
+    base = namespace()
+    ns = opt_namespace(P)
+    ns.update({"Mol": _PinMol, "MolEmb": base["MolEmb"], "Lattice": base["Lattice"], "AVOCONST": base["AVOCONST"],
+               "KAYBEETEE": base["KAYBEETEE"], "KJPERHARTREE": base["KJPERHARTREE"], "PrintTMTIMER": lambda: None, "os": os,
+               "map": lambda f, it: list(map(f, it)),          # Periodic.py:309 relies on Python 2's list-returning map
+               "GetRDF_Bin": base["MolEmb"].GetRDF_Bin})
+    exec(_defs("TensorMol/Math/LinearOperations.py", {"MovingAverage"}), ns)
+    exec(_defs("TensorMol/Math/Statistics.py", {"OnlineEstimator"}), ns)
+    exec(_defs("TensorMol/ForceModifiers/Periodic.py", {"LocalForce", "PeriodicForce"}), ns)
+    exec(_defs("TensorMol/Simulations/SimpleMD.py", {"VelocityVerletStep", "KineticEnergy", "Thermostat", "NoseThermostat", "VelocityVerlet"}), ns)
+    exec(_defs("TensorMol/Simulations/PeriodicMD.py", {"PeriodicVelocityVerletStep", "PeriodicNoseThermostat", "PeriodicVelocityVerlet"}), ns)
+    exec(_defs("TensorMol/Simulations/PeriodicMC.py", {"PeriodicMonteCarlo"}), ns)
+    exec(_defs("TensorMol/Simulations/OptPeriodic.py", {"PeriodicGeomOptimizer"}), ns)
+    ns["np"] = _SaveLess()
+    return ns
+
+
+class _SaveLess(_NumpyCompat):
+    """numpy whose savetxt is a no-op (the drivers write logs under ./results/)."""
+
+    def savetxt(self, *a, **k):
+        pass
+
+
+def periodic_driver_pins(atoms, x0, lat, P, nsteps=6):
+    """PeriodicForce energy / force / RDF / Density, a seeded Metropolis chain of PeriodicMonteCarlo and a
+    PeriodicGeomOptimizer.Opt run of the reference on the toy local force."""
+    out = {}
+    ns = periodic_driver_namespace(P)
+    pf = ns["PeriodicForce"](_PinMol(atoms, x0), np.array(lat))
+    pf.BindForce(toy_local_force, 6.0)
+    out["mol0"] = pf.mol0.coords.copy()
+    e, f = pf(pf.mol0.coords)
+    out["e"], out["f"] = np.float64(e), f
+    out["e_only"] = np.float64(pf(pf.mol0.coords, DoForce=False)[0])
+    out["density"] = np.float64(pf.Density())
+    out["rdf"] = pf.RDF(pf.mol0.coords, 8, 1, 7.0, 0.05)
+    np.random.seed(11)
+    mc = ns["PeriodicMonteCarlo"](pf, "pinMC")
+    tr = []
+    for _ in range(nsteps):
+        mc.MetropolisHastings(mc.x)
+        tr.append(np.concatenate([mc.x.ravel(), [mc.eold, mc.Pacc, mc.Eav, mc.dE2]]))
+    out["mc"] = np.array(tr)
+    out["mc_kbt"] = np.float64(mc.kbt)
+    pf2 = ns["PeriodicForce"](_PinMol(atoms, x0), np.array(lat))
+    pf2.BindForce(toy_local_force, 6.0)
+    pf2.Save = lambda *a, **k: None
+    m = ns["PeriodicGeomOptimizer"](pf2).Opt(_PinMol(atoms, pf2.mol0.coords.copy()))
+    out["popt_coords"] = m.coords
+    pf3 = ns["PeriodicForce"](_PinMol(atoms, x0), np.array(lat))
+    pf3.BindForce(toy_local_force, 6.0)
+    ns["PARAMS"]["OptLatticeStep"] = 0.05
+    out["latstep_x"] = pf3.LatticeStep(pf3.mol0.coords)
+    out["latstep_lattice"] = pf3.lattice.lattice.copy()
+    out["latstep_step"] = np.float64(ns["PARAMS"]["OptLatticeStep"])
+    cube = 6.0
+    xc = np.mod(np.array(x0), cube)
+    out["rdf_inc"] = pf3.RDF_inC(xc, np.asarray(atoms), cube, 8, 1, 7.0, 0.05)
+    return out
+
+
+def host_pin_inputs():
+    """Seeded inputs of the host-driver pins (shared by the generator and tests/test_host_api.py)."""
+    atoms = np.array([8, 1, 1, 6, 1], np.uint8)
+    rs = np.random.RandomState(5)
+    x0 = np.cumsum(np.abs(rs.randn(5, 3)) * 0.7, axis=0)
+    x0[0, 0] = -1.05
+    x1 = x0.copy()
+    x1[0, 0] = 1.02
+    x1[1:] += 0.05 * rs.randn(4, 3)
+    return atoms, x0, x1

@@ -5,12 +5,12 @@ import sys, time
 import numpy as np
 sys.path.insert(0, '.'); sys.path.insert(0, 'tests')
 from conftest import load_golden
-from oracle import oracle_graph as og
+from tensormol_b200.engine import default_params
 from tensormol_b200.SystemBuilders import perturbed_molecule_batch
 from tensormol_b200.engine import Engine, random_weights
 nmol = int(sys.argv[1]) if len(sys.argv) > 1 else 10000
 g = load_golden("morphine")
-P = og.default_params()
+P = default_params()
 hidden = [500, 500, 500]
 eng = Engine(list(g["eles"]), hidden, P)
 eng.set_weights(random_weights(eng.eles, eng.D, hidden, 0))

@@ -9,12 +9,12 @@ def say(*a):
     print(f"[{time.perf_counter() - t0:7.2f}]", *a, flush=True)
 H, mode, which = int(sys.argv[1]), int(sys.argv[2]), sys.argv[3]
 from conftest import load_golden
-from oracle import oracle_graph as og
+from tensormol_b200.engine import default_params
 from tensormol_b200.engine import Engine, random_weights
 g = load_golden(which)
 eles = [int(e) for e in g["eles"]]
 say("start", which, "H", H, "mode", mode)
-eng = Engine(eles, [H] * 3, og.default_params())
+eng = Engine(eles, [H] * 3, default_params())
 W = random_weights(eng.eles, eng.D, [H] * 3, 1)
 say("weights made")
 eng.set_weights(W)

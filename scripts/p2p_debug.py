@@ -2,14 +2,14 @@ import sys, ctypes as C
 import numpy as np, torch
 sys.path.insert(0, '.'); sys.path.insert(0, 'tests')
 from common import water_box
-from oracle import oracle_graph as og
+from tensormol_b200.engine import default_params
 from tensormol_b200.engine import Engine, random_weights
 from tensormol_b200.parallel import EngineSlabBackend
 from tensormol_b200._lib import TM_F_FORCE, TM_F_VDW
 from tensormol_b200.SystemBuilders import wrap_into_cell
 world = 2
 Z, X, lat = water_box(5, jitter=0.03); X = wrap_into_cell(X, lat); n = len(Z)
-P = og.default_params(); hidden = [64, 48]; W = random_weights([1, 8], 256, hidden, 3)
+P = default_params(); hidden = [64, 48]; W = random_weights([1, 8], 256, hidden, 3)
 dev = torch.device("cuda", 0)
 backs, streams = [], []
 for r in range(world):

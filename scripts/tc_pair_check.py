@@ -4,13 +4,13 @@ os.environ.setdefault("TM_NO_GRAPH", "1")   # per-stage timings need the kernel-
 import sys, time
 import numpy as np
 sys.path.insert(0, '.'); sys.path.insert(0, 'tests')
-from oracle import oracle_graph as og
+from tensormol_b200.engine import default_params
 from tensormol_b200.SystemBuilders import water_box, wrap_into_cell
 from tensormol_b200.engine import Engine, random_weights
 nx = int(sys.argv[1]) if len(sys.argv) > 1 else 6
 hidden = [500, 500, 500]
 Z, X, lat = water_box(nx); X = wrap_into_cell(X, lat)
-P = og.default_params()
+P = default_params()
 eng = Engine([1, 8], hidden, P)
 eng.set_weights(random_weights([1, 8], eng.D, hidden, 0))
 res = {}

@@ -145,6 +145,34 @@ class PeriodicForce:
         latmet = MatrixPower(np.dot(lat0_, lat0_.T), -1)
         return np.dot(np.dot(x_, np.dot(lat0_.T, latmet)), latp_)
 
+    def LatticeStep(self, x_):
+        """Coordinate search over the nine lattice components (reference Periodic.py:319-363): each component is tried
+        at +/- PARAMS["OptLatticeStep"]; a trial cell is adopted when the LAST bound local force gives an energy lower
+        by more than 1e-5; sweeps repeat while any trial was adopted; the step is halved when a call adopts none."""
+        xx = x_.copy()
+        e, f = self.__call__(xx)
+        dlat = PARAMS["OptLatticeStep"]
+        moved_once, moved = False, True
+        while moved:
+            moved = False
+            for i in range(3):
+                for j in range(3):
+                    for sign in (1.0, -1.0):
+                        trial = self.lattice.lattice.copy()
+                        trial[i, j] += sign * dlat
+                        latt = Lattice(trial)
+                        xtmp = latt.ModuloLattice(xx)
+                        z, x = latt.TessLattice(self.atoms, xtmp, self.maxrng)
+                        et, ft = (self.LocalForces[-1])(z, x, self.natomsReal)
+                        if et < e and abs(e - et) > 0.00001:
+                            e = et
+                            self.ReLattice(trial)
+                            xx = xtmp
+                            moved = moved_once = True
+        if not moved_once and PARAMS["OptLatticeStep"] > 0.001:
+            PARAMS["OptLatticeStep"] = PARAMS["OptLatticeStep"] / 2.0
+        return xx
+
     def Save(self, x_, name_="PMol"):
         m = Mol(self.atoms, x_)
         m.properties["Lattice"] = self.lattice.lattice.copy()
@@ -202,4 +230,19 @@ class PeriodicForce:
         x2gi = np.gradient(ni / (12.56637 * density), dx)
         gi = np.zeros(ri.shape)
         gi[1:] = x2gi[1:] / (ri[1:] * ri[1:])
+        return MovingAverage(gi, 2)
+
+    def RDF_inC(self, x_, z_, lat_, z1=8, z2=8, rng=10.0, dx=0.02, name_="RDF.txt"):
+        """Radial distribution function of a CUBIC cell of edge lat_ from MolEmb.GetRDF_Bin (reference Periodic.py:451-472)."""
+        from .. import MolEmb
+        ri = np.arange(0.0, rng, dx)
+        ni = np.zeros(ri.shape)
+        for index in MolEmb.GetRDF_Bin(x_, z_, rng, dx, lat_, z1, z2):
+            ni[index:] += 1
+        ni /= float(np.count_nonzero(np.asarray(z_) == z1))
+        density = ni[-1] / (4.18879 * ri[-1] * ri[-1] * ri[-1])
+        x2gi = np.gradient(ni / (12.56637 * density), dx)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            gi = x2gi / (ri * ri)
+        gi[0] = 0.0
         return MovingAverage(gi, 2)

@@ -41,6 +41,14 @@ def DSF_Gradient(R, R_c, alpha):
     return -((math.erfc(alpha * R) / R / R + 1.1283791671 * alpha * math.exp(-alpha * R * alpha * R) / R) - (ZZ / R_c + YY))
 
 
+def default_params():
+    """Hyper-parameters of the hot path with the reference's defaults (TMParams.py:26-38, 150-165) as set by its water /
+    chemspider scripts (EECutoffOn = 0, sigmoid_with_param)."""
+    return dict(AN1_r_Rc=4.6, AN1_a_Rc=3.1, AN1_eta=4.0, AN1_zeta=8.0, AN1_num_r_Rs=32, AN1_num_a_Rs=8, AN1_num_a_As=8,
+                EECutoffOn=0.0, EECutoffOff=15.0, Elu_Width=4.6, Poly_Width=4.6, DSFAlpha=0.18, AddEcc=True,
+                sigmoid_alpha=100.0, NeuronType="sigmoid_with_param")
+
+
 def element_pairs(eles):
     """eles ascending; pairs upper-triangular row-major (TFMolInstanceDirect.py:1262-1267)."""
     eles = sorted(int(e) for e in eles)

@@ -1,4 +1,4 @@
-"""Dev check: tcgen05 3xTF32 GEMM mode against the fp32 FFMA mode and the oracle."""
+"""Dev check (test infrastructure, run by hand: python tests/dev_tc_check.py [nx]): GEMM modes against the fp32 FFMA mode and the oracle."""
 import os
 os.environ.setdefault("TM_NO_GRAPH", "1")   # per-stage timings need the kernel-by-kernel path
 import sys

@@ -316,7 +316,7 @@ def test_integrators_equal_reference_python():
 
 def _host_pin_setup():
     from conftest import load_golden
-    from oracle.make_golden import host_pin_inputs
+    from oracle.ref_py import host_pin_inputs
     from oracle.ref_py import toy_surface
     return load_golden("ref_host_pins"), toy_surface, host_pin_inputs()
 
@@ -437,7 +437,7 @@ def test_neb_batched_beads_equal_per_bead_path(solver):
     """NudgedElasticBand(fb_=...) evaluates the whole band with one batched callback per solver iteration; with a
     batched callback that returns what the per-geometry callback returns, every iterate equals the per-bead path's
     (climbing image included: 14 iterations)."""
-    from oracle.make_golden import host_pin_inputs
+    from oracle.ref_py import host_pin_inputs
     from oracle.ref_py import toy_surface as ts
     atoms, x0, x1 = host_pin_inputs()
     calls = []
@@ -557,3 +557,49 @@ def test_reference_import_paths_resolve_to_the_same_modules():
     assert top.Make_NListNaive is tensormol_b200.MolEmb.Make_NListNaive
     for f in ("Make_NListNaive", "Make_NListLinear", "Make_DistMat", "Make_DistMat_ForReal", "CountInRange", "GetRDF_Bin"):
         assert callable(getattr(top, f))
+
+
+def test_periodic_force_and_drivers_equal_reference_python(tmp_path):
+    """PeriodicForce (centred molecule, energy / force / energy-only call, Density, RDF, RDF_inC, LatticeStep), a seeded
+    Metropolis chain of PeriodicMonteCarlo (accepted and rejected moves) and PeriodicGeomOptimizer.Opt against
+    ForceModifiers/Periodic.py:277-473, Simulations/PeriodicMC.py:17-123 and OptPeriodic.py:8-60 executed in place on a toy
+    local force."""
+    from conftest import load_golden
+    from oracle.ref_py import toy_local_force as tl
+    from tensormol_b200 import PeriodicGeomOptimizer, PeriodicMonteCarlo
+    p = load_golden("ref_host_pins")
+    atoms, x0, lat = p["pd_atoms"], p["pd_x0"], p["pd_lat"]
+    keys = ("OptMaxCycles", "MDV0", "MDTemp", "OptLatticeStep", "OptThresh")
+    old = {k: PARAMS[k] for k in keys}
+    PARAMS["OptMaxCycles"], PARAMS["MDV0"], PARAMS["MDTemp"], PARAMS["OptThresh"] = 12, None, 300.0, 0.0001
+    try:
+        pf = PeriodicForce(Mol(atoms, x0), lat)
+        pf.BindForce(tl, 6.0)
+        assert np.array_equal(pf.mol0.coords, p["pd_mol0"])
+        e, f = pf(pf.mol0.coords)
+        assert e == float(p["pd_e"]) and np.array_equal(f, p["pd_f"])
+        assert pf(pf.mol0.coords, DoForce=False)[0] == float(p["pd_e_only"])
+        assert abs(pf.Density() - float(p["pd_density"])) <= 1e-15
+        assert np.array_equal(pf.RDF(pf.mol0.coords, 8, 1, 7.0, 0.05), p["pd_rdf"])
+        np.random.seed(11)
+        mc = PeriodicMonteCarlo(pf, "pinMC")
+        assert mc.kbt == float(p["pd_mc_kbt"])
+        accepted = []
+        for row in p["pd_mc"]:
+            mc.MetropolisHastings(mc.x)
+            accepted.append(mc.Pacc)
+            assert np.abs(np.concatenate([mc.x.ravel(), [mc.eold, mc.Pacc, mc.Eav, mc.dE2]]) - row).max() <= 1e-10
+        assert min(accepted) < 1.0            # the pinned chain contains a rejected move
+        pf2 = PeriodicForce(Mol(atoms, x0), lat)
+        pf2.BindForce(tl, 6.0)
+        m = PeriodicGeomOptimizer(pf2).Opt(Mol(atoms, pf2.mol0.coords.copy()))
+        assert np.abs(m.coords - p["pd_popt_coords"]).max() <= 1e-10
+        pf3 = PeriodicForce(Mol(atoms, x0), lat)
+        pf3.BindForce(tl, 6.0)
+        PARAMS["OptLatticeStep"] = 0.05
+        xx = pf3.LatticeStep(pf3.mol0.coords)
+        assert np.abs(xx - p["pd_latstep_x"]).max() <= 1e-12 and np.abs(pf3.lattice.lattice - p["pd_latstep_lattice"]).max() <= 1e-12
+        assert PARAMS["OptLatticeStep"] == float(p["pd_latstep_step"])
+        assert np.array_equal(pf3.RDF_inC(np.mod(x0, 6.0), atoms, 6.0, 8, 1, 7.0, 0.05), p["pd_rdf_inc"])
+    finally:
+        PARAMS.update(old)
