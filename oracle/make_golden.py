@@ -293,6 +293,7 @@ def host_pins():
     out["smd_m"], out["smd_v0"] = md_m, md_v0
     for k, v in ref_py.simple_md_pins(x0, md_m, md_v0, 0.2, 8, PM).items():
         out["smd_" + k] = v
+    out.update(ref_py.harmonic_pins(atoms, x0, P))
     pd_atoms = np.array([1, 1, 8] * 3, np.uint8)
     pd_x0 = np.random.RandomState(2).rand(9, 3) * 6.0
     pd_lat = np.array([[6.0, 0, 0], [0.4, 6.2, 0], [0, 0.3, 6.5]])

@@ -701,3 +701,23 @@ def host_pin_inputs():
     x1[0, 0] = 1.02
     x1[1:] += 0.05 * rs.randn(4, 3)
     return atoms, x0, x1
+
+
+def harmonic_pins(atoms, x0, P):
+    """FdiffGradient, FdiffHessian (forward / central / gradient modes) and HarmonicSpectra (Math/QuasiNewtonTools.py:43-156,
+    188-293) of the reference on the toy surface."""
+    base = namespace()
+    ns = opt_namespace(P)
+    ns.update({k: base[k] for k in ("ELECTRONPERPROTONMASS", "WAVENUMBERPERHARTREE", "BOHRPERA", "ATOMICMASSESAMU")})
+    ns["map"] = lambda f, it: list(map(f, it))
+    exec(_defs("TensorMol/Math/LinearOperations.py", {"PairOrthogonalize", "SchmidtStep", "Normalize"}), ns)
+    exec(_defs("TensorMol/Math/QuasiNewtonTools.py", {"FdiffHessian", "DirectedFdiffHessian", "InternalCoordinates", "HarmonicSpectra",
+                                                      "FourPointHessQuad"}), ns)
+    energy = lambda x: np.float64(toy_surface(x, False))             # noqa: E731
+    grad = lambda x: -toy_surface(x)[1] / 2625499.638                # noqa: E731
+    out = {"fd_gradient": ns["FdiffGradient"](energy, x0), "fd_hess_forward": ns["FdiffHessian"](energy, x0, 0.001),
+           "fd_hess_central": ns["FdiffHessian"](energy, x0, 0.001, "central"),
+           "fd_hess_gradient": ns["FdiffHessian"](energy, x0, 0.001, "gradient", grad)}
+    w, v = ns["HarmonicSpectra"](energy, x0, np.asarray(atoms))
+    out["harm_w"], out["harm_v"] = w, v
+    return out

@@ -23,17 +23,15 @@ def InertiaTensor(x_, m_):
 
 
 def FdiffGradient(f_, x_, eps_=0.0001):
-    """Central finite-difference gradient of a scalar (or array valued) function."""
-    x_t = np.array(x_, dtype=np.float64)
-    f0 = np.asarray(f_(x_t))
-    tore = np.zeros(x_t.shape + f0.shape)
-    it = np.nditer(x_t, flags=['multi_index'])
-    while not it.finished:
-        xp, xm = x_t.copy(), x_t.copy()
-        xp[it.multi_index] += eps_
-        xm[it.multi_index] -= eps_
-        tore[it.multi_index] = (np.asarray(f_(xp)) - np.asarray(f_(xm))) / (2.0 * eps_)
-        it.iternext()
+    """One-sided (forward) finite-difference gradient of a scalar or array valued function, (f(x + eps e_k) - f(x)) / eps
+    as the reference's debugging helper (:43-58); output shape x_.shape + f(x).shape."""
+    x0 = np.array(x_, dtype=np.float64)
+    f0 = np.asarray(f_(x0))
+    tore = np.zeros(x0.shape + f0.shape)
+    for k in np.ndindex(*x0.shape):
+        xk = x0.copy()
+        xk[k] += eps_
+        tore[k] = (np.asarray(f_(xk)) - f0) / eps_
     return tore
 
 

@@ -167,7 +167,7 @@ def test_conj_gradient_and_fdiff():
         x, e, g = CG(x)
     assert np.allclose(x, 1.0, atol=1e-3)
     g = FdiffGradient(lambda y: np.sum(y ** 3), np.ones((2, 3)))
-    assert np.allclose(g, 3.0, atol=1e-6)
+    assert np.allclose(g, 3.0 + 3.0e-4, atol=1e-6)      # forward difference, eps = 1e-4: 3 + 3 eps + eps^2, like the reference's
 
 
 def test_harmonic_spectra_diatomic():
@@ -603,3 +603,19 @@ def test_periodic_force_and_drivers_equal_reference_python(tmp_path):
         assert np.array_equal(pf3.RDF_inC(np.mod(x0, 6.0), atoms, 6.0, 8, 1, 7.0, 0.05), p["pd_rdf_inc"])
     finally:
         PARAMS.update(old)
+
+
+def test_finite_difference_tools_and_harmonic_spectra_equal_reference_python():
+    """FdiffGradient, FdiffHessian (forward, central, gradient modes) and HarmonicSpectra (wavenumbers and modes) against
+    Math/QuasiNewtonTools.py:43-156,228-293 executed in place on the toy surface."""
+    from tensormol_b200.Math.QuasiNewtonTools import FdiffHessian
+    p, ts, (atoms, x0, x1) = _host_pin_setup()
+    energy = lambda x: np.float64(ts(x, False))           # noqa: E731
+    grad = lambda x: -ts(x)[1] / 2625499.638               # noqa: E731
+    assert np.abs(FdiffGradient(energy, x0) - p["fd_gradient"]).max() <= 1e-12
+    assert np.abs(FdiffHessian(energy, x0, 0.001) - p["fd_hess_forward"]).max() <= 1e-9
+    assert np.abs(FdiffHessian(energy, x0, 0.001, "central") - p["fd_hess_central"]).max() <= 1e-9
+    assert np.abs(FdiffHessian(energy, x0, 0.001, "gradient", grad) - p["fd_hess_gradient"]).max() <= 1e-9
+    w, v = HarmonicSpectra(energy, x0, atoms)
+    assert np.abs(w - p["harm_w"]).max() <= 1e-6 * np.abs(p["harm_w"]).max()
+    assert np.abs(np.abs(v) - np.abs(p["harm_v"])).max() <= 1e-6
