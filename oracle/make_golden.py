@@ -271,7 +271,7 @@ def host_pins():
     ConjGradient, RemoveInvariantForce, GeomOptimizer.Opt, NudgedElasticBand with each solver (default windows and
     windows of 3 so that the history roll-over is exercised), the aperiodic integrator / thermostat steps of
     Simulations/SimpleMD.py, PeriodicForce (energy, force, RDF, RDF_inC, Density, LatticeStep), a seeded PeriodicMonteCarlo
-    chain and PeriodicGeomOptimizer.Opt on a toy local force, MolEmb.CountInRange / GetRDF_Bin of the reference build, and the
+    chain and PeriodicGeomOptimizer.Opt on a toy local force, whole Prop() runs of the eight MD drivers, MolEmb.CountInRange / GetRDF_Bin of the reference build, and the
     xyz text the reference's Mol writes -> tests/golden/ref_host_pins.npz."""
     from oracle import ref_py
     from tensormol_b200 import PARAMS
@@ -302,6 +302,10 @@ def host_pins():
     out["pd_atoms"], out["pd_x0"], out["pd_lat"] = pd_atoms, pd_x0, pd_lat
     for k, v in ref_py.periodic_driver_pins(pd_atoms, pd_x0, pd_lat, PD, 6).items():
         out["pd_" + k] = v
+    PMD = dict(PD)
+    PMD.update(MDV0=None, MDMaxStep=10, MDdt=0.2, MDTemp=300.0, MDLogTrajectory=False, OptMaxCycles=PARAMS["OptMaxCycles"])
+    for k, v in ref_py.md_driver_pins(atoms, x0, pd_lat, PMD).items():
+        out["mdd_" + k] = v
     M = ref_py.namespace()["MolEmb"]
     rs = np.random.RandomState(11)
     x = rs.uniform(0.0, 6.0, (30, 3))

@@ -721,3 +721,73 @@ def harmonic_pins(atoms, x0, P):
     w, v = ns["HarmonicSpectra"](energy, x0, np.asarray(atoms))
     out["harm_w"], out["harm_v"] = w, v
     return out
+
+
+def toy_surface_bound(x, DoForce=True):
+    """toy_surface shifted down by one Hartree: a negative energy, like a bound molecule's, which the annealers need
+    (their best-energy tracker starts from 0.0, SimpleMD.py:472)."""
+    if not DoForce:
+        return toy_surface(x, False) - 1.0
+    e, f = toy_surface(x)
+    return e - 1.0, f
+
+
+def toy_charges(x):
+    """Smooth geometry-dependent charges for the IR / annealing driver pins (neutral by construction)."""
+    q = 0.3 * np.sin(x[:, 0]) + 0.1 * np.cos(x[:, 1] + x[:, 2])
+    return q - q.mean()
+
+
+def md_driver_pins(atoms, x0, lat, P):
+    """Whole Prop() runs of the reference's MD drivers with PARAMS["MDV0"] = None (zero initial velocities; "Random"
+    reseeds numpy from the OS): VelocityVerlet (NVE and Nose), IRTrajectory with a field pulse and geometry-dependent
+    charges, Annealer (Simulations/SimpleMD.py:322-619), PeriodicVelocityVerlet (NVE and Nose), PeriodicAnnealer and
+    PeriodicBoxingDynamics (Simulations/PeriodicMD.py:44-285). Recorded: final x, v and the driver's own log."""
+    out = {}
+
+    def nsfor(**kw):
+        Q = dict(P)
+        Q.update(kw)
+        ns = periodic_driver_namespace(Q)
+        ns["WeightedCoordAverage"] = None
+        exec(_defs("TensorMol/ForceModels/Electrostatics.py", {"Dipole_Naive", "ElectricFieldForce"}), ns)
+        ns["Dipole"] = ns["Dipole_Naive"]        # Electrostatics.Dipole = the same sum through WeightedCoordAverage
+        exec(_defs("TensorMol/Simulations/SimpleMD.py", {"IRTrajectory", "Annealer"}), ns)
+        exec(_defs("TensorMol/Simulations/PeriodicMD.py", {"PeriodicAnnealer", "PeriodicBoxingDynamics"}), ns)
+        return ns
+
+    force = lambda x: toy_surface(x)[1]          # noqa: E731
+    for tag, thermo in (("nve", None), ("nose", "Nose")):
+        ns = nsfor(MDThermostat=thermo)
+        d = ns["VelocityVerlet"](force, _PinMol(atoms, x0), "pin", toy_surface)
+        d.Prop()
+        out["vv_" + tag + "_x"], out["vv_" + tag + "_v"], out["vv_" + tag + "_log"] = d.x, d.v, d.md_log
+    ns = nsfor(MDThermostat=None, MDFieldAmp=2.0)
+    d = ns["IRTrajectory"](toy_surface_bound, toy_charges, _PinMol(atoms, x0), "pinir")
+    d.Prop()
+    out["ir_x"], out["ir_v"], out["ir_log"] = d.x, d.v, d.mu_his
+    ns = nsfor(MDAnnealSteps=8, MDAnnealT0=40.0, MDAnnealTF=5.0)
+    d = ns["Annealer"](toy_surface_bound, toy_charges, _PinMol(atoms, x0), "pinan")
+    d.Prop()
+    out["an_x"], out["an_v"], out["an_minx"], out["an_mine"] = d.x, d.v, d.Minx, np.float64(d.MinE)
+    patoms, px0 = np.array([1, 1, 8] * 3, np.uint8), np.random.RandomState(2).rand(9, 3) * 6.0
+    for tag, thermo in (("nve", None), ("nose", "Nose")):
+        ns = nsfor(MDThermostat=thermo)
+        pf = ns["PeriodicForce"](_PinMol(patoms, px0), np.array(lat))
+        pf.BindForce(toy_local_force, 6.0)
+        d = ns["PeriodicVelocityVerlet"](pf, "pinp")
+        d.Prop()
+        out["pvv_" + tag + "_x"], out["pvv_" + tag + "_v"], out["pvv_" + tag + "_log"] = d.x, d.v, d.md_log
+    ns = nsfor(MDAnnealSteps=8, MDAnnealT0=40.0, MDAnnealTF=5.0)
+    pf = ns["PeriodicForce"](_PinMol(patoms, px0), np.array(lat))
+    pf.BindForce(toy_local_force, 6.0)
+    d = ns["PeriodicAnnealer"](pf, "pinpa")
+    d.Prop()
+    out["pan_x"], out["pan_v"], out["pan_minx"], out["pan_mine"] = d.x, d.v, d.Minx, np.float64(d.MinE)
+    ns = nsfor(MDThermostat="Nose")
+    pf = ns["PeriodicForce"](_PinMol(patoms, px0), np.array(lat))
+    pf.BindForce(toy_local_force, 6.0)
+    d = ns["PeriodicBoxingDynamics"](pf, np.array(lat) * 0.97, "pinbox", 1.0)
+    d.Prop()
+    out["box_x"], out["box_v"], out["box_log"], out["box_lattice"] = d.x, d.v, d.md_log, pf.lattice.lattice.copy()
+    return out

@@ -36,7 +36,8 @@ def KineticEnergy(v_, m_):
 
 
 def Dipole_Naive(x_, q_):
-    return np.einsum("ax,a->x", x_, np.asarray(q_))
+    """sum_a q_a x_a in e Bohr for positions in Angstrom (reference ForceModels/Electrostatics.py:28-33)."""
+    return np.einsum("ax,a->x", x_, np.asarray(q_)) * BOHRPERA   # noqa: F405
 
 
 def ElectricFieldForce(q_, E_):

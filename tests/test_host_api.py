@@ -619,3 +619,63 @@ def test_finite_difference_tools_and_harmonic_spectra_equal_reference_python():
     w, v = HarmonicSpectra(energy, x0, atoms)
     assert np.abs(w - p["harm_w"]).max() <= 1e-6 * np.abs(p["harm_w"]).max()
     assert np.abs(np.abs(v) - np.abs(p["harm_v"])).max() <= 1e-6
+
+
+def test_md_drivers_whole_runs_equal_reference_python():
+    """Ten-step Prop() runs (zero initial velocities) of VelocityVerlet (NVE, Nose), IRTrajectory with a field pulse and
+    geometry-dependent charges, Annealer, PeriodicVelocityVerlet (NVE, Nose), PeriodicAnnealer and PeriodicBoxingDynamics
+    against Simulations/SimpleMD.py:322-619 and PeriodicMD.py:44-285 executed in place: final positions, velocities, the
+    drivers' logs (time, dipole, KE, EPot, total), best annealed geometry, final boxed lattice."""
+    from conftest import load_golden
+    from oracle import ref_py
+    from tensormol_b200 import Annealer, IRTrajectory, PeriodicAnnealer, PeriodicBoxingDynamics
+    p = load_golden("ref_host_pins")
+    atoms, x0, _ = ref_py.host_pin_inputs()
+    patoms, px0, lat = p["pd_atoms"], p["pd_x0"], p["pd_lat"]
+    ts, tsb, tq, tl = ref_py.toy_surface, ref_py.toy_surface_bound, ref_py.toy_charges, ref_py.toy_local_force
+    keys = ("MDV0", "MDMaxStep", "MDdt", "MDTemp", "MDLogTrajectory", "MDThermostat", "MDFieldAmp", "MDAnnealSteps", "MDAnnealT0", "MDAnnealTF")
+    old = {k: PARAMS[k] for k in keys}
+
+    def setp(**kw):
+        PARAMS.update(old)
+        PARAMS.update(dict(MDV0=None, MDMaxStep=10, MDdt=0.2, MDTemp=300.0, MDLogTrajectory=False))
+        PARAMS.update(kw)
+
+    def same(tag, **got):
+        for k, a in got.items():
+            ref = p["mdd_" + tag + "_" + k]
+            assert np.abs(np.asarray(a, np.float64) - ref).max() <= 1e-12 * max(1.0, np.abs(ref).max()), (tag, k)
+
+    def pforce():
+        pf = PeriodicForce(Mol(patoms, px0), lat)
+        pf.BindForce(tl, 6.0)
+        return pf
+
+    try:
+        for tag, th in (("nve", None), ("nose", "Nose")):
+            setp(MDThermostat=th)
+            d = VelocityVerlet(lambda x: ts(x)[1], Mol(atoms, x0), "pin", ts)
+            d.Prop()
+            same("vv_" + tag, x=d.x, v=d.v, log=d.md_log)
+            d = PeriodicVelocityVerlet(pforce(), "pinp")
+            d.Prop()
+            same("pvv_" + tag, x=d.x, v=d.v, log=d.md_log)
+        setp(MDThermostat=None, MDFieldAmp=2.0)
+        d = IRTrajectory(tsb, tq, Mol(atoms, x0), "pinir")
+        d.Prop()
+        same("ir", x=d.x, v=d.v, log=d.mu_his)
+        assert np.abs(d.mu_his[:, 1:4]).max() > 0
+        setp(MDAnnealSteps=8, MDAnnealT0=40.0, MDAnnealTF=5.0)
+        d = Annealer(tsb, tq, Mol(atoms, x0), "pinan")
+        d.Prop()
+        same("an", x=d.x, v=d.v, minx=d.Minx, mine=d.MinE)
+        d = PeriodicAnnealer(pforce(), "pinpa")
+        d.Prop()
+        same("pan", x=d.x, v=d.v, minx=d.Minx, mine=d.MinE)
+        setp(MDThermostat="Nose")
+        pf = pforce()
+        d = PeriodicBoxingDynamics(pf, lat * 0.97, "pinbox", 1.0)
+        d.Prop()
+        same("box", x=d.x, v=d.v, log=d.md_log, lattice=pf.lattice.lattice)
+    finally:
+        PARAMS.update(old)
