@@ -679,3 +679,43 @@ def test_md_drivers_whole_runs_equal_reference_python():
         same("box", x=d.x, v=d.v, log=d.md_log, lattice=pf.lattice.lattice)
     finally:
         PARAMS.update(old)
+
+
+def test_names_used_by_the_reference_sample_scripts_resolve():
+    """Static check of the drop-in surface: every global name the reference's hot-path sample scripts
+    use (samples/test_tensormol01.py, test_h2o.py: BoxAndDensity / TestNeb / Eval, test_neb.py: GetChemSpider12 / Eval /
+    TestBetaHairpin) and every TFMolManage method they call exists in `from TensorMol import *` plus the two explicit
+    imports those scripts make. Needs the reference tree (skipped on the GPU box)."""
+    import ast
+    import builtins
+    import TensorMol as tm
+    import TensorMol.Interfaces.TMIPIinterface as ipi
+    ref = os.environ.get("TM_REFERENCE", "/root/reference")
+    if not os.path.isdir(os.path.join(ref, "samples")):
+        pytest.skip("reference tree not present")
+    wanted = {"test_tensormol01.py": None, "test_h2o.py": {"BoxAndDensity", "TestNeb", "Eval"},
+              "test_neb.py": {"GetChemSpider12", "Eval", "TestBetaHairpin"}}
+    off_path = {"WriteDerDipoleCorrelationFunction"}           # IR post-processing (Simulations/InfraredMD.py): out of scope
+    problems = []
+    for fname, funcs in wanted.items():
+        tree = ast.parse(open(os.path.join(ref, "samples", fname)).read())
+        top = {n.name for n in tree.body if isinstance(n, (ast.FunctionDef, ast.ClassDef))}
+        top |= {t.id for n in ast.walk(tree) if isinstance(n, ast.Assign) for t in n.targets if isinstance(t, ast.Name)}   # script globals
+        for node in tree.body:
+            if not isinstance(node, ast.FunctionDef) or (funcs is not None and node.name not in funcs):
+                continue
+            bound, used, mgr = set(), set(), set()
+            for n in ast.walk(node):
+                if isinstance(n, ast.Name):
+                    (bound if isinstance(n.ctx, (ast.Store, ast.Del)) else used).add(n.id)
+                elif isinstance(n, ast.arg):
+                    bound.add(n.arg)
+                elif isinstance(n, ast.FunctionDef):
+                    bound.add(n.name)
+                elif isinstance(n, ast.Attribute) and isinstance(n.value, ast.Name) and n.value.id == "manager" and n.attr != "Instances":
+                    mgr.add(n.attr)
+            for u in sorted(used - bound - top - off_path):
+                if not (hasattr(builtins, u) or hasattr(tm, u) or hasattr(ipi, u)):
+                    problems.append((fname, node.name, u))
+            problems += [(fname, node.name, "TFMolManage." + a) for a in sorted(mgr) if not hasattr(tm.TFMolManage, a)]
+    assert not problems, problems
