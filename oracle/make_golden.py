@@ -326,6 +326,13 @@ def host_pins():
     r.FromXYZString("3\nComment: ;;;energy -1.5;;;foo bar\nO 0 0 0\nH 1.5*^-3 0 0\nH 0 12.25*^2 0\n")
     out["xyz_parsed_coords"], out["xyz_parsed_atoms"] = r.coords, r.atoms
     out["xyz_parsed_energy"] = np.float64(r.properties["energy"])
+    import random
+    dm = RMol(np.array([8, 1, 1, 1], np.uint8), np.array([[0., 0, 0], [0.757, 0.586, 0], [-0.757, 0.586, 0], [0.3, 0.3, 0.2]]))
+    out["distort_in"] = dm.coords.copy()
+    np.random.seed(3)
+    random.seed(3)
+    dm.Distort(0.3, 0.9)
+    out["distort_out"] = dm.coords.copy()
     np.savez_compressed(os.path.join(ROOT, "tests", "golden", "ref_host_pins.npz"), **out)
     print("ref_host_pins:", {k: np.asarray(v).shape for k, v in out.items()})
 

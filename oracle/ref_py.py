@@ -459,7 +459,7 @@ def mol_class():
     """The reference's Mol class (Containers/Mol.py:7-...) executed in place; only the xyz reading / writing members are
     exercised (FromXYZString, ParseProperties, PropertyString, __str__, WriteXYZfile)."""
     base = namespace()
-    ns = {"np": _NumpyCompat(), "os": os, "errno": __import__("errno"), "atoi": base["atoi"], "PARAMS": {}, "LOGGER": base["LOGGER"],
+    ns = {"np": _NumpyCompat(), "os": os, "errno": __import__("errno"), "atoi": base["atoi"], "PARAMS": {"GoK": 1.0}, "LOGGER": base["LOGGER"], "random": __import__("random"),
           "MolEmb": base["MolEmb"], "ELEHEATFORM": {}, "re": __import__("re")}
     exec(_defs("TensorMol/Util.py", {"scitodeci", "AtomicNumber", "AtomicSymbol"}), ns)
     exec(_defs("TensorMol/Containers/Mol.py", {"Mol"}), ns)

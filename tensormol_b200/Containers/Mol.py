@@ -48,11 +48,21 @@ class Mol:
 
     # ---- modifiers ---------------------------------------------------------------------------
     def Distort(self, disp=0.38, movechance=.20):
-        """Randomly distort my coords with probability movechance per coordinate (reference Mol.py:394)."""
-        for i in range(self.atoms.shape[0]):
+        """Randomly displace coordinates (reference Mol.py:160-177): each coordinate moves with probability
+        `movechance` (Python's `random.uniform`) by normal(0, disp) draws (numpy's generator) that are ADDED one after
+        another, up to 100 of them, until the moved atom is farther than 0.35 Angstrom from every other atom -- the
+        reference retries on the same array, so rejected trial displacements accumulate."""
+        import random
+        n = self.NAtoms()
+        for i in range(n):
             for j in range(3):
-                if np.random.uniform(0, 1) < movechance:
-                    self.coords[i, j] = self.coords[i, j] + disp * np.random.normal(0, 1)
+                if random.uniform(0, 1) < movechance:
+                    for _ in range(100):
+                        self.coords[i, j] += np.random.normal(0.0, disp)
+                        d = np.linalg.norm(self.coords - self.coords[i], axis=1)
+                        d[i] = 1.0
+                        if np.min(d) > 0.35:
+                            break
 
     def Transform(self, ltransf, center=np.array([0.0, 0.0, 0.0])):
         self.coords = np.einsum("ij,kj->ki", ltransf, self.coords - center) + center

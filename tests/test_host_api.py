@@ -398,6 +398,13 @@ def test_xyz_text_equals_reference_mol():
     r.FromXYZString("3\nComment: ;;;energy -1.5;;;foo bar\nO 0 0 0\nH 1.5*^-3 0 0\nH 0 12.25*^2 0\n")
     assert np.array_equal(r.coords, p["xyz_parsed_coords"]) and np.array_equal(r.atoms, p["xyz_parsed_atoms"])
     assert r.properties["energy"] == float(p["xyz_parsed_energy"])
+    # Mol.Distort with both generators seeded (collision-avoiding retries included: Mol.py:160-177)
+    import random
+    d = Mol(np.array([8, 1, 1, 1], np.uint8), p["distort_in"].copy())
+    np.random.seed(3)
+    random.seed(3)
+    d.Distort(0.3, 0.9)
+    assert np.array_equal(d.coords, p["distort_out"]) and np.abs(d.coords - p["distort_in"]).max() > 0.1
 
 
 def test_aperiodic_integrators_equal_reference_python():
