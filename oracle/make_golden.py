@@ -337,14 +337,33 @@ def host_pins():
     print("ref_host_pins:", {k: np.asarray(v).shape for k, v in out.items()})
 
 
+TRAIN_PIN_PARAMS = {"TestRatio": 0.4, "AN1_r_Rc": 4.6, "AN1_a_Rc": 3.1, "EECutoffOff": 15.0}
+
+
+def train_pins():
+    """Batches of the reference's training-style provider (TensorMolData_BP_Direct_EE_WithEle.GetTrainBatch / GetTestBatch
+    on top of LoadData / LoadDataToScratch, Containers/TensorMolData.py:1679-1745, 1860-1904), executed in place on the
+    seeded set of oracle/ref_py.py:train_set_inputs -> tests/golden/ref_train_pins.npz (data side)."""
+    from oracle import ref_py
+    out = ref_py.train_batch_pins(dict(TRAIN_PIN_PARAMS))
+    for i, d in enumerate(ref_py.train_set_inputs()):
+        for k, v in d.items():
+            out["in%d_%s" % (i, k)] = np.asarray(v)
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "ref_train_pins.npz"), **out)
+    print("ref_train_pins:", len(out), "arrays; shuffled order", out["order"])
+
+
 def main():
     os.makedirs(os.path.join(ROOT, "tests", "golden"), exist_ok=True)
+    if "--only-train" in sys.argv:
+        return train_pins()
     if "--only-host" in sys.argv:
         return host_pins()
     if "--only-protein" in sys.argv:
         return protein_case("evq2_periodic", [200, 200, 200], 5)
     reference_python_pins()
     host_pins()
+    train_pins()
     Z, X, _ = read_xyz_frames(os.path.join(REF, "datasets", "H2O_cluster.xyz"))[0]
     aperiodic_case("h2o_cluster", Z, X, [64, 48, 32], 0, True)
     Z, X, _ = read_xyz_frames(os.path.join(REF, "datasets", "morphine.xyz"))[0]

@@ -791,3 +791,66 @@ def md_driver_pins(atoms, x0, lat, P):
     d.Prop()
     out["box_x"], out["box_v"], out["box_log"], out["box_lattice"] = d.x, d.v, d.md_log, pf.lattice.lattice.copy()
     return out
+
+
+def train_set_inputs():
+    """Seeded little training set of the batch-provider pins (shared by the generator and the tests): 11 molecules of two
+    sizes (H2O, CH2O + H) with labels."""
+    rs = np.random.RandomState(21)
+    water = (np.array([8, 1, 1], np.uint8), np.array([[0.0, 0.0, 0.0], [0.757, 0.586, 0.0], [-0.757, 0.586, 0.0]]))
+    form = (np.array([6, 8, 1, 1, 1], np.uint8), np.array([[0.0, 0.0, 0.0], [1.21, 0.0, 0.0], [-0.55, 0.94, 0.0], [-0.55, -0.94, 0.0],
+                                                            [0.4, 0.1, 1.7]]))
+    mols = []
+    for i in range(11):
+        z, x = form if i % 3 == 0 else water
+        mols.append({"atoms": z.copy(), "coords": x + 0.08 * rs.randn(*x.shape), "atomization": float(-0.3 - 0.01 * i + 0.001 * rs.randn()),
+                     "dipole": 0.5 * rs.randn(3), "gradients": 0.02 * rs.randn(*x.shape)})
+    return mols
+
+
+class _TrainSelf:
+    """The attributes TensorMolData.__init__ (Containers/TensorMolData.py:24-75, 1222-1245, 1546-1553, 1670-1677) leaves on a
+    TensorMolData_BP_Direct_EE_WithEle plus what the network instance assigns (ele / elep, TFMolInstanceDirect.py:4963-4964)."""
+
+    def __init__(self, mols, eles_np, elep_np, P, with_grad):
+        self.set = type("S", (), {})()
+        self.set.mols = mols
+        self.Nmols = len(mols)
+        self.MaxNAtoms = max(m.NAtoms() for m in mols)
+        self.dig = type("D", (), {"OType": "EnergyAndDipole"})()
+        self.HasGrad = with_grad
+        self.TestRatio = P["TestRatio"]
+        self.ScratchState = 0
+        self.ScratchPointer = 0
+        self.Rr_cut, self.Ra_cut, self.Ree_cut = P["AN1_r_Rc"], P["AN1_a_Rc"], P["EECutoffOff"]
+        self.ele, self.elep = eles_np, elep_np
+
+
+def train_batch_pins(P, ncases=3, ntrain_calls=5, ncases_test=2, ntest_calls=4, seed=7, with_grad=True):
+    """LoadData / LoadDataToScratch of TensorMolData_BP_Direct_EE (Containers/TensorMolData.py:1679-1745) and GetTrainBatch /
+    GetTestBatch of TensorMolData_BP_Direct_EE_WithEle (:1860-1904) executed in place on train_set_inputs(), Python's
+    `random` seeded.  Returns {name: array}: the shuffled order and every entry of every batch."""
+    import random
+    base = namespace()
+    ns = {"np": np, "random": random, "LOGGER": base["LOGGER"], "NeighborListSet": base["NeighborListSet"], "AUPERDEBYE": base["AUPERDEBYE"],
+          "print": lambda *a, **k: None}
+    exec(_method_defs("TensorMol/Containers/TensorMolData.py", ["LoadData", "LoadDataToScratch"], "TensorMolData_BP_Direct_EE"), ns)
+    exec(_method_defs("TensorMol/Containers/TensorMolData.py", ["GetTrainBatch", "GetTestBatch"], "TensorMolData_BP_Direct_EE_WithEle"), ns)
+    mols = []
+    for i, d in enumerate(train_set_inputs()):
+        m = _PinMol(d["atoms"], d["coords"])
+        m.properties = {"atomization": d["atomization"], "dipole": d["dipole"], "gradients": d["gradients"], "serial": i}
+        mols.append(m)
+    eles_np, elep_np = element_tables(np.concatenate([m.atoms for m in mols]))
+    s = _TrainSelf(mols, eles_np, elep_np, P, with_grad)
+    for name in ("LoadData", "LoadDataToScratch", "GetTrainBatch", "GetTestBatch"):
+        setattr(_TrainSelf, name, ns[name])
+    random.seed(seed)
+    s.LoadDataToScratch(None)
+    out = {"order": np.array([m.properties["serial"] for m in s.set.mols]), "NTrain": np.int64(s.NTrain), "NTest": np.int64(s.NTest)}
+    names = ["xyzs", "Zs", "Elabels", "Dlabels"] + (["grads"] if with_grad else []) + ["rad_p_ele", "ang_t_elep", "rad_eep", "mil_jk", "inv_natom"]
+    for kind, n, nc, fn in (("train", ntrain_calls, ncases, s.GetTrainBatch), ("test", ntest_calls, ncases_test, s.GetTestBatch)):
+        for c in range(n):
+            for nm, v in zip(names, fn(nc)):
+                out["%s%d_%s" % (kind, c, nm)] = np.asarray(v)
+    return out

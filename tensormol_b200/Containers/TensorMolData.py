@@ -29,6 +29,10 @@ class TensorMolData_BP_Direct_EE_WithEle:
         self.ele = None
         self.elep = None
         self.ScratchPointer = 0
+        self.ScratchState = None
+        self.TestRatio = PARAMS["TestRatio"]
+        self.NTrain = 0
+        self.NTest = 0
 
     def AtomTypes(self):
         return np.asarray(self.eles)
@@ -45,33 +49,79 @@ class TensorMolData_BP_Direct_EE_WithEle:
             natom[i] = mol.NAtoms()
         return xyzs, Zs, natom
 
-    def GetTrainBatch(self, ncases):
-        """[xyzs, Zs, Elabels, Dlabels, (grads,) rad_p_ele, ang_t_elep, rad_eep, mil_jk, 1/natom] as in the
-        reference (TensorMolData.py:1860-1881); labels come from mol.properties when present."""
-        from ..ForceModifiers.Neighbors import NeighborListSet
+    # ---- training-style batches (reference TensorMolData.py:1679-1745, 1860-1904) ---------------------------------------
+    def LoadData(self):
+        """Shuffles the set's molecules (Python's `random`, as the reference) and returns padded arrays
+        xyzs, Zs, Elabels (properties["atomization"]), Dlabels (properties["dipole"] * AUPERDEBYE), natom[, grads]."""
+        import random
+        if self.dig is not None and getattr(self.dig, "OType", "EnergyAndDipole") != "EnergyAndDipole":
+            raise Exception("Output Type is not implemented yet")
+        random.shuffle(self.set.mols)
         xyzs, Zs, natom = self.raw_arrays()
-        n = xyzs.shape[0]
-        if ncases > n:
-            raise Exception("Insufficent training data to fill a batch" + str(n) + " vs " + str(ncases))
-        if self.ScratchPointer + ncases > n:
-            self.ScratchPointer = 0
-        sl = slice(self.ScratchPointer, self.ScratchPointer + ncases)
-        self.ScratchPointer += ncases
-        xyzs, Zs, natom = xyzs[sl], Zs[sl], natom[sl]
-        mols = self.set.mols[sl]
-        El = np.array([m.properties.get("atomization", m.properties.get("energy", 0.0)) for m in mols], np.float64)
-        Dl = np.array([np.asarray(m.properties.get("dipole", np.zeros(3)), np.float64) for m in mols])
+        Elabels = np.zeros(self.Nmols, dtype=np.float64)
+        Dlabels = np.zeros((self.Nmols, 3), dtype=np.float64)
+        grads = np.zeros((self.Nmols, self.MaxNAtoms, 3), dtype=np.float64) if self.HasGrad else None
+        for i, mol in enumerate(self.set.mols):
+            Elabels[i] = mol.properties["atomization"]
+            Dlabels[i] = np.asarray(mol.properties["dipole"]) * AUPERDEBYE   # noqa: F405
+            if self.HasGrad:
+                grads[i][:mol.NAtoms()] = mol.properties["gradients"]
+        if self.HasGrad:
+            return xyzs, Zs, Elabels, Dlabels, natom, grads
+        return xyzs, Zs, Elabels, Dlabels, natom
+
+    def LoadDataToScratch(self, tformer=None):
+        """Loads once, then splits: the last int(TestRatio * N) molecules of the shuffled order are the test cases."""
+        if self.ScratchState == 1:
+            return
+        data = self.LoadData()
+        self.xyzs, self.Zs, self.Elabels, self.Dlabels, self.natom = data[:5]
+        self.grads = data[5] if self.HasGrad else None
+        self.NTestMols = int(self.TestRatio * self.Zs.shape[0])
+        self.LastTrainMol = int(self.Zs.shape[0] - self.NTestMols)
+        self.NTrain = self.LastTrainMol
+        self.NTest = self.NTestMols
+        self.test_ScratchPointer = self.LastTrainMol
+        self.ScratchPointer = 0
+        self.ScratchState = 1
+
+    def _batch_window(self, ncases, test):
+        """The reference's batch pointers: training batches wrap to 0 when pointer + ncases >= NTrain (so the last
+        partial AND the last exactly-fitting batch are skipped), test batches wrap to LastTrainMol when pointer + ncases
+        would pass the end of the data."""
+        if self.ScratchState != 1:
+            self.LoadDataToScratch()      # the reference leaves this to the network instance (TFMolInstanceDirect.py)
+        if not test:
+            if ncases > self.NTrain:
+                raise Exception("Insufficent training data to fill a batch" + str(self.NTrain) + " vs " + str(ncases))
+            if self.ScratchPointer + ncases >= self.NTrain:
+                self.ScratchPointer = 0
+            self.ScratchPointer += ncases
+            return slice(self.ScratchPointer - ncases, self.ScratchPointer)
+        if ncases > self.NTest:
+            raise Exception("Insufficent training data to fill a batch" + str(self.NTest) + " vs " + str(ncases))
+        if self.test_ScratchPointer + ncases > self.Zs.shape[0]:
+            self.test_ScratchPointer = self.LastTrainMol
+        self.test_ScratchPointer += ncases
+        return slice(self.test_ScratchPointer - ncases, self.test_ScratchPointer)
+
+    def _batch(self, ncases, test):
+        from ..ForceModifiers.Neighbors import NeighborListSet
+        w = self._batch_window(ncases, test)
+        xyzs, Zs, natom = self.xyzs[w], self.Zs[w], self.natom[w]
         NL = NeighborListSet(xyzs, natom, True, True, Zs, sort_=True)
         rad_p_ele, ang_t_elep, mil_jk, jk_max = NL.buildPairsAndTriplesWithEleIndex(self.Rr_cut, self.Ra_cut, self.ele, self.elep)
         NLEE = NeighborListSet(xyzs, natom, False, False, None)
         rad_eep = NLEE.buildPairs(self.Ree_cut)
-        out = [xyzs, Zs, El, Dl]
+        out = [xyzs, Zs, self.Elabels[w], self.Dlabels[w]]
         if self.HasGrad:
-            g = np.zeros_like(xyzs)
-            for i, m in enumerate(mols):
-                if "gradients" in m.properties:
-                    g[i, :m.NAtoms()] = m.properties["gradients"]
-            out.append(g)
+            out.append(self.grads[w])
         return out + [rad_p_ele, ang_t_elep, rad_eep, mil_jk, 1.0 / natom]
 
-    GetTestBatch = GetTrainBatch
+    def GetTrainBatch(self, ncases):
+        """[xyzs, Zs, Elabels, Dlabels, (grads,) rad_p_ele, ang_t_elep, rad_eep, mil_jk, 1/natom] (TensorMolData.py:1860-1881);
+        the neighbour tables are built on the GPU (NeighborListSet -> tm_pairs_triples_ele)."""
+        return self._batch(ncases, False)
+
+    def GetTestBatch(self, ncases):
+        return self._batch(ncases, True)

@@ -54,6 +54,7 @@ class TMParams(dict):
         self["GSSearchAlpha"] = 0.05
         self["SDStep"] = 0.05
         self["MaxBFGS"] = 7
+        self["TestRatio"] = 0.2          # fraction of the cases withheld for testing (reference TMParams.py:71)
         self["NebSolver"] = "Verlet"
         self["NebNumBeads"] = 18
         self["NebK"] = 0.07

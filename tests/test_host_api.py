@@ -726,3 +726,80 @@ def test_names_used_by_the_reference_sample_scripts_resolve():
                     problems.append((fname, node.name, u))
             problems += [(fname, node.name, "TFMolManage." + a) for a in sorted(mgr) if not hasattr(tm.TFMolManage, a)]
     assert not problems, problems
+
+
+TRAIN_BATCH_NAMES = ["xyzs", "Zs", "Elabels", "Dlabels", "grads", "rad_p_ele", "ang_t_elep", "rad_eep", "mil_jk", "inv_natom"]
+
+
+def train_pin_set(g):
+    """The molecule set of tests/golden/ref_train_pins.npz as this package's containers."""
+    from tensormol_b200 import MolDigester, TensorMolData_BP_Direct_EE_WithEle
+    a = MSet("train_pins")
+    i = 0
+    while "in%d_atoms" % i in g:
+        m = Mol(g["in%d_atoms" % i], g["in%d_coords" % i])
+        m.properties = {"atomization": float(g["in%d_atomization" % i]), "dipole": g["in%d_dipole" % i],
+                        "gradients": g["in%d_gradients" % i], "serial": i}
+        a.mols.append(m)
+        i += 1
+    old = PARAMS["TestRatio"]
+    PARAMS["TestRatio"] = 0.4            # oracle/make_golden.py:TRAIN_PIN_PARAMS
+    try:
+        t = TensorMolData_BP_Direct_EE_WithEle(a, MolDigester(a.AtomTypes(), name_="ANI1_Sym_Direct", OType_="EnergyAndDipole"),
+                                               order_=1, num_indis_=1, type_="mol", WithGrad_=True)
+    finally:
+        PARAMS["TestRatio"] = old
+    eles = sorted(int(e) for e in a.AtomTypes())
+    t.ele = np.asarray(eles).reshape(-1, 1)
+    t.elep = np.asarray([[eles[i], eles[j]] for i in range(len(eles)) for j in range(i, len(eles))])
+    return t
+
+
+def check_train_batches(t, g):
+    import random
+    random.seed(7)
+    t.LoadDataToScratch(None)
+    assert [m.properties["serial"] for m in t.set.mols] == list(g["order"])
+    assert (t.NTrain, t.NTest) == (int(g["NTrain"]), int(g["NTest"]))
+    for kind, n, nc, fn in (("train", 5, 3, t.GetTrainBatch), ("test", 4, 2, t.GetTestBatch)):
+        for c in range(n):
+            batch = fn(nc)
+            assert len(batch) == len(TRAIN_BATCH_NAMES)
+            for nm, v in zip(TRAIN_BATCH_NAMES, batch):
+                ref = g["%s%d_%s" % (kind, c, nm)]
+                v = np.asarray(v)
+                assert v.shape == ref.shape, (kind, c, nm)
+                if nm == "rad_eep":      # the unsorted list keeps MolEmb's x-sweep order inside a row: equal as sets of rows
+                    rows = lambda a: a[np.lexsort((a[:, 2], a[:, 1], a[:, 0]))]                   # noqa: E731
+                    assert v.dtype == ref.dtype and np.array_equal(rows(v), rows(ref)), (kind, c, nm)
+                elif nm in ("Zs", "rad_p_ele", "ang_t_elep", "mil_jk"):
+                    assert v.dtype == ref.dtype and np.array_equal(v, ref), (kind, c, nm)        # index work: bit-exact
+                else:
+                    assert np.array_equal(v, ref), (kind, c, nm)                                  # copies of the inputs / 1/natom
+    with pytest.raises(Exception, match="Insufficent training data"):
+        t.GetTrainBatch(t.NTrain + 1)
+    with pytest.raises(Exception, match="Insufficent training data"):
+        t.GetTestBatch(t.NTest + 1)
+
+
+def test_train_batches_equal_reference_python(monkeypatch):
+    """GetTrainBatch / GetTestBatch (data side): shuffle, train / test split, the wrapping batch pointers, labels
+    and gradient blocks equal the reference's Python executed in place (tests/golden/ref_train_pins.npz).  No GPU here, so the
+    neighbour tables of this CPU test come from the oracle through a stand-in for NeighborListSet -- which pins the oracle's
+    multi-molecule tables against the reference at the same time; tests/test_zz_gpu_widen.py runs the same check on the CUDA tables."""
+    from conftest import load_golden
+    import tensormol_b200.ForceModifiers.Neighbors as NB
+
+    class OracleNeighborListSet:
+        def __init__(self, x_, nnz_, DoTriples_=False, DoPerms_=False, ele_=None, alg_=None, sort_=False):
+            self.x, self.nnz, self.perms, self.Zs = x_, np.asarray(nnz_), DoPerms_, ele_
+
+        def buildPairsAndTriplesWithEleIndex(self, rr, ra, ele, elep):
+            return onp.build_pairs_and_triples_with_ele_index(self.x, self.nnz, self.nnz, self.Zs, rr, ra, ele, elep)
+
+        def buildPairs(self, rng):
+            return onp.set_build_pairs(self.x, self.nnz, self.nnz, rng, self.perms)
+
+    monkeypatch.setattr(NB, "NeighborListSet", OracleNeighborListSet)
+    g = load_golden("ref_train_pins")
+    check_train_batches(train_pin_set(g), g)

@@ -74,3 +74,11 @@ def test_neb_batched_beads_on_gpu_potential():
             assert np.abs(a.Es - b.Es).max() <= 1e-6 * np.abs(a.Es).max()
     finally:
         PARAMS["NebSolver"] = old
+
+
+def test_train_batches_equal_reference_python_on_cuda_tables():
+    """The training-style batch provider (TensorMolData_BP_Direct_EE_WithEle.GetTrainBatch / GetTestBatch) with its neighbour
+    tables built by the CUDA path equals the reference's Python executed in place, entry by entry (index tables bit-exact)."""
+    from test_host_api import check_train_batches, train_pin_set
+    g = load_golden("ref_train_pins")
+    check_train_batches(train_pin_set(g), g)
