@@ -338,6 +338,10 @@ def host_pins():
 
 
 TRAIN_PIN_PARAMS = {"TestRatio": 0.4, "AN1_r_Rc": 4.6, "AN1_a_Rc": 3.1, "EECutoffOff": 15.0}
+TRAIN_BATCH_NAMES = ["xyzs", "Zs", "Elabels", "Dlabels", "grads", "rad_p_ele", "ang_t_elep", "rad_eep", "mil_jk", "inv_natom"]
+TRAIN_PIN_ELES, TRAIN_PIN_HIDDEN, TRAIN_PIN_SEED = (1, 6, 8), (8, 8, 6), 4
+TRAIN_PIN_SCALARS = {"EnergyScalar": 1.0, "GradScalar": 1.0 / 20.0, "DipoleScalar": 1.0}
+TRAIN_PIN_GRAPHS = (("train0", True), ("test1", True), ("test0", False))
 
 
 def train_pins():
@@ -349,6 +353,31 @@ def train_pins():
     for i, d in enumerate(ref_py.train_set_inputs()):
         for k, v in d.items():
             out["in%d_%s" % (i, k)] = np.asarray(v)
+    # the training graph on three of those batches: TrainPrepare's losses and the gradients its three train ops hand to Adam
+    # (loss_op / loss_op_dipole / loss_op_EandG and _variable_with_weight_decay executed in place on the torch stand-in)
+    from oracle.oracle_graph import default_params
+    from tensormol_b200.engine import descriptor_width, random_weights
+    P = default_params()
+    eles, hidden = list(TRAIN_PIN_ELES), list(TRAIN_PIN_HIDDEN)
+    W = ref_py.weights_with_biases(random_weights(eles, descriptor_width(len(eles), P), hidden, TRAIN_PIN_SEED), 100 + TRAIN_PIN_SEED)
+    for tag, ecc in TRAIN_PIN_GRAPHS:
+        batch = [out["%s_%s" % (tag, n)] for n in TRAIN_BATCH_NAMES]
+        Q = dict(P)
+        Q["AddEcc"] = ecc          # what the step feeds AddEcc_pl: PARAMS["AddEcc"], or False in train_step_dipole / test_dipole
+        r = ref_py.train_graph(batch, eles, hidden, W, Q, TRAIN_PIN_SCALARS, add_ecc=ecc)
+        pre = "tq_%s_ecc%d_" % (tag, int(ecc))
+        for k, v in r.items():
+            if not k.startswith("grad_train_op"):
+                out[pre + k] = np.asarray(v)
+        for op, d in (("all_charge", r["grad_train_op"]["charge"]), ("all_energy", r["grad_train_op"]["energy"]),
+                      ("dipole", r["grad_train_op_dipole"]), ("EandG", r["grad_train_op_EandG"])):
+            for z in eles:
+                for l, (gW, gb) in enumerate(d[z]):
+                    if tag == TRAIN_PIN_GRAPHS[0][0]:      # whole gradients for the first graph, Frobenius norms for the others (file size)
+                        out["%sg_%s_%d_%d_W" % (pre, op, z, l)] = gW
+                        out["%sg_%s_%d_%d_b" % (pre, op, z, l)] = gb
+                    else:
+                        out["%sgnorm_%s_%d_%d" % (pre, op, z, l)] = np.array([np.linalg.norm(gW), np.linalg.norm(gb)])
     np.savez_compressed(os.path.join(ROOT, "tests", "golden", "ref_train_pins.npz"), **out)
     print("ref_train_pins:", len(out), "arrays; shuffled order", out["order"])
 

@@ -234,6 +234,20 @@ def vdw_poly_lr(Rb, c6_i, c6_j, Rv_i, Rv_j, R_cut, pairs, P):
 
 
 # --------------------------------------------------------------------------------------
+# Adam as TensorFlow 1.x applies it (tf.train.AdamOptimizer, training(), TMD:2639).  TensorFlow is an un-vendored,
+# un-pinned dependency of the reference (README.md:42): restated from its published documentation -- parity unpinned.
+#     lr_t = lr sqrt(1 - beta2^t) / (1 - beta1^t);  m = beta1 m + (1 - beta1) g;  v = beta2 v + (1 - beta2) g^2;
+#     variable -= lr_t m / (sqrt(v) + epsilon)          (epsilon OUTSIDE the bias correction: TF's "epsilon hat")
+# --------------------------------------------------------------------------------------
+def adam_update(g, m, v, t, lr, beta1=0.9, beta2=0.999, epsilon=1e-8):
+    """Returns (step to SUBTRACT from the variable, new m, new v) for the t-th application (t = 1, 2, ...)."""
+    m = beta1 * m + (1.0 - beta1) * g
+    v = beta2 * v + (1.0 - beta2) * g * g
+    lr_t = lr * math.sqrt(1.0 - beta2 ** t) / (1.0 - beta1 ** t)
+    return lr_t * m / (np.sqrt(v) + epsilon), m, v
+
+
+# --------------------------------------------------------------------------------------
 # Whole evaluation (TMD:5164-5285 aperiodic, 5774-5898 periodic; MGR:1260-1358)
 # --------------------------------------------------------------------------------------
 class Oracle:
@@ -253,7 +267,7 @@ class Oracle:
             raise Exception("EECutoffOn should equal to zero in DSF_elu")      # TMD:4366
         self.elu_shift = dsf(P["Elu_Width"] * BOHRPERA, P["EECutoffOff"] * BOHRPERA, P["DSFAlpha"] / BOHRPERA)      # TMD:4371
         self.elu_alpha = dsf_gradient(P["Elu_Width"] * BOHRPERA, P["EECutoffOff"] * BOHRPERA, P["DSFAlpha"] / BOHRPERA)
-        self.w = {net: {int(z): [(torch.as_tensor(np.asarray(W, np.float64)), torch.as_tensor(np.asarray(b, np.float64)))
+        self.w = {net: {int(z): [(torch.tensor(np.asarray(W, np.float64)), torch.tensor(np.asarray(b, np.float64)))     # copies: train_step updates in place
                                  for W, b in layers] for z, layers in d.items()} for net, d in weights.items()}
 
     # ---- shared pieces -------------------------------------------------------------
@@ -272,9 +286,8 @@ class Oracle:
         return out.reshape(nmol, nrows)
 
     # ---- aperiodic -----------------------------------------------------------------
-    def evaluate(self, xyzs, Zs, natom, has_vdw=True, want=("all",)):
-        """EvalBPDirectEEUpdateSet/Single (MGR:1260-1321) + evaluate (TMD:5684-5711).
-        xyzs (nmol,N,3) f64 padded with zeros, Zs (nmol,N) int padded with 0, natom (nmol,)."""
+    def _graph(self, xyzs, Zs, natom):
+        """The aperiodic graph up to Etotal as torch tensors (coordinates are the differentiable leaf R)."""
         P = self.P
         xyzs = np.ascontiguousarray(xyzs, np.float64)
         Zs = np.asarray(Zs)
@@ -309,11 +322,89 @@ class Oracle:
         else:
             Evdw = torch.zeros(nmol, dtype=F64)
         Etotal = Ebp + Ecc + Evdw                                            # TMD:5213-5215
-        (grad,) = torch.autograd.grad(Etotal.sum(), R)                       # TMD:5761
-        return dict(Etotal=Etotal.detach().numpy(), Ebp=Ebp.detach().numpy(), Ebp_atom=Ebp_atom.detach().numpy(),
-                    Ecc=Ecc.detach().numpy(), Evdw=Evdw.detach().numpy(), dipole=dipole.detach().numpy(),
-                    charge=q.detach().numpy(), gradient=grad.numpy(), force=-JOULEPERHARTREE * grad.numpy(),
-                    descriptors=GM.detach().numpy(), rad_p_ele=rp.numpy(), ang_t_elep=tt.numpy(), ree=ree.numpy())
+        return dict(R=R, GM=GM, q=q, dipole=dipole, Ecc=Ecc, Ebp_atom=Ebp_atom, Ebp=Ebp, Evdw=Evdw, Etotal=Etotal, rp=rp, tt=tt, ree=ree)
+
+    def evaluate(self, xyzs, Zs, natom, has_vdw=True, want=("all",)):
+        """EvalBPDirectEEUpdateSet/Single (MGR:1260-1321) + evaluate (TMD:5684-5711).
+        xyzs (nmol,N,3) f64 padded with zeros, Zs (nmol,N) int padded with 0, natom (nmol,)."""
+        g = self._graph(xyzs, Zs, natom)
+        (grad,) = torch.autograd.grad(g["Etotal"].sum(), g["R"])             # TMD:5761
+        n = lambda k: g[k].detach().numpy()                                  # noqa: E731
+        return dict(Etotal=n("Etotal"), Ebp=n("Ebp"), Ebp_atom=n("Ebp_atom"), Ecc=n("Ecc"), Evdw=n("Evdw"), dipole=n("dipole"),
+                    charge=n("q"), gradient=grad.numpy(), force=-JOULEPERHARTREE * grad.numpy(),
+                    descriptors=n("GM"), rad_p_ele=g["rp"].numpy(), ang_t_elep=g["tt"].numpy(), ree=g["ree"].numpy())
+
+    # ---- training quantities (SURVEY 8f N2) ------------------------------------------
+    def train_quantities(self, xyzs, Zs, natom, Elabels, Dlabels, grads, EnergyScalar=1.0, GradScalar=1.0 / 20.0, DipoleScalar=1.0,
+                         weight_decay=0.001):
+        """Losses of one minibatch and the gradients the three train ops hand to Adam (TrainPrepare, TMD:4997-5049).
+        With w = maxatom / natom per molecule (natom_pl is fed 1/natom, TMD:5146-5160; maxatom = the padded width, TMD:4861):
+            energy_loss = 1/2 sum_m ((E_m - Elabel_m) w_m)^2,   grads_loss = 1/2 sum ((dE/dx - grads) w_m)^2,
+            dipole_loss = 1/2 sum ((dipole - Dlabel) w_m)^2                               (tf.nn.l2_loss = sum(t^2)/2; TMD:4860-4868)
+            loss = EnergyScalar energy_loss + GradScalar grads_loss + DipoleScalar dipole_loss; loss_dipole = dipole_loss;
+            loss_EandG = EnergyScalar energy_loss + GradScalar grads_loss                   (TMD:4870-4901)
+        The ops add to ONE 'losses' collection which already holds weight_decay * l2_loss(W) of every hidden-layer weight matrix
+        of both nets (TFInstance.py:292-295, var_wd=0.001 at TMD:5188-5196, 5244-5256; the linear output layers have none),
+        and every total is the sum of the collection AS IT STANDS when the op is built, so
+            total_loss = decay + loss;  total_loss_dipole = total_loss + loss_dipole;  total_loss_EandG = total_loss_dipole + loss_EandG.
+        train_op minimises total_loss over all variables, train_op_dipole total_loss_dipole over the DipoleNet variables,
+        train_op_EandG total_loss_EandG over the EnergyNet variables (TMD:5046-5048, 2626-2646)."""
+        frozen = self.w
+        self.w = {net: {z: [(W.clone().requires_grad_(True), b.clone().requires_grad_(True)) for W, b in layers] for z, layers in d.items()}
+                  for net, d in frozen.items()}
+        try:
+            g = self._graph(xyzs, Zs, natom)
+            (dEdx,) = torch.autograd.grad(g["Etotal"].sum(), g["R"], create_graph=True)
+            w = torch.as_tensor(float(np.asarray(Zs).shape[1]) / np.asarray(natom, np.float64))
+            e_loss = (((g["Etotal"] - torch.as_tensor(np.asarray(Elabels, np.float64))) * w) ** 2).sum() / 2
+            g_loss = (((dEdx - torch.as_tensor(np.asarray(grads, np.float64))) * w[:, None, None]) ** 2).sum() / 2
+            d_loss = (((g["dipole"] - torch.as_tensor(np.asarray(Dlabels, np.float64))) * w[:, None]) ** 2).sum() / 2
+            loss_eg = e_loss * EnergyScalar + g_loss * GradScalar
+            loss = loss_eg + d_loss * DipoleScalar
+            decay = sum((W ** 2).sum() / 2 * weight_decay for d in self.w.values() for layers in d.values() for W, _ in layers[:-1])
+            total = decay + loss
+            total_d = total + d_loss
+            total_eg = total_d + loss_eg
+            flat = lambda net: [t for z in self.eles for Wb in self.w[net][z] for t in Wb]      # noqa: E731
+            cv, ev = flat("charge"), flat("energy")
+            zero = lambda gs, vs: [torch.zeros_like(v) if a is None else a for a, v in zip(gs, vs)]   # noqa: E731
+            g_all = zero(torch.autograd.grad(total, cv + ev, retain_graph=True, allow_unused=True), cv + ev)
+            g_dip = zero(torch.autograd.grad(total_d, cv, retain_graph=True, allow_unused=True), cv)
+            g_eg = zero(torch.autograd.grad(total_eg, ev, allow_unused=True), ev)
+        finally:
+            live, self.w = self.w, frozen
+
+        def unflat(net, gs):
+            it = iter(gs)
+            return {z: [(next(it).numpy(), next(it).numpy()) for _ in live[net][z]] for z in self.eles}
+
+        n = lambda t: t.detach().numpy()                                     # noqa: E731
+        return dict(Etotal=n(g["Etotal"]), dipole=n(g["dipole"]), gradient=n(dEdx), energy_loss=n(e_loss), grads_loss=n(g_loss),
+                    dipole_loss=n(d_loss), loss=n(loss), loss_dipole=n(d_loss), loss_EandG=n(loss_eg), total_loss=n(total),
+                    total_loss_dipole=n(total_d), total_loss_EandG=n(total_eg),
+                    grad_train_op={"charge": unflat("charge", g_all[:len(cv)]), "energy": unflat("energy", g_all[len(cv):])},
+                    grad_train_op_dipole=unflat("charge", g_dip), grad_train_op_EandG=unflat("energy", g_eg))
+
+    def train_step(self, op, state, xyzs, Zs, natom, Elabels, Dlabels, grads, learning_rate, **scalars):
+        """One minibatch of train_op ("all"), train_op_dipole ("dipole") or train_op_EandG ("EandG"): the gradients of
+        train_quantities applied by Adam to that op's variable list (TMD:2626-2646: tf.train.AdamOptimizer(learning_rate) with
+        TensorFlow's defaults, one optimizer -- its own moments and step count -- per op; `state` is that optimizer's dict,
+        {} before its first step).  Updates self.w in place; returns train_quantities' dict (values BEFORE the update, as
+        sess.run fetches them together with the train op)."""
+        r = self.train_quantities(xyzs, Zs, natom, Elabels, Dlabels, grads, **scalars)
+        sets = {"all": (("charge", r["grad_train_op"]["charge"]), ("energy", r["grad_train_op"]["energy"])),
+                "dipole": (("charge", r["grad_train_op_dipole"]),), "EandG": (("energy", r["grad_train_op_EandG"]),)}[op]
+        state["t"] = state.get("t", 0) + 1
+        for net, gs in sets:
+            for z in self.eles:
+                for l, (gW, gb) in enumerate(gs[z]):
+                    W, b = self.w[net][z][l]
+                    for name, var, gr in (("W", W, gW), ("b", b, gb)):
+                        m, v = state.setdefault((net, z, l, name), (np.zeros(gr.shape), np.zeros(gr.shape)))
+                        step, m, v = adam_update(gr, m, v, state["t"], learning_rate)
+                        state[(net, z, l, name)] = (m, v)
+                        var -= torch.as_tensor(step)
+        return r
 
     # ---- periodic (images supplied by the caller) -----------------------------------
     def evaluate_periodic(self, xyz_tess, Z_tess, nreal, do_force=True):

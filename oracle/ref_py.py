@@ -854,3 +854,94 @@ def train_batch_pins(P, ncases=3, ntrain_calls=5, ncases_test=2, ntest_calls=4, 
             for nm, v in zip(names, fn(nc)):
                 out["%s%d_%s" % (kind, c, nm)] = np.asarray(v)
     return out
+
+
+LOSS_CLASS = "MolInstance_DirectBP_EE_ChargeEncode_Update_vdw_DSF_elu_Normalize"     # defines the loss ops the Dropout class inherits
+
+
+class _TrainInstance(_FakeInstance):
+    """_FakeInstance whose variables are torch leaves and whose `_variable_with_weight_decay` is the reference's own
+    (TFInstance.py:277-297, executed in place: it registers the 0.001 * l2 weight-decay terms in the 'losses' collection)."""
+
+    def load(self, net):
+        from oracle import tf_shim
+        assert not tf_shim._weight_queue and not tf_shim._bias_queue
+        ws, bs = [], []
+        for z in self.eles:
+            for W, b in self._weights[net][int(z)]:
+                ws.append(W)
+                bs.append(b)
+        tf_shim.push_weights(ws)
+        tf_shim.push_biases(bs)
+
+
+def train_graph(batch, eles, hidden, weights, P, scalars, add_ecc=True):
+    """One minibatch through TrainPrepare's graph (TFMolInstanceDirect.py:4997-5049) on the torch stand-in: descriptors,
+    dipole_inference, energy_inference, tf.gradients, then the reference's loss_op / loss_op_dipole / loss_op_EandG
+    (:4860-4901) in that order, so that the 'losses' collection grows as in the reference: total_loss = weight decay + loss,
+    total_loss_dipole = that + loss_dipole, total_loss_EandG = that + loss_EandG.  Returns the fetched values and the
+    gradients the three train ops hand to Adam: d total_loss / d(all variables), d total_loss_dipole / d(DipoleNet variables),
+    d total_loss_EandG / d(EnergyNet variables) (TFMolInstanceDirect.py:2626-2646, 5046-5048).
+    batch: [xyzs, Zs, Elabels, Dlabels, grads, rad_p_ele, ang_t_elep, rad_eep, mil_jk, 1/natom] as GetTrainBatch returns.
+    weights: {"charge"|"energy": {Z: [(W, b), ...]}} numpy; scalars: EnergyScalar, GradScalar, DipoleScalar."""
+    import torch
+    from oracle import tf_shim as tf
+    ns = graph_namespace(P)
+    if "loss_op" not in ns:
+        exec(_method_defs("TensorMol/TFNetworks/TFMolInstanceDirect.py", ["loss_op", "loss_op_dipole", "loss_op_EandG"], LOSS_CLASS), ns)
+        exec(_method_defs("TensorMol/TFNetworks/TFInstance.py", ["_variable_with_weight_decay"]), ns)
+    xyz_np, Zs_np, El, Dl, gl, rad, ang, reep, mil_jk, inv_natom = batch
+    nmol, maxn = Zs_np.shape
+    T = torch.as_tensor
+    leaves = {net: {int(z): [(torch.tensor(np.asarray(W, np.float64), requires_grad=True), torch.tensor(np.asarray(b, np.float64), requires_grad=True))
+                             for W, b in weights[net][int(z)]] for z in eles} for net in ("charge", "energy")}
+    inst = _TrainInstance(ns, eles, hidden, P, nmol, maxn, leaves)
+    _TrainInstance._variable_with_weight_decay = ns["_variable_with_weight_decay"]
+    inst.EnergyScalar, inst.GradScalar, inst.DipoleScalar = scalars["EnergyScalar"], scalars["GradScalar"], scalars["DipoleScalar"]
+    tf.reset_collections()
+    tf.CREATE_GRAPH = True
+    try:
+        xyzs = torch.tensor(np.asarray(xyz_np, np.float64), requires_grad=True)
+        Zt = T(np.asarray(Zs_np, np.int64))
+        natom = T(np.asarray(inv_natom, np.float64))
+        keep = torch.ones(len(hidden) + 1, dtype=torch.float64)
+        Ele, Elep = T(inst.eles_np), T(inst.eles_pairs_np)
+        reep_t = T(np.asarray(reep).astype(np.int64))
+        sym, idx = ns["TFSymSet_Scattered_Linear_WithEle"](xyzs, Zt, Ele, T(inst.SFPr2), inst.Rr_cut, Elep, T(inst.SFPa2), inst.zeta, inst.eta,
+                                                           inst.Ra_cut, T(np.asarray(rad).astype(np.int64)), T(np.asarray(ang).astype(np.int64)),
+                                                           T(np.asarray(mil_jk).astype(np.int64)))
+        inst.load("charge")
+        Ecc, dipole, charge, _ = ns["dipole_inference"](inst, sym, idx, xyzs, natom, P["Elu_Width"], P["EECutoffOff"], reep_t, bool(add_ecc), keep)
+        inst.load("energy")
+        Etotal, Ebp, Evdw, _, Ebp_atom = ns["energy_inference"](inst, sym, idx, Ecc, xyzs, Zt, Ele, T(inst.C6), T(inst.vdw_R), reep_t,
+                                                                P["EECutoffOn"], P["EECutoffOff"], keep)
+        gradient = tf.gradients(Etotal, xyzs)
+        args = (inst, Etotal, gradient, dipole, T(np.asarray(El, np.float64)), T(np.asarray(gl, np.float64)), T(np.asarray(Dl, np.float64)), natom)
+        total, loss, e_loss, g_loss, d_loss = ns["loss_op"](*args)
+        total_d, loss_d, _, _, _ = ns["loss_op_dipole"](*args)
+        total_eg, loss_eg, _, _, _ = ns["loss_op_EandG"](*args)
+        flat = lambda net: [t for z in eles for Wb in leaves[net][int(z)] for t in Wb]          # noqa: E731
+        cv, ev = flat("charge"), flat("energy")
+        g_all = torch.autograd.grad(total, cv + ev, retain_graph=True, allow_unused=True)
+        g_dip = torch.autograd.grad(total_d, cv, retain_graph=True, allow_unused=True)
+        g_eg = torch.autograd.grad(total_eg, ev, retain_graph=True, allow_unused=True)
+    finally:
+        tf.CREATE_GRAPH = False
+        tf.reset_collections()
+
+    def unflat(net, gs):
+        it = iter(gs)
+        out = {}
+        for z in eles:
+            out[int(z)] = []
+            for W, b in leaves[net][int(z)]:
+                gW, gb = next(it), next(it)
+                out[int(z)].append((np.zeros(W.shape) if gW is None else gW.detach().numpy(), np.zeros(b.shape) if gb is None else gb.detach().numpy()))
+        return out
+
+    n = lambda t: t.detach().numpy()       # noqa: E731
+    return dict(Etotal=n(Etotal), Ecc=n(Ecc), Evdw=n(Evdw), dipole=n(dipole), charge=n(charge), gradient=n(gradient[0]),
+                total_loss=n(total), loss=n(loss), energy_loss=n(e_loss), grads_loss=n(g_loss), dipole_loss=n(d_loss),
+                total_loss_dipole=n(total_d), loss_dipole=n(loss_d), total_loss_EandG=n(total_eg), loss_EandG=n(loss_eg),
+                grad_train_op={"charge": unflat("charge", g_all[:len(cv)]), "energy": unflat("energy", g_all[len(cv):])},
+                grad_train_op_dipole=unflat("charge", g_dip), grad_train_op_EandG=unflat("energy", g_eg))

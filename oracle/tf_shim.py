@@ -22,6 +22,8 @@ def push_biases(values):
 def _t(x, dtype=None):
     if isinstance(x, torch.Tensor):
         return x if dtype is None else x.to(dtype)
+    if isinstance(x, (list, tuple)) and any(isinstance(v, torch.Tensor) and v.numel() > 1 for v in x):
+        return torch.stack(list(x))                      # tf.gradients() returns a list; TF packs it into one tensor (loss_op)
     if isinstance(x, (list, tuple)) and any(isinstance(v, torch.Tensor) for v in x):
         x = [int(v) if isinstance(v, torch.Tensor) else v for v in x]
     return torch.as_tensor(np.asarray(x), dtype=dtype)
@@ -59,6 +61,20 @@ def convert_to_tensor(v, dtype=None):
 
 def identity(x, name=None):
     return x
+
+
+_weight_queue = []
+
+
+def push_weights(values):
+    """Values for the variables TFInstance._variable_with_weight_decay creates (tf.Variable(tf.truncated_normal(...)))."""
+    _weight_queue.extend(values)
+
+
+def truncated_normal(shp, stddev=1.0, dtype=None):
+    W = _weight_queue.pop(0)
+    assert list(W.shape) == _ints(shp), (W.shape, shp)
+    return W
 
 
 def Variable(init, trainable=True, dtype=None, name=None):
@@ -143,15 +159,15 @@ def pow(x, y):   # noqa: A001
     return torch.pow(_t(x, float64) if not isinstance(x, torch.Tensor) else x, y)
 
 
-def multiply(a, b):
+def multiply(a, b, name=None):
     return _t(a) * _t(b)
 
 
-def add(a, b):
+def add(a, b, name=None):
     return _t(a) + _t(b)
 
 
-def subtract(a, b):
+def subtract(a, b, name=None):
     return _t(a) - _t(b)
 
 
@@ -237,8 +253,28 @@ def verify_tensor_all_finite(x, msg):
     return x
 
 
+_collections = {}
+
+
+def reset_collections():
+    _collections.clear()
+
+
+def add_to_collection(key, value):
+    _collections.setdefault(key, []).append(value)
+
+
 def get_collection(key, scope=None):
-    return []
+    """Only the 'losses' collection is kept (the loss ops and the weight-decay terms add to it, TFInstance.py:292-295,
+    TFMolInstanceDirect.py:4872-4873); variable collections are the caller's own bookkeeping."""
+    return list(_collections.get(key, [])) if key == "losses" else []
+
+
+def add_n(xs, name=None):
+    out = xs[0]
+    for x in xs[1:]:
+        out = out + x
+    return out
 
 
 class GraphKeys:
@@ -257,6 +293,13 @@ class nn:   # noqa: N801
         assert kp == 1.0, "evaluation runs with keep_prob = 1"
         return x
 
+    @staticmethod
+    def l2_loss(x, name=None):
+        return (_t(x) ** 2).sum() / 2
+
+
+CREATE_GRAPH = False      # True: the coordinate gradient stays differentiable (the force term of the training loss)
+
 
 def gradients(y, x, name=None):
-    return list(torch.autograd.grad(y.sum(), x, retain_graph=True))
+    return list(torch.autograd.grad(y.sum(), x, retain_graph=True, create_graph=CREATE_GRAPH))

@@ -71,6 +71,69 @@ class BPInstance:
         self.engine.set_weights(w)
         self.weights = w
 
+    # ---- the evaluation half of the training loop (reference TFMolInstanceDirect.py:4860-4901, 5420-5494) ----
+    def batch_losses(self, batch_data, AddEcc=None):
+        """The reference's loss values of one minibatch, from ONE forward + force evaluation on the CUDA path.
+        batch_data = [xyzs, Zs, Elabels, Dlabels, grads, rad_p_ele, ang_t_elep, rad_eep, mil_jk, 1/natom] as
+        TData.GetTrainBatch / GetTestBatch return it (WithGrad_=True); the neighbour tables in it are not needed, the
+        library builds its own.  With w_m = MaxNAtoms / natom_m (the graph is fed 1/natom and multiplies by the padded
+        width, :4861): energy_loss = 1/2 sum ((E - Elabel) w)^2, grads_loss = 1/2 sum ((dE/dx - grads) w)^2,
+        dipole_loss = 1/2 sum ((dipole - Dlabel) w)^2; loss = EnergyScalar energy_loss + GradScalar grads_loss +
+        DipoleScalar dipole_loss, loss_dipole = dipole_loss, loss_EandG = the first two terms.  Sums in float64 on the host
+        (a few numbers per molecule).  Returns a dict with those six plus Etotal, Ecc, Evdw, dipole, charge."""
+        if len(batch_data) < 10:
+            raise Exception("batch_losses needs batches with gradient labels (TensorMolData built with WithGrad_=True)")
+        xyzs, Zs, Elabels, Dlabels, grads = batch_data[:5]
+        inv_natom = np.asarray(batch_data[9], np.float64)
+        if not np.all(np.isfinite(Elabels)):
+            raise Exception("DontEatShit")                                   # fill_feed_dict, :5157-5159
+        natom = np.rint(1.0 / inv_natom).astype(np.int32)
+        old = PARAMS["AddEcc"]
+        if AddEcc is not None:
+            PARAMS["AddEcc"] = bool(AddEcc)
+        try:
+            self.refresh()
+            r = self.engine.evaluate(xyzs, Zs, natom, do_force=True, has_vdw=True)
+        finally:
+            PARAMS["AddEcc"] = old
+        w = float(np.asarray(Zs).shape[1]) * inv_natom
+        e_loss = 0.5 * np.sum(((r["Etotal"] - Elabels) * w) ** 2)
+        g_loss = 0.5 * np.sum(((r["gradient"] - grads) * w[:, None, None]) ** 2)
+        d_loss = 0.5 * np.sum(((r["dipole"] - Dlabels) * w[:, None]) ** 2)
+        loss_eg = e_loss * PARAMS["EnergyScalar"] + g_loss * PARAMS["GradScalar"]
+        return dict(loss=loss_eg + d_loss * PARAMS["DipoleScalar"], loss_dipole=d_loss, loss_EandG=loss_eg, energy_loss=e_loss,
+                    grads_loss=g_loss, dipole_loss=d_loss, Etotal=r["Etotal"], Ecc=r["Ecc"], Evdw=r["Evdw"], dipole=r["dipole"], charge=r["charge"])
+
+    def _test(self, step, which, AddEcc):
+        import time
+        bs = int(PARAMS["batch_size"])
+        start = time.time()
+        tot = dict(loss=0.0, energy_loss=0.0, grads_loss=0.0, dipole_loss=0.0)
+        nmols = 0
+        for _ in range(int(self.TData.NTest / bs)):
+            L = self.batch_losses(self.TData.GetTestBatch(bs), AddEcc)
+            tot["loss"] += L[which]
+            for k in ("energy_loss", "grads_loss", "dipole_loss"):
+                tot[k] += L[k]
+            nmols += bs
+        LOGGER.info("testing...")
+        self.print_training(step, tot["loss"], tot["energy_loss"], tot["grads_loss"], tot["dipole_loss"], nmols, time.time() - start, False)
+        return tot["loss"]
+
+    def test(self, step):
+        """Sum of `loss` over the test batches (:5600-5640); test_dipole feeds AddEcc = False, the others PARAMS["AddEcc"]."""
+        return self._test(step, "loss", PARAMS["AddEcc"])
+
+    def test_dipole(self, step):
+        return self._test(step, "loss_dipole", False)
+
+    def test_EandG(self, step):
+        return self._test(step, "loss_EandG", PARAMS["AddEcc"])
+
+    def print_training(self, step, loss, energy_loss, grads_loss, dipole_loss, Ncase, duration, Train=True):
+        LOGGER.info("step: %7d  duration: %.5f  %s loss: %.10f  energy_loss: %.10f  grad_loss: %.10f, dipole_loss: %.10f", step, duration,
+                    "train" if Train else "test", float(loss) / Ncase, float(energy_loss) / Ncase, float(grads_loss) / Ncase, float(dipole_loss) / Ncase)
+
 
 class TFMolManage:
     def __init__(self, Name_="", TData_=None, Train_=True, NetType_="fc_sqdiff", RandomTData_=True, Trainable_=True):

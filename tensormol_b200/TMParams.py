@@ -41,7 +41,14 @@ class TMParams(dict):
         self["Profiling"] = False
         self["GradScalar"] = 1.0 / 20.0
         self["EnergyScalar"] = 1.0
-        self["DipoleScaler"] = 1.0
+        self["DipoleScaler"] = 1.0          # (sic) reference TMParams.py:82; the instance reads "DipoleScalar" (:40)
+        self["DipoleScalar"] = 1.0
+        self["learning_rate"] = 0.001
+        self["learning_rate_dipole"] = 0.0001
+        self["learning_rate_energy"] = 0.00001
+        self["momentum"] = 0.9
+        self["max_steps"] = 1001
+        self["test_freq"] = 10
         # optimisation
         self["OptMaxCycles"] = 50
         self["OptThresh"] = 0.0001

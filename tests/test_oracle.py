@@ -398,3 +398,98 @@ def test_oracle_equals_reference_graph_periodic():
         assert abs(o[k][0] - p["graph_periodic_" + k][0]) <= 1e-11 * max(abs(p["graph_periodic_" + k][0]), 1e-6), k
     assert np.abs(o["gradient"][0][:nreal] - p["graph_periodic_gradient"][0]).max() <= 1e-13
     assert np.abs(np.asarray(o["charge"])[0][:nreal] - p["graph_periodic_charge"][0]).max() <= 1e-14
+
+
+# ---- training quantities: the oracle's restatement of TrainPrepare's losses and of the gradients its three train
+# ops hand to Adam, against the reference's loss_op / loss_op_dipole / loss_op_EandG / _variable_with_weight_decay executed in
+# place on the torch stand-in (oracle/ref_py.py:train_graph -> tests/golden/ref_train_pins.npz) ----
+TRAIN_PIN_ELES, TRAIN_PIN_HIDDEN, TRAIN_PIN_SEED = [1, 6, 8], [8, 8, 6], 4       # oracle/make_golden.py
+TRAIN_PIN_GRAPHS = (("train0", True), ("test1", True), ("test0", False))
+LOSS_KEYS = ("energy_loss", "grads_loss", "dipole_loss", "loss", "loss_dipole", "loss_EandG", "total_loss", "total_loss_dipole", "total_loss_EandG")
+
+
+def train_pin_weights():
+    from oracle.ref_py import weights_with_biases
+    P = og.default_params()
+    return weights_with_biases(random_weights(TRAIN_PIN_ELES, descriptor_width(len(TRAIN_PIN_ELES), P), TRAIN_PIN_HIDDEN, TRAIN_PIN_SEED),
+                               100 + TRAIN_PIN_SEED)
+
+
+def _train_quantities(g, tag, ecc, W):
+    P = og.default_params()
+    P["AddEcc"] = ecc
+    b = {n: g["%s_%s" % (tag, n)] for n in ("xyzs", "Zs", "Elabels", "Dlabels", "grads", "inv_natom")}
+    natom = np.rint(1.0 / b["inv_natom"]).astype(np.int64)
+    return og.Oracle(TRAIN_PIN_ELES, W, P).train_quantities(b["xyzs"], b["Zs"], natom, b["Elabels"], b["Dlabels"], b["grads"],
+                                                            EnergyScalar=1.0, GradScalar=1.0 / 20.0, DipoleScalar=1.0)
+
+
+@pytest.mark.parametrize("tag,ecc", TRAIN_PIN_GRAPHS)
+def test_oracle_training_losses_and_weight_gradients_equal_reference_graph(tag, ecc):
+    g = load_golden("ref_train_pins")
+    r = _train_quantities(g, tag, ecc, train_pin_weights())
+    pre = "tq_%s_ecc%d_" % (tag, int(ecc))
+    for k in LOSS_KEYS + ("Etotal", "dipole", "gradient"):
+        ref = g[pre + k]
+        assert np.abs(r[k] - ref).max() <= 1e-12 * max(np.abs(ref).max(), 1e-30), k
+    # the 'losses' collection quirk: every total is the sum of all losses registered so far, weight decay included
+    assert abs(g[pre + "total_loss_dipole"] - g[pre + "total_loss"] - g[pre + "loss_dipole"]) <= 1e-13
+    assert abs(g[pre + "total_loss_EandG"] - g[pre + "total_loss_dipole"] - g[pre + "loss_EandG"]) <= 1e-13
+    assert g[pre + "total_loss"] > g[pre + "loss"]
+    sets = (("all_charge", r["grad_train_op"]["charge"]), ("all_energy", r["grad_train_op"]["energy"]),
+            ("dipole", r["grad_train_op_dipole"]), ("EandG", r["grad_train_op_EandG"]))
+    for op, d in sets:
+        for z in TRAIN_PIN_ELES:
+            for l, (gW, gb) in enumerate(d[z]):
+                if pre + "g_%s_%d_%d_W" % (op, z, l) in g:
+                    rW, rb = g[pre + "g_%s_%d_%d_W" % (op, z, l)], g[pre + "g_%s_%d_%d_b" % (op, z, l)]
+                    assert np.abs(gW - rW).max() <= 1e-11 * max(np.abs(rW).max(), 1e-6), (op, z, l)
+                    assert np.abs(gb - rb).max() <= 1e-11 * max(np.abs(rb).max(), 1e-6), (op, z, l)
+                else:
+                    nW, nb = g[pre + "gnorm_%s_%d_%d" % (op, z, l)]
+                    assert abs(np.linalg.norm(gW) - nW) <= 1e-11 * max(nW, 1e-6) and abs(np.linalg.norm(gb) - nb) <= 1e-11 * max(nb, 1e-6)
+
+
+def test_oracle_weight_gradient_equals_finite_difference_of_total_loss():
+    """An independent check of the double back-pass (the force term of the loss differentiates dE/dx w.r.t. the weights):
+    central differences of total_loss in single entries of an energy-net and a charge-net weight matrix."""
+    g = load_golden("ref_train_pins")
+    W = train_pin_weights()
+    r = _train_quantities(g, "train0", True, W)
+    for net, z, l, ij in (("energy", 8, 1, (2, 3)), ("charge", 1, 0, (40, 1)), ("energy", 6, 3, (4, 0))):
+        h = 1e-5
+        vals = []
+        for s in (+1, -1):
+            Wp = {n: {e: [(a.copy(), b.copy()) for a, b in layers] for e, layers in d.items()} for n, d in W.items()}
+            Wp[net][z][l][0][ij] += s * h
+            vals.append(float(_train_quantities(g, "train0", True, Wp)["total_loss"]))
+        fd = (vals[0] - vals[1]) / (2 * h)
+        an = r["grad_train_op"][net][z][l][0][ij]
+        assert abs(fd - an) <= 1e-6 * max(abs(an), 1e-3), (net, z, l, fd, an)
+
+
+def test_adam_known_answers_and_dipole_stage_descends():
+    """TensorFlow's Adam (un-vendored third party; restated from its documentation): the first step of any component is
+    lr sqrt(1-b2) g / (sqrt(1-b2) |g| + eps) ~ lr sign(g); a constant gradient keeps that step size; and ten train_op_dipole
+    steps on one pinned minibatch lower its dipole loss while leaving the EnergyNet untouched."""
+    gvec = np.array([0.5, -2.0, 1e-3])
+    step, m, v = og.adam_update(gvec, np.zeros(3), np.zeros(3), 1, 0.01)
+    want = 0.01 * np.sqrt(1 - 0.999) * gvec / (np.sqrt(1 - 0.999) * np.abs(gvec) + 1e-8)
+    assert np.allclose(step, want, rtol=1e-14, atol=0) and np.allclose(step, 0.01 * np.sign(gvec), rtol=1e-3)
+    assert np.allclose(m, 0.1 * gvec) and np.allclose(v, 0.001 * gvec ** 2)
+    for t in range(2, 6):
+        step, m, v = og.adam_update(gvec, m, v, t, 0.01)
+        assert np.allclose(step, 0.01 * np.sign(gvec), rtol=1e-3)
+    g = load_golden("ref_train_pins")
+    P = og.default_params()
+    o = og.Oracle(TRAIN_PIN_ELES, train_pin_weights(), P)
+    b = {n: g["train0_" + n] for n in ("xyzs", "Zs", "Elabels", "Dlabels", "grads", "inv_natom")}
+    natom = np.rint(1.0 / b["inv_natom"]).astype(np.int64)
+    e0 = [W.clone() for z in o.eles for W, _ in o.w["energy"][z]]
+    state, hist = {}, []
+    for _ in range(10):
+        r = o.train_step("dipole", state, b["xyzs"], b["Zs"], natom, b["Elabels"], b["Dlabels"], b["grads"], 1e-3)
+        hist.append(float(r["dipole_loss"]))
+    assert abs(hist[0] - float(g["tq_train0_ecc1_dipole_loss"])) <= 1e-12 * hist[0]
+    assert hist[-1] < hist[0] and state["t"] == 10
+    assert all(torch.equal(a, W) for a, W in zip(e0, [W for z in o.eles for W, _ in o.w["energy"][z]]))

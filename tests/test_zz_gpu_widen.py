@@ -82,3 +82,50 @@ def test_train_batches_equal_reference_python_on_cuda_tables():
     from test_host_api import check_train_batches, train_pin_set
     g = load_golden("ref_train_pins")
     check_train_batches(train_pin_set(g), g)
+
+
+def test_batch_losses_and_test_steps_equal_reference_graph():
+    """The evaluation half of the reference's training loop on the CUDA path: BPInstance.batch_losses on the
+    reference's own minibatches against the reference's loss ops executed in place (tests/golden/ref_train_pins.npz), and
+    test() / test_dipole() / test_EandG() over the test cases against the oracle (itself pinned to those loss ops).
+    Tolerances: the losses are sums of squared differences between fp32-path outputs and O(0.1) labels, so the north-star
+    tolerances (energy 1e-5 relative, force 1e-4 Hartree/Bohr) map to 1e-4 relative on energy_loss / dipole_loss and 1e-3
+    relative on grads_loss."""
+    import random
+    from test_gpu_api import NET, _setup_params
+    from test_host_api import train_pin_set
+    from test_oracle import TRAIN_PIN_ELES, TRAIN_PIN_HIDDEN, _train_quantities, train_pin_weights
+    from tensormol_b200 import PARAMS, TFMolManage
+    g = load_golden("ref_train_pins")
+    _setup_params(TRAIN_PIN_HIDDEN)
+    PARAMS["EnergyScalar"], PARAMS["GradScalar"], PARAMS["DipoleScalar"] = 1.0, 1.0 / 20.0, 1.0
+    t = train_pin_set(g)
+    assert [int(e) for e in t.eles] == TRAIN_PIN_ELES
+    manager = TFMolManage("", t, False, NET, False, False)
+    W = train_pin_weights()
+    manager.SetWeights(W)
+    I = manager.Instances
+    random.seed(7)
+    t.LoadDataToScratch(None)
+    rtol = dict(energy_loss=1e-4, dipole_loss=1e-4, grads_loss=1e-3, loss=1e-4, loss_dipole=1e-4, loss_EandG=1e-4)
+
+    def check(L, pre):
+        for k, tol in rtol.items():
+            assert abs(L[k] - float(g[pre + k])) <= tol * abs(float(g[pre + k])), (pre, k, L[k], float(g[pre + k]))
+        assert np.abs(L["Etotal"] - g[pre + "Etotal"]).max() <= 1e-5 * np.abs(g[pre + "Etotal"]).max()
+
+    check(I.batch_losses(t.GetTrainBatch(3), True), "tq_train0_ecc1_")
+    check(I.batch_losses(t.GetTestBatch(2), False), "tq_test0_ecc0_")
+    check(I.batch_losses(t.GetTestBatch(2), True), "tq_test1_ecc1_")
+    assert PARAMS["AddEcc"] is True
+    # whole test steps: two test batches of two molecules (NTest = 4), pointer back at the first test case
+    old = PARAMS["batch_size"]
+    PARAMS["batch_size"] = 2
+    try:
+        for fn, key, ecc in ((I.test_EandG, "loss_EandG", True), (I.test_dipole, "loss_dipole", False), (I.test, "loss", True)):
+            t.test_ScratchPointer = t.LastTrainMol
+            want = sum(float(_train_quantities(g, tag, ecc, W)[key]) for tag in ("test0", "test1"))
+            got = fn(0)
+            assert abs(got - want) <= 1e-4 * abs(want), (key, got, want)
+    finally:
+        PARAMS["batch_size"] = old
