@@ -166,3 +166,82 @@ class EngineSlabBackend:
 
     def slab_phase_c(self, e, flags, grad):
         check(self.lib.tm_slab_phase_c(self.eng.ctx, C.c_void_p(e.data_ptr()), int(flags), C.c_void_p(grad.data_ptr())), "tm_slab_phase_c")
+
+
+# ---- molecule batches: independent units, sharded across the ranks -------------------------
+def batch_shard_bounds(natom, world):
+    """Contiguous molecule blocks [b[r], b[r+1]) per rank, cut where the running atom count crosses r/world of the total, so a
+    ragged batch is balanced by work rather than by molecule count.  Deterministic, every molecule in exactly one block,
+    blocks may be empty (fewer molecules than ranks)."""
+    natom = np.asarray(natom, np.int64)
+    csum = np.concatenate([[0], np.cumsum(natom)])
+    total = int(csum[-1])
+    b = [0]
+    for r in range(1, int(world)):
+        target = total * r / float(world)
+        cut = int(np.searchsorted(csum, target, side="left"))
+        # csum[cut] >= target > csum[cut-1]: take the nearer of the two cuts
+        if cut > 0 and target - csum[cut - 1] < csum[min(cut, len(natom))] - target:
+            cut -= 1
+        b.append(min(max(cut, b[-1]), len(natom)))
+    b.append(len(natom))
+    return np.asarray(b, np.int64)
+
+
+class BatchShardEvaluator:
+    """Energy + force of a padded molecule batch (the EvalBPDirectEEUpdateSet / training-style contract) with the molecules
+    sharded over the ranks: each rank evaluates its block with ONE tm_eval call; there is no data-path collective, only the
+    final gather of the per-molecule results (one all_gather of a packed float64 table, blocks padded to the largest).
+    `backend.evaluate(xyzs, Zs, natom, do_force=..., has_vdw=...)` is Engine.evaluate (CUDA) or a stand-in with the same
+    signature (the gloo CPU test).  The reference has no counterpart (single process)."""
+
+    KEYS = ("Etotal", "Ebp", "Ecc", "Evdw", "dipole", "Ebp_atom", "charge", "gradient")
+
+    def __init__(self, backend, rank, world, dist=None, device="cpu"):
+        self.backend, self.rank, self.world, self.dist, self.device = backend, int(rank), int(world), dist, device
+
+    @staticmethod
+    def _pack(r, nloc, maxn):
+        row = np.zeros((nloc, 7 + 5 * maxn))
+        row[:, 0], row[:, 1], row[:, 2], row[:, 3] = r["Etotal"], r["Ebp"], r["Ecc"], r["Evdw"]
+        row[:, 4:7] = r["dipole"]
+        row[:, 7:7 + maxn] = r["Ebp_atom"]
+        row[:, 7 + maxn:7 + 2 * maxn] = r["charge"]
+        row[:, 7 + 2 * maxn:] = np.asarray(r["gradient"]).reshape(nloc, 3 * maxn)
+        return row
+
+    @staticmethod
+    def _unpack(row, maxn):
+        n = row.shape[0]
+        return dict(Etotal=row[:, 0].copy(), Ebp=row[:, 1].copy(), Ecc=row[:, 2].copy(), Evdw=row[:, 3].copy(), dipole=row[:, 4:7].copy(),
+                    Ebp_atom=row[:, 7:7 + maxn].copy(), charge=row[:, 7 + maxn:7 + 2 * maxn].copy(),
+                    gradient=row[:, 7 + 2 * maxn:].reshape(n, maxn, 3).copy())
+
+    def evaluate_local(self, xyzs, Zs, natom, do_force=True, has_vdw=True):
+        """This rank's block only: (lo, hi, result dict of the block's molecules).  What a training-style step needs (its
+        losses are sums over molecules: one scalar all-reduce instead of the gather)."""
+        b = batch_shard_bounds(natom, self.world)
+        lo, hi = int(b[self.rank]), int(b[self.rank + 1])
+        maxn = np.asarray(Zs).shape[1]
+        if hi == lo:
+            return lo, hi, self._unpack(np.zeros((0, 7 + 5 * maxn)), maxn)
+        return lo, hi, self.backend.evaluate(xyzs[lo:hi], Zs[lo:hi], np.asarray(natom)[lo:hi], do_force=do_force, has_vdw=has_vdw)
+
+    def evaluate(self, xyzs, Zs, natom, do_force=True, has_vdw=True):
+        """Every rank returns the results of the WHOLE batch, in batch order."""
+        import torch
+        lo, hi, r = self.evaluate_local(xyzs, Zs, natom, do_force, has_vdw)
+        nmol, maxn = np.asarray(Zs).shape
+        if self.world == 1 or self.dist is None:
+            return r
+        b = batch_shard_bounds(natom, self.world)
+        cap = int(np.max(np.diff(b)))
+        mine = np.zeros((cap, 7 + 5 * maxn))
+        mine[:hi - lo] = self._pack(r, hi - lo, maxn)
+        send = torch.from_numpy(mine).to(self.device)
+        recv = torch.empty((self.world * cap, send.shape[1]), dtype=send.dtype, device=self.device)     # concatenation along dim 0
+        self.dist.all_gather_into_tensor(recv, send)
+        recv = recv.cpu().numpy().reshape(self.world, cap, send.shape[1])
+        rows = np.concatenate([recv[k, :int(b[k + 1] - b[k])] for k in range(self.world)], axis=0)
+        assert rows.shape[0] == nmol
+        return self._unpack(rows, maxn)

@@ -117,3 +117,82 @@ def test_two_rank_gloo_matches_single_rank():
     assert e1[0] == pytest.approx(e1[1] + e1[2] + e1[3])
     assert np.allclose(g1, g2, rtol=1e-12, atol=1e-14)
     assert np.abs(g1).max() > 0
+
+
+# ---- molecule batches sharded over the ranks (config C2: independent units, no data-path collective, one final gather) ----
+from tensormol_b200.parallel import BatchShardEvaluator, batch_shard_bounds   # noqa: E402
+
+
+class MoleculeBackend:
+    """Engine.evaluate's signature on a toy per-molecule model: every output depends on that molecule only."""
+
+    def evaluate(self, xyzs, Zs, natom, do_force=True, has_vdw=True):
+        nmol, maxn = Zs.shape
+        mask = (np.arange(maxn)[None, :] < np.asarray(natom)[:, None]).astype(float)
+        r2 = (xyzs ** 2).sum(-1) * mask
+        q = (Zs * 0.01 + r2) * mask
+        return dict(Etotal=r2.sum(1) + q.sum(1), Ebp=r2.sum(1), Ecc=q.sum(1), Evdw=np.zeros(nmol), dipole=(q[:, :, None] * xyzs).sum(1),
+                    Ebp_atom=r2, charge=q, gradient=2 * xyzs * mask[:, :, None] * (1.0 if do_force else 0.0))
+
+
+def _ragged_batch(nmol, seed=3):
+    rng = np.random.default_rng(seed)
+    natom = rng.integers(1, 9, nmol)
+    maxn = 8
+    xyzs = rng.normal(size=(nmol, maxn, 3))
+    Zs = rng.choice([1, 6, 8], size=(nmol, maxn)).astype(np.int32)
+    for m in range(nmol):
+        xyzs[m, natom[m]:] = 0
+        Zs[m, natom[m]:] = 0
+    return xyzs, Zs, natom
+
+
+def test_batch_shard_bounds_cover_and_balance():
+    for nmol in (0, 1, 2, 7, 100):
+        natom = np.random.default_rng(nmol).integers(1, 50, nmol)
+        for w in (1, 2, 3, 4, 8):
+            b = batch_shard_bounds(natom, w)
+            assert b[0] == 0 and b[-1] == nmol and len(b) == w + 1 and np.all(np.diff(b) >= 0)
+    natom = np.random.default_rng(5).integers(1, 50, 1000)
+    b = batch_shard_bounds(natom, 8)
+    work = np.add.reduceat(natom, b[:-1])
+    assert work.max() - work.min() <= 2 * natom.max()            # balanced by atoms to within a molecule either side
+    assert batch_shard_bounds(np.full(16, 40), 4).tolist() == [0, 4, 8, 12, 16]
+
+
+def _batch_worker(rank, world, port, q, nmol):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    xyzs, Zs, natom = _ragged_batch(nmol)
+    ev = BatchShardEvaluator(MoleculeBackend(), rank, world, dist, "cpu")
+    r = ev.evaluate(xyzs, Zs, natom)
+    lo, hi, loc = ev.evaluate_local(xyzs, Zs, natom)
+    s = torch.tensor([loc["Etotal"].sum()])
+    dist.all_reduce(s)
+    q.put((rank, r, float(s[0]), (lo, hi)))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("nmol", [11, 1])
+def test_two_rank_gloo_batch_shards_equal_whole_batch(nmol):
+    """Both ranks end with the whole batch's results in batch order, equal to one unsharded call (bit-exact: the units are
+    independent); a batch smaller than the world leaves a rank with an empty block."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_batch_worker, args=(r, 2, port, q, nmol)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=120) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    xyzs, Zs, natom = _ragged_batch(nmol)
+    whole = MoleculeBackend().evaluate(xyzs, Zs, natom)
+    blocks = sorted(g[3] for g in got)
+    assert blocks[0][0] == 0 and blocks[0][1] == blocks[1][0] and blocks[1][1] == nmol
+    for rank, r, esum, _ in got:
+        for k in BatchShardEvaluator.KEYS:
+            assert np.array_equal(r[k], whole[k]), (rank, k)
+        assert esum == pytest.approx(whole["Etotal"].sum(), rel=1e-13)
