@@ -286,8 +286,8 @@ class Oracle:
         return out.reshape(nmol, nrows)
 
     # ---- aperiodic -----------------------------------------------------------------
-    def _graph(self, xyzs, Zs, natom):
-        """The aperiodic graph up to Etotal as torch tensors (coordinates are the differentiable leaf R)."""
+    def _graph(self, xyzs, Zs, natom, R=None):
+        """The aperiodic graph up to Etotal as torch tensors (coordinates are the differentiable leaf R, or the tensor handed in)."""
         P = self.P
         xyzs = np.ascontiguousarray(xyzs, np.float64)
         Zs = np.asarray(Zs)
@@ -298,7 +298,8 @@ class Oracle:
         rp = torch.as_tensor(rp.astype(np.int64))
         tt = torch.as_tensor(tt.astype(np.int64))
         ree = torch.as_tensor(ree)
-        R = torch.tensor(xyzs, dtype=F64, requires_grad=True)
+        if R is None:
+            R = torch.tensor(xyzs, dtype=F64, requires_grad=True)
         GM = descriptors(R, rp, tt, P, self.nele, self.nelep, N)
         # charges
         q_raw = self._nets(GM, Zs, "charge")
@@ -384,6 +385,39 @@ class Oracle:
                     total_loss_dipole=n(total_d), total_loss_EandG=n(total_eg),
                     grad_train_op={"charge": unflat("charge", g_all[:len(cv)]), "energy": unflat("energy", g_all[len(cv):])},
                     grad_train_op_dipole=unflat("charge", g_dip), grad_train_op_EandG=unflat("energy", g_eg))
+
+    def total_loss_gradient_by_tangent_pass(self, xyzs, Zs, natom, Elabels, Dlabels, grads, EnergyScalar=1.0, GradScalar=1.0 / 20.0,
+                                            DipoleScalar=1.0, weight_decay=0.001):
+        """d total_loss / d(all variables) WITHOUT differentiating the force back-pass -- the algorithm planned for the device
+        (DESIGN.md section 6b).  With v = w^2 (dE/dx - g_label) held constant,
+            d grads_loss / dW = d/dW <v, dE/dx> = d/dW [ d/d(eps) E(x + eps v; W) at eps = 0 ],
+        so ONE forward-mode (tangent) pass of the energy graph along v gives a scalar whose ordinary back-pass is the force
+        term of the weight gradient; the energy / dipole / decay terms are ordinary back-passes.  Returns the same nested dict
+        as train_quantities()["grad_train_op"]; tests/test_oracle.py checks it equals that (double-backward) result."""
+        import torch.autograd.forward_ad as fwAD
+        r0 = self.evaluate(xyzs, Zs, natom)
+        w = float(np.asarray(Zs).shape[1]) / np.asarray(natom, np.float64)
+        v = (r0["gradient"] - np.asarray(grads, np.float64)) * (w ** 2)[:, None, None]
+        frozen = self.w
+        self.w = {net: {z: [(W.clone().requires_grad_(True), b.clone().requires_grad_(True)) for W, b in layers] for z, layers in d.items()}
+                  for net, d in frozen.items()}
+        try:
+            wt = torch.as_tensor(w)
+            with fwAD.dual_level():
+                R = fwAD.make_dual(torch.tensor(np.ascontiguousarray(xyzs, np.float64)), torch.as_tensor(v))
+                g = self._graph(xyzs, Zs, natom, R=R)
+                E, dE = fwAD.unpack_dual(g["Etotal"])
+                dip = fwAD.unpack_dual(g["dipole"]).primal
+                e_loss = (((E - torch.as_tensor(np.asarray(Elabels, np.float64))) * wt) ** 2).sum() / 2
+                d_loss = (((dip - torch.as_tensor(np.asarray(Dlabels, np.float64))) * wt[:, None]) ** 2).sum() / 2
+                decay = sum((W ** 2).sum() / 2 * weight_decay for d in self.w.values() for layers in d.values() for W, _ in layers[:-1])
+                total = decay + EnergyScalar * e_loss + DipoleScalar * d_loss + GradScalar * dE.sum()
+                flat = [t for net in ("charge", "energy") for z in self.eles for Wb in self.w[net][z] for t in Wb]
+                gs = torch.autograd.grad(total, flat, allow_unused=True)
+        finally:
+            live, self.w = self.w, frozen
+        it = iter(torch.zeros_like(t) if a is None else a for a, t in zip(gs, flat))
+        return {net: {z: [(next(it).numpy(), next(it).numpy()) for _ in live[net][z]] for z in self.eles} for net in ("charge", "energy")}
 
     def train_step(self, op, state, xyzs, Zs, natom, Elabels, Dlabels, grads, learning_rate, **scalars):
         """One minibatch of train_op ("all"), train_op_dipole ("dipole") or train_op_EandG ("EandG"): the gradients of

@@ -493,3 +493,21 @@ def test_adam_known_answers_and_dipole_stage_descends():
     assert abs(hist[0] - float(g["tq_train0_ecc1_dipole_loss"])) <= 1e-12 * hist[0]
     assert hist[-1] < hist[0] and state["t"] == 10
     assert all(torch.equal(a, W) for a, W in zip(e0, [W for z in o.eles for W, _ in o.w["energy"][z]]))
+
+
+def test_tangent_pass_weight_gradient_equals_double_backward():
+    """The algorithm planned for the device training step: the force term of the weight gradient from ONE
+    forward-mode pass of the energy graph along v = w^2 (dE/dx - g_label) followed by an ordinary back-pass, instead of
+    differentiating the force back-pass.  Equal to the pinned double-backward gradients of train_op."""
+    g = load_golden("ref_train_pins")
+    P = og.default_params()
+    o = og.Oracle(TRAIN_PIN_ELES, train_pin_weights(), P)
+    b = {n: g["train0_" + n] for n in ("xyzs", "Zs", "Elabels", "Dlabels", "grads", "inv_natom")}
+    natom = np.rint(1.0 / b["inv_natom"]).astype(np.int64)
+    t = o.total_loss_gradient_by_tangent_pass(b["xyzs"], b["Zs"], natom, b["Elabels"], b["Dlabels"], b["grads"])
+    for net, op in (("charge", "all_charge"), ("energy", "all_energy")):
+        for z in TRAIN_PIN_ELES:
+            for l, (gW, gb) in enumerate(t[net][z]):
+                rW, rb = g["tq_train0_ecc1_g_%s_%d_%d_W" % (op, z, l)], g["tq_train0_ecc1_g_%s_%d_%d_b" % (op, z, l)]
+                assert np.abs(gW - rW).max() <= 1e-10 * max(np.abs(rW).max(), 1e-6), (net, z, l)
+                assert np.abs(gb - rb).max() <= 1e-10 * max(np.abs(rb).max(), 1e-6), (net, z, l)
