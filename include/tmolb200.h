@@ -48,7 +48,9 @@ enum {
 enum { TM_NET_CHARGE = 0, TM_NET_ENERGY = 1 };
 
 /* activation ids: TFInstance.py:108-140 AssignActivation */
-enum { TM_ACT_SIGMOID_WITH_PARAM = 0, TM_ACT_RELU = 1, TM_ACT_SOFTPLUS = 2, TM_ACT_TANH = 3, TM_ACT_SIGMOID = 4 };
+enum { TM_ACT_SIGMOID_WITH_PARAM = 0, TM_ACT_RELU = 1, TM_ACT_SOFTPLUS = 2, TM_ACT_TANH = 3, TM_ACT_SIGMOID = 4,
+       TM_ACT_ELU = 5, TM_ACT_SELU = 6 };   /* PARAMS["NeuronType"] of TFInstance.AssignActivation (TFInstance.py:108-140); the
+                                                 gaussian / square variants are not monotonic or not released and are refused */
 
 /* GEMM arithmetic of the per-element MLPs */
 enum {

@@ -109,6 +109,8 @@ def activation(x, P):
         return torch.sigmoid(x)
     if kind == "elu":
         return torch.nn.functional.elu(x)
+    if kind == "selu":                       # TFInstance.py:365-369: scale * where(x >= 0, x, alpha * elu(x))
+        return 1.0507009873554804934193349852946 * torch.where(x >= 0, x, 1.6732632423543772848170429916717 * torch.nn.functional.elu(x))
     raise ValueError(kind)
 
 

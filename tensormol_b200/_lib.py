@@ -12,7 +12,7 @@ TM_MAX_ELE = 8
 TM_MAX_HIDDEN = 4
 
 TM_NET_CHARGE, TM_NET_ENERGY = 0, 1
-TM_ACT = {"sigmoid_with_param": 0, "relu": 1, "softplus": 2, "tanh": 3, "sigmoid": 4}
+TM_ACT = {"sigmoid_with_param": 0, "relu": 1, "softplus": 2, "tanh": 3, "sigmoid": 4, "elu": 5, "selu": 6}
 TM_GEMM_FP32, TM_GEMM_TC_SPLIT, TM_GEMM_TC_SPLIT_PAIR, TM_GEMM_TC_SPLIT_N64, TM_GEMM_TC_SPLIT_N128 = 0, 1, 2, 3, 4
 TM_GEMM_TC_3XTF32 = TM_GEMM_TC_SPLIT   # name of the same mode before the fp16 split replaced the tf32 split
 TM_F_FORCE, TM_F_VDW, TM_F_DESCRIPTORS, TM_F_FOLD_IMAGES = 1, 2, 4, 8

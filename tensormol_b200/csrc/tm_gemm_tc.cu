@@ -218,6 +218,8 @@ __device__ __forceinline__ float tc_act_fwd(float z, float b, int kind, float al
     case TM_ACT_RELU: return fmaxf(z + b, 0.f);
     case TM_ACT_SOFTPLUS: return fmaxf(z + b, 0.f) + log1pf(expf(-fabsf(z + b)));
     case TM_ACT_TANH: return tanhf(z + b);
+    case TM_ACT_ELU: { float x = z + b; return x > 0.f ? x : expm1f(x); }
+    case TM_ACT_SELU: { float x = z + b; return x >= 0.f ? TM_SELU_SCALE * x : TM_SELU_SCALE * TM_SELU_ALPHA * expm1f(x); }
     default: return 1.0f / (1.0f + expf(-(z + b)));
   }
 }
@@ -227,6 +229,8 @@ __device__ __forceinline__ float tc_act_bwd(float h, int kind, float alpha) {
     case TM_ACT_RELU: return h > 0.f ? 1.f : 0.f;
     case TM_ACT_SOFTPLUS: return -expm1f(-h);
     case TM_ACT_TANH: return 1.0f - h * h;
+    case TM_ACT_ELU: return h > 0.f ? 1.f : h + 1.0f;                                        // e^x = h + 1 for x <= 0
+    case TM_ACT_SELU: return h >= 0.f ? TM_SELU_SCALE : h + TM_SELU_SCALE * TM_SELU_ALPHA;   // scale alpha e^x = h + scale alpha
     default: return h * (1.0f - h);
   }
 }

@@ -10,6 +10,9 @@
 #define TM_ANG_CAP 64            // angular neighbours per centre held in shared memory
 #define TM_NB_STRIDE 256         // radial neighbour slots per centre row (liquid water: 48 max)
 #define TM_MAX_ELEP (TM_MAX_ELE * (TM_MAX_ELE + 1) / 2)
+// selu constants of the reference (TFInstance.py:365-369)
+#define TM_SELU_ALPHA 1.6732632423543772848170429916717f
+#define TM_SELU_SCALE 1.0507009873554804934193349852946f
 #define TM_MAX_SYM 16            // max num_a_As / num_a_Rs
 #define TM_BOHRPERA 1.889725989  // PhysicalData.py:30
 

@@ -29,6 +29,8 @@ __device__ __forceinline__ float act_fwd(float z, int kind, float alpha) {
     case TM_ACT_RELU: return fmaxf(z, 0.f);
     case TM_ACT_SOFTPLUS: return fmaxf(z, 0.f) + log1pf(expf(-fabsf(z)));
     case TM_ACT_TANH: return tanhf(z);
+    case TM_ACT_ELU: return z > 0.f ? z : expm1f(z);
+    case TM_ACT_SELU: return z >= 0.f ? TM_SELU_SCALE * z : TM_SELU_SCALE * TM_SELU_ALPHA * expm1f(z);
     default: return 1.0f / (1.0f + expf(-z));
   }
 }
@@ -39,6 +41,8 @@ __device__ __forceinline__ float act_bwd_from_h(float h, int kind, float alpha) 
     case TM_ACT_RELU: return h > 0.f ? 1.f : 0.f;
     case TM_ACT_SOFTPLUS: return -expm1f(-h);
     case TM_ACT_TANH: return 1.0f - h * h;
+    case TM_ACT_ELU: return h > 0.f ? 1.f : h + 1.0f;
+    case TM_ACT_SELU: return h >= 0.f ? TM_SELU_SCALE : h + TM_SELU_SCALE * TM_SELU_ALPHA;
     default: return h * (1.0f - h);
   }
 }

@@ -511,3 +511,14 @@ def test_tangent_pass_weight_gradient_equals_double_backward():
                 rW, rb = g["tq_train0_ecc1_g_%s_%d_%d_W" % (op, z, l)], g["tq_train0_ecc1_g_%s_%d_%d_b" % (op, z, l)]
                 assert np.abs(gW - rW).max() <= 1e-10 * max(np.abs(rW).max(), 1e-6), (net, z, l)
                 assert np.abs(gb - rb).max() <= 1e-10 * max(np.abs(rb).max(), 1e-6), (net, z, l)
+
+
+def test_oracle_elu_and_selu_formulas():
+    """tf.nn.elu and TFInstance.selu (TFInstance.py:365-369) written out."""
+    x = torch.tensor([-3.0, -0.5, 0.0, 0.25, 2.0], dtype=torch.float64)
+    P = og.default_params()
+    P["NeuronType"] = "elu"
+    assert torch.allclose(og.activation(x, P), torch.where(x > 0, x, torch.exp(x) - 1), rtol=1e-15, atol=0)
+    P["NeuronType"] = "selu"
+    a, s = 1.6732632423543772848170429916717, 1.0507009873554804934193349852946
+    assert torch.allclose(og.activation(x, P), s * torch.where(x >= 0, x, a * (torch.exp(x) - 1)), rtol=1e-15, atol=1e-300)

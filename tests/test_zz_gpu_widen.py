@@ -129,3 +129,35 @@ def test_batch_losses_and_test_steps_equal_reference_graph():
             assert abs(got - want) <= 1e-4 * abs(want), (key, got, want)
     finally:
         PARAMS["batch_size"] = old
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("kind", ["relu", "softplus", "tanh", "sigmoid", "elu", "selu"])
+def test_other_neuron_types_against_oracle(kind, mode):
+    """PARAMS["NeuronType"] other than the released nets' sigmoid_with_param (TFInstance.AssignActivation, TFInstance.py:108-140;
+    SURVEY 8a a15): energy, charges and forces of the H2O cluster against the float64 oracle at the north-star tolerances, both
+    GEMM paths.  (The back-pass forms a'(z) from the stored activation, which is why only the monotonic options are offered.)"""
+    from oracle import oracle_graph as og
+    from test_gpu_parity import _check_energy, _check_grad, _engine
+    g = load_golden("h2o_cluster")
+    eng, W, P = _engine(g["eles"], [64, 48, 32], 3, gemm_mode=mode, params={"NeuronType": kind})
+    X, Z = g["xyz"][None], g["Z"][None].astype(np.int32)
+    natom = np.array([Z.shape[1]])
+    r = eng.evaluate(X, Z, natom)
+    o = og.Oracle(g["eles"], W, P).evaluate(X, Z, natom)
+    # signed activations let the atomic energies cancel in the sum: the 1e-5 is taken relative to sum |E_atom| (the conditioning
+    # scale of Etotal) where that is larger than |Etotal|
+    scale = max(abs(o["Etotal"][0]), np.abs(o["Ebp_atom"]).sum())
+    assert abs(r["Etotal"][0] - o["Etotal"][0]) <= 1e-5 * scale, (kind, r["Etotal"], o["Etotal"])
+    _check_energy(r["Ecc"], o["Ecc"], kind + " Ecc")
+    assert np.abs(r["charge"] - o["charge"]).max() <= 1e-5 * max(np.abs(o["charge"]).max(), 1e-3)
+    _check_grad(r["gradient"], o["gradient"])
+
+
+def test_unknown_neuron_type_is_refused():
+    from oracle import oracle_graph as og
+    from tensormol_b200.engine import Engine
+    P = og.default_params()
+    P["NeuronType"] = "gaussian"
+    with pytest.raises(ValueError, match="not supported"):
+        Engine([1, 8], [8], P)
