@@ -79,3 +79,11 @@ def test_c_oracle_matches_numpy_oracle():
         o_off, o_idx = onp.nlist_csr(x, rc, nreal, perms)
         assert np.array_equal(off, o_off) and np.array_equal(idx, o_idx)
         lib.tm_oracle_free(p)
+
+
+def test_neuron_type_ids_match_header_enum():
+    """The Python mirror's NeuronType -> id table equals the TM_ACT_* enum of include/tmolb200.h."""
+    from tensormol_b200 import _lib
+    src = open(os.path.join(ROOT, "include", "tmolb200.h")).read()
+    ids = {m.group(1).lower(): int(m.group(2)) for m in re.finditer(r"TM_ACT_([A-Z_]+)\s*=\s*(\d+)", src)}
+    assert ids == _lib.TM_ACT and len(ids) == 7
