@@ -87,3 +87,12 @@ def test_neuron_type_ids_match_header_enum():
     src = open(os.path.join(ROOT, "include", "tmolb200.h")).read()
     ids = {m.group(1).lower(): int(m.group(2)) for m in re.finditer(r"TM_ACT_([A-Z_]+)\s*=\s*(\d+)", src)}
     assert ids == _lib.TM_ACT and len(ids) == 7
+
+
+def test_unknown_neuron_type_is_refused():
+    from oracle import oracle_graph as og
+    from tensormol_b200.engine import Engine
+    P = og.default_params()
+    P["NeuronType"] = "gaussian"
+    with pytest.raises(ValueError, match="not supported"):
+        Engine([1, 8], [8], P)

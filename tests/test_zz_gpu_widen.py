@@ -154,15 +154,6 @@ def test_other_neuron_types_against_oracle(kind, mode):
     _check_grad(r["gradient"], o["gradient"])
 
 
-def test_unknown_neuron_type_is_refused():
-    from oracle import oracle_graph as og
-    from tensormol_b200.engine import Engine
-    P = og.default_params()
-    P["NeuronType"] = "gaussian"
-    with pytest.raises(ValueError, match="not supported"):
-        Engine([1, 8], [8], P)
-
-
 def test_batch_shards_on_the_engine_equal_the_whole_batch():
     """parallel.BatchShardEvaluator's blocks evaluated one after another on ONE GPU (emulated ranks, no process group) and
     stitched together equal the unsharded tm_eval call member by member (molecules are independent units; fp32 sums inside a
