@@ -49,6 +49,13 @@ class TMParams(dict):
         self["momentum"] = 0.9
         self["max_steps"] = 1001
         self["test_freq"] = 10
+        # read by other network families of the reference; kept so that scripts which touch them run (TMParams.py:67-95)
+        self["hidden1"], self["hidden2"], self["hidden3"] = 512, 512, 512
+        self["GradWeight"] = 0.01
+        self["weight_decay"] = 0.001
+        self["InNormRoutine"], self["OutNormRoutine"] = None, None
+        self["RandomizeData"] = True
+        self["train_gradients"], self["train_dipole"], self["train_quadrupole"], self["train_rotation"] = True, True, False, True
         # optimisation
         self["OptMaxCycles"] = 50
         self["OptThresh"] = 0.0001
