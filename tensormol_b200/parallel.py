@@ -245,3 +245,27 @@ class BatchShardEvaluator:
         rows = np.concatenate([recv[k, :int(b[k + 1] - b[k])] for k in range(self.world)], axis=0)
         assert rows.shape[0] == nmol
         return self._unpack(rows, maxn)
+
+
+def sharded_batch_losses(backend, batch_data, rank, world, dist=None, device="cpu", EnergyScalar=1.0, GradScalar=1.0 / 20.0, DipoleScalar=1.0):
+    """The reference's minibatch losses (BPInstance.batch_losses, TFMolInstanceDirect.py:4860-4901) with the molecules of the
+    batch sharded over the ranks: each rank evaluates its block (BatchShardEvaluator.evaluate_local, one tm_eval), forms its
+    partial sums of the three squared-residual losses in float64, and ONE all-reduce of three scalars completes them --
+    the training-style, batch-sharded form of config C2.  batch_data as TData.GetTrainBatch / GetTestBatch return it
+    (WithGrad_=True).  Returns the same six losses on every rank."""
+    xyzs, Zs, Elabels, Dlabels, grads = batch_data[:5]
+    inv_natom = np.asarray(batch_data[9], np.float64)
+    natom = np.rint(1.0 / inv_natom).astype(np.int64)
+    lo, hi, r = BatchShardEvaluator(backend, rank, world).evaluate_local(xyzs, Zs, natom)
+    w = float(np.asarray(Zs).shape[1]) * inv_natom[lo:hi]
+    part = np.array([0.5 * np.sum(((np.asarray(r["Etotal"]) - Elabels[lo:hi]) * w) ** 2),
+                     0.5 * np.sum(((np.asarray(r["gradient"]) - grads[lo:hi]) * w[:, None, None]) ** 2),
+                     0.5 * np.sum(((np.asarray(r["dipole"]) - Dlabels[lo:hi]) * w[:, None]) ** 2)])
+    if world > 1 and dist is not None:
+        import torch
+        t = torch.from_numpy(part).to(device)
+        dist.all_reduce(t)
+        part = t.cpu().numpy()
+    e_loss, g_loss, d_loss = (float(v) for v in part)
+    loss_eg = e_loss * EnergyScalar + g_loss * GradScalar
+    return dict(loss=loss_eg + d_loss * DipoleScalar, loss_dipole=d_loss, loss_EandG=loss_eg, energy_loss=e_loss, grads_loss=g_loss, dipole_loss=d_loss)

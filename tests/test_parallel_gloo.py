@@ -147,6 +147,13 @@ def _ragged_batch(nmol, seed=3):
     return xyzs, Zs, natom
 
 
+def _labelled_batch(xyzs, Zs, natom):
+    """GetTrainBatch's layout with seeded labels (the four index tables are not read by the loss code)."""
+    rng = np.random.default_rng(9)
+    n = len(natom)
+    return [xyzs, Zs, rng.normal(size=n), rng.normal(size=(n, 3)), rng.normal(size=xyzs.shape), None, None, None, None, 1.0 / natom]
+
+
 def test_batch_shard_bounds_cover_and_balance():
     for nmol in (0, 1, 2, 7, 100):
         natom = np.random.default_rng(nmol).integers(1, 50, nmol)
@@ -170,7 +177,9 @@ def _batch_worker(rank, world, port, q, nmol):
     lo, hi, loc = ev.evaluate_local(xyzs, Zs, natom)
     s = torch.tensor([loc["Etotal"].sum()])
     dist.all_reduce(s)
-    q.put((rank, r, float(s[0]), (lo, hi)))
+    from tensormol_b200.parallel import sharded_batch_losses
+    L = sharded_batch_losses(MoleculeBackend(), _labelled_batch(xyzs, Zs, natom), rank, world, dist)
+    q.put((rank, r, float(s[0]), (lo, hi), L))
     dist.destroy_process_group()
 
 
@@ -192,7 +201,13 @@ def test_two_rank_gloo_batch_shards_equal_whole_batch(nmol):
     whole = MoleculeBackend().evaluate(xyzs, Zs, natom)
     blocks = sorted(g[3] for g in got)
     assert blocks[0][0] == 0 and blocks[0][1] == blocks[1][0] and blocks[1][1] == nmol
-    for rank, r, esum, _ in got:
+    from tensormol_b200.parallel import sharded_batch_losses
+    L1 = sharded_batch_losses(MoleculeBackend(), _labelled_batch(xyzs, Zs, natom), 0, 1)
+    w = xyzs.shape[1] / natom
+    assert L1["energy_loss"] == pytest.approx(0.5 * np.sum(((whole["Etotal"] - _labelled_batch(xyzs, Zs, natom)[2]) * w) ** 2), rel=1e-13)
+    for rank, r, esum, _, L in got:
         for k in BatchShardEvaluator.KEYS:
             assert np.array_equal(r[k], whole[k]), (rank, k)
         assert esum == pytest.approx(whole["Etotal"].sum(), rel=1e-13)
+        for k in L1:
+            assert L[k] == pytest.approx(L1[k], rel=1e-12), (rank, k)     # the sharded sums equal the single-rank losses

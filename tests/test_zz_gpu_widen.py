@@ -118,6 +118,12 @@ def test_batch_losses_and_test_steps_equal_reference_graph():
     check(I.batch_losses(t.GetTestBatch(2), False), "tq_test0_ecc0_")
     check(I.batch_losses(t.GetTestBatch(2), True), "tq_test1_ecc1_")
     assert PARAMS["AddEcc"] is True
+    # the sharded form on one rank is the same arithmetic (tensormol_b200.parallel.sharded_batch_losses)
+    from tensormol_b200.parallel import sharded_batch_losses
+    b = t.GetTrainBatch(3)
+    one, sh = I.batch_losses(b, True), sharded_batch_losses(I.engine, b, 0, 1, GradScalar=PARAMS["GradScalar"])
+    for k in sh:
+        assert abs(one[k] - sh[k]) <= 1e-5 * abs(one[k]), k
     # whole test steps: two test batches of two molecules (NTest = 4), pointer back at the first test case
     old = PARAMS["batch_size"]
     PARAMS["batch_size"] = 2
