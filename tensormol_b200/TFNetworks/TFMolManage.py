@@ -96,6 +96,7 @@ class BPInstance:
             r = self.engine.evaluate(xyzs, Zs, natom, do_force=True, has_vdw=True)
         finally:
             PARAMS["AddEcc"] = old
+            self.refresh()                      # the engine follows PARAMS again (a no-op when nothing changed)
         w = float(np.asarray(Zs).shape[1]) * inv_natom
         e_loss = 0.5 * np.sum(((r["Etotal"] - Elabels) * w) ** 2)
         g_loss = 0.5 * np.sum(((r["gradient"] - grads) * w[:, None, None]) ** 2)
