@@ -421,6 +421,18 @@ class Oracle:
         it = iter(torch.zeros_like(t) if a is None else a for a, t in zip(gs, flat))
         return {net: {z: [(next(it).numpy(), next(it).numpy()) for _ in live[net][z]] for z in self.eles} for net in ("charge", "energy")}
 
+    def tangent_stage_quantities(self, xyzs, Zs, natom, v):
+        """Stage outputs of the tangent pass along the coordinate direction v (same shape as xyzs), as parity targets for the
+        device kernels of the training step: descriptor tangents dG = (dG/dx) v, tangents of the atomic charges and atomic
+        energies, and dE = <v, dE/dx> per molecule."""
+        import torch.autograd.forward_ad as fwAD
+        with torch.no_grad(), fwAD.dual_level():
+            R = fwAD.make_dual(torch.tensor(np.ascontiguousarray(xyzs, np.float64)), torch.as_tensor(np.ascontiguousarray(v, np.float64)))
+            g = self._graph(xyzs, Zs, natom, R=R)
+            t = lambda k: fwAD.unpack_dual(g[k]).tangent                     # noqa: E731
+            return dict(dG=t("GM").numpy().copy(), dq=t("q").numpy().copy(), dEbp_atom=t("Ebp_atom").numpy().copy(),
+                        dEcc=t("Ecc").numpy().copy(), dEvdw=t("Evdw").numpy().copy(), dEtotal=t("Etotal").numpy().copy())
+
     def train_step(self, op, state, xyzs, Zs, natom, Elabels, Dlabels, grads, learning_rate, **scalars):
         """One minibatch of train_op ("all"), train_op_dipole ("dipole") or train_op_EandG ("EandG"): the gradients of
         train_quantities applied by Adam to that op's variable list (TMD:2626-2646: tf.train.AdamOptimizer(learning_rate) with

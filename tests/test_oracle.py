@@ -522,3 +522,24 @@ def test_oracle_elu_and_selu_formulas():
     P["NeuronType"] = "selu"
     a, s = 1.6732632423543772848170429916717, 1.0507009873554804934193349852946
     assert torch.allclose(og.activation(x, P), s * torch.where(x >= 0, x, a * (torch.exp(x) - 1)), rtol=1e-15, atol=1e-300)
+
+
+def test_tangent_stage_quantities_are_directional_derivatives():
+    """The per-stage tangents the device training kernels will be checked against: dEtotal equals <v, dE/dx> of the pinned
+    gradient, and dG / dq equal central differences of the descriptors / charges along v."""
+    g = load_golden("ref_train_pins")
+    P = og.default_params()
+    o = og.Oracle(TRAIN_PIN_ELES, train_pin_weights(), P)
+    b = {n: g["train0_" + n] for n in ("xyzs", "Zs", "inv_natom")}
+    natom = np.rint(1.0 / b["inv_natom"]).astype(np.int64)
+    mask = (np.arange(b["Zs"].shape[1])[None, :] < natom[:, None])[:, :, None]
+    v = np.random.default_rng(0).normal(size=b["xyzs"].shape) * mask
+    t = o.tangent_stage_quantities(b["xyzs"], b["Zs"], natom, v)
+    want = (g["tq_train0_ecc1_gradient"] * v).sum((1, 2))
+    assert np.abs(t["dEtotal"] - want).max() <= 1e-12 * np.abs(want).max()
+    assert np.abs(t["dEtotal"] - (t["dEbp_atom"].sum(1) + t["dEcc"] + t["dEvdw"])).max() <= 1e-14
+    h = 1e-6
+    p, m = (o.evaluate(b["xyzs"] + s * h * v, b["Zs"], natom) for s in (1, -1))
+    for key, ref in (("dG", "descriptors"), ("dq", "charge")):
+        fd = (p[ref] - m[ref]) / (2 * h)
+        assert np.abs(t[key] - fd).max() <= 1e-7 * max(np.abs(fd).max(), 1e-3), key
