@@ -3,7 +3,7 @@ step, on-device integrator (DevicePeriodicVelocityVerlet) vs the host driver.  P
 import sys, time
 import numpy as np
 sys.path.insert(0, '.'); sys.path.insert(0, 'tests')
-from test_gpu_api import _manager
+from test_c_gpu_api import _manager
 from tensormol_b200 import PARAMS, Mol, PeriodicForce, PeriodicVelocityVerlet
 from tensormol_b200.PhysicalData import JOULEPERHARTREE
 from tensormol_b200.Simulations.DeviceMD import DevicePeriodicVelocityVerlet

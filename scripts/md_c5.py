@@ -8,7 +8,7 @@ os.environ.setdefault("TM_NO_GRAPH", "1")   # stage timings need the kernel-by-k
 import numpy as np
 sys.path.insert(0, '.'); sys.path.insert(0, 'tests')
 from conftest import load_golden
-from test_gpu_api import _manager
+from test_c_gpu_api import _manager
 from tensormol_b200 import PARAMS, Mol
 from tensormol_b200.PhysicalData import IDEALGASR
 from tensormol_b200.Simulations.DeviceMD import DevicePeriodicVelocityVerlet

@@ -6,7 +6,8 @@ descriptors within 1e-5 relative; energies within 1e-5 relative; forces within 1
 import numpy as np
 
 BOHRPERA = 1.889725989
-DESC_RTOL = 1e-5          # relative to the largest descriptor entry of the system (row scale)
+DESC_RTOL = 1e-5          # per entry
+DESC_ABS_FLOOR_ULPS = 4.0  # + this many fp32 ulps of the row's largest entry (absolute floor)
 ENERGY_RTOL = 1e-5
 FORCE_ATOL_HA_BOHR = 1e-4
 

@@ -76,7 +76,7 @@ def test_manager_weights_save_load_round_trip(tmp_path):
     manager2, _ = _manager([m], [32, 16], 99)
     manager2.LoadWeights(p)
     e2 = manager2.EvalBPDirectEEUpdateSingle(m, PARAMS["AN1_r_Rc"], PARAMS["AN1_a_Rc"], PARAMS["EECutoffOff"], True)[0][0]
-    assert e1 == e2
+    assert abs(e1 - e2) <= 1e-9 * abs(e1)        # same weights; reductions use atomics, so not bit-equal by contract
 
 
 def test_manager_restores_a_reference_style_network_by_name(tmp_path):
@@ -109,7 +109,9 @@ def test_manager_restores_a_reference_style_network_by_name(tmp_path):
                                                   num_indis_=1, type_="mol", WithGrad_=True)
         manager2 = TFMolManage("water_network", tset, False, NET, False, False)
         out = manager2.EvalBPDirectEEUpdateSingle(*args)
-        assert out[0][0] == e1 and np.array_equal(out[7], f1)
+        # same weights through the checkpoint: equal up to the summation order of the atomically reduced forces
+        assert abs(out[0][0] - e1) <= 1e-9 * abs(e1)
+        assert np.abs(out[7] - f1).max() <= 1e-5 * np.abs(f1).max()
         PARAMS["HiddenLayers"] = [32, 16, 25]      # a network of another shape is refused, not silently mis-read
         with pytest.raises(Exception, match="HiddenLayers"):
             TFMolManage("water_network", tset, False, NET, False, False)
@@ -253,7 +255,7 @@ def test_device_md_matches_host_driver(thermostat, graph):
     assert np.abs(d).max() < 1e-7
     assert np.abs(dev.v - host.v).max() < 1e-7 * max(1.0, np.abs(host.v).max() / 1e-3)
     assert abs(dev.EPot - host.EPot) < 1e-6 * abs(host.EPot)
-    assert np.all(np.isfinite(log)) and log[nstep - 1, 5] == dev.EPot
+    assert np.all(np.isfinite(log)) and abs(log[nstep - 1, 5] - dev.EPot) <= 1e-9 * abs(dev.EPot)
 
 
 def test_geometry_optimizer_lowers_energy_on_gpu_potential():

@@ -1,5 +1,5 @@
 """GPU tests of the widening rows added after the round's GPU budget was spent: they were written
-against paths that ARE covered on the GPU elsewhere (the molecule-batch call of tests/test_gpu_parity.py), but were
+against paths that ARE covered on the GPU elsewhere (the molecule-batch call of tests/test_a_gpu_parity.py), but were
 themselves never run on a B200 before the round end -- hence a file that sorts last, so that under `-x` a surprise
 here cannot hide the results of the established parity tests."""
 import numpy as np
@@ -20,7 +20,7 @@ def _tmp_results(tmp_path):
 
 
 def _manager_and_mol():
-    from test_gpu_api import _manager
+    from test_c_gpu_api import _manager
     from tensormol_b200 import Mol
     g = load_golden("h2o_cluster")
     m = Mol(g["Z"].astype(np.uint8), g["xyz"])
@@ -92,7 +92,7 @@ def test_batch_losses_and_test_steps_equal_reference_graph():
     tolerances (energy 1e-5 relative, force 1e-4 Hartree/Bohr) map to 1e-4 relative on energy_loss / dipole_loss and 1e-3
     relative on grads_loss."""
     import random
-    from test_gpu_api import NET, _setup_params
+    from test_c_gpu_api import NET, _setup_params
     from test_host_api import train_pin_set
     from test_oracle import TRAIN_PIN_ELES, TRAIN_PIN_HIDDEN, _train_quantities, train_pin_weights
     from tensormol_b200 import PARAMS, TFMolManage
@@ -144,7 +144,7 @@ def test_other_neuron_types_against_oracle(kind, mode):
     SURVEY 8a a15): energy, charges and forces of the H2O cluster against the float64 oracle at the north-star tolerances, both
     GEMM paths.  (The back-pass forms a'(z) from the stored activation, which is why only the monotonic options are offered.)"""
     from oracle import oracle_graph as og
-    from test_gpu_parity import _check_energy, _check_grad, _engine
+    from test_a_gpu_parity import _check_energy, _check_grad, _engine
     g = load_golden("h2o_cluster")
     eng, W, P = _engine(g["eles"], [64, 48, 32], 3, gemm_mode=mode, params={"NeuronType": kind})
     X, Z = g["xyz"][None], g["Z"][None].astype(np.int32)
@@ -164,7 +164,7 @@ def test_batch_shards_on_the_engine_equal_the_whole_batch():
     """parallel.BatchShardEvaluator's blocks evaluated one after another on ONE GPU (emulated ranks, no process group) and
     stitched together equal the unsharded tm_eval call member by member (molecules are independent units; fp32 sums inside a
     molecule do not depend on its neighbours in the batch: 1e-6 relative on energies, 1e-6 Ha/A on gradients)."""
-    from test_gpu_parity import _engine
+    from test_a_gpu_parity import _engine
     from tensormol_b200.parallel import BatchShardEvaluator, batch_shard_bounds
     g = load_golden("h2o_cluster")
     eng, W, P = _engine(g["eles"], [32, 32], 5)
