@@ -447,6 +447,10 @@ static SysView make_view(tm_ctx* c, int64_t nslots, int64_t nmol, int64_t maxnat
   s.win_ntess = 0; s.win_ilo = -1000; s.win_ihi = 1000;
   s.grid_host = 0;
   memset(&s.hgrid, 0, sizeof(s.hgrid));
+  s.lat_bin = 0; s.lat_ntess = 0; s.xyz_real = nullptr; s.Z_real = nullptr;
+  memset(&s.lat, 0, sizeof(s.lat));
+  for (int d = 0; d < 9; d++) s.ginv[d] = 0.0;
+  for (int d = 0; d < 3; d++) { s.wlo[d] = 0.0; s.whi[d] = 0.0; }
   return s;
 }
 
@@ -478,10 +482,15 @@ static int stage_a(tm_ctx* c, const SysView& s) {
   TM_CUDA(cudaMemsetAsync(c->b_F.p, 0, (size_t)nq * 3 * 4, c->stream));
   cudaEventRecord(c->ev[1], c->stream);
   tm_trace(c, "inputs");
-  if ((rc = tm_launch_nlist_build(c, s, c->params.r_Rc))) return rc;
-  tm_trace(c, "cell list");
-  if ((rc = tm_launch_rows(c, s))) return rc;
-  tm_trace(c, "rows");
+  if (s.lat_bin) {
+    if ((rc = tm_launch_lattice_bin(c, s))) return rc;
+    tm_trace(c, "windowed lattice binning + rows");
+  } else {
+    if ((rc = tm_launch_nlist_build(c, s, c->params.r_Rc))) return rc;
+    tm_trace(c, "cell list");
+    if ((rc = tm_launch_rows(c, s))) return rc;
+    tm_trace(c, "rows");
+  }
   if ((rc = tm_launch_neighbours(c, s))) return rc;
   tm_trace(c, "neighbour rows");
   cudaEventRecord(c->ev[2], c->stream);
@@ -558,6 +567,7 @@ static int check_flags(tm_ctx* c) {
   if (f[0] & 32) { tm_set_error("slab exchange: a peer rank never signalled (timed out after ~8 s)"); return TM_ECUDA; }
   if (f[0] & 8) { tm_set_error("coordinates are not wrapped into the cell (apply Lattice.ModuloLattice before tm_eval_lattice)"); return TM_EINVAL; }
   if (f[0] & 4) { tm_set_error("more than %d neighbours inside the angular cutoff of one centre", TM_ANG_CAP); return TM_ECAP; }
+  if (f[0] & 64) { tm_set_error("a slab rank owns more centres than its row allocation (density far from uniform)"); return TM_ECAP; }
   return TM_OK;
 }
 
@@ -715,7 +725,7 @@ static int64_t tess_count(int64_t nreal, int ntess) {
 
 // device-side tessellation; xyz_dev / Z_dev are DEVICE pointers to the primitive cell
 
-static int prepare_lattice(tm_ctx* c, const double* xyz_dev, const int32_t* Z_dev, int64_t nreal, const double* lattice, int ntess, SysView* sv,
+static int prepare_lattice_full(tm_ctx* c, const double* xyz_dev, const int32_t* Z_dev, int64_t nreal, const double* lattice, int ntess, SysView* sv,
                            int ilo = -1000, int ihi = 1000) {
   int rc;
   if (ntess < 1 || ntess > 8) { tm_set_error("ntess must be 1..8"); return TM_EINVAL; }
@@ -744,12 +754,16 @@ static int prepare_lattice(tm_ctx* c, const double* xyz_dev, const int32_t* Z_de
 // host, so the cell grid is laid out here instead of by a bounding-box pass over the slots (same rules as
 // k_grid_params).  Atoms outside it (unwrapped input) raise flag 8 in k_cell_count.
 static void host_grid(tm_ctx* c, SysView* sv, const double* L, int ntess) {
-  double flo = -(double)ntess, fhi = (double)ntess + 1.0;
-  double alo = flo, ahi = fhi;
-  if (sv->window_on) { alo = std::max(alo, sv->win_lo); ahi = std::min(ahi, sv->win_hi); }
+  double flo[3], fhi[3];
+  for (int d = 0; d < 3; d++) { flo[d] = -(double)ntess; fhi[d] = (double)ntess + 1.0; }
+  if (sv->lat_bin) {
+    for (int d = 0; d < 3; d++) { flo[d] = std::max(flo[d], sv->wlo[d]); fhi[d] = std::min(fhi[d], sv->whi[d]); }
+  } else if (sv->window_on) {
+    flo[0] = std::max(flo[0], sv->win_lo); fhi[0] = std::min(fhi[0], sv->win_hi);
+  }
   double mn[3] = {1e300, 1e300, 1e300}, mx[3] = {-1e300, -1e300, -1e300};
   for (int k = 0; k < 8; k++) {
-    double fa = (k & 1) ? ahi : alo, fb = (k & 2) ? fhi : flo, fc = (k & 4) ? fhi : flo;
+    double fa = (k & 1) ? fhi[0] : flo[0], fb = (k & 2) ? fhi[1] : flo[1], fc = (k & 4) ? fhi[2] : flo[2];
     for (int d = 0; d < 3; d++) {
       double v = fa * L[d] + fb * L[3 + d] + fc * L[6 + d];
       mn[d] = std::min(mn[d], v);
@@ -776,6 +790,40 @@ static void host_grid(tm_ctx* c, SysView* sv, const double* L, int ntess) {
   sv->grid_host = 1;
 }
 
+// Lattice path, windowed binning (tm_launch_lattice_bin, tm_nlist.cu): nothing is tessellated here; the view carries the
+// lattice, its inverse and the fractional window per axis -- the cell (or this slab rank's share of it along the first
+// lattice vector) widened by the largest interaction range, measured in plane spacings -- plus the host-laid cell grid.
+static int prepare_lattice(tm_ctx* c, const double* xyz_dev, const int32_t* Z_dev, int64_t nreal, const double* lattice, int ntess, SysView* sv,
+                           int rank = 0, int world = 1) {
+  if (ntess < 1 || ntess > 8) { tm_set_error("ntess must be 1..8"); return TM_EINVAL; }
+  const double* L = lattice;
+  double det = L[0] * (L[4] * L[8] - L[5] * L[7]) - L[1] * (L[3] * L[8] - L[5] * L[6]) + L[2] * (L[3] * L[7] - L[4] * L[6]);
+  if (fabs(det) < 1e-12) { tm_set_error("singular lattice"); return TM_EINVAL; }
+  int64_t nslots = tess_count(nreal, ntess);
+  *sv = make_view(c, nslots, 1, nslots, nreal, 1, nreal);
+  double* gi = sv->ginv;   // inv(L), row-major: x = f L  =>  f_d = sum_r x_r inv[r][d]
+  gi[0] = (L[4] * L[8] - L[5] * L[7]) / det; gi[1] = -(L[1] * L[8] - L[2] * L[7]) / det; gi[2] = (L[1] * L[5] - L[2] * L[4]) / det;
+  gi[3] = -(L[3] * L[8] - L[5] * L[6]) / det; gi[4] = (L[0] * L[8] - L[2] * L[6]) / det; gi[5] = -(L[0] * L[5] - L[2] * L[3]) / det;
+  gi[6] = (L[3] * L[7] - L[4] * L[6]) / det; gi[7] = -(L[0] * L[7] - L[1] * L[6]) / det; gi[8] = (L[0] * L[4] - L[1] * L[3]) / det;
+  sv->slab_g[0] = gi[0]; sv->slab_g[1] = gi[3]; sv->slab_g[2] = gi[6];
+  const double range = std::max(c->params.ee_cutoff_off, c->params.r_Rc) + 0.05;
+  for (int d = 0; d < 3; d++) {
+    double gn = sqrt(gi[d] * gi[d] + gi[3 + d] * gi[3 + d] + gi[6 + d] * gi[6 + d]);   // 1 / plane spacing along axis d
+    double halo = range * gn + 1e-5;    // real atoms are accepted up to 1e-6 outside [0, 1)
+    sv->wlo[d] = -halo; sv->whi[d] = 1.0 + halo;
+    if (d == 0 && world > 1) {
+      sv->wlo[0] = (rank == 0) ? -halo - 1e-3 : (double)rank / world - halo;
+      sv->whi[0] = (rank == world - 1) ? 1.0 + halo + 1e-3 : (double)(rank + 1) / world + halo;
+    }
+  }
+  memcpy(sv->lat.v, lattice, 72);
+  sv->lat.v[9] = 1.0 / (double)nreal;
+  sv->lat_bin = 1; sv->lat_ntess = ntess;
+  sv->xyz_real = xyz_dev; sv->Z_real = Z_dev;
+  host_grid(c, sv, lattice, ntess);
+  return TM_OK;
+}
+
 static int eval_lattice_impl(tm_ctx* c, const double* xyz, const int32_t* Z, int64_t nreal, const double* lattice, int ntess, int flags,
                              tm_outputs* out, bool use_host_grid) {
   int rc;
@@ -790,8 +838,11 @@ static int eval_lattice_impl(tm_ctx* c, const double* xyz, const int32_t* Z, int
   cudaEventRecord(c->ev[0], c->stream);
   TM_CUDA(cudaMemcpyAsync(c->b_acc.p, hs, bx + bz, cudaMemcpyHostToDevice, c->stream));
   SysView s;
-  if ((rc = prepare_lattice(c, (const double*)c->b_acc.p, (const int32_t*)((char*)c->b_acc.p + bx), nreal, lattice, ntess, &s))) return rc;
-  if (use_host_grid) host_grid(c, &s, lattice, ntess);
+  // windowed binning needs coordinates wrapped into the cell; unwrapped input (device flag 8) is redone by the caller with
+  // use_host_grid = false: full tessellation (k_tessellate) and a bounding-box grid, as the reference does it
+  if (use_host_grid) rc = prepare_lattice(c, (const double*)c->b_acc.p, (const int32_t*)((char*)c->b_acc.p + bx), nreal, lattice, ntess, &s);
+  else rc = prepare_lattice_full(c, (const double*)c->b_acc.p, (const int32_t*)((char*)c->b_acc.p + bx), nreal, lattice, ntess, &s);
+  if (rc) return rc;
   OutLayout o = out_layout(1, nreal);
   if ((rc = run_all(c, s, flags, o))) return rc;
   rc = deliver(c, s, flags, o, out, nreal);   // charges of the real atoms only: the image blocks are copies
@@ -831,7 +882,7 @@ static int lattice_graph_call(tm_ctx* c, const double* xyz, const int32_t* Z, in
     SysView s;
     rc = (cudaMemcpyAsync(c->b_acc.p, hs, bx + bz, cudaMemcpyHostToDevice, c->stream) == cudaSuccess) ? TM_OK : TM_ECUDA;
     if (!rc) rc = prepare_lattice(c, (const double*)c->b_acc.p, (const int32_t*)((char*)c->b_acc.p + bx), nreal, lattice, ntess, &s);
-    if (!rc) { host_grid(c, &s, lattice, ntess); rc = run_all(c, s, flags, o); }
+    if (!rc) rc = run_all(c, s, flags, o);
     if (!rc && cudaMemcpyAsync(hs, c->b_out.p, bytes, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) rc = TM_ECUDA;
     if (!rc && cudaMemcpyAsync(hs + bytes, c->b_flags.p, 8, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) rc = TM_ECUDA;
     cudaError_t ce = cudaStreamEndCapture(c->stream, &graph);
@@ -902,7 +953,6 @@ extern "C" int tm_eval_lattice_dev(tm_ctx* c, const double* xyz_dev, const int32
   cudaEventRecord(c->ev[0], c->stream);
   SysView s;
   if ((rc = prepare_lattice(c, xyz_dev, Z_dev, nreal, lattice, ntess, &s))) return rc;
-  host_grid(c, &s, lattice, ntess);
   OutLayout o = out_layout(1, nreal);
   if ((rc = run_all(c, s, flags, o))) return rc;
   const double* out = (const double*)c->b_out.p;
@@ -1098,34 +1148,15 @@ extern "C" int tm_slab_phase_a(tm_ctx* c, const double* xyz_dev, const int32_t* 
   c->timings_final = false;
   cudaEventRecord(c->ev[0], c->stream);
   SysView s;
-  // the slab window along the first lattice vector: the owned slab plus the largest interaction range on both sides.
-  // Everything an owned centre can interact with lies inside; slots outside are not binned, and image blocks whose
-  // whole range [i, i+1) misses the window are not even tessellated (the input must be wrapped into the cell).
-  int ilo = -1000, ihi = 1000;
-  double win_lo = 0.0, win_hi = 0.0;
-  if (world > 1) {
-    const double* L = lattice;
-    double det = L[0] * (L[4] * L[8] - L[5] * L[7]) - L[1] * (L[3] * L[8] - L[5] * L[6]) + L[2] * (L[3] * L[7] - L[4] * L[6]);
-    if (fabs(det) < 1e-12) { tm_set_error("singular lattice"); return TM_EINVAL; }
-    double g0 = (L[4] * L[8] - L[5] * L[7]) / det, g1 = -(L[3] * L[8] - L[5] * L[6]) / det, g2 = (L[3] * L[7] - L[4] * L[6]) / det;
-    double gn = sqrt(g0 * g0 + g1 * g1 + g2 * g2);   // 1 / plane spacing
-    double halo = (std::max(c->params.ee_cutoff_off, c->params.r_Rc) + 0.05) * gn + 1e-6;
-    win_lo = (rank == 0) ? -halo - 1e-3 : (double)rank / world - halo;
-    win_hi = (rank == world - 1) ? 1.0 + halo + 1e-3 : (double)(rank + 1) / world + halo;
-    ilo = std::max(-ntess, (int)floor(win_lo - 1.0 - 1e-6) + 1);
-    ihi = std::min(ntess, (int)ceil(win_hi + 1e-6) - 1);
-  }
-  if ((rc = prepare_lattice(c, xyz_dev, Z_dev, nreal, lattice, ntess, &s, ilo, ihi))) return rc;
+  // the slab window along the first lattice vector (the owned slab plus the largest interaction range on both sides) is
+  // laid out by prepare_lattice; everything an owned centre can interact with lies inside, nothing else is binned
+  if ((rc = prepare_lattice(c, xyz_dev, Z_dev, nreal, lattice, ntess, &s, rank, world))) return rc;
   s.slab_rank = rank; s.slab_world = world; s.slab_api = 1;
-  // a slab holds ~nreal/world centres; keep head-room for density fluctuations without a host round trip
+  // a slab holds ~nreal/world centres; keep head-room for density fluctuations without a host round trip (device flag 64)
   if (world > 1) {
     s.ncent_max = std::min<int64_t>(nreal, nreal / world + nreal / (2 * world) + 4096);
     s.nrows = s.ncent_max + (int64_t)TM_ROW_TILE * c->hp.n_ele;
-    s.window_on = 1;
-    s.win_lo = win_lo; s.win_hi = win_hi;
-    s.win_ntess = ntess; s.win_ilo = ilo; s.win_ihi = ihi;
   }
-  host_grid(c, &s, lattice, ntess);
   c->slab_view = s;
   if ((rc = stage_a(c, s))) return rc;
   if ((rc = tm_launch_mlp_backward(c, s))) return rc;

@@ -126,6 +126,16 @@ struct SysView {
   // lattice path: the cell grid is laid out on the host from the lattice (no bounding-box pass); grid_host = 1
   int grid_host;
   GridParams hgrid;
+  // lattice path with windowed binning (tm_launch_lattice_bin): the images are never materialised as slots; every real
+  // atom enumerates the lattice shifts that put it inside the fractional-coordinate window [wlo, whi] per axis (cell +
+  // interaction halo, or a slab rank's share of it) and bins those, with the reference's slot ids and image arithmetic.
+  int lat_bin;
+  LatArgs lat;            // lattice rows + 1/natom
+  double ginv[9];         // inverse lattice: frac_d = x ginv[d] + y ginv[3+d] + z ginv[6+d]
+  double wlo[3], whi[3];
+  int lat_ntess;
+  const double* xyz_real;
+  const int32_t* Z_real;
 };
 
 struct tm_ctx {
@@ -146,6 +156,7 @@ struct tm_ctx {
   // ---- per-evaluation workspace (grow-only) ----
   DevBuf b_pos, b_Z, b_cellid, b_rank, b_count, b_cstart, b_sorted, b_satom, b_scan_tmp;
   DevBuf b_rowslot, b_rowsidx, b_rowofslot, b_blkcnt, b_rowmeta;
+  DevBuf b_cntall, b_offall;
   DevBuf b_nbcnt, b_nboff, b_nbr, b_G, b_Gs, b_ypart, b_act[2][TM_MAX_HIDDEN], b_delta0, b_delta1, b_dG[2], b_y[2];
   DevBuf b_q, b_qs, b_dedq, b_F, b_acc, b_bbox, b_grid, b_flags, b_out, b_molacc;
   DevBuf b_natom;
@@ -207,6 +218,7 @@ int tm_host_stage(tm_ctx* c, size_t bytes);
 int tm_launch_tessellate(tm_ctx* c, const double* xyz_real, const int32_t* Z_real, int64_t nreal, const LatArgs& lattice, int ntess, int ilo, int ihi);
 int tm_launch_nlist_build(tm_ctx* c, const SysView& s, double rc_grid);
 int tm_launch_rows(tm_ctx* c, const SysView& s);
+int tm_launch_lattice_bin(tm_ctx* c, const SysView& s);   // windowed binning + cell sort + centre rows of the lattice path
 int tm_launch_neighbours(tm_ctx* c, const SysView& s);
 int tm_launch_desc(tm_ctx* c, const SysView& s);
 void tm_trace(tm_ctx* c, const char* what);   // TM_TRACE=1: synchronise + name the stage on stderr (tm_api.cu)

@@ -824,3 +824,300 @@ int tm_launch_nlist_csr(tm_ctx* c, const SysView& s, double rc, int do_perms, in
   for (int64_t t = 0; t < total; t++) c->h_idx[t] = hi[t];
   return TM_OK;
 }
+
+// ================================================================ lattice path: windowed binning
+// Periodic systems given as cell + lattice (tm_eval_lattice*, the slab phases).  The reference tessellates every atom
+// into (2 ntess + 1)^3 images (Periodic.py:131-168: 648,000 positions for the 24,000-atom box) and lets the neighbour
+// search sort out which of them matter.  Here only what can matter is ever touched: each real atom enumerates the
+// lattice shifts (i, j, k) that put it inside the fractional window [wlo, whi] per axis -- the cell plus the interaction
+// halo, or a slab rank's share of it -- and bins those images, carrying the reference's slot id  b * nreal + a  and the
+// reference's left-to-right float64 arithmetic for the image position, so that everything downstream (neighbour rows,
+// descriptor / pair / force kernels, the reference force convention on slot ids) is unchanged and bit-identical.
+//   k_lat_count   counts per cell (all binned atoms) and per (element, cell) (centres), copies the real block
+//   k_scan_block  one exclusive scan over [cell counts | centre counts e = 0 | e = 1 | ...]
+//   k_lat_scatter 32-byte records into their cells (arrival order)
+//   k_lat_sort_rows  one warp per cell: order by slot id, assign the centre rows (element, cell order, slot)
+struct LatBin {
+  double L[9], ginv[9], wlo[3], whi[3], inv_n;
+  int ntess;
+  int slab_rank, slab_world;
+  int64_t nreal;
+  GridParams g;
+};
+
+__device__ __forceinline__ double lat_frac(double x, double y, double z, const double* __restrict__ gi, int d) {
+  return __fma_rn(z, gi[6 + d], __fma_rn(y, gi[3 + d], __dmul_rn(x, gi[d])));
+}
+// owner of a real atom among the slab ranks (floor(frac0 * world), clamped): same expression in every kernel
+__device__ __forceinline__ int lat_owner(double f0, int world) {
+  int o = (int)floor(f0 * (double)world);
+  return o < 0 ? 0 : (o >= world ? world - 1 : o);
+}
+__device__ __forceinline__ int lat_block(int i, int j, int k, int nt) {
+  const int side = 2 * nt + 1;
+  const int lin = ((i + nt) * side + (j + nt)) * side + (k + nt), centre = (nt * side + nt) * side + nt;
+  return lin < centre ? lin + 1 : (lin == centre ? 0 : lin);
+}
+
+// ONE enumeration shared by the counting and the scattering pass: calls f(b, x, y, z, cid) for every binned image of
+// real atom a (b = 0 is the atom itself).
+template <typename F>
+__device__ __forceinline__ void lat_enumerate(const LatBin& B, double x0, double y0, double z0, const double* f, F&& fn) {
+  int lo[3], hi[3];
+#pragma unroll
+  for (int d = 0; d < 3; d++) {
+    lo[d] = max(-B.ntess, (int)ceil(B.wlo[d] - f[d]));
+    hi[d] = min(B.ntess, (int)floor(B.whi[d] - f[d]));
+  }
+  const GridParams& g = B.g;
+  for (int i = lo[0]; i <= hi[0]; i++)
+    for (int j = lo[1]; j <= hi[1]; j++)
+      for (int k = lo[2]; k <= hi[2]; k++) {
+        double x = x0, y = y0, z = z0;
+        if (i | j | k) {   // coords_ + i*L0 + j*L1 + k*L2, left to right with separate roundings (numpy)
+          double di = (double)i, dj = (double)j, dk = (double)k;
+          x = __dadd_rn(__dadd_rn(__dadd_rn(x0, __dmul_rn(di, B.L[0])), __dmul_rn(dj, B.L[3])), __dmul_rn(dk, B.L[6]));
+          y = __dadd_rn(__dadd_rn(__dadd_rn(y0, __dmul_rn(di, B.L[1])), __dmul_rn(dj, B.L[4])), __dmul_rn(dk, B.L[7]));
+          z = __dadd_rn(__dadd_rn(__dadd_rn(z0, __dmul_rn(di, B.L[2])), __dmul_rn(dj, B.L[5])), __dmul_rn(dk, B.L[8]));
+        }
+        int cx = cell_coord(x, g.ox, g.inv_cell, g.gx), cy = cell_coord(y, g.oy, g.inv_cell, g.gy), cz = cell_coord(z, g.oz, g.inv_cell, g.gz);
+        fn(lat_block(i, j, k, B.ntess), x, y, z, (cx * g.gy + cy) * g.gz + cz);
+      }
+}
+
+__device__ __forceinline__ int ele_index(const DevParams& P, int z) {
+  int ei = -1;
+  for (int k = 0; k < P.n_ele; k++) if (P.eles[k] == z) ei = k;
+  return ei;
+}
+
+// cnt_all = [ncells cell counts | n_ele x ncells centre counts], zeroed by the launcher
+__global__ void k_lat_count(const double* __restrict__ xyz, const int32_t* __restrict__ Z, const __grid_constant__ LatBin B,
+                            const __grid_constant__ DevParams P, double* __restrict__ pos, int32_t* __restrict__ Zo, double* __restrict__ inv_n,
+                            GridParams* __restrict__ gp, int32_t* __restrict__ cnt_all, int32_t* __restrict__ flags, int32_t* __restrict__ rowslot,
+                            int64_t nrows, int32_t* __restrict__ rowofslot) {
+  const int64_t t0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
+  if (t0 == 0) { inv_n[0] = B.inv_n; *gp = B.g; }
+  for (int64_t t = t0; t < nrows; t += stride) rowslot[t] = -1;
+  const int ncells = B.g.ncells;
+  for (int64_t a = t0; a < B.nreal; a += stride) {
+    double x = xyz[3 * a], y = xyz[3 * a + 1], z = xyz[3 * a + 2];
+    int zz = Z[a];
+    pos[3 * a] = x; pos[3 * a + 1] = y; pos[3 * a + 2] = z;   // the real block: read by k_charges (dipole)
+    Zo[a] = zz;
+    rowofslot[a] = -1;
+    if (zz <= 0) continue;
+    double f[3];
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+      f[d] = lat_frac(x, y, z, B.ginv, d);
+      if (f[d] < -1e-6 || f[d] > 1.0 + 1e-6) atomicOr(flags, 8);   // not wrapped into the cell: the caller falls back
+    }
+    const int e = ele_index(P, zz);
+    const bool centre = e >= 0 && (B.slab_world <= 1 || lat_owner(f[0], B.slab_world) == B.slab_rank);
+    lat_enumerate(B, x, y, z, f, [&](int b, double, double, double, int cid) {
+      atomicAdd(&cnt_all[cid], 1);
+      if (b == 0 && centre) atomicAdd(&cnt_all[(1 + e) * ncells + cid], 1);
+    });
+  }
+}
+
+// exclusive scan of in[0..n) by ONE block (n up to a few 100k: the cell tables of the lattice path), out[n] = total
+__global__ void __launch_bounds__(1024) k_scan_block(const int32_t* __restrict__ in, int32_t* __restrict__ out, int n) {
+  __shared__ int32_t wsum[32];
+  __shared__ int32_t carry_s, tot_s;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  for (int base = 0; base < n; base += 1024 * 8) {
+    const int32_t carry = carry_s;
+    int i0 = base + threadIdx.x * 8;
+    int32_t v[8], s = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) { v[k] = (i0 + k < n) ? in[i0 + k] : 0; s += v[k]; }
+    int32_t inc = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { int32_t t = __shfl_up_sync(FULL, inc, o); if (lane >= o) inc += t; }
+    if (lane == 31) wsum[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+      int32_t x = wsum[lane], xi = x;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { int32_t t = __shfl_up_sync(FULL, xi, o); if (lane >= o) xi += t; }
+      wsum[lane] = xi - x;            // exclusive warp offsets
+      if (lane == 31) tot_s = xi;     // chunk total
+    }
+    __syncthreads();
+    int32_t run = carry + wsum[w] + inc - s;
+#pragma unroll
+    for (int k = 0; k < 8; k++) { if (i0 + k < n) out[i0 + k] = run; run += v[k]; }
+    __syncthreads();
+    if (threadIdx.x == 0) carry_s = carry + tot_s;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[n] = carry_s;
+}
+
+__global__ void k_lat_scatter(const double* __restrict__ xyz, const int32_t* __restrict__ Z, const __grid_constant__ LatBin B,
+                              const __grid_constant__ DevParams P, int32_t* __restrict__ cnt_all, const int32_t* __restrict__ off_all,
+                              SAtom* __restrict__ sat) {
+  const int64_t t0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t a = t0; a < B.nreal; a += stride) {
+    int zz = Z[a];
+    if (zz <= 0) continue;
+    double x = xyz[3 * a], y = xyz[3 * a + 1], z = xyz[3 * a + 2];
+    double f[3];
+#pragma unroll
+    for (int d = 0; d < 3; d++) f[d] = lat_frac(x, y, z, B.ginv, d);
+    const int e = ele_index(P, zz);
+    lat_enumerate(B, x, y, z, f, [&](int b, double xi, double yi, double zi, int cid) {
+      int p = atomicSub(&cnt_all[cid], 1) - 1;     // the counts run back to zero: arrival rank inside the cell
+      SAtom r;
+      r.x = xi; r.y = yi; r.z = zi;
+      r.slot = (int32_t)((int64_t)b * B.nreal + a);
+      r.e = e;
+      sat[off_all[cid] + p] = r;
+    });
+  }
+}
+
+// One warp per cell: order the records by slot id (removes the arrival nondeterminism), then give every centre of the
+// cell its row: rows are ordered by (element, cell, slot) and each element's range starts at a multiple of TM_ROW_TILE.
+// off_all = scan of [cell counts | centre counts per element]: off_all[cid] = first record of the cell,
+// off_all[(1+e) ncells + cid] - off_all[(1+e) ncells] = centres of element e in the cells before cid.
+__global__ void k_lat_sort_rows(const __grid_constant__ LatBin B, int n_ele, const int32_t* __restrict__ off_all, int32_t* __restrict__ cstart,
+                                SAtom* __restrict__ sat, int32_t* __restrict__ rowmeta, int32_t* __restrict__ rowslot, int32_t* __restrict__ rowsidx,
+                                int32_t* __restrict__ rowofslot, int64_t nrows, int32_t* __restrict__ flags) {
+  const int ncells = B.g.ncells;
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  // element row bases (every warp: n_ele <= 8 cached loads)
+  int ebase[TM_MAX_ELE];
+  {
+    int base = 0, total = 0;
+#pragma unroll
+    for (int e = 0; e < TM_MAX_ELE; e++) {
+      int cnt = (e < n_ele) ? off_all[(2 + e) * ncells] - off_all[(1 + e) * ncells] : 0;
+      ebase[e] = base;
+      if (blockIdx.x == 0 && threadIdx.x == 0) { rowmeta[2 * e] = base; rowmeta[2 * e + 1] = cnt; }
+      base += ((cnt + TM_ROW_TILE - 1) / TM_ROW_TILE) * TM_ROW_TILE;
+      total += cnt;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { rowmeta[2 * TM_MAX_ELE] = total; rowmeta[2 * TM_MAX_ELE + 1] = base; }
+  }
+  for (int cid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; cid <= ncells; cid += warps) {
+    if (cid == ncells) { if (lane == 0) cstart[ncells] = off_all[ncells]; continue; }
+    const int b = off_all[cid], e = off_all[cid + 1], n = e - b;
+    if (lane == 0) cstart[cid] = b;
+    if (n <= 0) continue;
+    if (n > 32) {     // dense cell: serial insertion sort by lane 0, then the generic tail below with one record per pass
+      if (lane == 0) {
+        for (int i = b + 1; i < e; i++) {
+          SAtom v = sat[i];
+          int j = i - 1;
+          while (j >= b && sat[j].slot > v.slot) { sat[j + 1] = sat[j]; j--; }
+          sat[j + 1] = v;
+        }
+      }
+      __syncwarp();
+    }
+    // centre rank bookkeeping per element across passes of 32 records
+    int seen[TM_MAX_ELE];
+#pragma unroll
+    for (int q = 0; q < TM_MAX_ELE; q++) seen[q] = 0;
+    for (int p0 = 0; p0 < n; p0 += 32) {
+      const int cnt = min(32, n - p0);
+      SAtom mine;
+      mine.slot = 0x7fffffff; mine.e = -1; mine.x = mine.y = mine.z = 0.0;
+      if (lane < cnt) mine = sat[b + p0 + lane];
+      int rank = lane;
+      if (n <= 32) {
+        rank = 0;
+        for (int k = 0; k < cnt; k++) {
+          int32_t other = __shfl_sync(FULL, mine.slot, k);
+          rank += (other < mine.slot) ? 1 : 0;
+        }
+        __syncwarp();
+        if (lane < cnt) sat[b + rank] = mine;
+      }
+      // centres: real slots owned by this rank
+      bool centre = false;
+      if (lane < cnt && mine.e >= 0 && mine.slot < B.nreal) {
+        centre = true;
+        if (B.slab_world > 1) centre = lat_owner(lat_frac(mine.x, mine.y, mine.z, B.ginv, 0), B.slab_world) == B.slab_rank;
+      }
+#pragma unroll
+      for (int q = 0; q < TM_MAX_ELE; q++) {
+        if (q >= n_ele) break;
+        // centres of element q of this pass as a bit mask over SORTED positions: those below this record come first
+        const unsigned mq = __reduce_or_sync(FULL, (centre && mine.e == q) ? (1u << rank) : 0u);
+        if (centre && mine.e == q) {
+          int row = ebase[q] + (off_all[(1 + q) * ncells + cid] - off_all[(1 + q) * ncells]) + seen[q] + __popc(mq & ((1u << rank) - 1u));
+          if (row < nrows) {
+            rowslot[row] = mine.slot;
+            rowsidx[row] = b + p0 + rank;
+            rowofslot[mine.slot] = row;
+          } else {
+            atomicOr(flags, 64);
+          }
+        }
+        seen[q] += __popc(mq);
+      }
+    }
+  }
+}
+
+int tm_launch_lattice_bin(tm_ctx* c, const SysView& s) {
+  int rc;
+  const int n_ele = c->hp.n_ele;
+  const int64_t ncells = s.hgrid.ncells;
+  const int64_t nall = (1 + (int64_t)n_ele) * ncells;
+  if ((rc = tm_buf(c, c->b_pos, (size_t)s.nreal * 24))) return rc;
+  if ((rc = tm_buf(c, c->b_Z, (size_t)s.nreal * 4))) return rc;
+  if ((rc = tm_buf(c, c->b_natom, 8))) return rc;
+  if ((rc = tm_buf(c, c->b_cntall, (size_t)(nall + 8) * 4))) return rc;
+  if ((rc = tm_buf(c, c->b_offall, (size_t)(nall + 8) * 4))) return rc;
+  if ((rc = tm_buf(c, c->b_cstart, (size_t)(ncells + 8) * 4))) return rc;
+  if ((rc = tm_buf(c, c->b_satom, (size_t)s.nslots * sizeof(SAtom)))) return rc;
+  if ((rc = tm_buf(c, c->b_grid, sizeof(GridParams)))) return rc;
+  if ((rc = tm_buf(c, c->b_rowmeta, (2 * TM_MAX_ELE + 2) * 4))) return rc;
+  if ((rc = tm_buf(c, c->b_rowslot, (size_t)s.nrows * 4))) return rc;
+  if ((rc = tm_buf(c, c->b_rowsidx, (size_t)s.nrows * 4))) return rc;
+  if ((rc = tm_buf(c, c->b_rowofslot, (size_t)s.nreal * 4))) return rc;
+  if ((rc = tm_buf(c, c->b_scan_tmp, (size_t)(nall / SCAN_TILE + 16) * 4 * 2))) return rc;
+  LatBin B;
+  memcpy(B.L, s.lat.v, 72);
+  memcpy(B.ginv, s.ginv, 72);
+  for (int d = 0; d < 3; d++) { B.wlo[d] = s.wlo[d]; B.whi[d] = s.whi[d]; }
+  B.inv_n = s.lat.v[9];
+  B.ntess = s.lat_ntess;
+  B.slab_rank = s.slab_rank; B.slab_world = s.slab_world;
+  B.nreal = s.nreal;
+  B.g = s.hgrid;
+  int32_t* cnt_all = (int32_t*)c->b_cntall.p;
+  int32_t* off_all = (int32_t*)c->b_offall.p;
+  TM_CUDA(cudaMemsetAsync(cnt_all, 0, (size_t)(nall + 8) * 4, c->stream));
+  int blocks = (int)((std::max<int64_t>(s.nreal, s.nrows) + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  k_lat_count<<<blocks, 256, 0, c->stream>>>(s.xyz_real, s.Z_real, B, c->hp, (double*)c->b_pos.p, (int32_t*)c->b_Z.p, (double*)c->b_natom.p,
+                                             (GridParams*)c->b_grid.p, cnt_all, (int32_t*)c->b_flags.p, (int32_t*)c->b_rowslot.p, s.nrows,
+                                             (int32_t*)c->b_rowofslot.p);
+  c->launches++;
+  if (nall <= 262144) {
+    k_scan_block<<<1, 1024, 0, c->stream>>>(cnt_all, off_all, (int)nall);
+    c->launches++;
+  } else if ((rc = scan_exclusive(c, cnt_all, off_all, nall, (int32_t*)c->b_scan_tmp.p))) {
+    return rc;
+  }
+  int sblocks = (int)((s.nreal + 255) / 256);
+  if (sblocks > 148 * 8) sblocks = 148 * 8;
+  k_lat_scatter<<<sblocks, 256, 0, c->stream>>>(s.xyz_real, s.Z_real, B, c->hp, cnt_all, off_all, (SAtom*)c->b_satom.p);
+  int cblocks = (int)(((ncells + 1) * 32 + 255) / 256);
+  if (cblocks > 148 * 16) cblocks = 148 * 16;
+  k_lat_sort_rows<<<cblocks, 256, 0, c->stream>>>(B, n_ele, off_all, (int32_t*)c->b_cstart.p, (SAtom*)c->b_satom.p, (int32_t*)c->b_rowmeta.p,
+                                                  (int32_t*)c->b_rowslot.p, (int32_t*)c->b_rowsidx.p, (int32_t*)c->b_rowofslot.p, s.nrows,
+                                                  (int32_t*)c->b_flags.p);
+  c->launches += 2;
+  TM_CUDA(cudaGetLastError());
+  return TM_OK;
+}

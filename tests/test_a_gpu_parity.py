@@ -328,6 +328,41 @@ def test_eval_lattice_unwrapped_input_falls_back_to_bbox_grid():
     _check_energy(r3["Etotal"], g["oracle_Etotal"], "Etotal")
 
 
+@pytest.mark.parametrize("nx,shear", [(3, 0.35), (6, 0.2)])
+def test_eval_lattice_triclinic_windowed_binning(nx, shear):
+    """The lattice path bins only the real atoms and the images inside the cell + halo window (fractional coordinates of a
+    general lattice).  A sheared water box must give what the caller-supplied full tessellation gives (same slot ids, same
+    image arithmetic), and what the oracle gives on that tessellation: nx = 3 needs two shells of images (125 blocks),
+    nx = 6 one shell with most of it outside the window."""
+    from oracle import oracle_graph as og
+    from oracle import oracle_np as onp
+    from tensormol_b200.SystemBuilders import water_box, wrap_into_cell
+    Z, X, lat = water_box(nx)
+    lat = lat.copy()
+    lat[1, 0] = shear * lat[0, 0]          # b leans along a, c leans along a and b
+    lat[2, 0] = -0.5 * shear * lat[0, 0]
+    lat[2, 1] = 0.7 * shear * lat[1, 1]
+    X = wrap_into_cell(X, lat)
+    hidden = [32, 32]
+    eng, W, P = _engine([1, 8], hidden, 5)
+    Zt, Xt = onp.tess_lattice(lat, Z.astype(np.uint8), X, P["EECutoffOff"])
+    nimg = len(Zt) // len(Z)
+    ntess = (round(nimg ** (1 / 3)) - 1) // 2
+    nreal = len(Z)
+    r1 = eng.evaluate_images(Xt, Zt.astype(np.int32), nreal, descriptors=True)
+    r2 = eng.evaluate_lattice(X, Z, lat, ntess, descriptors=True)
+    for k in ("Etotal", "Ebp", "Ecc", "Evdw"):
+        _check_energy(r2[k], r1[k], k)
+    _check_desc(r2["descriptors"][0], r1["descriptors"][0].astype(np.float64))
+    assert np.abs(r2["charge"][0] - r1["charge"][0, :nreal]).max() <= 1e-6 * max(np.abs(r1["charge"]).max(), 1e-3)
+    assert np.abs(r2["gradient"] - r1["gradient"]).max() <= 1e-5 * np.abs(r1["gradient"]).max()
+    if nx == 3:
+        o = og.Oracle([1, 8], W, P).evaluate_periodic(Xt, Zt, nreal)
+        for k in ("Etotal", "Ebp", "Ecc", "Evdw"):
+            _check_energy(r2[k], o[k], k)
+        _check_grad(r2["gradient"][0], o["gradient"][0, :nreal])
+
+
 def test_graph_replay_equals_eager_device_call():
     """engine.GraphedCall: the captured tm_eval_lattice_dev step, replayed after the positions were changed in place,
     gives the numbers of an eager call on the new positions."""
