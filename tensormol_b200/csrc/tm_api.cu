@@ -177,6 +177,7 @@ extern "C" int tm_set_params(tm_ctx* c, const tm_params* params) {
   if (!c || !params) { tm_set_error("null argument"); return TM_EINVAL; }
   tm_params old = c->params;
   c->cfg_gen++;
+  c->params_gen++;
   c->params = *params;
   int rc = build_dev_params(c);
   if (rc) { c->params = old; build_dev_params(c); return rc; }
@@ -224,7 +225,7 @@ extern "C" void tm_destroy(tm_ctx* c) {
   DevBuf* all[] = {&c->b_pos, &c->b_Z, &c->b_cellid, &c->b_rank, &c->b_count, &c->b_cstart, &c->b_sorted, &c->b_satom, &c->b_scan_tmp,
                    &c->b_rowslot, &c->b_rowsidx, &c->b_rowofslot, &c->b_blkcnt, &c->b_rowmeta, &c->b_nbcnt, &c->b_nboff, &c->b_nbr, &c->b_G, &c->b_Gs, &c->b_ypart,
                    &c->b_delta0, &c->b_delta1, &c->b_dG[0], &c->b_dG[1], &c->b_y[0], &c->b_y[1], &c->b_q, &c->b_qs, &c->b_dedq, &c->b_F,
-                   &c->b_acc, &c->b_bbox, &c->b_grid, &c->b_flags, &c->b_out, &c->b_molacc, &c->b_natom};
+                   &c->b_acc, &c->b_bbox, &c->b_grid, &c->b_flags, &c->b_out, &c->b_molacc, &c->b_natom, &c->b_cntall, &c->b_offall, &c->b_pe, &c->b_pairtab};
   for (DevBuf* b : all) free_buf(*b);
   for (int n = 0; n < 2; n++)
     for (int l = 0; l < TM_MAX_HIDDEN; l++) free_buf(c->b_act[n][l]);
@@ -773,16 +774,18 @@ static void host_grid(tm_ctx* c, SysView* sv, const double* L, int ntess) {
   GridParams g;
   double cell = c->params.r_Rc * (1.0 + 1e-6);
   int gx = 1, gy = 1, gz = 1;
+  const int zdiv = sv->lat_bin ? 4 : 1;     // z bins per cell edge (GridParams)
   for (int d = 0; d < 3; d++) { double pad = 1e-6 * (1.0 + fabs(mn[d]) + fabs(mx[d])); mn[d] -= pad; mx[d] += pad; }
   for (int it = 0; it < 200; it++) {
     gx = (int)floor((mx[0] - mn[0]) / cell) + 1;
     gy = (int)floor((mx[1] - mn[1]) / cell) + 1;
-    gz = (int)floor((mx[2] - mn[2]) / cell) + 1;
+    gz = ((int)floor((mx[2] - mn[2]) / cell) + 1) * zdiv;
     if ((double)gx * gy * gz <= (double)sv->ncells_cap) break;
     cell *= 1.2599210498948732;
   }
   g.ox = mn[0]; g.oy = mn[1]; g.oz = mn[2];
   g.cell = cell; g.inv_cell = 1.0 / cell;
+  g.zcell = cell / zdiv; g.inv_zcell = (double)zdiv / cell; g.zdiv = zdiv;
   g.gx = gx; g.gy = gy; g.gz = gz;
   g.ncell_mol = gx * gy * gz;
   g.ncells = g.ncell_mol;

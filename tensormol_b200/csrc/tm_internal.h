@@ -42,9 +42,14 @@ struct GridParams {
   double ox, oy, oz;   // origin
   double inv_cell;     // 1/cell edge
   double cell;
-  int gx, gy, gz;      // cells per molecule box
+  int gx, gy, gz;      // cells per molecule box; gz counts the (possibly finer) z bins
   int ncell_mol;       // gx*gy*gz
   int ncells;          // nmol*ncell_mol
+  // z is the fastest cell index, so any z-range of a column is ONE contiguous run of the cell-sorted array whatever the
+  // bin height: the lattice path uses zdiv bins per cell edge, which clips the runs of the pair / neighbour kernels to
+  // their sphere four times tighter at no cost per candidate (the molecule path keeps zdiv = 1)
+  double zcell, inv_zcell;
+  int zdiv;
 };
 
 // Constant hyper-parameters as the kernels consume them (fp32 + a few f64).
@@ -156,7 +161,10 @@ struct tm_ctx {
   // ---- per-evaluation workspace (grow-only) ----
   DevBuf b_pos, b_Z, b_cellid, b_rank, b_count, b_cstart, b_sorted, b_satom, b_scan_tmp;
   DevBuf b_rowslot, b_rowsidx, b_rowofslot, b_blkcnt, b_rowmeta;
-  DevBuf b_cntall, b_offall;
+  DevBuf b_cntall, b_offall, b_pe, b_pairtab;
+  // pair-potential tables of tm_pair.cu (rebuilt when the hyper-parameters change)
+  uint64_t params_gen = 1, pairtab_gen = 0;
+  int pt_kmin = 0, pt_nnodes = 0, pt_nfn = 0, pt_kink_k = -1, pt_kink_v = -1;
   DevBuf b_nbcnt, b_nboff, b_nbr, b_G, b_Gs, b_ypart, b_act[2][TM_MAX_HIDDEN], b_delta0, b_delta1, b_dG[2], b_y[2];
   DevBuf b_q, b_qs, b_dedq, b_F, b_acc, b_bbox, b_grid, b_flags, b_out, b_molacc;
   DevBuf b_natom;

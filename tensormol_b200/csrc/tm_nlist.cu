@@ -163,6 +163,7 @@ __global__ void k_grid_params(const unsigned long long* bb, double rc, int64_t n
   g->cell = cell;
   g->inv_cell = 1.0 / cell;
   g->gx = gx; g->gy = gy; g->gz = gz;
+  g->zcell = cell; g->inv_zcell = 1.0 / cell; g->zdiv = 1;
   g->ncell_mol = gx * gy * gz;
   g->ncells = (int)(nmol * (int64_t)(gx * gy * gz));
 }
@@ -181,12 +182,12 @@ __global__ void k_cell_count(const double* __restrict__ pos, const int32_t* __re
     if (image_block_skipped(t, win)) continue;   // k_scatter applies the same test: cellid / rank of these slots are never read
     if (Z[t] <= 0 || !slot_in_window(pos, t, win)) { cellid[t] = -1; rank[t] = -1; continue; }   // rank[] is reused as sidx_of_slot (-1 = absent)
     if (check_inside) {
-      double fx = (pos[3 * t] - g.ox) * g.inv_cell, fy = (pos[3 * t + 1] - g.oy) * g.inv_cell, fz = (pos[3 * t + 2] - g.oz) * g.inv_cell;
+      double fx = (pos[3 * t] - g.ox) * g.inv_cell, fy = (pos[3 * t + 1] - g.oy) * g.inv_cell, fz = (pos[3 * t + 2] - g.oz) * g.inv_zcell;
       if (fx < 0.0 || fy < 0.0 || fz < 0.0 || fx > (double)g.gx || fy > (double)g.gy || fz > (double)g.gz) atomicOr(flags, 8);
     }
     int cx = cell_coord(pos[3 * t], g.ox, g.inv_cell, g.gx);
     int cy = cell_coord(pos[3 * t + 1], g.oy, g.inv_cell, g.gy);
-    int cz = cell_coord(pos[3 * t + 2], g.oz, g.inv_cell, g.gz);
+    int cz = cell_coord(pos[3 * t + 2], g.oz, g.inv_zcell, g.gz);
     int m = (int)(t / maxnatom);
     int cid = m * g.ncell_mol + (cx * g.gy + cy) * g.gz + cz;   // z fastest: a +-1 z-run is contiguous
     cellid[t] = cid;
@@ -656,8 +657,8 @@ __global__ void k_neighbours(const SAtom* __restrict__ sat, const int32_t* __res
   int m = (int)(slot / maxnatom);
   int cx = cell_coord(ci.x, g.ox, g.inv_cell, g.gx);
   int cy = cell_coord(ci.y, g.oy, g.inv_cell, g.gy);
-  int cz = cell_coord(ci.z, g.oz, g.inv_cell, g.gz);
-  int z0 = max(cz - 1, 0), z1 = min(cz + 1, g.gz - 1);
+  // z bins that can hold a neighbour, from the centre's position (the bins may be finer than the cell edge)
+  int z0 = cell_coord(ci.z - rr * (1.0 + 1e-9), g.oz, g.inv_zcell, g.gz), z1 = cell_coord(ci.z + rr * (1.0 + 1e-9), g.oz, g.inv_zcell, g.gz);
   // lane c < 9 owns column (dx, dy) = (c / 3 - 1, c % 3 - 1): run [cb, ce)
   int cb = 0, ce = 0;
   if (lane < 9) {
@@ -753,8 +754,7 @@ __global__ void k_nlist_csr(const SAtom* __restrict__ sat, const int32_t* __rest
   int m = (int)(i / maxnatom);
   int cx = cell_coord(ci.x, g.ox, g.inv_cell, g.gx);
   int cy = cell_coord(ci.y, g.oy, g.inv_cell, g.gy);
-  int cz = cell_coord(ci.z, g.oz, g.inv_cell, g.gz);
-  int z0 = max(cz - 1, 0), z1 = min(cz + 1, g.gz - 1);
+  int z0 = cell_coord(ci.z - rc * (1.0 + 1e-9), g.oz, g.inv_zcell, g.gz), z1 = cell_coord(ci.z + rc * (1.0 + 1e-9), g.oz, g.inv_zcell, g.gz);
   int total = 0;
   int64_t wbase = FILL ? off[i] : 0;
   for (int dx = -1; dx <= 1; dx++) {
@@ -834,7 +834,7 @@ int tm_launch_nlist_csr(tm_ctx* c, const SysView& s, double rc, int do_perms, in
 // reference's left-to-right float64 arithmetic for the image position, so that everything downstream (neighbour rows,
 // descriptor / pair / force kernels, the reference force convention on slot ids) is unchanged and bit-identical.
 //   k_lat_count   counts per cell (all binned atoms) and per (element, cell) (centres), copies the real block
-//   k_scan_block  one exclusive scan over [cell counts | centre counts e = 0 | e = 1 | ...]
+//   k_scan_segments  exclusive scans of [cell counts | centre counts e = 0 | e = 1 | ...], one block per segment
 //   k_lat_scatter 32-byte records into their cells (arrival order)
 //   k_lat_sort_rows  one warp per cell: order by slot id, assign the centre rows (element, cell order, slot)
 struct LatBin {
@@ -845,6 +845,8 @@ struct LatBin {
   GridParams g;
 };
 
+// table segments are padded to 4 ints with room for the total behind the n entries
+__device__ __forceinline__ int pad4(int n) { return (n + 4) & ~3; }
 __device__ __forceinline__ double lat_frac(double x, double y, double z, const double* __restrict__ gi, int d) {
   return __fma_rn(z, gi[6 + d], __fma_rn(y, gi[3 + d], __dmul_rn(x, gi[d])));
 }
@@ -859,30 +861,32 @@ __device__ __forceinline__ int lat_block(int i, int j, int k, int nt) {
   return lin < centre ? lin + 1 : (lin == centre ? 0 : lin);
 }
 
-// ONE enumeration shared by the counting and the scattering pass: calls f(b, x, y, z, cid) for every binned image of
-// real atom a (b = 0 is the atom itself).
+// ONE enumeration shared by the counting and the scattering pass: calls fn(b, x, y, z, cid) for every binned image of
+// real atom a (b = 0 is the atom itself).  LAT_SUB threads share an atom and take its images round-robin (an atom near a
+// corner of the cell has 8 images inside the window, the average one 3: the atomics of the passes then run side by side).
+#define LAT_SUB 4
 template <typename F>
-__device__ __forceinline__ void lat_enumerate(const LatBin& B, double x0, double y0, double z0, const double* f, F&& fn) {
-  int lo[3], hi[3];
+__device__ __forceinline__ void lat_enumerate(const LatBin& B, double x0, double y0, double z0, const double* f, int sub, F&& fn) {
+  int lo[3], n[3];
 #pragma unroll
   for (int d = 0; d < 3; d++) {
     lo[d] = max(-B.ntess, (int)ceil(B.wlo[d] - f[d]));
-    hi[d] = min(B.ntess, (int)floor(B.whi[d] - f[d]));
+    n[d] = max(0, min(B.ntess, (int)floor(B.whi[d] - f[d])) - lo[d] + 1);
   }
   const GridParams& g = B.g;
-  for (int i = lo[0]; i <= hi[0]; i++)
-    for (int j = lo[1]; j <= hi[1]; j++)
-      for (int k = lo[2]; k <= hi[2]; k++) {
-        double x = x0, y = y0, z = z0;
-        if (i | j | k) {   // coords_ + i*L0 + j*L1 + k*L2, left to right with separate roundings (numpy)
-          double di = (double)i, dj = (double)j, dk = (double)k;
-          x = __dadd_rn(__dadd_rn(__dadd_rn(x0, __dmul_rn(di, B.L[0])), __dmul_rn(dj, B.L[3])), __dmul_rn(dk, B.L[6]));
-          y = __dadd_rn(__dadd_rn(__dadd_rn(y0, __dmul_rn(di, B.L[1])), __dmul_rn(dj, B.L[4])), __dmul_rn(dk, B.L[7]));
-          z = __dadd_rn(__dadd_rn(__dadd_rn(z0, __dmul_rn(di, B.L[2])), __dmul_rn(dj, B.L[5])), __dmul_rn(dk, B.L[8]));
-        }
-        int cx = cell_coord(x, g.ox, g.inv_cell, g.gx), cy = cell_coord(y, g.oy, g.inv_cell, g.gy), cz = cell_coord(z, g.oz, g.inv_cell, g.gz);
-        fn(lat_block(i, j, k, B.ntess), x, y, z, (cx * g.gy + cy) * g.gz + cz);
-      }
+  const int nimg = n[0] * n[1] * n[2];
+  for (int m = sub; m < nimg; m += LAT_SUB) {
+    const int k = lo[2] + m % n[2], j = lo[1] + (m / n[2]) % n[1], i = lo[0] + m / (n[2] * n[1]);
+    double x = x0, y = y0, z = z0;
+    if (i | j | k) {   // coords_ + i*L0 + j*L1 + k*L2, left to right with separate roundings (numpy)
+      double di = (double)i, dj = (double)j, dk = (double)k;
+      x = __dadd_rn(__dadd_rn(__dadd_rn(x0, __dmul_rn(di, B.L[0])), __dmul_rn(dj, B.L[3])), __dmul_rn(dk, B.L[6]));
+      y = __dadd_rn(__dadd_rn(__dadd_rn(y0, __dmul_rn(di, B.L[1])), __dmul_rn(dj, B.L[4])), __dmul_rn(dk, B.L[7]));
+      z = __dadd_rn(__dadd_rn(__dadd_rn(z0, __dmul_rn(di, B.L[2])), __dmul_rn(dj, B.L[5])), __dmul_rn(dk, B.L[8]));
+    }
+    int cx = cell_coord(x, g.ox, g.inv_cell, g.gx), cy = cell_coord(y, g.oy, g.inv_cell, g.gy), cz = cell_coord(z, g.oz, g.inv_zcell, g.gz);
+    fn(lat_block(i, j, k, B.ntess), x, y, z, (cx * g.gy + cy) * g.gz + cz);
+  }
 }
 
 __device__ __forceinline__ int ele_index(const DevParams& P, int z) {
@@ -891,7 +895,7 @@ __device__ __forceinline__ int ele_index(const DevParams& P, int z) {
   return ei;
 }
 
-// cnt_all = [ncells cell counts | n_ele x ncells centre counts], zeroed by the launcher
+// cnt_all = [ncells (fine) cell counts | n_ele x ngroups centre counts per group of zdiv z bins], zeroed by the launcher
 __global__ void k_lat_count(const double* __restrict__ xyz, const int32_t* __restrict__ Z, const __grid_constant__ LatBin B,
                             const __grid_constant__ DevParams P, double* __restrict__ pos, int32_t* __restrict__ Zo, double* __restrict__ inv_n,
                             GridParams* __restrict__ gp, int32_t* __restrict__ cnt_all, int32_t* __restrict__ flags, int32_t* __restrict__ rowslot,
@@ -899,58 +903,87 @@ __global__ void k_lat_count(const double* __restrict__ xyz, const int32_t* __res
   const int64_t t0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
   if (t0 == 0) { inv_n[0] = B.inv_n; *gp = B.g; }
   for (int64_t t = t0; t < nrows; t += stride) rowslot[t] = -1;
-  const int ncells = B.g.ncells;
-  for (int64_t a = t0; a < B.nreal; a += stride) {
+  const int ncells = B.g.ncells, zdiv = B.g.zdiv, ngroups = ncells / zdiv;
+  for (int64_t t = t0; t < B.nreal * LAT_SUB; t += stride) {
+    const int64_t a = t / LAT_SUB;
+    const int sub = (int)(t - a * LAT_SUB);
     double x = xyz[3 * a], y = xyz[3 * a + 1], z = xyz[3 * a + 2];
     int zz = Z[a];
-    pos[3 * a] = x; pos[3 * a + 1] = y; pos[3 * a + 2] = z;   // the real block: read by k_charges (dipole)
-    Zo[a] = zz;
-    rowofslot[a] = -1;
+    if (sub == 0) {
+      pos[3 * a] = x; pos[3 * a + 1] = y; pos[3 * a + 2] = z;   // the real block: read by k_charges (dipole)
+      Zo[a] = zz;
+      rowofslot[a] = -1;
+    }
     if (zz <= 0) continue;
     double f[3];
 #pragma unroll
     for (int d = 0; d < 3; d++) {
       f[d] = lat_frac(x, y, z, B.ginv, d);
-      if (f[d] < -1e-6 || f[d] > 1.0 + 1e-6) atomicOr(flags, 8);   // not wrapped into the cell: the caller falls back
+      if (sub == 0 && (f[d] < -1e-6 || f[d] > 1.0 + 1e-6)) atomicOr(flags, 8);   // not wrapped into the cell: the caller falls back
     }
     const int e = ele_index(P, zz);
     const bool centre = e >= 0 && (B.slab_world <= 1 || lat_owner(f[0], B.slab_world) == B.slab_rank);
-    lat_enumerate(B, x, y, z, f, [&](int b, double, double, double, int cid) {
+    lat_enumerate(B, x, y, z, f, sub, [&](int b, double, double, double, int cid) {
       atomicAdd(&cnt_all[cid], 1);
-      if (b == 0 && centre) atomicAdd(&cnt_all[(1 + e) * ncells + cid], 1);
+      if (b == 0 && centre) atomicAdd(&cnt_all[pad4(ncells) + e * pad4(ngroups) + cid / zdiv], 1);
     });
   }
 }
 
-// exclusive scan of in[0..n) by ONE block (n up to a few 100k: the cell tables of the lattice path), out[n] = total
-__global__ void __launch_bounds__(1024) k_scan_block(const int32_t* __restrict__ in, int32_t* __restrict__ out, int n) {
+// exclusive scans of the segments [n0 | n1 | n1 | ...] of `in` (segment s starts at s ? p0 + (s-1) p1 : 0, strides
+// padded to 4 ints), one 1024-thread block each; `out` has the same layout, with the segment total behind its n entries.
+// A warp owns 1024 consecutive ints of a 32k pass and reads them as 8 coalesced int4 rows (lane = 4 ints), carrying its
+// running sum from row to row; the 32 warp totals are scanned once per pass.
+#define SEG_ROWS 8
+__global__ void __launch_bounds__(1024) k_scan_segments(const int32_t* __restrict__ in, int32_t* __restrict__ out, int n0, int n1) {
   __shared__ int32_t wsum[32];
   __shared__ int32_t carry_s, tot_s;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int sgm = blockIdx.x;
+  const int n = sgm == 0 ? n0 : n1;
+  const int64_t off = sgm == 0 ? 0 : (int64_t)pad4(n0) + (int64_t)(sgm - 1) * pad4(n1);
+  in += off;
+  out += off;
   if (threadIdx.x == 0) carry_s = 0;
   __syncthreads();
-  for (int base = 0; base < n; base += 1024 * 8) {
+  for (int base = 0; base < n; base += 1024 * 4 * SEG_ROWS) {
     const int32_t carry = carry_s;
-    int i0 = base + threadIdx.x * 8;
-    int32_t v[8], s = 0;
+    const int wb = base + w * (128 * SEG_ROWS);
+    int4 v[SEG_ROWS];
+    int32_t ex[SEG_ROWS];
+    int32_t running = 0;
 #pragma unroll
-    for (int k = 0; k < 8; k++) { v[k] = (i0 + k < n) ? in[i0 + k] : 0; s += v[k]; }
-    int32_t inc = s;
+    for (int k = 0; k < SEG_ROWS; k++) {
+      const int i = wb + k * 128 + lane * 4;
+      v[k] = make_int4(0, 0, 0, 0);
+      if (i + 3 < n) v[k] = *reinterpret_cast<const int4*>(in + i);
+      else if (i < n) { v[k].x = in[i]; if (i + 1 < n) v[k].y = in[i + 1]; if (i + 2 < n) v[k].z = in[i + 2]; }
+      const int32_t t = v[k].x + v[k].y + v[k].z + v[k].w;
+      int32_t inc = t;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { int32_t t = __shfl_up_sync(FULL, inc, o); if (lane >= o) inc += t; }
-    if (lane == 31) wsum[w] = inc;
+      for (int o = 1; o < 32; o <<= 1) { int32_t u = __shfl_up_sync(FULL, inc, o); if (lane >= o) inc += u; }
+      ex[k] = running + inc - t;
+      running += __shfl_sync(FULL, inc, 31);
+    }
+    if (lane == 0) wsum[w] = running;
     __syncthreads();
     if (w == 0) {
       int32_t x = wsum[lane], xi = x;
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) { int32_t t = __shfl_up_sync(FULL, xi, o); if (lane >= o) xi += t; }
+      for (int o = 1; o < 32; o <<= 1) { int32_t u = __shfl_up_sync(FULL, xi, o); if (lane >= o) xi += u; }
       wsum[lane] = xi - x;            // exclusive warp offsets
-      if (lane == 31) tot_s = xi;     // chunk total
+      if (lane == 31) tot_s = xi;     // pass total
     }
     __syncthreads();
-    int32_t run = carry + wsum[w] + inc - s;
+    const int32_t b0 = carry + wsum[w];
 #pragma unroll
-    for (int k = 0; k < 8; k++) { if (i0 + k < n) out[i0 + k] = run; run += v[k]; }
+    for (int k = 0; k < SEG_ROWS; k++) {
+      const int i = wb + k * 128 + lane * 4;
+      const int32_t e0 = b0 + ex[k];
+      const int4 o4 = make_int4(e0, e0 + v[k].x, e0 + v[k].x + v[k].y, e0 + v[k].x + v[k].y + v[k].z);
+      if (i + 3 < n) *reinterpret_cast<int4*>(out + i) = o4;
+      else if (i < n) { out[i] = o4.x; if (i + 1 < n) out[i + 1] = o4.y; if (i + 2 < n) out[i + 2] = o4.z; }
+    }
     __syncthreads();
     if (threadIdx.x == 0) carry_s = carry + tot_s;
     __syncthreads();
@@ -962,7 +995,9 @@ __global__ void k_lat_scatter(const double* __restrict__ xyz, const int32_t* __r
                               const __grid_constant__ DevParams P, int32_t* __restrict__ cnt_all, const int32_t* __restrict__ off_all,
                               SAtom* __restrict__ sat) {
   const int64_t t0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t a = t0; a < B.nreal; a += stride) {
+  for (int64_t t = t0; t < B.nreal * LAT_SUB; t += stride) {
+    const int64_t a = t / LAT_SUB;
+    const int sub = (int)(t - a * LAT_SUB);
     int zz = Z[a];
     if (zz <= 0) continue;
     double x = xyz[3 * a], y = xyz[3 * a + 1], z = xyz[3 * a + 2];
@@ -970,7 +1005,7 @@ __global__ void k_lat_scatter(const double* __restrict__ xyz, const int32_t* __r
 #pragma unroll
     for (int d = 0; d < 3; d++) f[d] = lat_frac(x, y, z, B.ginv, d);
     const int e = ele_index(P, zz);
-    lat_enumerate(B, x, y, z, f, [&](int b, double xi, double yi, double zi, int cid) {
+    lat_enumerate(B, x, y, z, f, sub, [&](int b, double xi, double yi, double zi, int cid) {
       int p = atomicSub(&cnt_all[cid], 1) - 1;     // the counts run back to zero: arrival rank inside the cell
       SAtom r;
       r.x = xi; r.y = yi; r.z = zi;
@@ -981,23 +1016,24 @@ __global__ void k_lat_scatter(const double* __restrict__ xyz, const int32_t* __r
   }
 }
 
-// One warp per cell: order the records by slot id (removes the arrival nondeterminism), then give every centre of the
-// cell its row: rows are ordered by (element, cell, slot) and each element's range starts at a multiple of TM_ROW_TILE.
-// off_all = scan of [cell counts | centre counts per element]: off_all[cid] = first record of the cell,
-// off_all[(1+e) ncells + cid] - off_all[(1+e) ncells] = centres of element e in the cells before cid.
+// One warp per group of zdiv z bins (one cell edge of a column: ~10 atoms in liquid water): order the records of every bin
+// by slot id (removes the arrival nondeterminism), then give every centre of the group its row: rows are ordered by
+// (element, bin, slot) and each element's range starts at a multiple of TM_ROW_TILE.
+// off_all = the scans of k_scan_segments: off_all[cid] = first record of bin cid (ncells + 1 entries), then per element
+// offc_e[g] = centres of element e in the groups before g (ngroups + 1 entries, total last).
 __global__ void k_lat_sort_rows(const __grid_constant__ LatBin B, int n_ele, const int32_t* __restrict__ off_all, int32_t* __restrict__ cstart,
                                 SAtom* __restrict__ sat, int32_t* __restrict__ rowmeta, int32_t* __restrict__ rowslot, int32_t* __restrict__ rowsidx,
                                 int32_t* __restrict__ rowofslot, int64_t nrows, int32_t* __restrict__ flags) {
-  const int ncells = B.g.ncells;
+  const int ncells = B.g.ncells, zdiv = B.g.zdiv, ngroups = ncells / zdiv;
   const int lane = threadIdx.x & 31;
   const int warps = (gridDim.x * blockDim.x) >> 5;
-  // element row bases (every warp: n_ele <= 8 cached loads)
+  const int32_t* offc = off_all + pad4(ncells);      // element e: offc + e pad4(ngroups), ngroups + 1 entries
   int ebase[TM_MAX_ELE];
   {
     int base = 0, total = 0;
 #pragma unroll
     for (int e = 0; e < TM_MAX_ELE; e++) {
-      int cnt = (e < n_ele) ? off_all[(2 + e) * ncells] - off_all[(1 + e) * ncells] : 0;
+      int cnt = (e < n_ele) ? offc[e * pad4(ngroups) + ngroups] : 0;
       ebase[e] = base;
       if (blockIdx.x == 0 && threadIdx.x == 0) { rowmeta[2 * e] = base; rowmeta[2 * e + 1] = cnt; }
       base += ((cnt + TM_ROW_TILE - 1) / TM_ROW_TILE) * TM_ROW_TILE;
@@ -1005,23 +1041,28 @@ __global__ void k_lat_sort_rows(const __grid_constant__ LatBin B, int n_ele, con
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) { rowmeta[2 * TM_MAX_ELE] = total; rowmeta[2 * TM_MAX_ELE + 1] = base; }
   }
-  for (int cid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; cid <= ncells; cid += warps) {
-    if (cid == ncells) { if (lane == 0) cstart[ncells] = off_all[ncells]; continue; }
-    const int b = off_all[cid], e = off_all[cid + 1], n = e - b;
-    if (lane == 0) cstart[cid] = b;
+  for (int grp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; grp <= ngroups; grp += warps) {
+    if (grp == ngroups) { if (lane == 0) cstart[ncells] = off_all[ncells]; continue; }
+    const int c0 = grp * zdiv;
+    // bin boundaries of the group (zdiv <= 31): lane k holds off_all[c0 + k]
+    const int mybound = (lane <= zdiv) ? off_all[c0 + lane] : 0x7fffffff;
+    if (lane < zdiv) cstart[c0 + lane] = mybound;
+    const int b = __shfl_sync(FULL, mybound, 0), e = __shfl_sync(FULL, mybound, zdiv), n = e - b;
     if (n <= 0) continue;
-    if (n > 32) {     // dense cell: serial insertion sort by lane 0, then the generic tail below with one record per pass
+    if (n > 32) {     // dense group: serial insertion sort per bin by lane 0, then the passes below only assign rows
       if (lane == 0) {
-        for (int i = b + 1; i < e; i++) {
-          SAtom v = sat[i];
-          int j = i - 1;
-          while (j >= b && sat[j].slot > v.slot) { sat[j + 1] = sat[j]; j--; }
-          sat[j + 1] = v;
+        for (int k = 0; k < zdiv; k++) {
+          const int bb = off_all[c0 + k], be = off_all[c0 + k + 1];
+          for (int i = bb + 1; i < be; i++) {
+            SAtom v = sat[i];
+            int j = i - 1;
+            while (j >= bb && sat[j].slot > v.slot) { sat[j + 1] = sat[j]; j--; }
+            sat[j + 1] = v;
+          }
         }
       }
       __syncwarp();
     }
-    // centre rank bookkeeping per element across passes of 32 records
     int seen[TM_MAX_ELE];
 #pragma unroll
     for (int q = 0; q < TM_MAX_ELE; q++) seen[q] = 0;
@@ -1032,10 +1073,14 @@ __global__ void k_lat_sort_rows(const __grid_constant__ LatBin B, int n_ele, con
       if (lane < cnt) mine = sat[b + p0 + lane];
       int rank = lane;
       if (n <= 32) {
+        // sort key (bin, slot): the bin of a record is known from its position (the scatter pass filled bin by bin)
+        int bin = 0;
+        for (int k = 1; k < zdiv; k++) bin += (b + lane >= __shfl_sync(FULL, mybound, k)) ? 1 : 0;
+        const long long key = (lane < cnt) ? (((long long)bin << 32) | (unsigned int)mine.slot) : 0x7fffffffffffffffll;
         rank = 0;
         for (int k = 0; k < cnt; k++) {
-          int32_t other = __shfl_sync(FULL, mine.slot, k);
-          rank += (other < mine.slot) ? 1 : 0;
+          long long other = __shfl_sync(FULL, key, k);
+          rank += (other < key) ? 1 : 0;
         }
         __syncwarp();
         if (lane < cnt) sat[b + rank] = mine;
@@ -1052,7 +1097,7 @@ __global__ void k_lat_sort_rows(const __grid_constant__ LatBin B, int n_ele, con
         // centres of element q of this pass as a bit mask over SORTED positions: those below this record come first
         const unsigned mq = __reduce_or_sync(FULL, (centre && mine.e == q) ? (1u << rank) : 0u);
         if (centre && mine.e == q) {
-          int row = ebase[q] + (off_all[(1 + q) * ncells + cid] - off_all[(1 + q) * ncells]) + seen[q] + __popc(mq & ((1u << rank) - 1u));
+          int row = ebase[q] + offc[q * pad4(ngroups) + grp] + seen[q] + __popc(mq & ((1u << rank) - 1u));
           if (row < nrows) {
             rowslot[row] = mine.slot;
             rowsidx[row] = b + p0 + rank;
@@ -1070,13 +1115,14 @@ __global__ void k_lat_sort_rows(const __grid_constant__ LatBin B, int n_ele, con
 int tm_launch_lattice_bin(tm_ctx* c, const SysView& s) {
   int rc;
   const int n_ele = c->hp.n_ele;
-  const int64_t ncells = s.hgrid.ncells;
-  const int64_t nall = (1 + (int64_t)n_ele) * ncells;
+  const int64_t ncells = s.hgrid.ncells, ngroups = ncells / s.hgrid.zdiv;
+  auto hpad4 = [](int64_t n) { return (n + 4) & ~(int64_t)3; };
+  const int64_t nall = hpad4(ncells) + (int64_t)n_ele * hpad4(ngroups);
   if ((rc = tm_buf(c, c->b_pos, (size_t)s.nreal * 24))) return rc;
   if ((rc = tm_buf(c, c->b_Z, (size_t)s.nreal * 4))) return rc;
   if ((rc = tm_buf(c, c->b_natom, 8))) return rc;
   if ((rc = tm_buf(c, c->b_cntall, (size_t)(nall + 8) * 4))) return rc;
-  if ((rc = tm_buf(c, c->b_offall, (size_t)(nall + 8) * 4))) return rc;
+  if ((rc = tm_buf(c, c->b_offall, (size_t)(nall + n_ele + 8) * 4))) return rc;
   if ((rc = tm_buf(c, c->b_cstart, (size_t)(ncells + 8) * 4))) return rc;
   if ((rc = tm_buf(c, c->b_satom, (size_t)s.nslots * sizeof(SAtom)))) return rc;
   if ((rc = tm_buf(c, c->b_grid, sizeof(GridParams)))) return rc;
@@ -1097,22 +1143,18 @@ int tm_launch_lattice_bin(tm_ctx* c, const SysView& s) {
   int32_t* cnt_all = (int32_t*)c->b_cntall.p;
   int32_t* off_all = (int32_t*)c->b_offall.p;
   TM_CUDA(cudaMemsetAsync(cnt_all, 0, (size_t)(nall + 8) * 4, c->stream));
-  int blocks = (int)((std::max<int64_t>(s.nreal, s.nrows) + 255) / 256);
+  int blocks = (int)((std::max<int64_t>(s.nreal * LAT_SUB, s.nrows) + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
   k_lat_count<<<blocks, 256, 0, c->stream>>>(s.xyz_real, s.Z_real, B, c->hp, (double*)c->b_pos.p, (int32_t*)c->b_Z.p, (double*)c->b_natom.p,
                                              (GridParams*)c->b_grid.p, cnt_all, (int32_t*)c->b_flags.p, (int32_t*)c->b_rowslot.p, s.nrows,
                                              (int32_t*)c->b_rowofslot.p);
   c->launches++;
-  if (nall <= 262144) {
-    k_scan_block<<<1, 1024, 0, c->stream>>>(cnt_all, off_all, (int)nall);
-    c->launches++;
-  } else if ((rc = scan_exclusive(c, cnt_all, off_all, nall, (int32_t*)c->b_scan_tmp.p))) {
-    return rc;
-  }
-  int sblocks = (int)((s.nreal + 255) / 256);
+  k_scan_segments<<<1 + n_ele, 1024, 0, c->stream>>>(cnt_all, off_all, (int)ncells, (int)ngroups);
+  c->launches++;
+  int sblocks = (int)((s.nreal * LAT_SUB + 255) / 256);
   if (sblocks > 148 * 8) sblocks = 148 * 8;
   k_lat_scatter<<<sblocks, 256, 0, c->stream>>>(s.xyz_real, s.Z_real, B, c->hp, cnt_all, off_all, (SAtom*)c->b_satom.p);
-  int cblocks = (int)(((ncells + 1) * 32 + 255) / 256);
+  int cblocks = (int)(((ngroups + 1) * 32 + 255) / 256);
   if (cblocks > 148 * 16) cblocks = 148 * 16;
   k_lat_sort_rows<<<cblocks, 256, 0, c->stream>>>(B, n_ele, off_all, (int32_t*)c->b_cstart.p, (SAtom*)c->b_satom.p, (int32_t*)c->b_rowmeta.p,
                                                   (int32_t*)c->b_rowslot.p, (int32_t*)c->b_rowsidx.p, (int32_t*)c->b_rowofslot.p, s.nrows,

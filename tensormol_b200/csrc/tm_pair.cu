@@ -19,6 +19,13 @@
 // so the erfc/exp work runs on full warps.
 #include "tm_internal.h"
 #include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <utility>
+#include <vector>
 
 #define FULL 0xffffffffu
 #define PAIR_WARPS 8
@@ -63,7 +70,7 @@ __global__ void k_mol_sum(const double* __restrict__ v, const int32_t* __restric
 __global__ void k_charges(const double* __restrict__ qraw_slot, double* __restrict__ molacc, const double* __restrict__ inv_n,
                           const double* __restrict__ pos, const int32_t* __restrict__ Z, int64_t maxnatom, int64_t nq_per_mol,
                           double* __restrict__ q_slot, const SAtom* __restrict__ sat, const int32_t* __restrict__ cstart,
-                          const GridParams* __restrict__ gp, int64_t nreal, int periodic, float4* __restrict__ pq) {
+                          const GridParams* __restrict__ gp, int64_t nreal, int periodic, float4* __restrict__ pq, uint8_t* __restrict__ pe) {
   int m = blockIdx.y;
   double mean = molacc[16 * m + 4] * inv_n[m];
   double d0 = 0, d1 = 0, d2 = 0;
@@ -89,11 +96,15 @@ __global__ void k_charges(const double* __restrict__ qraw_slot, double* __restri
   // (2): every binned atom has Z > 0, so its charge is qraw - mean (the value (1) stores for its slot)
   GridParams g = *gp;
   int ib = cstart[m * g.ncell_mol], ie = cstart[(m + 1) * g.ncell_mol];
+  // positions relative to the CENTRE of the grid (halves the magnitude, i.e. the fp32 rounding step: 3.8e-6 A for a 92 A grid)
+  const double mx = g.ox + 0.5 * g.gx * g.cell, my = g.oy + 0.5 * g.gy * g.cell, mz = g.oz + 0.5 * g.gz * g.zcell;
   for (int i = ib + blockIdx.x * blockDim.x + threadIdx.x; i < ie; i += gridDim.x * blockDim.x) {
     SAtom a = sat[i];
     int64_t s = a.slot;
-    if (periodic) s = s % nreal;
-    pq[i] = make_float4((float)(a.x - g.ox), (float)(a.y - g.oy), (float)(a.z - g.oz), (float)(qraw_slot[s] - mean));
+    bool img = false;
+    if (periodic) { img = s >= nreal; s = s % nreal; }
+    pq[i] = make_float4((float)(a.x - mx), (float)(a.y - my), (float)(a.z - mz), (float)(qraw_slot[s] - mean));
+    pe[i] = (uint8_t)((a.e & 7) | (img ? 0x80 : 0));
   }
 }
 
@@ -103,6 +114,7 @@ int tm_launch_charges(tm_ctx* c, const SysView& s) {
   int64_t nq_per_mol = s.periodic ? s.nreal : s.maxnatom;
   if ((rc = tm_buf(c, c->b_q, (size_t)nq * 8 * 2))) return rc;  // [qraw_slot | q_slot]
   if ((rc = tm_buf(c, c->b_qs, (size_t)s.nslots * 16))) return rc;
+  if ((rc = tm_buf(c, c->b_pe, (size_t)s.nslots))) return rc;
   double* qraw = (double*)c->b_q.p;
   double* q = qraw + nq;
   // molacc (zeroed by the caller at the start of the evaluation), stride 16 doubles per molecule:
@@ -126,7 +138,7 @@ int tm_launch_charges(tm_ctx* c, const SysView& s) {
   dim3 g((unsigned)std::max<int64_t>(1, std::min<int64_t>((per_mol + 255) / 256, 148 * 8)), (unsigned)s.nmol);
   k_charges<<<g, 256, 0, c->stream>>>(qraw, molacc, (const double*)c->b_natom.p, (const double*)c->b_pos.p, (const int32_t*)c->b_Z.p, s.maxnatom,
                                       nq_per_mol, q, (const SAtom*)c->b_satom.p, (const int32_t*)c->b_cstart.p, (const GridParams*)c->b_grid.p, s.nreal,
-                                      s.periodic, (float4*)c->b_qs.p);
+                                      s.periodic, (float4*)c->b_qs.p, (uint8_t*)c->b_pe.p);
   c->launches++;
   TM_CUDA(cudaGetLastError());
   return TM_OK;
@@ -231,12 +243,14 @@ k_pair(const SAtom* __restrict__ sat, const float4* __restrict__ pq, const int32
   if (lane < TM_MAX_ELE) { s_c6[warp][lane] = P.pk_c6[ei][lane]; s_rs12[warp][lane] = P.pk_rs12[ei][lane]; }
   __syncwarp();
   int m = (int)(slot / maxnatom);
-  float cell = (float)g.cell, icell = (float)g.inv_cell;
+  float cell = (float)g.cell, icell = (float)g.inv_cell, izcell = (float)g.inv_zcell;
   float rc2 = cutoff_A * cutoff_A;
   const unsigned lt_mask = (1u << lane) - 1u;
+  // the candidate records are relative to the grid centre; the column arithmetic wants the origin
+  const float ox_ = (float)(ci.x - g.ox), oy_ = (float)(ci.y - g.oy), oz_ = (float)(ci.z - g.oz);
   // cell columns that can hold a partner, from the centre's actual position (not its cell): |dx| <= rc
-  int x0 = max(0, (int)floorf((pi.x - cutoff_A) * icell)), x1 = min(g.gx - 1, (int)floorf((pi.x + cutoff_A) * icell));
-  int y0 = max(0, (int)floorf((pi.y - cutoff_A) * icell)), y1 = min(g.gy - 1, (int)floorf((pi.y + cutoff_A) * icell));
+  int x0 = max(0, (int)floorf((ox_ - cutoff_A) * icell)), x1 = min(g.gx - 1, (int)floorf((ox_ + cutoff_A) * icell));
+  int y0 = max(0, (int)floorf((oy_ - cutoff_A) * icell)), y1 = min(g.gy - 1, (int)floorf((oy_ + cutoff_A) * icell));
   int ny = y1 - y0 + 1, ncol = (x1 - x0 + 1) * ny;
   PairAcc A = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   int qn = 0;
@@ -255,12 +269,12 @@ k_pair(const SAtom* __restrict__ sat, const float4* __restrict__ pq, const int32
     int cidx = (c0 + lane) * split + sub;
     if (cidx < ncol) {
       int x = x0 + cidx / ny, y = y0 + cidx % ny;
-      float lx = fmaxf(0.f, fmaxf(x * cell - pi.x, pi.x - (x + 1) * cell));   // distance from the centre to the column's slab in x
-      float ly = fmaxf(0.f, fmaxf(y * cell - pi.y, pi.y - (y + 1) * cell));
+      float lx = fmaxf(0.f, fmaxf(x * cell - ox_, ox_ - (x + 1) * cell));   // distance from the centre to the column's slab in x
+      float ly = fmaxf(0.f, fmaxf(y * cell - oy_, oy_ - (y + 1) * cell));
       float rem = rc2 - lx * lx - ly * ly;
       if (rem > 0.f) {
         float zr = sqrtf(rem);
-        int z0 = max(0, (int)floorf((pi.z - zr) * icell)), z1 = min(g.gz - 1, (int)floorf((pi.z + zr) * icell));
+        int z0 = max(0, (int)floorf((oz_ - zr) * izcell)), z1 = min(g.gz - 1, (int)floorf((oz_ + zr) * izcell));
         if (z1 >= z0) {
           int cbase = m * g.ncell_mol + (x * g.gy + y) * g.gz;
           cb = cstart[cbase + z0];
@@ -345,6 +359,287 @@ k_pair(const SAtom* __restrict__ sat, const float4* __restrict__ pq, const int32
   }
 }
 
+// ---- table-driven pair kernel -------------------------------------------------------------------
+// The pair energy is  e_ij = q_i q_j kappa(s) + w_p(s)  with s = r^2 (Angstrom^2) and p the element-pair type.  kappa and
+// the w_p are tabulated on the host in float64 as cubic Hermite pieces on a grid that is uniform in the BITS of the fp32
+// value of s: node k <-> s_k = float((k + kmin) << 17), i.e. 64 nodes per octave of s (1.1 % spacing in r at every
+// distance: 640 nodes from r = 0.5 A to 16 A).  A piece holds (c0, c1, c2, c3) with f(s_k + u) = c0 + u (c1 + u (c2 + u c3));
+// the force needs df/ds = c1 + u (2 c2 + 3 c3 u) only, because  d e_ij / d x_i = -2 (x_j - x_i) de/ds: no square root, no
+// reciprocal, no exponential per pair (the analytic form costs ~110 instructions and 3 MUFU per pair, this one ~40).
+// Interpolation error < 3e-7 relative (checked at build time against the analytic values at the piece mid-points).  The
+// two pieces that contain a kink of the reference's potentials -- the ELU / DSF switch at Elu_Width (RawSymFunc.py:1353)
+// and the end of the vdW polynomial switch (RawSymFunc.py:1391-1393), both continuous in value and slope only -- and
+// anything closer than 0.5 A are evaluated analytically (pair_eval above).
+#define PT_SHIFT 17
+#define PT_SMIN 0.25f
+#define PT_SMAX 256.0f
+
+struct PairTabMeta { int kmin, nnodes, nfn, kink_k, kink_v; };
+
+static void pair_fn_host(const tm_params& p, int fn, const int* ei_ej, double s, double* f, double* dfds) {
+  const double B = TM_BOHRPERA;
+  const double r = sqrt(s);
+  if (fn == 0) {      // kappa(R), R = B r  (TFCoulombEluSRDSFLR, RawSymFunc.py:1307-1359)
+    const double R = B * r, alpha = p.dsf_alpha / B, Rl = p.ee_cutoff_off * B, Rs = p.elu_width * B;
+    const double Zc = erfc(alpha * Rl) / Rl, Yc = 1.1283791671 * alpha * exp(-alpha * alpha * Rl * Rl) / Rl;
+    double k = 0.0, dk = 0.0;
+    if (R > Rs) {
+      if (R <= Rl) {
+        k = erfc(alpha * R) / R - Zc + (R - Rl) * (Zc / Rl + Yc);
+        dk = -erfc(alpha * R) / (R * R) - M_2_SQRTPI * alpha * exp(-alpha * alpha * R * R) / R + (Zc / Rl + Yc);
+      }
+    } else {
+      k = p.elu_alpha * (exp(R - Rs) - 1.0) + p.elu_shift;
+      dk = p.elu_alpha * exp(R - Rs);
+    }
+    *f = k;
+    *dfds = dk * B / (2.0 * r);
+    return;
+  }
+  // w(R'), R' = B^2 r: the reference scales coordinates that are already in Bohr once more (TFVdwPolyLR, RawSymFunc.py:1377)
+  const double Rp = B * B * r, pw = p.poly_width * B, t = Rp / pw;
+  const double c6 = sqrt(p.C6[ei_ej[0]]) * sqrt(p.C6[ei_ej[1]]), Rsum = p.Rvdw[ei_ej[0]] + p.Rvdw[ei_ej[1]];
+  double S = 1.0, dS = 0.0;
+  if (t <= 0.0) { S = 0.0; }
+  else if (t <= 1.0) { S = t * t * (3.0 - 2.0 * t); dS = 6.0 * t * (1.0 - t) / pw; }
+  const double ff = c6 / pow(Rp, 6.0), X = 6.0 * pow(Rsum / Rp, 12.0), g = 1.0 / (1.0 + X);
+  *f = -S * ff * g;
+  const double dw = -(dS * ff * g + S * (-6.0 * ff / Rp) * g + S * ff * (12.0 * X * g * g / Rp));
+  *dfds = dw * B * B / (2.0 * r);
+}
+
+static inline float pt_node_s(int k) {
+  uint32_t b = (uint32_t)k << PT_SHIFT;
+  float f;
+  memcpy(&f, &b, 4);
+  return f;
+}
+static inline int pt_node_of(float s) {
+  uint32_t b;
+  memcpy(&b, &s, 4);
+  return (int)(b >> PT_SHIFT);
+}
+
+// (re)builds the device tables when the hyper-parameters changed; leaves pt_nfn = 0 when they would not fit
+static int pair_tables(tm_ctx* c) {
+  if (c->pairtab_gen == c->params_gen) return TM_OK;
+  const tm_params& p = c->params;
+  const int n_ele = c->desc.n_ele, n_elep = n_ele * (n_ele + 1) / 2, nfn = 1 + n_elep;
+  const int kmin = pt_node_of(PT_SMIN), kmax = pt_node_of(PT_SMAX);
+  const int nnodes = kmax - kmin;
+  c->pt_nfn = 0;
+  c->pairtab_gen = c->params_gen;
+  if ((size_t)nnodes * nfn * 16 > 150 * 1024) return TM_OK;          // analytic kernel instead (more than 4 elements)
+  if (p.ee_cutoff_off * p.ee_cutoff_off >= PT_SMAX * 0.999 || p.ee_cutoff_off < 1.0) return TM_OK;
+  std::vector<float> tab((size_t)nnodes * nfn * 4);
+  double worst = 0.0;
+  for (int fn = 0; fn < nfn; fn++) {
+    int ee[2] = {0, 0};
+    if (fn > 0) {
+      int l = 0;
+      for (int i = 0; i < n_ele; i++)
+        for (int j = i; j < n_ele; j++, l++)
+          if (l == fn - 1) { ee[0] = i; ee[1] = j; }
+    }
+    const double rc2 = p.ee_cutoff_off * p.ee_cutoff_off, sk = p.elu_width * p.elu_width, rv0 = p.poly_width / TM_BOHRPERA, sv = rv0 * rv0;
+    // error measure: |error| weighted by s = r^2 (the number of partners grows like r^2 dr) against the largest s |f|
+    double scale = 1e-300;
+    for (int k = 0; k <= nnodes; k++) {
+      const double s0 = pt_node_s(k + kmin);
+      double f0, d0;
+      if (s0 > rc2) break;
+      pair_fn_host(p, fn, ee, s0, &f0, &d0);
+      scale = std::max(scale, s0 * fabs(f0));
+    }
+    for (int k = 0; k < nnodes; k++) {
+      const double s0 = pt_node_s(k + kmin), s1 = pt_node_s(k + kmin + 1), h = s1 - s0;
+      double f0, d0, f1, d1;
+      pair_fn_host(p, fn, ee, s0, &f0, &d0);
+      pair_fn_host(p, fn, ee, s1, &f1, &d1);
+      const double c2 = (3.0 * (f1 - f0) / h - 2.0 * d0 - d1) / h, c3 = (2.0 * (f0 - f1) / h + d0 + d1) / (h * h);
+      float* t = &tab[((size_t)fn * nnodes + k) * 4];
+      t[0] = (float)f0; t[1] = (float)d0; t[2] = (float)c2; t[3] = (float)c3;
+      // accuracy inside the piece (pieces with a kink are replaced by the analytic path, see the kernel)
+      const bool kink = (fn == 0) ? (s0 < sk && sk <= s1) : (s0 < sv && sv <= s1);
+      if (kink || s0 >= rc2) continue;
+      for (int q = 1; q < 4; q++) {
+        double fm, dm, u = 0.25 * q * h;
+        pair_fn_host(p, fn, ee, s0 + u, &fm, &dm);
+        worst = std::max(worst, (s0 + u) * fabs(f0 + u * (d0 + u * (c2 + u * c3)) - fm) / scale);
+      }
+    }
+  }
+  if (getenv("TM_TRACE")) fprintf(stderr, "[tm_trace] pair tables: %d nodes x %d functions, weighted interpolation error %.2e\n", nnodes, nfn, worst);
+  if (!(worst < 1e-6)) return TM_OK;     // unusual parameters: keep the analytic kernel
+  int rc;
+  if ((rc = tm_buf(c, c->b_pairtab, tab.size() * 4))) return rc;
+  TM_CUDA(cudaMemcpyAsync(c->b_pairtab.p, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice, c->stream));
+  TM_CUDA(cudaStreamSynchronize(c->stream));
+  c->pt_kmin = kmin; c->pt_nnodes = nnodes; c->pt_nfn = nfn;
+  c->pt_kink_k = pt_node_of((float)(p.elu_width * p.elu_width)) - kmin;
+  const double rv = p.poly_width / TM_BOHRPERA;
+  c->pt_kink_v = pt_node_of((float)(rv * rv)) - kmin;
+  return TM_OK;
+}
+
+// Persistent CTAs (the tables are staged once per CTA); warps take centres round-robin.  Per centre the cell columns that
+// can hold a partner are resolved one per lane (z-range from the centre's actual position: ONE contiguous run of the
+// cell-sorted copy per column), the non-empty runs of 32 columns are laid end to end as one flat index space, and the
+// warp walks that space 32 candidates at a time: fp32 distance test on the float4 record, then the table evaluation
+// right there under the predicate (two thirds of the candidates are inside the sphere with the fine z bins of the
+// lattice path, so compacting the survivors first would cost more than the idle lanes do).
+template <bool ECC, bool VDW>
+__global__ void __launch_bounds__(PAIR_WARPS * 32)
+k_pair_tab(const SAtom* __restrict__ sat, const float4* __restrict__ pq, const uint8_t* __restrict__ pe, const int32_t* __restrict__ cstart,
+           const GridParams* __restrict__ gp, const int32_t* __restrict__ rowsidx, const int32_t* __restrict__ rowslot, int64_t nrows,
+           int64_t maxnatom, const __grid_constant__ DevParams P, const __grid_constant__ PairTabMeta M, const float4* __restrict__ tab_g,
+           int do_force, float cutoff_A, int split, double* __restrict__ dedq_slot, float* __restrict__ F, double* __restrict__ molacc) {
+  extern __shared__ float4 s_tab[];                    // [nfn][nnodes]: a warp's 32 random nodes spread over all banks
+  __shared__ int8_t s_fn[TM_MAX_ELE][TM_MAX_ELE];      // table of the vdW function of an element pair
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < M.nnodes * M.nfn; i += blockDim.x) s_tab[i] = tab_g[i];
+  if (threadIdx.x < TM_MAX_ELE * TM_MAX_ELE) s_fn[threadIdx.x / TM_MAX_ELE][threadIdx.x % TM_MAX_ELE] = (int8_t)(1 + P.pair_index[threadIdx.x / TM_MAX_ELE][threadIdx.x % TM_MAX_ELE]);
+  __syncthreads();
+  const GridParams g = *gp;
+  const float cell = (float)g.cell, icell = (float)g.inv_cell, izcell = (float)g.inv_zcell;
+  const float rc2 = cutoff_A * cutoff_A;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  const float w_img = (do_force & 2) ? 1.0f : 0.5f;    // see k_pair
+  const int kmin = M.kmin, kink_k = M.kink_k, kink_v = M.kink_v, nnodes = M.nnodes;
+  const int64_t nwork = nrows * split;
+  for (int64_t gw = (int64_t)blockIdx.x * PAIR_WARPS + warp; gw < nwork; gw += (int64_t)gridDim.x * PAIR_WARPS) {
+    const int64_t row = gw / split;
+    const int sub = (int)(gw - row * split);
+    const int slot = rowslot[row];
+    if (slot < 0) continue;
+    const int si = rowsidx[row];
+    const SAtom ci = sat[si];
+    const float4 pi = pq[si];
+    const float qi = pi.w;
+    const int ei = ci.e;
+    const int m = (int)(slot / maxnatom);
+    const float ox_ = (float)(ci.x - g.ox), oy_ = (float)(ci.y - g.oy), oz_ = (float)(ci.z - g.oz);
+    int x0 = max(0, (int)floorf((ox_ - cutoff_A) * icell)), x1 = min(g.gx - 1, (int)floorf((ox_ + cutoff_A) * icell));
+    int y0 = max(0, (int)floorf((oy_ - cutoff_A) * icell)), y1 = min(g.gy - 1, (int)floorf((oy_ + cutoff_A) * icell));
+    const int ny = y1 - y0 + 1, ncol = (x1 - x0 + 1) * ny;
+    const int8_t* fnrow = s_fn[ei];
+    PairAcc A = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int c0 = 0; c0 * split < ncol; c0 += 32) {
+      int cb = 0, len = 0;
+      const int cidx = (c0 + lane) * split + sub;
+      if (cidx < ncol) {
+        int x = x0 + cidx / ny, y = y0 + cidx % ny;
+        float lx = fmaxf(0.f, fmaxf(x * cell - ox_, ox_ - (x + 1) * cell));
+        float ly = fmaxf(0.f, fmaxf(y * cell - oy_, oy_ - (y + 1) * cell));
+        float rem = rc2 - lx * lx - ly * ly;
+        if (rem > 0.f) {
+          float zr = sqrtf(rem);
+          int z0 = max(0, (int)floorf((oz_ - zr) * izcell)), z1 = min(g.gz - 1, (int)floorf((oz_ + zr) * izcell));
+          if (z1 >= z0) {
+            int cbase = m * g.ncell_mol + (x * g.gy + y) * g.gz;
+            cb = cstart[cbase + z0];
+            len = cstart[cbase + z1 + 1] - cb;
+          }
+        }
+      }
+      // pack the non-empty runs into the low lanes, then lay them end to end: lane c holds run c as [endv - len, endv)
+      const unsigned live = __ballot_sync(FULL, len > 0);
+      const int nlive = __popc(live);
+      if (nlive == 0) continue;
+      {
+        const int src = (lane < nlive) ? __fns(live, 0, lane + 1) : 0;
+        const int cb2 = __shfl_sync(FULL, cb, src), len2 = __shfl_sync(FULL, len, src);
+        cb = cb2;
+        len = (lane < nlive) ? len2 : 0;
+      }
+      int endv = len;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(FULL, endv, o);
+        if (lane >= o) endv += t;
+      }
+      const int T = __shfl_sync(FULL, endv, 31);
+      const int offv = cb - (endv - len);          // j = flat index + offv
+      int c = 0;                                   // run of this lane's flat index (monotone over the passes)
+      for (int f0 = 0; f0 < T; f0 += 32) {
+        const int idx = f0 + lane;
+        const bool valid = idx < T;
+        // advance to the run that holds idx: a few probes (runs are ~40 long), more only behind very short runs
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+          int e = __shfl_sync(FULL, endv, c);
+          c += (valid && idx >= e) ? 1 : 0;
+        }
+        for (;;) {   // (the shuffle is evaluated by every lane: never put a *_sync intrinsic behind a short-circuit)
+          const int e = __shfl_sync(FULL, endv, c);
+          const bool more = valid && idx >= e;
+          if (!__any_sync(FULL, more)) break;
+          c += more ? 1 : 0;
+        }
+        const int j = idx + __shfl_sync(FULL, offv, c);
+        float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
+        float d2 = 3.0e38f;
+        if (valid && j != si) {
+          d = pq[j];
+          d.x -= pi.x; d.y -= pi.y; d.z -= pi.z;
+          d2 = fmaf(d.x, d.x, fmaf(d.y, d.y, d.z * d.z));
+        }
+        if (d2 < rc2) {
+          const int pej = pe[j];
+          const int ej = pej & 7;
+          const float wj = (pej & 0x80) ? w_img : 1.0f;
+          const uint32_t bits = __float_as_uint(d2);
+          const int idn = (int)(bits >> PT_SHIFT) - kmin;
+          if (idn < 0 || idn == kink_k || idn == kink_v) {       // closer than 0.5 A, or a piece with a kink: analytic
+            pair_eval<ECC, VDW>(P, d2, d.x, d.y, d.z, qi, d.w, P.pk_c6[ei][ej], P.pk_rs12[ei][ej], wj, A);
+          } else {
+            const float u = d2 - __uint_as_float(bits & (0xffffffffu << PT_SHIFT));
+            const float4* node = s_tab + idn;
+            float deds = 0.f;
+            if (ECC) {
+              const float4 k = node[0];
+              const float kap = fmaf(u, fmaf(u, fmaf(u, k.w, k.z), k.y), k.x);
+              const float dk = fmaf(u, fmaf(u, 3.0f * k.w, 2.0f * k.z), k.y);
+              const float qq = qi * d.w;
+              A.ecc = fmaf(qq, kap, A.ecc);
+              A.dedq = fmaf(d.w, kap, A.dedq);
+              deds = qq * dk;
+            }
+            if (VDW) {
+              const float4 v = node[fnrow[ej] * nnodes];
+              A.evdw += fmaf(u, fmaf(u, fmaf(u, v.w, v.z), v.y), v.x);
+              deds += fmaf(u, fmaf(u, 3.0f * v.w, 2.0f * v.z), v.y);
+            }
+            const float sc = -2.0f * wj * deds;          // d e / d x_i = de/ds * d s / d x_i = -2 (x_j - x_i) de/ds
+            A.gx = fmaf(sc, d.x, A.gx); A.gy = fmaf(sc, d.y, A.gy); A.gz = fmaf(sc, d.z, A.gz);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      A.ecc += __shfl_xor_sync(FULL, A.ecc, o);
+      A.evdw += __shfl_xor_sync(FULL, A.evdw, o);
+      A.dedq += __shfl_xor_sync(FULL, A.dedq, o);
+      A.gx += __shfl_xor_sync(FULL, A.gx, o);
+      A.gy += __shfl_xor_sync(FULL, A.gy, o);
+      A.gz += __shfl_xor_sync(FULL, A.gz, o);
+    }
+    if (lane == 0) {
+      if (split == 1) dedq_slot[slot] = (double)A.dedq;
+      else atomicAdd(&dedq_slot[slot], (double)A.dedq);   // zeroed by the launcher
+      if (do_force & 1) {
+        atomicAdd(F + 3 * (int64_t)slot, A.gx);
+        atomicAdd(F + 3 * (int64_t)slot + 1, A.gy);
+        atomicAdd(F + 3 * (int64_t)slot + 2, A.gz);
+      }
+      atomicAdd(&molacc[16 * m + 2], 0.5 * (double)A.ecc);
+      atomicAdd(&molacc[16 * m + 3], 0.5 * (double)A.evdw);
+      atomicAdd(&molacc[16 * m + 5], (double)A.dedq);
+    }
+  }
+}
+
 int tm_launch_pair(tm_ctx* c, const SysView& s, int flags) {
   int rc;
   int64_t nq = s.periodic ? s.nreal : s.nslots;
@@ -363,6 +658,36 @@ int tm_launch_pair(tm_ctx* c, const SysView& s, int flags) {
                                                     (float)c->params.ee_cutoff_off, split, (double*)c->b_dedq.p, (float*)c->b_F.p, (double*)c->b_molacc.p);
   };
   bool ecc = c->hp.add_ecc != 0, vdw = (flags & TM_F_VDW) != 0;
+  static const bool analytic_only = getenv("TM_PAIR_ANALYTIC") != nullptr;   // measurements / tests of the analytic kernel
+  if ((rc = pair_tables(c))) return rc;
+  if (c->pt_nfn > 0 && !analytic_only && (ecc || vdw)) {
+    PairTabMeta M{c->pt_kmin, c->pt_nnodes, c->pt_nfn, c->pt_kink_k, c->pt_kink_v};
+    const size_t smem = (size_t)M.nnodes * M.nfn * 16;
+    auto launch_tab = [&](auto kern) -> int {
+      // per kernel AND device (the three instantiations share this lambda body: same pointer type)
+      static std::map<std::pair<const void*, int>, size_t> conf;
+      size_t& have = conf[std::make_pair((const void*)kern, c->device)];
+      if (smem > have) {
+        TM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        have = smem;
+      }
+      int occ = 1, sms = 148;
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, PAIR_WARPS * 32, smem);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
+      int grid = std::max(1, std::min(blocks, sms * std::max(1, occ)));
+      kern<<<grid, PAIR_WARPS * 32, smem, c->stream>>>((const SAtom*)c->b_satom.p, (const float4*)c->b_qs.p, (const uint8_t*)c->b_pe.p,
+                                                      (const int32_t*)c->b_cstart.p, (const GridParams*)c->b_grid.p, (const int32_t*)c->b_rowsidx.p,
+                                                      (const int32_t*)c->b_rowslot.p, s.nrows, s.maxnatom, c->hp, M, (const float4*)c->b_pairtab.p,
+                                                      ((flags & TM_F_FORCE) ? 1 : 0) | ((flags & TM_F_FOLD_IMAGES) ? 2 : 0), (float)c->params.ee_cutoff_off,
+                                                      split, (double*)c->b_dedq.p, (float*)c->b_F.p, (double*)c->b_molacc.p);
+      c->launches++;
+      TM_CUDA(cudaGetLastError());
+      return TM_OK;
+    };
+    if (ecc && vdw) return launch_tab(k_pair_tab<true, true>);
+    if (ecc) return launch_tab(k_pair_tab<true, false>);
+    return launch_tab(k_pair_tab<false, true>);
+  }
   if (ecc && vdw) launch(k_pair<true, true>);
   else if (ecc) launch(k_pair<true, false>);
   else if (vdw) launch(k_pair<false, true>);

@@ -363,6 +363,25 @@ def test_eval_lattice_triclinic_windowed_binning(nx, shear):
         _check_grad(r2["gradient"][0], o["gradient"][0, :nreal])
 
 
+@pytest.mark.parametrize("delta", [-1e-4, -2e-6, 2e-6, 1e-4])
+def test_ee_cutoff_boundary_pair_set_has_no_energy_effect(delta):
+    """The 15 A electrostatics pair SET is decided in fp32 on the device (reference: float64, strict, MolEmb.cpp:1217-1218).
+    A pair that sits on the boundary may therefore be kept or dropped differently -- the DSF kernel and its slope vanish at
+    EECutoffOff and the C6 tail is 5e-10 Hartree there, so this must not be visible: both sides of the boundary against the
+    oracle, energies at the usual tolerance with a 1e-9 Hartree floor, forces at 1e-7 Hartree/Bohr."""
+    from oracle import oracle_graph as og
+    eng, W, P = _engine([1, 8], [32, 32], 2)
+    d = P["EECutoffOff"] + delta
+    X = np.array([[[0.0, 0.0, 0.0], [0.7, 0.6, 0.0], [-0.7, 0.6, 0.0],
+                   [d, 0.0, 0.0], [d + 0.7, 0.6, 0.0], [d - 0.25, -0.9, 0.0]]])
+    Z = np.array([[8, 1, 1, 8, 1, 1]], np.int32)
+    r = eng.evaluate(X, Z, np.array([6]))
+    o = og.Oracle([1, 8], W, P).evaluate(X, Z, np.array([6]))
+    for k in ("Etotal", "Ecc", "Evdw"):
+        assert abs(r[k][0] - o[k][0]) <= ENERGY_RTOL * abs(o[k][0]) + 1e-9, (k, r[k], o[k])
+    assert np.abs(grad_ha_bohr(r["gradient"]) - grad_ha_bohr(o["gradient"])).max() <= 1e-6
+
+
 def test_graph_replay_equals_eager_device_call():
     """engine.GraphedCall: the captured tm_eval_lattice_dev step, replayed after the positions were changed in place,
     gives the numbers of an eager call on the new positions."""
