@@ -355,7 +355,10 @@ class TFMolManage:
         (2 ntess+1)^3 image blocks are generated on the GPU (tm_eval_lattice)."""
         self.Instances.refresh()
         nreal = len(atoms)
-        r = self.Instances.engine.evaluate_lattice(coords_wrapped, np.asarray(atoms, np.int32), lattice, int(ntess), do_force=DoForce, has_vdw=True)
+        # only what this call returns crosses the bus (the reference returns Etotal, force[, charge]: TFMolManage.py:1353-1358)
+        want = ("Etotal",) + (("gradient",) if DoForce else ()) + (("charge",) if DoCharge else ())
+        r = self.Instances.engine.evaluate_lattice(coords_wrapped, np.asarray(atoms, np.int32), lattice, int(ntess), do_force=DoForce, has_vdw=True,
+                                                   outputs=want)
         if not DoForce:
             return r["Etotal"]
         F = -JOULEPERHARTREE * r["gradient"][0].reshape(1, nreal, 3)   # noqa: F405

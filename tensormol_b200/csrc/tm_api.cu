@@ -573,13 +573,34 @@ static int check_flags(tm_ctx* c) {
 }
 
 static int validate_Z(tm_ctx* c, const int32_t* Z, int64_t n) {
+  bool known[256] = {};
+  for (int k = 0; k < c->desc.n_ele; k++)
+    if (c->desc.eles[k] > 0 && c->desc.eles[k] < 256) known[c->desc.eles[k]] = true;
   for (int64_t i = 0; i < n; i++) {
     int z = Z[i];
     if (z <= 0) continue;
-    bool ok = false;
-    for (int k = 0; k < c->desc.n_ele; k++) ok |= (c->desc.eles[k] == z);
-    if (!ok) { tm_set_error("atomic number %d (slot %lld) is not in the model's element list", z, (long long)i); return TM_EINVAL; }
+    if (z > 255 || !known[z]) { tm_set_error("atomic number %d (slot %lld) is not in the model's element list", z, (long long)i); return TM_EINVAL; }
   }
+  return TM_OK;
+}
+
+// which per-atom blocks of the packed output the caller asked for (bit 0 Ebp_atom, 1 charge, 2 gradient): only those
+// cross the bus (the reference's periodic callback returns Etotal and the force, TFMolManage.py:1353-1358)
+static int out_mask(int flags, const tm_outputs* out) {
+  return (out->Ebp_atom ? 1 : 0) | (out->charge ? 2 : 0) | ((out->gradient && (flags & TM_F_FORCE)) ? 4 : 0);
+}
+// D2H of the energies (always) and the requested blocks, each to its own offset of the pinned staging buffer
+static int copy_packed_d2h(tm_ctx* c, const OutLayout& o, int mask) {
+  char* hs = (char*)c->h_stage;
+  const char* d = (const char*)c->b_out.p;
+  TM_CUDA(cudaMemcpyAsync(hs, d, (size_t)7 * o.nmol * 8, cudaMemcpyDeviceToHost, c->stream));
+  if (mask == 7) {   // everything: one copy
+    TM_CUDA(cudaMemcpyAsync(hs + o.off_ebp_atom * 8, d + o.off_ebp_atom * 8, (size_t)(o.total - o.off_ebp_atom) * 8, cudaMemcpyDeviceToHost, c->stream));
+    return TM_OK;
+  }
+  if (mask & 1) TM_CUDA(cudaMemcpyAsync(hs + o.off_ebp_atom * 8, d + o.off_ebp_atom * 8, (size_t)o.nq * 8, cudaMemcpyDeviceToHost, c->stream));
+  if (mask & 2) TM_CUDA(cudaMemcpyAsync(hs + o.off_charge * 8, d + o.off_charge * 8, (size_t)o.nq * 8, cudaMemcpyDeviceToHost, c->stream));
+  if (mask & 4) TM_CUDA(cudaMemcpyAsync(hs + o.off_grad * 8, d + o.off_grad * 8, (size_t)3 * o.nq * 8, cudaMemcpyDeviceToHost, c->stream));
   return TM_OK;
 }
 
@@ -591,7 +612,7 @@ static int deliver(tm_ctx* c, const SysView& s, int flags, const OutLayout& o, t
   size_t bytes = (size_t)o.total * 8;
   size_t dbytes = (flags & TM_F_DESCRIPTORS) && out->descriptors ? (size_t)o.nq * c->hp.D * 4 : 0;
   if ((rc = tm_host_stage(c, bytes + dbytes))) return rc;
-  TM_CUDA(cudaMemcpyAsync(c->h_stage, c->b_out.p, bytes, cudaMemcpyDeviceToHost, c->stream));
+  if ((rc = copy_packed_d2h(c, o, out_mask(flags, out)))) return rc;
   if (dbytes) {
     if ((rc = tm_buf(c, c->b_acc, dbytes))) return rc;
     k_desc_out<<<(unsigned)o.nq, 128, 0, c->stream>>>((const float*)c->b_G.p, (const int32_t*)c->b_rowofslot.p, o.nq, c->hp.D, c->hp.Dp, (float*)c->b_acc.p);
@@ -860,11 +881,12 @@ static int eval_lattice_impl(tm_ctx* c, const double* xyz, const int32_t* Z, int
 static int lattice_graph_call(tm_ctx* c, const double* xyz, const int32_t* Z, int64_t nreal, const double* lattice, int ntess, int flags,
                               tm_outputs* out) {
   tm_ctx::LatGraph& G = c->lg;
-  bool same = G.nreal == nreal && G.ntess == ntess && G.flags == flags && G.cfg_gen == c->cfg_gen && G.alloc_gen == c->alloc_gen &&
-              memcmp(G.lat, lattice, 72) == 0;
+  const int mask = out_mask(flags, out);
+  bool same = G.nreal == nreal && G.ntess == ntess && G.flags == flags && G.outmask == mask && G.cfg_gen == c->cfg_gen &&
+              G.alloc_gen == c->alloc_gen && memcmp(G.lat, lattice, 72) == 0;
   if (!same) {
     if (G.exec) { cudaGraphExecDestroy(G.exec); G.exec = nullptr; }
-    G.nreal = nreal; G.ntess = ntess; G.flags = flags; G.cfg_gen = c->cfg_gen; G.alloc_gen = c->alloc_gen;
+    G.nreal = nreal; G.ntess = ntess; G.flags = flags; G.outmask = mask; G.cfg_gen = c->cfg_gen; G.alloc_gen = c->alloc_gen;
     memcpy(G.lat, lattice, 72);
     G.streak = 1; G.failed = false;
     return 1;
@@ -886,7 +908,7 @@ static int lattice_graph_call(tm_ctx* c, const double* xyz, const int32_t* Z, in
     rc = (cudaMemcpyAsync(c->b_acc.p, hs, bx + bz, cudaMemcpyHostToDevice, c->stream) == cudaSuccess) ? TM_OK : TM_ECUDA;
     if (!rc) rc = prepare_lattice(c, (const double*)c->b_acc.p, (const int32_t*)((char*)c->b_acc.p + bx), nreal, lattice, ntess, &s);
     if (!rc) rc = run_all(c, s, flags, o);
-    if (!rc && cudaMemcpyAsync(hs, c->b_out.p, bytes, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) rc = TM_ECUDA;
+    if (!rc) rc = copy_packed_d2h(c, o, mask);
     if (!rc && cudaMemcpyAsync(hs + bytes, c->b_flags.p, 8, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) rc = TM_ECUDA;
     cudaError_t ce = cudaStreamEndCapture(c->stream, &graph);
     if (rc || ce != cudaSuccess || !graph || c->alloc_gen != G.alloc_gen) {

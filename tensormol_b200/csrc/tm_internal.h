@@ -186,7 +186,7 @@ struct tm_ctx {
   struct LatGraph {
     cudaGraphExec_t exec = nullptr;
     int64_t nreal = -1;
-    int ntess = 0, flags = 0, streak = 0, launches = 0;
+    int ntess = 0, flags = 0, streak = 0, launches = 0, outmask = 0;
     double lat[9];
     uint64_t alloc_gen = 0, cfg_gen = 0;
     bool failed = false;         // capture failed for this key: stay eager

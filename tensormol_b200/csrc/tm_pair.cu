@@ -560,11 +560,10 @@ k_pair_tab(const SAtom* __restrict__ sat, const float4* __restrict__ pq, const u
       }
       const int T = __shfl_sync(FULL, endv, 31);
       const int offv = cb - (endv - len);          // j = flat index + offv
-      int c = 0;                                   // run of this lane's flat index (monotone over the passes)
-      for (int f0 = 0; f0 < T; f0 += 32) {
-        const int idx = f0 + lane;
-        const bool valid = idx < T;
-        // advance to the run that holds idx: a few probes (runs are ~40 long), more only behind very short runs
+      // two independent 32-candidate groups per pass (lane: flat indices f0 + lane and f0 + 32 + lane): their loads and
+      // table lookups overlap, which is what this latency-bound loop needs
+      int ca = 0, cbb = 0;                          // runs of this lane's two flat indices (monotone over the passes)
+      auto locate = [&](int idx, bool valid, int& c) {
 #pragma unroll
         for (int k = 0; k < 2; k++) {
           int e = __shfl_sync(FULL, endv, c);
@@ -576,44 +575,58 @@ k_pair_tab(const SAtom* __restrict__ sat, const float4* __restrict__ pq, const u
           if (!__any_sync(FULL, more)) break;
           c += more ? 1 : 0;
         }
-        const int j = idx + __shfl_sync(FULL, offv, c);
-        float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
-        float d2 = 3.0e38f;
-        if (valid && j != si) {
-          d = pq[j];
-          d.x -= pi.x; d.y -= pi.y; d.z -= pi.z;
-          d2 = fmaf(d.x, d.x, fmaf(d.y, d.y, d.z * d.z));
-        }
-        if (d2 < rc2) {
-          const int pej = pe[j];
-          const int ej = pej & 7;
-          const float wj = (pej & 0x80) ? w_img : 1.0f;
-          const uint32_t bits = __float_as_uint(d2);
-          const int idn = (int)(bits >> PT_SHIFT) - kmin;
-          if (idn < 0 || idn == kink_k || idn == kink_v) {       // closer than 0.5 A, or a piece with a kink: analytic
-            pair_eval<ECC, VDW>(P, d2, d.x, d.y, d.z, qi, d.w, P.pk_c6[ei][ej], P.pk_rs12[ei][ej], wj, A);
-          } else {
-            const float u = d2 - __uint_as_float(bits & (0xffffffffu << PT_SHIFT));
-            const float4* node = s_tab + idn;
-            float deds = 0.f;
-            if (ECC) {
-              const float4 k = node[0];
-              const float kap = fmaf(u, fmaf(u, fmaf(u, k.w, k.z), k.y), k.x);
-              const float dk = fmaf(u, fmaf(u, 3.0f * k.w, 2.0f * k.z), k.y);
-              const float qq = qi * d.w;
-              A.ecc = fmaf(qq, kap, A.ecc);
-              A.dedq = fmaf(d.w, kap, A.dedq);
-              deds = qq * dk;
-            }
-            if (VDW) {
-              const float4 v = node[fnrow[ej] * nnodes];
-              A.evdw += fmaf(u, fmaf(u, fmaf(u, v.w, v.z), v.y), v.x);
-              deds += fmaf(u, fmaf(u, 3.0f * v.w, 2.0f * v.z), v.y);
-            }
-            const float sc = -2.0f * wj * deds;          // d e / d x_i = de/ds * d s / d x_i = -2 (x_j - x_i) de/ds
-            A.gx = fmaf(sc, d.x, A.gx); A.gy = fmaf(sc, d.y, A.gy); A.gz = fmaf(sc, d.z, A.gz);
+        return idx + __shfl_sync(FULL, offv, c);
+      };
+      auto evaluate = [&](const float4& d, float d2, int j) {
+        const int pej = pe[j];
+        const int ej = pej & 7;
+        const float wj = (pej & 0x80) ? w_img : 1.0f;
+        const uint32_t bits = __float_as_uint(d2);
+        const int idn = (int)(bits >> PT_SHIFT) - kmin;
+        if (idn < 0 || idn == kink_k || idn == kink_v) {       // closer than 0.5 A, or a piece with a kink: analytic
+          pair_eval<ECC, VDW>(P, d2, d.x, d.y, d.z, qi, d.w, P.pk_c6[ei][ej], P.pk_rs12[ei][ej], wj, A);
+        } else {
+          const float u = d2 - __uint_as_float(bits & (0xffffffffu << PT_SHIFT));
+          const float4* node = s_tab + idn;
+          float deds = 0.f;
+          if (ECC) {
+            const float4 k = node[0];
+            const float kap = fmaf(u, fmaf(u, fmaf(u, k.w, k.z), k.y), k.x);
+            const float dk = fmaf(u, fmaf(u, 3.0f * k.w, 2.0f * k.z), k.y);
+            const float qq = qi * d.w;
+            A.ecc = fmaf(qq, kap, A.ecc);
+            A.dedq = fmaf(d.w, kap, A.dedq);
+            deds = qq * dk;
           }
+          if (VDW) {
+            const float4 v = node[fnrow[ej] * nnodes];
+            A.evdw += fmaf(u, fmaf(u, fmaf(u, v.w, v.z), v.y), v.x);
+            deds += fmaf(u, fmaf(u, 3.0f * v.w, 2.0f * v.z), v.y);
+          }
+          const float sc = -2.0f * wj * deds;          // d e / d x_i = de/ds * d s / d x_i = -2 (x_j - x_i) de/ds
+          A.gx = fmaf(sc, d.x, A.gx); A.gy = fmaf(sc, d.y, A.gy); A.gz = fmaf(sc, d.z, A.gz);
         }
+      };
+      for (int f0 = 0; f0 < T; f0 += 64) {
+        const int ia = f0 + lane, ib = ia + 32;
+        const bool va = ia < T, vb = ib < T;
+        if (cbb < ca) cbb = ca;
+        const int ja = locate(ia, va, ca);
+        const int jb = locate(ib, vb, cbb);
+        float4 da = make_float4(0.f, 0.f, 0.f, 0.f), db = da;
+        float d2a = 3.0e38f, d2b = 3.0e38f;
+        if (va && ja != si) da = pq[ja];
+        if (vb && jb != si) db = pq[jb];
+        if (va && ja != si) {
+          da.x -= pi.x; da.y -= pi.y; da.z -= pi.z;
+          d2a = fmaf(da.x, da.x, fmaf(da.y, da.y, da.z * da.z));
+        }
+        if (vb && jb != si) {
+          db.x -= pi.x; db.y -= pi.y; db.z -= pi.z;
+          d2b = fmaf(db.x, db.x, fmaf(db.y, db.y, db.z * db.z));
+        }
+        if (d2a < rc2) evaluate(da, d2a, ja);
+        if (d2b < rc2) evaluate(db, d2b, jb);
       }
     }
 #pragma unroll

@@ -252,9 +252,12 @@ class Engine:
         check(self.lib.tm_eval(self.ctx, _ptr(xyzs), _ptr(Zs), nmol, maxn, _ptr(natom), self._flags(do_force, has_vdw, descriptors), C.byref(out)), "tm_eval")
         return res
 
-    def _periodic_result(self, nreal, ntot, descriptors):
-        res = dict(Etotal=np.zeros(1), Ebp=np.zeros(1), Ebp_atom=np.zeros((1, nreal)), Ecc=np.zeros(1), Evdw=np.zeros(1),
-                   dipole=np.zeros((1, 3)), charge=np.zeros((1, ntot)), gradient=np.zeros((1, nreal, 3)))
+    def _periodic_result(self, nreal, ntot, descriptors, outputs=None):
+        """Result arrays + the tm_outputs that points at them.  `outputs` = names to compute AND transfer (None = all):
+        a pointer left NULL is skipped by the library, and its block never crosses the bus."""
+        shapes = dict(Etotal=(1,), Ebp=(1,), Ebp_atom=(1, nreal), Ecc=(1,), Evdw=(1,), dipole=(1, 3), charge=(1, ntot), gradient=(1, nreal, 3))
+        names = list(shapes) if outputs is None else [k for k in shapes if k in outputs]
+        res = {k: np.zeros(shapes[k]) for k in names}
         if descriptors:
             res["descriptors"] = np.zeros((1, nreal, self.D), np.float32)
         out = tm_outputs()
@@ -271,12 +274,14 @@ class Engine:
               "tm_eval_images")
         return res
 
-    def evaluate_lattice(self, xyz, Z, lattice, ntess, do_force=True, has_vdw=True, descriptors=False, fold=False):
+    def evaluate_lattice(self, xyz, Z, lattice, ntess, do_force=True, has_vdw=True, descriptors=False, fold=False, outputs=None):
+        """Periodic cell + lattice.  outputs: e.g. ("Etotal", "gradient") = what the reference's periodic callback returns
+        (TFMolManage.py:1353-1358); None = every output."""
         xyz = np.ascontiguousarray(xyz, np.float64)
         Z = np.ascontiguousarray(Z, np.int32)
         lat = np.ascontiguousarray(lattice, np.float64).reshape(9)
         n = xyz.shape[0]
-        res, out = self._periodic_result(n, n, descriptors)   # charges of the real atoms only
+        res, out = self._periodic_result(n, n, descriptors, outputs)   # charges of the real atoms only
         check(self.lib.tm_eval_lattice(self.ctx, _ptr(xyz), _ptr(Z), n, _ptr(lat), int(ntess), self._flags(do_force, has_vdw, descriptors, fold), C.byref(out)),
               "tm_eval_lattice")
         return res
