@@ -73,6 +73,7 @@ struct alignas(64) TcParams {
   float act_alpha;
   int fuse_n;                 // single-CTA tiles: A_hi x [B_hi | B_lo] as ONE MMA of N = 2 BN (see the MMA issuer)
   unsigned long long* prof;   // TC_PROFILE builds: per-CTA cycle counters
+  int exp;                    // TC_EXP builds (measurements): bit 0 no output phase, bit 1 no MMAs, bit 2 no TMA loads
 };
 
 // ------------------------------------------------------------------------------------------------ PTX helpers
@@ -351,6 +352,9 @@ k_gemm_tc(const __grid_constant__ TcParams P, const int32_t* __restrict__ rowmet
             tma_load_2d_pair(&G.mapB_hi, fb, st + 2 * A_BYTES, kb * TC_BK, n0);
             tma_load_2d_pair(&G.mapB_lo, fb, st + 2 * A_BYTES + B_BYTES, kb * TC_BK, n0);
           } else {
+#ifdef TC_EXP
+            if (P.exp & 4) { mbar_arrive(&full_bar[stage]); if (++stage == STAGES) { stage = 0; phase ^= 1; } continue; }
+#endif
             mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
             tma_load_2d(&G.mapA_hi, &full_bar[stage], st, kb * TC_BK, row0);
             tma_load_2d(&G.mapA_lo, &full_bar[stage], st + A_BYTES, kb * TC_BK, row0);
@@ -398,6 +402,9 @@ k_gemm_tc(const __grid_constant__ TcParams P, const int32_t* __restrict__ rowmet
             uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
             uint64_t a_hi = umma_desc(sa), a_lo = umma_desc(sa + A_BYTES);
             uint64_t b_hi = umma_desc(sa + 2 * A_BYTES), b_lo = umma_desc(sa + 2 * A_BYTES + B_BYTES);
+#ifdef TC_EXP
+            if (!(P.exp & 2))
+#endif
 #pragma unroll
             for (int k = 0; k < TC_BK / 16; k++) {
               uint64_t koff = (uint64_t)((k * 16 * 2) >> 4);   // 32 bytes per K=16 step inside the 128B swizzle row
@@ -498,6 +505,9 @@ k_gemm_tc(const __grid_constant__ TcParams P, const int32_t* __restrict__ rowmet
       PROF_T(t_out);
       // ---- output phase: thread = row of the warp's 32-row band, NC = 64 consecutive columns
       if (!live) continue;
+#ifdef TC_EXP
+      if (P.exp & 1) { if (accr[0] == 123.456f) P.g[g].C32[0] = accr[1]; continue; }
+#endif
       if (EPI == TM_EPI_DACT) {
         // act'(h) for the band: lanes work slab-wise (4 lanes per row, 8 rows per instruction) on two 32-column passes,
         // join hi/lo, evaluate act', and hand the fp32 values to the row threads through the swizzled tile.
@@ -754,6 +764,10 @@ int tm_gemm_tc_launch(tm_ctx* c, const GemmGroup* groups, int ngroups, const int
   if (fuse_env < 0) { const char* e = getenv("TM_GEMM_FUSE"); fuse_env = (e && atoi(e) == 0) ? 0 : 1; }
   P.fuse_n = fuse_env;
   P.prof = nullptr;
+  P.exp = 0;
+#ifdef TC_EXP
+  { const char* e = getenv("TC_EXP"); P.exp = e ? atoi(e) : 0; }
+#endif
 #ifdef TC_PROFILE
   {
     static unsigned long long* dprof = nullptr;
