@@ -2,7 +2,8 @@
 import sys, time
 import numpy as np, torch
 sys.path.insert(0, '.')
-from bench import hot_params, HIDDEN
+from bench import hot_params
+HIDDEN = [500, 500, 500]
 from tensormol_b200.SystemBuilders import water_box, wrap_into_cell
 from tensormol_b200.engine import Engine, random_weights
 from tensormol_b200.parallel import EngineSlabBackend

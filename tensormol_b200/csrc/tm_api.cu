@@ -20,6 +20,11 @@ void tm_set_error(const char* fmt, ...) {
   va_end(ap);
 }
 extern "C" const char* tm_last_error(void) { return g_err; }
+int tm_pdl_enabled() {
+  static int on = -1;
+  if (on < 0) on = getenv("TM_NO_PDL") ? 0 : 1;
+  return on;
+}
 extern "C" int tm_version(void) { return 100; }
 extern "C" int tm_device_count(void) {
   int n = 0;
@@ -225,7 +230,7 @@ extern "C" void tm_destroy(tm_ctx* c) {
   DevBuf* all[] = {&c->b_pos, &c->b_Z, &c->b_cellid, &c->b_rank, &c->b_count, &c->b_cstart, &c->b_sorted, &c->b_satom, &c->b_scan_tmp,
                    &c->b_rowslot, &c->b_rowsidx, &c->b_rowofslot, &c->b_blkcnt, &c->b_rowmeta, &c->b_nbcnt, &c->b_nboff, &c->b_nbr, &c->b_G, &c->b_Gs, &c->b_ypart,
                    &c->b_delta0, &c->b_delta1, &c->b_dG[0], &c->b_dG[1], &c->b_y[0], &c->b_y[1], &c->b_q, &c->b_qs, &c->b_dedq, &c->b_F,
-                   &c->b_acc, &c->b_bbox, &c->b_grid, &c->b_flags, &c->b_out, &c->b_molacc, &c->b_natom, &c->b_cntall, &c->b_offall, &c->b_pe, &c->b_pairtab};
+                   &c->b_acc, &c->b_bbox, &c->b_grid, &c->b_flags, &c->b_out, &c->b_molacc, &c->b_natom, &c->b_cntall, &c->b_offall, &c->b_pe, &c->b_pairtab, &c->b_lscan};
   for (DevBuf* b : all) free_buf(*b);
   for (int n = 0; n < 2; n++)
     for (int l = 0; l < TM_MAX_HIDDEN; l++) free_buf(c->b_act[n][l]);
@@ -351,6 +356,7 @@ static int check_weights(tm_ctx* c) {
 // per-molecule Ebp (fp32 GEMM mode only: the tensor-core forward pass sums it in k_y_reduce)
 __global__ void k_ebp(const float* __restrict__ y, const int32_t* __restrict__ rowslot, int64_t nrows, int64_t maxnatom,
                       double* __restrict__ molacc) {
+  TM_PDL_PROLOGUE;
   int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   int slot = (r < nrows) ? rowslot[r] : -1;
   double v = 0.0;
@@ -380,6 +386,7 @@ __global__ void k_ebp(const float* __restrict__ y, const int32_t* __restrict__ r
 __global__ void k_pack_all(const double* __restrict__ molacc, int64_t nmol, int add_ecc, const float* __restrict__ y_e,
                            const int32_t* __restrict__ rowofslot, const double* __restrict__ q_slot, const float* __restrict__ F, int64_t nq,
                            int do_force, double* __restrict__ out) {
+  TM_PDL_PROLOGUE;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x, t0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   for (int64_t m = t0; m < nmol; m += stride) {
     double ebp = molacc[16 * m + 1], ecc = add_ecc ? molacc[16 * m + 2] : 0.0, evdw = molacc[16 * m + 3];
@@ -403,15 +410,18 @@ __global__ void k_pack_all(const double* __restrict__ molacc, int64_t nmol, int 
     for (int64_t t = t0; t < 3 * nq; t += stride) grad[t] = (double)F[t];
 }
 __global__ void k_f2d(const float* __restrict__ in, double* __restrict__ out, int64_t n) {
+  TM_PDL_PROLOGUE;
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) out[t] = (double)in[t];
 }
 __global__ void k_desc_out(const float* __restrict__ G, const int32_t* __restrict__ rowofslot, int64_t nq, int D, int Dp, float* __restrict__ out) {
+  TM_PDL_PROLOGUE;
   int64_t slot = blockIdx.x;
   if (slot >= nq) return;
   int row = rowofslot[slot];
   for (int d = threadIdx.x; d < D; d += blockDim.x) out[slot * D + d] = (row >= 0) ? G[(int64_t)row * Dp + d] : 0.f;
 }
 __global__ void k_set_i32(int32_t* p, int64_t n, int32_t v) {
+  TM_PDL_PROLOGUE;
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) p[t] = v;
 }
 
@@ -535,12 +545,12 @@ static int stage_pack(tm_ctx* c, const SysView& s, int flags, const OutLayout& o
   if ((rc = tm_buf(c, c->b_out, (size_t)o.total * 8))) return rc;
   double* out = (double*)c->b_out.p;
   if (!c->y_fused) {
-    k_ebp<<<(int)((s.nrows + 255) / 256), 256, 0, c->stream>>>((const float*)c->b_y[TM_NET_ENERGY].p, (const int32_t*)c->b_rowslot.p, s.nrows, s.maxnatom,
+    TM_LAUNCH(k_ebp, (int)((s.nrows + 255) / 256), 256, 0, c->stream, (const float*)c->b_y[TM_NET_ENERGY].p, (const int32_t*)c->b_rowslot.p, s.nrows, s.maxnatom,
                                                               (double*)c->b_molacc.p);
     c->launches++;
   }
   const int do_force = (flags & TM_F_FORCE) ? 1 : 0;
-  k_pack_all<<<nblk(std::max<int64_t>(s.nmol, (do_force ? 3 : 1) * o.nq)), 256, 0, c->stream>>>(
+  TM_LAUNCH(k_pack_all, nblk(std::max<int64_t>(s.nmol, (do_force ? 3 : 1) * o.nq)), 256, 0, c->stream, 
       (const double*)c->b_molacc.p, s.nmol, c->hp.add_ecc, (const float*)c->b_y[TM_NET_ENERGY].p, (const int32_t*)c->b_rowofslot.p,
       (const double*)c->b_q.p + o.nq, (const float*)c->b_F.p, o.nq, do_force, out);
   c->launches++;
@@ -615,7 +625,7 @@ static int deliver(tm_ctx* c, const SysView& s, int flags, const OutLayout& o, t
   if ((rc = copy_packed_d2h(c, o, out_mask(flags, out)))) return rc;
   if (dbytes) {
     if ((rc = tm_buf(c, c->b_acc, dbytes))) return rc;
-    k_desc_out<<<(unsigned)o.nq, 128, 0, c->stream>>>((const float*)c->b_G.p, (const int32_t*)c->b_rowofslot.p, o.nq, c->hp.D, c->hp.Dp, (float*)c->b_acc.p);
+    TM_LAUNCH(k_desc_out, (unsigned)o.nq, 128, 0, c->stream, (const float*)c->b_G.p, (const int32_t*)c->b_rowofslot.p, o.nq, c->hp.D, c->hp.Dp, (float*)c->b_acc.p);
     c->launches++;
     TM_CUDA(cudaMemcpyAsync((char*)c->h_stage + bytes, c->b_acc.p, dbytes, cudaMemcpyDeviceToHost, c->stream));
   }
@@ -1010,12 +1020,14 @@ extern "C" int tm_get_timings(tm_ctx* c, tm_timings* t) {
 // host (tensormol_b200/parallel.py, torch.distributed/NCCL) performs the three small all-reduces
 // between the phases.  See include/tmolb200.h.
 __global__ void k_owned_qraw(const float* __restrict__ y, const int32_t* __restrict__ rowslot, int64_t nrows, double* __restrict__ q) {
+  TM_PDL_PROLOGUE;
   for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < nrows; r += (int64_t)gridDim.x * blockDim.x) {
     int s = rowslot[r];
     if (s >= 0) q[s] = (double)y[r];
   }
 }
 __global__ void k_slab_e(const double* __restrict__ molacc, double* __restrict__ e, int add_ecc) {
+  TM_PDL_PROLOGUE;
   e[0] = 0.0;
   e[1] = molacc[1];
   e[2] = add_ecc ? molacc[2] : 0.0;
@@ -1023,7 +1035,8 @@ __global__ void k_slab_e(const double* __restrict__ molacc, double* __restrict__
   e[4] = molacc[5];
   e[5] = 0.0;
 }
-__global__ void k_slab_set_dedq(double* __restrict__ molacc, const double* __restrict__ e) { molacc[5] = e[4]; }
+__global__ void k_slab_set_dedq(double* __restrict__ molacc, const double* __restrict__ e) {
+  TM_PDL_PROLOGUE; molacc[5] = e[4]; }
 
 // ---- peer-memory exchange (see include/tmolb200.h) ---------------------------------------------------------------------
 // symmetric buffer layout: [ q_raw f64[nreal] | e partials f64[16][8] | force partials f32[world][3 nreal] | flags ]
@@ -1073,6 +1086,7 @@ static PeerPtrs peer_ptrs(const tm_ctx* c, int64_t off) {
 
 // q_raw of the owned centres, stored into every peer's copy (each slot has exactly one owner: no reduction needed)
 __global__ void k_owned_qraw_p2p(const float* __restrict__ y, const int32_t* __restrict__ rowslot, int64_t nrows, PeerPtrs q, int world) {
+  TM_PDL_PROLOGUE;
   for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < nrows; r += (int64_t)gridDim.x * blockDim.x) {
     int s = rowslot[r];
     if (s < 0) continue;
@@ -1082,6 +1096,7 @@ __global__ void k_owned_qraw_p2p(const float* __restrict__ y, const int32_t* __r
 }
 // this rank's energy partials into slot [rank] of every peer
 __global__ void k_slab_e_p2p(const double* __restrict__ molacc, int add_ecc, PeerPtrs e, int world, int rank) {
+  TM_PDL_PROLOGUE;
   int p = threadIdx.x;
   if (p >= world) return;
   double* d = (double*)e.p[p] + 8 * rank;
@@ -1089,6 +1104,7 @@ __global__ void k_slab_e_p2p(const double* __restrict__ molacc, int add_ecc, Pee
 }
 // this rank's force partial (fp32, every atom: zeros outside its slab + halo) into slot [rank] of every peer
 __global__ void k_push_grad_p2p(const float* __restrict__ F, int64_t n3, int64_t stride, PeerPtrs g, int world, int rank) {
+  TM_PDL_PROLOGUE;
   int64_t n4 = n3 / 4;     // 3*nreal floats, float4 body + scalar tail; stride = n3 rounded up to 4 floats
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n4; t += (int64_t)gridDim.x * blockDim.x) {
     float4 v = reinterpret_cast<const float4*>(F)[t];
@@ -1101,12 +1117,14 @@ __global__ void k_push_grad_p2p(const float* __restrict__ F, int64_t n3, int64_t
 }
 // all of this device's earlier stores are out: bump arrival counter `which` on every peer (one thread per peer)
 __global__ void k_p2p_signal(PeerPtrs f, int world, int which) {
+  TM_PDL_PROLOGUE;
   __threadfence_system();
   int p = threadIdx.x;
   if (p < world) atomicAdd_system((unsigned int*)(f.p[p]) + 16 * which, 1u);
 }
 // wait until every rank has signalled the next epoch of exchange `which` (epoch kept on the device: graph replayable)
 __global__ void k_p2p_wait(char* flags, int world, int which, int32_t* errflags) {
+  TM_PDL_PROLOGUE;
   volatile unsigned int* cnt = (volatile unsigned int*)flags + 16 * which;
   unsigned int* epoch = (unsigned int*)flags + 16 * (4 + which);
   unsigned int target = (*epoch + 1u) * (unsigned int)world;
@@ -1122,6 +1140,7 @@ __global__ void k_p2p_wait(char* flags, int world, int which, int32_t* errflags)
 // exchange `which` (same protocol as k_p2p_wait)
 __global__ void k_p2p_wait_reduce_e(char* flags, int world, int which, int32_t* errflags, const double* eparts, double* __restrict__ molacc,
                                     double* __restrict__ e_out) {
+  TM_PDL_PROLOGUE;
   volatile unsigned int* cnt = (volatile unsigned int*)flags + 16 * which;
   unsigned int* epoch = (unsigned int*)flags + 16 * (4 + which);
   unsigned int target = (*epoch + 1u) * (unsigned int)world;
@@ -1141,6 +1160,7 @@ __global__ void k_p2p_wait_reduce_e(char* flags, int world, int which, int32_t* 
   for (int k = 0; k < 6; k++) e_out[k] = s[k];
 }
 __global__ void k_sum_grad_p2p(const float* __restrict__ gparts, int world, int64_t n3, int64_t stride, double* __restrict__ out) {
+  TM_PDL_PROLOGUE;
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n3; t += (int64_t)gridDim.x * blockDim.x) {
     double s = 0.0;
     for (int r = 0; r < world; r++) s += (double)gparts[(int64_t)r * stride + t];
@@ -1188,13 +1208,13 @@ extern "C" int tm_slab_phase_a(tm_ctx* c, const double* xyz_dev, const int32_t* 
   cudaEventRecord(c->ev[6], c->stream);
   if (c->p2p.on) {
     if (c->p2p.world != world || c->p2p.rank != rank || c->p2p.nreal != nreal) { tm_set_error("tm_slab_phase_a: does not match tm_slab_p2p_setup"); return TM_EINVAL; }
-    k_owned_qraw_p2p<<<nblk(s.nrows), 256, 0, c->stream>>>((const float*)c->b_y[TM_NET_CHARGE].p, (const int32_t*)c->b_rowslot.p, s.nrows,
+    TM_LAUNCH(k_owned_qraw_p2p, nblk(s.nrows), 256, 0, c->stream, (const float*)c->b_y[TM_NET_CHARGE].p, (const int32_t*)c->b_rowslot.p, s.nrows,
                                                           peer_ptrs(c, c->p2p.off_q), world);
-    k_p2p_signal<<<1, 32, 0, c->stream>>>(peer_ptrs(c, c->p2p.off_flag), world, 0);
+    TM_LAUNCH(k_p2p_signal, 1, 32, 0, c->stream, peer_ptrs(c, c->p2p.off_flag), world, 0);
     c->launches += 2;
   } else {
     TM_CUDA(cudaMemsetAsync(qraw_dev, 0, (size_t)nreal * 8, c->stream));
-    k_owned_qraw<<<nblk(s.nrows), 256, 0, c->stream>>>((const float*)c->b_y[TM_NET_CHARGE].p, (const int32_t*)c->b_rowslot.p, s.nrows, qraw_dev);
+    TM_LAUNCH(k_owned_qraw, nblk(s.nrows), 256, 0, c->stream, (const float*)c->b_y[TM_NET_CHARGE].p, (const int32_t*)c->b_rowslot.p, s.nrows, qraw_dev);
     c->launches++;
   }
   TM_CUDA(cudaGetLastError());
@@ -1210,7 +1230,7 @@ extern "C" int tm_slab_phase_b(tm_ctx* c, const double* qraw_dev, double* e_dev)
   if ((rc = tm_buf(c, c->b_q, (size_t)nq * 8 * 2))) return rc;
   if (c->p2p.on) {   // every owner has stored its charges into this rank's copy once all ranks have signalled
     char* mine = c->p2p.base[c->p2p.rank];
-    k_p2p_wait<<<1, 1, 0, c->stream>>>(mine + c->p2p.off_flag, c->p2p.world, 0, (int32_t*)c->b_flags.p);
+    TM_LAUNCH(k_p2p_wait, 1, 1, 0, c->stream, mine + c->p2p.off_flag, c->p2p.world, 0, (int32_t*)c->b_flags.p);
     c->launches++;
     qraw_dev = (const double*)(mine + c->p2p.off_q);
   }
@@ -1220,16 +1240,16 @@ extern "C" int tm_slab_phase_b(tm_ctx* c, const double* qraw_dev, double* e_dev)
   if ((rc = tm_launch_charges(c, s2))) return rc;
   if ((rc = tm_launch_pair(c, s, TM_F_FORCE | TM_F_VDW))) return rc;
   if (!c->y_fused) {
-    k_ebp<<<(int)((s.nrows + 255) / 256), 256, 0, c->stream>>>((const float*)c->b_y[TM_NET_ENERGY].p, (const int32_t*)c->b_rowslot.p, s.nrows, s.maxnatom,
+    TM_LAUNCH(k_ebp, (int)((s.nrows + 255) / 256), 256, 0, c->stream, (const float*)c->b_y[TM_NET_ENERGY].p, (const int32_t*)c->b_rowslot.p, s.nrows, s.maxnatom,
                                                               (double*)c->b_molacc.p);
     c->launches++;
   }
   if (c->p2p.on) {
-    k_slab_e_p2p<<<1, 32, 0, c->stream>>>((const double*)c->b_molacc.p, c->hp.add_ecc, peer_ptrs(c, c->p2p.off_e), c->p2p.world, c->p2p.rank);
-    k_p2p_signal<<<1, 32, 0, c->stream>>>(peer_ptrs(c, c->p2p.off_flag), c->p2p.world, 1);
+    TM_LAUNCH(k_slab_e_p2p, 1, 32, 0, c->stream, (const double*)c->b_molacc.p, c->hp.add_ecc, peer_ptrs(c, c->p2p.off_e), c->p2p.world, c->p2p.rank);
+    TM_LAUNCH(k_p2p_signal, 1, 32, 0, c->stream, peer_ptrs(c, c->p2p.off_flag), c->p2p.world, 1);
     c->launches++;
   } else {
-    k_slab_e<<<1, 1, 0, c->stream>>>((const double*)c->b_molacc.p, e_dev, c->hp.add_ecc);
+    TM_LAUNCH(k_slab_e, 1, 1, 0, c->stream, (const double*)c->b_molacc.p, e_dev, c->hp.add_ecc);
   }
   c->launches++;
   cudaEventRecord(c->ev[5], c->stream);
@@ -1244,23 +1264,23 @@ extern "C" int tm_slab_phase_c(tm_ctx* c, const double* e_dev, int flags, double
   SysView s = c->slab_view;
   if (c->p2p.on) {
     char* mine = c->p2p.base[c->p2p.rank];
-    k_p2p_wait_reduce_e<<<1, 1, 0, c->stream>>>(mine + c->p2p.off_flag, c->p2p.world, 1, (int32_t*)c->b_flags.p, (const double*)(mine + c->p2p.off_e),
+    TM_LAUNCH(k_p2p_wait_reduce_e, 1, 1, 0, c->stream, mine + c->p2p.off_flag, c->p2p.world, 1, (int32_t*)c->b_flags.p, (const double*)(mine + c->p2p.off_e),
                                                 (double*)c->b_molacc.p, (double*)e_dev);
   } else {
-    k_slab_set_dedq<<<1, 1, 0, c->stream>>>((double*)c->b_molacc.p, e_dev);
+    TM_LAUNCH(k_slab_set_dedq, 1, 1, 0, c->stream, (double*)c->b_molacc.p, e_dev);
   }
   c->launches++;
   if ((rc = tm_launch_force(c, s, flags))) return rc;
   if (c->p2p.on) {
     char* mine = c->p2p.base[c->p2p.rank];
     int64_t n3 = 3 * s.nreal, stride = (n3 + 3) / 4 * 4;
-    k_push_grad_p2p<<<nblk(n3 / 4 + 1), 256, 0, c->stream>>>((const float*)c->b_F.p, n3, stride, peer_ptrs(c, c->p2p.off_g), c->p2p.world, c->p2p.rank);
-    k_p2p_signal<<<1, 32, 0, c->stream>>>(peer_ptrs(c, c->p2p.off_flag), c->p2p.world, 2);
-    k_p2p_wait<<<1, 1, 0, c->stream>>>(mine + c->p2p.off_flag, c->p2p.world, 2, (int32_t*)c->b_flags.p);
-    k_sum_grad_p2p<<<nblk(n3), 256, 0, c->stream>>>((const float*)(mine + c->p2p.off_g), c->p2p.world, n3, stride, grad_dev);
+    TM_LAUNCH(k_push_grad_p2p, nblk(n3 / 4 + 1), 256, 0, c->stream, (const float*)c->b_F.p, n3, stride, peer_ptrs(c, c->p2p.off_g), c->p2p.world, c->p2p.rank);
+    TM_LAUNCH(k_p2p_signal, 1, 32, 0, c->stream, peer_ptrs(c, c->p2p.off_flag), c->p2p.world, 2);
+    TM_LAUNCH(k_p2p_wait, 1, 1, 0, c->stream, mine + c->p2p.off_flag, c->p2p.world, 2, (int32_t*)c->b_flags.p);
+    TM_LAUNCH(k_sum_grad_p2p, nblk(n3), 256, 0, c->stream, (const float*)(mine + c->p2p.off_g), c->p2p.world, n3, stride, grad_dev);
     c->launches += 3;
   } else {
-    k_f2d<<<nblk(3 * s.nreal), 256, 0, c->stream>>>((const float*)c->b_F.p, grad_dev, 3 * s.nreal);
+    TM_LAUNCH(k_f2d, nblk(3 * s.nreal), 256, 0, c->stream, (const float*)c->b_F.p, grad_dev, 3 * s.nreal);
   }
   c->launches++;
   cudaEventRecord(c->ev[7], c->stream);

@@ -6,6 +6,7 @@
 #include <cstring>
 
 __global__ void k_fill_const_i32(int32_t* p, int64_t n, int32_t v) {
+  TM_PDL_PROLOGUE;
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) p[t] = v;
 }
 
@@ -39,7 +40,7 @@ extern "C" int tm_nlist(tm_ctx* c, const double* xyz, int64_t n, int64_t nreal, 
   TM_CUDA(cudaMemsetAsync(c->b_flags.p, 0, 64, c->stream));
   TM_CUDA(cudaMemcpyAsync(c->b_pos.p, xyz, (size_t)n * 24, cudaMemcpyHostToDevice, c->stream));
   int blocks = (int)std::min<int64_t>((n + 255) / 256, 148 * 8);
-  k_fill_const_i32<<<blocks, 256, 0, c->stream>>>((int32_t*)c->b_Z.p, n, 1);
+  TM_LAUNCH(k_fill_const_i32, blocks, 256, 0, c->stream, (int32_t*)c->b_Z.p, n, 1);
   c->launches++;
   SysView s = compat_view(n, 1, n, nreal, nreal < n ? 1 : 0);
   if (nreal == n) { s.periodic = 0; s.nreal = 0; }

@@ -52,6 +52,7 @@ __global__ void __launch_bounds__(DESC_WARPS * 32)
 k_desc(const SAtom* __restrict__ sat, const int32_t* __restrict__ rowsidx, const int32_t* __restrict__ rowslot,
        const int32_t* __restrict__ nbcnt, const uint32_t* __restrict__ nbr, int64_t nrows, const __grid_constant__ DevParams P,
        float* __restrict__ G, __half* __restrict__ Ghi, __half* __restrict__ Glo, int32_t* __restrict__ flags, int wfloats) {
+  TM_PDL_PROLOGUE;
   constexpr int NELEP = NE * (NE + 1) / 2;
   extern __shared__ float smem[];
   int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -245,6 +246,7 @@ __global__ void __launch_bounds__(DESC_WARPS * 32)
 k_desc_fast(const SAtom* __restrict__ sat, const int32_t* __restrict__ rowsidx, const int32_t* __restrict__ rowslot,
             const int32_t* __restrict__ nbcnt, const uint32_t* __restrict__ nbr, int64_t nrows, const __grid_constant__ DevParams P,
             float* __restrict__ G, __half* __restrict__ Ghi, __half* __restrict__ Glo, int32_t* __restrict__ flags, int wfloats) {
+  TM_PDL_PROLOGUE;
   constexpr int NELEP = NE * (NE + 1) / 2;
   constexpr int NA = 8, NR = 8, NSYM = NA * NR;
   extern __shared__ float smem[];
@@ -425,7 +427,7 @@ static int launch_desc_fast(tm_ctx* c, const SysView& s) {
   }
   int blocks = (int)((s.nrows + DESC_WARPS - 1) / DESC_WARPS);
   const bool split = c->gemm_mode != TM_GEMM_FP32;
-  k_desc_fast<NE><<<blocks, DESC_WARPS * 32, smem, c->stream>>>((const SAtom*)c->b_satom.p, (const int32_t*)c->b_rowsidx.p,
+  TM_LAUNCH(k_desc_fast<NE>, blocks, DESC_WARPS * 32, smem, c->stream, (const SAtom*)c->b_satom.p, (const int32_t*)c->b_rowsidx.p,
                                                                (const int32_t*)c->b_rowslot.p, (const int32_t*)c->b_nbcnt.p,
                                                                (const uint32_t*)c->b_nbr.p, s.nrows, P, (float*)c->b_G.p,
                                                                split ? (__half*)c->b_Gs.p : nullptr,
@@ -449,7 +451,7 @@ static int launch_desc(tm_ctx* c, const SysView& s) {
   }
   int blocks = (int)((s.nrows + DESC_WARPS - 1) / DESC_WARPS);
   const bool split = c->gemm_mode != TM_GEMM_FP32;
-  k_desc<NE, OPLT><<<blocks, DESC_WARPS * 32, smem, c->stream>>>((const SAtom*)c->b_satom.p, (const int32_t*)c->b_rowsidx.p,
+  TM_LAUNCH((k_desc<NE, OPLT>), blocks, DESC_WARPS * 32, smem, c->stream, (const SAtom*)c->b_satom.p, (const int32_t*)c->b_rowsidx.p,
                                                                 (const int32_t*)c->b_rowslot.p, (const int32_t*)c->b_nbcnt.p,
                                                                 (const uint32_t*)c->b_nbr.p, s.nrows, P, (float*)c->b_G.p,
                                                                 split ? (__half*)c->b_Gs.p : nullptr,

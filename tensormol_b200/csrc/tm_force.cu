@@ -46,6 +46,7 @@ k_force(const SAtom* __restrict__ sat, const int32_t* __restrict__ rowsidx, cons
         const int32_t* __restrict__ nbcnt, const uint32_t* __restrict__ nbr, int64_t nrows, const __grid_constant__ DevParams P,
         const float* __restrict__ dGe, const float* __restrict__ dGq, const double* __restrict__ dedq_slot, const double* __restrict__ molacc,
         const double* __restrict__ inv_n, int64_t maxnatom, int64_t nreal_slots, int fold, float* __restrict__ F, int wfloats) {
+  TM_PDL_PROLOGUE;
   extern __shared__ float smem[];
   int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int64_t row = (int64_t)blockIdx.x * FORCE_WARPS + warp;
@@ -279,6 +280,7 @@ k_force_fast(const SAtom* __restrict__ sat, const int32_t* __restrict__ rowsidx,
              const int32_t* __restrict__ nbcnt, const uint32_t* __restrict__ nbr, int64_t nrows, const __grid_constant__ DevParams P,
              const float* __restrict__ dGe, const float* __restrict__ dGq, const double* __restrict__ dedq_slot, const double* __restrict__ molacc,
              const double* __restrict__ inv_n, int64_t maxnatom, int64_t nreal_slots, int fold, float* __restrict__ F, int wfloats) {
+  TM_PDL_PROLOGUE;
   constexpr int NA = 8, NR = 8, NSYM = 64, NRAD = 32;
   extern __shared__ float smem[];
   int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -557,7 +559,7 @@ int tm_launch_force(tm_ctx* c, const SysView& s, int flags) {
       TM_CUDA(cudaFuncSetAttribute(k_force_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smf));
       conf_fast = smf;
     }
-    k_force_fast<<<blocks, FORCE_WARPS * 32, smf, c->stream>>>(
+    TM_LAUNCH(k_force_fast, blocks, FORCE_WARPS * 32, smf, c->stream, 
         (const SAtom*)c->b_satom.p, (const int32_t*)c->b_rowsidx.p, (const int32_t*)c->b_rowslot.p, (const int32_t*)c->b_nbcnt.p,
         (const uint32_t*)c->b_nbr.p, s.nrows, P, (const float*)c->b_dG[TM_NET_ENERGY].p, (const float*)c->b_dG[TM_NET_CHARGE].p,
         (const double*)c->b_dedq.p, (const double*)c->b_molacc.p, (const double*)c->b_natom.p, s.maxnatom, nreal_slots, fold, (float*)c->b_F.p,
@@ -576,7 +578,7 @@ int tm_launch_force(tm_ctx* c, const SysView& s, int flags) {
       TM_CUDA(cudaFuncSetAttribute(k_force<8, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       conf_small = smem;
     }
-    k_force<8, 8><<<blocks, FORCE_WARPS * 32, smem, c->stream>>>(
+    TM_LAUNCH((k_force<8, 8>), blocks, FORCE_WARPS * 32, smem, c->stream, 
         (const SAtom*)c->b_satom.p, (const int32_t*)c->b_rowsidx.p, (const int32_t*)c->b_rowslot.p, (const int32_t*)c->b_nbcnt.p,
         (const uint32_t*)c->b_nbr.p, s.nrows, P, (const float*)c->b_dG[TM_NET_ENERGY].p, (const float*)c->b_dG[TM_NET_CHARGE].p,
         (const double*)c->b_dedq.p, (const double*)c->b_molacc.p, (const double*)c->b_natom.p, s.maxnatom, nreal_slots, fold, (float*)c->b_F.p,
@@ -586,7 +588,7 @@ int tm_launch_force(tm_ctx* c, const SysView& s, int flags) {
       TM_CUDA(cudaFuncSetAttribute(k_force<TM_MAX_SYM, TM_MAX_SYM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       conf_big = smem;
     }
-    k_force<TM_MAX_SYM, TM_MAX_SYM><<<blocks, FORCE_WARPS * 32, smem, c->stream>>>(
+    TM_LAUNCH((k_force<TM_MAX_SYM, TM_MAX_SYM>), blocks, FORCE_WARPS * 32, smem, c->stream, 
         (const SAtom*)c->b_satom.p, (const int32_t*)c->b_rowsidx.p, (const int32_t*)c->b_rowslot.p, (const int32_t*)c->b_nbcnt.p,
         (const uint32_t*)c->b_nbr.p, s.nrows, P, (const float*)c->b_dG[TM_NET_ENERGY].p, (const float*)c->b_dG[TM_NET_CHARGE].p,
         (const double*)c->b_dedq.p, (const double*)c->b_molacc.p, (const double*)c->b_natom.p, s.maxnatom, nreal_slots, fold, (float*)c->b_F.p,

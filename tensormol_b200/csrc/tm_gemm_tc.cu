@@ -258,6 +258,9 @@ __device__ __forceinline__ float2 join2(uint32_t hi, uint32_t lo) {
 template <int EPI, int ACTK, int NCTA, int BN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_gemm_tc(const __grid_constant__ TcParams P, const int32_t* __restrict__ rowmeta) {
+  // programmatic dependent launch: the successor may be scheduled as this grid drains; this grid's own wait for its
+  // predecessor sits below, behind the barrier / TMEM set-up that needs none of the predecessor's data
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // BN = 128, or 64 (NCTA = 1 only) for launches with few row tiles (slab ranks, small systems): twice the tiles of half
   // the width fill the 148 SMs more evenly (208 tiles of 128 columns = 2 waves for 1.4 waves of work).  With BN = 64 a
@@ -286,15 +289,6 @@ k_gemm_tc(const __grid_constant__ TcParams P, const int32_t* __restrict__ rowmet
   const int unit = blockIdx.x / NCTA, nunits = gridDim.x / NCTA;   // persistent loop over tiles (NCTA = 1) or tile pairs
 
   if (threadIdx.x == 0) {
-    int acc = 0;
-    for (int g = 0; g < P.ngroups; g++) {
-      tile_base[g] = acc;
-      int rows = rowmeta[2 * P.g[g].ele + 1];
-      row_first[g] = rowmeta[2 * P.g[g].ele];
-      row_tiles[g] = (rows + TC_BM - 1) / TC_BM;
-      acc += ((row_tiles[g] + NCTA - 1) / NCTA) * (P.g[g].N / BN);
-    }
-    tile_base[P.ngroups] = acc;
     for (int s = 0; s < STAGES; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     for (int a = 0; a < NPAIR; a++) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], NCTA * DRAIN_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -307,6 +301,18 @@ k_gemm_tc(const __grid_constant__ TcParams P, const int32_t* __restrict__ rowmet
       asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)(NPAIR * 2 * BN)));
       asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
+  }
+  asm volatile("griddepcontrol.wait;" ::: "memory");      // the row counts, operands and bias of this launch are valid from here on
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    for (int g = 0; g < P.ngroups; g++) {
+      tile_base[g] = acc;
+      int rows = rowmeta[2 * P.g[g].ele + 1];
+      row_first[g] = rowmeta[2 * P.g[g].ele];
+      row_tiles[g] = (rows + TC_BM - 1) / TC_BM;
+      acc += ((row_tiles[g] + NCTA - 1) / NCTA) * (P.g[g].N / BN);
+    }
+    tile_base[P.ngroups] = acc;
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   if (NCTA == 2) cluster_sync_all();   // barrier initialisation must be visible to the peer before any remote arrive
@@ -699,18 +705,20 @@ static int launch_tc(tm_ctx* c, const TcParams& P, const int* rowmeta_dev, int t
   if (total_units_bound < units) units = total_units_bound;
   if (units < 1) units = 1;
   if (NCTA == 1) {
-    k_gemm_tc<EPI, ACTK, NCTA, BN><<<units, TC_THREADS, smem, c->stream>>>(P, rowmeta_dev);
+    TM_LAUNCH((k_gemm_tc<EPI, ACTK, NCTA, BN>), units, TC_THREADS, smem, c->stream, P, rowmeta_dev);
   } else {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(units * NCTA));
     cfg.blockDim = dim3(TC_THREADS);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = c->stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = NCTA; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = tm_pdl_enabled() ? 2 : 1;
     TM_CUDA(cudaLaunchKernelEx(&cfg, k_gemm_tc<EPI, ACTK, NCTA, BN>, P, rowmeta_dev));
   }
   c->launches++;

@@ -161,7 +161,7 @@ struct tm_ctx {
   // ---- per-evaluation workspace (grow-only) ----
   DevBuf b_pos, b_Z, b_cellid, b_rank, b_count, b_cstart, b_sorted, b_satom, b_scan_tmp;
   DevBuf b_rowslot, b_rowsidx, b_rowofslot, b_blkcnt, b_rowmeta;
-  DevBuf b_cntall, b_offall, b_pe, b_pairtab;
+  DevBuf b_cntall, b_offall, b_pe, b_pairtab, b_lscan;
   // pair-potential tables of tm_pair.cu (rebuilt when the hyper-parameters change)
   uint64_t params_gen = 1, pairtab_gen = 0;
   int pt_kmin = 0, pt_nnodes = 0, pt_nfn = 0, pt_kink_k = -1, pt_kink_v = -1;
@@ -212,7 +212,24 @@ struct tm_ctx {
   int slab_flags = 0;
 };
 
+// Programmatic dependent launch: every kernel of the step lets its successor be scheduled early (its blocks start as the
+// SMs drain, launch latency and prologue overlap the predecessor's tail) and itself waits for its predecessors' memory
+// before touching anything.  TM_NO_PDL=1 in the environment launches without the attribute (measurements).
+int tm_pdl_enabled();
 #ifdef __CUDACC__
+#define TM_PDL_PROLOGUE asm volatile("griddepcontrol.launch_dependents;\n\tgriddepcontrol.wait;" ::: "memory")
+template <typename... KArgs, typename... Args>
+static inline cudaError_t tm_launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = tm_pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+#define TM_LAUNCH(kern, grid, block, smem, stream, ...) tm_launch_kernel(kern, dim3(grid), dim3(block), (size_t)(smem), stream, __VA_ARGS__)
 __device__ __forceinline__ int cell_coord(double v, double o, double inv, int g) {
   int c = (int)floor((v - o) * inv);
   return c < 0 ? 0 : (c >= g ? g - 1 : c);

@@ -58,6 +58,7 @@ __device__ __forceinline__ float act_bwd_from_h(float h, int kind, float alpha) 
 
 __global__ void __launch_bounds__(256)
 k_gemm_simt(const __grid_constant__ GemmGroupTbl tbl, const int32_t* __restrict__ rowmeta, int epilogue, int act_kind, float act_alpha) {
+  TM_PDL_PROLOGUE;
   const GemmGroup& G = tbl.g[blockIdx.z];
   int rows_e = rowmeta[2 * G.ele + 1];
   int rt = blockIdx.x;
@@ -161,7 +162,7 @@ int tm_launch_gemm(tm_ctx* c, const GemmGroup* groups, int ngroups, const int* r
     }
   }
   dim3 grid((unsigned)max_row_tiles, (unsigned)(maxN / BN), (unsigned)ngroups);
-  k_gemm_simt<<<grid, 256, 0, c->stream>>>(tbl, rowmeta_dev, epilogue, c->hp.activation, c->hp.act_alpha);
+  TM_LAUNCH(k_gemm_simt, grid, 256, 0, c->stream, tbl, rowmeta_dev, epilogue, c->hp.activation, c->hp.act_alpha);
   c->launches++;
   TM_CUDA(cudaGetLastError());
   return TM_OK;
@@ -192,6 +193,7 @@ __device__ __forceinline__ int row_element(const int32_t* rowmeta, int64_t row, 
 // one warp per (row, net): y = h . w + b ; delta = w * a'(h)
 __global__ void k_out_layer(const __grid_constant__ OutTbl T, const int32_t* __restrict__ rowmeta, int64_t nrows, int n_ele, int act_kind,
                             float act_alpha) {
+  TM_PDL_PROLOGUE;
   int64_t wid = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   int lane = threadIdx.x & 31;
   int net = (int)(wid & 1);
@@ -227,6 +229,7 @@ struct YTbl {
 __global__ void __launch_bounds__(256)
 k_y_reduce(const __grid_constant__ YTbl T, const int32_t* __restrict__ rowmeta, int64_t nrows, int n_ele, int np,
            const int32_t* __restrict__ rowslot, int64_t maxnatom, double* __restrict__ qraw_slot, double* __restrict__ molacc, int sum_q) {
+  TM_PDL_PROLOGUE;
   __shared__ int s_m[8];
   __shared__ double s_q[8], s_e[8];
   int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -375,7 +378,7 @@ int tm_launch_mlp_forward(tm_ctx* c, const SysView& s) {
       qraw = (double*)c->b_q.p;
       TM_CUDA(cudaMemsetAsync(qraw, 0, (size_t)nq * 8, c->stream));   // slots without a row (padding) stay 0
     }
-    k_y_reduce<<<(unsigned)((2 * s.nrows + 255) / 256), 256, 0, c->stream>>>(Y, (const int32_t*)c->b_rowmeta.p, s.nrows, ne, np,
+    TM_LAUNCH(k_y_reduce, (unsigned)((2 * s.nrows + 255) / 256), 256, 0, c->stream, Y, (const int32_t*)c->b_rowmeta.p, s.nrows, ne, np,
                                                                            (const int32_t*)c->b_rowslot.p, s.maxnatom, qraw, (double*)c->b_molacc.p,
                                                                            s.slab_api ? 0 : 1);
     c->launches++;
@@ -398,7 +401,7 @@ int tm_launch_mlp_forward(tm_ctx* c, const SysView& s) {
   T.H = c->desc.hidden[nh - 1];
   int64_t nw = s.nrows * 2;
   int blocks = (int)((nw * 32 + 255) / 256);
-  k_out_layer<<<blocks, 256, 0, c->stream>>>(T, (const int32_t*)c->b_rowmeta.p, s.nrows, ne, c->hp.activation, c->hp.act_alpha);
+  TM_LAUNCH(k_out_layer, blocks, 256, 0, c->stream, T, (const int32_t*)c->b_rowmeta.p, s.nrows, ne, c->hp.activation, c->hp.act_alpha);
   c->launches++;
   TM_CUDA(cudaGetLastError());
   return TM_OK;

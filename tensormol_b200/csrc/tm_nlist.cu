@@ -35,6 +35,7 @@ __device__ __forceinline__ double dec_d(unsigned long long b) {
 __global__ void k_tessellate(const double* __restrict__ xyz, const int32_t* __restrict__ Z, int64_t nreal,
                              const __grid_constant__ LatArgs L, int ntess, int ilo, int ihi, double* __restrict__ pos, int32_t* __restrict__ Zo,
                              double* __restrict__ inv_n) {
+  TM_PDL_PROLOGUE;
   const double* lat = L.v;
   if (blockIdx.x == 0 && threadIdx.x == 0) inv_n[0] = L.v[9];
   int side = 2 * ntess + 1;
@@ -71,7 +72,7 @@ int tm_launch_tessellate(tm_ctx* c, const double* xyz_real, const int32_t* Z_rea
   int64_t total = (int64_t)side * side * side * nreal;
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
-  k_tessellate<<<blocks, 256, 0, c->stream>>>(xyz_real, Z_real, nreal, lat, ntess, ilo, ihi, (double*)c->b_pos.p, (int32_t*)c->b_Z.p, (double*)c->b_natom.p);
+  TM_LAUNCH(k_tessellate, blocks, 256, 0, c->stream, xyz_real, Z_real, nreal, lat, ntess, ilo, ihi, (double*)c->b_pos.p, (int32_t*)c->b_Z.p, (double*)c->b_natom.p);
   c->launches++;
   TM_CUDA(cudaGetLastError());
   return TM_OK;
@@ -101,11 +102,13 @@ __device__ __forceinline__ bool slot_in_window(const double* __restrict__ pos, i
   return f >= w.lo && f <= w.hi;
 }
 __global__ void k_bbox_init(unsigned long long* bb) {
+  TM_PDL_PROLOGUE;
   if (threadIdx.x < 3) bb[threadIdx.x] = 0xffffffffffffffffull;   // mins
   else if (threadIdx.x < 6) bb[threadIdx.x] = 0ull;               // maxs
 }
 
 __global__ void k_bbox(const double* __restrict__ pos, const int32_t* __restrict__ Z, int64_t n, Window win, unsigned long long* bb) {
+  TM_PDL_PROLOGUE;
   double mn[3] = {1e300, 1e300, 1e300}, mx[3] = {-1e300, -1e300, -1e300};
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
     if (image_block_skipped(t, win) || Z[t] <= 0 || !slot_in_window(pos, t, win)) continue;
@@ -143,6 +146,7 @@ __global__ void k_bbox(const double* __restrict__ pos, const int32_t* __restrict
 
 // one thread: grid geometry from the bbox; grows the cell edge until nmol*gx*gy*gz fits the cap
 __global__ void k_grid_params(const unsigned long long* bb, double rc, int64_t nmol, int64_t ncells_cap, GridParams* g) {
+  TM_PDL_PROLOGUE;
   double mn[3], mx[3];
   for (int d = 0; d < 3; d++) {
     mn[d] = dec_d(bb[d]);
@@ -176,6 +180,7 @@ __global__ void k_grid_params(const unsigned long long* bb, double rc, int64_t n
 __global__ void k_cell_count(const double* __restrict__ pos, const int32_t* __restrict__ Z, int64_t n, int64_t maxnatom,
                              GridParams* gp, const __grid_constant__ GridParams hg, Window win, int check_inside, int32_t* __restrict__ cellid,
                              int32_t* __restrict__ rank, int32_t* __restrict__ count, int32_t* __restrict__ flags) {
+  TM_PDL_PROLOGUE;
   GridParams g = check_inside ? hg : *gp;
   if (check_inside && blockIdx.x == 0 && threadIdx.x == 0) *gp = hg;
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
@@ -198,6 +203,7 @@ __global__ void k_cell_count(const double* __restrict__ pos, const int32_t* __re
 // ---------------------------------------------------------------- exclusive scan (3 kernels, int32)
 #define SCAN_TILE 2048   // elements per block (256 threads x 8)
 __global__ void k_scan_local(const int32_t* __restrict__ in, int32_t* __restrict__ out, int32_t* __restrict__ blksum, int64_t n) {
+  TM_PDL_PROLOGUE;
   __shared__ int32_t wsum[8];
   int64_t base = (int64_t)blockIdx.x * SCAN_TILE + threadIdx.x * 8;
   int32_t v[8], s = 0;
@@ -227,6 +233,7 @@ __global__ void k_scan_local(const int32_t* __restrict__ in, int32_t* __restrict
 }
 // single block: exclusive scan of block sums (nblk <= 1<<20), also writes the grand total at [nblk]
 __global__ void k_scan_blocks(int32_t* blksum, int nblk) {
+  TM_PDL_PROLOGUE;
   __shared__ int32_t wsum[32];
   __shared__ int32_t carry;
   if (threadIdx.x == 0) carry = 0;
@@ -262,6 +269,7 @@ __global__ void k_scan_blocks(int32_t* blksum, int nblk) {
   if (threadIdx.x == 0) blksum[nblk] = carry;
 }
 __global__ void k_scan_add(int32_t* __restrict__ out, const int32_t* __restrict__ blksum, int64_t n, int nblk) {
+  TM_PDL_PROLOGUE;
   int64_t base = (int64_t)blockIdx.x * SCAN_TILE + threadIdx.x * 8;
   int32_t off = blksum[blockIdx.x];
 #pragma unroll
@@ -273,6 +281,7 @@ __global__ void k_scan_add(int32_t* __restrict__ out, const int32_t* __restrict_
 // k_scan_blocks + k_scan_add in one launch for moderate block counts: every block sums the (unscanned) totals of the
 // blocks before it by itself
 __global__ void k_scan_add_self(int32_t* __restrict__ out, const int32_t* __restrict__ blksum, int64_t n, int nblk) {
+  TM_PDL_PROLOGUE;
   __shared__ int32_t wsum[8];
   __shared__ int32_t off_s;
   int32_t part = 0;
@@ -300,15 +309,15 @@ __global__ void k_scan_add_self(int32_t* __restrict__ out, const int32_t* __rest
 static int scan_exclusive(tm_ctx* c, const int32_t* in, int32_t* out, int64_t n, int32_t* tmp) {
   int nblk = (int)((n + SCAN_TILE - 1) / SCAN_TILE);
   if (nblk < 1) nblk = 1;
-  k_scan_local<<<nblk, 256, 0, c->stream>>>(in, out, tmp, n);
+  TM_LAUNCH(k_scan_local, nblk, 256, 0, c->stream, in, out, tmp, n);
   if (nblk <= 2048) {
-    k_scan_add_self<<<nblk, 256, 0, c->stream>>>(out, tmp, n, nblk);
+    TM_LAUNCH(k_scan_add_self, nblk, 256, 0, c->stream, out, tmp, n, nblk);
     c->launches += 2;
     TM_CUDA(cudaGetLastError());
     return TM_OK;
   }
-  k_scan_blocks<<<1, 1024, 0, c->stream>>>(tmp, nblk);
-  k_scan_add<<<nblk, 256, 0, c->stream>>>(out, tmp, n, nblk);
+  TM_LAUNCH(k_scan_blocks, 1, 1024, 0, c->stream, tmp, nblk);
+  TM_LAUNCH(k_scan_add, nblk, 256, 0, c->stream, out, tmp, n, nblk);
   c->launches += 3;
   TM_CUDA(cudaGetLastError());
   return TM_OK;
@@ -316,6 +325,7 @@ static int scan_exclusive(tm_ctx* c, const int32_t* in, int32_t* out, int64_t n,
 
 __global__ void k_scatter(const int32_t* __restrict__ cellid, const int32_t* __restrict__ rank, const int32_t* __restrict__ cstart,
                           int64_t n, Window win, int32_t* __restrict__ sorted) {
+  TM_PDL_PROLOGUE;
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
     if (image_block_skipped(t, win)) continue;
     int cid = cellid[t];
@@ -329,6 +339,7 @@ __global__ void k_scatter(const int32_t* __restrict__ cellid, const int32_t* __r
 __global__ void k_cell_sort_gather(const GridParams* __restrict__ gp, const int32_t* __restrict__ cstart, int32_t* __restrict__ sorted,
                                    const double* __restrict__ pos, const int32_t* __restrict__ Z, const __grid_constant__ DevParams P,
                                    SAtom* __restrict__ sat, int32_t* __restrict__ sidx_of_slot) {
+  TM_PDL_PROLOGUE;
   int ncells = gp->ncells;
   int lane = threadIdx.x & 31;
   int warps = (gridDim.x * blockDim.x) >> 5;
@@ -392,21 +403,21 @@ int tm_launch_nlist_build(tm_ctx* c, const SysView& s, double rc_grid) {
   if (s.grid_host) {
     ncs = s.hgrid.ncells;     // k_cell_count publishes the grid
   } else {
-    k_bbox_init<<<1, 32, 0, c->stream>>>(bb);
-    k_bbox<<<blocks, 256, 0, c->stream>>>((const double*)c->b_pos.p, (const int32_t*)c->b_Z.p, n, win, bb);
-    k_grid_params<<<1, 1, 0, c->stream>>>(bb, rc_grid, s.nmol, s.ncells_cap, gp);
+    TM_LAUNCH(k_bbox_init, 1, 32, 0, c->stream, bb);
+    TM_LAUNCH(k_bbox, blocks, 256, 0, c->stream, (const double*)c->b_pos.p, (const int32_t*)c->b_Z.p, n, win, bb);
+    TM_LAUNCH(k_grid_params, 1, 1, 0, c->stream, bb, rc_grid, s.nmol, s.ncells_cap, gp);
     c->launches += 3;
   }
   TM_CUDA(cudaMemsetAsync(c->b_count.p, 0, (ncs + 8) * 4, c->stream));
-  k_cell_count<<<blocks, 256, 0, c->stream>>>((const double*)c->b_pos.p, (const int32_t*)c->b_Z.p, n, s.maxnatom, gp, s.hgrid, win, s.grid_host,
+  TM_LAUNCH(k_cell_count, blocks, 256, 0, c->stream, (const double*)c->b_pos.p, (const int32_t*)c->b_Z.p, n, s.maxnatom, gp, s.hgrid, win, s.grid_host,
                                               (int32_t*)c->b_cellid.p, (int32_t*)c->b_rank.p, (int32_t*)c->b_count.p, (int32_t*)c->b_flags.p);
   c->launches += 1;
   if ((rc = scan_exclusive(c, (const int32_t*)c->b_count.p, (int32_t*)c->b_cstart.p, ncs, (int32_t*)c->b_scan_tmp.p))) return rc;
-  k_scatter<<<blocks, 256, 0, c->stream>>>((const int32_t*)c->b_cellid.p, (const int32_t*)c->b_rank.p, (const int32_t*)c->b_cstart.p, n, win,
+  TM_LAUNCH(k_scatter, blocks, 256, 0, c->stream, (const int32_t*)c->b_cellid.p, (const int32_t*)c->b_rank.p, (const int32_t*)c->b_cstart.p, n, win,
                                            (int32_t*)c->b_sorted.p);
   int cblocks = (int)((ncs * 32 + 255) / 256);
   if (cblocks > 148 * 32) cblocks = 148 * 32;
-  k_cell_sort_gather<<<cblocks, 256, 0, c->stream>>>(gp, (const int32_t*)c->b_cstart.p, (int32_t*)c->b_sorted.p, (const double*)c->b_pos.p,
+  TM_LAUNCH(k_cell_sort_gather, cblocks, 256, 0, c->stream, gp, (const int32_t*)c->b_cstart.p, (int32_t*)c->b_sorted.p, (const double*)c->b_pos.p,
                                                      (const int32_t*)c->b_Z.p, c->hp, (SAtom*)c->b_satom.p, (int32_t*)c->b_rank.p);
   c->launches += 2;
   TM_CUDA(cudaGetLastError());
@@ -438,6 +449,7 @@ __device__ __forceinline__ bool is_centre(const SAtom& a, int64_t nreal, int per
 __global__ void k_rows_count(const SAtom* __restrict__ sat, const int32_t* __restrict__ cstart, const GridParams* __restrict__ gp,
                              int64_t nreal, int periodic, SlabFilter sf, int32_t* __restrict__ blkcnt, int32_t* __restrict__ rowslot,
                              int64_t nrows, int32_t* __restrict__ rowofslot, int64_t nq) {
+  TM_PDL_PROLOGUE;
   __shared__ int32_t cnt[TM_MAX_ELE];
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < nrows + nq; t += (int64_t)gridDim.x * blockDim.x) {
     if (t < nrows) rowslot[t] = -1;
@@ -460,6 +472,7 @@ __global__ void k_rows_count(const SAtom* __restrict__ sat, const int32_t* __res
 // single block: per element exclusive scan over blocks; element bases padded to TM_ROW_TILE
 __global__ void k_rows_scan(int32_t* __restrict__ blkcnt, int nblk, int n_ele, const int32_t* __restrict__ cstart,
                             const GridParams* __restrict__ gp, int32_t* __restrict__ rowmeta) {
+  TM_PDL_PROLOGUE;
   __shared__ int32_t tot[TM_MAX_ELE];
   nblk = min(nblk, (cstart[gp->ncells] + ROWS_BLOCK - 1) / ROWS_BLOCK);
   int e = threadIdx.x >> 5, lane = threadIdx.x & 31;   // one warp per element; a lane owns 32 consecutive blocks of a 1024-block chunk
@@ -512,6 +525,7 @@ __global__ void k_rows_fill(const SAtom* __restrict__ sat, const int32_t* __rest
                             int64_t nreal, int periodic, SlabFilter sf, const int32_t* __restrict__ blkcnt,
                             int32_t* __restrict__ rowmeta, int32_t* __restrict__ rowslot, int32_t* __restrict__ rowsidx,
                             int32_t* __restrict__ rowofslot, int self_scan, int nblk, int n_ele) {
+  TM_PDL_PROLOGUE;
   __shared__ int32_t wcnt[32][TM_MAX_ELE];
   __shared__ int32_t s_pre[32][TM_MAX_ELE], s_tot[32][TM_MAX_ELE];
   __shared__ int32_t s_base[TM_MAX_ELE], s_mine[TM_MAX_ELE];
@@ -593,15 +607,15 @@ int tm_launch_rows(tm_ctx* c, const SysView& s) {
   const SAtom* sat = (const SAtom*)c->b_satom.p;
   const GridParams* gp = (const GridParams*)c->b_grid.p;
   SlabFilter sf{s.slab_rank, s.slab_world, s.slab_g[0], s.slab_g[1], s.slab_g[2]};
-  k_rows_count<<<nblk, ROWS_BLOCK, 0, c->stream>>>(sat, (const int32_t*)c->b_cstart.p, gp, s.nreal, s.periodic, sf,
+  TM_LAUNCH(k_rows_count, nblk, ROWS_BLOCK, 0, c->stream, sat, (const int32_t*)c->b_cstart.p, gp, s.nreal, s.periodic, sf,
                                                    (int32_t*)c->b_blkcnt.p, (int32_t*)c->b_rowslot.p, s.nrows, (int32_t*)c->b_rowofslot.p, nq);
   const int self_scan = nblk <= 2048 ? 1 : 0;   // every fill block re-reads the nblk counts: only while that is cheap
   if (!self_scan) {
-    k_rows_scan<<<1, 32 * TM_MAX_ELE, 0, c->stream>>>((int32_t*)c->b_blkcnt.p, nblk, c->hp.n_ele, (const int32_t*)c->b_cstart.p, gp,
+    TM_LAUNCH(k_rows_scan, 1, 32 * TM_MAX_ELE, 0, c->stream, (int32_t*)c->b_blkcnt.p, nblk, c->hp.n_ele, (const int32_t*)c->b_cstart.p, gp,
                                                       (int32_t*)c->b_rowmeta.p);
     c->launches++;
   }
-  k_rows_fill<<<nblk, ROWS_BLOCK, 0, c->stream>>>(sat, (const int32_t*)c->b_cstart.p, gp, s.nreal, s.periodic, sf,
+  TM_LAUNCH(k_rows_fill, nblk, ROWS_BLOCK, 0, c->stream, sat, (const int32_t*)c->b_cstart.p, gp, s.nreal, s.periodic, sf,
                                                   (const int32_t*)c->b_blkcnt.p, (int32_t*)c->b_rowmeta.p, (int32_t*)c->b_rowslot.p,
                                                   (int32_t*)c->b_rowsidx.p, (int32_t*)c->b_rowofslot.p, self_scan, nblk, c->hp.n_ele);
   c->launches += 2;
@@ -646,6 +660,7 @@ __device__ __forceinline__ bool accept(double d2, const AcceptBand& a) {
 __global__ void k_neighbours(const SAtom* __restrict__ sat, const int32_t* __restrict__ cstart, const GridParams* __restrict__ gp,
                              const int32_t* __restrict__ rowsidx, const int32_t* __restrict__ rowslot, int64_t nrows, int64_t maxnatom,
                              double rr, double ra, int32_t* __restrict__ nbcnt, uint32_t* __restrict__ nbr, int32_t* __restrict__ flags) {
+  TM_PDL_PROLOGUE;
   int64_t row = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   int lane = threadIdx.x & 31;
   if (row >= nrows) return;
@@ -729,7 +744,7 @@ int tm_launch_neighbours(tm_ctx* c, const SysView& s) {
   if ((rc = tm_buf(c, c->b_nbcnt, (s.nrows + 8) * 4))) return rc;
   if ((rc = tm_buf(c, c->b_nbr, (size_t)s.nrows * TM_NB_STRIDE * 4))) return rc;
   int blocks = (int)((s.nrows * 32 + 255) / 256);
-  k_neighbours<<<blocks, 256, 0, c->stream>>>((const SAtom*)c->b_satom.p, (const int32_t*)c->b_cstart.p, (const GridParams*)c->b_grid.p,
+  TM_LAUNCH(k_neighbours, blocks, 256, 0, c->stream, (const SAtom*)c->b_satom.p, (const int32_t*)c->b_cstart.p, (const GridParams*)c->b_grid.p,
                                               (const int32_t*)c->b_rowsidx.p, (const int32_t*)c->b_rowslot.p, s.nrows, s.maxnatom,
                                               c->hp.rr_exact, c->hp.ra_exact, (int32_t*)c->b_nbcnt.p, (uint32_t*)c->b_nbr.p,
                                               (int32_t*)c->b_flags.p);
@@ -744,6 +759,7 @@ template <bool FILL>
 __global__ void k_nlist_csr(const SAtom* __restrict__ sat, const int32_t* __restrict__ cstart, const GridParams* __restrict__ gp,
                             const int32_t* __restrict__ sidx_of_slot, int64_t ncentres, int64_t maxnatom, double rc, int do_perms,
                             int32_t* __restrict__ cnt, const int64_t* __restrict__ off, int32_t* __restrict__ out) {
+  TM_PDL_PROLOGUE;
   int64_t i = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   int lane = threadIdx.x & 31;
   if (i >= ncentres) return;
@@ -785,6 +801,7 @@ __global__ void k_nlist_csr(const SAtom* __restrict__ sat, const int32_t* __rest
 }
 
 __global__ void k_mark_unsorted(int32_t* sidx_of_slot, int64_t n) {
+  TM_PDL_PROLOGUE;
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) sidx_of_slot[t] = -1;
 }
 
@@ -799,7 +816,7 @@ int tm_launch_nlist_csr(tm_ctx* c, const SysView& s, double rc, int do_perms, in
   const GridParams* gp = (const GridParams*)c->b_grid.p;
   int blocks = (int)((ncent * 32 + 255) / 256);
   if (blocks < 1) blocks = 1;
-  k_nlist_csr<false><<<blocks, 256, 0, c->stream>>>(sat, (const int32_t*)c->b_cstart.p, gp, (const int32_t*)c->b_rank.p, ncent, s.maxnatom, rc,
+  TM_LAUNCH(k_nlist_csr<false>, blocks, 256, 0, c->stream, sat, (const int32_t*)c->b_cstart.p, gp, (const int32_t*)c->b_rank.p, ncent, s.maxnatom, rc,
                                                     do_perms, (int32_t*)c->b_nbcnt.p, nullptr, nullptr);
   c->launches++;
   TM_CUDA(cudaGetLastError());
@@ -813,7 +830,7 @@ int tm_launch_nlist_csr(tm_ctx* c, const SysView& s, double rc, int do_perms, in
   if ((r = tm_buf(c, c->b_nboff, (ncent + 8) * 8))) return r;
   if ((r = tm_buf(c, c->b_nbr, (size_t)(total + 8) * 4))) return r;
   TM_CUDA(cudaMemcpyAsync(c->b_nboff.p, c->h_off.data(), (size_t)(ncent + 1) * 8, cudaMemcpyHostToDevice, c->stream));
-  k_nlist_csr<true><<<blocks, 256, 0, c->stream>>>(sat, (const int32_t*)c->b_cstart.p, gp, (const int32_t*)c->b_rank.p, ncent, s.maxnatom, rc,
+  TM_LAUNCH(k_nlist_csr<true>, blocks, 256, 0, c->stream, sat, (const int32_t*)c->b_cstart.p, gp, (const int32_t*)c->b_rank.p, ncent, s.maxnatom, rc,
                                                    do_perms, nullptr, (const int64_t*)c->b_nboff.p, (int32_t*)c->b_nbr.p);
   c->launches++;
   TM_CUDA(cudaGetLastError());
@@ -834,7 +851,7 @@ int tm_launch_nlist_csr(tm_ctx* c, const SysView& s, double rc, int do_perms, in
 // reference's left-to-right float64 arithmetic for the image position, so that everything downstream (neighbour rows,
 // descriptor / pair / force kernels, the reference force convention on slot ids) is unchanged and bit-identical.
 //   k_lat_count   counts per cell (all binned atoms) and per (element, cell) (centres), copies the real block
-//   k_scan_segments  exclusive scans of [cell counts | centre counts e = 0 | e = 1 | ...], one block per segment
+//   k_lat_scan    exclusive scans of [cell counts | centre counts e = 0 | e = 1 | ...]: chunk-local + chunk offsets, one launch
 //   k_lat_scatter 32-byte records into their cells (arrival order)
 //   k_lat_sort_rows  one warp per cell: order by slot id, assign the centre rows (element, cell order, slot)
 struct LatBin {
@@ -900,6 +917,7 @@ __global__ void k_lat_count(const double* __restrict__ xyz, const int32_t* __res
                             const __grid_constant__ DevParams P, double* __restrict__ pos, int32_t* __restrict__ Zo, double* __restrict__ inv_n,
                             GridParams* __restrict__ gp, int32_t* __restrict__ cnt_all, int32_t* __restrict__ flags, int32_t* __restrict__ rowslot,
                             int64_t nrows, int32_t* __restrict__ rowofslot) {
+  TM_PDL_PROLOGUE;
   const int64_t t0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
   if (t0 == 0) { inv_n[0] = B.inv_n; *gp = B.g; }
   for (int64_t t = t0; t < nrows; t += stride) rowslot[t] = -1;
@@ -930,70 +948,79 @@ __global__ void k_lat_count(const double* __restrict__ xyz, const int32_t* __res
   }
 }
 
-// exclusive scans of the segments [n0 | n1 | n1 | ...] of `in` (segment s starts at s ? p0 + (s-1) p1 : 0, strides
-// padded to 4 ints), one 1024-thread block each; `out` has the same layout, with the segment total behind its n entries.
-// A warp owns 1024 consecutive ints of a 32k pass and reads them as 8 coalesced int4 rows (lane = 4 ints), carrying its
-// running sum from row to row; the 32 warp totals are scanned once per pass.
-#define SEG_ROWS 8
-__global__ void __launch_bounds__(1024) k_scan_segments(const int32_t* __restrict__ in, int32_t* __restrict__ out, int n0, int n1) {
-  __shared__ int32_t wsum[32];
-  __shared__ int32_t carry_s, tot_s;
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int sgm = blockIdx.x;
-  const int n = sgm == 0 ? n0 : n1;
-  const int64_t off = sgm == 0 ? 0 : (int64_t)pad4(n0) + (int64_t)(sgm - 1) * pad4(n1);
-  in += off;
-  out += off;
-  if (threadIdx.x == 0) carry_s = 0;
-  __syncthreads();
-  for (int base = 0; base < n; base += 1024 * 4 * SEG_ROWS) {
-    const int32_t carry = carry_s;
-    const int wb = base + w * (128 * SEG_ROWS);
-    int4 v[SEG_ROWS];
-    int32_t ex[SEG_ROWS];
-    int32_t running = 0;
+// Exclusive scans of the segments [n0 | n1 | n1 | ...] of `in` (segment s starts at s ? p0 + (s-1) p1 : 0, strides padded
+// to 4 ints with at least one zero behind the n entries, so the scan value at index n is the segment total).  One launch:
+// block b scans one 2048-element chunk locally and publishes the chunk total; the block that finishes last scans the
+// chunk totals of every segment.  Readers combine the two levels: off(i) = local[i] + coff[chunk of i] (LatScan::at).
+#define LSCAN_CH 2048
+struct LatScan {
+  const int32_t* local;   // chunk-local exclusive scans, same layout as `in`
+  const int32_t* coff;    // exclusive scan of the chunk totals, per segment: [nch0 | nch1 | nch1 | ...]
+  int p0, p1, nch0, nch1;
+  __device__ __forceinline__ int at0(int i) const { return local[i] + coff[i / LSCAN_CH]; }                          // segment 0
+  __device__ __forceinline__ int at(int e, int i) const { return local[p0 + e * p1 + i] + coff[nch0 + e * nch1 + i / LSCAN_CH]; }   // segment 1 + e
+};
+__global__ void __launch_bounds__(256) k_lat_scan(const int32_t* __restrict__ in, int32_t* __restrict__ local, int32_t* __restrict__ ctot,
+                                                  int32_t* __restrict__ coff, int32_t* __restrict__ done, int n0, int n1, int nseg) {
+  TM_PDL_PROLOGUE;
+  __shared__ int32_t wsum[8];
+  __shared__ int is_last;
+  const int p0 = pad4(n0), p1 = pad4(n1);
+  const int nch0 = (n0 + 1 + LSCAN_CH - 1) / LSCAN_CH, nch1 = (n1 + 1 + LSCAN_CH - 1) / LSCAN_CH;
+  int blk = blockIdx.x, sgm = 0, ch = blk;
+  if (blk >= nch0) { sgm = 1 + (blk - nch0) / nch1; ch = (blk - nch0) % nch1; }
+  const int n = (sgm == 0 ? n0 : n1) + 1;                         // the zero behind the entries is scanned too
+  const int64_t off = sgm == 0 ? 0 : (int64_t)p0 + (int64_t)(sgm - 1) * p1;
+  const int base = ch * LSCAN_CH + threadIdx.x * 8;
+  int32_t v[8], sum = 0;
+  if (base + 7 < n) {
+    const int4 a = *reinterpret_cast<const int4*>(in + off + base), b2 = *reinterpret_cast<const int4*>(in + off + base + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b2.x; v[5] = b2.y; v[6] = b2.z; v[7] = b2.w;
+  } else {
 #pragma unroll
-    for (int k = 0; k < SEG_ROWS; k++) {
-      const int i = wb + k * 128 + lane * 4;
-      v[k] = make_int4(0, 0, 0, 0);
-      if (i + 3 < n) v[k] = *reinterpret_cast<const int4*>(in + i);
-      else if (i < n) { v[k].x = in[i]; if (i + 1 < n) v[k].y = in[i + 1]; if (i + 2 < n) v[k].z = in[i + 2]; }
-      const int32_t t = v[k].x + v[k].y + v[k].z + v[k].w;
-      int32_t inc = t;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) { int32_t u = __shfl_up_sync(FULL, inc, o); if (lane >= o) inc += u; }
-      ex[k] = running + inc - t;
-      running += __shfl_sync(FULL, inc, 31);
-    }
-    if (lane == 0) wsum[w] = running;
-    __syncthreads();
-    if (w == 0) {
-      int32_t x = wsum[lane], xi = x;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) { int32_t u = __shfl_up_sync(FULL, xi, o); if (lane >= o) xi += u; }
-      wsum[lane] = xi - x;            // exclusive warp offsets
-      if (lane == 31) tot_s = xi;     // pass total
-    }
-    __syncthreads();
-    const int32_t b0 = carry + wsum[w];
-#pragma unroll
-    for (int k = 0; k < SEG_ROWS; k++) {
-      const int i = wb + k * 128 + lane * 4;
-      const int32_t e0 = b0 + ex[k];
-      const int4 o4 = make_int4(e0, e0 + v[k].x, e0 + v[k].x + v[k].y, e0 + v[k].x + v[k].y + v[k].z);
-      if (i + 3 < n) *reinterpret_cast<int4*>(out + i) = o4;
-      else if (i < n) { out[i] = o4.x; if (i + 1 < n) out[i + 1] = o4.y; if (i + 2 < n) out[i + 2] = o4.z; }
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) carry_s = carry + tot_s;
-    __syncthreads();
+    for (int i = 0; i < 8; i++) v[i] = (base + i < n) ? in[off + base + i] : 0;
   }
-  if (threadIdx.x == 0) out[n] = carry_s;
+#pragma unroll
+  for (int i = 0; i < 8; i++) sum += v[i];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int32_t inc = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { int32_t t = __shfl_up_sync(FULL, inc, o); if (lane >= o) inc += t; }
+  if (lane == 31) wsum[w] = inc;
+  __syncthreads();
+  int32_t woff = 0, tot = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) { if (i < w) woff += wsum[i]; tot += wsum[i]; }
+  int32_t run = woff + inc - sum;
+#pragma unroll
+  for (int i = 0; i < 8; i++) { if (base + i < n) local[off + base + i] = run; run += v[i]; }
+  if (threadIdx.x == 0) {
+    ctot[blk] = tot;
+    __threadfence();
+    is_last = (atomicAdd(done, 1) == (int)gridDim.x - 1) ? 1 : 0;
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  // the last block: exclusive scan of the chunk totals of every segment (a few dozen values each), one warp per segment
+  for (int sg = w; sg < nseg; sg += 8) {
+    const int c0 = sg == 0 ? 0 : nch0 + (sg - 1) * nch1, nc = sg == 0 ? nch0 : nch1;
+    int32_t carry = 0;
+    for (int b0 = 0; b0 < nc; b0 += 32) {
+      int32_t x = (b0 + lane < nc) ? ((volatile int32_t*)ctot)[c0 + b0 + lane] : 0, xi = x;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { int32_t t = __shfl_up_sync(FULL, xi, o); if (lane >= o) xi += t; }
+      if (b0 + lane < nc) coff[c0 + b0 + lane] = carry + xi - x;
+      carry += __shfl_sync(FULL, xi, 31);
+    }
+  }
+  if (threadIdx.x == 0) *done = 0;     // ready for the next step without a memset
 }
 
 __global__ void k_lat_scatter(const double* __restrict__ xyz, const int32_t* __restrict__ Z, const __grid_constant__ LatBin B,
-                              const __grid_constant__ DevParams P, int32_t* __restrict__ cnt_all, const int32_t* __restrict__ off_all,
+                              const __grid_constant__ DevParams P, int32_t* __restrict__ cnt_all, const LatScan SC,
                               SAtom* __restrict__ sat) {
+  TM_PDL_PROLOGUE;
   const int64_t t0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t t = t0; t < B.nreal * LAT_SUB; t += stride) {
     const int64_t a = t / LAT_SUB;
@@ -1011,7 +1038,7 @@ __global__ void k_lat_scatter(const double* __restrict__ xyz, const int32_t* __r
       r.x = xi; r.y = yi; r.z = zi;
       r.slot = (int32_t)((int64_t)b * B.nreal + a);
       r.e = e;
-      sat[off_all[cid] + p] = r;
+      sat[SC.at0(cid) + p] = r;
     });
   }
 }
@@ -1019,21 +1046,21 @@ __global__ void k_lat_scatter(const double* __restrict__ xyz, const int32_t* __r
 // One warp per group of zdiv z bins (one cell edge of a column: ~10 atoms in liquid water): order the records of every bin
 // by slot id (removes the arrival nondeterminism), then give every centre of the group its row: rows are ordered by
 // (element, bin, slot) and each element's range starts at a multiple of TM_ROW_TILE.
-// off_all = the scans of k_scan_segments: off_all[cid] = first record of bin cid (ncells + 1 entries), then per element
+// SC = the two-level scans of k_lat_scan: SC.at0(cid) = first record of bin cid (ncells + 1 entries), SC.at(e, g) per element
 // offc_e[g] = centres of element e in the groups before g (ngroups + 1 entries, total last).
-__global__ void k_lat_sort_rows(const __grid_constant__ LatBin B, int n_ele, const int32_t* __restrict__ off_all, int32_t* __restrict__ cstart,
+__global__ void k_lat_sort_rows(const __grid_constant__ LatBin B, int n_ele, const LatScan SC, int32_t* __restrict__ cstart,
                                 SAtom* __restrict__ sat, int32_t* __restrict__ rowmeta, int32_t* __restrict__ rowslot, int32_t* __restrict__ rowsidx,
                                 int32_t* __restrict__ rowofslot, int64_t nrows, int32_t* __restrict__ flags) {
+  TM_PDL_PROLOGUE;
   const int ncells = B.g.ncells, zdiv = B.g.zdiv, ngroups = ncells / zdiv;
   const int lane = threadIdx.x & 31;
   const int warps = (gridDim.x * blockDim.x) >> 5;
-  const int32_t* offc = off_all + pad4(ncells);      // element e: offc + e pad4(ngroups), ngroups + 1 entries
   int ebase[TM_MAX_ELE];
   {
     int base = 0, total = 0;
 #pragma unroll
     for (int e = 0; e < TM_MAX_ELE; e++) {
-      int cnt = (e < n_ele) ? offc[e * pad4(ngroups) + ngroups] : 0;
+      int cnt = (e < n_ele) ? SC.at(e, ngroups) : 0;
       ebase[e] = base;
       if (blockIdx.x == 0 && threadIdx.x == 0) { rowmeta[2 * e] = base; rowmeta[2 * e + 1] = cnt; }
       base += ((cnt + TM_ROW_TILE - 1) / TM_ROW_TILE) * TM_ROW_TILE;
@@ -1042,17 +1069,17 @@ __global__ void k_lat_sort_rows(const __grid_constant__ LatBin B, int n_ele, con
     if (blockIdx.x == 0 && threadIdx.x == 0) { rowmeta[2 * TM_MAX_ELE] = total; rowmeta[2 * TM_MAX_ELE + 1] = base; }
   }
   for (int grp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; grp <= ngroups; grp += warps) {
-    if (grp == ngroups) { if (lane == 0) cstart[ncells] = off_all[ncells]; continue; }
+    if (grp == ngroups) { if (lane == 0) cstart[ncells] = SC.at0(ncells); continue; }
     const int c0 = grp * zdiv;
     // bin boundaries of the group (zdiv <= 31): lane k holds off_all[c0 + k]
-    const int mybound = (lane <= zdiv) ? off_all[c0 + lane] : 0x7fffffff;
+    const int mybound = (lane <= zdiv) ? SC.at0(c0 + lane) : 0x7fffffff;
     if (lane < zdiv) cstart[c0 + lane] = mybound;
     const int b = __shfl_sync(FULL, mybound, 0), e = __shfl_sync(FULL, mybound, zdiv), n = e - b;
     if (n <= 0) continue;
     if (n > 32) {     // dense group: serial insertion sort per bin by lane 0, then the passes below only assign rows
       if (lane == 0) {
         for (int k = 0; k < zdiv; k++) {
-          const int bb = off_all[c0 + k], be = off_all[c0 + k + 1];
+          const int bb = SC.at0(c0 + k), be = SC.at0(c0 + k + 1);
           for (int i = bb + 1; i < be; i++) {
             SAtom v = sat[i];
             int j = i - 1;
@@ -1097,7 +1124,7 @@ __global__ void k_lat_sort_rows(const __grid_constant__ LatBin B, int n_ele, con
         // centres of element q of this pass as a bit mask over SORTED positions: those below this record come first
         const unsigned mq = __reduce_or_sync(FULL, (centre && mine.e == q) ? (1u << rank) : 0u);
         if (centre && mine.e == q) {
-          int row = ebase[q] + offc[q * pad4(ngroups) + grp] + seen[q] + __popc(mq & ((1u << rank) - 1u));
+          int row = ebase[q] + SC.at(q, grp) + seen[q] + __popc(mq & ((1u << rank) - 1u));
           if (row < nrows) {
             rowslot[row] = mine.slot;
             rowsidx[row] = b + p0 + rank;
@@ -1130,7 +1157,6 @@ int tm_launch_lattice_bin(tm_ctx* c, const SysView& s) {
   if ((rc = tm_buf(c, c->b_rowslot, (size_t)s.nrows * 4))) return rc;
   if ((rc = tm_buf(c, c->b_rowsidx, (size_t)s.nrows * 4))) return rc;
   if ((rc = tm_buf(c, c->b_rowofslot, (size_t)s.nreal * 4))) return rc;
-  if ((rc = tm_buf(c, c->b_scan_tmp, (size_t)(nall / SCAN_TILE + 16) * 4 * 2))) return rc;
   LatBin B;
   memcpy(B.L, s.lat.v, 72);
   memcpy(B.ginv, s.ginv, 72);
@@ -1142,21 +1168,28 @@ int tm_launch_lattice_bin(tm_ctx* c, const SysView& s) {
   B.g = s.hgrid;
   int32_t* cnt_all = (int32_t*)c->b_cntall.p;
   int32_t* off_all = (int32_t*)c->b_offall.p;
+  const int nch0 = (int)((ncells + 1 + LSCAN_CH - 1) / LSCAN_CH), nch1 = (int)((ngroups + 1 + LSCAN_CH - 1) / LSCAN_CH);
+  const int nchunks = nch0 + n_ele * nch1;
+  if ((rc = tm_buf(c, c->b_lscan, (size_t)(2 * nchunks + 16) * 4))) return rc;    // [chunk totals | chunk offsets | done counter]
+  int32_t* ctot = (int32_t*)c->b_lscan.p;
+  int32_t* coff = ctot + nchunks;
+  int32_t* done = coff + nchunks;      // zero from the allocation, reset by the kernel itself
+  LatScan SC{off_all, coff, (int)hpad4(ncells), (int)hpad4(ngroups), nch0, nch1};
   TM_CUDA(cudaMemsetAsync(cnt_all, 0, (size_t)(nall + 8) * 4, c->stream));
   int blocks = (int)((std::max<int64_t>(s.nreal * LAT_SUB, s.nrows) + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
-  k_lat_count<<<blocks, 256, 0, c->stream>>>(s.xyz_real, s.Z_real, B, c->hp, (double*)c->b_pos.p, (int32_t*)c->b_Z.p, (double*)c->b_natom.p,
+  TM_LAUNCH(k_lat_count, blocks, 256, 0, c->stream, s.xyz_real, s.Z_real, B, c->hp, (double*)c->b_pos.p, (int32_t*)c->b_Z.p, (double*)c->b_natom.p,
                                              (GridParams*)c->b_grid.p, cnt_all, (int32_t*)c->b_flags.p, (int32_t*)c->b_rowslot.p, s.nrows,
                                              (int32_t*)c->b_rowofslot.p);
   c->launches++;
-  k_scan_segments<<<1 + n_ele, 1024, 0, c->stream>>>(cnt_all, off_all, (int)ncells, (int)ngroups);
+  TM_LAUNCH(k_lat_scan, nchunks, 256, 0, c->stream, cnt_all, off_all, ctot, coff, done, (int)ncells, (int)ngroups, 1 + n_ele);
   c->launches++;
   int sblocks = (int)((s.nreal * LAT_SUB + 255) / 256);
   if (sblocks > 148 * 8) sblocks = 148 * 8;
-  k_lat_scatter<<<sblocks, 256, 0, c->stream>>>(s.xyz_real, s.Z_real, B, c->hp, cnt_all, off_all, (SAtom*)c->b_satom.p);
+  TM_LAUNCH(k_lat_scatter, sblocks, 256, 0, c->stream, s.xyz_real, s.Z_real, B, c->hp, cnt_all, SC, (SAtom*)c->b_satom.p);
   int cblocks = (int)(((ngroups + 1) * 32 + 255) / 256);
   if (cblocks > 148 * 16) cblocks = 148 * 16;
-  k_lat_sort_rows<<<cblocks, 256, 0, c->stream>>>(B, n_ele, off_all, (int32_t*)c->b_cstart.p, (SAtom*)c->b_satom.p, (int32_t*)c->b_rowmeta.p,
+  TM_LAUNCH(k_lat_sort_rows, cblocks, 256, 0, c->stream, B, n_ele, SC, (int32_t*)c->b_cstart.p, (SAtom*)c->b_satom.p, (int32_t*)c->b_rowmeta.p,
                                                   (int32_t*)c->b_rowslot.p, (int32_t*)c->b_rowsidx.p, (int32_t*)c->b_rowofslot.p, s.nrows,
                                                   (int32_t*)c->b_flags.p);
   c->launches += 2;

@@ -34,6 +34,7 @@
 // ---- charges -----------------------------------------------------------------------------------
 // y_charge[row] -> qraw_slot[slot]; per-molecule sums in double
 __global__ void k_qraw_scatter(const float* __restrict__ y, const int32_t* __restrict__ rowslot, int64_t nrows, double* __restrict__ qraw_slot) {
+  TM_PDL_PROLOGUE;
   for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < nrows; r += (int64_t)gridDim.x * blockDim.x) {
     int s = rowslot[r];
     if (s >= 0) qraw_slot[s] = (double)y[r];
@@ -42,6 +43,7 @@ __global__ void k_qraw_scatter(const float* __restrict__ y, const int32_t* __res
 
 // molsum[m] = sum over real slots of molecule m (one block per molecule chunk)
 __global__ void k_mol_sum(const double* __restrict__ v, const int32_t* __restrict__ Z, int64_t maxnatom, int64_t nvalid_per_mol, double* __restrict__ molacc, int field) {
+  TM_PDL_PROLOGUE;
   int m = blockIdx.x;
   double s = 0.0;
   for (int64_t a = blockIdx.y * (int64_t)blockDim.x + threadIdx.x; a < nvalid_per_mol; a += (int64_t)gridDim.y * blockDim.x) {
@@ -70,9 +72,37 @@ __global__ void k_mol_sum(const double* __restrict__ v, const int32_t* __restric
 __global__ void k_charges(const double* __restrict__ qraw_slot, double* __restrict__ molacc, const double* __restrict__ inv_n,
                           const double* __restrict__ pos, const int32_t* __restrict__ Z, int64_t maxnatom, int64_t nq_per_mol,
                           double* __restrict__ q_slot, const SAtom* __restrict__ sat, const int32_t* __restrict__ cstart,
-                          const GridParams* __restrict__ gp, int64_t nreal, int periodic, float4* __restrict__ pq, uint8_t* __restrict__ pe) {
+                          const GridParams* __restrict__ gp, int64_t nreal, int periodic, float4* __restrict__ pq, uint8_t* __restrict__ pe,
+                          int self_sum) {
+  TM_PDL_PROLOGUE;
   int m = blockIdx.y;
-  double mean = molacc[16 * m + 4] * inv_n[m];
+  // self_sum (one molecule, slab runs): every block forms sum q_raw by itself, all in the same order, instead of a separate
+  // reduction launch; block 0 publishes it
+  __shared__ double s_part[32];
+  __shared__ double s_total;
+  if (self_sum) {
+    double t = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0;     // four loads in flight per thread (the loop is pure L2 latency)
+    const int64_t bd = blockDim.x;
+    for (int64_t a = threadIdx.x; a < nq_per_mol; a += 4 * bd) {
+      t += (Z[a] > 0) ? qraw_slot[a] : 0.0;
+      if (a + bd < nq_per_mol) t1 += (Z[a + bd] > 0) ? qraw_slot[a + bd] : 0.0;
+      if (a + 2 * bd < nq_per_mol) t2 += (Z[a + 2 * bd] > 0) ? qraw_slot[a + 2 * bd] : 0.0;
+      if (a + 3 * bd < nq_per_mol) t3 += (Z[a + 3 * bd] > 0) ? qraw_slot[a + 3 * bd] : 0.0;
+    }
+    t = (t + t1) + (t2 + t3);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(FULL, t, o);
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = t;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double tt = 0.0;
+      for (int w = 0; w < (int)(blockDim.x >> 5); w++) tt += s_part[w];
+      s_total = tt;
+      if (blockIdx.x == 0) molacc[4] = tt;
+    }
+    __syncthreads();
+  }
+  double mean = (self_sum ? s_total : molacc[16 * m + 4]) * inv_n[m];
   double d0 = 0, d1 = 0, d2 = 0;
   for (int64_t a = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; a < nq_per_mol; a += (int64_t)gridDim.x * blockDim.x) {
     int64_t slot = (int64_t)m * maxnatom + a;
@@ -123,22 +153,26 @@ int tm_launch_charges(tm_ctx* c, const SysView& s) {
   // slab mode: qraw_slot was already combined over the ranks and written into b_q; otherwise the tensor-core forward
   // pass has scattered q_raw and summed it per molecule (k_y_reduce), and the fp32 mode does both here
   const bool fused = c->y_fused && !s.slab_api;
-  if (!fused) {
+  const int self_sum = (!fused && s.nmol == 1 && s.slab_api) ? 1 : 0;
+  if (!fused && !self_sum) {
     if (!s.slab_api) {
       int blocks = (int)((s.nrows + 255) / 256);
       TM_CUDA(cudaMemsetAsync(qraw, 0, (size_t)nq * 8, c->stream));
-      k_qraw_scatter<<<blocks, 256, 0, c->stream>>>((const float*)c->b_y[TM_NET_CHARGE].p, (const int32_t*)c->b_rowslot.p, s.nrows, qraw);
+      TM_LAUNCH(k_qraw_scatter, blocks, 256, 0, c->stream, (const float*)c->b_y[TM_NET_CHARGE].p, (const int32_t*)c->b_rowslot.p, s.nrows, qraw);
       c->launches++;
     }
     dim3 gms((unsigned)s.nmol, (unsigned)std::max<int64_t>(1, std::min<int64_t>((nq_per_mol + 2047) / 2048, 64)));
-    k_mol_sum<<<gms, 256, 0, c->stream>>>(qraw, (const int32_t*)c->b_Z.p, s.maxnatom, nq_per_mol, molacc, 4);
+    TM_LAUNCH(k_mol_sum, gms, 256, 0, c->stream, qraw, (const int32_t*)c->b_Z.p, s.maxnatom, nq_per_mol, molacc, 4);
     c->launches++;
   }
   int64_t per_mol = std::max<int64_t>(nq_per_mol, s.nslots / std::max<int64_t>(1, s.nmol));
-  dim3 g((unsigned)std::max<int64_t>(1, std::min<int64_t>((per_mol + 255) / 256, 148 * 8)), (unsigned)s.nmol);
-  k_charges<<<g, 256, 0, c->stream>>>(qraw, molacc, (const double*)c->b_natom.p, (const double*)c->b_pos.p, (const int32_t*)c->b_Z.p, s.maxnatom,
+  // the lattice path bins a few images per atom at most (window = cell + halo), and a block that sums q_raw by itself
+  // should not be one of thousands
+  int64_t cap_blocks = self_sum ? 74 : (s.lat_bin ? 148 * 2 : 148 * 8);
+  dim3 g((unsigned)std::max<int64_t>(1, std::min<int64_t>((per_mol + 255) / 256, cap_blocks)), (unsigned)s.nmol);
+  TM_LAUNCH(k_charges, g, self_sum ? 1024 : 256, 0, c->stream, qraw, molacc, (const double*)c->b_natom.p, (const double*)c->b_pos.p, (const int32_t*)c->b_Z.p, s.maxnatom,
                                       nq_per_mol, q, (const SAtom*)c->b_satom.p, (const int32_t*)c->b_cstart.p, (const GridParams*)c->b_grid.p, s.nreal,
-                                      s.periodic, (float4*)c->b_qs.p, (uint8_t*)c->b_pe.p);
+                                      s.periodic, (float4*)c->b_qs.p, (uint8_t*)c->b_pe.p, self_sum);
   c->launches++;
   TM_CUDA(cudaGetLastError());
   return TM_OK;
@@ -224,6 +258,7 @@ k_pair(const SAtom* __restrict__ sat, const float4* __restrict__ pq, const int32
        const int32_t* __restrict__ rowsidx, const int32_t* __restrict__ rowslot, int64_t nrows, int64_t maxnatom, int nreal_slots,
        const __grid_constant__ DevParams P, int do_force, float cutoff_A, int split, double* __restrict__ dedq_slot, float* __restrict__ F,
        double* __restrict__ molacc) {
+  TM_PDL_PROLOGUE;
   __shared__ int q_j[PAIR_WARPS][QCAP];
   __shared__ float s_c6[PAIR_WARPS][TM_MAX_ELE], s_rs12[PAIR_WARPS][TM_MAX_ELE];
   int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -493,12 +528,16 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32)
 k_pair_tab(const SAtom* __restrict__ sat, const float4* __restrict__ pq, const uint8_t* __restrict__ pe, const int32_t* __restrict__ cstart,
            const GridParams* __restrict__ gp, const int32_t* __restrict__ rowsidx, const int32_t* __restrict__ rowslot, int64_t nrows,
            int64_t maxnatom, const __grid_constant__ DevParams P, const __grid_constant__ PairTabMeta M, const float4* __restrict__ tab_g,
-           int do_force, float cutoff_A, int split, double* __restrict__ dedq_slot, float* __restrict__ F, double* __restrict__ molacc) {
+           int do_force, float cutoff_A, int split, double* __restrict__ dedq_slot, float* __restrict__ F, double* __restrict__ molacc,
+           const int32_t* __restrict__ rowmeta, int single_mol) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // (the wait is below, behind the table staging)
   extern __shared__ float4 s_tab[];                    // [nfn][nnodes]: a warp's 32 random nodes spread over all banks
   __shared__ int8_t s_fn[TM_MAX_ELE][TM_MAX_ELE];      // table of the vdW function of an element pair
+  __shared__ double s_sum[PAIR_WARPS][3];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int i = threadIdx.x; i < M.nnodes * M.nfn; i += blockDim.x) s_tab[i] = tab_g[i];
   if (threadIdx.x < TM_MAX_ELE * TM_MAX_ELE) s_fn[threadIdx.x / TM_MAX_ELE][threadIdx.x % TM_MAX_ELE] = (int8_t)(1 + P.pair_index[threadIdx.x / TM_MAX_ELE][threadIdx.x % TM_MAX_ELE]);
+  asm volatile("griddepcontrol.wait;" ::: "memory");   // the tables are constants; everything else comes from the predecessors
   __syncthreads();
   const GridParams g = *gp;
   const float cell = (float)g.cell, icell = (float)g.inv_cell, izcell = (float)g.inv_zcell;
@@ -506,7 +545,9 @@ k_pair_tab(const SAtom* __restrict__ sat, const float4* __restrict__ pq, const u
   const unsigned lt_mask = (1u << lane) - 1u;
   const float w_img = (do_force & 2) ? 1.0f : 0.5f;    // see k_pair
   const int kmin = M.kmin, kink_k = M.kink_k, kink_v = M.kink_v, nnodes = M.nnodes;
-  const int64_t nwork = nrows * split;
+  // rows in use (element ranges incl. their padding to the row tile): the allocation behind them is never visited
+  const int64_t nwork = (int64_t)min((int64_t)rowmeta[2 * TM_MAX_ELE + 1], nrows) * split;
+  double tE = 0.0, tV = 0.0, tD = 0.0;                  // single molecule: this warp's share of Ecc, Evdw, sum dE/dq
   for (int64_t gw = (int64_t)blockIdx.x * PAIR_WARPS + warp; gw < nwork; gw += (int64_t)gridDim.x * PAIR_WARPS) {
     const int64_t row = gw / split;
     const int sub = (int)(gw - row * split);
@@ -646,9 +687,22 @@ k_pair_tab(const SAtom* __restrict__ sat, const float4* __restrict__ pq, const u
         atomicAdd(F + 3 * (int64_t)slot + 1, A.gy);
         atomicAdd(F + 3 * (int64_t)slot + 2, A.gz);
       }
-      atomicAdd(&molacc[16 * m + 2], 0.5 * (double)A.ecc);
-      atomicAdd(&molacc[16 * m + 3], 0.5 * (double)A.evdw);
-      atomicAdd(&molacc[16 * m + 5], (double)A.dedq);
+      if (single_mol) {
+        tE += 0.5 * (double)A.ecc; tV += 0.5 * (double)A.evdw; tD += (double)A.dedq;
+      } else {
+        atomicAdd(&molacc[16 * m + 2], 0.5 * (double)A.ecc);
+        atomicAdd(&molacc[16 * m + 3], 0.5 * (double)A.evdw);
+        atomicAdd(&molacc[16 * m + 5], (double)A.dedq);
+      }
+    }
+  }
+  if (single_mol) {   // one set of atomics per CTA instead of one per centre (they all hit the same three addresses)
+    if (lane == 0) { s_sum[warp][0] = tE; s_sum[warp][1] = tV; s_sum[warp][2] = tD; }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+      double t = 0.0;
+      for (int w = 0; w < PAIR_WARPS; w++) t += s_sum[w][threadIdx.x];
+      if (t != 0.0) atomicAdd(&molacc[threadIdx.x == 0 ? 2 : (threadIdx.x == 1 ? 3 : 5)], t);
     }
   }
 }
@@ -665,7 +719,7 @@ int tm_launch_pair(tm_ctx* c, const SysView& s, int flags) {
   int blocks = (int)((s.nrows * split + PAIR_WARPS - 1) / PAIR_WARPS);
   if (nq > 0x7fffffff) { tm_set_error("too many slots"); return TM_EINVAL; }
   auto launch = [&](auto kern) {
-    kern<<<blocks, PAIR_WARPS * 32, 0, c->stream>>>((const SAtom*)c->b_satom.p, (const float4*)c->b_qs.p, (const int32_t*)c->b_cstart.p,
+    TM_LAUNCH(kern, blocks, PAIR_WARPS * 32, 0, c->stream, (const SAtom*)c->b_satom.p, (const float4*)c->b_qs.p, (const int32_t*)c->b_cstart.p,
                                                     (const GridParams*)c->b_grid.p, (const int32_t*)c->b_rowsidx.p, (const int32_t*)c->b_rowslot.p,
                                                     s.nrows, s.maxnatom, (int)nq, c->hp, ((flags & TM_F_FORCE) ? 1 : 0) | ((flags & TM_F_FOLD_IMAGES) ? 2 : 0),
                                                     (float)c->params.ee_cutoff_off, split, (double*)c->b_dedq.p, (float*)c->b_F.p, (double*)c->b_molacc.p);
@@ -688,11 +742,12 @@ int tm_launch_pair(tm_ctx* c, const SysView& s, int flags) {
       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, PAIR_WARPS * 32, smem);
       cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
       int grid = std::max(1, std::min(blocks, sms * std::max(1, occ)));
-      kern<<<grid, PAIR_WARPS * 32, smem, c->stream>>>((const SAtom*)c->b_satom.p, (const float4*)c->b_qs.p, (const uint8_t*)c->b_pe.p,
+      TM_LAUNCH(kern, grid, PAIR_WARPS * 32, smem, c->stream, (const SAtom*)c->b_satom.p, (const float4*)c->b_qs.p, (const uint8_t*)c->b_pe.p,
                                                       (const int32_t*)c->b_cstart.p, (const GridParams*)c->b_grid.p, (const int32_t*)c->b_rowsidx.p,
                                                       (const int32_t*)c->b_rowslot.p, s.nrows, s.maxnatom, c->hp, M, (const float4*)c->b_pairtab.p,
                                                       ((flags & TM_F_FORCE) ? 1 : 0) | ((flags & TM_F_FOLD_IMAGES) ? 2 : 0), (float)c->params.ee_cutoff_off,
-                                                      split, (double*)c->b_dedq.p, (float*)c->b_F.p, (double*)c->b_molacc.p);
+                                                      split, (double*)c->b_dedq.p, (float*)c->b_F.p, (double*)c->b_molacc.p,
+                                                      (const int32_t*)c->b_rowmeta.p, s.nmol == 1 ? 1 : 0);
       c->launches++;
       TM_CUDA(cudaGetLastError());
       return TM_OK;
