@@ -69,7 +69,8 @@ enum {
   TM_F_FORCE = 1,        /* compute the gradient / force */
   TM_F_VDW = 2,          /* HasVdw */
   TM_F_DESCRIPTORS = 4,  /* also copy descriptors out (parity tests) */
-  TM_F_FOLD_IMAGES = 8   /* NON-reference option: fold image-row gradients back onto their real atom */
+  TM_F_FOLD_IMAGES = 8,  /* NON-reference option: fold image-row gradients back onto their real atom */
+  TM_F_REUSE_NLIST = 16  /* tm_eval_lattice_dev: keep the cell list / neighbour rows of the previous call (see tm_set_skin) */
 };
 
 typedef struct tm_ctx tm_ctx;
@@ -179,6 +180,15 @@ int tm_eval_lattice(tm_ctx* ctx, const double* xyz, const int32_t* Z, int64_t nr
  * grad_dev [nreal*3] f64, charge_dev [nreal] f64.  No host synchronisation. */
 int tm_eval_lattice_dev(tm_ctx* ctx, const double* xyz_dev, const int32_t* Z_dev, int64_t nreal, const double* lattice, int ntess,
                         int flags, double* e_dev, double* grad_dev, double* charge_dev);
+
+/* Verlet skin (the idea at ForceModifiers/Periodic.py:224,262-268; the reference itself rebuilds every step).  With
+ * skin > 0 the lattice path builds its cell list and neighbour rows out to cutoff + skin, and the descriptor, force and
+ * pair kernels apply the cutoffs themselves, so every evaluation still sees exactly the neighbours inside the cutoffs.
+ * A following tm_eval_lattice_dev call with TM_F_REUSE_NLIST then skips the neighbour build: it only refreshes the
+ * positions (images with the reference's arithmetic).  Contract: same nreal / lattice / ntess, positions NOT re-wrapped
+ * since the building call, no atom displaced by more than skin / 2 from where it was at the build (checked on the
+ * device: tm_sync reports it).  skin = 0 (default) restores rebuild-every-call with no tests in the kernels. */
+int tm_set_skin(tm_ctx* ctx, double skin_angstrom);
 
 /* Slab-partitioned evaluation for multi-GPU runs: like tm_eval_lattice_dev but this rank only
  * evaluates centres whose row index r satisfies  lo <= r < hi  in the x-sorted centre order, in three

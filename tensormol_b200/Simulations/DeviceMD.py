@@ -22,9 +22,14 @@ _ACC = pow(10.0, -10.0)
 
 
 class DevicePeriodicVelocityVerlet:
-    def __init__(self, manager_, mol_, lattice_, name_="DevPdicMD", v0_=None, rng_=15.0, device_=0, graph_=True, sync_every_=100):
+    def __init__(self, manager_, mol_, lattice_, name_="DevPdicMD", v0_=None, rng_=15.0, device_=0, graph_=True, sync_every_=100,
+                 skin_=0.0, nl_every_=1):
         """manager_: a TFMolManage (its engine evaluates the forces); mol_: Mol of the primitive cell; lattice_: 3x3 rows.
-        PARAMS: MDMaxStep, MDTemp, MDdt, MDV0 (None | "Random"), MDThermostat (None | "Nose")."""
+        PARAMS: MDMaxStep, MDTemp, MDdt, MDV0 (None | "Random"), MDThermostat (None | "Nose").
+        skin_ > 0 and nl_every_ > 1: Verlet skin (the idea at ForceModifiers/Periodic.py:224,262-268) -- the neighbour rows
+        are built every nl_every_ steps out to cutoff + skin_ and reused in between (tm_set_skin / TM_F_REUSE_NLIST); the
+        coordinates are wrapped into the cell only on the building steps.  The library checks on the device that no atom
+        moved more than skin_ / 2 between builds and raises at the next synchronisation if one did."""
         import torch
         from ..ForceModifiers.Periodic import Lattice
         from ..engine import GraphedCall
@@ -82,6 +87,10 @@ class DevicePeriodicVelocityVerlet:
             self._eta = torch.zeros((), **f64)
             self._ke = torch.zeros((), **f64)
         self.sync_every = int(sync_every_)
+        self.skin, self.nl_every = float(skin_), max(1, int(nl_every_))
+        if self.nl_every > 1 and not self.skin > 0.0:
+            raise ValueError("nl_every_ > 1 needs skin_ > 0")
+        self.engine.set_skin(self.skin if self.nl_every > 1 else 0.0)
         self.t = 0.0
         self.md_log = None
         # initial energy (EPot0); like the reference's VelocityVerlet the acceleration starts at zero (SimpleMD.py:355)
@@ -93,6 +102,10 @@ class DevicePeriodicVelocityVerlet:
         self.KE = 0.0
         step = self._step_nose if self.nose else self._step_nve
         self._replay = GraphedCall(step, self.stream, warmup=1) if graph_ else step
+        self._replay_reuse = self._replay
+        if self.nl_every > 1:      # a second step that keeps the neighbour rows (and does not wrap)
+            reuse = lambda: step(True)
+            self._replay_reuse = GraphedCall(reuse, self.stream, warmup=1) if graph_ else reuse
         if graph_:   # the capture and its warm-up advanced the state: rewind
             with torch.cuda.stream(self.stream):
                 self._x.copy_(torch.tensor(self.mol0.coords, **f64))
@@ -104,9 +117,9 @@ class DevicePeriodicVelocityVerlet:
             self.stream.synchronize()
 
     # ---- device pieces (static shapes, in-place: capturable) --------------------------------------------------
-    def _force(self):
+    def _force(self, reuse=False):
         self.engine.evaluate_lattice_dev(C.c_void_p(self._x.data_ptr()), C.c_void_p(self._Z.data_ptr()), self.natoms, self.lattice.lattice,
-                                         self.ntess, C.c_void_p(self._e.data_ptr()), C.c_void_p(self._g.data_ptr()))
+                                         self.ntess, C.c_void_p(self._e.data_ptr()), C.c_void_p(self._g.data_ptr()), reuse_nlist=reuse)
 
     def _wrap(self):
         torch = self.torch
@@ -123,17 +136,18 @@ class DevicePeriodicVelocityVerlet:
         self._log.index_copy_(0, self._count, self._row)
         self._count.add_(1)
 
-    def _step_nve(self):
+    def _step_nve(self, reuse=False):
         dt = self.dt
         self._x.add_(self._v, alpha=dt).add_(self._a, alpha=0.5 * dt * dt)
-        self._wrap()
-        self._force()
+        if not reuse:
+            self._wrap()
+        self._force(reuse)
         self.torch.mul(self._g, self._gscale, out=self._anew)
         self._v.add_(self._a, alpha=0.5 * dt).add_(self._anew, alpha=0.5 * dt)
         self._a.copy_(self._anew)
         self._record()
 
-    def _step_nose(self):
+    def _step_nose(self, reuse=False):
         torch = self.torch
         dt = self.dt
         # x += v dt + 1/2 (a - eta v) dt^2 ; v(dt/2) = v + 1/2 (a - eta v) dt      (PeriodicMD.py:28-31)
@@ -141,9 +155,10 @@ class DevicePeriodicVelocityVerlet:
         torch.sub(self._a, self._tmp, out=self._tmp)
         ke = 0.5 * torch.dot((self._v * self._v).sum(dim=1), self._m)
         self._x.add_(self._v, alpha=dt).add_(self._tmp, alpha=0.5 * dt * dt)
-        self._wrap()
+        if not reuse:
+            self._wrap()
         self._v.add_(self._tmp, alpha=0.5 * dt)                       # now v(dt/2)
-        self._force()
+        self._force(reuse)
         torch.mul(self._g, self._gscale, out=self._a)
         kedto2 = 0.5 * torch.dot((self._v * self._v).sum(dim=1), self._m)
         self._eta.add_((dt / (2.0 * self._Q)) * (ke - self._target))
@@ -193,7 +208,10 @@ class DevicePeriodicVelocityVerlet:
         self.md_log = np.zeros((self.maxstep, 7))
         with torch.cuda.stream(self.stream):
             for step in range(n):
-                self._replay()
+                if step % self.nl_every == 0:
+                    self._replay()
+                else:
+                    self._replay_reuse()
                 if (step + 1) % self.sync_every == 0:
                     self.stream.synchronize()
                     self._pull_log(step + 1)
@@ -203,6 +221,7 @@ class DevicePeriodicVelocityVerlet:
                     LOGGER.info("Step: %i time: %.1f(fs) KE(kJ/mol): %.5f EPot(Eh): %.5f Etot(kJ/mol): %.5f",   # noqa: F405
                                 step + 1, self.t, self.KE / 1000.0, self.EPot, self.KE / 1000.0 + self.EPot * KJPERHARTREE)   # noqa: F405
         self.stream.synchronize()
+        self.engine.sync()      # device flags of the graph replays (e.g. an atom that outran the Verlet skin) surface here
         self._pull_log(n)
         self.t = n * self.dt
         return self.md_log

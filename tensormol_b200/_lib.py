@@ -15,7 +15,7 @@ TM_NET_CHARGE, TM_NET_ENERGY = 0, 1
 TM_ACT = {"sigmoid_with_param": 0, "relu": 1, "softplus": 2, "tanh": 3, "sigmoid": 4, "elu": 5, "selu": 6}
 TM_GEMM_FP32, TM_GEMM_TC_SPLIT, TM_GEMM_TC_SPLIT_PAIR, TM_GEMM_TC_SPLIT_N64, TM_GEMM_TC_SPLIT_N128 = 0, 1, 2, 3, 4
 TM_GEMM_TC_3XTF32 = TM_GEMM_TC_SPLIT   # name of the same mode before the fp16 split replaced the tf32 split
-TM_F_FORCE, TM_F_VDW, TM_F_DESCRIPTORS, TM_F_FOLD_IMAGES = 1, 2, 4, 8
+TM_F_FORCE, TM_F_VDW, TM_F_DESCRIPTORS, TM_F_FOLD_IMAGES, TM_F_REUSE_NLIST = 1, 2, 4, 8, 16
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libtmolb200.so")
@@ -45,7 +45,7 @@ class tm_timings(C.Structure):
 
 # every symbol declared in include/tmolb200.h (tests/test_abi.py checks the library exports them all)
 SYMBOLS = ["tm_version", "tm_last_error", "tm_device_count", "tm_create", "tm_destroy", "tm_set_params", "tm_set_weights",
-           "tm_set_gemm_mode", "tm_get_gemm_mode", "tm_set_stream", "tm_descriptor_width", "tm_nlist", "tm_pairs_triples_ele",
+           "tm_set_gemm_mode", "tm_get_gemm_mode", "tm_set_skin", "tm_set_stream", "tm_descriptor_width", "tm_nlist", "tm_pairs_triples_ele",
            "tm_eval", "tm_eval_images", "tm_eval_lattice", "tm_eval_lattice_dev", "tm_slab_phase_a", "tm_slab_phase_b",
            "tm_slab_phase_c", "tm_slab_p2p_bytes", "tm_slab_p2p_setup", "tm_get_timings", "tm_sync"]
 
@@ -77,6 +77,7 @@ def load():
     lib.tm_set_params.argtypes = [vp, P(tm_params)]
     lib.tm_set_weights.argtypes = [vp, i32, i32, i32, vp, vp, i32, i32]
     lib.tm_set_gemm_mode.argtypes = [vp, i32]
+    lib.tm_set_skin.argtypes = [vp, dbl]
     lib.tm_get_gemm_mode.argtypes = [vp]
     lib.tm_set_stream.argtypes = [vp, vp]
     lib.tm_descriptor_width.argtypes = [vp]

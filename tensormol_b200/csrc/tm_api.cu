@@ -175,6 +175,8 @@ static int build_dev_params(tm_ctx* c) {
   }
   P.add_ecc = p.add_ecc; P.activation = p.activation; P.act_alpha = (float)p.sigmoid_alpha;
   P.rr_exact = p.r_Rc; P.ra_exact = p.a_Rc;
+  P.skin_on = c->skin > 0.0 ? 1 : 0;
+  P.skin = (float)c->skin;
   return TM_OK;
 }
 
@@ -230,7 +232,7 @@ extern "C" void tm_destroy(tm_ctx* c) {
   DevBuf* all[] = {&c->b_pos, &c->b_Z, &c->b_cellid, &c->b_rank, &c->b_count, &c->b_cstart, &c->b_sorted, &c->b_satom, &c->b_scan_tmp,
                    &c->b_rowslot, &c->b_rowsidx, &c->b_rowofslot, &c->b_blkcnt, &c->b_rowmeta, &c->b_nbcnt, &c->b_nboff, &c->b_nbr, &c->b_G, &c->b_Gs, &c->b_ypart,
                    &c->b_delta0, &c->b_delta1, &c->b_dG[0], &c->b_dG[1], &c->b_y[0], &c->b_y[1], &c->b_q, &c->b_qs, &c->b_dedq, &c->b_F,
-                   &c->b_acc, &c->b_bbox, &c->b_grid, &c->b_flags, &c->b_out, &c->b_molacc, &c->b_natom, &c->b_cntall, &c->b_offall, &c->b_pe, &c->b_pairtab, &c->b_lscan};
+                   &c->b_acc, &c->b_bbox, &c->b_grid, &c->b_flags, &c->b_out, &c->b_molacc, &c->b_natom, &c->b_cntall, &c->b_offall, &c->b_pe, &c->b_pairtab, &c->b_lscan, &c->b_pos0};
   for (DevBuf* b : all) free_buf(*b);
   for (int n = 0; n < 2; n++)
     for (int l = 0; l < TM_MAX_HIDDEN; l++) free_buf(c->b_act[n][l]);
@@ -265,6 +267,13 @@ extern "C" int tm_set_gemm_mode(tm_ctx* c, int mode) {
   return TM_OK;
 }
 extern "C" int tm_get_gemm_mode(tm_ctx* c) { return c ? c->gemm_mode : TM_EINVAL; }
+extern "C" int tm_set_skin(tm_ctx* c, double skin) {
+  if (!c || !(skin >= 0.0) || skin > 4.0) { tm_set_error("tm_set_skin: skin must be in [0, 4] Angstrom"); return TM_EINVAL; }
+  c->skin = skin;
+  c->nl_ok = false;
+  c->cfg_gen++;
+  return build_dev_params(c);
+}
 extern "C" int tm_descriptor_width(tm_ctx* c) { return c ? c->hp.D : TM_EINVAL; }
 static int check_flags(tm_ctx* c);
 extern "C" int tm_sync(tm_ctx* c) {
@@ -482,28 +491,33 @@ void tm_trace(tm_ctx* c, const char* what) {
 }
 
 // stages up to and including the nets' forward pass (pos/Z/inv_n already on the device)
-static int stage_a(tm_ctx* c, const SysView& s) {
+static int stage_a(tm_ctx* c, const SysView& s, bool reuse = false) {
   int rc;
   int64_t nq = s.periodic ? s.nreal : s.nslots;
   if ((rc = tm_buf(c, c->b_flags, 64))) return rc;
   if ((rc = tm_buf(c, c->b_molacc, (size_t)s.nmol * 16 * 8))) return rc;
   if ((rc = tm_buf(c, c->b_F, (size_t)nq * 3 * 4))) return rc;
-  TM_CUDA(cudaMemsetAsync(c->b_flags.p, 0, 64, c->stream));
+  TM_CUDA(cudaMemsetAsync(c->b_flags.p, 0, 32, c->stream));   // words 8.. are sticky (read and cleared by check_flags)
   TM_CUDA(cudaMemsetAsync(c->b_molacc.p, 0, (size_t)s.nmol * 16 * 8, c->stream));
   TM_CUDA(cudaMemsetAsync(c->b_F.p, 0, (size_t)nq * 3 * 4, c->stream));
   cudaEventRecord(c->ev[1], c->stream);
   tm_trace(c, "inputs");
-  if (s.lat_bin) {
+  if (reuse) {
+    if ((rc = tm_launch_lattice_refresh(c, s))) return rc;
+    tm_trace(c, "position refresh (neighbour rows reused)");
+  } else if (s.lat_bin) {
     if ((rc = tm_launch_lattice_bin(c, s))) return rc;
     tm_trace(c, "windowed lattice binning + rows");
   } else {
-    if ((rc = tm_launch_nlist_build(c, s, c->params.r_Rc))) return rc;
+    if ((rc = tm_launch_nlist_build(c, s, c->params.r_Rc + c->skin))) return rc;
     tm_trace(c, "cell list");
     if ((rc = tm_launch_rows(c, s))) return rc;
     tm_trace(c, "rows");
   }
-  if ((rc = tm_launch_neighbours(c, s))) return rc;
-  tm_trace(c, "neighbour rows");
+  if (!reuse) {
+    if ((rc = tm_launch_neighbours(c, s))) return rc;
+    tm_trace(c, "neighbour rows");
+  }
   cudaEventRecord(c->ev[2], c->stream);
   if ((rc = tm_launch_desc(c, s))) return rc;
   tm_trace(c, "descriptors");
@@ -571,13 +585,20 @@ static int finish_timings(tm_ctx* c, const SysView& s) {
 
 static int check_flags(tm_ctx* c) {
   int32_t f[2] = {0, 0};
+  int32_t sticky[2] = {0, 0};
   TM_CUDA(cudaMemcpyAsync(f, c->b_flags.p, 8, cudaMemcpyDeviceToHost, c->stream));
+  TM_CUDA(cudaMemcpyAsync(sticky, (char*)c->b_flags.p + 32, 8, cudaMemcpyDeviceToHost, c->stream));
   TM_CUDA(cudaStreamSynchronize(c->stream));
+  if (sticky[0]) {      // raised by a step that may have been replayed from a graph many steps ago (TM_F_REUSE_NLIST)
+    TM_CUDA(cudaMemsetAsync((char*)c->b_flags.p + 32, 0, 8, c->stream));
+    f[0] |= sticky[0];
+  }
   c->last_flags = f[0];
   if (f[0] & 2) { tm_set_error("more than %d radial neighbours of one centre", TM_NB_STRIDE); return TM_ECAP; }
   if (f[0] & 32) { tm_set_error("slab exchange: a peer rank never signalled (timed out after ~8 s)"); return TM_ECUDA; }
   if (f[0] & 8) { tm_set_error("coordinates are not wrapped into the cell (apply Lattice.ModuloLattice before tm_eval_lattice)"); return TM_EINVAL; }
   if (f[0] & 4) { tm_set_error("more than %d neighbours inside the angular cutoff of one centre", TM_ANG_CAP); return TM_ECAP; }
+  if (f[0] & 128) { tm_set_error("TM_F_REUSE_NLIST: an atom moved more than skin / 2 since the neighbour rows were built (rebuild more often or raise the skin)"); return TM_ESTATE; }
   if (f[0] & 64) { tm_set_error("a slab rank owns more centres than its row allocation (density far from uniform)"); return TM_ECAP; }
   return TM_OK;
 }
@@ -671,9 +692,9 @@ static int upload_inv_n(tm_ctx* c, const double* inv_n, int64_t nmol) {
   return TM_OK;
 }
 
-static int run_all(tm_ctx* c, const SysView& s, int flags, const OutLayout& o) {
+static int run_all(tm_ctx* c, const SysView& s, int flags, const OutLayout& o, bool reuse = false) {
   int rc;
-  if ((rc = stage_a(c, s))) return rc;
+  if ((rc = stage_a(c, s, reuse))) return rc;
   if ((rc = stage_b(c, s, flags))) return rc;
   if ((rc = stage_c(c, s, flags))) return rc;
   return stage_pack(c, s, flags, o);
@@ -681,6 +702,7 @@ static int run_all(tm_ctx* c, const SysView& s, int flags, const OutLayout& o) {
 
 extern "C" int tm_eval(tm_ctx* c, const double* xyzs, const int32_t* Zs, int64_t nmol, int64_t maxnatom, const int64_t* natom, int flags,
                        tm_outputs* out) {
+  if (c) c->nl_ok = false;
   if (!c || !xyzs || !Zs || !natom || !out || nmol < 1 || maxnatom < 1) { tm_set_error("tm_eval: bad argument"); return TM_EINVAL; }
   int rc;
   TM_CUDA(cudaSetDevice(c->device));
@@ -722,6 +744,7 @@ extern "C" int tm_eval(tm_ctx* c, const double* xyzs, const int32_t* Zs, int64_t
 
 extern "C" int tm_eval_images(tm_ctx* c, const double* xyz_tess, const int32_t* Z_tess, int64_t ntess_atoms, int64_t nreal, int flags,
                               tm_outputs* out) {
+  if (c) c->nl_ok = false;
   if (!c || !xyz_tess || !Z_tess || !out || nreal < 1 || ntess_atoms < nreal) { tm_set_error("tm_eval_images: bad argument"); return TM_EINVAL; }
   int rc;
   TM_CUDA(cudaSetDevice(c->device));
@@ -803,7 +826,7 @@ static void host_grid(tm_ctx* c, SysView* sv, const double* L, int ntess) {
     }
   }
   GridParams g;
-  double cell = c->params.r_Rc * (1.0 + 1e-6);
+  double cell = (c->params.r_Rc + c->skin) * (1.0 + 1e-6);     // neighbour rows reach out to the cutoff + skin
   int gx = 1, gy = 1, gz = 1;
   const int zdiv = sv->lat_bin ? 4 : 1;     // z bins per cell edge (GridParams)
   for (int d = 0; d < 3; d++) { double pad = 1e-6 * (1.0 + fabs(mn[d]) + fabs(mx[d])); mn[d] -= pad; mx[d] += pad; }
@@ -840,7 +863,7 @@ static int prepare_lattice(tm_ctx* c, const double* xyz_dev, const int32_t* Z_de
   gi[3] = -(L[3] * L[8] - L[5] * L[6]) / det; gi[4] = (L[0] * L[8] - L[2] * L[6]) / det; gi[5] = -(L[0] * L[5] - L[2] * L[3]) / det;
   gi[6] = (L[3] * L[7] - L[4] * L[6]) / det; gi[7] = -(L[0] * L[7] - L[1] * L[6]) / det; gi[8] = (L[0] * L[4] - L[1] * L[3]) / det;
   sv->slab_g[0] = gi[0]; sv->slab_g[1] = gi[3]; sv->slab_g[2] = gi[6];
-  const double range = std::max(c->params.ee_cutoff_off, c->params.r_Rc) + 0.05;
+  const double range = std::max(c->params.ee_cutoff_off, c->params.r_Rc) + c->skin + 0.05;
   for (int d = 0; d < 3; d++) {
     double gn = sqrt(gi[d] * gi[d] + gi[3 + d] * gi[3 + d] + gi[6 + d] * gi[6 + d]);   // 1 / plane spacing along axis d
     double halo = range * gn + 1e-5;    // real atoms are accepted up to 1e-6 outside [0, 1)
@@ -959,6 +982,7 @@ static int lattice_graph_call(tm_ctx* c, const double* xyz, const int32_t* Z, in
 
 extern "C" int tm_eval_lattice(tm_ctx* c, const double* xyz, const int32_t* Z, int64_t nreal, const double* lattice, int ntess, int flags,
                                tm_outputs* out) {
+  if (c) c->nl_ok = false;
   if (!c || !xyz || !Z || !lattice || !out || nreal < 1) { tm_set_error("tm_eval_lattice: bad argument"); return TM_EINVAL; }
   int rc;
   TM_CUDA(cudaSetDevice(c->device));
@@ -987,9 +1011,21 @@ extern "C" int tm_eval_lattice_dev(tm_ctx* c, const double* xyz_dev, const int32
   c->timings_final = false;
   cudaEventRecord(c->ev[0], c->stream);
   SysView s;
-  if ((rc = prepare_lattice(c, xyz_dev, Z_dev, nreal, lattice, ntess, &s))) return rc;
+  bool reuse = (flags & TM_F_REUSE_NLIST) != 0;
+  if (reuse) {
+    if (!c->nl_ok || !c->hp.skin_on || c->nl_view.nreal != nreal || c->nl_view.lat_ntess != ntess || memcmp(c->nl_view.lat.v, lattice, 72) != 0) {
+      tm_set_error("TM_F_REUSE_NLIST needs a previous tm_eval_lattice_dev call on this context with the same cell, and tm_set_skin > 0");
+      return TM_ESTATE;
+    }
+    s = c->nl_view;
+    s.xyz_real = xyz_dev; s.Z_real = Z_dev;
+  } else {
+    if ((rc = prepare_lattice(c, xyz_dev, Z_dev, nreal, lattice, ntess, &s))) return rc;
+    c->nl_view = s;
+    c->nl_ok = true;
+  }
   OutLayout o = out_layout(1, nreal);
-  if ((rc = run_all(c, s, flags, o))) return rc;
+  if ((rc = run_all(c, s, flags, o, reuse))) return rc;
   const double* out = (const double*)c->b_out.p;
   if (e_dev) TM_CUDA(cudaMemcpyAsync(e_dev, out, 4 * 8, cudaMemcpyDeviceToDevice, c->stream));
   if (grad_dev && (flags & TM_F_FORCE)) TM_CUDA(cudaMemcpyAsync(grad_dev, out + o.off_grad, (size_t)3 * nreal * 8, cudaMemcpyDeviceToDevice, c->stream));
@@ -1185,6 +1221,7 @@ static int p2p_preload(tm_ctx* c) {
 
 extern "C" int tm_slab_phase_a(tm_ctx* c, const double* xyz_dev, const int32_t* Z_dev, int64_t nreal, const double* lattice, int ntess,
                                int rank, int world, double* qraw_dev) {
+  if (c) c->nl_ok = false;
   if (!c || !xyz_dev || !Z_dev || !lattice || (!qraw_dev && !c->p2p.on) || world < 1 || rank < 0 || rank >= world) { tm_set_error("tm_slab_phase_a: bad argument"); return TM_EINVAL; }
   int rc;
   TM_CUDA(cudaSetDevice(c->device));

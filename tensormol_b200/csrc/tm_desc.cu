@@ -113,6 +113,10 @@ k_desc(const SAtom* __restrict__ sat, const int32_t* __restrict__ rowsidx, const
       r = sqrtf(dx * dx + dy * dy + dz * dz);
       ej = a.e;
       fc = 0.5f * (__cosf(P.pi_over_rRc * r) + 1.0f);
+      if (P.skin_on) {   // the rows reach out to cutoff + skin (tm_set_skin): the cutoffs are applied here
+        if (!(r < P.r_Rc)) fc = 0.f;
+        isang = isang && (r < P.a_Rc);
+      }
     }
     unsigned mk = __ballot_sync(FULL, isang);
     if (isang) {
@@ -313,6 +317,10 @@ k_desc_fast(const SAtom* __restrict__ sat, const int32_t* __restrict__ rowsidx, 
       r = sqrtf(dx * dx + dy * dy + dz * dz);
       ej = a.e;
       fc = 0.5f * (__cosf(P.pi_over_rRc * r) + 1.0f);
+      if (P.skin_on) {   // the rows reach out to cutoff + skin (tm_set_skin): the cutoffs are applied here
+        if (!(r < P.r_Rc)) fc = 0.f;
+        isang = isang && (r < P.a_Rc);
+      }
     }
     rr[lane] = r;
     ffq[lane] = make_float4(ej == 0 ? fc : 0.f, ej == 1 ? fc : 0.f, ej == 2 ? fc : 0.f, ej == 3 ? fc : 0.f);

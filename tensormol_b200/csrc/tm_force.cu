@@ -117,6 +117,10 @@ k_force(const SAtom* __restrict__ sat, const int32_t* __restrict__ rowsidx, cons
       __sincosf(arg, &sn, &cs);                     // arg in [0, pi]: absolute error < 5e-7
       float fc = 0.5f * (cs + 1.0f);
       float dfc = -0.5f * sn * P.pi_over_rRc;
+      if (P.skin_on) {   // the rows reach out to cutoff + skin (tm_set_skin): the cutoffs are applied here
+        if (!(r < P.r_Rc)) { fc = 0.f; dfc = 0.f; }
+        isang = isang && (r < P.a_Rc);
+      }
       const float* Arow = Ar + ej * rstr;
       float dEdr = 0.f;
       const float m2ef = -2.0f * P.eta * fc;
@@ -361,6 +365,10 @@ k_force_fast(const SAtom* __restrict__ sat, const int32_t* __restrict__ rowsidx,
       __sincosf(P.pi_over_rRc * r, &sn, &cs);      // arg in [0, pi]: absolute error < 5e-7
       fc = 0.5f * (cs + 1.0f);
       dfc = -0.5f * sn * P.pi_over_rRc;
+      if (P.skin_on) {   // the rows reach out to cutoff + skin (tm_set_skin): the cutoffs are applied here
+        if (!(r < P.r_Rc)) { fc = 0.f; dfc = 0.f; }
+        isang = isang && (r < P.a_Rc);
+      }
     }
     // radial: dE/dr = sum_s A[e_j][s] * d/dr [ exp(-eta (r-Rs)^2) fc(r) ]
     const float* Arow = Ar + ej * FF_RSTR;

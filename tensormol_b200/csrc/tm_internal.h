@@ -86,6 +86,8 @@ struct DevParams {
   int activation;
   float act_alpha;
   double rr_exact, ra_exact;      // exact f64 cutoffs for the reference accept test
+  int skin_on;                    // lists were built out to cutoff + skin: the kernels apply the cutoffs themselves
+  float skin;
 };
 
 struct Layer {
@@ -162,6 +164,11 @@ struct tm_ctx {
   DevBuf b_pos, b_Z, b_cellid, b_rank, b_count, b_cstart, b_sorted, b_satom, b_scan_tmp;
   DevBuf b_rowslot, b_rowsidx, b_rowofslot, b_blkcnt, b_rowmeta;
   DevBuf b_cntall, b_offall, b_pe, b_pairtab, b_lscan;
+  // Verlet skin (tm_set_skin): state of the last list-building lattice call
+  double skin = 0.0;
+  bool nl_ok = false;
+  SysView nl_view;
+  DevBuf b_pos0;
   // pair-potential tables of tm_pair.cu (rebuilt when the hyper-parameters change)
   uint64_t params_gen = 1, pairtab_gen = 0;
   int pt_kmin = 0, pt_nnodes = 0, pt_nfn = 0, pt_kink_k = -1, pt_kink_v = -1;
@@ -243,7 +250,8 @@ int tm_host_stage(tm_ctx* c, size_t bytes);
 int tm_launch_tessellate(tm_ctx* c, const double* xyz_real, const int32_t* Z_real, int64_t nreal, const LatArgs& lattice, int ntess, int ilo, int ihi);
 int tm_launch_nlist_build(tm_ctx* c, const SysView& s, double rc_grid);
 int tm_launch_rows(tm_ctx* c, const SysView& s);
-int tm_launch_lattice_bin(tm_ctx* c, const SysView& s);   // windowed binning + cell sort + centre rows of the lattice path
+int tm_launch_lattice_bin(tm_ctx* c, const SysView& s);
+int tm_launch_lattice_refresh(tm_ctx* c, const SysView& s);   // Verlet-skin reuse: new positions into the existing cell-sorted records   // windowed binning + cell sort + centre rows of the lattice path
 int tm_launch_neighbours(tm_ctx* c, const SysView& s);
 int tm_launch_desc(tm_ctx* c, const SysView& s);
 void tm_trace(tm_ctx* c, const char* what);   // TM_TRACE=1: synchronise + name the stage on stderr (tm_api.cu)

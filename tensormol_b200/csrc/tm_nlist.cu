@@ -746,7 +746,7 @@ int tm_launch_neighbours(tm_ctx* c, const SysView& s) {
   int blocks = (int)((s.nrows * 32 + 255) / 256);
   TM_LAUNCH(k_neighbours, blocks, 256, 0, c->stream, (const SAtom*)c->b_satom.p, (const int32_t*)c->b_cstart.p, (const GridParams*)c->b_grid.p,
                                               (const int32_t*)c->b_rowsidx.p, (const int32_t*)c->b_rowslot.p, s.nrows, s.maxnatom,
-                                              c->hp.rr_exact, c->hp.ra_exact, (int32_t*)c->b_nbcnt.p, (uint32_t*)c->b_nbr.p,
+                                              c->hp.rr_exact + c->skin, c->hp.ra_exact + c->skin, (int32_t*)c->b_nbcnt.p, (uint32_t*)c->b_nbr.p,
                                               (int32_t*)c->b_flags.p);
   c->launches++;
   TM_CUDA(cudaGetLastError());
@@ -914,7 +914,8 @@ __device__ __forceinline__ int ele_index(const DevParams& P, int z) {
 
 // cnt_all = [ncells (fine) cell counts | n_ele x ngroups centre counts per group of zdiv z bins], zeroed by the launcher
 __global__ void k_lat_count(const double* __restrict__ xyz, const int32_t* __restrict__ Z, const __grid_constant__ LatBin B,
-                            const __grid_constant__ DevParams P, double* __restrict__ pos, int32_t* __restrict__ Zo, double* __restrict__ inv_n,
+                            const __grid_constant__ DevParams P, double* __restrict__ pos, double* __restrict__ pos0, int32_t* __restrict__ Zo,
+                            double* __restrict__ inv_n,
                             GridParams* __restrict__ gp, int32_t* __restrict__ cnt_all, int32_t* __restrict__ flags, int32_t* __restrict__ rowslot,
                             int64_t nrows, int32_t* __restrict__ rowofslot) {
   TM_PDL_PROLOGUE;
@@ -929,6 +930,7 @@ __global__ void k_lat_count(const double* __restrict__ xyz, const int32_t* __res
     int zz = Z[a];
     if (sub == 0) {
       pos[3 * a] = x; pos[3 * a + 1] = y; pos[3 * a + 2] = z;   // the real block: read by k_charges (dipole)
+      if (pos0) { pos0[3 * a] = x; pos0[3 * a + 1] = y; pos0[3 * a + 2] = z; }   // Verlet skin: where the lists were built
       Zo[a] = zz;
       rowofslot[a] = -1;
     }
@@ -1148,6 +1150,7 @@ int tm_launch_lattice_bin(tm_ctx* c, const SysView& s) {
   if ((rc = tm_buf(c, c->b_pos, (size_t)s.nreal * 24))) return rc;
   if ((rc = tm_buf(c, c->b_Z, (size_t)s.nreal * 4))) return rc;
   if ((rc = tm_buf(c, c->b_natom, 8))) return rc;
+  if (c->skin > 0.0 && (rc = tm_buf(c, c->b_pos0, (size_t)s.nreal * 24))) return rc;
   if ((rc = tm_buf(c, c->b_cntall, (size_t)(nall + 8) * 4))) return rc;
   if ((rc = tm_buf(c, c->b_offall, (size_t)(nall + n_ele + 8) * 4))) return rc;
   if ((rc = tm_buf(c, c->b_cstart, (size_t)(ncells + 8) * 4))) return rc;
@@ -1170,15 +1173,16 @@ int tm_launch_lattice_bin(tm_ctx* c, const SysView& s) {
   int32_t* off_all = (int32_t*)c->b_offall.p;
   const int nch0 = (int)((ncells + 1 + LSCAN_CH - 1) / LSCAN_CH), nch1 = (int)((ngroups + 1 + LSCAN_CH - 1) / LSCAN_CH);
   const int nchunks = nch0 + n_ele * nch1;
-  if ((rc = tm_buf(c, c->b_lscan, (size_t)(2 * nchunks + 16) * 4))) return rc;    // [chunk totals | chunk offsets | done counter]
-  int32_t* ctot = (int32_t*)c->b_lscan.p;
+  if ((rc = tm_buf(c, c->b_lscan, (size_t)(2 * nchunks + 16) * 4))) return rc;    // [done counter | chunk totals | chunk offsets]
+  int32_t* done = (int32_t*)c->b_lscan.p;   // at a FIXED place (the chunk count changes with the grid): zero from the allocation, reset by the kernel itself
+  int32_t* ctot = done + 4;
   int32_t* coff = ctot + nchunks;
-  int32_t* done = coff + nchunks;      // zero from the allocation, reset by the kernel itself
   LatScan SC{off_all, coff, (int)hpad4(ncells), (int)hpad4(ngroups), nch0, nch1};
   TM_CUDA(cudaMemsetAsync(cnt_all, 0, (size_t)(nall + 8) * 4, c->stream));
   int blocks = (int)((std::max<int64_t>(s.nreal * LAT_SUB, s.nrows) + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
-  TM_LAUNCH(k_lat_count, blocks, 256, 0, c->stream, s.xyz_real, s.Z_real, B, c->hp, (double*)c->b_pos.p, (int32_t*)c->b_Z.p, (double*)c->b_natom.p,
+  TM_LAUNCH(k_lat_count, blocks, 256, 0, c->stream, s.xyz_real, s.Z_real, B, c->hp, (double*)c->b_pos.p, c->skin > 0.0 ? (double*)c->b_pos0.p : (double*)nullptr,
+            (int32_t*)c->b_Z.p, (double*)c->b_natom.p,
                                              (GridParams*)c->b_grid.p, cnt_all, (int32_t*)c->b_flags.p, (int32_t*)c->b_rowslot.p, s.nrows,
                                              (int32_t*)c->b_rowofslot.p);
   c->launches++;
@@ -1193,6 +1197,62 @@ int tm_launch_lattice_bin(tm_ctx* c, const SysView& s) {
                                                   (int32_t*)c->b_rowslot.p, (int32_t*)c->b_rowsidx.p, (int32_t*)c->b_rowofslot.p, s.nrows,
                                                   (int32_t*)c->b_flags.p);
   c->launches += 2;
+  TM_CUDA(cudaGetLastError());
+  return TM_OK;
+}
+
+// ---------------------------------------------------------------- Verlet-skin reuse
+// New positions into the existing cell-sorted records (cells, neighbour rows and centre rows stay as built): record i
+// belongs to slot b nreal + a, i.e. to real atom a shifted by the lattice vector of image block b, recomputed with the
+// reference's arithmetic from the atom's new position.  Also refreshes the real block (dipole) and checks the contract:
+// no atom further than skin / 2 from where it was when the rows were built (flag 128).
+__global__ void k_lat_refresh(const double* __restrict__ xyz, const __grid_constant__ LatBin B, const int32_t* __restrict__ cstart,
+                              SAtom* __restrict__ sat, double* __restrict__ pos, const double* __restrict__ pos0, double half_skin2,
+                              int32_t* __restrict__ flags) {
+  TM_PDL_PROLOGUE;
+  const int64_t t0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t a = t0; a < B.nreal; a += stride) {
+    double x = xyz[3 * a], y = xyz[3 * a + 1], z = xyz[3 * a + 2];
+    pos[3 * a] = x; pos[3 * a + 1] = y; pos[3 * a + 2] = z;
+    double dx = x - pos0[3 * a], dy = y - pos0[3 * a + 1], dz = z - pos0[3 * a + 2];
+    if (dx * dx + dy * dy + dz * dz > half_skin2) atomicOr(flags + 8, 128);   // sticky word: survives the per-step reset
+  }
+  const int ntot = cstart[B.g.ncells];
+  const int nt = B.ntess, side = 2 * nt + 1, centre = (nt * side + nt) * side + nt;
+  for (int64_t r = t0; r < ntot; r += stride) {
+    const int slot = sat[r].slot;
+    const int b = (int)(slot / B.nreal);
+    const int64_t a = slot - (int64_t)b * B.nreal;
+    double x = xyz[3 * a], y = xyz[3 * a + 1], z = xyz[3 * a + 2];
+    if (b > 0) {
+      const int lin = (b - 1 < centre) ? (b - 1) : b;
+      const double dk = (double)(lin % side - nt), dj = (double)((lin / side) % side - nt), di = (double)(lin / (side * side) - nt);
+      const double x0 = x, y0 = y, z0 = z;
+      x = __dadd_rn(__dadd_rn(__dadd_rn(x0, __dmul_rn(di, B.L[0])), __dmul_rn(dj, B.L[3])), __dmul_rn(dk, B.L[6]));
+      y = __dadd_rn(__dadd_rn(__dadd_rn(y0, __dmul_rn(di, B.L[1])), __dmul_rn(dj, B.L[4])), __dmul_rn(dk, B.L[7]));
+      z = __dadd_rn(__dadd_rn(__dadd_rn(z0, __dmul_rn(di, B.L[2])), __dmul_rn(dj, B.L[5])), __dmul_rn(dk, B.L[8]));
+    }
+    sat[r].x = x; sat[r].y = y; sat[r].z = z;
+  }
+}
+
+int tm_launch_lattice_refresh(tm_ctx* c, const SysView& s) {
+  LatBin B;
+  memcpy(B.L, s.lat.v, 72);
+  memcpy(B.ginv, s.ginv, 72);
+  for (int d = 0; d < 3; d++) { B.wlo[d] = s.wlo[d]; B.whi[d] = s.whi[d]; }
+  B.inv_n = s.lat.v[9];
+  B.ntess = s.lat_ntess;
+  B.slab_rank = s.slab_rank; B.slab_world = s.slab_world;
+  B.nreal = s.nreal;
+  B.g = s.hgrid;
+  if (!c->b_pos0.p || !c->b_satom.p) { tm_set_error("no neighbour rows to reuse"); return TM_ESTATE; }
+  int blocks = (int)((4 * s.nreal + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  const double hs = 0.5 * c->skin;
+  TM_LAUNCH(k_lat_refresh, blocks, 256, 0, c->stream, s.xyz_real, B, (const int32_t*)c->b_cstart.p, (SAtom*)c->b_satom.p, (double*)c->b_pos.p,
+            (const double*)c->b_pos0.p, hs * hs, (int32_t*)c->b_flags.p);
+  c->launches++;
   TM_CUDA(cudaGetLastError());
   return TM_OK;
 }

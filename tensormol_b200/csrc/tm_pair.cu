@@ -283,9 +283,11 @@ k_pair(const SAtom* __restrict__ sat, const float4* __restrict__ pq, const int32
   const unsigned lt_mask = (1u << lane) - 1u;
   // the candidate records are relative to the grid centre; the column arithmetic wants the origin
   const float ox_ = (float)(ci.x - g.ox), oy_ = (float)(ci.y - g.oy), oz_ = (float)(ci.z - g.oz);
-  // cell columns that can hold a partner, from the centre's actual position (not its cell): |dx| <= rc
-  int x0 = max(0, (int)floorf((ox_ - cutoff_A) * icell)), x1 = min(g.gx - 1, (int)floorf((ox_ + cutoff_A) * icell));
-  int y0 = max(0, (int)floorf((oy_ - cutoff_A) * icell)), y1 = min(g.gy - 1, (int)floorf((oy_ + cutoff_A) * icell));
+  // cell columns that can hold a partner, from the centre's actual position (not its cell): |dx| <= rc (+ the Verlet skin:
+  // with reused lists an atom may have left the cell it was binned in by up to skin / 2)
+  const float rcw = cutoff_A + P.skin, rcw2 = rcw * rcw;
+  int x0 = max(0, (int)floorf((ox_ - rcw) * icell)), x1 = min(g.gx - 1, (int)floorf((ox_ + rcw) * icell));
+  int y0 = max(0, (int)floorf((oy_ - rcw) * icell)), y1 = min(g.gy - 1, (int)floorf((oy_ + rcw) * icell));
   int ny = y1 - y0 + 1, ncol = (x1 - x0 + 1) * ny;
   PairAcc A = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   int qn = 0;
@@ -306,7 +308,7 @@ k_pair(const SAtom* __restrict__ sat, const float4* __restrict__ pq, const int32
       int x = x0 + cidx / ny, y = y0 + cidx % ny;
       float lx = fmaxf(0.f, fmaxf(x * cell - ox_, ox_ - (x + 1) * cell));   // distance from the centre to the column's slab in x
       float ly = fmaxf(0.f, fmaxf(y * cell - oy_, oy_ - (y + 1) * cell));
-      float rem = rc2 - lx * lx - ly * ly;
+      float rem = rcw2 - lx * lx - ly * ly;
       if (rem > 0.f) {
         float zr = sqrtf(rem);
         int z0 = max(0, (int)floorf((oz_ - zr) * izcell)), z1 = min(g.gz - 1, (int)floorf((oz_ + zr) * izcell));
@@ -542,6 +544,7 @@ k_pair_tab(const SAtom* __restrict__ sat, const float4* __restrict__ pq, const u
   const GridParams g = *gp;
   const float cell = (float)g.cell, icell = (float)g.inv_cell, izcell = (float)g.inv_zcell;
   const float rc2 = cutoff_A * cutoff_A;
+  const float rcw = cutoff_A + P.skin, rcw2 = rcw * rcw;   // column walk: cutoff + Verlet skin (see k_pair)
   const unsigned lt_mask = (1u << lane) - 1u;
   const float w_img = (do_force & 2) ? 1.0f : 0.5f;    // see k_pair
   const int kmin = M.kmin, kink_k = M.kink_k, kink_v = M.kink_v, nnodes = M.nnodes;
@@ -560,8 +563,8 @@ k_pair_tab(const SAtom* __restrict__ sat, const float4* __restrict__ pq, const u
     const int ei = ci.e;
     const int m = (int)(slot / maxnatom);
     const float ox_ = (float)(ci.x - g.ox), oy_ = (float)(ci.y - g.oy), oz_ = (float)(ci.z - g.oz);
-    int x0 = max(0, (int)floorf((ox_ - cutoff_A) * icell)), x1 = min(g.gx - 1, (int)floorf((ox_ + cutoff_A) * icell));
-    int y0 = max(0, (int)floorf((oy_ - cutoff_A) * icell)), y1 = min(g.gy - 1, (int)floorf((oy_ + cutoff_A) * icell));
+    int x0 = max(0, (int)floorf((ox_ - rcw) * icell)), x1 = min(g.gx - 1, (int)floorf((ox_ + rcw) * icell));
+    int y0 = max(0, (int)floorf((oy_ - rcw) * icell)), y1 = min(g.gy - 1, (int)floorf((oy_ + rcw) * icell));
     const int ny = y1 - y0 + 1, ncol = (x1 - x0 + 1) * ny;
     const int8_t* fnrow = s_fn[ei];
     PairAcc A = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -572,7 +575,7 @@ k_pair_tab(const SAtom* __restrict__ sat, const float4* __restrict__ pq, const u
         int x = x0 + cidx / ny, y = y0 + cidx % ny;
         float lx = fmaxf(0.f, fmaxf(x * cell - ox_, ox_ - (x + 1) * cell));
         float ly = fmaxf(0.f, fmaxf(y * cell - oy_, oy_ - (y + 1) * cell));
-        float rem = rc2 - lx * lx - ly * ly;
+        float rem = rcw2 - lx * lx - ly * ly;
         if (rem > 0.f) {
           float zr = sqrtf(rem);
           int z0 = max(0, (int)floorf((oz_ - zr) * izcell)), z1 = min(g.gz - 1, (int)floorf((oz_ + zr) * izcell));

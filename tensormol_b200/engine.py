@@ -11,7 +11,7 @@ import math
 import numpy as np
 
 from . import _lib
-from ._lib import (TM_ACT, TM_F_DESCRIPTORS, TM_F_FOLD_IMAGES, TM_F_FORCE, TM_F_VDW, TM_GEMM_FP32, TM_GEMM_TC_3XTF32, TM_GEMM_TC_SPLIT,
+from ._lib import (TM_ACT, TM_F_DESCRIPTORS, TM_F_FOLD_IMAGES, TM_F_FORCE, TM_F_REUSE_NLIST, TM_F_VDW, TM_GEMM_FP32, TM_GEMM_TC_3XTF32, TM_GEMM_TC_SPLIT,
                    TM_NET_CHARGE, TM_NET_ENERGY, check, tm_model_desc, tm_outputs, tm_params, tm_timings)
 
 BOHRPERA = 1.889725989
@@ -286,11 +286,18 @@ class Engine:
               "tm_eval_lattice")
         return res
 
-    def evaluate_lattice_dev(self, xyz_ptr, Z_ptr, nreal, lattice, ntess, e_ptr, grad_ptr, charge_ptr=None, do_force=True, has_vdw=True):
-        """Device pointers in, device pointers out, no host synchronisation."""
+    def evaluate_lattice_dev(self, xyz_ptr, Z_ptr, nreal, lattice, ntess, e_ptr, grad_ptr, charge_ptr=None, do_force=True, has_vdw=True,
+                             reuse_nlist=False):
+        """Device pointers in, device pointers out, no host synchronisation.  reuse_nlist: keep the neighbour rows of the
+        previous call (set_skin > 0; positions not re-wrapped and within skin / 2 of those of the building call)."""
         lat = np.ascontiguousarray(lattice, np.float64).reshape(9)
-        check(self.lib.tm_eval_lattice_dev(self.ctx, xyz_ptr, Z_ptr, int(nreal), _ptr(lat), int(ntess), self._flags(do_force, has_vdw, False),
+        flags = self._flags(do_force, has_vdw, False) | (TM_F_REUSE_NLIST if reuse_nlist else 0)
+        check(self.lib.tm_eval_lattice_dev(self.ctx, xyz_ptr, Z_ptr, int(nreal), _ptr(lat), int(ntess), flags,
                                            e_ptr, grad_ptr, charge_ptr), "tm_eval_lattice_dev")
+
+    def set_skin(self, skin):
+        """Verlet skin in Angstrom (0 = rebuild every call, the reference's behaviour): see tm_set_skin in include/tmolb200.h."""
+        check(self.lib.tm_set_skin(self.ctx, float(skin)), "tm_set_skin")
 
     def set_stream(self, cuda_stream):
         check(self.lib.tm_set_stream(self.ctx, cuda_stream), "tm_set_stream")

@@ -7,6 +7,7 @@ from common import ENERGY_RTOL, FORCE_ATOL_HA_BOHR, water_box
 from conftest import load_golden
 
 pytestmark = pytest.mark.gpu
+from tensormol_b200._lib import TMolB200Error  # noqa: E402
 
 NET = "fc_sqdiff_BP_Direct_EE_ChargeEncode_Update_vdw_DSF_elu_Normalize_Dropout"
 
@@ -403,3 +404,96 @@ def test_slab_peer_memory_exchange_on_one_gpu(world):
             assert abs(e[2] - ref["Ecc"][0]) <= 1e-6 * abs(ref["Ecc"][0]) + 1e-9
             assert abs(e[3] - ref["Evdw"][0]) <= 5e-7 * abs(ref["Evdw"][0])
             assert np.abs(gs[r].cpu().numpy() - ref["gradient"][0]).max() <= 2e-6 * np.abs(ref["gradient"]).max()
+
+
+# ---------------------------------------------------------------------------------------- Verlet skin
+def _skin_system(nx, margin=0.75):
+    """Water box whose atoms keep `margin` A clear of the cell faces (cell = box + 2 margin), so that displaced coordinates
+    are still inside the cell and can be evaluated from scratch without re-wrapping."""
+    from tensormol_b200.SystemBuilders import water_box, wrap_into_cell
+    Z, X, lat = water_box(nx)
+    X = wrap_into_cell(X, lat) + margin
+    return Z, X, lat + 2.0 * margin * np.eye(3)
+
+
+@pytest.mark.parametrize("nx", [3, 6])
+def test_verlet_skin_reuse_equals_rebuild_and_oracle(nx):
+    """tm_set_skin + TM_F_REUSE_NLIST: rows built once out to cutoff + skin, then evaluations at displaced positions that only
+    refresh the coordinates must equal a from-scratch evaluation of the same coordinates (engine without skin), and the
+    oracle on the reference's tessellation of them (nx = 3: two image shells)."""
+    import ctypes as C
+    import torch
+    from oracle import oracle_graph as og
+    from oracle import oracle_np as onp
+    from test_a_gpu_parity import _check_energy, _check_grad, _engine
+    Z, X0, lat = _skin_system(nx)
+    n = len(Z)
+    eng, W, P = _engine([1, 8], [32, 32], 7)
+    ref, _, _ = _engine([1, 8], [32, 32], 7)
+    eng.set_skin(0.6)
+    dev = torch.device("cuda", 0)
+    Zt, Xt = onp.tess_lattice(lat, Z.astype(np.uint8), X0, P["EECutoffOff"])
+    ntess = (round((len(Zt) / n) ** (1 / 3)) - 1) // 2
+    xd = torch.tensor(X0, dtype=torch.float64, device=dev)
+    zd = torch.tensor(Z, dtype=torch.int32, device=dev)
+    e = torch.zeros(6, dtype=torch.float64, device=dev)
+    g = torch.zeros(n, 3, dtype=torch.float64, device=dev)
+    args = lambda: (C.c_void_p(xd.data_ptr()), C.c_void_p(zd.data_ptr()), n, lat, ntess, C.c_void_p(e.data_ptr()), C.c_void_p(g.data_ptr()))
+    eng.evaluate_lattice_dev(*args())                      # builds the rows (with skin)
+    eng.sync()
+    r0 = ref.evaluate_lattice(X0, Z, lat, ntess)
+    _check_energy(e.cpu().numpy()[0:1], r0["Etotal"], "Etotal (build step)")
+    rs = np.random.RandomState(3)
+    X = X0.copy()
+    for step in range(3):                                   # a short walk, every atom stays within skin / 2 of X0
+        d = rs.randn(n, 3)
+        d *= (0.09 * rs.rand(n, 1)) / np.linalg.norm(d, axis=1, keepdims=True)
+        X = X + d
+        xd.copy_(torch.tensor(X, dtype=torch.float64))
+        eng.evaluate_lattice_dev(*args(), reuse_nlist=True)
+        eng.sync()
+        r = ref.evaluate_lattice(X, Z, lat, ntess)
+        ee, gg = e.cpu().numpy(), g.cpu().numpy()
+        scale = abs(r["Ebp"][0]) + abs(r["Ecc"][0]) + abs(r["Evdw"][0])     # (the parts cancel in Etotal for a small box)
+        for k, name in enumerate(("Etotal", "Ebp", "Ecc", "Evdw")):
+            assert abs(ee[k] - r[name][0]) <= 1e-6 * scale, (step, name, ee[k], r[name][0])
+        assert np.abs(gg - r["gradient"][0]).max() <= 2e-6 * np.abs(r["gradient"]).max()
+    if nx == 3:
+        Zt, Xt = onp.tess_lattice(lat, Z.astype(np.uint8), X, P["EECutoffOff"])
+        o = og.Oracle([1, 8], W, P).evaluate_periodic(Xt, Zt, n)
+        _check_energy(ee[0:1], o["Etotal"], "Etotal vs oracle")
+        _check_grad(gg, o["gradient"][0, :n])
+    # an atom that outruns the skin is reported at the next synchronisation, and a rebuild clears the condition
+    X[0] += 0.5
+    xd.copy_(torch.tensor(X, dtype=torch.float64))
+    eng.evaluate_lattice_dev(*args(), reuse_nlist=True)
+    with pytest.raises(TMolB200Error, match="skin"):
+        eng.sync()
+    eng.evaluate_lattice_dev(*args())
+    eng.sync()
+    r = ref.evaluate_lattice(X, Z, lat, ntess)
+    assert abs(e.cpu().numpy()[0] - r["Etotal"][0]) <= 1e-6 * (abs(r["Ebp"][0]) + abs(r["Ecc"][0]) + abs(r["Evdw"][0]))
+
+
+def test_device_md_with_verlet_skin_follows_the_every_step_rebuild():
+    """DevicePeriodicVelocityVerlet(skin_, nl_every_): 40 NVE steps with the rows rebuilt every 8 steps stay on the trajectory
+    of the run that rebuilds every step (same forces up to summation order)."""
+    from tensormol_b200 import PARAMS, Mol
+    from tensormol_b200.Simulations.DeviceMD import DevicePeriodicVelocityVerlet
+    Z, X, lat = _skin_system(4)
+    m = Mol(Z.astype(np.uint8), X)
+    manager, _ = _manager([m], [32, 32], 1)
+    PARAMS["MDMaxStep"] = 40; PARAMS["MDdt"] = 0.2; PARAMS["MDV0"] = None; PARAMS["MDThermostat"] = None; PARAMS["MDTemp"] = 300.0
+    PARAMS["MDLogTrajectory"] = False
+    v0 = 2e-3 * np.random.RandomState(5).randn(len(Z), 3)
+    a = DevicePeriodicVelocityVerlet(manager, m, lat, "md_every", v0_=v0.copy(), sync_every_=20)
+    la = a.Prop()
+    xa, va = a.x.copy(), a.v.copy()
+    b = DevicePeriodicVelocityVerlet(manager, m, lat, "md_skin", v0_=v0.copy(), sync_every_=20, skin_=0.5, nl_every_=8)
+    lb = b.Prop()
+    d = b.x - xa
+    d -= np.round(d @ np.linalg.inv(lat)) @ lat          # same point modulo the lattice (b wraps only on building steps)
+    assert np.abs(d).max() < 1e-6
+    assert np.abs(b.v - va).max() < 1e-6 * max(1.0, np.abs(va).max() / 1e-3)
+    assert np.abs(lb[:40, 5] - la[:40, 5]).max() <= 1e-6 * np.abs(la[:40, 5]).max()
+    manager.Instances.engine.set_skin(0.0)
