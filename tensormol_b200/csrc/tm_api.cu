@@ -214,6 +214,9 @@ extern "C" tm_ctx* tm_create(int device, const tm_model_desc* desc, const tm_par
   }
   if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) { tm_set_error("stream create failed"); delete c; return nullptr; }
   c->stream = c->own_stream;
+  cudaStreamCreateWithFlags(&c->aux, cudaStreamNonBlocking);
+  cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming);
   for (int i = 0; i < 12; i++) cudaEventCreate(&c->ev[i]);
   c->graphs_on = getenv("TM_NO_GRAPH") ? 0 : 1;
   c->ev_ok = true;
@@ -251,6 +254,9 @@ extern "C" void tm_destroy(tm_ctx* c) {
   if (c->h_stage) cudaFreeHost(c->h_stage);
   if (c->ev_ok) for (int i = 0; i < 12; i++) cudaEventDestroy(c->ev[i]);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
+  if (c->aux) cudaStreamDestroy(c->aux);
+  if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+  if (c->ev_join) cudaEventDestroy(c->ev_join);
   delete c;
 }
 
@@ -538,10 +544,45 @@ static int stage_b(tm_ctx* c, const SysView& s, int flags) {
   return TM_OK;
 }
 
+// Small problems (slab ranks, small cells): the backward GEMMs leave most SMs idle in their second tile round and the
+// pair kernel has long per-warp chains; neither needs the other's result, so the backward pass goes to the side stream
+// right after the forward pass and the two fill each other's gaps.  Large problems keep the single stream (both kernels
+// fill the machine on their own, and the stage timings stay separable).  TM_NO_OVERLAP=1 disables it.
+static bool overlap_backward(const tm_ctx* c, const SysView& s) {
+  static int off = -1;
+  if (off < 0) off = getenv("TM_NO_OVERLAP") ? 1 : 0;
+  if (off || !c->aux) return false;
+  int64_t expect = s.slab_world > 1 ? (s.periodic ? s.nreal : s.nslots) / s.slab_world : s.ncent_max;
+  return expect <= 8192;
+}
+static int fork_backward(tm_ctx* c, const SysView& s) {
+  TM_CUDA(cudaEventRecord(c->ev_fork, c->stream));
+  TM_CUDA(cudaStreamWaitEvent(c->aux, c->ev_fork, 0));
+  cudaStream_t keep = c->stream;
+  c->stream = c->aux;
+  int rc = tm_launch_mlp_backward(c, s);
+  c->stream = keep;
+  if (rc) return rc;
+  TM_CUDA(cudaEventRecord(c->ev_join, c->aux));
+  c->fork_open = true;
+  return TM_OK;
+}
+static int join_backward(tm_ctx* c) {
+  if (c->fork_open) {
+    TM_CUDA(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+    c->fork_open = false;
+  }
+  return TM_OK;
+}
+
 static int stage_c(tm_ctx* c, const SysView& s, int flags) {
   int rc;
   if (flags & TM_F_FORCE) {
-    if ((rc = tm_launch_mlp_backward(c, s))) return rc;
+    if (c->fork_open) {
+      if ((rc = join_backward(c))) return rc;
+    } else if ((rc = tm_launch_mlp_backward(c, s))) {
+      return rc;
+    }
     tm_trace(c, "nets backward");
     cudaEventRecord(c->ev[6], c->stream);
     if ((rc = tm_launch_force(c, s, flags))) return rc;
@@ -695,6 +736,7 @@ static int upload_inv_n(tm_ctx* c, const double* inv_n, int64_t nmol) {
 static int run_all(tm_ctx* c, const SysView& s, int flags, const OutLayout& o, bool reuse = false) {
   int rc;
   if ((rc = stage_a(c, s, reuse))) return rc;
+  if ((flags & TM_F_FORCE) && overlap_backward(c, s) && (rc = fork_backward(c, s))) return rc;
   if ((rc = stage_b(c, s, flags))) return rc;
   if ((rc = stage_c(c, s, flags))) return rc;
   return stage_pack(c, s, flags, o);
@@ -1241,7 +1283,14 @@ extern "C" int tm_slab_phase_a(tm_ctx* c, const double* xyz_dev, const int32_t* 
   }
   c->slab_view = s;
   if ((rc = stage_a(c, s))) return rc;
-  if ((rc = tm_launch_mlp_backward(c, s))) return rc;
+  // peer-memory exchange (the three phases are one stream of device work, possibly one CUDA graph): the backward GEMMs run on
+  // the side stream while this stream pushes q_raw, waits for the peers and runs the pair kernel; joined in phase C.
+  // Host collectives between the phases (NCCL fallback: one graph per phase) need the join inside this phase.
+  if (c->p2p.on && overlap_backward(c, s)) {
+    if ((rc = fork_backward(c, s))) return rc;
+  } else if ((rc = tm_launch_mlp_backward(c, s))) {
+    return rc;
+  }
   cudaEventRecord(c->ev[6], c->stream);
   if (c->p2p.on) {
     if (c->p2p.world != world || c->p2p.rank != rank || c->p2p.nreal != nreal) { tm_set_error("tm_slab_phase_a: does not match tm_slab_p2p_setup"); return TM_EINVAL; }
@@ -1307,6 +1356,7 @@ extern "C" int tm_slab_phase_c(tm_ctx* c, const double* e_dev, int flags, double
     TM_LAUNCH(k_slab_set_dedq, 1, 1, 0, c->stream, (double*)c->b_molacc.p, e_dev);
   }
   c->launches++;
+  if ((rc = join_backward(c))) return rc;
   if ((rc = tm_launch_force(c, s, flags))) return rc;
   if (c->p2p.on) {
     char* mine = c->p2p.base[c->p2p.rank];

@@ -149,6 +149,11 @@ struct tm_ctx {
   int device = 0;
   cudaStream_t own_stream = nullptr;
   cudaStream_t stream = nullptr;
+  // side stream for the nets' backward GEMMs of small problems (they depend on the forward pass only, not on the charge
+  // exchange or the pair kernel): fork after the forward pass, join before the force kernel
+  cudaStream_t aux = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  bool fork_open = false;
   tm_model_desc desc;
   tm_params params;
   DevParams hp;                  // host copy
