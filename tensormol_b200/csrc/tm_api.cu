@@ -235,7 +235,7 @@ extern "C" void tm_destroy(tm_ctx* c) {
   DevBuf* all[] = {&c->b_pos, &c->b_Z, &c->b_cellid, &c->b_rank, &c->b_count, &c->b_cstart, &c->b_sorted, &c->b_satom, &c->b_scan_tmp,
                    &c->b_rowslot, &c->b_rowsidx, &c->b_rowofslot, &c->b_blkcnt, &c->b_rowmeta, &c->b_nbcnt, &c->b_nboff, &c->b_nbr, &c->b_G, &c->b_Gs, &c->b_ypart,
                    &c->b_delta0, &c->b_delta1, &c->b_dG[0], &c->b_dG[1], &c->b_y[0], &c->b_y[1], &c->b_q, &c->b_qs, &c->b_dedq, &c->b_F,
-                   &c->b_acc, &c->b_bbox, &c->b_grid, &c->b_flags, &c->b_out, &c->b_molacc, &c->b_natom, &c->b_cntall, &c->b_offall, &c->b_pe, &c->b_pairtab, &c->b_lscan, &c->b_pos0};
+                   &c->b_acc, &c->b_bbox, &c->b_grid, &c->b_flags, &c->b_out, &c->b_molacc, &c->b_natom, &c->b_cntall, &c->b_offall, &c->b_pe, &c->b_pairtab, &c->b_lscan, &c->b_pos0, &c->b_gemm_ready[0], &c->b_gemm_ready[1]};
   for (DevBuf* b : all) free_buf(*b);
   for (int n = 0; n < 2; n++)
     for (int l = 0; l < TM_MAX_HIDDEN; l++) free_buf(c->b_act[n][l]);
@@ -639,6 +639,7 @@ static int check_flags(tm_ctx* c) {
   if (f[0] & 32) { tm_set_error("slab exchange: a peer rank never signalled (timed out after ~8 s)"); return TM_ECUDA; }
   if (f[0] & 8) { tm_set_error("coordinates are not wrapped into the cell (apply Lattice.ModuloLattice before tm_eval_lattice)"); return TM_EINVAL; }
   if (f[0] & 4) { tm_set_error("more than %d neighbours inside the angular cutoff of one centre", TM_ANG_CAP); return TM_ECAP; }
+  if (f[0] & 256) { tm_set_error("fused GEMM: a layer dependency was never published (timed out)"); return TM_ECUDA; }
   if (f[0] & 128) { tm_set_error("TM_F_REUSE_NLIST: an atom moved more than skin / 2 since the neighbour rows were built (rebuild more often or raise the skin)"); return TM_ESTATE; }
   if (f[0] & 64) { tm_set_error("a slab rank owns more centres than its row allocation (density far from uniform)"); return TM_ECAP; }
   return TM_OK;

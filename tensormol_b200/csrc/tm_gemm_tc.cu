@@ -27,9 +27,11 @@
 #include "tm_internal.h"
 #include <cuda.h>
 #include <cuda_fp16.h>
+#include <algorithm>
 #include <cstdlib>
 #include <cstdio>
 #include <map>
+#include <utility>
 #include <tuple>
 
 #define TC_BM 128
@@ -652,6 +654,376 @@ k_gemm_tc(const __grid_constant__ TcParams P, const int32_t* __restrict__ rowmet
   }
 }
 
+// ------------------------------------------------------------------------------------------------ all layers of a pass in one launch
+// k_gemm_tc_multi: the layers of the nets' forward pass (or of the backward-data pass) in ONE persistent launch.  Tiles are
+// numbered layer by layer (then group, row tile, column tile) and taken round-robin by the CTAs in that order; a tile of
+// layer l + 1 needs the 128 rows of its row tile from ALL column tiles of layer l, which other CTAs produce: the epilogue
+// warps publish a finished tile piece with a release increment of ready[l][group][row tile], and the TMA producer of a
+// dependent tile acquires that counter (bounded spin) before its first load.  Every dependency points to a lower tile
+// number, and a CTA takes its tiles in increasing order, so the CTAs that hold the awaited tiles are either running them
+// or already past them: no cycle (CTAs that have not been scheduled yet hold nothing back but their own tiles).
+// What it buys: two launches, prologues and tail rounds per pass disappear, and the tail of one layer overlaps the head
+// of the next -- the difference between 17 and ~11 us per layer for a slab rank's 3,000 rows.
+// Single-CTA 128 x 128 tiles only (gemm mode 1); same arithmetic, chunking and epilogues as k_gemm_tc.
+#define TCM_MAX_LAYERS 4
+#define TCM_MAX_GROUPS 8
+struct alignas(64) TcMulti {
+  TcGroup g[TCM_MAX_LAYERS][TCM_MAX_GROUPS];
+  int epi[TCM_MAX_LAYERS];
+  int nlayers, ngroups, act_kind, max_row_tiles;
+  float act_alpha;
+  int32_t* ready;       // [nlayers][ngroups][max_row_tiles] + 1 (CTAs done): zero at allocation, zeroed again by the last CTA
+  int nflags;
+  int32_t* errflags;
+};
+
+__device__ __forceinline__ int ld_acquire_gpu(const int32_t* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_gpu(int32_t* p, int v) {
+  asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+template <bool BWD, int ACTK>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k_gemm_tc_multi(const __grid_constant__ TcMulti P, const int32_t* __restrict__ rowmeta) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  constexpr int BN = TC_BN, STAGES = TC_STAGES, NPAIR = 512 / (2 * BN);
+  constexpr uint32_t A_BYTES = TC_BM * TC_BK * 2, B_BYTES = BN * TC_BK * 2, STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = (uint64_t*)(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* tempty_bar = tfull_bar + NPAIR;
+  uint32_t* tmem_slot = (uint32_t*)(tempty_bar + NPAIR);
+  int* tile_base = (int*)(tmem_slot + 4);                          // [TCM_MAX_LAYERS * TCM_MAX_GROUPS + 1]
+  int* row_first = tile_base + TCM_MAX_LAYERS * TCM_MAX_GROUPS + 1; // [TCM_MAX_GROUPS]
+  int* row_tiles = row_first + TCM_MAX_GROUPS;                     // [TCM_MAX_GROUPS]
+  float* tbuf = (float*)(((uintptr_t)(row_tiles + TCM_MAX_GROUPS) + 15) & ~(uintptr_t)15);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int W_TMA = TC_EPI_WARPS, W_MMA = TC_EPI_WARPS + 1;
+  const int unit = blockIdx.x, nunits = gridDim.x;
+  const int ngroups = P.ngroups, nlayers = P.nlayers;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int a = 0; a < NPAIR; a++) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], TC_EPI_WARPS); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == W_MMA) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)(NPAIR * 2 * BN)));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    for (int g = 0; g < ngroups; g++) {
+      int rows = rowmeta[2 * P.g[0][g].ele + 1];
+      row_first[g] = rowmeta[2 * P.g[0][g].ele];
+      row_tiles[g] = (rows + TC_BM - 1) / TC_BM;
+    }
+    for (int l = 0; l < nlayers; l++)
+      for (int g = 0; g < ngroups; g++) {
+        tile_base[l * ngroups + g] = acc;
+        acc += row_tiles[g] * (P.g[l][g].N / BN);
+      }
+    tile_base[nlayers * ngroups] = acc;
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+  const int nlg = nlayers * ngroups;
+  const int total_tiles = tile_base[nlg];
+
+  auto decode = [&](int t, int& l, int& g, int& rt, int& ct) {
+    int i = 0;
+    while (i + 1 < nlg && t >= tile_base[i + 1]) i++;
+    l = i / ngroups;
+    g = i - l * ngroups;
+    int local = t - tile_base[i];
+    int nct = P.g[l][g].N / BN;
+    rt = local / nct;
+    ct = local - rt * nct;
+  };
+
+  if (warp == W_TMA) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      for (int l = 0; l < nlayers; l++)
+        for (int g = 0; g < ngroups; g++) {
+          prefetch_tmap(&P.g[l][g].mapA_hi); prefetch_tmap(&P.g[l][g].mapA_lo);
+          prefetch_tmap(&P.g[l][g].mapB_hi); prefetch_tmap(&P.g[l][g].mapB_lo);
+        }
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = unit; t < total_tiles; t += nunits) {
+        int l, g, rt, ct;
+        decode(t, l, g, rt, ct);
+        const TcGroup& G = P.g[l][g];
+        if (l > 0) {
+          // the A rows of this tile are the previous layer's output for the same group and row tile: all its column tiles
+          const int32_t* flag = P.ready + ((size_t)(l - 1) * ngroups + g) * P.max_row_tiles + rt;
+          const int target = (P.g[l - 1][g].N / BN) * TC_EPI_WARPS;
+          long long t0 = clock64();
+          while (ld_acquire_gpu(flag) < target) {
+            if (clock64() - t0 > 8000000000ll) { atomicOr(P.errflags, 256); break; }   // ~4 s: something is badly wrong
+            __nanosleep(64);
+          }
+          asm volatile("fence.proxy.async;" ::: "memory");    // what the generic proxy acquired, the TMA may now read
+        }
+        int row0 = row_first[g] + rt * TC_BM, n0 = ct * BN;
+        int nkb = G.K / TC_BK;
+        for (int kb = 0; kb < nkb; kb++) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* st = smem + stage * STAGE_BYTES;
+          mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+          tma_load_2d(&G.mapA_hi, &full_bar[stage], st, kb * TC_BK, row0);
+          tma_load_2d(&G.mapA_lo, &full_bar[stage], st + A_BYTES, kb * TC_BK, row0);
+          tma_load_2d(&G.mapB_hi, &full_bar[stage], st + 2 * A_BYTES, kb * TC_BK, n0);
+          tma_load_2d(&G.mapB_lo, &full_bar[stage], st + 2 * A_BYTES + B_BYTES, kb * TC_BK, n0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == W_MMA) {
+    // ===================== MMA issuer =====================
+    if (elect_one()) {
+      constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      constexpr uint32_t idesc2 = (1u << 4) | ((uint32_t)((2 * BN) >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t chunk_it = 0;
+      for (int t = unit; t < total_tiles; t += nunits) {
+        int l, g, rt, ct;
+        decode(t, l, g, rt, ct);
+        int nkb = P.g[l][g].K / TC_BK;
+        for (int kb0 = 0; kb0 < nkb; kb0 += TC_CHUNK, chunk_it++) {
+          int pair = chunk_it % NPAIR;
+          uint32_t pair_phase = (chunk_it / NPAIR) & 1;
+          mbar_wait(&tempty_bar[pair], pair_phase ^ 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          uint32_t d_main = tmem_base + (uint32_t)(pair * 2 * BN);
+          uint32_t d_cross = d_main + BN;
+          int kb1 = min(kb0 + TC_CHUNK, nkb);
+          for (int kb = kb0; kb < kb1; kb++) {
+            mbar_wait(&full_bar[stage], phase);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+            uint64_t a_hi = umma_desc(sa), a_lo = umma_desc(sa + A_BYTES);
+            uint64_t b_hi = umma_desc(sa + 2 * A_BYTES);
+#pragma unroll
+            for (int k = 0; k < TC_BK / 16; k++) {
+              uint64_t koff = (uint64_t)((k * 16 * 2) >> 4);
+              uint32_t acc = ((kb - kb0) | k) ? 1u : 0u;
+              umma_f16(d_main, a_hi + koff, b_hi + koff, idesc2, acc);     // A_hi x [B_hi | B_lo] -> [main | cross]
+              umma_f16(d_cross, a_lo + koff, b_hi + koff, idesc, 1u);      // A_lo x B_hi -> cross
+            }
+            umma_commit(&empty_bar[stage]);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+          umma_commit(&tfull_bar[pair]);
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 0..7) =====================
+    const int q = warp & 3;
+    const int half = warp >> 2;
+    constexpr int NC = 64;
+    const int act_kind = (ACTK >= 0) ? ACTK : P.act_kind;
+    const float act_alpha = P.act_alpha;
+    const uint32_t tb = smem_u32(tbuf) + (uint32_t)warp * 4096u;
+    uint32_t chunk_it = 0;
+    for (int t = unit; t < total_tiles; t += nunits) {
+      int l, g, rt, ct;
+      decode(t, l, g, rt, ct);
+      const TcGroup& G = P.g[l][g];
+      const int epi = P.epi[l];
+      const int nkb = G.K / TC_BK;
+      const int64_t ldc = G.ldc;
+      const int64_t wrow0 = (int64_t)row_first[g] + (int64_t)rt * TC_BM + q * 32;
+      const int n0 = ct * BN + half * NC;
+      float bias_a = 0.f, bias_b = 0.f, wout_a = 0.f, wout_b = 0.f;
+      if (!BWD) {
+        const float* bp = G.bias + n0;
+        bias_a = __ldg(bp + lane);
+        bias_b = __ldg(bp + 32 + lane);
+        if (epi == TM_EPI_ACT_OUT) {
+          const float* wp = G.wout + n0;
+          wout_a = __ldg(wp + lane);
+          wout_b = __ldg(wp + 32 + lane);
+        }
+      }
+      float accr[NC];
+#pragma unroll
+      for (int i = 0; i < NC; i++) accr[i] = 0.f;
+      for (int kb0 = 0; kb0 < nkb; kb0 += TC_CHUNK, chunk_it++) {
+        int pair = chunk_it % NPAIR;
+        uint32_t pair_phase = (chunk_it / NPAIR) & 1;
+        mbar_wait(&tfull_bar[pair], pair_phase);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        uint32_t taddr = tmem_base + (uint32_t)(pair * 2 * BN + half * NC) + ((uint32_t)(q * 32) << 16);
+        uint32_t v[NC];
+#pragma unroll
+        for (int c = 0; c < NC / 32; c++) tmem_ld32(taddr + c * 32, v + c * 32);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int i = 0; i < NC; i++) accr[i] += __uint_as_float(v[i]);
+#pragma unroll
+        for (int c = 0; c < NC / 32; c++) tmem_ld32(taddr + BN + c * 32, v + c * 32);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[pair]);
+#pragma unroll
+        for (int i = 0; i < NC; i++) accr[i] = fmaf(__uint_as_float(v[i]), TC_LO_INV, accr[i]);
+      }
+      // ---- output phase (see k_gemm_tc): thread = row of the warp's 32-row band, NC = 64 consecutive columns
+      if (BWD && epi == TM_EPI_DACT) {
+        const __half* Hh = G.Hmul_hi;
+        const __half* Hl = G.Hmul_lo;
+        const int srow = lane >> 2, sc = lane & 3;
+        uint4 hh[2][4], ll[2][4];
+#pragma unroll
+        for (int p = 0; p < 2; p++)
+#pragma unroll
+          for (int it = 0; it < 4; it++) {
+            int64_t o = (wrow0 + it * 8 + srow) * ldc + n0 + p * 32 + sc * 8;
+            hh[p][it] = __ldg(reinterpret_cast<const uint4*>(Hh + o));
+            ll[p][it] = __ldg(reinterpret_cast<const uint4*>(Hl + o));
+          }
+#pragma unroll
+        for (int p = 0; p < 2; p++) {
+#pragma unroll
+          for (int it = 0; it < 4; it++) {
+            float2 a = join2(hh[p][it].x, ll[p][it].x), b = join2(hh[p][it].y, ll[p][it].y);
+            float2 c2 = join2(hh[p][it].z, ll[p][it].z), d = join2(hh[p][it].w, ll[p][it].w);
+            int r = it * 8 + srow;
+            sts128f(tb + 4u * TB_OFF(r, 2 * sc), tc_act_bwd(a.x, act_kind, act_alpha), tc_act_bwd(a.y, act_kind, act_alpha),
+                    tc_act_bwd(b.x, act_kind, act_alpha), tc_act_bwd(b.y, act_kind, act_alpha));
+            sts128f(tb + 4u * TB_OFF(r, 2 * sc + 1), tc_act_bwd(c2.x, act_kind, act_alpha), tc_act_bwd(c2.y, act_kind, act_alpha),
+                    tc_act_bwd(d.x, act_kind, act_alpha), tc_act_bwd(d.y, act_kind, act_alpha));
+          }
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 8; i++) {
+            uint4 dv = lds128(tb + 4u * TB_OFF(lane, i));
+            accr[p * 32 + 4 * i + 0] *= __uint_as_float(dv.x);
+            accr[p * 32 + 4 * i + 1] *= __uint_as_float(dv.y);
+            accr[p * 32 + 4 * i + 2] *= __uint_as_float(dv.z);
+            accr[p * 32 + 4 * i + 3] *= __uint_as_float(dv.w);
+          }
+          __syncwarp();
+        }
+      } else if (!BWD) {
+        // bias (and, for the last hidden layer, the output weights) through the tile; uniform-address 128-bit loads back
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(tb + 4u * lane), "f"(bias_a) : "memory");
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(tb + 128u + 4u * lane), "f"(bias_b) : "memory");
+        if (epi == TM_EPI_ACT_OUT) {
+          asm volatile("st.shared.f32 [%0], %1;" ::"r"(tb + 256u + 4u * lane), "f"(wout_a) : "memory");
+          asm volatile("st.shared.f32 [%0], %1;" ::"r"(tb + 384u + 4u * lane), "f"(wout_b) : "memory");
+        }
+        __syncwarp();
+        if (epi == TM_EPI_ACT_OUT) {
+          float part = 0.f;
+#pragma unroll
+          for (int i = 0; i < NC / 4; i++) {
+            uint4 b4 = lds128(tb + 16u * i);
+            uint4 w4 = lds128(tb + 256u + 16u * i);
+            const float bb[4] = {__uint_as_float(b4.x), __uint_as_float(b4.y), __uint_as_float(b4.z), __uint_as_float(b4.w)};
+            const float ww[4] = {__uint_as_float(w4.x), __uint_as_float(w4.y), __uint_as_float(w4.z), __uint_as_float(w4.w)};
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+              float h = tc_act_fwd(accr[4 * i + k], bb[k], act_kind, act_alpha);
+              part = fmaf(h, ww[k], part);
+              accr[4 * i + k] = ww[k] * tc_act_bwd(h, act_kind, act_alpha);
+            }
+          }
+          G.ypart[(int64_t)(ct * 2 + half) * G.ystride + wrow0 + lane] = part;
+        } else {
+#pragma unroll
+          for (int i = 0; i < NC / 4; i++) {
+            uint4 b4 = lds128(tb + 16u * i);
+            accr[4 * i + 0] = tc_act_fwd(accr[4 * i + 0], __uint_as_float(b4.x), act_kind, act_alpha);
+            accr[4 * i + 1] = tc_act_fwd(accr[4 * i + 1], __uint_as_float(b4.y), act_kind, act_alpha);
+            accr[4 * i + 2] = tc_act_fwd(accr[4 * i + 2], __uint_as_float(b4.z), act_kind, act_alpha);
+            accr[4 * i + 3] = tc_act_fwd(accr[4 * i + 3], __uint_as_float(b4.w), act_kind, act_alpha);
+          }
+        }
+        __syncwarp();
+      }
+      const int trow = lane >> 3, tc16 = lane & 7;
+      if (BWD && epi == TM_EPI_NONE) {
+        float* C32 = G.C32;
+#pragma unroll
+        for (int c = 0; c < NC / 32; c++) {
+#pragma unroll
+          for (int i = 0; i < 8; i++)
+            sts128f(tb + 4u * TB_OFF(lane, i), accr[c * 32 + 4 * i], accr[c * 32 + 4 * i + 1], accr[c * 32 + 4 * i + 2], accr[c * 32 + 4 * i + 3]);
+          __syncwarp();
+#pragma unroll
+          for (int it = 0; it < 8; it++) {
+            uint4 v4 = lds128(tb + 4u * TB_OFF(it * 4 + trow, tc16));
+            *reinterpret_cast<uint4*>(C32 + (wrow0 + it * 4 + trow) * ldc + n0 + c * 32 + tc16 * 4) = v4;
+          }
+          __syncwarp();
+        }
+      } else {
+        __half* Ch = G.C_hi;
+        __half* Cl = G.C_lo;
+        uint32_t hp[NC / 2], lp[NC / 2];
+#pragma unroll
+        for (int i = 0; i < NC / 2; i++) split2(accr[2 * i], accr[2 * i + 1], hp[i], lp[i]);
+#pragma unroll
+        for (int plane = 0; plane < 2; plane++) {
+          __half* Cp = plane ? Cl : Ch;
+#pragma unroll
+          for (int i = 0; i < 8; i++) {
+            uint4 u = plane ? make_uint4(lp[4 * i], lp[4 * i + 1], lp[4 * i + 2], lp[4 * i + 3])
+                            : make_uint4(hp[4 * i], hp[4 * i + 1], hp[4 * i + 2], hp[4 * i + 3]);
+            sts128(tb + 4u * TB_OFF(lane, i), u);
+          }
+          __syncwarp();
+#pragma unroll
+          for (int it = 0; it < 8; it++) {
+            uint4 u = lds128(tb + 4u * TB_OFF(it * 4 + trow, tc16));
+            *reinterpret_cast<uint4*>(Cp + (wrow0 + it * 4 + trow) * ldc + n0 + tc16 * 8) = u;
+          }
+          __syncwarp();
+        }
+      }
+      // this warp's piece of the tile is in global memory: let the next layer's tiles of this row tile know
+      if (l + 1 < nlayers) {
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) red_release_gpu(P.ready + ((size_t)l * ngroups + g) * P.max_row_tiles + rt, 1);
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == W_MMA) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(NPAIR * 2 * BN)));
+  }
+  // the CTA that finishes last (every tile, hence every reader of the counters, is done) zeroes them for the next launch:
+  // no memset node between the kernels of the step
+  __shared__ int s_last;
+  if (threadIdx.x == 0) {
+    __threadfence();
+    s_last = (atomicAdd(P.ready + P.nflags, 1) == (int)gridDim.x - 1) ? 1 : 0;
+  }
+  __syncthreads();
+  if (s_last) {
+    for (int i = threadIdx.x; i <= P.nflags; i += blockDim.x) P.ready[i] = 0;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ host side
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                     const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -832,8 +1204,81 @@ int tm_gemm_tc_launch(tm_ctx* c, const GemmGroup* groups, int ngroups, const int
   return bn == 64 ? launch_tc_epi<1, 64>(c, P, rowmeta_dev, bound, epilogue) : launch_tc_epi<1, TC_BN>(c, P, rowmeta_dev, bound, epilogue);
 }
 
+// All layers of one pass (forward: ACT .. ACT, ACT_OUT; backward: DACT .. DACT, NONE) in one k_gemm_tc_multi launch.
+// groups[l * ngroups + g], layers in execution order.  Returns +1 when the fused kernel does not apply (the caller then
+// launches layer by layer).
+int tm_gemm_tc_launch_multi(tm_ctx* c, const GemmGroup* groups, int nlayers, int ngroups, const int* rowmeta_dev, int max_row_tiles,
+                            int64_t expect_rows, const int* epilogues, bool backward) {
+  static int off = -1;
+  if (off < 0) off = getenv("TM_GEMM_NO_MULTI") ? 1 : 0;
+  if (off || c->gemm_mode != TM_GEMM_TC_SPLIT || nlayers < 2 || nlayers > TCM_MAX_LAYERS || ngroups > TCM_MAX_GROUPS) return 1;
+  // measured: a rank of eight (3,000 rows) gains 10 % of its GEMM time, the 24,000-row launch loses 3 % (the layer-by-layer
+  // kernels already run ~10 tile rounds per SM there): fused only while a layer has few tile rounds
+  static int force = -1;
+  if (force < 0) force = getenv("TM_GEMM_MULTI") ? 1 : 0;
+  if (!force && expect_rows > 8192) return 1;
+  int rc;
+  if ((rc = get_encode())) return rc;
+  for (int i = 0; i < nlayers * ngroups; i++)
+    if (groups[i].K % TC_BK || groups[i].N % TC_BN || !groups[i].A2 || !groups[i].B2) return 1;
+  if (!c->tc_multi) c->tc_multi = new TcMulti();     // 20 KB: per context (calls on a context are serialised by contract)
+  TcMulti& P = *(TcMulti*)c->tc_multi;
+  P.nlayers = nlayers; P.ngroups = ngroups; P.act_kind = c->hp.activation; P.act_alpha = c->hp.act_alpha;
+  P.max_row_tiles = max_row_tiles;
+  int64_t tiles = 0;
+  for (int l = 0; l < nlayers; l++) {
+    P.epi[l] = epilogues[l];
+    for (int gi = 0; gi < ngroups; gi++) {
+      const GemmGroup& g = groups[l * ngroups + gi];
+      TcGroup& T = P.g[l][gi];
+      if ((rc = make_map(c, &T.mapA_hi, g.A, g.rows_alloc, g.K, g.lda, TC_BM))) return rc;
+      if ((rc = make_map(c, &T.mapA_lo, g.A2, g.rows_alloc, g.K, g.lda, TC_BM))) return rc;
+      if ((rc = make_map(c, &T.mapB_hi, g.B, g.N, g.K, g.ldb, TC_BN))) return rc;
+      if ((rc = make_map(c, &T.mapB_lo, g.B2, g.N, g.K, g.ldb, TC_BN))) return rc;
+      T.bias = g.bias; T.Hmul_hi = (const __half*)g.Hmul; T.Hmul_lo = (const __half*)g.Hmul2;
+      T.C_hi = (__half*)g.C; T.C_lo = (__half*)g.C2; T.C32 = (float*)g.C;
+      T.wout = g.wout; T.ypart = g.ypart; T.ystride = g.rows_alloc;
+      if (epilogues[l] == TM_EPI_ACT_OUT && (!g.wout || !g.ypart)) { tm_set_error("tc gemm: output-layer epilogue without w_out / ypart"); return TM_EINVAL; }
+      T.ldc = g.ldc; T.K = g.K; T.N = g.N; T.ele = g.ele;
+      tiles += (int64_t)max_row_tiles * (g.N / TC_BN);
+    }
+  }
+  const size_t nflags = (size_t)nlayers * ngroups * max_row_tiles;
+  DevBuf& fb = backward ? c->b_gemm_ready[1] : c->b_gemm_ready[0];
+  const size_t cap_before = fb.cap;
+  if ((rc = tm_buf(c, fb, (nflags + 1) * 4))) return rc;
+  if (fb.cap != cap_before || c->gemm_ready_n[backward ? 1 : 0] != nflags) {   // new buffer or another layout: start from zero
+    TM_CUDA(cudaMemsetAsync(fb.p, 0, fb.cap, c->stream));
+    c->gemm_ready_n[backward ? 1 : 0] = nflags;
+  }
+  P.ready = (int32_t*)fb.p;
+  P.nflags = (int)nflags;
+  P.errflags = (int32_t*)c->b_flags.p;
+  constexpr size_t smem = (size_t)TC_STAGES * (2 * TC_BM * TC_BK * 2 + 2 * TC_BN * TC_BK * 2) + 1024 + 512 + TC_EPI_WARPS * 32 * 32 * 4;
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
+  int units = (int)std::min<int64_t>(sms, std::max<int64_t>(1, tiles));
+  const bool spec = P.act_kind == TM_ACT_SIGMOID_WITH_PARAM;
+  auto launch = [&](auto kern) -> int {
+    static std::map<std::pair<const void*, int>, bool> conf;
+    bool& done = conf[std::make_pair((const void*)kern, c->device)];
+    if (!done) {
+      TM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      done = true;
+    }
+    TM_CUDA(TM_LAUNCH(kern, units, TC_THREADS, smem, c->stream, P, rowmeta_dev));
+    c->launches++;
+    TM_CUDA(cudaGetLastError());
+    return TM_OK;
+  };
+  if (backward) return spec ? launch(k_gemm_tc_multi<true, TM_ACT_SIGMOID_WITH_PARAM>) : launch(k_gemm_tc_multi<true, -1>);
+  return spec ? launch(k_gemm_tc_multi<false, TM_ACT_SIGMOID_WITH_PARAM>) : launch(k_gemm_tc_multi<false, -1>);
+}
+
 void tm_gemm_tc_release(tm_ctx* c) {
   delete (TcParams*)c->tc_params;
+  delete (TcMulti*)c->tc_multi;
+  c->tc_multi = nullptr;
   delete (MapCache*)c->tc_maps;
   c->tc_params = nullptr;
   c->tc_maps = nullptr;

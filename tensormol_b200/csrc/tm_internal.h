@@ -168,7 +168,7 @@ struct tm_ctx {
   // ---- per-evaluation workspace (grow-only) ----
   DevBuf b_pos, b_Z, b_cellid, b_rank, b_count, b_cstart, b_sorted, b_satom, b_scan_tmp;
   DevBuf b_rowslot, b_rowsidx, b_rowofslot, b_blkcnt, b_rowmeta;
-  DevBuf b_cntall, b_offall, b_pe, b_pairtab, b_lscan;
+  DevBuf b_cntall, b_offall, b_pe, b_pairtab, b_lscan, b_gemm_ready[2];
   // Verlet skin (tm_set_skin): state of the last list-building lattice call
   double skin = 0.0;
   bool nl_ok = false;
@@ -203,6 +203,8 @@ struct tm_ctx {
     uint64_t alloc_gen = 0, cfg_gen = 0;
     bool failed = false;         // capture failed for this key: stay eager
   } lg;
+  size_t gemm_ready_n[2] = {0, 0};
+  void* tc_multi = nullptr;      // TcMulti scratch of the fused multi-layer GEMM launch
   void* tc_params = nullptr;     // TcParams scratch of tm_gemm_tc.cu (kernel argument block, one per context)
   void* tc_maps = nullptr;       // tensor-map cache of tm_gemm_tc.cu
   int graphs_on = 1;             // TM_NO_GRAPH=1 in the environment disables the replay
@@ -289,6 +291,8 @@ struct GemmGroup {
   float* ypart = nullptr;
 };
 void tm_gemm_tc_release(tm_ctx* c);
+int tm_gemm_tc_launch_multi(tm_ctx* c, const GemmGroup* groups, int nlayers, int ngroups, const int* rowmeta_dev, int max_row_tiles,
+                            int64_t expect_rows, const int* epilogues, bool backward);   // +1 = not applicable, launch layer by layer
 int tm_launch_gemm(tm_ctx* c, const GemmGroup* groups, int ngroups, const int* rowmeta_dev, int max_row_tiles, int64_t expect_rows, int epilogue);
 // TM_EPI_ACT_OUT (tensor-core mode, last hidden layer): h = act(z + b) is not stored; the epilogue emits the output layer's
 // partial dot products  ypart[p][row] = sum_cols h*w_out  (p = 128-column half-tile index) and C = w_out * act'(h), the

@@ -331,9 +331,12 @@ int tm_launch_mlp_forward(tm_ctx* c, const SysView& s) {
   int max_tiles = (int)((s.ncent_max + TM_ROW_TILE - 1) / TM_ROW_TILE) + 1;
   const int* rowmeta = (const int*)c->b_rowmeta.p;
   // (tensor-core mode: k_desc already wrote the descriptor rows as fp16 hi/lo planes into b_Gs)
+  GemmGroup all[TM_MAX_HIDDEN][2 * TM_MAX_ELE];
+  int epis[TM_MAX_HIDDEN];
+  int ng = 0;
   for (int l = 0; l < nh; l++) {
-    GemmGroup gg[2 * TM_MAX_ELE];
-    int ng = 0;
+    GemmGroup* gg = all[l];
+    ng = 0;
     for (int net = 0; net < 2; net++)
       for (int e = 0; e < ne; e++) {
         const Layer& L = c->nets[net][e].layers[l];
@@ -359,9 +362,23 @@ int tm_launch_mlp_forward(tm_ctx* c, const SysView& s) {
           g.ypart = (float*)c->b_ypart.p + (size_t)net * (2 * c->Hmax / 128) * s.nrows;
         }
       }
-    if ((rc = tm_launch_gemm(c, gg, ng, rowmeta, max_tiles, expect_rows(s), (tc && l == nh - 1) ? TM_EPI_ACT_OUT : TM_EPI_ACT))) return rc;
-    tm_trace(c, l == 0 ? "forward GEMM layer 0" : l == 1 ? "forward GEMM layer 1" : "forward GEMM layer 2+");
+    epis[l] = (tc && l == nh - 1) ? TM_EPI_ACT_OUT : TM_EPI_ACT;
   }
+  // tensor-core mode: all layers in one persistent launch when the fused kernel applies, else layer by layer
+  rc = 1;
+  if (tc) {
+    GemmGroup flat[TM_MAX_HIDDEN * 2 * TM_MAX_ELE];
+    for (int l = 0; l < nh; l++)
+      for (int i = 0; i < ng; i++) flat[l * ng + i] = all[l][i];
+    rc = tm_gemm_tc_launch_multi(c, flat, nh, ng, rowmeta, max_tiles, expect_rows(s), epis, false);
+    if (rc < 0) return rc;
+    if (rc == 0) tm_trace(c, "forward GEMMs (all layers, one launch)");
+  }
+  if (rc == 1)
+    for (int l = 0; l < nh; l++) {
+      if ((rc = tm_launch_gemm(c, all[l], ng, rowmeta, max_tiles, expect_rows(s), epis[l]))) return rc;
+      tm_trace(c, l == 0 ? "forward GEMM layer 0" : l == 1 ? "forward GEMM layer 1" : "forward GEMM layer 2+");
+    }
   if (tc) {
     YTbl Y;
     for (int net = 0; net < 2; net++) {
@@ -413,9 +430,12 @@ int tm_launch_mlp_backward(tm_ctx* c, const SysView& s) {
   int nh = c->desc.n_hidden, ne = c->hp.n_ele;
   int max_tiles = (int)((s.ncent_max + TM_ROW_TILE - 1) / TM_ROW_TILE) + 1;
   const int* rowmeta = (const int*)c->b_rowmeta.p;
+  GemmGroup all[TM_MAX_HIDDEN][2 * TM_MAX_ELE];   // in execution order: index 0 = the last hidden layer
+  int epis[TM_MAX_HIDDEN];
+  int ng = 0;
   for (int l = nh - 1; l >= 0; l--) {
-    GemmGroup gg[2 * TM_MAX_ELE];
-    int ng = 0;
+    GemmGroup* gg = all[nh - 1 - l];
+    ng = 0;
     for (int net = 0; net < 2; net++)
       for (int e = 0; e < ne; e++) {
         const Layer& L = c->nets[net][e].layers[l];
@@ -435,8 +455,22 @@ int tm_launch_mlp_backward(tm_ctx* c, const SysView& s) {
           g.C = c->b_dG[net].p; g.ldc = c->hp.Dp;
         }
       }
-    if ((rc = tm_launch_gemm(c, gg, ng, rowmeta, max_tiles, expect_rows(s), l > 0 ? TM_EPI_DACT : TM_EPI_NONE))) return rc;
-    tm_trace(c, l == 0 ? "backward GEMM layer 0" : l == 1 ? "backward GEMM layer 1" : "backward GEMM layer 2+");
+    epis[nh - 1 - l] = l > 0 ? TM_EPI_DACT : TM_EPI_NONE;
   }
+  rc = 1;
+  if (tc) {
+    GemmGroup flat[TM_MAX_HIDDEN * 2 * TM_MAX_ELE];
+    for (int l = 0; l < nh; l++)
+      for (int i = 0; i < ng; i++) flat[l * ng + i] = all[l][i];
+    rc = tm_gemm_tc_launch_multi(c, flat, nh, ng, rowmeta, max_tiles, expect_rows(s), epis, true);
+    if (rc < 0) return rc;
+    if (rc == 0) tm_trace(c, "backward GEMMs (all layers, one launch)");
+  }
+  if (rc == 1)
+    for (int l = 0; l < nh; l++) {
+      if ((rc = tm_launch_gemm(c, all[l], ng, rowmeta, max_tiles, expect_rows(s), epis[l]))) return rc;
+      tm_trace(c, "backward GEMM layer");
+    }
+
   return TM_OK;
 }
