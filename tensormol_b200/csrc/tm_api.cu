@@ -235,7 +235,7 @@ extern "C" void tm_destroy(tm_ctx* c) {
   DevBuf* all[] = {&c->b_pos, &c->b_Z, &c->b_cellid, &c->b_rank, &c->b_count, &c->b_cstart, &c->b_sorted, &c->b_satom, &c->b_scan_tmp,
                    &c->b_rowslot, &c->b_rowsidx, &c->b_rowofslot, &c->b_blkcnt, &c->b_rowmeta, &c->b_nbcnt, &c->b_nboff, &c->b_nbr, &c->b_G, &c->b_Gs, &c->b_ypart,
                    &c->b_delta0, &c->b_delta1, &c->b_dG[0], &c->b_dG[1], &c->b_y[0], &c->b_y[1], &c->b_q, &c->b_qs, &c->b_dedq, &c->b_F,
-                   &c->b_acc, &c->b_bbox, &c->b_grid, &c->b_flags, &c->b_out, &c->b_molacc, &c->b_natom, &c->b_cntall, &c->b_offall, &c->b_pe, &c->b_pairtab, &c->b_lscan, &c->b_pos0, &c->b_gemm_ready[0], &c->b_gemm_ready[1]};
+                   &c->b_acc, &c->b_bbox, &c->b_grid, &c->b_flags, &c->b_out, &c->b_molacc, &c->b_natom, &c->b_cntall, &c->b_offall, &c->b_pe, &c->b_pairtab, &c->b_lscan, &c->b_pos0, &c->b_gemm_ready[0], &c->b_gemm_ready[1], &c->b_p2pdone};
   for (DevBuf* b : all) free_buf(*b);
   for (int n = 0; n < 2; n++)
     for (int l = 0; l < TM_MAX_HIDDEN; l++) free_buf(c->b_act[n][l]);
@@ -1201,6 +1201,80 @@ __global__ void k_p2p_signal(PeerPtrs f, int world, int which) {
   int p = threadIdx.x;
   if (p < world) atomicAdd_system((unsigned int*)(f.p[p]) + 16 * which, 1u);
 }
+// The exchange kernels below carry their own signal: a block that has issued its peer stores fences them system-wide and
+// counts itself done; the block that finishes last bumps arrival counter `which` on every peer (k_p2p_signal's job without
+// the extra launch).  `done` is a device counter that the last block resets.
+__device__ __forceinline__ void p2p_signal_when_last(PeerPtrs f, int world, int which, int32_t* done) {
+  __shared__ int s_last;
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(done, 1) == (int)gridDim.x - 1) ? 1 : 0;
+  __syncthreads();
+  if (s_last) {
+    __threadfence_system();
+    if ((int)threadIdx.x < world) atomicAdd_system((unsigned int*)(f.p[threadIdx.x]) + 16 * which, 1u);
+    if (threadIdx.x == 0) *done = 0;
+  }
+}
+__global__ void k_owned_qraw_p2p_sig(const float* __restrict__ y, const int32_t* __restrict__ rowslot, int64_t nrows, PeerPtrs q, PeerPtrs f, int world,
+                                     int32_t* __restrict__ done) {
+  TM_PDL_PROLOGUE;
+  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < nrows; r += (int64_t)gridDim.x * blockDim.x) {
+    int s = rowslot[r];
+    if (s < 0) continue;
+    double v = (double)y[r];
+    for (int p = 0; p < world; p++) ((double*)q.p[p])[s] = v;
+  }
+  p2p_signal_when_last(f, world, 0, done);
+}
+// this rank's energy partials into slot [rank] of every peer, then the signal (one warp: lane p serves peer p)
+__global__ void k_slab_e_p2p_sig(const double* __restrict__ molacc, int add_ecc, PeerPtrs e, PeerPtrs f, int world, int rank) {
+  TM_PDL_PROLOGUE;
+  int p = threadIdx.x;
+  if (p < world) {
+    double* d = (double*)e.p[p] + 8 * rank;
+    d[0] = 0.0; d[1] = molacc[1]; d[2] = add_ecc ? molacc[2] : 0.0; d[3] = molacc[3]; d[4] = molacc[5]; d[5] = 0.0;
+    __threadfence_system();
+    atomicAdd_system((unsigned int*)(f.p[p]) + 16 * 1, 1u);
+  }
+}
+__global__ void k_push_grad_p2p_sig(const float* __restrict__ F, int64_t n3, int64_t stride, PeerPtrs g, PeerPtrs f, int world, int rank,
+                                    int32_t* __restrict__ done) {
+  TM_PDL_PROLOGUE;
+  int64_t n4 = n3 / 4;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n4; t += (int64_t)gridDim.x * blockDim.x) {
+    float4 v = reinterpret_cast<const float4*>(F)[t];
+    for (int p = 0; p < world; p++) reinterpret_cast<float4*>((float*)g.p[p] + (int64_t)rank * stride)[t] = v;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n3 & 3)) {
+    int64_t t = n4 * 4 + threadIdx.x;
+    for (int p = 0; p < world; p++) ((float*)g.p[p] + (int64_t)rank * stride)[t] = F[t];
+  }
+  p2p_signal_when_last(f, world, 2, done);
+}
+// the force sum with the wait for exchange 2 in front of it: every block spins (bounded) until all ranks have signalled.
+// Epoch = the one k_p2p_wait of exchange 0 has set for this step (stable until the next step's phase B).
+__global__ void k_wait_sum_grad_p2p(char* flags, int world, int32_t* errflags, const float* __restrict__ gparts, int64_t n3, int64_t stride,
+                                    double* __restrict__ out) {
+  TM_PDL_PROLOGUE;
+  if (threadIdx.x == 0) {
+    volatile unsigned int* cnt = (volatile unsigned int*)flags + 16 * 2;
+    const unsigned int target = *((volatile unsigned int*)flags + 16 * 4) * (unsigned int)world;
+    long long t0 = clock64();
+    while ((int)(*cnt - target) < 0) {
+      if (clock64() - t0 > 16000000000ll) { atomicOr(errflags, 32); break; }
+      __nanosleep(100);
+    }
+    __threadfence_system();
+  }
+  __syncthreads();
+  const volatile float* gp = gparts;     // written by the peers: no cached / hoisted reads
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n3; t += (int64_t)gridDim.x * blockDim.x) {
+    double s = 0.0;
+    for (int r = 0; r < world; r++) s += (double)gp[(int64_t)r * stride + t];
+    out[t] = s;
+  }
+}
 // wait until every rank has signalled the next epoch of exchange `which` (epoch kept on the device: graph replayable)
 __global__ void k_p2p_wait(char* flags, int world, int which, int32_t* errflags) {
   TM_PDL_PROLOGUE;
@@ -1259,6 +1333,10 @@ static int p2p_preload(tm_ctx* c) {
   TM_CUDA(cudaFuncGetAttributes(&fa, k_p2p_wait));
   TM_CUDA(cudaFuncGetAttributes(&fa, k_p2p_wait_reduce_e));
   TM_CUDA(cudaFuncGetAttributes(&fa, k_sum_grad_p2p));
+  TM_CUDA(cudaFuncGetAttributes(&fa, k_owned_qraw_p2p_sig));
+  TM_CUDA(cudaFuncGetAttributes(&fa, k_slab_e_p2p_sig));
+  TM_CUDA(cudaFuncGetAttributes(&fa, k_push_grad_p2p_sig));
+  TM_CUDA(cudaFuncGetAttributes(&fa, k_wait_sum_grad_p2p));
   return TM_OK;
 }
 
@@ -1295,10 +1373,10 @@ extern "C" int tm_slab_phase_a(tm_ctx* c, const double* xyz_dev, const int32_t* 
   cudaEventRecord(c->ev[6], c->stream);
   if (c->p2p.on) {
     if (c->p2p.world != world || c->p2p.rank != rank || c->p2p.nreal != nreal) { tm_set_error("tm_slab_phase_a: does not match tm_slab_p2p_setup"); return TM_EINVAL; }
-    TM_LAUNCH(k_owned_qraw_p2p, nblk(s.nrows), 256, 0, c->stream, (const float*)c->b_y[TM_NET_CHARGE].p, (const int32_t*)c->b_rowslot.p, s.nrows,
-                                                          peer_ptrs(c, c->p2p.off_q), world);
-    TM_LAUNCH(k_p2p_signal, 1, 32, 0, c->stream, peer_ptrs(c, c->p2p.off_flag), world, 0);
-    c->launches += 2;
+    if ((rc = tm_buf(c, c->b_p2pdone, 64))) return rc;
+    TM_LAUNCH(k_owned_qraw_p2p_sig, nblk(s.nrows), 256, 0, c->stream, (const float*)c->b_y[TM_NET_CHARGE].p, (const int32_t*)c->b_rowslot.p, s.nrows,
+              peer_ptrs(c, c->p2p.off_q), peer_ptrs(c, c->p2p.off_flag), world, (int32_t*)c->b_p2pdone.p);
+    c->launches += 1;
   } else {
     TM_CUDA(cudaMemsetAsync(qraw_dev, 0, (size_t)nreal * 8, c->stream));
     TM_LAUNCH(k_owned_qraw, nblk(s.nrows), 256, 0, c->stream, (const float*)c->b_y[TM_NET_CHARGE].p, (const int32_t*)c->b_rowslot.p, s.nrows, qraw_dev);
@@ -1332,9 +1410,8 @@ extern "C" int tm_slab_phase_b(tm_ctx* c, const double* qraw_dev, double* e_dev)
     c->launches++;
   }
   if (c->p2p.on) {
-    TM_LAUNCH(k_slab_e_p2p, 1, 32, 0, c->stream, (const double*)c->b_molacc.p, c->hp.add_ecc, peer_ptrs(c, c->p2p.off_e), c->p2p.world, c->p2p.rank);
-    TM_LAUNCH(k_p2p_signal, 1, 32, 0, c->stream, peer_ptrs(c, c->p2p.off_flag), c->p2p.world, 1);
-    c->launches++;
+    TM_LAUNCH(k_slab_e_p2p_sig, 1, 32, 0, c->stream, (const double*)c->b_molacc.p, c->hp.add_ecc, peer_ptrs(c, c->p2p.off_e), peer_ptrs(c, c->p2p.off_flag),
+              c->p2p.world, c->p2p.rank);
   } else {
     TM_LAUNCH(k_slab_e, 1, 1, 0, c->stream, (const double*)c->b_molacc.p, e_dev, c->hp.add_ecc);
   }
@@ -1362,11 +1439,11 @@ extern "C" int tm_slab_phase_c(tm_ctx* c, const double* e_dev, int flags, double
   if (c->p2p.on) {
     char* mine = c->p2p.base[c->p2p.rank];
     int64_t n3 = 3 * s.nreal, stride = (n3 + 3) / 4 * 4;
-    TM_LAUNCH(k_push_grad_p2p, nblk(n3 / 4 + 1), 256, 0, c->stream, (const float*)c->b_F.p, n3, stride, peer_ptrs(c, c->p2p.off_g), c->p2p.world, c->p2p.rank);
-    TM_LAUNCH(k_p2p_signal, 1, 32, 0, c->stream, peer_ptrs(c, c->p2p.off_flag), c->p2p.world, 2);
-    TM_LAUNCH(k_p2p_wait, 1, 1, 0, c->stream, mine + c->p2p.off_flag, c->p2p.world, 2, (int32_t*)c->b_flags.p);
-    TM_LAUNCH(k_sum_grad_p2p, nblk(n3), 256, 0, c->stream, (const float*)(mine + c->p2p.off_g), c->p2p.world, n3, stride, grad_dev);
-    c->launches += 3;
+    TM_LAUNCH(k_push_grad_p2p_sig, nblk(n3 / 4 + 1), 256, 0, c->stream, (const float*)c->b_F.p, n3, stride, peer_ptrs(c, c->p2p.off_g), peer_ptrs(c, c->p2p.off_flag),
+              c->p2p.world, c->p2p.rank, (int32_t*)c->b_p2pdone.p + 8);
+    TM_LAUNCH(k_wait_sum_grad_p2p, nblk(n3), 256, 0, c->stream, mine + c->p2p.off_flag, c->p2p.world, (int32_t*)c->b_flags.p, (const float*)(mine + c->p2p.off_g),
+              n3, stride, grad_dev);
+    c->launches += 1;
   } else {
     TM_LAUNCH(k_f2d, nblk(3 * s.nreal), 256, 0, c->stream, (const float*)c->b_F.p, grad_dev, 3 * s.nreal);
   }

@@ -1209,9 +1209,9 @@ int tm_gemm_tc_launch(tm_ctx* c, const GemmGroup* groups, int ngroups, const int
 // launches layer by layer).
 int tm_gemm_tc_launch_multi(tm_ctx* c, const GemmGroup* groups, int nlayers, int ngroups, const int* rowmeta_dev, int max_row_tiles,
                             int64_t expect_rows, const int* epilogues, bool backward) {
-  static int off = -1;
-  if (off < 0) off = getenv("TM_GEMM_NO_MULTI") ? 1 : 0;
-  if (off || c->gemm_mode != TM_GEMM_TC_SPLIT || nlayers < 2 || nlayers > TCM_MAX_LAYERS || ngroups > TCM_MAX_GROUPS) return 1;
+  static int off = -1, off_f = 0, off_b = 0;
+  if (off < 0) { off = getenv("TM_GEMM_NO_MULTI") ? 1 : 0; off_f = getenv("TM_GEMM_NO_MULTI_FWD") ? 1 : 0; off_b = getenv("TM_GEMM_NO_MULTI_BWD") ? 1 : 0; }
+  if ((backward ? off_b : off_f) || off || c->gemm_mode != TM_GEMM_TC_SPLIT || nlayers < 2 || nlayers > TCM_MAX_LAYERS || ngroups > TCM_MAX_GROUPS) return 1;
   // measured: a rank of eight (3,000 rows) gains 10 % of its GEMM time, the 24,000-row launch loses 3 % (the layer-by-layer
   // kernels already run ~10 tile rounds per SM there): fused only while a layer has few tile rounds
   static int force = -1;

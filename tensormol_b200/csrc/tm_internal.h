@@ -168,7 +168,7 @@ struct tm_ctx {
   // ---- per-evaluation workspace (grow-only) ----
   DevBuf b_pos, b_Z, b_cellid, b_rank, b_count, b_cstart, b_sorted, b_satom, b_scan_tmp;
   DevBuf b_rowslot, b_rowsidx, b_rowofslot, b_blkcnt, b_rowmeta;
-  DevBuf b_cntall, b_offall, b_pe, b_pairtab, b_lscan, b_gemm_ready[2];
+  DevBuf b_cntall, b_offall, b_pe, b_pairtab, b_lscan, b_gemm_ready[2], b_p2pdone;
   // Verlet skin (tm_set_skin): state of the last list-building lattice call
   double skin = 0.0;
   bool nl_ok = false;

@@ -458,7 +458,9 @@ int tm_launch_mlp_backward(tm_ctx* c, const SysView& s) {
     epis[nh - 1 - l] = l > 0 ? TM_EPI_DACT : TM_EPI_NONE;
   }
   rc = 1;
-  if (tc) {
+  // (measured on two GPUs, 3,300 rows per rank: beside the peer exchange and the pair kernel the fused backward launch is 3.5 %
+  // slower than three launches, while single-GPU small problems gain 3-8 %: slab ranks keep the layer-by-layer backward pass)
+  if (tc && !s.slab_api) {
     GemmGroup flat[TM_MAX_HIDDEN * 2 * TM_MAX_ELE];
     for (int l = 0; l < nh; l++)
       for (int i = 0; i < ng; i++) flat[l * ng + i] = all[l][i];
