@@ -1139,6 +1139,15 @@ extern "C" int64_t tm_slab_p2p_bytes(int world, int64_t nreal) {
 }
 
 static int p2p_preload(tm_ctx* c);
+// The exchange runs as separate store / signal / wait / sum launches.  TM_P2P_MERGED=1 selects the variants that fold the
+// signal into the producing kernel (last block) and the wait into the force sum: two launches fewer per exchange, but the
+// system-wide fence in every block costs more than the launches do (same box, 2 GPUs: 0.260 vs 0.247 ms at 3,300 atoms
+// per rank, 0.572 vs 0.555 ms at 12,000), so they are kept for reference only.
+static bool p2p_split_kernels() {
+  static int v = -1;
+  if (v < 0) v = getenv("TM_P2P_MERGED") ? 0 : 1;
+  return v != 0;
+}
 
 extern "C" int tm_slab_p2p_setup(tm_ctx* c, int world, int rank, int64_t nreal, void* const* peer_base) {
   if (!c) { tm_set_error("tm_slab_p2p_setup: null context"); return TM_EINVAL; }
@@ -1374,9 +1383,16 @@ extern "C" int tm_slab_phase_a(tm_ctx* c, const double* xyz_dev, const int32_t* 
   if (c->p2p.on) {
     if (c->p2p.world != world || c->p2p.rank != rank || c->p2p.nreal != nreal) { tm_set_error("tm_slab_phase_a: does not match tm_slab_p2p_setup"); return TM_EINVAL; }
     if ((rc = tm_buf(c, c->b_p2pdone, 64))) return rc;
-    TM_LAUNCH(k_owned_qraw_p2p_sig, nblk(s.nrows), 256, 0, c->stream, (const float*)c->b_y[TM_NET_CHARGE].p, (const int32_t*)c->b_rowslot.p, s.nrows,
-              peer_ptrs(c, c->p2p.off_q), peer_ptrs(c, c->p2p.off_flag), world, (int32_t*)c->b_p2pdone.p);
-    c->launches += 1;
+    if (p2p_split_kernels()) {
+      TM_LAUNCH(k_owned_qraw_p2p, nblk(s.nrows), 256, 0, c->stream, (const float*)c->b_y[TM_NET_CHARGE].p, (const int32_t*)c->b_rowslot.p, s.nrows,
+                peer_ptrs(c, c->p2p.off_q), world);
+      TM_LAUNCH(k_p2p_signal, 1, 32, 0, c->stream, peer_ptrs(c, c->p2p.off_flag), world, 0);
+      c->launches += 2;
+    } else {
+      TM_LAUNCH(k_owned_qraw_p2p_sig, nblk(s.nrows), 256, 0, c->stream, (const float*)c->b_y[TM_NET_CHARGE].p, (const int32_t*)c->b_rowslot.p, s.nrows,
+                peer_ptrs(c, c->p2p.off_q), peer_ptrs(c, c->p2p.off_flag), world, (int32_t*)c->b_p2pdone.p);
+      c->launches += 1;
+    }
   } else {
     TM_CUDA(cudaMemsetAsync(qraw_dev, 0, (size_t)nreal * 8, c->stream));
     TM_LAUNCH(k_owned_qraw, nblk(s.nrows), 256, 0, c->stream, (const float*)c->b_y[TM_NET_CHARGE].p, (const int32_t*)c->b_rowslot.p, s.nrows, qraw_dev);
@@ -1410,8 +1426,14 @@ extern "C" int tm_slab_phase_b(tm_ctx* c, const double* qraw_dev, double* e_dev)
     c->launches++;
   }
   if (c->p2p.on) {
-    TM_LAUNCH(k_slab_e_p2p_sig, 1, 32, 0, c->stream, (const double*)c->b_molacc.p, c->hp.add_ecc, peer_ptrs(c, c->p2p.off_e), peer_ptrs(c, c->p2p.off_flag),
-              c->p2p.world, c->p2p.rank);
+    if (p2p_split_kernels()) {
+      TM_LAUNCH(k_slab_e_p2p, 1, 32, 0, c->stream, (const double*)c->b_molacc.p, c->hp.add_ecc, peer_ptrs(c, c->p2p.off_e), c->p2p.world, c->p2p.rank);
+      TM_LAUNCH(k_p2p_signal, 1, 32, 0, c->stream, peer_ptrs(c, c->p2p.off_flag), c->p2p.world, 1);
+      c->launches++;
+    } else {
+      TM_LAUNCH(k_slab_e_p2p_sig, 1, 32, 0, c->stream, (const double*)c->b_molacc.p, c->hp.add_ecc, peer_ptrs(c, c->p2p.off_e), peer_ptrs(c, c->p2p.off_flag),
+                c->p2p.world, c->p2p.rank);
+    }
   } else {
     TM_LAUNCH(k_slab_e, 1, 1, 0, c->stream, (const double*)c->b_molacc.p, e_dev, c->hp.add_ecc);
   }
@@ -1439,11 +1461,19 @@ extern "C" int tm_slab_phase_c(tm_ctx* c, const double* e_dev, int flags, double
   if (c->p2p.on) {
     char* mine = c->p2p.base[c->p2p.rank];
     int64_t n3 = 3 * s.nreal, stride = (n3 + 3) / 4 * 4;
-    TM_LAUNCH(k_push_grad_p2p_sig, nblk(n3 / 4 + 1), 256, 0, c->stream, (const float*)c->b_F.p, n3, stride, peer_ptrs(c, c->p2p.off_g), peer_ptrs(c, c->p2p.off_flag),
-              c->p2p.world, c->p2p.rank, (int32_t*)c->b_p2pdone.p + 8);
-    TM_LAUNCH(k_wait_sum_grad_p2p, nblk(n3), 256, 0, c->stream, mine + c->p2p.off_flag, c->p2p.world, (int32_t*)c->b_flags.p, (const float*)(mine + c->p2p.off_g),
-              n3, stride, grad_dev);
-    c->launches += 1;
+    if (p2p_split_kernels()) {
+      TM_LAUNCH(k_push_grad_p2p, nblk(n3 / 4 + 1), 256, 0, c->stream, (const float*)c->b_F.p, n3, stride, peer_ptrs(c, c->p2p.off_g), c->p2p.world, c->p2p.rank);
+      TM_LAUNCH(k_p2p_signal, 1, 32, 0, c->stream, peer_ptrs(c, c->p2p.off_flag), c->p2p.world, 2);
+      TM_LAUNCH(k_p2p_wait, 1, 1, 0, c->stream, mine + c->p2p.off_flag, c->p2p.world, 2, (int32_t*)c->b_flags.p);
+      TM_LAUNCH(k_sum_grad_p2p, nblk(n3), 256, 0, c->stream, (const float*)(mine + c->p2p.off_g), c->p2p.world, n3, stride, grad_dev);
+      c->launches += 3;
+    } else {
+      TM_LAUNCH(k_push_grad_p2p_sig, nblk(n3 / 4 + 1), 256, 0, c->stream, (const float*)c->b_F.p, n3, stride, peer_ptrs(c, c->p2p.off_g), peer_ptrs(c, c->p2p.off_flag),
+                c->p2p.world, c->p2p.rank, (int32_t*)c->b_p2pdone.p + 8);
+      TM_LAUNCH(k_wait_sum_grad_p2p, nblk(n3), 256, 0, c->stream, mine + c->p2p.off_flag, c->p2p.world, (int32_t*)c->b_flags.p, (const float*)(mine + c->p2p.off_g),
+                n3, stride, grad_dev);
+      c->launches += 1;
+    }
   } else {
     TM_LAUNCH(k_f2d, nblk(3 * s.nreal), 256, 0, c->stream, (const float*)c->b_F.p, grad_dev, 3 * s.nreal);
   }
