@@ -407,6 +407,9 @@ k_pair(const SAtom* __restrict__ sat, const float4* __restrict__ pq, const int32
 // two pieces that contain a kink of the reference's potentials -- the ELU / DSF switch at Elu_Width (RawSymFunc.py:1353)
 // and the end of the vdW polynomial switch (RawSymFunc.py:1391-1393), both continuous in value and slope only -- and
 // anything closer than 0.5 A are evaluated analytically (pair_eval above).
+#ifndef PT_MIN_CTAS
+#define PT_MIN_CTAS 3
+#endif
 #define PT_SHIFT 17
 #define PT_SMIN 0.25f
 #define PT_SMAX 256.0f
@@ -526,7 +529,7 @@ static int pair_tables(tm_ctx* c) {
 // right there under the predicate (two thirds of the candidates are inside the sphere with the fine z bins of the
 // lattice path, so compacting the survivors first would cost more than the idle lanes do).
 template <bool ECC, bool VDW>
-__global__ void __launch_bounds__(PAIR_WARPS * 32)
+__global__ void __launch_bounds__(PAIR_WARPS * 32, PT_MIN_CTAS)
 k_pair_tab(const SAtom* __restrict__ sat, const float4* __restrict__ pq, const uint8_t* __restrict__ pe, const int32_t* __restrict__ cstart,
            const GridParams* __restrict__ gp, const int32_t* __restrict__ rowsidx, const int32_t* __restrict__ rowslot, int64_t nrows,
            int64_t maxnatom, const __grid_constant__ DevParams P, const __grid_constant__ PairTabMeta M, const float4* __restrict__ tab_g,
