@@ -382,6 +382,45 @@ def test_ee_cutoff_boundary_pair_set_has_no_energy_effect(delta):
     assert np.abs(grad_ha_bohr(r["gradient"]) - grad_ha_bohr(o["gradient"])).max() <= 1e-6
 
 
+@pytest.mark.parametrize("case", ["one_water_small_cell", "single_atom", "long_thin_cell"])
+def test_eval_lattice_edge_cells_vs_oracle(case):
+    """Windowed binning at its corners: a cell far smaller than the cutoffs (ntess = 3: every atom has 343 images inside the
+    window), a single atom (no neighbours inside the descriptor cutoffs, images only at Coulomb range), and a long thin
+    triclinic cell (different image counts per axis)."""
+    from oracle import oracle_graph as og
+    from oracle import oracle_np as onp
+    from tensormol_b200.SystemBuilders import wrap_into_cell
+    eng, W, P = _engine([1, 8], [16, 16], 11)
+    if case == "one_water_small_cell":
+        Z = np.array([1, 1, 8], np.int32)
+        X = np.array([[0.76, 0.59, 0.1], [-0.76, 0.59, 0.0], [0.0, 0.0, 0.05]]) + 2.9
+        lat = np.eye(3) * 6.0
+    elif case == "single_atom":
+        Z = np.array([8], np.int32)
+        X = np.array([[1.0, 2.0, 3.0]])
+        lat = np.eye(3) * 9.0
+    else:
+        rs = np.random.RandomState(4)
+        lat = np.array([[5.2, 0.0, 0.0], [1.1, 7.3, 0.0], [0.4, -0.9, 31.0]])
+        nw = 9
+        f = rs.rand(nw, 3)
+        O = f @ lat
+        X = np.concatenate([np.stack([o + [0.76, 0.59, 0.0], o + [-0.76, 0.59, 0.0], o]) for o in O])
+        Z = np.tile(np.array([1, 1, 8], np.int32), nw)
+    X = wrap_into_cell(X, lat)
+    Zt, Xt = onp.tess_lattice(lat, Z.astype(np.uint8), X, P["EECutoffOff"])
+    n = len(Z)
+    ntess = (round((len(Zt) / n) ** (1 / 3)) - 1) // 2
+    r = eng.evaluate_lattice(X, Z, lat, ntess, descriptors=True)
+    o = og.Oracle([1, 8], W, P).evaluate_periodic(Xt, Zt, n)
+    for k in ("Etotal", "Ebp", "Ecc", "Evdw"):
+        _check_energy(r[k], o[k], k)
+    _check_desc(r["descriptors"][0], o["descriptors"][0])
+    _check_grad(r["gradient"][0], o["gradient"][0, :n])
+    r1 = eng.evaluate_images(Xt, Zt.astype(np.int32), n)
+    assert np.abs(r["gradient"] - r1["gradient"]).max() <= 1e-5 * max(np.abs(r1["gradient"]).max(), 1e-6)
+
+
 def test_graph_replay_equals_eager_device_call():
     """engine.GraphedCall: the captured tm_eval_lattice_dev step, replayed after the positions were changed in place,
     gives the numbers of an eager call on the new positions."""
