@@ -662,11 +662,28 @@ static int validate_Z(tm_ctx* c, const int32_t* Z, int64_t n) {
 static int out_mask(int flags, const tm_outputs* out) {
   return (out->Ebp_atom ? 1 : 0) | (out->charge ? 2 : 0) | ((out->gradient && (flags & TM_F_FORCE)) ? 4 : 0);
 }
-// D2H of the energies (always) and the requested blocks, each to its own offset of the pinned staging buffer
-static int copy_packed_d2h(tm_ctx* c, const OutLayout& o, int mask) {
+// page-locked host memory (cudaMallocHost / cudaHostRegister / a torch pinned tensor): the copy engine reads and writes
+// it directly, so a caller who keeps its arrays there skips the staging memcpy on both sides
+static bool host_pinned(const void* p) {
+  if (!p) return false;
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeHost;
+}
+// D2H of the energies (always) and the requested blocks, each to its own offset of the pinned staging buffer, or
+// straight into the caller's array where `direct` names one (page-locked; blocks 0 Ebp_atom, 1 charge, 2 gradient)
+static int copy_packed_d2h(tm_ctx* c, const OutLayout& o, int mask, void* const* direct = nullptr) {
   char* hs = (char*)c->h_stage;
   const char* d = (const char*)c->b_out.p;
   TM_CUDA(cudaMemcpyAsync(hs, d, (size_t)7 * o.nmol * 8, cudaMemcpyDeviceToHost, c->stream));
+  if (direct && (direct[0] || direct[1] || direct[2])) {
+    const int64_t off[3] = {o.off_ebp_atom, o.off_charge, o.off_grad};
+    const int64_t cnt[3] = {o.nq, o.nq, 3 * o.nq};
+    for (int b = 0; b < 3; b++)
+      if (mask & (1 << b))
+        TM_CUDA(cudaMemcpyAsync(direct[b] ? (char*)direct[b] : hs + off[b] * 8, d + off[b] * 8, (size_t)cnt[b] * 8, cudaMemcpyDeviceToHost, c->stream));
+    return TM_OK;
+  }
   if (mask == 7) {   // everything: one copy
     TM_CUDA(cudaMemcpyAsync(hs + o.off_ebp_atom * 8, d + o.off_ebp_atom * 8, (size_t)(o.total - o.off_ebp_atom) * 8, cudaMemcpyDeviceToHost, c->stream));
     return TM_OK;
@@ -677,7 +694,8 @@ static int copy_packed_d2h(tm_ctx* c, const OutLayout& o, int mask) {
   return TM_OK;
 }
 
-static int copy_out(tm_ctx* c, int flags, const OutLayout& o, tm_outputs* out, int64_t charge_tile_to, size_t bytes, size_t dbytes);
+static int copy_out(tm_ctx* c, int flags, const OutLayout& o, tm_outputs* out, int64_t charge_tile_to, size_t bytes, size_t dbytes,
+                    void* const* direct = nullptr);
 
 // copy the packed device outputs to the user's arrays
 static int deliver(tm_ctx* c, const SysView& s, int flags, const OutLayout& o, tm_outputs* out, int64_t charge_tile_to) {
@@ -699,7 +717,8 @@ static int deliver(tm_ctx* c, const SysView& s, int flags, const OutLayout& o, t
 }
 
 // host side of a delivery: the packed outputs are in the pinned staging buffer
-static int copy_out(tm_ctx* c, int flags, const OutLayout& o, tm_outputs* out, int64_t charge_tile_to, size_t bytes, size_t dbytes) {
+static int copy_out(tm_ctx* c, int flags, const OutLayout& o, tm_outputs* out, int64_t charge_tile_to, size_t bytes, size_t dbytes,
+                    void* const* direct) {
   const double* h = (const double*)c->h_stage;
   int64_t nm = o.nmol;
   for (int64_t m = 0; m < nm; m++)
@@ -713,8 +732,8 @@ static int copy_out(tm_ctx* c, int flags, const OutLayout& o, tm_outputs* out, i
   if (out->Ecc) memcpy(out->Ecc, h + 2 * nm, nm * 8);
   if (out->Evdw) memcpy(out->Evdw, h + 3 * nm, nm * 8);
   if (out->dipole) memcpy(out->dipole, h + 4 * nm, 3 * nm * 8);
-  if (out->Ebp_atom) memcpy(out->Ebp_atom, h + o.off_ebp_atom, o.nq * 8);
-  if (out->charge) {
+  if (out->Ebp_atom && !(direct && direct[0])) memcpy(out->Ebp_atom, h + o.off_ebp_atom, o.nq * 8);
+  if (out->charge && !(direct && direct[1])) {
     int64_t done = 0;
     while (done < charge_tile_to) {   // periodic: tile q over the image blocks (TFMolInstanceDirect.py:5892-5893)
       int64_t n = std::min(o.nq, charge_tile_to - done);
@@ -722,7 +741,7 @@ static int copy_out(tm_ctx* c, int flags, const OutLayout& o, tm_outputs* out, i
       done += n;
     }
   }
-  if (out->gradient && (flags & TM_F_FORCE)) memcpy(out->gradient, h + o.off_grad, 3 * o.nq * 8);
+  if (out->gradient && (flags & TM_F_FORCE) && !(direct && direct[2])) memcpy(out->gradient, h + o.off_grad, 3 * o.nq * 8);
   if (dbytes) memcpy(out->descriptors, (const char*)c->h_stage + bytes, dbytes);
   return TM_OK;
 }
@@ -958,12 +977,20 @@ static int lattice_graph_call(tm_ctx* c, const double* xyz, const int32_t* Z, in
                               tm_outputs* out) {
   tm_ctx::LatGraph& G = c->lg;
   const int mask = out_mask(flags, out);
+  // page-locked caller arrays are wired into the graph's copy nodes (no staging memcpy); the graph is then tied to
+  // those addresses, and a call with other arrays re-captures like any other change of shape
+  const void* pin[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  if (host_pinned(xyz) && host_pinned(Z)) { pin[0] = xyz; pin[1] = Z; }
+  if ((mask & 1) && host_pinned(out->Ebp_atom)) pin[2] = out->Ebp_atom;
+  if ((mask & 2) && host_pinned(out->charge)) pin[3] = out->charge;
+  if ((mask & 4) && host_pinned(out->gradient)) pin[4] = out->gradient;
   bool same = G.nreal == nreal && G.ntess == ntess && G.flags == flags && G.outmask == mask && G.cfg_gen == c->cfg_gen &&
-              G.alloc_gen == c->alloc_gen && memcmp(G.lat, lattice, 72) == 0;
+              G.alloc_gen == c->alloc_gen && memcmp(G.lat, lattice, 72) == 0 && memcmp(G.pin, pin, sizeof(pin)) == 0;
   if (!same) {
     if (G.exec) { cudaGraphExecDestroy(G.exec); G.exec = nullptr; }
     G.nreal = nreal; G.ntess = ntess; G.flags = flags; G.outmask = mask; G.cfg_gen = c->cfg_gen; G.alloc_gen = c->alloc_gen;
     memcpy(G.lat, lattice, 72);
+    memcpy(G.pin, pin, sizeof(pin));
     G.streak = 1; G.failed = false;
     return 1;
   }
@@ -974,17 +1001,24 @@ static int lattice_graph_call(tm_ctx* c, const double* xyz, const int32_t* Z, in
   size_t bx = (size_t)nreal * 24, bz = (size_t)nreal * 4, bytes = (size_t)o.total * 8;
   if (c->h_cap < std::max(bx + bz, bytes) + 64 || c->b_acc.cap < bx + bz + 64) return 1;   // the eager calls size these
   char* hs = (char*)c->h_stage;
-  memcpy(hs, xyz, bx);
-  memcpy(hs + bx, Z, bz);
+  if (!pin[0]) {
+    memcpy(hs, xyz, bx);
+    memcpy(hs + bx, Z, bz);
+  }
+  void* const* direct = (void* const*)(pin + 2);
   if (!G.exec) {
     cudaGraph_t graph = nullptr;
     if (cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); G.failed = true; return 1; }
     c->launches = 0;
     SysView s;
-    rc = (cudaMemcpyAsync(c->b_acc.p, hs, bx + bz, cudaMemcpyHostToDevice, c->stream) == cudaSuccess) ? TM_OK : TM_ECUDA;
+    if (pin[0])
+      rc = (cudaMemcpyAsync(c->b_acc.p, xyz, bx, cudaMemcpyHostToDevice, c->stream) == cudaSuccess &&
+            cudaMemcpyAsync((char*)c->b_acc.p + bx, Z, bz, cudaMemcpyHostToDevice, c->stream) == cudaSuccess) ? TM_OK : TM_ECUDA;
+    else
+      rc = (cudaMemcpyAsync(c->b_acc.p, hs, bx + bz, cudaMemcpyHostToDevice, c->stream) == cudaSuccess) ? TM_OK : TM_ECUDA;
     if (!rc) rc = prepare_lattice(c, (const double*)c->b_acc.p, (const int32_t*)((char*)c->b_acc.p + bx), nreal, lattice, ntess, &s);
     if (!rc) rc = run_all(c, s, flags, o);
-    if (!rc) rc = copy_packed_d2h(c, o, mask);
+    if (!rc) rc = copy_packed_d2h(c, o, mask, direct);
     if (!rc && cudaMemcpyAsync(hs + bytes, c->b_flags.p, 8, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) rc = TM_ECUDA;
     cudaError_t ce = cudaStreamEndCapture(c->stream, &graph);
     if (rc || ce != cudaSuccess || !graph || c->alloc_gen != G.alloc_gen) {
@@ -1008,7 +1042,7 @@ static int lattice_graph_call(tm_ctx* c, const double* xyz, const int32_t* Z, in
   if (f0 & 8) return 1;   // unwrapped input: the eager path redoes it with the bounding-box grid
   if (f0 & 2) { tm_set_error("more than %d radial neighbours of one centre", TM_NB_STRIDE); return TM_ECAP; }
   if (f0 & 4) { tm_set_error("more than %d neighbours inside the angular cutoff of one centre", TM_ANG_CAP); return TM_ECAP; }
-  if ((rc = copy_out(c, flags, o, out, nreal, bytes, 0))) return rc;
+  if ((rc = copy_out(c, flags, o, out, nreal, bytes, 0, direct))) return rc;
   tm_timings& t = c->last;
   memset(&t, 0, sizeof(t));
   c->timings_final = true;

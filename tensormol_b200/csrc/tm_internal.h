@@ -200,6 +200,7 @@ struct tm_ctx {
     int64_t nreal = -1;
     int ntess = 0, flags = 0, streak = 0, launches = 0, outmask = 0;
     double lat[9];
+    const void* pin[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // page-locked caller arrays wired into the copy nodes
     uint64_t alloc_gen = 0, cfg_gen = 0;
     bool failed = false;         // capture failed for this key: stay eager
   } lg;

@@ -252,12 +252,18 @@ class Engine:
         check(self.lib.tm_eval(self.ctx, _ptr(xyzs), _ptr(Zs), nmol, maxn, _ptr(natom), self._flags(do_force, has_vdw, descriptors), C.byref(out)), "tm_eval")
         return res
 
-    def _periodic_result(self, nreal, ntot, descriptors, outputs=None):
+    def _periodic_result(self, nreal, ntot, descriptors, outputs=None, into=None):
         """Result arrays + the tm_outputs that points at them.  `outputs` = names to compute AND transfer (None = all):
-        a pointer left NULL is skipped by the library, and its block never crosses the bus."""
+        a pointer left NULL is skipped by the library, and its block never crosses the bus.  `into`: caller-owned float64
+        arrays by name, written in place (page-locked ones — Engine.pinned — receive the device copy directly)."""
         shapes = dict(Etotal=(1,), Ebp=(1,), Ebp_atom=(1, nreal), Ecc=(1,), Evdw=(1,), dipole=(1, 3), charge=(1, ntot), gradient=(1, nreal, 3))
         names = list(shapes) if outputs is None else [k for k in shapes if k in outputs]
-        res = {k: np.zeros(shapes[k]) for k in names}
+        res = {}
+        for k in names:
+            a = into.get(k) if into else None
+            if a is not None and not (a.dtype == np.float64 and a.flags.c_contiguous and a.size == int(np.prod(shapes[k]))):
+                raise ValueError("evaluate: into[%r] must be C-contiguous float64 with %d elements" % (k, int(np.prod(shapes[k]))))
+            res[k] = a if a is not None else np.zeros(shapes[k])
         if descriptors:
             res["descriptors"] = np.zeros((1, nreal, self.D), np.float32)
         out = tm_outputs()
@@ -274,17 +280,47 @@ class Engine:
               "tm_eval_images")
         return res
 
-    def evaluate_lattice(self, xyz, Z, lattice, ntess, do_force=True, has_vdw=True, descriptors=False, fold=False, outputs=None):
+    def pinned(self, shape, dtype=np.float64):
+        """A page-locked numpy array (torch pinned tensor underneath, kept alive by the array).  Coordinates, atomic
+        numbers and result arrays kept in such memory go to and from the device without the staging memcpy."""
+        import torch
+        t = torch.zeros(shape, dtype={np.dtype(np.float64): torch.float64, np.dtype(np.int32): torch.int32,
+                                      np.dtype(np.float32): torch.float32}[np.dtype(dtype)]).pin_memory()
+        return t.numpy()
+
+    def evaluate_lattice(self, xyz, Z, lattice, ntess, do_force=True, has_vdw=True, descriptors=False, fold=False, outputs=None, into=None):
         """Periodic cell + lattice.  outputs: e.g. ("Etotal", "gradient") = what the reference's periodic callback returns
-        (TFMolManage.py:1353-1358); None = every output."""
+        (TFMolManage.py:1353-1358); None = every output.  into: see _periodic_result."""
         xyz = np.ascontiguousarray(xyz, np.float64)
         Z = np.ascontiguousarray(Z, np.int32)
         lat = np.ascontiguousarray(lattice, np.float64).reshape(9)
         n = xyz.shape[0]
-        res, out = self._periodic_result(n, n, descriptors, outputs)   # charges of the real atoms only
+        res, out = self._periodic_result(n, n, descriptors, outputs, into)   # charges of the real atoms only
         check(self.lib.tm_eval_lattice(self.ctx, _ptr(xyz), _ptr(Z), n, _ptr(lat), int(ntess), self._flags(do_force, has_vdw, descriptors, fold), C.byref(out)),
               "tm_eval_lattice")
         return res
+
+    def bind_lattice(self, xyz, Z, lattice, ntess, do_force=True, has_vdw=True, outputs=None, into=None):
+        """evaluate_lattice with everything but the numbers fixed: returns call() -> the same result dict every time,
+        re-reading `xyz` / `Z` (the arrays themselves, which must be C-contiguous float64 / int32 — update them in place)
+        and overwriting the result arrays.  For MD-style loops: no per-call argument conversion, and with page-locked
+        arrays (Engine.pinned) no host-side copy either."""
+        if not (isinstance(xyz, np.ndarray) and xyz.dtype == np.float64 and xyz.flags.c_contiguous and
+                isinstance(Z, np.ndarray) and Z.dtype == np.int32 and Z.flags.c_contiguous):
+            raise ValueError("bind_lattice: xyz must be C-contiguous float64 and Z C-contiguous int32 numpy arrays")
+        lat = np.ascontiguousarray(lattice, np.float64).reshape(9).copy()
+        n = xyz.shape[0]
+        res, out = self._periodic_result(n, n, False, outputs, into)
+        args = (self.ctx, _ptr(xyz), _ptr(Z), n, _ptr(lat), int(ntess), self._flags(do_force, has_vdw, False, False), C.byref(out))
+        fn, keep = self.lib.tm_eval_lattice, (xyz, Z, lat, out)
+
+        def call():
+            rc = fn(*args)
+            if rc:
+                check(rc, "tm_eval_lattice")
+            return res
+        call.keep = keep
+        return call
 
     def evaluate_lattice_dev(self, xyz_ptr, Z_ptr, nreal, lattice, ntess, e_ptr, grad_ptr, charge_ptr=None, do_force=True, has_vdw=True,
                              reuse_nlist=False):

@@ -497,3 +497,45 @@ def test_device_md_with_verlet_skin_follows_the_every_step_rebuild():
     assert np.abs(b.v - va).max() < 1e-6 * max(1.0, np.abs(va).max() / 1e-3)
     assert np.abs(lb[:40, 5] - la[:40, 5]).max() <= 1e-6 * np.abs(la[:40, 5]).max()
     manager.Instances.engine.set_skin(0.0)
+
+
+@pytest.mark.gpu
+def test_page_locked_caller_arrays_and_bound_call_match_the_plain_call():
+    """tm_eval_lattice wires page-locked caller arrays straight into the replayed graph's copy nodes: results equal
+    the staged path, the arrays are re-read every call, and a change of arrays re-captures."""
+    from oracle import oracle_graph as og
+    from tensormol_b200.SystemBuilders import wrap_into_cell
+    from tensormol_b200.engine import Engine, random_weights
+    Z, X, lat = water_box(5, jitter=0.03)
+    X = wrap_into_cell(X, lat)
+    n = len(Z)
+    eng = Engine([1, 8], [64, 64, 64], og.default_params())
+    eng.set_weights(random_weights([1, 8], eng.D, [64, 64, 64], 0))
+    ref = eng.evaluate_lattice(X, Z, lat, 1)
+    Xp, Zp = eng.pinned(X.shape), eng.pinned(Z.shape, np.int32)
+    Xp[:] = X
+    Zp[:] = Z
+    into = {"gradient": eng.pinned((1, n, 3)), "charge": np.zeros((1, n))}   # one page-locked, one ordinary
+    call = eng.bind_lattice(Xp, Zp, lat, 1, into=into)
+    for it in range(5):          # eager calls, capture, replays
+        into["gradient"][:] = 7.0
+        into["charge"][:] = 7.0
+        r = call()
+        assert r["gradient"] is into["gradient"]
+        np.testing.assert_allclose(r["gradient"], ref["gradient"], rtol=0, atol=2e-8)
+        np.testing.assert_allclose(r["charge"], ref["charge"], rtol=0, atol=1e-9)
+        np.testing.assert_allclose(r["Etotal"], ref["Etotal"], rtol=1e-12)
+    X2 = wrap_into_cell(X + 0.05 * np.random.default_rng(1).normal(size=X.shape), lat)
+    Xp[:] = X2                    # same arrays, new numbers: the replay must read them
+    r2 = {k: v.copy() for k, v in call().items()}
+    ref2 = eng.evaluate_lattice(X2, Z, lat, 1)
+    assert abs(ref2["Etotal"][0] - ref["Etotal"][0]) > 1e-6
+    np.testing.assert_allclose(r2["gradient"], ref2["gradient"], rtol=0, atol=2e-8)
+    np.testing.assert_allclose(r2["Etotal"], ref2["Etotal"], rtol=1e-12)
+    other = {"gradient": eng.pinned((1, n, 3))}     # different page-locked array: must not write the old one
+    into["gradient"][:] = -3.0
+    r3 = eng.evaluate_lattice(Xp, Zp, lat, 1, into=other)
+    np.testing.assert_allclose(r3["gradient"], ref2["gradient"], rtol=0, atol=2e-8)
+    assert np.all(into["gradient"] == -3.0)
+    with pytest.raises(ValueError):
+        eng.evaluate_lattice(Xp, Zp, lat, 1, into={"gradient": np.zeros((n, 2))})
