@@ -171,7 +171,12 @@ int tm_eval_images(tm_ctx* ctx, const double* xyz_tess, const int32_t* Z_tess, i
 /* Periodic from the primitive cell: wraps (Lattice.ModuloLattice must already be applied by
  * the caller), tessellates on the device exactly like Lattice.TessLattice (Periodic.py:131-168)
  * with the given ntess, then evaluates like tm_eval_images, except that out->charge is [nreal]
- * (the image blocks would be copies).  lattice [9] row vectors. */
+ * (the image blocks would be copies).  lattice [9] row vectors.
+ * Repeated calls of one shape replay a captured CUDA graph (copies included).  Caller arrays in page-locked host
+ * memory (cudaMallocHost / cudaHostRegister / a pinned torch tensor) — xyz and Z together, and each of Ebp_atom, charge,
+ * gradient on its own — are wired into that graph's copy nodes and never pass through the library's staging buffer;
+ * the graph is then tied to those addresses (other arrays: a few eager calls, then a new capture).  Pageable arrays
+ * work the same way as before, through one staging memcpy each way. */
 int tm_eval_lattice(tm_ctx* ctx, const double* xyz, const int32_t* Z, int64_t nreal, const double* lattice, int ntess,
                     int flags, tm_outputs* out);
 

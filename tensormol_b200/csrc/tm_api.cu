@@ -552,8 +552,7 @@ static bool overlap_backward(const tm_ctx* c, const SysView& s) {
   static int off = -1;
   if (off < 0) off = getenv("TM_NO_OVERLAP") ? 1 : 0;
   if (off || !c->aux) return false;
-  int64_t expect = s.slab_world > 1 ? (s.periodic ? s.nreal : s.nslots) / s.slab_world : s.ncent_max;
-  return expect <= 8192;
+  return tm_expected_centres(s) <= 8192;
 }
 static int fork_backward(tm_ctx* c, const SysView& s) {
   TM_CUDA(cudaEventRecord(c->ev_fork, c->stream));
