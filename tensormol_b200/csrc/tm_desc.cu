@@ -53,7 +53,6 @@ k_desc(const SAtom* __restrict__ sat, const int32_t* __restrict__ rowsidx, const
        const int32_t* __restrict__ nbcnt, const uint32_t* __restrict__ nbr, int64_t nrows, const __grid_constant__ DevParams P,
        float* __restrict__ G, __half* __restrict__ Ghi, __half* __restrict__ Glo, int32_t* __restrict__ flags, int wfloats) {
   TM_PDL_PROLOGUE;
-  constexpr int wsplit = 1, wpart = 0, wshift = 0;   // one warp per centre in the general kernel
   constexpr int NELEP = NE * (NE + 1) / 2;
   extern __shared__ float smem[];
   int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -72,8 +71,7 @@ k_desc(const SAtom* __restrict__ sat, const int32_t* __restrict__ rowsidx, const
   };
   int slot = rowslot[row];
   if (slot < 0) {
-    if (wpart == 0)
-      for (int i = lane; i < P.Dp; i += 32) put(i, 0.f);
+    for (int i = lane; i < P.Dp; i += 32) put(i, 0.f);
     return;
   }
   float* ws = smem + (size_t)warp * wfloats;
@@ -101,7 +99,6 @@ k_desc(const SAtom* __restrict__ sat, const int32_t* __restrict__ rowsidx, const
   const float neg_eta = -P.eta;
   int nang = 0;
   for (int j0 = b; j0 < e; j0 += 32) {
-    const bool mine = (((j0 - b) >> 5) & (wsplit - 1)) == wpart;   // the radial sums of this chunk are this warp's
     int j = j0 + lane;
     float dx = 0.f, dy = 0.f, dz = 0.f, r = 1.f, fc = 0.f;
     int ej = 0;
@@ -175,7 +172,7 @@ k_desc(const SAtom* __restrict__ sat, const int32_t* __restrict__ rowsidx, const
     for (int q = 0; q < NELEP; q++) ga[q][k] = 0.f;
   }
   int ntrip = nang * (nang - 1) / 2;
-  for (int t0 = ((wsplit - 1 - wpart) << 5); t0 < ntrip; t0 += (32 << wshift)) {   // dealt from the other end than the chunks
+  for (int t0 = 0; t0 < ntrip; t0 += 32) {
     int t = t0 + lane;
     if (t < ntrip) {
       int j, k;
@@ -252,19 +249,13 @@ template <int NE>
 __global__ void __launch_bounds__(DESC_WARPS * 32)
 k_desc_fast(const SAtom* __restrict__ sat, const int32_t* __restrict__ rowsidx, const int32_t* __restrict__ rowslot,
             const int32_t* __restrict__ nbcnt, const uint32_t* __restrict__ nbr, int64_t nrows, const __grid_constant__ DevParams P,
-            float* __restrict__ G, __half* __restrict__ Ghi, __half* __restrict__ Glo, int32_t* __restrict__ flags, int wfloats,
-            int wshift) {
+            float* __restrict__ G, __half* __restrict__ Ghi, __half* __restrict__ Glo, int32_t* __restrict__ flags, int wfloats) {
   TM_PDL_PROLOGUE;
   constexpr int NELEP = NE * (NE + 1) / 2;
   constexpr int NA = 8, NR = 8, NSYM = NA * NR;
   extern __shared__ float smem[];
   int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // 2^wshift adjacent warps per centre when centres are few (tm_centre_warp_shift): each gathers the neighbour geometry
-  // for itself and takes every 2^wshift-th radial chunk and angular round; the partial rows meet in shared memory
-  // behind a named barrier of just those warps, and the first warp writes the row.
-  const int wsplit = 1 << wshift;
-  const int wpart = warp & (wsplit - 1);
-  int64_t row = ((int64_t)blockIdx.x * DESC_WARPS + warp) >> wshift;
+  int64_t row = (int64_t)blockIdx.x * DESC_WARPS + warp;
   if (row >= nrows) return;
   float* Grow = G + row * P.Dp;
   auto put = [&](int i, float v) {
@@ -286,8 +277,7 @@ k_desc_fast(const SAtom* __restrict__ sat, const int32_t* __restrict__ rowsidx, 
   };
   int slot = rowslot[row];
   if (slot < 0) {
-    if (wpart == 0)
-      for (int i = lane; i < P.Dp; i += 32) put(i, 0.f);
+    for (int i = lane; i < P.Dp; i += 32) put(i, 0.f);
     return;
   }
   float* ws = smem + (size_t)warp * wfloats;
@@ -313,7 +303,6 @@ k_desc_fast(const SAtom* __restrict__ sat, const int32_t* __restrict__ rowsidx, 
   const float c2 = -P.eta * 1.4426950408889634f;   // exp(-eta x) = 2^(c2 x)
   int nang = 0;
   for (int j0 = b; j0 < e; j0 += 32) {
-    const bool mine = (((j0 - b) >> 5) & (wsplit - 1)) == wpart;   // the radial sums of this chunk are this warp's
     int j = j0 + lane;
     float dx = 0.f, dy = 0.f, dz = 0.f, r = 1.f, fc = 0.f;
     int ej = 0;
@@ -348,7 +337,7 @@ k_desc_fast(const SAtom* __restrict__ sat, const int32_t* __restrict__ rowsidx, 
     }
     nang += __popc(mk);
     __syncwarp();
-    int cnt = mine ? min(32, e - j0) : 0;
+    int cnt = min(32, e - j0);
 #pragma unroll 4
     for (int t = 0; t < cnt; t++) {
       float d = rr[t] - rs0;
@@ -363,12 +352,18 @@ k_desc_fast(const SAtom* __restrict__ sat, const int32_t* __restrict__ rowsidx, 
   }
   nang = min(nang, TM_ANG_CAP);
 
+  if (lane < P.nRs_r) {
+#pragma unroll
+    for (int q = 0; q < NE; q++)
+      if (q < P.n_ele) put(q * P.nRs_r + lane, acc[q]);
+  }
+
   float ga[NELEP][2];
 #pragma unroll
   for (int q = 0; q < NELEP; q++) ga[q][0] = ga[q][1] = 0.f;
   const int la = lane >> 2, ls = 2 * (lane & 3);
   int ntrip = nang * (nang - 1) / 2;
-  for (int t0 = ((wsplit - 1 - wpart) << 5); t0 < ntrip; t0 += (32 << wshift)) {   // dealt from the other end than the chunks
+  for (int t0 = 0; t0 < ntrip; t0 += 32) {
     int t = t0 + lane;
     if (t < ntrip) {
       int j, k;
@@ -419,36 +414,6 @@ k_desc_fast(const SAtom* __restrict__ sat, const int32_t* __restrict__ rowsidx, 
     __syncwarp();
   }
 
-  if (wsplit > 1) {
-    // partial sums of the other warps of this centre: [NE + 2 NELEP][32] at the start of each one's workspace
-    const int bar_id = 1 + (warp >> wshift), bar_n = 32 << wshift;
-    if (wpart != 0) {
-#pragma unroll
-      for (int q = 0; q < NE; q++) ws[q * 32 + lane] = acc[q];
-#pragma unroll
-      for (int q = 0; q < NELEP; q++) {
-        ws[(NE + 2 * q) * 32 + lane] = ga[q][0];
-        ws[(NE + 2 * q + 1) * 32 + lane] = ga[q][1];
-      }
-    }
-    asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(bar_n) : "memory");
-    if (wpart != 0) return;
-    for (int w = 1; w < wsplit; w++) {
-      const float* o = ws + (size_t)w * wfloats;
-#pragma unroll
-      for (int q = 0; q < NE; q++) acc[q] += o[q * 32 + lane];
-#pragma unroll
-      for (int q = 0; q < NELEP; q++) {
-        ga[q][0] += o[(NE + 2 * q) * 32 + lane];
-        ga[q][1] += o[(NE + 2 * q + 1) * 32 + lane];
-      }
-    }
-  }
-  if (lane < P.nRs_r) {
-#pragma unroll
-    for (int q = 0; q < NE; q++)
-      if (q < P.n_ele) put(q * P.nRs_r + lane, acc[q]);
-  }
   // angular block (lane owns outputs 2 lane, 2 lane + 1 of every pair channel), zero padding
   int off = P.n_ele * P.nRs_r;
 #pragma unroll
@@ -468,15 +433,14 @@ static int launch_desc_fast(tm_ctx* c, const SysView& s) {
     TM_CUDA(cudaFuncSetAttribute(k_desc_fast<NE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured[dv] = smem;
   }
-  const int wshift = tm_centre_warp_shift(s);
-  int blocks = (int)(((s.nrows << wshift) + DESC_WARPS - 1) / DESC_WARPS);
+  int blocks = (int)((s.nrows + DESC_WARPS - 1) / DESC_WARPS);
   const bool split = c->gemm_mode != TM_GEMM_FP32;
   TM_LAUNCH(k_desc_fast<NE>, blocks, DESC_WARPS * 32, smem, c->stream, (const SAtom*)c->b_satom.p, (const int32_t*)c->b_rowsidx.p,
                                                                (const int32_t*)c->b_rowslot.p, (const int32_t*)c->b_nbcnt.p,
                                                                (const uint32_t*)c->b_nbr.p, s.nrows, P, (float*)c->b_G.p,
                                                                split ? (__half*)c->b_Gs.p : nullptr,
                                                                split ? (__half*)c->b_Gs.p + (size_t)s.nrows * P.Dp : nullptr,
-                                                               (int32_t*)c->b_flags.p, (int)wf, wshift);
+                                                               (int32_t*)c->b_flags.p, (int)wf);
   c->launches++;
   TM_CUDA(cudaGetLastError());
   return TM_OK;

@@ -255,7 +255,7 @@ k_force(const SAtom* __restrict__ sat, const int32_t* __restrict__ rowsidx, cons
     giy += __shfl_xor_sync(FULL, giy, o);
     giz += __shfl_xor_sync(FULL, giz, o);
   }
-  if (lane == 0 && (gix != 0.f || giy != 0.f || giz != 0.f)) {
+  if (lane == 0) {
     atomicAdd(F + 3 * (int64_t)slot, gix);
     atomicAdd(F + 3 * (int64_t)slot + 1, giy);
     atomicAdd(F + 3 * (int64_t)slot + 2, giz);
@@ -283,19 +283,12 @@ __global__ void __launch_bounds__(FORCE_WARPS * 32, 3)
 k_force_fast(const SAtom* __restrict__ sat, const int32_t* __restrict__ rowsidx, const int32_t* __restrict__ rowslot,
              const int32_t* __restrict__ nbcnt, const uint32_t* __restrict__ nbr, int64_t nrows, const __grid_constant__ DevParams P,
              const float* __restrict__ dGe, const float* __restrict__ dGq, const double* __restrict__ dedq_slot, const double* __restrict__ molacc,
-             const double* __restrict__ inv_n, int64_t maxnatom, int64_t nreal_slots, int fold, float* __restrict__ F, int wfloats,
-             int wshift) {
+             const double* __restrict__ inv_n, int64_t maxnatom, int64_t nreal_slots, int fold, float* __restrict__ F, int wfloats) {
   TM_PDL_PROLOGUE;
   constexpr int NA = 8, NR = 8, NSYM = 64, NRAD = 32;
   extern __shared__ float smem[];
   int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // 2^wshift warps per centre (few centres: a centre's serial chain, not the issue rate, sets the kernel time). The
-  // warps of a centre are independent: each stages A and the neighbour geometry for itself, and takes every
-  // 2^wshift-th radial chunk and angular round; all results leave through the atomics below.
-  const int wsplit = 1 << wshift;
-  const int64_t gw = (int64_t)blockIdx.x * FORCE_WARPS + warp;
-  const int wpart = (int)(gw & (wsplit - 1));
-  int64_t row = gw >> wshift;
+  int64_t row = (int64_t)blockIdx.x * FORCE_WARPS + warp;
   if (row >= nrows) return;
   int slot = rowslot[row];
   if (slot < 0) return;
@@ -345,9 +338,7 @@ k_force_fast(const SAtom* __restrict__ sat, const int32_t* __restrict__ rowsidx,
   const float nel2 = -P.eta * 1.4426950408889634f;   // exp(-eta x) = 2^(nel2 x)
   float gix = 0.f, giy = 0.f, giz = 0.f;   // dE/dx_i accumulated by this lane
   int nang = 0;
-  int chunk = 0;
-  for (int j0 = b; j0 < e; chunk++) {
-    const bool mine = (chunk & (wsplit - 1)) == wpart;   // the radial sums of this chunk are this warp's
+  for (int j0 = b; j0 < e;) {
     // lanes per neighbour in this chunk: 1 for a full chunk, else as many as fit (interleaved Gaussians)
     const int remaining = e - j0;
     int lsub = 0;
@@ -383,8 +374,7 @@ k_force_fast(const SAtom* __restrict__ sat, const int32_t* __restrict__ rowsidx,
     const float* Arow = Ar + ej * FF_RSTR;
     const float m2ef = -2.0f * P.eta * fc;
     float dEdr = 0.f;
-    if (!mine) {
-    } else if (sub == 1) {
+    if (sub == 1) {
 #pragma unroll 8
       for (int s = 0; s < NRAD; s++) {
         float d = r - P.Rs_r[s];
@@ -399,7 +389,7 @@ k_force_fast(const SAtom* __restrict__ sat, const int32_t* __restrict__ rowsidx,
       }
       for (int o = 1; o < sub; o <<= 1) dEdr += __shfl_xor_sync(FULL, dEdr, o);
     }
-    if (mine && valid && part == 0) {
+    if (valid && part == 0) {
       float sc = dEdr * f_rcp(r);
       float gx = sc * dx, gy = sc * dy, gz = sc * dz;   // dE/dx_j  (d = x_j - x_i)
       gix -= gx; giy -= gy; giz -= gz;
@@ -431,9 +421,7 @@ k_force_fast(const SAtom* __restrict__ sat, const int32_t* __restrict__ rowsidx,
   // forces on the angular neighbours n = lane and n = lane + 32, accumulated over the rounds
   float f0x = 0.f, f0y = 0.f, f0z = 0.f, f1x = 0.f, f1y = 0.f, f1z = 0.f;
   int ntrip = nang * (nang - 1) / 2;
-  // rounds are dealt from the other end than the radial chunks (water: the full radial chunk and the short last round
-  // go to one warp, the short radial chunk and the full round to the other)
-  for (int t0 = ((wsplit - 1 - wpart) << 5); t0 < ntrip; t0 += (32 << wshift)) {
+  for (int t0 = 0; t0 < ntrip; t0 += 32) {
     int t = t0 + lane;
     const int cnt = min(32, ntrip - t0);
     int j = 0, k = 1;
@@ -554,7 +542,7 @@ k_force_fast(const SAtom* __restrict__ sat, const int32_t* __restrict__ rowsidx,
     giy += __shfl_xor_sync(FULL, giy, o);
     giz += __shfl_xor_sync(FULL, giz, o);
   }
-  if (lane == 0 && (gix != 0.f || giy != 0.f || giz != 0.f)) {
+  if (lane == 0) {
     atomicAdd(F + 3 * (int64_t)slot, gix);
     atomicAdd(F + 3 * (int64_t)slot + 1, giy);
     atomicAdd(F + 3 * (int64_t)slot + 2, giz);
@@ -579,14 +567,11 @@ int tm_launch_force(tm_ctx* c, const SysView& s, int flags) {
       TM_CUDA(cudaFuncSetAttribute(k_force_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smf));
       conf_fast = smf;
     }
-    // few centres (a slab rank, a small cell): 2 or 4 warps per centre so that the SMs still hold enough independent chains
-    const int wshift = tm_centre_warp_shift(s);
-    blocks = (int)(((s.nrows << wshift) + FORCE_WARPS - 1) / FORCE_WARPS);
     TM_LAUNCH(k_force_fast, blocks, FORCE_WARPS * 32, smf, c->stream, 
         (const SAtom*)c->b_satom.p, (const int32_t*)c->b_rowsidx.p, (const int32_t*)c->b_rowslot.p, (const int32_t*)c->b_nbcnt.p,
         (const uint32_t*)c->b_nbr.p, s.nrows, P, (const float*)c->b_dG[TM_NET_ENERGY].p, (const float*)c->b_dG[TM_NET_CHARGE].p,
         (const double*)c->b_dedq.p, (const double*)c->b_molacc.p, (const double*)c->b_natom.p, s.maxnatom, nreal_slots, fold, (float*)c->b_F.p,
-        (int)wff, wshift);
+        (int)wff);
     c->launches++;
     TM_CUDA(cudaGetLastError());
     return TM_OK;

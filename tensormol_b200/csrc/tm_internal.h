@@ -263,15 +263,6 @@ int tm_launch_rows(tm_ctx* c, const SysView& s);
 static inline int64_t tm_expected_centres(const SysView& s) {
   return s.slab_world > 1 ? (s.periodic ? s.nreal : s.nslots) / s.slab_world : s.ncent_max;
 }
-// warps per centre (log2) of the descriptor and force kernels.  Measured on B200 at 3,000 centres (a rank of 8, config
-// C3): 1 warp 22.6 + 22.9 us, 2 warps 23.0 + 27.0, 4 warps 26.6 + 35.2 — the per-warp set-up (A staging, neighbour
-// geometry) that every extra warp repeats costs more than the shorter chains save, so one warp per centre stays the
-// default at every size; TM_CENTRE_WARPS=2|4 selects the split (tests, measurements).
-static inline int tm_centre_warp_shift(const SysView& s) {
-  static const int wenv = getenv("TM_CENTRE_WARPS") ? atoi(getenv("TM_CENTRE_WARPS")) : 0;
-  (void)s;
-  return wenv == 2 ? 1 : wenv == 4 ? 2 : 0;
-}
 int tm_launch_lattice_bin(tm_ctx* c, const SysView& s);
 int tm_launch_lattice_refresh(tm_ctx* c, const SysView& s);   // Verlet-skin reuse: new positions into the existing cell-sorted records   // windowed binning + cell sort + centre rows of the lattice path
 int tm_launch_neighbours(tm_ctx* c, const SysView& s);
