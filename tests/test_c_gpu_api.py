@@ -539,3 +539,73 @@ def test_page_locked_caller_arrays_and_bound_call_match_the_plain_call():
     assert np.all(into["gradient"] == -3.0)
     with pytest.raises(ValueError):
         eng.evaluate_lattice(Xp, Zp, lat, 1, into={"gradient": np.zeros((n, 2))})
+
+
+@pytest.mark.gpu
+def test_c3_nve_1000_steps_with_skin_sets_at_rebuild_steps_and_conservation():
+    """Config C3 (3,000-atom water box), 1,000 NVE steps on the device driver with a 0.5 A Verlet skin and a rebuild every
+    5 steps, run as four legs of 250 steps.  Every leg ends on a rebuild step: there the neighbour SETS of the current
+    wrapped positions (tm_nlist through the MolEmb drop-in, images included) are bit-exact against the reference's own
+    compiled Make_NListNaive (C_API/MolEmb.cpp:1180-1247, oracle/_ref), the evaluation that reuses the skin rows equals
+    one that rebuilds them, and the total energy is conserved over the whole run."""
+    import glob, importlib.util, os
+    import MolEmb
+    from conftest import ROOT
+    from oracle import oracle_np as onp
+    from tensormol_b200 import PARAMS, Mol
+    from tensormol_b200.PhysicalData import JOULEPERHARTREE
+    from tensormol_b200.Simulations.DeviceMD import DevicePeriodicVelocityVerlet
+    from tensormol_b200.SystemBuilders import water_box as big_water_box, wrap_into_cell
+    so = glob.glob(os.path.join(ROOT, "oracle", "_ref", "MolEmb*.so"))
+    if not so:
+        pytest.skip("oracle/_ref/MolEmb not built (make -C oracle ref)")
+    spec = importlib.util.spec_from_file_location("MolEmb", so[0])   # (not registered in sys.modules: `MolEmb` stays the drop-in)
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    Z, X, lat = big_water_box(10, spacing=3.1072, seed=3, jitter=0.02)
+    n = len(Z)
+    m = Mol(Z.astype(np.uint8), wrap_into_cell(X, lat))
+    manager, _ = _manager([m], [64, 64, 64], 0)
+    eng = manager.Instances.engine
+    PARAMS["MDMaxStep"] = 250; PARAMS["MDdt"] = 0.2; PARAMS["MDV0"] = None; PARAMS["MDThermostat"] = None; PARAMS["MDTemp"] = 300.0
+    PARAMS["MDLogTrajectory"] = False
+    v = 1e-3 * np.random.RandomState(1).randn(n, 3)
+    etot, ekin = [], []
+    for leg in range(4):
+        md = DevicePeriodicVelocityVerlet(manager, m, lat, "c3_leg%d" % leg, v0_=v.copy(), sync_every_=250, skin_=0.5, nl_every_=5)
+        log = md.Prop()
+        etot.append(log[:250, 4] * n + log[:250, 5] * JOULEPERHARTREE)   # J/mol: kinetic per atom * n + potential
+        ekin.append(log[:250, 4] * n)
+        x = wrap_into_cell(md.x, lat)
+        v = md.v.copy()
+        m = Mol(Z.astype(np.uint8), x)
+        # neighbour sets of the wrapped positions with their images, radial and angular cutoffs
+        Zt, Xt = onp.tess_lattice(lat, Z.astype(np.uint8), x, PARAMS["EECutoffOff"])
+        Xt = np.ascontiguousarray(Xt)
+        for rc in (PARAMS["AN1_r_Rc"], PARAMS["AN1_a_Rc"]):
+            want = ref.Make_NListNaive(Xt, float(rc), n, 1)
+            got = MolEmb.Make_NListNaive(Xt, float(rc), n, 1)
+            assert [sorted(r) for r in got] == [sorted(r) for r in want], "leg %d rc %g" % (leg, rc)
+        # skin rows reused vs rebuilt, same positions (one more build with the skin on, then a reuse call through the driver's engine)
+        eng.set_skin(0.5)
+        want_out = ("Etotal", "Ebp", "Ecc", "Evdw", "gradient")
+        a = eng.evaluate_lattice(x, Z, lat, md.ntess, outputs=want_out)
+        eng.set_skin(0.0)
+        b = eng.evaluate_lattice(x, Z, lat, md.ntess, outputs=want_out)
+        scale = abs(b["Ebp"][0]) + abs(b["Ecc"][0]) + abs(b["Evdw"][0])      # the parts cancel in Etotal
+        assert abs(a["Etotal"][0] - b["Etotal"][0]) <= 1e-7 * scale           # same sets, other summation order (fp32)
+        assert np.abs(a["gradient"] - b["gradient"]).max() < 2e-7
+    # the first leg again with a rebuild on every step: the skin run follows it energy for energy (same forces up to the
+    # fp32 summation order; 50 fs is far below the time over which two such trajectories part)
+    PARAMS["MDMaxStep"] = 250
+    md0 = DevicePeriodicVelocityVerlet(manager, Mol(Z.astype(np.uint8), wrap_into_cell(X, lat)), lat, "c3_every",
+                                       v0_=1e-3 * np.random.RandomState(1).randn(n, 3), sync_every_=250)
+    log0 = md0.Prop()
+    etot0 = log0[:250, 4] * n + log0[:250, 5] * JOULEPERHARTREE
+    assert np.abs(etot[0] - etot0).max() < 1e-4 * np.ptp(ekin[0]), (np.abs(etot[0] - etot0).max(), np.ptp(ekin[0]))
+    etot, ekin = np.concatenate(etot), np.concatenate(ekin)
+    # kinetic and potential energy trade an amount ptp(ekin) (the random-weight potential is far from its minimum and, with
+    # softplus(100 x) neurons, nearly piecewise linear: the box heats from 6 K to ~900 K); what velocity Verlet at 0.2 fs
+    # loses or gains on that surface stays a small part of it
+    assert np.ptp(etot[5:]) < 0.10 * np.ptp(ekin), (np.ptp(etot[5:]), np.ptp(ekin))
+    eng.set_skin(0.0)
