@@ -162,6 +162,15 @@ int tm_pairs_triples_ele(tm_ctx* ctx, const double* xyzs, const int32_t* Zs, int
 int tm_eval(tm_ctx* ctx, const double* xyzs, const int32_t* Zs, int64_t nmol, int64_t maxnatom,
             const int64_t* natom, int flags, tm_outputs* out);
 
+/* Device-resident variant of tm_eval (the molecule-set form of tm_eval_lattice_dev; on-device MD / optimisation of
+ * isolated molecules, SimpleMD.py:322-425): xyz_dev [nmol*maxnatom*3] f64 and Z_dev [nmol*maxnatom] i32 are DEVICE
+ * pointers, Z zero in the padding slots (atoms of a molecule first); the outputs (any may be NULL) are device pointers:
+ * e_dev [4*nmol] = Etotal | Ebp | Ecc | Evdw blocks (f64), grad_dev [nmol*maxnatom*3], charge_dev [nmol*maxnatom].
+ * No host copy or synchronisation (capturable in a CUDA graph); atomic numbers are not validated (an element outside
+ * the model's list is the caller's error); capacity flags surface from tm_sync. */
+int tm_eval_dev(tm_ctx* ctx, const double* xyz_dev, const int32_t* Z_dev, int64_t nmol, int64_t maxnatom, int flags,
+                double* e_dev, double* grad_dev, double* charge_dev);
+
 /* Periodic, images supplied by the caller (the PeriodicForce callback form,
  * EvalBPDirectEEUpdateSinglePeriodic, TFMolManage.py:1323-1358): real atoms first, then
  * images with  slot = b*nreal + a  <->  real atom a  (Periodic.py:158-165). Host buffers. */

@@ -30,8 +30,14 @@ class DevicePeriodicVelocityVerlet:
         are built every nl_every_ steps out to cutoff + skin_ and reused in between (tm_set_skin / TM_F_REUSE_NLIST); the
         coordinates are wrapped into the cell only on the building steps.  The library checks on the device that no atom
         moved more than skin_ / 2 between builds and raises at the next synchronisation if one did."""
-        import torch
         from ..ForceModifiers.Periodic import Lattice
+        self.lattice = Lattice(np.asarray(lattice_, np.float64))
+        self.ntess = self.lattice.NTess(rng_)
+        self.mol0 = self.lattice.CenteredInLattice(mol_)          # like PeriodicForce.__init__ (Periodic.py:288)
+        self._setup(manager_, mol_, self.mol0.coords, name_, v0_, device_, graph_, sync_every_, skin_, nl_every_)
+
+    def _setup(self, manager_, mol_, coords0, name_, v0_, device_, graph_, sync_every_, skin_=0.0, nl_every_=1):
+        import torch
         from ..engine import GraphedCall
         self.torch = torch
         self.name = name_
@@ -40,8 +46,6 @@ class DevicePeriodicVelocityVerlet:
         self.dt = float(PARAMS["MDdt"])           # noqa: F405
         manager_.Instances.refresh()
         self.engine = manager_.Instances.engine
-        self.lattice = Lattice(np.asarray(lattice_, np.float64))
-        self.ntess = self.lattice.NTess(rng_)
         self.atoms = mol_.atoms.copy()
         self.natoms = len(self.atoms)
         self.m = np.array([ATOMICMASSES[z - 1] for z in self.atoms])   # noqa: F405
@@ -50,11 +54,11 @@ class DevicePeriodicVelocityVerlet:
         f64 = dict(dtype=torch.float64, device=dev)
         self.stream = torch.cuda.Stream(device=dev)
         self.engine.set_stream(C.c_void_p(self.stream.cuda_stream))
-        L = self.lattice.lattice
-        self._L = torch.tensor(L, **f64)
-        self._toLat = torch.tensor(np.dot(L.T, np.linalg.inv(np.dot(L, L.T))), **f64)   # Lattice.InLat
-        self.mol0 = self.lattice.CenteredInLattice(mol_)          # like PeriodicForce.__init__ (Periodic.py:288)
-        self._x = torch.tensor(self.mol0.coords, **f64)
+        if getattr(self, "lattice", None) is not None:
+            L = self.lattice.lattice
+            self._L = torch.tensor(L, **f64)
+            self._toLat = torch.tensor(np.dot(L.T, np.linalg.inv(np.dot(L, L.T))), **f64)   # Lattice.InLat
+        self._x = torch.tensor(coords0, **f64)
         v0 = np.zeros((self.natoms, 3)) if v0_ is None else np.asarray(v0_, np.float64)
         if v0_ is None and PARAMS["MDV0"] == "Random":   # noqa: F405
             from .SimpleMD import Thermostat
@@ -108,7 +112,7 @@ class DevicePeriodicVelocityVerlet:
             self._replay_reuse = GraphedCall(reuse, self.stream, warmup=1) if graph_ else reuse
         if graph_:   # the capture and its warm-up advanced the state: rewind
             with torch.cuda.stream(self.stream):
-                self._x.copy_(torch.tensor(self.mol0.coords, **f64))
+                self._x.copy_(torch.tensor(coords0, **f64))
                 self._v.copy_(torch.tensor(vv if self.nose else v0, **f64))
                 if self.nose:
                     self._eta.zero_()
@@ -195,7 +199,8 @@ class DevicePeriodicVelocityVerlet:
 
     def WriteTrajectory(self):
         m = Mol(self.atoms, self.x)
-        m.properties["Lattice"] = self.lattice.lattice.copy()
+        if getattr(self, "lattice", None) is not None:
+            m.properties["Lattice"] = self.lattice.lattice.copy()
         m.properties["Time"] = self.t
         m.properties["KineticEnergy"] = self.KE
         m.properties["PotEnergy"] = self.EPot
@@ -225,3 +230,24 @@ class DevicePeriodicVelocityVerlet:
         self._pull_log(n)
         self.t = n * self.dt
         return self.md_log
+
+
+class DeviceVelocityVerlet(DevicePeriodicVelocityVerlet):
+    """Isolated molecule: VelocityVerlet / NoseThermostat of the reference (Simulations/SimpleMD.py:14-38, 90-129, 322-425)
+    with the state on the GPU; the force call is tm_eval_dev (device pointers in and out), one CUDA graph per MD step.
+    Same PARAMS, attributes and md_log columns as the periodic device driver (column 4 is the kinetic energy of the step
+    it is logged with; the reference's host loop logs the previous step's there, SimpleMD.py:406-411)."""
+
+    def __init__(self, manager_, mol_, name_="DevMD", v0_=None, device_=0, graph_=True, sync_every_=100):
+        self.lattice = None
+        self._setup(manager_, mol_, np.asarray(mol_.coords, np.float64).copy(), name_, v0_, device_, graph_, sync_every_)
+
+    def _force(self, reuse=False):
+        self.engine.evaluate_dev(C.c_void_p(self._x.data_ptr()), C.c_void_p(self._Z.data_ptr()), 1, self.natoms,
+                                 C.c_void_p(self._e.data_ptr()), C.c_void_p(self._g.data_ptr()))
+
+    def _wrap(self):
+        pass
+
+    def Density(self):
+        raise AttributeError("an isolated molecule has no cell")

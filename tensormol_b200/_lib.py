@@ -46,7 +46,7 @@ class tm_timings(C.Structure):
 # every symbol declared in include/tmolb200.h (tests/test_abi.py checks the library exports them all)
 SYMBOLS = ["tm_version", "tm_last_error", "tm_device_count", "tm_create", "tm_destroy", "tm_set_params", "tm_set_weights",
            "tm_set_gemm_mode", "tm_get_gemm_mode", "tm_set_skin", "tm_set_stream", "tm_descriptor_width", "tm_nlist", "tm_pairs_triples_ele",
-           "tm_eval", "tm_eval_images", "tm_eval_lattice", "tm_eval_lattice_dev", "tm_slab_phase_a", "tm_slab_phase_b",
+           "tm_eval", "tm_eval_dev", "tm_eval_images", "tm_eval_lattice", "tm_eval_lattice_dev", "tm_slab_phase_a", "tm_slab_phase_b",
            "tm_slab_phase_c", "tm_slab_p2p_bytes", "tm_slab_p2p_setup", "tm_get_timings", "tm_sync"]
 
 _lib = None
@@ -87,6 +87,7 @@ def load():
     lib.tm_eval_images.argtypes = [vp, vp, vp, i64, i64, i32, P(tm_outputs)]
     lib.tm_eval_lattice.argtypes = [vp, vp, vp, i64, vp, i32, i32, P(tm_outputs)]
     lib.tm_eval_lattice_dev.argtypes = [vp, vp, vp, i64, vp, i32, i32, vp, vp, vp]
+    lib.tm_eval_dev.argtypes = [vp, vp, vp, i64, i64, i32, vp, vp, vp]
     lib.tm_slab_phase_a.argtypes = [vp, vp, vp, i64, vp, i32, i32, i32, vp]
     lib.tm_slab_phase_b.argtypes = [vp, vp, vp]
     lib.tm_slab_phase_c.argtypes = [vp, vp, i32, vp]

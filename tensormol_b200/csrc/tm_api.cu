@@ -803,6 +803,49 @@ extern "C" int tm_eval(tm_ctx* c, const double* xyzs, const int32_t* Zs, int64_t
   return rc;
 }
 
+// 1 / natom per molecule from the zero-padded atomic numbers (device form of upload_inv_n)
+__global__ void k_inv_n_from_Z(const int32_t* __restrict__ Z, int64_t nmol, int64_t maxnatom, double* __restrict__ inv_n) {
+  TM_PDL_PROLOGUE;
+  int64_t m = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (m >= nmol) return;
+  int cnt = 0;
+  for (int64_t a = lane; a < maxnatom; a += 32) cnt += Z[m * maxnatom + a] > 0 ? 1 : 0;
+  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  if (lane == 0) inv_n[m] = cnt > 0 ? 1.0 / (double)cnt : 0.0;
+}
+
+// Device-resident form of tm_eval (see include/tmolb200.h): no host copy, no synchronisation, capturable.
+extern "C" int tm_eval_dev(tm_ctx* c, const double* xyz_dev, const int32_t* Z_dev, int64_t nmol, int64_t maxnatom, int flags,
+                           double* e_dev, double* grad_dev, double* charge_dev) {
+  if (c) c->nl_ok = false;
+  if (!c || !xyz_dev || !Z_dev || nmol < 1 || maxnatom < 1) { tm_set_error("tm_eval_dev: bad argument"); return TM_EINVAL; }
+  int rc;
+  TM_CUDA(cudaSetDevice(c->device));
+  if ((rc = check_weights(c))) return rc;
+  const int64_t nslots = nmol * maxnatom;
+  c->launches = 0;
+  c->timings_final = false;
+  cudaEventRecord(c->ev[0], c->stream);
+  if ((rc = tm_buf(c, c->b_pos, (size_t)nslots * 24))) return rc;
+  if ((rc = tm_buf(c, c->b_Z, (size_t)nslots * 4))) return rc;
+  if ((rc = tm_buf(c, c->b_natom, (size_t)nmol * 8))) return rc;
+  TM_CUDA(cudaMemcpyAsync(c->b_pos.p, xyz_dev, (size_t)nslots * 24, cudaMemcpyDeviceToDevice, c->stream));
+  TM_CUDA(cudaMemcpyAsync(c->b_Z.p, Z_dev, (size_t)nslots * 4, cudaMemcpyDeviceToDevice, c->stream));
+  TM_LAUNCH(k_inv_n_from_Z, (unsigned)((nmol * 32 + 255) / 256), 256, 0, c->stream, (const int32_t*)c->b_Z.p, nmol, maxnatom, (double*)c->b_natom.p);
+  c->launches++;
+  SysView s = make_view(c, nslots, nmol, maxnatom, 0, 0, nslots);   // every slot may be a centre
+  OutLayout o = out_layout(nmol, nslots);
+  if ((rc = run_all(c, s, flags, o))) return rc;
+  const double* out = (const double*)c->b_out.p;
+  if (e_dev) TM_CUDA(cudaMemcpyAsync(e_dev, out, (size_t)4 * nmol * 8, cudaMemcpyDeviceToDevice, c->stream));
+  if (grad_dev && (flags & TM_F_FORCE)) TM_CUDA(cudaMemcpyAsync(grad_dev, out + o.off_grad, (size_t)3 * nslots * 8, cudaMemcpyDeviceToDevice, c->stream));
+  if (charge_dev) TM_CUDA(cudaMemcpyAsync(charge_dev, out + o.off_charge, (size_t)nslots * 8, cudaMemcpyDeviceToDevice, c->stream));
+  cudaEventRecord(c->ev[8], c->stream);
+  c->cur_nslots = nslots;
+  return TM_OK;
+}
+
 extern "C" int tm_eval_images(tm_ctx* c, const double* xyz_tess, const int32_t* Z_tess, int64_t ntess_atoms, int64_t nreal, int flags,
                               tm_outputs* out) {
   if (c) c->nl_ok = false;

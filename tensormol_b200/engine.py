@@ -331,6 +331,12 @@ class Engine:
         check(self.lib.tm_eval_lattice_dev(self.ctx, xyz_ptr, Z_ptr, int(nreal), _ptr(lat), int(ntess), flags,
                                            e_ptr, grad_ptr, charge_ptr), "tm_eval_lattice_dev")
 
+    def evaluate_dev(self, xyz_ptr, Z_ptr, nmol, maxnatom, e_ptr, grad_ptr, charge_ptr=None, do_force=True, has_vdw=True):
+        """Molecule set, device pointers in and out, no host synchronisation (tm_eval_dev): xyz [nmol*maxnatom*3] f64,
+        Z [nmol*maxnatom] i32 (zero = padding), e [4*nmol] = Etotal | Ebp | Ecc | Evdw, grad [nmol*maxnatom*3], charge."""
+        check(self.lib.tm_eval_dev(self.ctx, xyz_ptr, Z_ptr, int(nmol), int(maxnatom), self._flags(do_force, has_vdw, False),
+                                   e_ptr, grad_ptr, charge_ptr), "tm_eval_dev")
+
     def set_skin(self, skin):
         """Verlet skin in Angstrom (0 = rebuild every call, the reference's behaviour): see tm_set_skin in include/tmolb200.h."""
         check(self.lib.tm_set_skin(self.ctx, float(skin)), "tm_set_skin")

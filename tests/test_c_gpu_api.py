@@ -609,3 +609,57 @@ def test_c3_nve_1000_steps_with_skin_sets_at_rebuild_steps_and_conservation():
     # loses or gains on that surface stays a small part of it
     assert np.ptp(etot[5:]) < 0.10 * np.ptp(ekin), (np.ptp(etot[5:]), np.ptp(ekin))
     eng.set_skin(0.0)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("thermostat", [None, "Nose"])
+def test_device_md_of_an_isolated_molecule_matches_the_host_driver(thermostat):
+    """SURVEY 8f N1 remainder: DeviceVelocityVerlet (state on the GPU, tm_eval_dev, one CUDA graph per step) follows the
+    host VelocityVerlet / NoseThermostat (numpy arrays, SimpleMD.py:14-129, 322-425) driven by the same device forces."""
+    from tensormol_b200 import PARAMS, Mol, VelocityVerlet
+    from tensormol_b200.Simulations.DeviceMD import DeviceVelocityVerlet
+    g = load_golden("h2o_cluster")
+    m = Mol(g["Z"].astype(np.uint8), g["xyz"])
+    manager, W = _manager([m], [64, 64], 3)
+    nstep = 15
+    PARAMS["MDMaxStep"] = nstep; PARAMS["MDdt"] = 0.2; PARAMS["MDV0"] = None; PARAMS["MDTemp"] = 300.0
+    PARAMS["MDThermostat"] = thermostat
+    PARAMS["MDLogTrajectory"] = False
+
+    def EnAndForce(x_, DoForce=True):
+        out = manager.EvalBPDirectEEUpdateSingle(Mol(m.atoms, x_), PARAMS["AN1_r_Rc"], PARAMS["AN1_a_Rc"], PARAMS["EECutoffOff"], True)
+        return (out[0][0], out[-1][0]) if DoForce else out[0][0]
+    v0 = 1e-3 * np.random.RandomState(8).randn(len(g["Z"]), 3)
+    host = VelocityVerlet(None, m, "host_mol_md", EnAndForce)
+    host.v = v0.copy()
+    if thermostat == "Nose":
+        from tensormol_b200.Simulations.SimpleMD import NoseThermostat
+        host.Tstat = NoseThermostat(host.m, host.v)     # rescales host.v to MDTemp, like the device driver's constructor
+    host.Prop()
+    dev = DeviceVelocityVerlet(manager, m, "dev_mol_md", v0_=v0.copy(), sync_every_=5)
+    log = dev.Prop()
+    assert np.abs(dev.x - host.x).max() < 1e-7
+    assert np.abs(dev.v - host.v).max() < 1e-7 * max(1.0, np.abs(host.v).max() / 1e-3)
+    assert abs(dev.EPot - host.EPot) < 1e-6 * abs(host.EPot)
+    assert np.all(np.isfinite(log)) and abs(log[nstep - 1, 5] - dev.EPot) <= 1e-9 * abs(dev.EPot)
+    # the library call itself: device pointers in and out, a padded two-molecule set against the host-buffer call
+    import ctypes as C
+    import torch
+    eng = manager.Instances.engine
+    n = len(g["Z"])
+    xyz = np.zeros((2, n + 3, 3)); Z = np.zeros((2, n + 3), np.int32)
+    xyz[0, :n] = g["xyz"]; Z[0, :n] = g["Z"]
+    xyz[1, :n - 3] = g["xyz"][:n - 3] + 0.01; Z[1, :n - 3] = g["Z"][:n - 3]
+    want = eng.evaluate(xyz, Z, np.array([n, n - 3]))
+    dv = torch.device("cuda", 0)
+    xt, zt = torch.tensor(xyz, device=dv), torch.tensor(Z, device=dv)
+    e = torch.zeros(8, dtype=torch.float64, device=dv); gr = torch.zeros(2, n + 3, 3, dtype=torch.float64, device=dv)
+    q = torch.zeros(2, n + 3, dtype=torch.float64, device=dv)
+    eng.evaluate_dev(C.c_void_p(xt.data_ptr()), C.c_void_p(zt.data_ptr()), 2, n + 3, C.c_void_p(e.data_ptr()), C.c_void_p(gr.data_ptr()),
+                     C.c_void_p(q.data_ptr()))
+    eng.sync()
+    e = e.cpu().numpy().reshape(4, 2)
+    np.testing.assert_allclose(e[0], want["Etotal"], rtol=1e-9)
+    np.testing.assert_allclose(e[2], want["Ecc"], rtol=1e-7)
+    np.testing.assert_allclose(gr.cpu().numpy(), want["gradient"], rtol=0, atol=2e-7)
+    np.testing.assert_allclose(q.cpu().numpy(), want["charge"], rtol=0, atol=1e-8)
