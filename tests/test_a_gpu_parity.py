@@ -590,3 +590,40 @@ def test_edge_cases_empty_single_atom_and_capacity():
     # the context stays usable afterwards
     r2 = eng.evaluate(xyzs, Zs, nat)
     assert np.allclose(r2["Etotal"], r["Etotal"], rtol=1e-9, atol=0)
+
+
+GRIDS = [dict(AN1_num_r_Rs=16, AN1_num_a_Rs=4, AN1_num_a_As=4, AN1_eta=3.5, AN1_zeta=6.0),      # small grid, zeta != 8
+         dict(AN1_num_r_Rs=24, AN1_num_a_Rs=6, AN1_num_a_As=10, AN1_eta=4.5, AN1_zeta=8.0),     # neither 8 x 8 nor 32
+         dict(AN1_r_Rc=5.2, AN1_a_Rc=3.5, AN1_num_r_Rs=32, AN1_num_a_Rs=8, AN1_num_a_As=8)]     # default counts, other cutoffs (fast kernels)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("grid", GRIDS, ids=["r16_a4x4_zeta6", "r24_a6x10", "cutoffs_5.2_3.5"])
+def test_other_symmetry_function_grids_vs_oracle(grid):
+    """SURVEY a17 (SetANI1Param, TFMolInstanceDirect.py:1262-1267, 1293-1328): grids other than the released 32 / 8 x 8 take the
+    general descriptor and force kernels (k_desc / k_force); descriptors, energies, charges and gradient against the
+    oracle built with the same PARAMS, for a molecule and for a small periodic box."""
+    from oracle import oracle_graph as og
+    from oracle import oracle_np as onp
+    from tensormol_b200.SystemBuilders import wrap_into_cell
+    g = load_golden("h2o_cluster")
+    hidden = [48, 32]
+    eng, W, P = _engine(g["eles"], hidden, 11, params=grid)
+    N = len(g["Z"])
+    r = eng.evaluate(g["xyz"][None], g["Z"][None], np.array([N]), descriptors=True)
+    o = og.Oracle(g["eles"], W, P).evaluate(g["xyz"][None], g["Z"][None], np.array([N]))
+    assert r["descriptors"].shape[-1] == o["descriptors"].shape[-1] == eng.D
+    _check_desc(r["descriptors"], o["descriptors"])
+    for k in ("Etotal", "Ebp", "Ecc", "Evdw"):
+        _check_energy(r[k], o[k], k)
+    assert np.abs(r["charge"] - o["charge"]).max() <= 1e-5 * max(np.abs(o["charge"]).max(), 1e-3)
+    _check_grad(r["gradient"], o["gradient"])
+    Z, X, lat = water_box(3, jitter=0.04)
+    Xw = wrap_into_cell(X, lat)
+    Zt, Xt = onp.tess_lattice(lat, Z.astype(np.uint8), Xw, P["EECutoffOff"])
+    rp = eng.evaluate_lattice(Xw, Z, lat, int(round((len(Zt) / len(Z)) ** (1 / 3.0)) - 1) // 2, descriptors=True)
+    op = og.Oracle(g["eles"], W, P).evaluate_periodic(Xt, Zt, len(Z))
+    _check_desc(rp["descriptors"][0], op["descriptors"][0])
+    for k in ("Etotal", "Ebp", "Ecc", "Evdw"):
+        _check_energy(rp[k], op[k], k)
+    _check_grad(rp["gradient"], op["gradient"][:, :len(Z)])
