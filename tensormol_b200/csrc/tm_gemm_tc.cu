@@ -58,6 +58,7 @@
 
 struct alignas(64) TcGroup {
   CUtensorMap mapA_hi, mapA_lo, mapB_hi, mapB_lo;
+  CUtensorMap mapC_hi, mapC_lo;   // output planes, box 64 columns x 32 rows (one epilogue warp's piece): TMA stores (k_gemm_tc, P.tma_store)
   const float* bias;
   const __half* Hmul_hi;
   const __half* Hmul_lo;
@@ -76,6 +77,7 @@ struct alignas(64) TcParams {
   int fuse_n;                 // single-CTA tiles: A_hi x [B_hi | B_lo] as ONE MMA of N = 2 BN (see the MMA issuer)
   unsigned long long* prof;   // TC_PROFILE builds: per-CTA cycle counters
   int exp;                    // TC_EXP builds (measurements): bit 0 no output phase, bit 1 no MMAs, bit 2 no TMA loads
+  int tma_store;              // fp16 output planes leave through cp.async.bulk.tensor stores instead of LDS + STG
 };
 
 // ------------------------------------------------------------------------------------------------ PTX helpers
@@ -105,6 +107,14 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* ba
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
+// shared tile (128B-swizzled, written by this warp) -> global through the tensor map; bulk async-group of the issuing thread
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src_shared, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"((uint64_t)map), "r"(src_shared), "r"(c0), "r"(c1) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)map) : "memory");
 }
@@ -284,7 +294,9 @@ k_gemm_tc(const __grid_constant__ TcParams P, const int32_t* __restrict__ rowmet
   int* tile_base = (int*)(tmem_slot + 4);       // [TC_MAX_GROUPS+1]
   int* row_first = tile_base + TC_MAX_GROUPS + 1;   // [TC_MAX_GROUPS]
   int* row_tiles = row_first + TC_MAX_GROUPS;       // [TC_MAX_GROUPS]
-  float* tbuf = (float*)(((uintptr_t)(row_tiles + TC_MAX_GROUPS) + 15) & ~(uintptr_t)15);  // TC_EPI_WARPS x 4 KB transpose tiles
+  // TC_EPI_WARPS x 4 KB transpose tiles, 1024-byte aligned (a TMA store reads them with the 128B swizzle); the barriers and
+  // tile tables above take the 1 KB in front of them
+  float* tbuf = (float*)(smem + STAGES * STAGE_BYTES + 1024);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // roles: warps 0..7 epilogue, warp 8 TMA producer, warp 9 MMA issuer.  The two single-thread roles get the HIGHEST warp
@@ -520,6 +532,10 @@ k_gemm_tc(const __grid_constant__ TcParams P, const int32_t* __restrict__ rowmet
 #ifdef TC_EXP
       if (P.exp & 1) { if (accr[0] == 123.456f) P.g[g].C32[0] = accr[1]; continue; }
 #endif
+      if (EPI != TM_EPI_NONE && P.tma_store) {   // the previous tile's last TMA store has read this warp's tile by now
+        if (lane == 0) bulk_wait_read_all();
+        __syncwarp();
+      }
       if (EPI == TM_EPI_DACT) {
         // act'(h) for the band: lanes work slab-wise (4 lanes per row, 8 rows per instruction) on two 32-column passes,
         // join hi/lo, evaluate act', and hand the fp32 values to the row threads through the swizzled tile.
@@ -626,11 +642,22 @@ k_gemm_tc(const __grid_constant__ TcParams P, const int32_t* __restrict__ rowmet
 #pragma unroll
         for (int plane = 0; plane < 2; plane++) {
           __half* Cp = plane ? Cl : Ch;
+          if (plane == 1 && P.tma_store) {   // the hi-plane store must have read the tile before the lo plane overwrites it
+            if (lane == 0) bulk_wait_read_all();
+            __syncwarp();
+          }
 #pragma unroll
           for (int i = 0; i < 8; i++) {
             uint4 u = plane ? make_uint4(lp[4 * i], lp[4 * i + 1], lp[4 * i + 2], lp[4 * i + 3])
                             : make_uint4(hp[4 * i], hp[4 * i + 1], hp[4 * i + 2], hp[4 * i + 3]);
             sts128(tb + 4u * TB_OFF(lane, i), u);
+          }
+          if (P.tma_store) {
+            // [32 rows][128 bytes], 16-byte pieces XOR-swizzled by row & 7 = the tensor map's SWIZZLE_128B: one bulk store
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) tma_store_2d(plane ? &P.g[g].mapC_lo : &P.g[g].mapC_hi, tb, n0, (int)wrow0);
+            continue;
           }
           __syncwarp();
 #pragma unroll
@@ -643,6 +670,7 @@ k_gemm_tc(const __grid_constant__ TcParams P, const int32_t* __restrict__ rowmet
       }
       if (warp == 0 && lane == 0) { PROF_ADD(4, t_out); if (P.prof) atomicAdd(&P.prof[5], 1ull); }
     }
+    if (EPI != TM_EPI_NONE && P.tma_store && lane == 0) bulk_wait_all();   // all of this thread's bulk stores have landed
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   if (NCTA == 2) cluster_sync_all();   // the peer's smem / TMEM stay alive until both CTAs are done
@@ -1069,7 +1097,7 @@ static int make_map(tm_ctx* c, CUtensorMap* m, const void* base, int64_t rows, i
 template <int EPI, int ACTK, int NCTA, int BN>
 static int launch_tc(tm_ctx* c, const TcParams& P, const int* rowmeta_dev, int total_units_bound) {
   // NCTA = 1, BN = 128: 3 stages x 64 KB; CTA pair or BN = 64: 4 stages x 48 KB -- the same 192 KB
-  constexpr size_t smem = (size_t)TC_STAGES * (2 * TC_BM * TC_BK * 2 + 2 * TC_BN * TC_BK * 2) + 1024 + 512 + TC_EPI_WARPS * 32 * 32 * 4;
+  constexpr size_t smem = (size_t)TC_STAGES * (2 * TC_BM * TC_BK * 2 + 2 * TC_BN * TC_BK * 2) + 1024 + 1024 + TC_EPI_WARPS * 32 * 32 * 4;
   static bool configured[64] = {};              // the attribute is per device
   if (c->device < 0 || c->device >= 64 || !configured[c->device]) {
     TM_CUDA(cudaFuncSetAttribute(k_gemm_tc<EPI, ACTK, NCTA, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1149,6 +1177,9 @@ int tm_gemm_tc_launch(tm_ctx* c, const GemmGroup* groups, int ngroups, const int
   P.fuse_n = fuse_env;
   P.prof = nullptr;
   P.exp = 0;
+  static int tma_store_env = -1;   // output planes through cp.async.bulk.tensor stores; TM_GEMM_TMA_STORE=0: LDS + STG (A/B in DESIGN.md section 4)
+  if (tma_store_env < 0) { const char* e = getenv("TM_GEMM_TMA_STORE"); tma_store_env = e ? atoi(e) : 1; }
+  P.tma_store = tma_store_env;
 #ifdef TC_EXP
   { const char* e = getenv("TC_EXP"); P.exp = e ? atoi(e) : 0; }
 #endif
@@ -1191,6 +1222,10 @@ int tm_gemm_tc_launch(tm_ctx* c, const GemmGroup* groups, int ngroups, const int
     if ((rc = make_map(c, &T.mapA_lo, g.A2, g.rows_alloc, g.K, g.lda, TC_BM))) return rc;
     if ((rc = make_map(c, &T.mapB_hi, g.B, g.N, g.K, g.ldb, bn / ncta))) return rc;   // a CTA of a pair stages half of the B rows
     if ((rc = make_map(c, &T.mapB_lo, g.B2, g.N, g.K, g.ldb, bn / ncta))) return rc;
+    if (epilogue != TM_EPI_NONE && P.tma_store) {
+      if ((rc = make_map(c, &T.mapC_hi, g.C, g.rows_alloc, g.N, g.ldc, 32))) return rc;
+      if ((rc = make_map(c, &T.mapC_lo, g.C2, g.rows_alloc, g.N, g.ldc, 32))) return rc;
+    }
     T.bias = g.bias; T.Hmul_hi = (const __half*)g.Hmul; T.Hmul_lo = (const __half*)g.Hmul2;
     T.C_hi = (__half*)g.C; T.C_lo = (__half*)g.C2; T.C32 = (float*)g.C;
     T.wout = g.wout; T.ypart = g.ypart; T.ystride = g.rows_alloc;
