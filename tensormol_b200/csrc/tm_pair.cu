@@ -718,10 +718,15 @@ int tm_launch_pair(tm_ctx* c, const SysView& s, int flags) {
   int64_t nq = s.periodic ? s.nreal : s.nslots;
   if ((rc = tm_buf(c, c->b_dedq, (size_t)nq * 8))) return rc;
   TM_CUDA(cudaMemsetAsync(c->b_dedq.p, 0, (size_t)nq * 8, c->stream));
-  // enough warps to fill the machine: one per centre for large systems, up to 8 per centre for small ones / slabs
+  // one warp per centre; only really small systems (under ~1,000 centres) split a centre's columns over 2-8 warps.  (The
+  // table kernel's persistent CTAs made the wider splitting of round 1 counterproductive — measured on B200, whole step:
+  // 3,000 centres 0.2123 / 0.2135 / 0.2179 / 0.2316 ms with 1 / 2 / 4 / 8 warps per centre, a rank of 8 0.2257 / 0.2268 /
+  // 0.2347 / 0.2414 ms, the 1,568-atom C5 box 0.5411 / 0.5440 / 0.5494 ms.)
   int64_t expect = std::max<int64_t>(1, s.slab_world > 1 ? (s.periodic ? s.nreal : s.nslots) / s.slab_world : s.ncent_max);
   int split = 1;
-  while (split < 8 && expect * split < 148 * 48) split *= 2;
+  while (split < 8 && expect * split < 1024) split *= 2;
+  static const int split_env = getenv("TM_PAIR_SPLIT") ? atoi(getenv("TM_PAIR_SPLIT")) : 0;   // measurements
+  if (split_env == 1 || split_env == 2 || split_env == 4 || split_env == 8) split = split_env;
   int blocks = (int)((s.nrows * split + PAIR_WARPS - 1) / PAIR_WARPS);
   if (nq > 0x7fffffff) { tm_set_error("too many slots"); return TM_EINVAL; }
   auto launch = [&](auto kern) {
