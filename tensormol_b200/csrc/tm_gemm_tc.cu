@@ -1179,7 +1179,7 @@ int tm_gemm_tc_launch(tm_ctx* c, const GemmGroup* groups, int ngroups, const int
   P.exp = 0;
   static int tma_store_env = -1;   // output planes through cp.async.bulk.tensor stores; TM_GEMM_TMA_STORE=0: LDS + STG (A/B in DESIGN.md section 4)
   if (tma_store_env < 0) { const char* e = getenv("TM_GEMM_TMA_STORE"); tma_store_env = e ? atoi(e) : 1; }
-  P.tma_store = tma_store_env;
+  P.tma_store = (ncta == 1) ? tma_store_env : 0;   // the CTA-pair variant (mode 2) keeps the LDS + STG epilogue it was measured with
 #ifdef TC_EXP
   { const char* e = getenv("TC_EXP"); P.exp = e ? atoi(e) : 0; }
 #endif

@@ -131,7 +131,7 @@ def test_pairs_triples_ele_tables(name):
 
 
 # ---------------------------------------------------------------------------------------- fused evaluation
-GEMM_MODES = [0, 1, 3, 4]    # 0 = fp32 FFMA tiles, 1 = tcgen05 split-fp16 (library default: tile width by size), 3 / 4 = 64- / 128-column tiles forced
+GEMM_MODES = [0, 1, 2, 3, 4]    # 0 = fp32 FFMA tiles, 1 = tcgen05 split-fp16 (library default: tile width by size), 2 = the same on CTA pairs (cta_group::2), 3 / 4 = 64- / 128-column tiles forced
 
 
 @pytest.mark.parametrize("mode", GEMM_MODES)
