@@ -64,3 +64,31 @@ def test_workloads_are_the_baseline_configs():
     assert w2["kind"] == "batch" and w2["Zs"].shape == (16, 40) and w2["xyzs"].shape == (16, 40, 3) and w2["natom"] == 640
     # both arms print the same `config` object
     assert bench.build_workload(_args(config="c4"))["config"] == w["config"]
+
+
+def _json_lines(out):
+    import json
+    return [json.loads(l) for l in out.splitlines() if l.startswith("{")]
+
+
+def test_reference_arm_prints_the_contract_line_alone_and_under_torchrun():
+    """`bench.py --impl reference`: the CPU arm (oracle port + the reference's compiled neighbour search when oracle/_ref is
+    built) on the bench's own config; under torchrun only rank 0 works and prints, the other ranks exit 0."""
+    import subprocess
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    base = [sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--config", "c3", "--steps", "1", "--warmup", "0"]
+    r = subprocess.run(base, capture_output=True, text=True, timeout=300, env=env, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = _json_lines(r.stdout)
+    assert len(lines) == 1
+    d = lines[0]
+    assert d["impl"] == "reference" and d["unit"] == "atom-steps/s" and d["higher_is_better"] is True and d["value"] > 0
+    assert d["config"] == bench.build_workload(_args(config="c3"))["config"]          # same config object as the B200 arm
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    cb = d["cpu_baseline"]
+    assert cb["kind"] in ("port", "reference") and cb["cores"] >= 1 and cb["value"] == d["value"] and "sample" in cb
+    tr = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port", "29577"]
+    r2 = subprocess.run(tr + base[1:] + ["--gpus", "2"], capture_output=True, text=True, timeout=400, env=env, cwd=ROOT)
+    assert r2.returncode == 0, r2.stderr[-2000:]
+    lines2 = _json_lines(r2.stdout)
+    assert len(lines2) == 1 and lines2[0]["impl"] == "reference" and lines2[0]["n_gpus"] == 2
